@@ -1,0 +1,224 @@
+/*
+ * ptrec_b200.h — C ABI of libptrec_b200.so, the sm_100a (B200) hot path of PyTorchRec.
+ *
+ * The reference (Troublem1/PyTorchRec) has no FFI: its hot path is the Python convention
+ *   nn.Embedding(column.category_num, D)[column.get_feature_data(batch)]  -> interaction -> loss
+ *   -> autograd embedding_dense_backward -> dense optimizer.step()
+ * (torchrec/model/FunkSVD.py:39-51, SVDPP.py:36-66, IModel.py:116-125).  Each entry point below
+ * names the reference lines whose work it replaces.  A maintainer binds these with ctypes
+ * (see INTEGRATION.md); pytorchrec_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - all buffers are caller-owned; the library never allocates memory that outlives a call;
+ *   - scratch is supplied by the caller: ask `*_workspace_bytes()` first;
+ *   - calls enqueue work on `stream` (a cudaStream_t passed as void*) and never synchronise;
+ *   - return value: 0 on success, a negative PTREC_E* code otherwise; text via ptrec_last_error().
+ *   - tables and optimizer state are updated IN PLACE.
+ */
+#ifndef PTREC_B200_H
+#define PTREC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTREC_ABI_VERSION 3
+
+/* error codes */
+#define PTREC_OK 0
+#define PTREC_EINVAL (-1)       /* bad argument                                   */
+#define PTREC_EALIGN (-2)       /* pointer / stride not aligned as required       */
+#define PTREC_EUNSUPPORTED (-3) /* unsupported D / dtype / size                   */
+#define PTREC_ECUDA (-4)        /* a CUDA runtime call failed                     */
+#define PTREC_EWORKSPACE (-5)   /* workspace too small                            */
+
+/* table element types */
+#define PTREC_F32 0
+#define PTREC_BF16 1
+
+/* pooling modes: reference idioms SVDPP.py:52-55 (sum / sqrt(count)), SASRec.py:109-110 (mean) */
+#define PTREC_POOL_SUM 0
+#define PTREC_POOL_MEAN 1
+#define PTREC_POOL_SQRTN 2
+
+/* which slots of a padded [B, L] bag are valid */
+#define PTREC_MASK_NONE 0           /* every slot (one-hot fields, candidate lists)                  */
+#define PTREC_MASK_PAD 1            /* id != 0              SVDPP.py:49                              */
+#define PTREC_MASK_PAD_KEEP_FIRST 2 /* id != 0 or slot 0    model/utils.py:5-10 (get_valid_his_index) */
+#define PTREC_MASK_LENS 3           /* slot < lens[b]       SASRec.py:109-110 / HistoryDataReader     */
+
+/* fused optimizers */
+#define PTREC_OPT_SGD 0
+#define PTREC_OPT_ADAGRAD 1
+#define PTREC_OPT_ROWWISE_ADAGRAD 2
+#define PTREC_OPT_LAZY_ADAM 3
+
+/*
+ * One sparse feature (= one CategoricalColumn feeding one table).  A batch of B samples carries,
+ * for feature f, a padded id matrix [B, bag_len] (bag_len == 1 for one-hot fields), stored at
+ * ids + id_base * B.  Features MUST be ordered by `table` so that every table's lookups are one
+ * contiguous range of `ids` (the segmented sort relies on it).  40 bytes, no padding.
+ */
+typedef struct ptrec_feature_desc {
+  int32_t table;     /* index into table_ptrs                                              */
+  int32_t bag_len;   /* L: padded bag length, >= 1                                         */
+  int32_t pooling;   /* PTREC_POOL_*                                                        */
+  int32_t mask_mode; /* PTREC_MASK_*                                                        */
+  int32_t lens_col;  /* row of `lens` ([n_cols, B] int32) used by PTREC_MASK_LENS, else -1  */
+  int32_t reserved;
+  int64_t id_base;   /* sum of bag_len over the features before this one                    */
+  int64_t out_col;   /* float offset of this feature's pooled vector inside an output row   */
+} ptrec_feature_desc;
+
+/* hyper-parameters of the fused row update; passed by value (host memory) */
+typedef struct ptrec_optim_args {
+  int32_t kind;  /* PTREC_OPT_* */
+  int32_t step;  /* 1-based step count (Adam bias correction, Adagrad lr_decay)             */
+  float lr;
+  float eps;
+  float beta1;
+  float beta2;
+  float weight_decay; /* L2 on touched rows only (g += wd * w); 0 for dense-parity         */
+  float lr_decay;     /* Adagrad: clr = lr / (1 + (step-1) * lr_decay)                      */
+} ptrec_optim_args;
+
+int ptrec_abi_version(void);
+const char* ptrec_last_error(void); /* thread-local, valid until the next failing call */
+
+/* ---------------------------------------------------------------------------------------------
+ * a1/a6 index preparation.  Replaces the mask/len arithmetic of SVDPP.py:49,53 and
+ * model/utils.py:5-10: turns one padded id matrix into CSR (ids of valid slots, in order, and
+ * bag offsets).  Bit-exact integer work.
+ *   ids_padded [B, L] int64; lens [B] int32 or NULL; mask_mode PTREC_MASK_*;
+ *   out_ids [B*L] (first out_offsets[B] entries meaningful); out_offsets [B+1] int64.
+ * workspace: ptrec_index_prep_workspace_bytes(B).
+ */
+size_t ptrec_index_prep_workspace_bytes(int64_t B);
+int ptrec_index_prep(const int64_t* ids_padded, const int32_t* lens, int64_t B, int64_t L,
+                     int32_t mask_mode, int64_t* out_ids, int64_t* out_offsets, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1 multi-table embedding gather + sum/mean/sqrtn pooling, forward.
+ * Replaces T x `nn.Embedding.forward` (FunkSVD.py:47-48, SVDPP.py:50,57-61, NCF.py:62-65) and the
+ * masked pooling chains SVDPP.py:49-55 / SASRec.py:109-110 in ONE launch per bag class.
+ *   table_ptrs [T] device array of table base pointers ([rows_t, D] row-major, 16-byte aligned)
+ *   table_rows [T] int64 (bounds check -> *err_flag = 1 on an out-of-range id, lookup skipped)
+ *   ids        [sum_f B*bag_len_f] int64, feature-major, each feature [B, bag_len]
+ *   lens       [n_cols, B] int32 or NULL
+ *   out        [B, out_row_stride] float32: out[b*out_row_stride + out_col_f + d]
+ *   bag_scale  [F, B] float32 or NULL: written with the factor the bag sum was multiplied by
+ *              (1, 1/count, 1/sqrt(count); count clamped to >= 1) — the backward needs it.
+ *   err_flag   int32 device word or NULL.
+ *   feats      [F] device copy of the descriptors; feats_host the same array in host memory
+ *              (launch geometry is derived from it without touching the device).
+ */
+int ptrec_embedding_gather_pool_fwd(const void* const* table_ptrs, const int64_t* table_rows,
+                                    int32_t T, int32_t D, int32_t dtype,
+                                    const ptrec_feature_desc* feats,
+                                    const ptrec_feature_desc* feats_host, int32_t F,
+                                    const int64_t* ids, const int32_t* lens, int64_t B, float* out,
+                                    int64_t out_row_stride, float* bag_scale, int32_t* err_flag,
+                                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2a segmented sort + dedup of the lookups of one batch (the integer half of the backward).
+ * Replaces the scatter order of aten::embedding_dense_backward (implicit at IModel.py:123).
+ * Positions p in [0, N), N = B * sum_f bag_len_f, are the slots of `ids`.  Per table, slots are
+ * stably sorted by id (masked slots get key 0xFFFFFFFF and sort last); equal-id runs are the
+ * segments.  Bit-exact against torch.sort(stable=True) / torch.unique(sorted=True) per table.
+ *   sorted_keys [N] uint32   id of the slot at sorted position j (0xFFFFFFFF = masked)
+ *   perm        [N] int32    slot p at sorted position j
+ *   seg_start   [N+1] int32  sorted position where segment u starts; seg_start[n_seg] = N
+ *   seg_table   [N] int32    table of segment u
+ *   n_seg       [1] int32    number of segments (masked runs included, one per table at most)
+ * workspace: ptrec_sort_dedup_workspace_bytes(N, T).  max_rows_host = max_t rows_t (bounds key bits);
+ * table_rows [T] device int64: ids outside [0, rows_t) are treated as masked.
+ */
+size_t ptrec_sort_dedup_workspace_bytes(int64_t N, int32_t T);
+int ptrec_sort_dedup(const ptrec_feature_desc* feats, const ptrec_feature_desc* feats_host, int32_t F,
+                     int32_t T, const int64_t* table_rows, int64_t max_rows_host,
+                     const int64_t* ids, const int32_t* lens, int64_t B, uint32_t* sorted_keys,
+                     int32_t* perm, int32_t* seg_start, int32_t* seg_table, int32_t* n_seg,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2b segment-reduce of the pooled-output gradient + fused row update.  Replaces
+ * aten::embedding_dense_backward + zero_grad + the dense optimizer sweep over every row
+ * (IModel.py:122-124, optim/optimizers.py:7-11, torch.optim.SGD/Adagrad/SparseAdam arithmetic).
+ * One pass per unique row: sum its gradient slots in sorted (= batch) order, read-modify-write
+ * the weight row and its state.  No [rows, D] gradient tensor is ever materialised.
+ *   state1_ptrs / state2_ptrs [T] device arrays (NULL when the optimizer has no such state):
+ *     ADAGRAD: state1 = sum of squares [rows, D];  ROWWISE_ADAGRAD: state1 = [rows];
+ *     LAZY_ADAM: state1 = exp_avg, state2 = exp_avg_sq, both [rows, D].
+ *   grad_out [B, grad_row_stride] float32, same column layout as the forward `out`.
+ *   bag_scale as written by the forward (NULL = all ones).
+ * workspace: ptrec_embedding_bwd_workspace_bytes(N, D).
+ */
+size_t ptrec_embedding_bwd_workspace_bytes(int64_t N, int32_t D);
+int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* state1_ptrs,
+                              void* const* state2_ptrs, int32_t T, int32_t D, int32_t dtype,
+                              const ptrec_feature_desc* feats,
+                              const ptrec_feature_desc* feats_host, int32_t F, int64_t B,
+                              const uint32_t* sorted_keys, const int32_t* perm,
+                              const int32_t* seg_start, const int32_t* seg_table,
+                              const int32_t* n_seg, const float* grad_out,
+                              int64_t grad_row_stride, const float* bag_scale,
+                              const ptrec_optim_args* opt_host, void* workspace,
+                              size_t workspace_bytes, void* stream);
+/* the four named entry points of SURVEY.md §8b; each checks opt_host->kind and forwards */
+int ptrec_embedding_bwd_fused_sgd(void* const*, void* const*, void* const*, int32_t, int32_t,
+                                  int32_t, const ptrec_feature_desc*, const ptrec_feature_desc*, int32_t, int64_t,
+                                  const uint32_t*, const int32_t*, const int32_t*, const int32_t*,
+                                  const int32_t*, const float*, int64_t, const float*,
+                                  const ptrec_optim_args*, void*, size_t, void*);
+int ptrec_embedding_bwd_fused_adagrad(void* const*, void* const*, void* const*, int32_t, int32_t,
+                                      int32_t, const ptrec_feature_desc*, const ptrec_feature_desc*, int32_t, int64_t,
+                                      const uint32_t*, const int32_t*, const int32_t*,
+                                      const int32_t*, const int32_t*, const float*, int64_t,
+                                      const float*, const ptrec_optim_args*, void*, size_t, void*);
+int ptrec_embedding_bwd_fused_rowwise_adagrad(void* const*, void* const*, void* const*, int32_t,
+                                              int32_t, int32_t, const ptrec_feature_desc*, const ptrec_feature_desc*, int32_t,
+                                              int64_t, const uint32_t*, const int32_t*,
+                                              const int32_t*, const int32_t*, const int32_t*,
+                                              const float*, int64_t, const float*,
+                                              const ptrec_optim_args*, void*, size_t, void*);
+int ptrec_embedding_bwd_fused_lazy_adam(void* const*, void* const*, void* const*, int32_t, int32_t,
+                                        int32_t, const ptrec_feature_desc*, const ptrec_feature_desc*, int32_t, int64_t,
+                                        const uint32_t*, const int32_t*, const int32_t*,
+                                        const int32_t*, const int32_t*, const float*, int64_t,
+                                        const float*, const ptrec_optim_args*, void*, size_t,
+                                        void*);
+
+/* Segment-reduce only (no update): writes the per-unique-row gradient sums so that a stock sparse
+ * optimizer (torch.optim.SparseAdam / SGD) can consume them.  row_grad [N, D] float32 (first
+ * n_seg rows meaningful; masked segments are written as zeros). */
+int ptrec_embedding_bwd_segment_sum(int32_t T, int32_t D, const ptrec_feature_desc* feats,
+                                    const ptrec_feature_desc* feats_host, int32_t F, int64_t B,
+                                    const uint32_t* sorted_keys, const int32_t* perm,
+                                    const int32_t* seg_start, const int32_t* seg_table,
+                                    const int32_t* n_seg, const float* grad_out,
+                                    int64_t grad_row_stride, const float* bag_scale,
+                                    float* row_grad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3 FM second-order interaction  y[b] = 0.5 * sum_k ((sum_f v[b,f,k])^2 - sum_f v[b,f,k]^2).
+ * Generalises the two-field dot of FunkSVD.py:51,62 / SVDPP.py:65 to F fields.
+ *   v [B, F, D] float32 with row stride v_row_stride (floats);  y [B].
+ * backward: grad_v[b,f,k] = gy[b] * (S[b,k] - v[b,f,k]) (+ grad_in[b,f,k] when grad_in != NULL,
+ * which fuses autograd's accumulation of the DNN-branch gradient).
+ */
+int ptrec_fm2_fwd(const float* v, int64_t v_row_stride, int64_t B, int32_t F, int32_t D, float* y,
+                  void* stream);
+int ptrec_fm2_bwd(const float* v, int64_t v_row_stride, const float* gy, const float* grad_in,
+                  int64_t grad_in_row_stride, int64_t B, int32_t F, int32_t D, float* grad_v,
+                  int64_t grad_v_row_stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTREC_B200_H */

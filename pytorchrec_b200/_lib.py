@@ -1,0 +1,122 @@
+"""ctypes binding of ``libptrec_b200.so`` (the C ABI declared in ``include/ptrec_b200.h``).
+
+There is no CPU fallback and no alternative backend: if the shared library has not been built
+(``python -c 'import __graft_entry__ as g; g.build()'`` or ``make -C pytorchrec_b200/csrc``) every
+product entry point raises.  The reference has no FFI of its own (its hot path is
+``nn.Embedding`` + autograd + ``torch.optim``, torchrec/model/IModel.py:116-125); this file is the
+binding a reference maintainer would add.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libptrec_b200.so")
+
+ABI_VERSION = 3
+
+# enums (mirror include/ptrec_b200.h)
+F32, BF16 = 0, 1
+POOL_SUM, POOL_MEAN, POOL_SQRTN = 0, 1, 2
+MASK_NONE, MASK_PAD, MASK_PAD_KEEP_FIRST, MASK_LENS = 0, 1, 2, 3
+OPT_SGD, OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD, OPT_LAZY_ADAM = 0, 1, 2, 3
+
+POOLING_NAMES = {"sum": POOL_SUM, "mean": POOL_MEAN, "sqrtn": POOL_SQRTN}
+MASK_NAMES = {"none": MASK_NONE, "pad": MASK_PAD, "pad_keep_first": MASK_PAD_KEEP_FIRST, "lens": MASK_LENS}
+
+
+class FeatureDesc(Structure):
+    _fields_ = [
+        ("table", c_int32),
+        ("bag_len", c_int32),
+        ("pooling", c_int32),
+        ("mask_mode", c_int32),
+        ("lens_col", c_int32),
+        ("reserved", c_int32),
+        ("id_base", c_int64),
+        ("out_col", c_int64),
+    ]
+
+
+class OptimArgs(Structure):
+    _fields_ = [
+        ("kind", c_int32),
+        ("step", c_int32),
+        ("lr", c_float),
+        ("eps", c_float),
+        ("beta1", c_float),
+        ("beta2", c_float),
+        ("weight_decay", c_float),
+        ("lr_decay", c_float),
+    ]
+
+
+assert ctypes.sizeof(FeatureDesc) == 40
+assert ctypes.sizeof(OptimArgs) == 32
+
+_FD = POINTER(FeatureDesc)
+_BWD_ARGS = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, _FD, _FD, c_int32, c_int64,
+             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+             POINTER(OptimArgs), c_void_p, c_size_t, c_void_p]
+
+# name -> (restype, argtypes); every symbol include/ptrec_b200.h declares
+PROTOTYPES = {
+    "ptrec_abi_version": (c_int, []),
+    "ptrec_last_error": (c_char_p, []),
+    "ptrec_index_prep_workspace_bytes": (c_size_t, [c_int64]),
+    "ptrec_index_prep": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
+                                 c_void_p, c_size_t, c_void_p]),
+    "ptrec_embedding_gather_pool_fwd": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, _FD, _FD,
+                                                c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                                c_void_p, c_void_p, c_void_p]),
+    "ptrec_sort_dedup_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "ptrec_sort_dedup": (c_int, [_FD, _FD, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p,
+                                 c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_size_t, c_void_p]),
+    "ptrec_embedding_bwd_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "ptrec_embedding_bwd_fused": (c_int, _BWD_ARGS),
+    "ptrec_embedding_bwd_fused_sgd": (c_int, _BWD_ARGS),
+    "ptrec_embedding_bwd_fused_adagrad": (c_int, _BWD_ARGS),
+    "ptrec_embedding_bwd_fused_rowwise_adagrad": (c_int, _BWD_ARGS),
+    "ptrec_embedding_bwd_fused_lazy_adam": (c_int, _BWD_ARGS),
+    "ptrec_embedding_bwd_segment_sum": (c_int, [c_int32, c_int32, _FD, _FD, c_int32, c_int64, c_void_p,
+                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                                c_void_p, c_void_p, c_void_p]),
+    "ptrec_fm2_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "ptrec_fm2_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
+                              c_void_p, c_int64, c_void_p]),
+}
+
+_lib = None
+
+
+class PtrecError(RuntimeError):
+    """A libptrec_b200 call returned a negative PTREC_E* code."""
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build the sm_100a extension first "
+            "(`make -C pytorchrec_b200/csrc` or `__graft_entry__.build()`). "
+            "pytorchrec_b200 has no CPU or library fallback for its hot path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = restype
+        fn.argtypes = argtypes
+    ver = lib.ptrec_abi_version()
+    if ver != ABI_VERSION:
+        raise RuntimeError(f"libptrec_b200.so ABI {ver} != binding ABI {ABI_VERSION}: rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().ptrec_last_error().decode("utf-8", "replace")
+        raise PtrecError(f"{what or 'libptrec_b200'} failed ({rc}): {msg}")

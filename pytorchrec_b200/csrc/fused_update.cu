@@ -1,0 +1,435 @@
+// K2b: segment-reduce of the pooled-output gradient fused with the sparse row update.
+//
+// Bound: HBM.  Algorithmic bytes per launch =
+//   lookups*(4 perm + D*4 grad row) + segments*(8 key/start + 2*D*4 weight RMW + 2*S state RMW),
+//   S = 0 (SGD), 4 (row-wise Adagrad), D*4 (Adagrad), 2*D*4 (lazy Adam).
+// One sub-warp of D/4 lanes owns one unique row: it sums the row's gradient slots in sorted
+// (= original batch) order with 128-bit loads, then read-modify-writes weight + state once.
+// Rows hit more than `kLongSeg` times in the batch (Zipf heads) are deferred to a second kernel in
+// which a whole CTA reduces the run with a fixed-shape shared-memory tree.  Both orders are fixed
+// by the sort, so results are run-to-run bit-reproducible; no atomics touch floating-point data.
+#include "common.cuh"
+
+namespace ptrec {
+
+constexpr int kUpdThreads = 128;
+constexpr int kLongThreads = 256;
+constexpr int kLongSeg = 32;
+constexpr int kOptNone = -1;  // segment-sum only
+
+struct OptParams {
+  float lr;         // already lr-decayed (Adagrad) / bias-corrected step size (Adam)
+  float eps;
+  float beta1;
+  float beta2;
+  float weight_decay;
+  float inv_D;
+};
+
+// lanes of the sub-warp that owns one row (all of them take the same branches)
+template <int LPR>
+__device__ __forceinline__ unsigned group_mask() {
+  if constexpr (LPR == 32) {
+    return 0xffffffffu;
+  } else {
+    return ((1u << LPR) - 1u) << (((threadIdx.x & 31) / LPR) * LPR);
+  }
+}
+template <int VEC, int LPR>
+__device__ __forceinline__ float group_sum_sq(const RowVec<VEC>& g) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) s += g.v[k] * g.v[k];
+  const unsigned m = group_mask<LPR>();
+#pragma unroll
+  for (int o = 1; o < LPR; o <<= 1) s += __shfl_xor_sync(m, s, o);
+  return s;
+}
+
+// apply the optimizer to this lane's VEC-float slice of row `row`
+template <int VEC, int LPR, int OPT>
+__device__ __forceinline__ void apply_update(RowVec<VEC> g, float* __restrict__ wrow,
+                                             float* __restrict__ s1, float* __restrict__ s2,
+                                             int64_t row, int D, int lane, bool lane_on,
+                                             const OptParams& op, float* row_grad_out) {
+  const int64_t off = row * (int64_t)D + lane * VEC;
+  if constexpr (OPT == kOptNone) {
+    if (lane_on) store_row<VEC>(row_grad_out + lane * VEC, g);
+    return;
+  }
+  RowVec<VEC> w;
+  w.zero();
+  if (lane_on) w = load_row<VEC>(wrow + off);
+  if (op.weight_decay != 0.f) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) g.v[k] += op.weight_decay * w.v[k];
+  }
+  if constexpr (OPT == PTREC_OPT_SGD) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) w.v[k] -= op.lr * g.v[k];
+  } else if constexpr (OPT == PTREC_OPT_ADAGRAD) {
+    // torch.optim.Adagrad: state_sum.addcmul_(g, g); std = sqrt(state_sum) + eps; p.addcdiv_(g, std, -clr)
+    RowVec<VEC> s;
+    s.zero();
+    if (lane_on) s = load_row<VEC>(s1 + off);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      s.v[k] += g.v[k] * g.v[k];
+      w.v[k] -= op.lr * (g.v[k] / (sqrtf(s.v[k]) + op.eps));
+    }
+    if (lane_on) store_row<VEC>(s1 + off, s);
+  } else if constexpr (OPT == PTREC_OPT_ROWWISE_ADAGRAD) {
+    // one accumulator per row: state += mean_k(g_k^2)
+    if (!lane_on) g.zero();
+    const float ss = group_sum_sq<VEC, LPR>(g) * op.inv_D;
+    const float st = s1[row] + ss;
+    const float inv = op.lr / (sqrtf(st) + op.eps);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) w.v[k] -= inv * g.v[k];
+    __syncwarp(group_mask<LPR>());  // every lane has read s1[row] before lane 0 overwrites it
+    if (lane == 0) s1[row] = st;
+  } else if constexpr (OPT == PTREC_OPT_LAZY_ADAM) {
+    // torch.optim.SparseAdam (_functional.sparse_adam): moments move only on touched rows
+    RowVec<VEC> m, v;
+    m.zero();
+    v.zero();
+    if (lane_on) {
+      m = load_row<VEC>(s1 + off);
+      v = load_row<VEC>(s2 + off);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      m.v[k] += (g.v[k] - m.v[k]) * (1.f - op.beta1);
+      v.v[k] += (g.v[k] * g.v[k] - v.v[k]) * (1.f - op.beta2);
+      w.v[k] -= op.lr * (m.v[k] / (sqrtf(v.v[k]) + op.eps));
+    }
+    if (lane_on) {
+      store_row<VEC>(s1 + off, m);
+      store_row<VEC>(s2 + off, v);
+    }
+  }
+  if (lane_on) store_row<VEC>(wrow + off, w);
+}
+
+// gradient row of slot p, scaled by its bag's pooling factor
+template <int VEC>
+__device__ __forceinline__ RowVec<VEC> slot_grad(const ptrec_feature_desc* s_feats, int F, int64_t B,
+                                                 int32_t p, const float* __restrict__ grad_out,
+                                                 int64_t stride, const float* __restrict__ bag_scale,
+                                                 int lane, bool lane_on) {
+  const int f = find_feature(s_feats, F, B, p);
+  const ptrec_feature_desc& fd = s_feats[f];
+  const int64_t b = ((int64_t)p - fd.id_base * B) / fd.bag_len;
+  RowVec<VEC> g;
+  g.zero();
+  if (lane_on) g = load_row_stream<VEC>(grad_out + b * stride + fd.out_col + lane * VEC);
+  if (fd.pooling != PTREC_POOL_SUM && bag_scale != nullptr &&
+      !(fd.bag_len == 1 && fd.mask_mode == PTREC_MASK_NONE)) {
+    g.scale(bag_scale[(int64_t)f * B + b]);
+  }
+  return g;
+}
+
+template <int VEC, int LPR, int OPT>
+__global__ void __launch_bounds__(kUpdThreads)
+fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restrict__ state1_ptrs,
+                    void* const* __restrict__ state2_ptrs, int D,
+                    const ptrec_feature_desc* __restrict__ feats, int F, int64_t B,
+                    const uint32_t* __restrict__ sorted_keys, const int32_t* __restrict__ perm,
+                    const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_table,
+                    const int32_t* __restrict__ n_seg_ptr, const float* __restrict__ grad_out,
+                    int64_t stride, const float* __restrict__ bag_scale, OptParams op,
+                    int* __restrict__ long_count, int32_t* __restrict__ long_list,
+                    float* __restrict__ row_grad) {
+  __shared__ ptrec_feature_desc s_feats[kMaxFeatures];
+  load_feats(s_feats, feats, F);
+  __syncthreads();
+  constexpr int NSG = kUpdThreads / LPR;
+  const int sg = threadIdx.x / LPR, lane = threadIdx.x % LPR;
+  const bool lane_on = lane * VEC < D;
+  const int n_seg = *n_seg_ptr;
+  // every sub-warp of a warp runs the same number of iterations (shuffles inside apply_update)
+  const int n_round = (n_seg + NSG - 1) / NSG;
+  for (int r = blockIdx.x; r < n_round; r += gridDim.x) {
+    const int u = r * NSG + sg;
+    const bool live = u < n_seg;
+    int start = 0, end = 0;
+    uint32_t key = kMaskedKey;
+    if (live) {
+      start = seg_start[u];
+      end = seg_start[u + 1];
+      key = sorted_keys[start];
+    }
+    const bool masked = key == kMaskedKey;
+    const bool is_long = live && !masked && (end - start) > kLongSeg && OPT != kOptNone;
+    if (is_long && lane == 0) long_list[atomicAdd(long_count, 1)] = u;
+    const bool work = live && !masked && !is_long;
+    RowVec<VEC> acc;
+    acc.zero();
+    if (work) {
+      for (int j0 = start; j0 < end; j0 += 4) {
+        RowVec<VEC> g[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          g[q].zero();
+          if (j0 + q < end)
+            g[q] = slot_grad<VEC>(s_feats, F, B, perm[j0 + q], grad_out, stride, bag_scale, lane, lane_on);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc.add(g[q]);
+      }
+    }
+    if constexpr (OPT == kOptNone) {
+      if (live) apply_update<VEC, LPR, OPT>(acc, nullptr, nullptr, nullptr, 0, D, lane, lane_on, op,
+                                            row_grad + (int64_t)u * D);
+    } else {
+      if (work) {
+        const int t = seg_table[u];
+        apply_update<VEC, LPR, OPT>(acc, reinterpret_cast<float*>(table_ptrs[t]),
+                                    state1_ptrs ? reinterpret_cast<float*>(state1_ptrs[t]) : nullptr,
+                                    state2_ptrs ? reinterpret_cast<float*>(state2_ptrs[t]) : nullptr,
+                                    (int64_t)key, D, lane, lane_on, op, nullptr);
+      }
+    }
+  }
+}
+
+// CTA per long segment
+template <int VEC, int LPR, int OPT>
+__global__ void __launch_bounds__(kLongThreads)
+fused_update_long_kernel(void* const* __restrict__ table_ptrs, void* const* __restrict__ state1_ptrs,
+                         void* const* __restrict__ state2_ptrs, int D,
+                         const ptrec_feature_desc* __restrict__ feats, int F, int64_t B,
+                         const uint32_t* __restrict__ sorted_keys, const int32_t* __restrict__ perm,
+                         const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_table,
+                         const float* __restrict__ grad_out, int64_t stride,
+                         const float* __restrict__ bag_scale, OptParams op,
+                         const int* __restrict__ long_count, const int32_t* __restrict__ long_list) {
+  __shared__ ptrec_feature_desc s_feats[kMaxFeatures];
+  constexpr int NSG = kLongThreads / LPR;
+  __shared__ float s_part[NSG * LPR * VEC];
+  load_feats(s_feats, feats, F);
+  __syncthreads();
+  const int sg = threadIdx.x / LPR, lane = threadIdx.x % LPR;
+  const bool lane_on = lane * VEC < D;
+  const int n_long = *long_count;
+  for (int i = blockIdx.x; i < n_long; i += gridDim.x) {
+    const int u = long_list[i];
+    const int start = seg_start[u], end = seg_start[u + 1];
+    RowVec<VEC> acc;
+    acc.zero();
+    for (int j0 = start + sg; j0 < end; j0 += NSG * 2) {
+      RowVec<VEC> g0, g1;
+      g0 = slot_grad<VEC>(s_feats, F, B, perm[j0], grad_out, stride, bag_scale, lane, lane_on);
+      g1.zero();
+      if (j0 + NSG < end)
+        g1 = slot_grad<VEC>(s_feats, F, B, perm[j0 + NSG], grad_out, stride, bag_scale, lane, lane_on);
+      acc.add(g0);
+      acc.add(g1);
+    }
+    float* mine = s_part + (sg * LPR + lane) * VEC;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) mine[k] = acc.v[k];
+    __syncthreads();
+    for (int h = NSG / 2; h > 0; h >>= 1) {
+      if (sg < h) {
+        const float* other = s_part + ((sg + h) * LPR + lane) * VEC;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) mine[k] += other[k];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x < 32) {  // first warp converged: sub-warp 0 applies, its warp-mates idle
+      const bool doit = sg == 0;
+      RowVec<VEC> tot;
+      tot.zero();
+      if (doit) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) tot.v[k] = mine[k];
+      }
+      const int t = seg_table[u];
+      const uint32_t key = sorted_keys[start];
+      if (doit) {
+        apply_update<VEC, LPR, OPT>(tot, reinterpret_cast<float*>(table_ptrs[t]),
+                                    state1_ptrs ? reinterpret_cast<float*>(state1_ptrs[t]) : nullptr,
+                                    state2_ptrs ? reinterpret_cast<float*>(state2_ptrs[t]) : nullptr,
+                                    (int64_t)key, D, lane, lane_on, op, nullptr);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int VEC, int LPR, int OPT>
+static int launch_update(void* const* table_ptrs, void* const* s1, void* const* s2, int D,
+                         const ptrec_feature_desc* feats, int F, int64_t B, int64_t N,
+                         const uint32_t* sorted_keys, const int32_t* perm, const int32_t* seg_start,
+                         const int32_t* seg_table, const int32_t* n_seg, const float* grad_out,
+                         int64_t stride, const float* bag_scale, const OptParams& op, int* long_count,
+                         int32_t* long_list, float* row_grad, cudaStream_t st) {
+  constexpr int NSG = kUpdThreads / LPR;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t rounds = ceil_div(N, NSG);
+  const unsigned grid = (unsigned)(rounds < (int64_t)sms * 16 ? (rounds > 0 ? rounds : 1) : (int64_t)sms * 16);
+  if (OPT != kOptNone) PTREC_CUDA(cudaMemsetAsync(long_count, 0, sizeof(int), st));
+  fused_update_kernel<VEC, LPR, OPT><<<grid, kUpdThreads, 0, st>>>(
+      table_ptrs, s1, s2, D, feats, F, B, sorted_keys, perm, seg_start, seg_table, n_seg, grad_out,
+      stride, bag_scale, op, long_count, long_list, row_grad);
+  PTREC_LAUNCH_CHECK("fused_update_kernel");
+  if (OPT != kOptNone) {
+    fused_update_long_kernel<VEC, LPR, OPT><<<sms * 2, kLongThreads, 0, st>>>(
+        table_ptrs, s1, s2, D, feats, F, B, sorted_keys, perm, seg_start, seg_table, grad_out, stride,
+        bag_scale, op, long_count, long_list);
+    PTREC_LAUNCH_CHECK("fused_update_long_kernel");
+  }
+  return PTREC_OK;
+}
+
+template <int OPT>
+static int dispatch_D(void* const* table_ptrs, void* const* s1, void* const* s2, int D,
+                      const ptrec_feature_desc* feats, int F, int64_t B, int64_t N,
+                      const uint32_t* sorted_keys, const int32_t* perm, const int32_t* seg_start,
+                      const int32_t* seg_table, const int32_t* n_seg, const float* grad_out,
+                      int64_t stride, const float* bag_scale, const OptParams& op, int* long_count,
+                      int32_t* long_list, float* row_grad, cudaStream_t st) {
+#define PTREC_UPD(V, P) \
+  return launch_update<V, P, OPT>(table_ptrs, s1, s2, D, feats, F, B, N, sorted_keys, perm, seg_start, \
+                                  seg_table, n_seg, grad_out, stride, bag_scale, op, long_count,        \
+                                  long_list, row_grad, st)
+  if (D == 1) PTREC_UPD(1, 1);
+  if (D == 2) PTREC_UPD(2, 1);
+  const int lanes = D / 4;
+  if (lanes <= 1) PTREC_UPD(4, 1);
+  if (lanes <= 2) PTREC_UPD(4, 2);
+  if (lanes <= 4) PTREC_UPD(4, 4);
+  if (lanes <= 8) PTREC_UPD(4, 8);
+  if (lanes <= 16) PTREC_UPD(4, 16);
+  PTREC_UPD(4, 32);
+#undef PTREC_UPD
+}
+
+}  // namespace ptrec
+
+using namespace ptrec;
+
+extern "C" size_t ptrec_embedding_bwd_workspace_bytes(int64_t N, int32_t D) {
+  (void)D;
+  return align_up(256 + ((size_t)N / kLongSeg + 2) * sizeof(int32_t), 256);
+}
+
+static int64_t total_slots(const ptrec_feature_desc* feats_host, int F, int64_t B) {
+  int64_t L = 0;
+  for (int f = 0; f < F; ++f) L += feats_host[f].bag_len;
+  return L * B;
+}
+
+static int check_common(int32_t T, int32_t D, int32_t dtype, int32_t F, const void* grad_out,
+                        int64_t stride) {
+  PTREC_CHECK_ARG(dtype == PTREC_F32, PTREC_EUNSUPPORTED, "bwd: only fp32 tables are built (dtype=%d)", dtype);
+  PTREC_CHECK_ARG(T >= 1 && T <= kMaxTables && F >= 1 && F <= kMaxFeatures, PTREC_EINVAL, "bwd: T=%d F=%d out of range", T, F);
+  const bool d_ok = D == 1 || D == 2 || (D >= 4 && D <= 128 && D % 4 == 0);
+  PTREC_CHECK_ARG(d_ok, PTREC_EUNSUPPORTED, "bwd: D=%d unsupported", D);
+  const int vec = D >= 4 ? 4 : D;
+  PTREC_CHECK_ARG(((uintptr_t)grad_out % (vec * 4)) == 0 && (stride % vec) == 0, PTREC_EALIGN,
+                  "bwd: grad_out / stride not aligned to %d bytes", vec * 4);
+  return PTREC_OK;
+}
+
+extern "C" int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* state1_ptrs,
+                                         void* const* state2_ptrs, int32_t T, int32_t D, int32_t dtype,
+                                         const ptrec_feature_desc* feats,
+                                         const ptrec_feature_desc* feats_host, int32_t F, int64_t B,
+                                         const uint32_t* sorted_keys, const int32_t* perm,
+                                         const int32_t* seg_start, const int32_t* seg_table,
+                                         const int32_t* n_seg, const float* grad_out,
+                                         int64_t grad_row_stride, const float* bag_scale,
+                                         const ptrec_optim_args* opt_host, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  int rc = check_common(T, D, dtype, F, grad_out, grad_row_stride);
+  if (rc != PTREC_OK) return rc;
+  PTREC_CHECK_ARG(table_ptrs && feats && feats_host && sorted_keys && perm && seg_start && seg_table && n_seg &&
+                      grad_out && opt_host, PTREC_EINVAL, "bwd_fused: null pointer");
+  const int64_t N = total_slots(feats_host, F, B);
+  PTREC_CHECK_ARG(workspace && workspace_bytes >= ptrec_embedding_bwd_workspace_bytes(N, D), PTREC_EWORKSPACE,
+                  "bwd_fused: workspace too small");
+  if (N == 0) return PTREC_OK;
+  for (int f = 0; f < F; ++f) {
+    const int vec = D >= 4 ? 4 : D;
+    PTREC_CHECK_ARG(feats_host[f].out_col % vec == 0, PTREC_EALIGN, "bwd_fused: feature %d out_col misaligned", f);
+  }
+  OptParams op;
+  op.eps = opt_host->eps;
+  op.beta1 = opt_host->beta1;
+  op.beta2 = opt_host->beta2;
+  op.weight_decay = opt_host->weight_decay;
+  op.inv_D = 1.0f / (float)D;
+  op.lr = opt_host->lr;
+  const int step = opt_host->step < 1 ? 1 : opt_host->step;
+  int* long_count = reinterpret_cast<int*>(workspace);
+  int32_t* long_list = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PTREC_ARGS                                                                                      \
+  table_ptrs, state1_ptrs, state2_ptrs, D, feats, F, B, N, sorted_keys, perm, seg_start, seg_table, n_seg, \
+      grad_out, grad_row_stride, bag_scale, op, long_count, long_list, nullptr, st
+  switch (opt_host->kind) {
+    case PTREC_OPT_SGD:
+      return dispatch_D<PTREC_OPT_SGD>(PTREC_ARGS);
+    case PTREC_OPT_ADAGRAD:
+      PTREC_CHECK_ARG(state1_ptrs, PTREC_EINVAL, "bwd_fused: Adagrad needs state1");
+      op.lr = (float)((double)opt_host->lr / (1.0 + (double)(step - 1) * (double)opt_host->lr_decay));
+      return dispatch_D<PTREC_OPT_ADAGRAD>(PTREC_ARGS);
+    case PTREC_OPT_ROWWISE_ADAGRAD:
+      PTREC_CHECK_ARG(state1_ptrs, PTREC_EINVAL, "bwd_fused: row-wise Adagrad needs state1");
+      op.lr = (float)((double)opt_host->lr / (1.0 + (double)(step - 1) * (double)opt_host->lr_decay));
+      return dispatch_D<PTREC_OPT_ROWWISE_ADAGRAD>(PTREC_ARGS);
+    case PTREC_OPT_LAZY_ADAM: {
+      PTREC_CHECK_ARG(state1_ptrs && state2_ptrs, PTREC_EINVAL, "bwd_fused: lazy Adam needs state1 and state2");
+      const double bc1 = 1.0 - pow((double)opt_host->beta1, (double)step);
+      const double bc2 = 1.0 - pow((double)opt_host->beta2, (double)step);
+      op.lr = (float)((double)opt_host->lr * sqrt(bc2) / bc1);
+      return dispatch_D<PTREC_OPT_LAZY_ADAM>(PTREC_ARGS);
+    }
+    default:
+      PTREC_CHECK_ARG(false, PTREC_EINVAL, "bwd_fused: unknown optimizer kind %d", opt_host->kind);
+  }
+#undef PTREC_ARGS
+  return PTREC_OK;
+}
+
+#define PTREC_NAMED(NAME, KIND)                                                                          \
+  extern "C" int NAME(void* const* a, void* const* b, void* const* c, int32_t T, int32_t D, int32_t dt,  \
+                      const ptrec_feature_desc* f, const ptrec_feature_desc* fh, int32_t F, int64_t B,   \
+                      const uint32_t* k, const int32_t* p, const int32_t* s, const int32_t* st,          \
+                      const int32_t* n, const float* g, int64_t gs, const float* bs,                     \
+                      const ptrec_optim_args* o, void* ws, size_t wsb, void* stream) {                   \
+    PTREC_CHECK_ARG(o && o->kind == KIND, PTREC_EINVAL, #NAME ": opt_host->kind must be " #KIND);        \
+    return ptrec_embedding_bwd_fused(a, b, c, T, D, dt, f, fh, F, B, k, p, s, st, n, g, gs, bs, o, ws,   \
+                                     wsb, stream);                                                        \
+  }
+PTREC_NAMED(ptrec_embedding_bwd_fused_sgd, PTREC_OPT_SGD)
+PTREC_NAMED(ptrec_embedding_bwd_fused_adagrad, PTREC_OPT_ADAGRAD)
+PTREC_NAMED(ptrec_embedding_bwd_fused_rowwise_adagrad, PTREC_OPT_ROWWISE_ADAGRAD)
+PTREC_NAMED(ptrec_embedding_bwd_fused_lazy_adam, PTREC_OPT_LAZY_ADAM)
+#undef PTREC_NAMED
+
+extern "C" int ptrec_embedding_bwd_segment_sum(int32_t T, int32_t D, const ptrec_feature_desc* feats,
+                                               const ptrec_feature_desc* feats_host, int32_t F,
+                                               int64_t B, const uint32_t* sorted_keys,
+                                               const int32_t* perm, const int32_t* seg_start,
+                                               const int32_t* seg_table, const int32_t* n_seg,
+                                               const float* grad_out, int64_t grad_row_stride,
+                                               const float* bag_scale, float* row_grad, void* stream) {
+  int rc = check_common(T, D, PTREC_F32, F, grad_out, grad_row_stride);
+  if (rc != PTREC_OK) return rc;
+  PTREC_CHECK_ARG(feats && feats_host && sorted_keys && perm && seg_start && seg_table && n_seg && row_grad,
+                  PTREC_EINVAL, "segment_sum: null pointer");
+  PTREC_CHECK_ARG(aligned16(row_grad), PTREC_EALIGN, "segment_sum: row_grad must be 16-byte aligned");
+  const int64_t N = total_slots(feats_host, F, B);
+  if (N == 0) return PTREC_OK;
+  OptParams op{};
+  return dispatch_D<kOptNone>(nullptr, nullptr, nullptr, D, feats, F, B, N, sorted_keys, perm, seg_start,
+                              seg_table, n_seg, grad_out, grad_row_stride, bag_scale, op, nullptr,
+                              nullptr, row_grad, (cudaStream_t)stream);
+}

@@ -1,0 +1,330 @@
+// K2a: per-table stable LSD radix sort of the batch's lookup slots + dedup into segments.
+//
+// Integer-only, bit-exact against torch.sort(stable=True) / torch.unique(sorted=True) per table.
+// Bound: launch latency at the configs' sizes (N = 4e5..2e6 keys move ~16 B each per pass);
+// the design goal is therefore few, wide, spin-free launches:
+//   per 8-bit pass: histogram (tile x digit counts) -> per-table scan -> stable scatter (warp
+//   match-any ranking, no atomics on the output path); then head flags -> scan -> segment list.
+// Tables are sorted independently (a tile never straddles two tables), so only ceil(log2(rows)/8)
+// passes are needed instead of covering a global (table, id) key.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace ptrec {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 8;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 2048
+constexpr int kRadix = 256;
+
+struct TableLayout {
+  int32_t T;
+  int32_t total_tiles;
+  int64_t Lstart[kMaxTables + 1];      // slots of table t: [Lstart[t]*B, Lstart[t+1]*B)
+  int32_t tile_prefix[kMaxTables + 1]; // first sort tile of table t
+};
+
+__device__ __forceinline__ int table_of_tile(const TableLayout& lay, int tile) {
+  int lo = 0, hi = lay.T - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (lay.tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+__device__ __forceinline__ int table_of_slot(const TableLayout& lay, int64_t B, int64_t j) {
+  int lo = 0, hi = lay.T - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (lay.Lstart[mid] * B <= j) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// key of slot p straight from the id matrices (first pass only)
+struct KeyGen {
+  const ptrec_feature_desc* feats;  // shared-memory copy
+  int F;
+  const int64_t* ids;
+  const int32_t* lens;
+  const int64_t* table_rows;
+  int64_t B;
+  __device__ __forceinline__ uint32_t operator()(int64_t p) const {
+    const int f = find_feature(feats, F, B, p);
+    const ptrec_feature_desc& fd = feats[f];
+    const int64_t rel = p - fd.id_base * B;
+    const int64_t b = rel / fd.bag_len;
+    const int l = (int)(rel - b * fd.bag_len);
+    const int64_t id = ids[p];
+    bool valid = slot_valid(fd.mask_mode, id, l, lens, fd.lens_col, B, b);
+    valid = valid && ((uint64_t)id < (uint64_t)table_rows[fd.table]);
+    return valid ? (uint32_t)id : kMaskedKey;
+  }
+};
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads)
+radix_hist_kernel(TableLayout lay, int64_t B, int shift, const uint32_t* __restrict__ keys_in,
+                  const ptrec_feature_desc* __restrict__ feats, int F, const int64_t* __restrict__ ids,
+                  const int32_t* __restrict__ lens, const int64_t* __restrict__ table_rows,
+                  int* __restrict__ hist) {
+  __shared__ int s_hist[kRadix];
+  __shared__ ptrec_feature_desc s_feats[FIRST ? kMaxFeatures : 1];
+  const int tile = blockIdx.x;
+  const int t = table_of_tile(lay, tile);
+  const int k = tile - lay.tile_prefix[t];
+  const int tiles_t = lay.tile_prefix[t + 1] - lay.tile_prefix[t];
+  const int64_t beg = lay.Lstart[t] * B + (int64_t)k * kSortTile;
+  const int64_t end = min(lay.Lstart[t + 1] * B, beg + kSortTile);
+  s_hist[threadIdx.x] = 0;
+  if (FIRST) load_feats(s_feats, feats, F);
+  __syncthreads();
+  KeyGen gen{s_feats, F, ids, lens, table_rows, B};
+  for (int64_t j = beg + threadIdx.x; j < end; j += kSortThreads) {
+    const uint32_t key = FIRST ? gen(j) : keys_in[j];
+    atomicAdd(&s_hist[(key >> shift) & (kRadix - 1)], 1);
+  }
+  __syncthreads();
+  hist[(int64_t)lay.tile_prefix[t] * kRadix + (int64_t)threadIdx.x * tiles_t + k] = s_hist[threadIdx.x];
+}
+
+// one CTA per table: exclusive scan of its [256][tiles_t] counts, seeded with the table's first slot
+__global__ void __launch_bounds__(1024) radix_scan_kernel(TableLayout lay, int64_t B, int* __restrict__ hist) {
+  __shared__ int s_warp[33];
+  __shared__ int s_carry;
+  const int t = blockIdx.x;
+  const int tiles_t = lay.tile_prefix[t + 1] - lay.tile_prefix[t];
+  const int M = tiles_t * kRadix;
+  int* h = hist + (int64_t)lay.tile_prefix[t] * kRadix;
+  if (threadIdx.x == 0) s_carry = (int)(lay.Lstart[t] * B);
+  __syncthreads();
+  for (int base = 0; base < M; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < M ? h[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, s_warp, &total);
+    const int carry = s_carry;
+    if (i < M) h[i] = ex + carry;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads)
+radix_scatter_kernel(TableLayout lay, int64_t B, int shift, const uint32_t* __restrict__ keys_in,
+                     const int32_t* __restrict__ perm_in, const ptrec_feature_desc* __restrict__ feats,
+                     int F, const int64_t* __restrict__ ids, const int32_t* __restrict__ lens,
+                     const int64_t* __restrict__ table_rows, const int* __restrict__ offsets,
+                     uint32_t* __restrict__ keys_out, int32_t* __restrict__ perm_out) {
+  constexpr int NW = kSortThreads / 32;
+  __shared__ int s_cnt[NW][kRadix];
+  __shared__ int s_goff[kRadix];
+  __shared__ ptrec_feature_desc s_feats[FIRST ? kMaxFeatures : 1];
+  const int tile = blockIdx.x;
+  const int t = table_of_tile(lay, tile);
+  const int k = tile - lay.tile_prefix[t];
+  const int tiles_t = lay.tile_prefix[t + 1] - lay.tile_prefix[t];
+  const int64_t beg = lay.Lstart[t] * B + (int64_t)k * kSortTile;
+  const int64_t end = min(lay.Lstart[t + 1] * B, beg + kSortTile);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) s_cnt[w][threadIdx.x] = 0;
+  s_goff[threadIdx.x] = offsets[(int64_t)lay.tile_prefix[t] * kRadix + (int64_t)threadIdx.x * tiles_t + k];
+  if (FIRST) load_feats(s_feats, feats, F);
+  __syncthreads();
+  KeyGen gen{s_feats, F, ids, lens, table_rows, B};
+
+  uint32_t key[kSortItems];
+  int32_t pay[kSortItems];
+  int rank[kSortItems];
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int64_t j = beg + warp * (32 * kSortItems) + i * 32 + lane;
+    const bool in = j < end;
+    key[i] = 0;
+    pay[i] = 0;
+    if (in) {
+      key[i] = FIRST ? gen(j) : keys_in[j];
+      pay[i] = FIRST ? (int32_t)j : perm_in[j];
+    }
+    const int d = in ? (int)((key[i] >> shift) & (kRadix - 1)) : kRadix;  // kRadix = "no key" group
+    const unsigned m = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (in) base = s_cnt[warp][d];
+    __syncwarp();
+    if (in && lane == leader) s_cnt[warp][d] = base + __popc(m);
+    __syncwarp();
+    rank[i] = base + __popc(m & lt);
+  }
+  __syncthreads();
+  {  // exclusive prefix over warps for digit d = threadIdx.x
+    int run = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const int c = s_cnt[w][threadIdx.x];
+      s_cnt[w][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int64_t j = beg + warp * (32 * kSortItems) + i * 32 + lane;
+    if (j < end) {
+      const int d = (int)((key[i] >> shift) & (kRadix - 1));
+      const int pos = s_goff[d] + s_cnt[warp][d] + rank[i];
+      keys_out[pos] = key[i];
+      perm_out[pos] = pay[i];
+    }
+  }
+}
+
+// ---- dedup: head flags -> exclusive scan -> segment list --------------------------------------
+struct HeadIn {
+  TableLayout lay;
+  int64_t B;
+  const uint32_t* keys;
+  __device__ int operator()(int64_t j) const {
+    if (j == 0) return 1;
+    if (keys[j] != keys[j - 1]) return 1;
+    const int t = table_of_slot(lay, B, j);
+    return (lay.Lstart[t] * B == j) ? 1 : 0;
+  }
+};
+struct SegOut {
+  TableLayout lay;
+  int64_t B;
+  int64_t N;
+  int32_t* seg_start;
+  int32_t* seg_table;
+  __device__ void operator()(int64_t j, int prefix, int v) const {
+    if (v) {
+      seg_start[prefix] = (int32_t)j;
+      seg_table[prefix] = table_of_slot(lay, B, j);
+    }
+    if (j == N - 1) seg_start[prefix + v] = (int32_t)N;
+  }
+};
+
+}  // namespace ptrec
+
+using namespace ptrec;
+
+static int build_layout(const ptrec_feature_desc* feats_host, int F, int T, int64_t B, TableLayout* lay,
+                        int64_t* N_out) {
+  PTREC_CHECK_ARG(T >= 1 && T <= kMaxTables && F >= 1 && F <= kMaxFeatures, PTREC_EINVAL,
+                  "sort_dedup: T=%d F=%d out of range", T, F);
+  lay->T = T;
+  int64_t L = 0;
+  int f = 0;
+  for (int t = 0; t < T; ++t) {
+    lay->Lstart[t] = L;
+    while (f < F && feats_host[f].table == t) {
+      PTREC_CHECK_ARG(feats_host[f].id_base == L && feats_host[f].bag_len >= 1, PTREC_EINVAL,
+                      "sort_dedup: feature %d id_base/bag_len inconsistent", f);
+      L += feats_host[f].bag_len;
+      ++f;
+    }
+  }
+  PTREC_CHECK_ARG(f == F, PTREC_EINVAL, "sort_dedup: features must be ordered by table (0..T-1)");
+  lay->Lstart[T] = L;
+  for (int t = T + 1; t <= kMaxTables; ++t) lay->Lstart[t] = L;
+  int tiles = 0;
+  for (int t = 0; t < T; ++t) {
+    lay->tile_prefix[t] = tiles;
+    tiles += (int)ceil_div((lay->Lstart[t + 1] - lay->Lstart[t]) * B, kSortTile);
+  }
+  for (int t = T; t <= kMaxTables; ++t) lay->tile_prefix[t] = tiles;
+  lay->total_tiles = tiles;
+  *N_out = L * B;
+  return PTREC_OK;
+}
+
+extern "C" size_t ptrec_sort_dedup_workspace_bytes(int64_t N, int32_t T) {
+  const size_t tiles = (size_t)ceil_div(N, kSortTile) + (size_t)T + 1;
+  size_t bytes = 0;
+  bytes += align_up((size_t)N * 4, 256);                       // keys_tmp
+  bytes += align_up((size_t)N * 4, 256);                       // perm_tmp
+  bytes += align_up(tiles * kRadix * 4, 256);                  // hist
+  bytes += align_up(((size_t)scan_num_tiles(N) + 1) * 4, 256); // head scan tile sums
+  return bytes + 256;
+}
+
+extern "C" int ptrec_sort_dedup(const ptrec_feature_desc* feats, const ptrec_feature_desc* feats_host,
+                                int32_t F, int32_t T, const int64_t* table_rows, int64_t max_rows_host,
+                                const int64_t* ids, const int32_t* lens, int64_t B,
+                                uint32_t* sorted_keys, int32_t* perm, int32_t* seg_start,
+                                int32_t* seg_table, int32_t* n_seg, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  PTREC_CHECK_ARG(feats && feats_host && table_rows && ids && sorted_keys && perm && seg_start && seg_table && n_seg,
+                  PTREC_EINVAL, "sort_dedup: null pointer");
+  PTREC_CHECK_ARG(max_rows_host >= 1 && max_rows_host < (int64_t)0xFFFFFFFFLL, PTREC_EUNSUPPORTED,
+                  "sort_dedup: tables must have < 2^32-1 rows");
+  TableLayout lay;
+  int64_t N = 0;
+  int rc = build_layout(feats_host, F, T, B, &lay, &N);
+  if (rc != PTREC_OK) return rc;
+  PTREC_CHECK_ARG(N < (int64_t)0x7fffffff, PTREC_EUNSUPPORTED, "sort_dedup: N=%lld slots must be < 2^31", (long long)N);
+  PTREC_CHECK_ARG(workspace && workspace_bytes >= ptrec_sort_dedup_workspace_bytes(N, T), PTREC_EWORKSPACE,
+                  "sort_dedup: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) {
+    PTREC_CUDA(cudaMemsetAsync(n_seg, 0, sizeof(int32_t), st));
+    PTREC_CUDA(cudaMemsetAsync(seg_start, 0, sizeof(int32_t), st));
+    return PTREC_OK;
+  }
+  // passes: smallest P with 2^(8P) - 1 >= max_rows (so the masked key sorts strictly last)
+  int P = 1;
+  while (P < 4 && ((1ull << (8 * P)) - 1ull) < (unsigned long long)max_rows_host) ++P;
+
+  unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+  uint32_t* keys_tmp = reinterpret_cast<uint32_t*>(w); w += align_up((size_t)N * 4, 256);
+  int32_t* perm_tmp = reinterpret_cast<int32_t*>(w);   w += align_up((size_t)N * 4, 256);
+  int* hist = reinterpret_cast<int*>(w);
+  w += align_up(((size_t)ceil_div(N, kSortTile) + (size_t)T + 1) * kRadix * 4, 256);
+  int* tile_sums = reinterpret_cast<int*>(w);
+
+  const uint32_t* kin = nullptr;
+  const int32_t* pin = nullptr;
+  for (int p = 0; p < P; ++p) {
+    const bool to_out = ((P - 1 - p) % 2) == 0;
+    uint32_t* kout = to_out ? sorted_keys : keys_tmp;
+    int32_t* pout = to_out ? perm : perm_tmp;
+    const int shift = 8 * p;
+    if (p == 0) {
+      radix_hist_kernel<true><<<lay.total_tiles, kSortThreads, 0, st>>>(lay, B, shift, nullptr, feats, F, ids,
+                                                                        lens, table_rows, hist);
+    } else {
+      radix_hist_kernel<false><<<lay.total_tiles, kSortThreads, 0, st>>>(lay, B, shift, kin, feats, F, ids,
+                                                                         lens, table_rows, hist);
+    }
+    PTREC_LAUNCH_CHECK("radix_hist_kernel");
+    radix_scan_kernel<<<T, 1024, 0, st>>>(lay, B, hist);
+    PTREC_LAUNCH_CHECK("radix_scan_kernel");
+    if (p == 0) {
+      radix_scatter_kernel<true><<<lay.total_tiles, kSortThreads, 0, st>>>(
+          lay, B, shift, nullptr, nullptr, feats, F, ids, lens, table_rows, hist, kout, pout);
+    } else {
+      radix_scatter_kernel<false><<<lay.total_tiles, kSortThreads, 0, st>>>(
+          lay, B, shift, kin, pin, feats, F, ids, lens, table_rows, hist, kout, pout);
+    }
+    PTREC_LAUNCH_CHECK("radix_scatter_kernel");
+    kin = kout;
+    pin = pout;
+  }
+
+  const int stiles = scan_num_tiles(N);
+  HeadIn hin{lay, B, sorted_keys};
+  SegOut sout{lay, B, N, seg_start, seg_table};
+  scan_tile_sums_kernel<<<stiles, kScanThreads, 0, st>>>(hin, N, tile_sums);
+  PTREC_LAUNCH_CHECK("scan_tile_sums_kernel(heads)");
+  scan_top_kernel<<<1, 1024, 0, st>>>(tile_sums, stiles, n_seg);
+  PTREC_LAUNCH_CHECK("scan_top_kernel(heads)");
+  scan_apply_kernel<<<stiles, kScanThreads, 0, st>>>(hin, sout, N, tile_sums);
+  PTREC_LAUNCH_CHECK("scan_apply_kernel(heads)");
+  return PTREC_OK;
+}

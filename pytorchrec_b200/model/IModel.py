@@ -1,0 +1,193 @@
+"""Training runtime with the reference's ``IModel`` surface (torchrec/model/IModel.py:34-321).
+
+Lifecycle is the reference's: ``set_torch_seed`` -> ``Module.__init__`` -> ``_init_weights()``
+(subclass builds its layers in declaration order) -> ``_reset_weights()`` re-draws N(0, 0.01) for
+every Linear / Embedding weight and bias (IModel.py:37-71).  ``compile`` type-checks its arguments
+the same way (:94-114) and ``train_step`` is the same five-line hot loop (:116-125).  What differs
+is underneath: embedding modules launch the sm_100a kernels, and a fused sparse optimizer applies
+the table update inside ``loss.backward()``.
+"""
+import copy
+import pickle
+from abc import ABC, abstractmethod
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+from torch.nn import Module
+from torch.nn.modules.loss import _Loss  # noqa
+from torch.optim.optimizer import Optimizer
+from torch.utils.data import DataLoader, Dataset
+
+from ..metric import IMetric, MetricList
+from ..utils import set_torch_seed, tensor_to_device
+
+
+class History:
+    """Per-epoch log accumulator (subset of torchrec/callback/History.py:26-40)."""
+
+    def __init__(self):
+        self.epoch: List[int] = []
+        self.history: Dict[str, List[Any]] = {}
+
+    def on_epoch_end(self, epoch: int, logs: Dict[str, Any]):
+        self.epoch.append(epoch)
+        for k, v in logs.items():
+            if isinstance(v, torch.Tensor):
+                v = v.item()
+            self.history.setdefault(k, []).append(v)
+
+
+class IModel(Module, ABC):
+    """Model interface: subclasses implement ``_init_weights`` and ``forward(data) -> (prediction, target)``."""
+
+    @classmethod
+    def get_argument_descriptions(cls) -> list:
+        return []
+
+    @classmethod
+    def check_argument_values(cls, arguments: Dict[str, Any]) -> None:
+        return None
+
+    def __init__(self, random_seed: int, **kwargs):  # noqa
+        set_torch_seed(random_seed)
+        super().__init__()
+        self.stop_training = False
+        self.best_state_dict = None
+        self.history: Optional[History] = None
+        self._is_compiled = False
+        self.compiled_optimizers: Optional[Optimizer] = None
+        self.compiled_loss: Optional[_Loss] = None
+        self.compiled_metrics: Optional[MetricList] = None
+        self.compiled_device: Optional[torch.device] = None
+        self._init_weights()
+        self._reset_weights()
+
+    @abstractmethod
+    def _init_weights(self):
+        pass
+
+    @staticmethod
+    def _reset_weights_fn(m):
+        # same predicate and draw order as IModel.py:61-68
+        if 'Linear' in str(type(m)):
+            torch.nn.init.normal_(m.weight, mean=0.0, std=0.01)
+            if m.bias is not None:
+                torch.nn.init.normal_(m.bias, mean=0.0, std=0.01)
+        elif 'Embedding' in str(type(m)):
+            torch.nn.init.normal_(m.weight, mean=0.0, std=0.01)
+
+    def _reset_weights(self):
+        self.apply(self._reset_weights_fn)
+
+    # ------------------------------------------------------------------ weights
+    def load_weights(self, filepath: str, device: torch.device):
+        state_dict = torch.load(filepath, map_location=device)
+        self.load_state_dict(state_dict)
+        self.to(device)
+
+    def save_weights(self, filepath: str):
+        torch.save(self.state_dict(), filepath, pickle_protocol=pickle.HIGHEST_PROTOCOL)
+
+    def get_parameters(self):
+        """Two param groups: weights, and biases with ``weight_decay=0`` (IModel.py:83-92)."""
+        weight_p, bias_p = [], []
+        for name, p in self.named_parameters():
+            if not p.requires_grad:
+                continue
+            (bias_p if 'bias' in name else weight_p).append(p)
+        return [{'params': weight_p}, {'params': bias_p, 'weight_decay': 0.0}]
+
+    # ------------------------------------------------------------------ compile / step
+    def compile(self, optimizer: Optimizer, loss: _Loss, metrics: List[IMetric], device: torch.device):
+        if not isinstance(optimizer, Optimizer):
+            raise ValueError(f"invalid optimizer: {optimizer}")
+        if not isinstance(loss, _Loss):
+            raise ValueError(f"invalid loss: {loss}")
+        if (not isinstance(metrics, list)) or not all(isinstance(m, IMetric) for m in metrics):
+            raise ValueError(f"invalid metrics: {metrics}")
+        if not isinstance(device, torch.device):
+            raise ValueError(f"invalid device: {device}")
+        self.compiled_optimizers = optimizer
+        self.compiled_loss = loss
+        self.compiled_metrics = MetricList(metrics)
+        self.compiled_device = device
+        self.to(device)
+        self._is_compiled = True
+
+    def train_step(self, data: Dict):
+        self.train()
+        data = tensor_to_device(data, self.compiled_device)
+        prediction, target = self(data)
+        loss = self.compiled_loss(prediction, target)
+        self.compiled_optimizers.zero_grad()
+        loss.backward()
+        self.compiled_optimizers.step(closure=None)
+        return {"loss": loss}
+
+    def test_step(self, data):
+        self.eval()
+        data = tensor_to_device(data, self.compiled_device)
+        prediction, target = self(data)
+        return prediction, target
+
+    def predict_step(self, data):
+        prediction, _ = self.test_step(data)
+        return prediction
+
+    # ------------------------------------------------------------------ fit / evaluate
+    def fit(self, dataset: Dataset, batch_size: int, epochs: int, dev_dataset: Optional[Dataset] = None,
+            train_mode=None, verbose: int = 0, callbacks: Optional[list] = None, shuffle: bool = True,
+            workers: int = 0, drop_last: bool = False, dev_batch_size: Optional[int] = None,
+            dev_freq: int = 1) -> History:
+        self._assert_compile_was_called()
+        callbacks = list(callbacks or [])
+        self.history = History()
+        self.stop_training = False
+        logs: Dict[str, Any] = {}
+        for epoch in range(epochs):
+            if train_mode is not None and getattr(train_mode, "value", train_mode) == "pair_wise" \
+                    and hasattr(dataset, "train_neg_sample"):
+                dataset.train_neg_sample()
+            loader = DataLoader(dataset=dataset, batch_size=batch_size, shuffle=shuffle, num_workers=workers,
+                                drop_last=drop_last)
+            for data in loader:
+                logs = self.train_step(data)
+            epoch_logs = copy.copy(logs)
+            if dev_dataset is not None and (epoch + 1) % dev_freq == 0:
+                epoch_logs.update(self.evaluate(dev_dataset, dev_batch_size or batch_size, workers=workers))
+            self.history.on_epoch_end(epoch, epoch_logs)
+            for cb in callbacks:
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(epoch, epoch_logs)
+            if self.stop_training:
+                break
+        return self.history
+
+    @torch.no_grad()
+    def evaluate(self, dataset: Dataset, batch_size: int, verbose: int = 0, callbacks=None, workers: int = 0):
+        self._assert_compile_was_called()
+        loader = DataLoader(dataset=dataset, batch_size=batch_size, num_workers=workers)
+        predictions, targets = [], []
+        for data in loader:
+            prediction, target = self.test_step(data)
+            predictions.append(prediction.detach().cpu().numpy())
+            targets.append(target.detach().cpu().numpy())
+        return self.compiled_metrics(np.concatenate(predictions), np.concatenate(targets))
+
+    @torch.no_grad()
+    def predict(self, dataset: Dataset, batch_size: int, verbose: int = 0, callbacks=None, workers: int = 0):
+        loader = DataLoader(dataset=dataset, batch_size=batch_size, num_workers=workers)
+        return np.concatenate([self.predict_step(d).detach().cpu().numpy() for d in loader])
+
+    def _assert_compile_was_called(self):
+        if not self._is_compiled:
+            raise RuntimeError('compile() must be called before fit/evaluate')
+
+    def save_best_weights(self):
+        self.best_state_dict = copy.deepcopy(tensor_to_device(dict(self.state_dict()), device=torch.device("cpu")))
+
+    def load_best_weights(self):
+        assert self.best_state_dict is not None
+        self.load_state_dict(self.best_state_dict)
+        self.to(self.compiled_device)

@@ -1,0 +1,24 @@
+"""Models with the reference's ``torchrec.model`` surface (``IModel`` + name registry,
+torchrec/model/models.py:8-30)."""
+from typing import Dict, Type
+
+from .IModel import History, IModel
+from .ctr import FM, DeepFM
+from .mf import SVDPP, FunkSVD
+
+_model_classes: Dict[str, Type[IModel]] = {
+    "funksvd": FunkSVD,
+    "svdpp": SVDPP,
+    "fm": FM,
+    "deepfm": DeepFM,
+}
+model_name_list = _model_classes.keys()
+
+
+def get_model_type(model_name: str) -> Type[IModel]:
+    if (not isinstance(model_name, str)) or (model_name not in _model_classes):
+        raise ValueError(f"invalid model_name: {model_name}")
+    return _model_classes[model_name]
+
+
+__all__ = ["IModel", "History", "FM", "DeepFM", "FunkSVD", "SVDPP", "get_model_type", "model_name_list"]

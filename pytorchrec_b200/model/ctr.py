@@ -1,0 +1,83 @@
+"""CTR models on the fused embedding path: FM and DeepFM.
+
+The reference ships neither; they are written in its idiom — column objects in the
+constructor, layers created in ``_init_weights`` (torchrec/model/FunkSVD.py:27-41), embedding + bias
++ global-bias layout of SVDPP.py:36-42, ``concat -> MLP -> Linear(..., 1, bias=False)`` head of
+NCF.py:44-51,68-74, point-wise target ``label.float()`` (FunkSVD.py:53-55).  Outputs are logits
+(train with the ``bce`` loss).  ``oracle/ref_models.py`` holds the plain-torch twins with identical
+parameter names and RNG draw order.
+
+  FM:      y = w0 + sum_f w_f[id_f] + <w_dense, x> + 0.5 * sum_k((sum_f v_fk)^2 - sum_f v_fk^2)
+  DeepFM:  y = FM + Linear(MLP(concat_f v_f || x))
+"""
+from typing import Dict, List, Optional
+
+import torch
+from torch import Tensor
+from torch.nn import Linear, Parameter
+
+from ..feature_column import CategoricalColumnWithIdentity, NumericColumn
+from .IModel import IModel
+from .layer import MLP, FMSecondOrder, MultiTableEmbedding
+
+
+def _dense_matrix(dense_columns: List[NumericColumn], data: Dict[str, Tensor]) -> Optional[Tensor]:
+    if not dense_columns:
+        return None
+    return torch.stack([c.get_feature_data(data) for c in dense_columns], dim=1)
+
+
+class FM(IModel):
+    def __init__(self, sparse_columns: List[CategoricalColumnWithIdentity], dense_columns: List[NumericColumn],
+                 label_column: CategoricalColumnWithIdentity, emb_size: int, **kwargs):
+        self.sparse_columns = list(sparse_columns)
+        self.dense_columns = list(dense_columns or [])
+        self.label_column = label_column
+        self.emb_size = emb_size
+        super().__init__(**kwargs)
+
+    def _init_weights(self):
+        self.embeddings = MultiTableEmbedding(self.sparse_columns, self.emb_size)
+        self.first_order = MultiTableEmbedding(self.sparse_columns, 1)
+        if self.dense_columns:
+            self.dense_linear = Linear(len(self.dense_columns), 1, bias=False)
+        self.global_bias = Parameter(torch.tensor(0.0))
+        self.fm2 = FMSecondOrder()
+
+    def _fm_logit(self, data, v: Tensor, x: Optional[Tensor]) -> Tensor:
+        w = self.first_order(data)  # [B, F, 1]
+        logit = w.sum(dim=(1, 2)) + self.fm2(v) + self.global_bias
+        if x is not None:
+            logit = logit + self.dense_linear(x).squeeze(-1)
+        return logit
+
+    def _target(self, data):
+        target = self.label_column.get_feature_data(data)
+        return target.float() if target is not None else None
+
+    def forward(self, data: Dict[str, Tensor]):
+        v = self.embeddings(data)  # [B, F, D]
+        x = _dense_matrix(self.dense_columns, data)
+        return self._fm_logit(data, v, x), self._target(data)
+
+
+class DeepFM(FM):
+    def __init__(self, sparse_columns, dense_columns, label_column, emb_size: int, layers: List[int],
+                 dropout: float = 0.0, **kwargs):
+        self.layers = list(layers)
+        self.dropout = dropout
+        super().__init__(sparse_columns, dense_columns, label_column, emb_size, **kwargs)
+
+    def _init_weights(self):
+        super()._init_weights()
+        in_units = len(self.sparse_columns) * self.emb_size + len(self.dense_columns)
+        self.mlp = MLP(input_units=in_units, hidden_units_list=self.layers, activation="relu", dropout=self.dropout)
+        self.deep_out = Linear(self.layers[-1], 1, bias=False)
+
+    def forward(self, data: Dict[str, Tensor]):
+        v = self.embeddings(data)
+        x = _dense_matrix(self.dense_columns, data)
+        flat = v.reshape(v.shape[0], -1)
+        deep_in = torch.cat([flat, x], dim=1) if x is not None else flat
+        logit = self._fm_logit(data, v, x) + self.deep_out(self.mlp(deep_in)).squeeze(-1)
+        return logit, self._target(data)

@@ -1,0 +1,5 @@
+from .dense import MLP, Dense
+from .embedding import EmbeddingTable, MultiTableEmbedding
+from .interaction import FMSecondOrder
+
+__all__ = ["Dense", "MLP", "EmbeddingTable", "MultiTableEmbedding", "FMSecondOrder"]

@@ -1,0 +1,280 @@
+"""Embedding modules backed by the sm_100a kernels.
+
+The reference's embedding seam is ``torch.nn.Embedding(column.category_num, emb_size)`` created in
+``_init_weights`` and indexed with ``column.get_feature_data(batch)`` (torchrec/model/FunkSVD.py:39-48,
+SVDPP.py:36-61, NCF.py:38-65).  ``EmbeddingTable`` is a drop-in for that module (same constructor,
+same ``weight`` parameter name, same RNG consumption at construction, caught by
+``IModel._reset_weights_fn`` because its type name contains 'Embedding', IModel.py:61-68).
+``MultiTableEmbedding`` is an ``nn.ModuleList`` of such tables built from a list of columns; it
+runs all lookups + pooling of a batch in one gather launch and one fused backward.
+
+Backward semantics: gradients never materialise as ``[rows, D]`` tensors.  When the tables are
+owned by a ``pytorchrec_b200.optim`` sparse optimizer the row update happens inside ``backward()``
+(sort -> dedup -> segment-sum -> update); otherwise ``weight.grad`` receives a coalesced
+``torch.sparse_coo_tensor`` built from the same segment sums.
+"""
+from typing import Dict, List, Optional, Sequence, Union
+
+import torch
+from torch import Tensor, nn
+
+from ... import ops
+from ...feature_column import CategoricalColumn
+
+_MASKED = -1  # 0xFFFFFFFF viewed as int32
+
+
+class EmbeddingGroup:
+    """Non-module helper: a set of tables sharing ``dim`` + the feature layout reading them."""
+
+    def __init__(self, tables: Sequence["EmbeddingTable"], dim: int):
+        self.tables = list(tables)
+        self.dim = dim
+        self.table_set = ops.TableSet()
+        self._err: Dict[torch.device, Tensor] = {}
+        self._state_cache = None
+
+    def weights(self) -> List[Tensor]:
+        return [t.weight for t in self.tables]
+
+    def err_flag(self, device) -> Tensor:
+        e = self._err.get(device)
+        if e is None:
+            e = torch.zeros(1, dtype=torch.int32, device=device)
+            self._err[device] = e
+        return e
+
+    def check_index_errors(self) -> None:
+        """Synchronising check: raises IndexError if any lookup so far was out of range (the
+        reference raises IndexError from ``index_select`` on CPU)."""
+        for e in self._err.values():
+            if int(e.item()) != 0:
+                e.zero_()
+                raise IndexError("embedding id out of range [0, category_num)")
+
+    # -------------------------------------------------------------------------------- backward
+    def binding(self):
+        b = None
+        for t in self.tables:
+            tb = getattr(t.weight, "_ptrec_optim", None)
+            if b is None:
+                b = tb
+            elif tb is not None and (tb[0] is not b[0] or tb[1] is not b[1]):
+                raise RuntimeError("all tables of one MultiTableEmbedding must sit in the same param "
+                                   "group of the same fused optimizer")
+            elif tb is None and b is not None:
+                raise RuntimeError("some tables of this embedding group are not owned by the fused optimizer")
+        return b
+
+    def apply_backward(self, layout, ids, lens, bag_scale, batch, grad_out):
+        tables = self.table_set.refresh([w.data for w in self.weights()])
+        srt = ops.sort_dedup(tables, layout, ids, lens, batch)
+        bind = self.binding()
+        if bind is not None:
+            optimizer, group = bind
+            s1, s2, args = optimizer._fused_prepare(self, group)
+            ops.bwd_fused(tables, s1, s2, layout, batch, srt, grad_out, bag_scale, args)
+            return [None] * len(self.tables)
+        # stock-optimizer mode: coalesced sparse gradients (one host sync for the segment count)
+        row_grad = ops.segment_sum(layout, batch, srt, grad_out, bag_scale)
+        n = int(srt.n_seg.item())
+        keys = srt.sorted_keys[srt.seg_start[:n].long()]
+        seg_table = srt.seg_table[:n]
+        valid = keys != _MASKED
+        grads = []
+        for t, table in enumerate(self.tables):
+            sel = valid & (seg_table == t)
+            idx = keys[sel].long() & 0xFFFFFFFF
+            grads.append(torch.sparse_coo_tensor(idx.unsqueeze(0), row_grad[:n][sel], size=table.weight.shape,
+                                                 is_coalesced=True))
+        return grads
+
+
+class _FusedLookup(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, group: EmbeddingGroup, layout, ids, lens, batch, *weights):
+        tables = group.table_set.refresh([w.detach() for w in weights])
+        needs_scale = any(fd.pooling != 0 for fd in layout.host)
+        out, bag_scale = ops.gather_pool_fwd(tables, layout, ids, lens, batch, want_scale=needs_scale,
+                                             err_flag=group.err_flag(ids.device))
+        ctx.group, ctx.layout, ctx.batch = group, layout, batch
+        ctx.save_for_backward(ids, lens, bag_scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ids, lens, bag_scale = ctx.saved_tensors
+        if not (grad_out.stride(1) == 1 and grad_out.data_ptr() % 16 == 0 and grad_out.stride(0) % 4 == 0):
+            grad_out = grad_out.contiguous()
+        grads = ctx.group.apply_backward(ctx.layout, ids, lens, bag_scale, ctx.batch, grad_out)
+        return (None, None, None, None, None, *grads)
+
+
+class EmbeddingTable(nn.Module):
+    """``nn.Embedding``-compatible table: ``EmbeddingTable(num_embeddings, embedding_dim)``,
+    parameter ``weight`` ``[num_embeddings, embedding_dim]`` fp32, N(0,1) at construction like
+    ``nn.Embedding.reset_parameters``.  ``forward(ids)`` returns ``weight[ids]`` for ids of any shape."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, device=None):
+        super().__init__()
+        self.num_embeddings = int(num_embeddings)
+        self.embedding_dim = int(embedding_dim)
+        self.weight = nn.Parameter(torch.empty(self.num_embeddings, self.embedding_dim, device=device))
+        nn.init.normal_(self.weight)
+        self._group = None
+        self._layout = None
+        self._tag()
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        self._tag()
+        return out
+
+    def _tag(self):
+        self.weight._ptrec_table = self
+
+    def forward(self, ids: Tensor) -> Tensor:
+        if self._group is None:
+            self._group = EmbeddingGroup([self], self.embedding_dim)
+            self._layout = ops.FeatureLayout([{"table": 0, "bag_len": 1}], self.embedding_dim, 1)
+        self._tag()
+        flat = ids.reshape(-1)
+        if flat.dtype != torch.int64:
+            flat = flat.long()
+        flat = flat.contiguous()
+        out = _FusedLookup.apply(self._group, self._layout, flat, None, flat.numel(), self.weight)
+        return out.view(*ids.shape, self.embedding_dim)
+
+    def pooled(self, ids: Tensor, pooling: str = "sum", mask: str = "pad", lens: Optional[Tensor] = None) -> Tensor:
+        """Masked bag pooling of padded ``ids [B, L]`` -> ``[B, D]`` without materialising ``[B, L, D]``:
+        the fused form of SVDPP.py:49-55 (``pooling='sqrtn', mask='pad'``) and SASRec.py:109-110
+        (``pooling='mean'``, ``mask='pad_keep_first'`` or ``'lens'``)."""
+        assert ids.dim() == 2
+        if self._group is None:
+            self._group = EmbeddingGroup([self], self.embedding_dim)
+            self._layout = ops.FeatureLayout([{"table": 0, "bag_len": 1}], self.embedding_dim, 1)
+        B, L = ids.shape
+        key = (L, pooling, mask)
+        cache = self.__dict__.setdefault("_bag_layouts", {})
+        lay = cache.get(key)
+        if lay is None:
+            lay = ops.FeatureLayout([{"table": 0, "bag_len": L, "pooling": pooling, "mask": mask,
+                                      "lens_col": 0 if mask == "lens" else -1}], self.embedding_dim, 1)
+            cache[key] = lay
+        self._tag()
+        flat = ids.reshape(-1)
+        flat = (flat if flat.dtype == torch.int64 else flat.long()).contiguous()
+        lens32 = None
+        if mask == "lens":
+            if lens is None:
+                raise ValueError("mask='lens' needs lens")
+            lens32 = lens.reshape(1, B).to(torch.int32).contiguous()
+        return _FusedLookup.apply(self._group, lay, flat, lens32, B, self.weight)
+
+    def extra_repr(self):
+        return f"{self.num_embeddings}, {self.embedding_dim}"
+
+
+class MultiTableEmbedding(nn.ModuleList):
+    """All sparse features of a model behind one fused lookup.
+
+    Children are ``EmbeddingTable`` modules, one per distinct table, registered in column order —
+    so ``state_dict()`` keys (``<name>.<i>.weight``) and seeded initialisation match an
+    ``nn.ModuleList([nn.Embedding(c.category_num, emb_size) for c in columns])`` written in the
+    reference's idiom.
+
+    :param columns: categorical columns, one per sparse feature.
+    :param emb_size: embedding dim D (1, 2 or a multiple of 4 up to 128).
+    :param pooling: 'sum' | 'mean' | 'sqrtn' for multi-hot features ([B, L] ids); one-hot ([B]) features ignore it.
+    :param mask: 'none' | 'pad' (id != 0, SVDPP.py:49) | 'pad_keep_first' (model/utils.py:5-10) | 'lens'.
+    :param lens_columns: for mask='lens', ``{feature_name: CategoricalColumn}`` giving the valid length.
+    :param share: ``{feature_name: feature_name_of_table_owner}`` — several features reading one table.
+    ``pooling`` / ``mask`` may also be dicts keyed by feature name.
+    ``forward(batch)`` returns ``[B, F, D]`` in ``columns`` order.
+    """
+
+    def __init__(self, columns: Sequence[CategoricalColumn], emb_size: int,
+                 pooling: Union[str, Dict[str, str]] = "sum", mask: Union[str, Dict[str, str]] = "none",
+                 lens_columns: Optional[Dict[str, CategoricalColumn]] = None,
+                 share: Optional[Dict[str, str]] = None, device=None):
+        super().__init__()
+        self.columns = list(columns)
+        self.emb_size = int(emb_size)
+        names = [getattr(c, "feature_name", str(i)) for i, c in enumerate(self.columns)]
+        self.feature_names = names
+        share = share or {}
+        self._table_of: List[int] = []
+        owner_index: Dict[str, int] = {}
+        for i, (c, name) in enumerate(zip(self.columns, names)):
+            owner = share.get(name, name)
+            if owner not in owner_index:
+                if owner != name:
+                    raise ValueError(f"feature {name} shares the table of {owner}, which must come first")
+                owner_index[owner] = len(self)
+                self.append(EmbeddingTable(c.category_num, self.emb_size, device=device))
+            self._table_of.append(owner_index[owner])
+        self._pooling = {n: (pooling.get(n, "sum") if isinstance(pooling, dict) else pooling) for n in names}
+        self._mask = {n: (mask.get(n, "none") if isinstance(mask, dict) else mask) for n in names}
+        self._lens_columns = lens_columns or {}
+        # internal feature order: by table, then by position
+        self._order = sorted(range(len(names)), key=lambda i: (self._table_of[i], i))
+        self._layouts: Dict[tuple, ops.FeatureLayout] = {}
+        self._group: Optional[EmbeddingGroup] = None
+
+    @property
+    def tables(self) -> List[EmbeddingTable]:
+        return [m for m in self]
+
+    @property
+    def weight(self) -> Tensor:
+        """Zero-size placeholder.  The reference's ``_reset_weights_fn`` (IModel.py:61-68) calls
+        ``normal_(m.weight)`` on every module whose type name contains 'Embedding'; the container
+        itself owns no parameter (its children do), and ``normal_`` on an empty tensor draws nothing."""
+        return torch.empty(0)
+
+    def _layout_for(self, bag_lens: tuple) -> ops.FeatureLayout:
+        lay = self._layouts.get(bag_lens)
+        if lay is None:
+            specs = []
+            lens_cols: List[str] = []
+            for i in self._order:
+                name = self.feature_names[i]
+                m = self._mask[name] if bag_lens[i] > 1 or self._mask[name] == "lens" else "none"
+                lens_col = -1
+                if m == "lens":
+                    if name not in self._lens_columns:
+                        raise ValueError(f"feature {name}: mask='lens' needs lens_columns[{name!r}]")
+                    if name not in lens_cols:
+                        lens_cols.append(name)
+                    lens_col = lens_cols.index(name)
+                specs.append({"table": self._table_of[i], "bag_len": bag_lens[i],
+                              "pooling": self._pooling[name], "mask": m, "lens_col": lens_col})
+            lay = ops.FeatureLayout(specs, self.emb_size, len(self))
+            # output columns follow the user's column order, not the internal (table-sorted) one
+            for k, i in enumerate(self._order):
+                lay.host[k].out_col = i * self.emb_size
+            lay.lens_names = lens_cols
+            self._layouts[bag_lens] = lay
+        return lay
+
+    def forward(self, batch: Dict[str, Tensor]) -> Tensor:
+        if self._group is None:
+            self._group = EmbeddingGroup(self.tables, self.emb_size)
+        id_list = [c.get_feature_data(batch) for c in self.columns]
+        B = id_list[0].shape[0]
+        bag_lens = tuple(1 if t.dim() == 1 else int(t.shape[1]) for t in id_list)
+        layout = self._layout_for(bag_lens)
+        ids = torch.cat([id_list[i].reshape(-1) for i in self._order]) if len(id_list) > 1 \
+            else id_list[0].reshape(-1).contiguous()
+        lens = None
+        if layout.lens_names:
+            lens = torch.stack([self._lens_columns[n].get_feature_data(batch).reshape(-1)
+                                for n in layout.lens_names]).to(torch.int32).contiguous()
+        for t in self.tables:
+            t._tag()
+        out = _FusedLookup.apply(self._group, layout, ids, lens, B, *[t.weight for t in self.tables])
+        return out.view(B, len(self.columns), self.emb_size)
+
+    def check_index_errors(self) -> None:
+        if self._group is not None:
+            self._group.check_index_errors()

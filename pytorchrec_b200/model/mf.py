@@ -1,0 +1,90 @@
+"""The reference's own embedding models re-hosted on the fused tables: FunkSVD and SVD++.
+
+Constructor arguments, attribute names (hence ``state_dict`` keys), forward shapes and outputs follow
+torchrec/model/FunkSVD.py:12-67 and SVDPP.py:12-91; only the embedding modules differ
+(``EmbeddingTable`` / ``MultiTableEmbedding`` instead of ``nn.Embedding``).  They exist so that the
+CUDA path can be checked against the UNMODIFIED reference models on identical weights and batches.
+"""
+from typing import Dict
+
+import torch
+from torch import Tensor
+from torch.nn import Parameter
+
+from ..feature_column import CategoricalColumnWithIdentity
+from .IModel import IModel
+from .layer import EmbeddingTable
+
+
+def _candidate_target(prediction: Tensor) -> Tensor:
+    target = torch.zeros_like(prediction, dtype=torch.float32)
+    target[:, 0] = 1
+    return target
+
+
+class FunkSVD(IModel):
+    def __init__(self, uid_column: CategoricalColumnWithIdentity, iid_column: CategoricalColumnWithIdentity,
+                 label_column: CategoricalColumnWithIdentity, emb_size: int, **kwargs):
+        self.uid_column = uid_column
+        self.iid_column = iid_column
+        self.label_column = label_column
+        self.emb_size = emb_size
+        super().__init__(**kwargs)
+
+    def _init_weights(self):
+        self.u_embeddings = EmbeddingTable(self.uid_column.category_num, self.emb_size)
+        self.i_embeddings = EmbeddingTable(self.iid_column.category_num, self.emb_size)
+
+    def forward(self, data: Dict[str, Tensor]):
+        u_ids = self.uid_column.get_feature_data(data)  # [B]
+        i_ids = self.iid_column.get_feature_data(data)  # [B] or [B, N]
+        u = self.u_embeddings(u_ids)
+        i = self.i_embeddings(i_ids)
+        if i_ids.dim() == 1:
+            prediction = (u * i).sum(dim=-1)
+            target = self.label_column.get_feature_data(data)
+            if target is not None:
+                target = target.float()
+        else:
+            prediction = (u.unsqueeze(1) * i).sum(dim=-1)  # [B, N]
+            target = _candidate_target(prediction)
+        return prediction, target
+
+
+class SVDPP(IModel):
+    def __init__(self, random_seed: int, uid_column: CategoricalColumnWithIdentity,
+                 iid_column: CategoricalColumnWithIdentity, iids_column: CategoricalColumnWithIdentity,
+                 label_column: CategoricalColumnWithIdentity, emb_size: int):
+        self.uid_column = uid_column
+        self.iid_column = iid_column
+        self.iids_column = iids_column
+        self.label_column = label_column
+        self.emb_size = emb_size
+        super().__init__(random_seed)
+
+    def _init_weights(self):
+        self.u_embeddings = EmbeddingTable(self.uid_column.category_num, self.emb_size)
+        self.i_embeddings = EmbeddingTable(self.iid_column.category_num, self.emb_size)
+        self.implicit_i_embeddings = EmbeddingTable(self.iid_column.category_num, self.emb_size)
+        self.u_bias = EmbeddingTable(self.uid_column.category_num, 1)
+        self.i_bias = EmbeddingTable(self.iid_column.category_num, 1)
+        self.global_bias = Parameter(torch.tensor(0.0))
+
+    def forward(self, data: Dict[str, Tensor]):
+        u_ids = self.uid_column.get_feature_data(data)
+        i_ids = self.iid_column.get_feature_data(data)
+        # implicit-feedback bag: masked sum / sqrt(count), SVDPP.py:49-55 -> pooling 'sqrtn', mask 'pad'
+        implicit = self.implicit_i_embeddings.pooled(self.iids_column.get_feature_data(data), "sqrtn", "pad")
+        u = self.u_embeddings(u_ids) + implicit
+        i = self.i_embeddings(i_ids)
+        u_bias = self.u_bias(u_ids).squeeze(-1)
+        i_bias = self.i_bias(i_ids).squeeze(-1)
+        if i_ids.dim() == 1:
+            prediction = (u * i).sum(dim=-1) + u_bias + i_bias + self.global_bias
+            target = self.label_column.get_feature_data(data)
+            if target is not None:
+                target = target.float()
+        else:
+            prediction = (u.unsqueeze(1) * i).sum(dim=-1) + u_bias.unsqueeze(1) + i_bias + self.global_bias
+            target = _candidate_target(prediction)
+        return prediction, target

@@ -1,0 +1,293 @@
+"""Thin torch-facing wrappers over the C ABI (``include/ptrec_b200.h``).
+
+Everything here runs on CUDA tensors and enqueues on the current torch stream; nothing
+synchronises with the host.  There is no CPU path: the CPU implementation of this hot path *is*
+the reference (torchrec/model/IModel.py:116-125 + nn.Embedding + torch.optim).
+"""
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import FeatureDesc, OptimArgs
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "pytorchrec_b200 kernels run on CUDA tensors only; there is no CPU fallback "
+                f"(got a tensor on {t.device})")
+
+
+# ----------------------------------------------------------------------------------------------
+# feature layout: the ptrec_feature_desc array, host and device copies
+# ----------------------------------------------------------------------------------------------
+class FeatureLayout:
+    """Descriptor array for the sparse features of one embedding group (all tables share ``dim``).
+
+    ``specs``: one dict per feature, ordered by table, with keys ``table`` (int), ``bag_len`` (int),
+    ``pooling`` ('sum'|'mean'|'sqrtn'), ``mask`` ('none'|'pad'|'pad_keep_first'|'lens'),
+    ``lens_col`` (int, -1 when unused).  Output columns are laid out feature after feature.
+    """
+
+    def __init__(self, specs: Sequence[Dict], dim: int, n_tables: int):
+        self.dim = int(dim)
+        self.n_tables = int(n_tables)
+        self.n_features = len(specs)
+        if self.n_features < 1 or self.n_features > 128 or self.n_tables > 128:
+            raise ValueError("between 1 and 128 features / tables per embedding group")
+        arr = (FeatureDesc * self.n_features)()
+        id_base = 0
+        prev_table = -1
+        for f, s in enumerate(specs):
+            if s["table"] < prev_table:
+                raise ValueError("features must be ordered by table index")
+            prev_table = s["table"]
+            arr[f].table = int(s["table"])
+            arr[f].bag_len = int(s.get("bag_len", 1))
+            arr[f].pooling = _lib.POOLING_NAMES[s.get("pooling", "sum")]
+            arr[f].mask_mode = _lib.MASK_NAMES[s.get("mask", "none")]
+            arr[f].lens_col = int(s.get("lens_col", -1))
+            arr[f].reserved = 0
+            arr[f].id_base = id_base
+            arr[f].out_col = f * self.dim
+            id_base += arr[f].bag_len
+        self.host = arr
+        self.total_bag_len = id_base
+        self.out_width = self.n_features * self.dim
+        self._dev: Dict[torch.device, torch.Tensor] = {}
+
+    def device_array(self, device: torch.device) -> torch.Tensor:
+        t = self._dev.get(device)
+        if t is None:
+            raw = bytes(self.host)
+            t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+            self._dev[device] = t
+        return t
+
+    def slots(self, batch: int) -> int:
+        return self.total_bag_len * batch
+
+
+_workspaces: Dict[Tuple[str, torch.device], torch.Tensor] = {}
+
+
+def _workspace(name: str, nbytes: int, device: torch.device) -> torch.Tensor:
+    """Grow-only byte scratch per (name, device).  Caller-owned memory, per the ABI contract."""
+    key = (name, device)
+    t = _workspaces.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = t
+    return t
+
+
+# ----------------------------------------------------------------------------------------------
+# index prep
+# ----------------------------------------------------------------------------------------------
+def index_prep(ids_padded: torch.Tensor, lens: Optional[torch.Tensor], mask: str):
+    """Padded ``[B, L]`` int64 ids -> (compact ids, offsets[B+1]).  Bit-exact integer work."""
+    lib = _lib.load()
+    _require_cuda(ids_padded, lens)
+    assert ids_padded.dtype == torch.int64 and ids_padded.dim() == 2 and ids_padded.is_contiguous()
+    B, L = ids_padded.shape
+    dev = ids_padded.device
+    if lens is not None:
+        lens = lens.to(torch.int32).contiguous()
+    out_ids = torch.empty(B * L, dtype=torch.int64, device=dev)
+    offsets = torch.empty(B + 1, dtype=torch.int64, device=dev)
+    nbytes = lib.ptrec_index_prep_workspace_bytes(B)
+    ws = _workspace("index_prep", nbytes, dev)
+    _lib.check(lib.ptrec_index_prep(_ptr(ids_padded), _ptr(lens), B, L, _lib.MASK_NAMES[mask],
+                                    _ptr(out_ids), _ptr(offsets), _ptr(ws), ws.numel(), _stream(dev)),
+               "ptrec_index_prep")
+    return out_ids, offsets
+
+
+# ----------------------------------------------------------------------------------------------
+# K1 / K2 raw calls
+# ----------------------------------------------------------------------------------------------
+class TableSet:
+    """Device pointer arrays for a list of table tensors (+ optimizer state), rebuilt when a
+    tensor moves (``.to(device)``, ``load_state_dict`` keeps pointers)."""
+
+    def __init__(self):
+        self._key = None
+        self.ptrs = None
+        self.rows = None
+        self.max_rows = 0
+
+    def refresh(self, weights: Sequence[torch.Tensor]):
+        key = tuple(w.data_ptr() for w in weights)
+        if key != self._key:
+            dev = weights[0].device
+            for w in weights:
+                _require_cuda(w)
+                if w.dtype != torch.float32 or not w.is_contiguous() or w.device != dev:
+                    raise RuntimeError("embedding tables must be contiguous fp32 CUDA tensors on one device")
+                if w.data_ptr() % 16 != 0:
+                    raise RuntimeError("embedding table base pointer must be 16-byte aligned")
+            self.ptrs = torch.tensor(list(key), dtype=torch.int64).to(dev)
+            self.rows = torch.tensor([w.shape[0] for w in weights], dtype=torch.int64).to(dev)
+            self.max_rows = max(w.shape[0] for w in weights)
+            self._key = key
+        return self
+
+
+def make_ptr_array(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+    dev = tensors[0].device
+    return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64).to(dev)
+
+
+def gather_pool_fwd(tables: TableSet, layout: FeatureLayout, ids: torch.Tensor,
+                    lens: Optional[torch.Tensor], batch: int, out: Optional[torch.Tensor] = None,
+                    want_scale: bool = False, err_flag: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    _require_cuda(ids, lens, out)
+    dev = ids.device
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.numel() == layout.slots(batch)
+    if out is None:
+        out = torch.empty(batch, layout.out_width, dtype=torch.float32, device=dev)
+    bag_scale = torch.empty(layout.n_features, batch, dtype=torch.float32, device=dev) if want_scale else None
+    _lib.check(_gather_call(lib, tables, layout, ids, lens, batch, out, bag_scale, err_flag, dev),
+               "ptrec_embedding_gather_pool_fwd")
+    return out, bag_scale
+
+
+def _gather_call(lib, tables, layout, ids, lens, batch, out, bag_scale, err_flag, dev):
+    feats_dev = layout.device_array(dev)
+    return lib.ptrec_embedding_gather_pool_fwd(
+        _ptr(tables.ptrs), _ptr(tables.rows), layout.n_tables, layout.dim, _lib.F32,
+        ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)), layout.host,
+        layout.n_features, _ptr(ids), _ptr(lens), batch, _ptr(out), out.stride(0), _ptr(bag_scale),
+        _ptr(err_flag), _stream(dev))
+
+
+class SortResult:
+    __slots__ = ("sorted_keys", "perm", "seg_start", "seg_table", "n_seg", "N")
+
+
+def sort_dedup(tables: TableSet, layout: FeatureLayout, ids: torch.Tensor,
+               lens: Optional[torch.Tensor], batch: int) -> SortResult:
+    lib = _lib.load()
+    _require_cuda(ids, lens)
+    dev = ids.device
+    N = layout.slots(batch)
+    r = SortResult()
+    r.N = N
+    # int32 view of uint32 keys (torch has no uint32 arithmetic; tests reinterpret)
+    r.sorted_keys = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    r.perm = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    r.seg_start = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    r.seg_table = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    r.n_seg = torch.empty(1, dtype=torch.int32, device=dev)
+    nbytes = lib.ptrec_sort_dedup_workspace_bytes(N, layout.n_tables)
+    ws = _workspace("sort_dedup", nbytes, dev)
+    feats_dev = layout.device_array(dev)
+    _lib.check(lib.ptrec_sort_dedup(
+        ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)), layout.host,
+        layout.n_features, layout.n_tables, _ptr(tables.rows), tables.max_rows, _ptr(ids), _ptr(lens),
+        batch, _ptr(r.sorted_keys), _ptr(r.perm), _ptr(r.seg_start), _ptr(r.seg_table), _ptr(r.n_seg),
+        _ptr(ws), ws.numel(), _stream(dev)), "ptrec_sort_dedup")
+    return r
+
+
+_BWD_FN = {
+    _lib.OPT_SGD: "ptrec_embedding_bwd_fused_sgd",
+    _lib.OPT_ADAGRAD: "ptrec_embedding_bwd_fused_adagrad",
+    _lib.OPT_ROWWISE_ADAGRAD: "ptrec_embedding_bwd_fused_rowwise_adagrad",
+    _lib.OPT_LAZY_ADAM: "ptrec_embedding_bwd_fused_lazy_adam",
+}
+
+
+def bwd_fused(tables: TableSet, state1_ptrs: Optional[torch.Tensor], state2_ptrs: Optional[torch.Tensor],
+              layout: FeatureLayout, batch: int, srt: SortResult, grad_out: torch.Tensor,
+              bag_scale: Optional[torch.Tensor], opt: OptimArgs) -> None:
+    lib = _lib.load()
+    _require_cuda(grad_out, bag_scale)
+    dev = grad_out.device
+    assert grad_out.dtype == torch.float32 and grad_out.dim() == 2 and grad_out.stride(1) == 1
+    nbytes = lib.ptrec_embedding_bwd_workspace_bytes(srt.N, layout.dim)
+    ws = _workspace("bwd_fused", nbytes, dev)
+    feats_dev = layout.device_array(dev)
+    fn = getattr(lib, _BWD_FN[opt.kind])
+    _lib.check(fn(_ptr(tables.ptrs), _ptr(state1_ptrs), _ptr(state2_ptrs), layout.n_tables, layout.dim,
+                  _lib.F32, ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)),
+                  layout.host, layout.n_features, batch, _ptr(srt.sorted_keys), _ptr(srt.perm),
+                  _ptr(srt.seg_start), _ptr(srt.seg_table), _ptr(srt.n_seg), _ptr(grad_out),
+                  grad_out.stride(0), _ptr(bag_scale), ctypes.byref(opt), _ptr(ws), ws.numel(),
+                  _stream(dev)), _BWD_FN[opt.kind])
+
+
+def segment_sum(layout: FeatureLayout, batch: int, srt: SortResult, grad_out: torch.Tensor,
+                bag_scale: Optional[torch.Tensor]) -> torch.Tensor:
+    """Per-segment gradient sums ``[N, D]`` (first ``n_seg`` rows meaningful)."""
+    lib = _lib.load()
+    _require_cuda(grad_out, bag_scale)
+    dev = grad_out.device
+    row_grad = torch.empty(max(srt.N, 1), layout.dim, dtype=torch.float32, device=dev)
+    feats_dev = layout.device_array(dev)
+    _lib.check(lib.ptrec_embedding_bwd_segment_sum(
+        layout.n_tables, layout.dim,
+        ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)), layout.host,
+        layout.n_features, batch, _ptr(srt.sorted_keys), _ptr(srt.perm), _ptr(srt.seg_start),
+        _ptr(srt.seg_table), _ptr(srt.n_seg), _ptr(grad_out), grad_out.stride(0), _ptr(bag_scale),
+        _ptr(row_grad), _stream(dev)), "ptrec_embedding_bwd_segment_sum")
+    return row_grad
+
+
+# ----------------------------------------------------------------------------------------------
+# K3 FM second-order interaction
+# ----------------------------------------------------------------------------------------------
+def fm2_fwd(v: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _require_cuda(v)
+    assert v.dtype == torch.float32 and v.dim() == 3 and v.stride(2) == 1 and v.stride(1) == v.shape[2]
+    B, F, D = v.shape
+    y = torch.empty(B, dtype=torch.float32, device=v.device)
+    _lib.check(lib.ptrec_fm2_fwd(_ptr(v), v.stride(0), B, F, D, _ptr(y), _stream(v.device)), "ptrec_fm2_fwd")
+    return y
+
+
+def fm2_bwd(v: torch.Tensor, gy: torch.Tensor, grad_in: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _require_cuda(v, gy, grad_in)
+    B, F, D = v.shape
+    gy = gy.contiguous()
+    gv = torch.empty(B, F, D, dtype=torch.float32, device=v.device)
+    gi_stride = 0
+    if grad_in is not None:
+        assert grad_in.dtype == torch.float32 and grad_in.stride(-1) == 1
+        gi_stride = grad_in.stride(0)
+    _lib.check(lib.ptrec_fm2_bwd(_ptr(v), v.stride(0), _ptr(gy), _ptr(grad_in), gi_stride, B, F, D, _ptr(gv),
+                                 gv.stride(0), _stream(v.device)), "ptrec_fm2_bwd")
+    return gv
+
+
+class _FM2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v):
+        ctx.save_for_backward(v)
+        return fm2_fwd(v)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (v,) = ctx.saved_tensors
+        return fm2_bwd(v, gy)
+
+
+def fm2(v: torch.Tensor) -> torch.Tensor:
+    """FM second-order term of ``v [B, F, D]`` -> ``[B]`` (fused CUDA forward and backward)."""
+    if not (v.stride(2) == 1 and v.stride(1) == v.shape[2]):
+        v = v.contiguous()
+    return _FM2.apply(v)
