@@ -88,6 +88,7 @@ typedef struct ptrec_optim_args {
 
 int ptrec_abi_version(void);
 const char* ptrec_last_error(void); /* thread-local, valid until the next failing call */
+int64_t ptrec_launch_count(void);   /* kernels launched by this library since load (process-wide) */
 
 /* ---------------------------------------------------------------------------------------------
  * a1/a6 index preparation.  Replaces the mask/len arithmetic of SVDPP.py:49,53 and

@@ -1,0 +1,211 @@
+"""Model-level CPU restatements in the reference's idiom (test oracle; see oracle/__init__.py).
+
+Every model here is built from stock ``torch.nn.Embedding`` / ``Linear`` modules, takes dense
+autograd gradients (``aten::embedding_dense_backward``) and is stepped by a dense ``torch.optim``
+optimizer — i.e. exactly what the reference does on this path.  Column objects are duck-typed
+(``get_feature_data(batch)``, ``category_num``) so this file imports nothing from the product.
+"""
+from typing import Dict, List, Optional
+
+import torch
+from torch import Tensor, nn
+from torch.nn import Embedding, Linear, Parameter
+
+
+def set_seed_ref(seed: int) -> None:
+    """torchrec/utils/global_utils.py:7-16 (CPU part; the cudnn flags do not affect CPU draws)."""
+    torch.manual_seed(seed)
+
+
+class IModelRef(nn.Module):
+    """Lifecycle + step of torchrec/model/IModel.py restated:
+    seed -> ``_init_weights`` -> re-draw N(0, 0.01) over Linear/Embedding weights and biases in
+    ``Module.apply`` order (:37-71); two param groups, biases undecayed (:83-92); ``train_step`` =
+    forward, loss, zero_grad, backward, step (:116-125)."""
+
+    def __init__(self, random_seed: int):
+        set_seed_ref(random_seed)
+        super().__init__()
+        self._init_weights()
+        self.apply(self._reset)
+
+    def _init_weights(self):
+        raise NotImplementedError
+
+    @staticmethod
+    def _reset(m):
+        tname = str(type(m))
+        if 'Linear' in tname:
+            nn.init.normal_(m.weight, mean=0.0, std=0.01)
+            if m.bias is not None:
+                nn.init.normal_(m.bias, mean=0.0, std=0.01)
+        elif 'Embedding' in tname:
+            nn.init.normal_(m.weight, mean=0.0, std=0.01)
+
+    def get_parameters(self):
+        weights = [p for n, p in self.named_parameters() if p.requires_grad and 'bias' not in n]
+        biases = [p for n, p in self.named_parameters() if p.requires_grad and 'bias' in n]
+        return [{'params': weights}, {'params': biases, 'weight_decay': 0.0}]
+
+    def compile(self, optimizer, loss):
+        self.opt, self.loss_fn = optimizer, loss
+
+    def train_step(self, data: Dict[str, Tensor]):
+        self.train()
+        prediction, target = self(data)
+        loss = self.loss_fn(prediction, target)
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        return {"loss": loss}
+
+
+def _one_hot_target(prediction: Tensor) -> Tensor:
+    t = torch.zeros_like(prediction, dtype=torch.float32)
+    t[:, 0] = 1
+    return t
+
+
+class FunkSVDRef(IModelRef):
+    """torchrec/model/FunkSVD.py:27-67: two tables, dot product; ``[B, N]`` candidates broadcast the user."""
+
+    def __init__(self, random_seed, uid_column, iid_column, label_column, emb_size):
+        self.uid_column, self.iid_column, self.label_column, self.emb_size = uid_column, iid_column, label_column, emb_size
+        super().__init__(random_seed)
+
+    def _init_weights(self):
+        self.u_embeddings = Embedding(self.uid_column.category_num, self.emb_size)
+        self.i_embeddings = Embedding(self.iid_column.category_num, self.emb_size)
+
+    def forward(self, data):
+        u = self.u_embeddings(self.uid_column.get_feature_data(data))
+        i_ids = self.iid_column.get_feature_data(data)
+        i = self.i_embeddings(i_ids)
+        if i_ids.dim() == 1:
+            target = self.label_column.get_feature_data(data)
+            return (u * i).sum(-1), (target.float() if target is not None else None)
+        pred = (u.unsqueeze(1) * i).sum(-1)
+        return pred, _one_hot_target(pred)
+
+
+class SVDPPRef(IModelRef):
+    """torchrec/model/SVDPP.py:36-91: user + sqrt-n pooled implicit items, item, two bias tables, global bias."""
+
+    def __init__(self, random_seed, uid_column, iid_column, iids_column, label_column, emb_size):
+        self.uid_column, self.iid_column, self.iids_column = uid_column, iid_column, iids_column
+        self.label_column, self.emb_size = label_column, emb_size
+        super().__init__(random_seed)
+
+    def _init_weights(self):
+        n_u, n_i = self.uid_column.category_num, self.iid_column.category_num
+        self.u_embeddings = Embedding(n_u, self.emb_size)
+        self.i_embeddings = Embedding(n_i, self.emb_size)
+        self.implicit_i_embeddings = Embedding(n_i, self.emb_size)
+        self.u_bias = Embedding(n_u, 1)
+        self.i_bias = Embedding(n_i, 1)
+        self.global_bias = Parameter(torch.tensor(0.0))
+
+    def forward(self, data):
+        u_ids = self.uid_column.get_feature_data(data)
+        i_ids = self.iid_column.get_feature_data(data)
+        his = self.iids_column.get_feature_data(data)
+        m = his.gt(0).float()                                            # :49
+        pooled = (self.implicit_i_embeddings(his) * m.unsqueeze(-1)).sum(1)  # :50-52
+        pooled = pooled / m.sum(-1).sqrt().unsqueeze(-1)                 # :53-55
+        u = self.u_embeddings(u_ids) + pooled
+        i = self.i_embeddings(i_ids)
+        bu = self.u_bias(u_ids).squeeze(-1)
+        bi = self.i_bias(i_ids).squeeze(-1)
+        if i_ids.dim() == 1:
+            target = self.label_column.get_feature_data(data)
+            return (u * i).sum(-1) + bu + bi + self.global_bias, (target.float() if target is not None else None)
+        pred = (u.unsqueeze(1) * i).sum(-1) + bu.unsqueeze(1) + bi + self.global_bias
+        return pred, _one_hot_target(pred)
+
+
+# ------------------------------------------------------------------------------------------------
+# FM / DeepFM (NOT in the reference: parity unpinned; restated in its idiom)
+# ------------------------------------------------------------------------------------------------
+class DenseRef(nn.Module):
+    """torchrec/model/layer/Dense.py:4-24: Linear -> ReLU -> Dropout (activation always ReLU)."""
+
+    def __init__(self, input_units: int, output_units: int, dropout: float):
+        super().__init__()
+        self.linear = Linear(input_units, output_units)
+        self.activation = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, x):
+        return self.dropout(self.activation(self.linear(x)))
+
+
+class MLPRef(nn.Module):
+    """torchrec/model/layer/MLP.py:8-23: ``Sequential`` of ``dense_{i}`` blocks under ``mlp``."""
+
+    def __init__(self, input_units: int, hidden: List[int], dropout: float):
+        super().__init__()
+        self.mlp = nn.Sequential()
+        units = input_units
+        for k, h in enumerate(hidden):
+            self.mlp.add_module(f"dense_{k}", DenseRef(units, h, dropout))
+            units = h
+
+    def forward(self, x):
+        return self.mlp(x)
+
+
+class FMRef(IModelRef):
+    """y = w0 + sum_f w_f[id_f] + <w_dense, x> + 0.5 sum_k((sum_f v_fk)^2 - sum_f v_fk^2).
+    One ``Embedding`` per column for v and for w (SVDPP.py:36-42 pattern), ``Linear(n_dense, 1, bias=False)``."""
+
+    def __init__(self, random_seed, sparse_columns, dense_columns, label_column, emb_size):
+        self.sparse_columns, self.dense_columns = list(sparse_columns), list(dense_columns or [])
+        self.label_column, self.emb_size = label_column, emb_size
+        super().__init__(random_seed)
+
+    def _init_weights(self):
+        self.embeddings = nn.ModuleList([Embedding(c.category_num, self.emb_size) for c in self.sparse_columns])
+        self.first_order = nn.ModuleList([Embedding(c.category_num, 1) for c in self.sparse_columns])
+        if self.dense_columns:
+            self.dense_linear = Linear(len(self.dense_columns), 1, bias=False)
+        self.global_bias = Parameter(torch.tensor(0.0))
+
+    def _parts(self, data):
+        ids = [c.get_feature_data(data) for c in self.sparse_columns]
+        v = torch.stack([e(i) for e, i in zip(self.embeddings, ids)], dim=1)        # [B, F, D]
+        w = torch.stack([e(i) for e, i in zip(self.first_order, ids)], dim=1)       # [B, F, 1]
+        x = torch.stack([c.get_feature_data(data) for c in self.dense_columns], dim=1) if self.dense_columns else None
+        s = v.sum(dim=1)
+        fm2 = 0.5 * (s * s - (v * v).sum(dim=1)).sum(dim=-1)
+        logit = w.sum(dim=(1, 2)) + fm2 + self.global_bias
+        if x is not None:
+            logit = logit + self.dense_linear(x).squeeze(-1)
+        return v, x, logit
+
+    def _target(self, data):
+        t = self.label_column.get_feature_data(data)
+        return t.float() if t is not None else None
+
+    def forward(self, data):
+        _, _, logit = self._parts(data)
+        return logit, self._target(data)
+
+
+class DeepFMRef(FMRef):
+    """FM + ``Linear(MLP(concat_f v_f || x), 1, bias=False)`` (head pattern of NCF.py:44-51,68-74)."""
+
+    def __init__(self, random_seed, sparse_columns, dense_columns, label_column, emb_size, layers, dropout=0.0):
+        self.layers, self.dropout = list(layers), dropout
+        super().__init__(random_seed, sparse_columns, dense_columns, label_column, emb_size)
+
+    def _init_weights(self):
+        super()._init_weights()
+        in_units = len(self.sparse_columns) * self.emb_size + len(self.dense_columns)
+        self.mlp = MLPRef(in_units, self.layers, self.dropout)
+        self.deep_out = Linear(self.layers[-1], 1, bias=False)
+
+    def forward(self, data):
+        v, x, logit = self._parts(data)
+        flat = v.reshape(v.shape[0], -1)
+        deep_in = torch.cat([flat, x], dim=1) if x is not None else flat
+        return logit + self.deep_out(self.mlp(deep_in)).squeeze(-1), self._target(data)

@@ -63,6 +63,7 @@ _BWD_ARGS = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, _FD, _FD, 
 PROTOTYPES = {
     "ptrec_abi_version": (c_int, []),
     "ptrec_last_error": (c_char_p, []),
+    "ptrec_launch_count": (c_int64, []),
     "ptrec_index_prep_workspace_bytes": (c_size_t, [c_int64]),
     "ptrec_index_prep": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
                                  c_void_p, c_size_t, c_void_p]),

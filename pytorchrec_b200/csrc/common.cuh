@@ -16,6 +16,7 @@ namespace ptrec {
 // ----------------------------------------------------------------------------- host error plumbing
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void count_launch();  // every kernel launch of this library is counted (ptrec_launch_count)
 
 #define PTREC_CHECK_ARG(cond, code, ...)  \
   do {                                     \
@@ -33,6 +34,7 @@ int cuda_fail(cudaError_t e, const char* what);
 
 #define PTREC_LAUNCH_CHECK(name)                                          \
   do {                                                                    \
+    ::ptrec::count_launch();                                              \
     cudaError_t _e = cudaPeekAtLastError();                               \
     if (_e != cudaSuccess) return ::ptrec::cuda_fail(_e, "launch " name); \
   } while (0)

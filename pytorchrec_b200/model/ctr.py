@@ -29,7 +29,10 @@ def _dense_matrix(dense_columns: List[NumericColumn], data: Dict[str, Tensor]) -
 
 class FM(IModel):
     def __init__(self, sparse_columns: List[CategoricalColumnWithIdentity], dense_columns: List[NumericColumn],
-                 label_column: CategoricalColumnWithIdentity, emb_size: int, **kwargs):
+                 label_column: CategoricalColumnWithIdentity, emb_size: int, table_device=None, **kwargs):
+        # table_device: build the tables directly on that device (skips the CPU init of multi-GB
+        # tables; seeded CPU-init parity with the reference then no longer applies)
+        self.table_device = table_device
         self.sparse_columns = list(sparse_columns)
         self.dense_columns = list(dense_columns or [])
         self.label_column = label_column
@@ -37,8 +40,8 @@ class FM(IModel):
         super().__init__(**kwargs)
 
     def _init_weights(self):
-        self.embeddings = MultiTableEmbedding(self.sparse_columns, self.emb_size)
-        self.first_order = MultiTableEmbedding(self.sparse_columns, 1)
+        self.embeddings = MultiTableEmbedding(self.sparse_columns, self.emb_size, device=self.table_device)
+        self.first_order = MultiTableEmbedding(self.sparse_columns, 1, device=self.table_device)
         if self.dense_columns:
             self.dense_linear = Linear(len(self.dense_columns), 1, bias=False)
         self.global_bias = Parameter(torch.tensor(0.0))
@@ -63,10 +66,10 @@ class FM(IModel):
 
 class DeepFM(FM):
     def __init__(self, sparse_columns, dense_columns, label_column, emb_size: int, layers: List[int],
-                 dropout: float = 0.0, **kwargs):
+                 dropout: float = 0.0, table_device=None, **kwargs):
         self.layers = list(layers)
         self.dropout = dropout
-        super().__init__(sparse_columns, dense_columns, label_column, emb_size, **kwargs)
+        super().__init__(sparse_columns, dense_columns, label_column, emb_size, table_device=table_device, **kwargs)
 
     def _init_weights(self):
         super()._init_weights()

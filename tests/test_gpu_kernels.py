@@ -1,0 +1,413 @@
+"""Kernel-level parity on the GPU: every call goes through the C ABI (ctypes) and is compared with
+the CPU oracle on the same seeded inputs.  Integer artefacts are bit-exact; fp32 outputs within
+1e-5 relative (segment-scaled where accumulation order differs)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops
+from pytorchrec_b200 import _lib, ops
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+RTOL = 1e-5
+
+
+def _tables(rows, D, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(r, D, generator=g) for r in rows]
+
+
+def _ids(shape, rows, seed, zipf=False, pad_frac=0.0):
+    rng = np.random.default_rng(seed)
+    if zipf:
+        x = rng.zipf(1.3, size=shape) % rows
+    else:
+        x = rng.integers(0, rows, size=shape)
+    if pad_frac > 0:
+        x[rng.random(shape) < pad_frac] = 0
+    return torch.from_numpy(x.astype(np.int64))
+
+
+def _u32(t):
+    return t.long() & 0xFFFFFFFF
+
+
+# ------------------------------------------------------------------------------------------ index prep
+@pytest.mark.parametrize("mask", ["none", "pad", "pad_keep_first", "lens"])
+@pytest.mark.parametrize("B,L", [(1, 1), (7, 5), (300, 33), (4099, 100)])
+def test_index_prep_bit_exact(mask, B, L):
+    ids = _ids((B, L), 50, seed=B * 131 + L, pad_frac=0.5)
+    lens = torch.from_numpy(np.random.default_rng(B).integers(0, L + 1, size=B).astype(np.int32))
+    out_ids, offsets = ops.index_prep(ids.to(DEV), lens.to(DEV) if mask == "lens" else None, mask)
+    ref_ids, ref_off = ref_ops.index_prep_ref(ids, mask, lens)
+    assert torch.equal(offsets.cpu(), ref_off)
+    n = int(ref_off[-1])
+    assert torch.equal(out_ids.cpu()[:n], ref_ids)
+
+
+def test_index_prep_all_pad_rows_are_empty_bags():
+    ids = torch.zeros(9, 4, dtype=torch.int64)
+    ids[3, 1] = 5
+    out_ids, offsets = ops.index_prep(ids.to(DEV), None, "pad")
+    assert offsets.cpu().tolist() == [0, 0, 0, 0, 1, 1, 1, 1, 1, 1]
+    assert out_ids.cpu()[0].item() == 5
+
+
+# ------------------------------------------------------------------------------------------ gather + pool
+def _run_gather(weights, specs, id_list, lens_list, D):
+    """specs: per feature dict(table, pooling, mask); returns CUDA out [B, F, D] and oracle out."""
+    F = len(specs)
+    B = id_list[0].shape[0]
+    lay_specs, lens_cols = [], []
+    for f, s in enumerate(specs):
+        L = 1 if id_list[f].dim() == 1 else id_list[f].shape[1]
+        lc = -1
+        if s.get("mask") == "lens":
+            lens_cols.append(lens_list[f])
+            lc = len(lens_cols) - 1
+        lay_specs.append(dict(table=s["table"], bag_len=L, pooling=s.get("pooling", "sum"),
+                              mask=s.get("mask", "none"), lens_col=lc))
+    layout = ops.FeatureLayout(lay_specs, D, len(weights))
+    dw = [w.to(DEV) for w in weights]
+    tables = ops.TableSet().refresh(dw)
+    ids = torch.cat([i.reshape(-1) for i in id_list]).to(DEV)
+    lens = torch.stack(lens_cols).to(torch.int32).to(DEV) if lens_cols else None
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out, scale = ops.gather_pool_fwd(tables, layout, ids, lens, B, want_scale=True, err_flag=err)
+    ref = ref_ops.multi_table_lookup_ref(weights, [s["table"] for s in specs], id_list,
+                                         [s.get("pooling", "sum") for s in specs],
+                                         [s.get("mask", "none") for s in specs], lens_list)
+    return out.view(B, F, D).cpu(), ref, err, (layout, tables, ids, lens, scale, dw)
+
+
+@pytest.mark.parametrize("D", [1, 2, 4, 8, 12, 16, 32, 64, 128])
+@pytest.mark.parametrize("B", [1, 33, 1024])
+def test_onehot_gather_is_bit_exact(D, B):
+    rows = [17, 1000, 5, 301]
+    weights = _tables(rows, D, seed=D)
+    id_list = [_ids((B,), rows[t], seed=100 * D + t) for t in range(4)]
+    out, ref, err, _ = _run_gather(weights, [dict(table=t) for t in range(4)], id_list, [None] * 4, D)
+    assert torch.equal(out, ref)  # values are copied, not computed
+    assert err.item() == 0
+
+
+def test_onehot_gather_criteo_shape_bit_exact():
+    F, D, B = 26, 16, 4096
+    rows = [1000 + 37 * f for f in range(F)]
+    weights = _tables(rows, D, seed=1)
+    id_list = [_ids((B,), rows[f], seed=f, zipf=(f % 2 == 0)) for f in range(F)]
+    out, ref, err, _ = _run_gather(weights, [dict(table=f) for f in range(F)], id_list, [None] * F, D)
+    assert torch.equal(out, ref) and err.item() == 0
+
+
+@pytest.mark.parametrize("pooling", ["sum", "mean", "sqrtn"])
+@pytest.mark.parametrize("mask", ["none", "pad", "pad_keep_first", "lens"])
+@pytest.mark.parametrize("B,L,D", [(5, 3, 8), (130, 100, 16), (64, 7, 32), (33, 50, 64), (9, 11, 1)])
+def test_bag_pooling_matches_reference_idioms(pooling, mask, B, L, D):
+    rows = [211, 97]
+    weights = _tables(rows, D, seed=L)
+    id_list = [_ids((B, L), rows[0], seed=B + L, pad_frac=0.4), _ids((B,), rows[1], seed=3)]
+    lens = torch.from_numpy(np.random.default_rng(L).integers(0, L + 1, size=B).astype(np.int64))
+    specs = [dict(table=0, pooling=pooling, mask=mask), dict(table=1)]
+    out, ref, err, _ = _run_gather(weights, specs, id_list, [lens, None], D)
+    # segment-scaled tolerance: |x - ref| <= 1e-5 * sum_l |v_l| (accumulation order differs)
+    bound = RTOL * torch.nn.functional.embedding(id_list[0], weights[0]).abs().sum(1) + 1e-7
+    assert ((out[:, 0] - ref[:, 0]).abs() <= bound).all()
+    assert torch.equal(out[:, 1], ref[:, 1])
+    assert err.item() == 0
+
+
+def test_shared_table_and_long_unstaged_bags():
+    D, B, L = 16, 6, 2500  # L > staging capacity -> direct index reads
+    weights = _tables([400], D, seed=9)
+    id_list = [_ids((B,), 400, seed=1), _ids((B, L), 400, seed=2, pad_frac=0.2)]
+    specs = [dict(table=0), dict(table=0, pooling="mean", mask="pad")]
+    out, ref, err, _ = _run_gather(weights, specs, id_list, [None, None], D)
+    assert torch.equal(out[:, 0], ref[:, 0])
+    np.testing.assert_allclose(out[:, 1].numpy(), ref[:, 1].numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_out_of_range_id_sets_error_flag_and_zero_row():
+    weights = _tables([10], 8, seed=0)
+    ids = torch.tensor([1, 10, 3, -1], dtype=torch.int64)
+    layout = ops.FeatureLayout([dict(table=0, bag_len=1)], 8, 1)
+    tables = ops.TableSet().refresh([weights[0].to(DEV)])
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out, _ = ops.gather_pool_fwd(tables, layout, ids.to(DEV), None, 4, err_flag=err)
+    assert err.item() == 1
+    assert torch.equal(out.cpu()[[0, 2]], weights[0][[1, 3]])
+    assert (out.cpu()[[1, 3]] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------ sort + dedup
+def _check_sort(layout, tables, ids_dev, lens_dev, B, specs, id_list, lens_list, rows):
+    srt = ops.sort_dedup(tables, layout, ids_dev, lens_dev, B)
+    torch.cuda.synchronize()
+    N = srt.N
+    keys = _u32(srt.sorted_keys.cpu()[:N])
+    perm = srt.perm.cpu()[:N].long()
+    n_seg = int(srt.n_seg.item())
+    seg_start = srt.seg_start.cpu()[: n_seg + 1].long()
+    seg_table = srt.seg_table.cpu()[:n_seg].long()
+    # oracle: per table, concatenate its features' slots in layout order
+    T = len(rows)
+    per_ids, per_valid, base = [], [], []
+    pos = 0
+    order = sorted(range(len(specs)), key=lambda f: (specs[f]["table"], f))
+    assert order == list(range(len(specs))), "test specs must already be ordered by table"
+    for t in range(T):
+        ids_t, val_t = [], []
+        base.append(pos)
+        for f, s in enumerate(specs):
+            if s["table"] != t:
+                continue
+            x = id_list[f] if id_list[f].dim() == 2 else id_list[f].unsqueeze(1)
+            v = ref_ops.valid_mask(x, s.get("mask", "none") if id_list[f].dim() == 2 or s.get("mask") == "lens" else "none",
+                                   lens_list[f])
+            ids_t.append(x.reshape(-1))
+            val_t.append(v.reshape(-1))
+            pos += x.numel()
+        per_ids.append(torch.cat(ids_t) if ids_t else torch.zeros(0, dtype=torch.int64))
+        per_valid.append(torch.cat(val_t) if val_t else torch.zeros(0, dtype=torch.bool))
+    ref = ref_ops.sort_dedup_ref(per_ids, per_valid, rows)
+    seg = 0
+    for t in range(T):
+        skey, rperm, uniq, counts = ref[t]
+        n_t = skey.numel()
+        assert torch.equal(keys[base[t]: base[t] + n_t], skey), f"sorted keys differ in table {t}"
+        assert torch.equal(perm[base[t]: base[t] + n_t] - base[t], rperm), f"perm differs in table {t}"
+        k = uniq.numel()
+        assert torch.equal(keys[seg_start[seg: seg + k]], uniq), f"unique ids differ in table {t}"
+        assert torch.equal(seg_start[seg + 1: seg + k + 1] - seg_start[seg: seg + k], counts)
+        assert (seg_table[seg: seg + k] == t).all()
+        seg += k
+    assert seg == n_seg and int(seg_start[n_seg]) == N
+    return srt
+
+
+@pytest.mark.parametrize("B", [1, 100, 2048, 5000])
+@pytest.mark.parametrize("rows", [[3, 70000, 257], [1 << 20, 9, 300]])
+def test_sort_dedup_bit_exact_onehot(B, rows):
+    D = 4
+    weights = _tables([min(r, 64) for r in rows], D, seed=1)  # contents irrelevant: only row counts matter
+    id_list = [_ids((B,), rows[t], seed=B + t, zipf=(t == 1)) for t in range(3)]
+    specs = [dict(table=t) for t in range(3)]
+    layout = ops.FeatureLayout([dict(table=t, bag_len=1) for t in range(3)], D, 3)
+    tables = ops.TableSet()
+    tables.ptrs = torch.zeros(3, dtype=torch.int64, device=DEV)
+    tables.rows = torch.tensor(rows, dtype=torch.int64, device=DEV)
+    tables.max_rows = max(rows)
+    ids = torch.cat(id_list).to(DEV)
+    _check_sort(layout, tables, ids, None, B, specs, id_list, [None] * 3, rows)
+
+
+@pytest.mark.parametrize("mask", ["pad", "pad_keep_first", "lens"])
+def test_sort_dedup_bags_masks_and_shared_table(mask):
+    B, L, D = 257, 19, 8
+    rows = [40, 1000]
+    id_list = [_ids((B,), rows[0], seed=1), _ids((B, L), rows[0], seed=2, pad_frac=0.5), _ids((B, 3), rows[1], seed=3)]
+    lens = torch.from_numpy(np.random.default_rng(5).integers(0, L + 1, size=B).astype(np.int64))
+    specs = [dict(table=0), dict(table=0, mask=mask), dict(table=1)]
+    layout = ops.FeatureLayout([dict(table=0, bag_len=1), dict(table=0, bag_len=L, mask=mask, lens_col=0 if mask == "lens" else -1),
+                                dict(table=1, bag_len=3)], D, 2)
+    tables = ops.TableSet()
+    tables.ptrs = torch.zeros(2, dtype=torch.int64, device=DEV)
+    tables.rows = torch.tensor(rows, dtype=torch.int64, device=DEV)
+    tables.max_rows = max(rows)
+    ids = torch.cat([i.reshape(-1) for i in id_list]).to(DEV)
+    lens_dev = lens.to(torch.int32).reshape(1, B).to(DEV) if mask == "lens" else None
+    _check_sort(layout, tables, ids, lens_dev, B, specs, id_list, [None, lens, None], rows)
+
+
+def test_sort_dedup_out_of_range_ids_are_masked():
+    rows = [10]
+    ids = torch.tensor([3, 10, -4, 3, 0, 9], dtype=torch.int64)
+    layout = ops.FeatureLayout([dict(table=0, bag_len=1)], 4, 1)
+    tables = ops.TableSet()
+    tables.ptrs = torch.zeros(1, dtype=torch.int64, device=DEV)
+    tables.rows = torch.tensor(rows, dtype=torch.int64, device=DEV)
+    tables.max_rows = 10
+    srt = ops.sort_dedup(tables, layout, ids.to(DEV), None, 6)
+    assert _u32(srt.sorted_keys.cpu()).tolist() == [0, 3, 3, 9, 0xFFFFFFFF, 0xFFFFFFFF]
+    assert srt.perm.cpu().tolist() == [4, 0, 3, 5, 1, 2]
+    assert srt.n_seg.item() == 4
+
+
+# ------------------------------------------------------------------------------------------ fused update
+def _dense_grads(weights, specs, id_list, lens_list, grad_out):
+    """Reference backward: dense [rows, D] gradient per table via autograd on the oracle forward."""
+    ws = [w.clone().requires_grad_(True) for w in weights]
+    out = ref_ops.multi_table_lookup_ref(ws, [s["table"] for s in specs], id_list,
+                                         [s.get("pooling", "sum") for s in specs],
+                                         [s.get("mask", "none") for s in specs], lens_list)
+    out.backward(grad_out)
+    return [w.grad if w.grad is not None else torch.zeros_like(w) for w in ws]
+
+
+OPT_CASES = [
+    ("sgd", dict(lr=0.3)),
+    ("adagrad", dict(lr=0.2, eps=1e-10, lr_decay=0.01)),
+    ("rowwise_adagrad", dict(lr=0.2, eps=1e-8)),
+    ("lazy_adam", dict(lr=0.05, beta1=0.9, beta2=0.999, eps=1e-8)),
+]
+
+
+@pytest.mark.parametrize("opt_name,hp", OPT_CASES)
+@pytest.mark.parametrize("D", [1, 8, 16, 64])
+@pytest.mark.parametrize("hot", [False, True])
+def test_fused_update_matches_dense_optimizers(opt_name, hp, D, hot):
+    """Three steps of sort+dedup+fused update vs torch's dense optimizer fed the dense reference gradient.
+    `hot` makes ids Zipf-heavy so that runs longer than 32 exercise the CTA-per-segment kernel."""
+    B, L = 600, 9
+    rows = [50, 3000]
+    weights = _tables(rows, D, seed=D + 1)
+    specs = [dict(table=0, pooling="mean", mask="pad"), dict(table=1)]
+    lay = ops.FeatureLayout([dict(table=0, bag_len=L, pooling="mean", mask="pad"), dict(table=1, bag_len=1)], D, 2)
+    dw = [w.clone().to(DEV) for w in weights]
+    tables = ops.TableSet().refresh(dw)
+    kind = {"sgd": _lib.OPT_SGD, "adagrad": _lib.OPT_ADAGRAD, "rowwise_adagrad": _lib.OPT_ROWWISE_ADAGRAD,
+            "lazy_adam": _lib.OPT_LAZY_ADAM}[opt_name]
+    if opt_name == "rowwise_adagrad":
+        s1 = [torch.zeros(r, device=DEV) for r in rows]
+    else:
+        s1 = [torch.zeros(r, D, device=DEV) for r in rows]
+    s2 = [torch.zeros(r, D, device=DEV) for r in rows]
+    p1 = ops.make_ptr_array(s1) if opt_name != "sgd" else None
+    p2 = ops.make_ptr_array(s2) if opt_name == "lazy_adam" else None
+
+    ref_w = [w.clone().requires_grad_(True) for w in weights]
+    if opt_name == "sgd":
+        ropt = torch.optim.SGD(ref_w, lr=hp["lr"])
+    elif opt_name == "adagrad":
+        ropt = torch.optim.Adagrad(ref_w, lr=hp["lr"], eps=hp["eps"], lr_decay=hp["lr_decay"])
+    elif opt_name == "lazy_adam":
+        ropt = torch.optim.SparseAdam(ref_w, lr=hp["lr"], betas=(hp["beta1"], hp["beta2"]), eps=hp["eps"])
+    else:
+        ropt, rstate = None, [torch.zeros(r) for r in rows]
+
+    gsum = [torch.zeros_like(w) for w in weights]
+    for step in range(1, 4):
+        id_list = [_ids((B, L), rows[0], seed=step, zipf=hot, pad_frac=0.3), _ids((B,), rows[1], seed=10 + step, zipf=hot)]
+        ids = torch.cat([i.reshape(-1) for i in id_list]).to(DEV)
+        go = torch.randn(B, 2, D, generator=torch.Generator().manual_seed(step))
+        out, scale = ops.gather_pool_fwd(tables, lay, ids, None, B, want_scale=True)
+        srt = ops.sort_dedup(tables, lay, ids, None, B)
+        args = _lib.OptimArgs(kind=kind, step=step, lr=hp["lr"], eps=hp.get("eps", 0.0), beta1=hp.get("beta1", 0.0),
+                              beta2=hp.get("beta2", 0.0), weight_decay=0.0, lr_decay=hp.get("lr_decay", 0.0))
+        ops.bwd_fused(tables, p1, p2, lay, B, srt, go.view(B, 2 * D).to(DEV), scale, args)
+        grads = _dense_grads([w.detach() for w in ref_w], specs, id_list, [None, None], go)
+        for t in range(2):
+            gsum[t] += grads[t].abs()
+        if opt_name == "lazy_adam":
+            ropt.zero_grad()
+            for w, g in zip(ref_w, grads):
+                w.grad = g.to_sparse(1)
+            ropt.step()
+        elif ropt is not None:
+            ropt.zero_grad()
+            for w, g in zip(ref_w, grads):
+                w.grad = g
+            ropt.step()
+        else:
+            with torch.no_grad():
+                for w, s, g in zip(ref_w, rstate, grads):
+                    ref_ops.rowwise_adagrad_ref(w, s, g, hp["lr"], hp["eps"])
+    for t in range(2):
+        got, want = dw[t].cpu(), ref_w[t].detach()
+        untouched = gsum[t].sum(1) == 0
+        assert torch.equal(got[untouched], weights[t][untouched]), "untouched rows must not move"
+        tol = 2e-5 * (want.abs() + 1.0) if opt_name != "sgd" else RTOL * (want.abs() + hp["lr"] * gsum[t])
+        assert ((got - want).abs() <= tol + 1e-7).all(), f"table {t}: max err {(got - want).abs().max()}"
+    if opt_name == "adagrad":
+        for t in range(2):
+            np.testing.assert_allclose(s1[t].cpu().numpy(), ropt.state[ref_w[t]]["sum"].numpy(), rtol=2e-5, atol=1e-7)
+    if opt_name == "lazy_adam":
+        for t in range(2):
+            np.testing.assert_allclose(s1[t].cpu().numpy(), ropt.state[ref_w[t]]["exp_avg"].numpy(), rtol=2e-5, atol=1e-7)
+            np.testing.assert_allclose(s2[t].cpu().numpy(), ropt.state[ref_w[t]]["exp_avg_sq"].numpy(), rtol=2e-5, atol=1e-9)
+
+
+def test_segment_sum_equals_dense_backward():
+    B, L, D = 300, 5, 16
+    rows = [64]
+    weights = _tables(rows, D, seed=4)
+    id_list = [_ids((B, L), rows[0], seed=8, zipf=True, pad_frac=0.2)]
+    specs = [dict(table=0, pooling="sqrtn", mask="pad")]
+    lay = ops.FeatureLayout([dict(table=0, bag_len=L, pooling="sqrtn", mask="pad")], D, 1)
+    tables = ops.TableSet().refresh([weights[0].to(DEV)])
+    ids = id_list[0].reshape(-1).to(DEV)
+    go = torch.randn(B, 1, D, generator=torch.Generator().manual_seed(1))
+    _, scale = ops.gather_pool_fwd(tables, lay, ids, None, B, want_scale=True)
+    srt = ops.sort_dedup(tables, lay, ids, None, B)
+    rg = ops.segment_sum(lay, B, srt, go.view(B, D).to(DEV), scale).cpu()
+    n = int(srt.n_seg.item())
+    keys = _u32(srt.sorted_keys.cpu())[srt.seg_start.cpu()[:n].long()]
+    dense = _dense_grads(weights, specs, id_list, [None], go)[0]
+    got = torch.zeros_like(dense)
+    valid = keys != 0xFFFFFFFF
+    got[keys[valid]] = rg[:n][valid]
+    np.testing.assert_allclose(got.numpy(), dense.numpy(), rtol=1e-4, atol=1e-5)
+    # run-to-run bit reproducibility (fixed reduction order)
+    rg2 = ops.segment_sum(lay, B, ops.sort_dedup(tables, lay, ids, None, B), go.view(B, D).to(DEV), scale).cpu()
+    assert torch.equal(rg[:n], rg2[:n])
+
+
+# ------------------------------------------------------------------------------------------ FM second order
+@pytest.mark.parametrize("B,F,D", [(1, 2, 4), (257, 26, 16), (64, 39, 32), (33, 5, 64), (100, 40, 128), (50, 7, 10), (31, 3, 1)])
+def test_fm2_forward_backward(B, F, D):
+    g = torch.Generator().manual_seed(B + F + D)
+    v = torch.randn(B, F, D, generator=g)
+    gy = torch.randn(B, generator=g)
+    vr = v.clone().requires_grad_(True)
+    yr = ref_ops.fm2_ref(vr)
+    yr.backward(gy)
+    vd = v.to(DEV).requires_grad_(True)
+    y = ops.fm2(vd)
+    y.backward(gy.to(DEV))
+    scale = 0.5 * ((v.sum(1) ** 2).sum(-1) + (v * v).sum((1, 2)))  # sum of |terms|
+    assert ((y.detach().cpu() - yr.detach()).abs() <= RTOL * scale + 1e-6).all()
+    gscale = gy.abs().view(B, 1, 1) * (v.abs().sum(1, keepdim=True) + v.abs())
+    assert ((vd.grad.cpu() - vr.grad).abs() <= RTOL * gscale + 1e-6).all()
+
+
+def test_fm2_backward_fused_accumulate():
+    B, F, D = 130, 26, 16
+    g = torch.Generator().manual_seed(0)
+    v, gy, gin = torch.randn(B, F, D, generator=g), torch.randn(B, generator=g), torch.randn(B, F, D, generator=g)
+    base = ops.fm2_bwd(v.to(DEV), gy.to(DEV))
+    fused = ops.fm2_bwd(v.to(DEV), gy.to(DEV), gin.to(DEV))
+    np.testing.assert_allclose(fused.cpu().numpy(), (base.cpu() + gin).numpy(), rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties_deepfm_config():
+    """cfg2 shape (26 tables x 1e6 rows x D16, B 16384): properties that need no CPU-sized oracle."""
+    F, R, D, B = 26, 1_000_000, 16, 16384
+    gen = torch.Generator(device=DEV).manual_seed(2020)
+    weights = [torch.randn(R, D, device=DEV, generator=gen) for _ in range(F)]
+    ids2d = torch.randint(0, R, (F, B), device=DEV, generator=gen)
+    lay = ops.FeatureLayout([dict(table=f, bag_len=1) for f in range(F)], D, F)
+    tables = ops.TableSet().refresh(weights)
+    ids = ids2d.reshape(-1).contiguous()
+    out, _ = ops.gather_pool_fwd(tables, lay, ids, None, B)
+    # gather == indexing (bit-exact), checked per table on the device
+    out3 = out.view(B, F, D)
+    for f in (0, 7, 25):
+        assert torch.equal(out3[:, f], weights[f][ids2d[f]])
+    srt = ops.sort_dedup(tables, lay, ids, None, B)
+    N = srt.N
+    keys = _u32(srt.sorted_keys)[:N].view(F, B)
+    assert (keys[:, 1:] >= keys[:, :-1]).all(), "each table's keys must be sorted"
+    perm = srt.perm[:N].long()
+    assert torch.equal(torch.sort(perm).values, torch.arange(N, device=DEV)), "perm must be a permutation"
+    assert torch.equal(ids[perm], _u32(srt.sorted_keys)[:N])
+    n_seg = int(srt.n_seg.item())
+    assert n_seg == sum(int(torch.unique(ids2d[f]).numel()) for f in range(F))
+    # SGD linearity: sum of all weights moves by -lr * sum of all upstream gradients
+    go = torch.randn(B, F * D, device=DEV, generator=gen)
+    before = torch.stack([w.double().sum() for w in weights]).sum()
+    args = _lib.OptimArgs(kind=_lib.OPT_SGD, step=1, lr=0.5, eps=0, beta1=0, beta2=0, weight_decay=0, lr_decay=0)
+    ops.bwd_fused(tables, None, None, lay, B, srt, go, None, args)
+    after = torch.stack([w.double().sum() for w in weights]).sum()
+    np.testing.assert_allclose((before - after).item(), 0.5 * go.double().sum().item(), rtol=1e-3, atol=2.0)

@@ -1,0 +1,170 @@
+"""Model-level parity on the GPU: the product models (fused CUDA embedding path + fused sparse
+optimizers) against (a) golden vectors from the unmodified reference run and (b) the CPU oracle
+twins, through the reference's own five-line ``train_step``."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import batch_from, state_from
+from oracle import ref_models
+from pytorchrec_b200.feature_column import CategoricalColumnWithIdentity as Col
+from pytorchrec_b200.feature_column import NumericColumn
+from pytorchrec_b200.loss import BPRLoss
+from pytorchrec_b200.metric import LogLoss
+from pytorchrec_b200.model import SVDPP, DeepFM, FM, FunkSVD
+from pytorchrec_b200.optim import SparseAdagrad, SparseAdam, SparseRowWiseAdagrad, SparseSGD
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def _mf_cols(g):
+    n_u, n_i, D, B, L, steps = (int(x) for x in g["dims"])
+    return dict(uid=Col(n_u, "uid"), iid=Col(n_i, "iid"), iids=Col(n_i, "iids"), label=Col(2, "label")), D, steps
+
+
+@pytest.mark.parametrize("case", ["svdpp_point_sgd", "svdpp_pair_sgd", "funksvd_point_sgd"])
+def test_reference_models_on_fused_tables_match_reference_run(golden_mf, case):
+    """SVD++ / FunkSVD on EmbeddingTable + SparseSGD reproduce the reference's own train_step results
+    (dense SGD == sparse SGD on touched rows; untouched rows do not move in either)."""
+    cols, D, steps = _mf_cols(golden_mf)
+    if case.startswith("svdpp"):
+        model = SVDPP(2020, cols["uid"], cols["iid"], cols["iids"], cols["label"], D)
+    else:
+        model = FunkSVD(cols["uid"], cols["iid"], cols["label"], D, random_seed=2020)
+    init = state_from(golden_mf, f"{case}/init")
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, init[k]), k
+    opt = SparseSGD(params=model.get_parameters(), lr=0.5)
+    loss = BPRLoss() if "_pair_" in case else torch.nn.MSELoss()
+    model.compile(opt, loss, [LogLoss()], DEV)
+    for s in range(steps):
+        batch = batch_from(golden_mf, f"{case}/batch{s}")
+        pred, target = model.test_step(batch)
+        np.testing.assert_allclose(pred.detach().cpu().numpy(), golden_mf[f"{case}/pred{s}"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_array_equal(target.cpu().numpy(), golden_mf[f"{case}/target{s}"])
+        logs = model.train_step(batch)
+        np.testing.assert_allclose(logs["loss"].item(), golden_mf[f"{case}/loss{s}"], rtol=1e-5)
+    final = state_from(golden_mf, f"{case}/final")
+    for k, v in model.state_dict().items():
+        np.testing.assert_allclose(v.cpu().numpy(), final[k].numpy(), rtol=1e-5, atol=1e-7, err_msg=k)
+
+
+def _ctr_setup(F=6, nd=3, D=16, rows=None, seed=11):
+    rows = rows or [50 + 13 * f for f in range(F)]
+    scols = [Col(rows[f], f"C{f}") for f in range(F)]
+    dcols = [NumericColumn(f"I{j}", 0.0, 1.0, 0.5, 0.25) for j in range(nd)]
+    return scols, dcols, Col(2, "label"), rows
+
+
+def _ctr_batch(rows, nd, B, seed, zipf=False):
+    rng = np.random.default_rng(seed)
+    b = {}
+    for f, r in enumerate(rows):
+        x = (rng.zipf(1.2, size=B) % r) if zipf else rng.integers(0, r, size=B)
+        b[f"C{f}"] = torch.from_numpy(x.astype(np.int32))
+    for j in range(nd):
+        b[f"I{j}"] = torch.from_numpy(rng.random(B).astype(np.float32))
+    b["label"] = torch.from_numpy(rng.integers(0, 2, size=B).astype(np.int32))
+    return b
+
+
+@pytest.mark.parametrize("model_name", ["fm", "deepfm"])
+@pytest.mark.parametrize("opt_name", ["sgd", "adagrad"])
+@pytest.mark.parametrize("zipf", [False, True])
+def test_ctr_models_match_oracle_twins(model_name, opt_name, zipf):
+    """Same seed -> bit-identical init; N train steps: logits, loss and every parameter within 1e-5 rel."""
+    scols, dcols, lab, rows = _ctr_setup()
+    D, B, nd = 16, 512, len(dcols)
+    if model_name == "fm":
+        prod, ref = FM(scols, dcols, lab, D, random_seed=7), ref_models.FMRef(7, scols, dcols, lab, D)
+    else:
+        prod = DeepFM(scols, dcols, lab, D, [32, 16], random_seed=7)
+        ref = ref_models.DeepFMRef(7, scols, dcols, lab, D, [32, 16])
+    for (k, v), (k2, v2) in zip(prod.state_dict().items(), ref.state_dict().items()):
+        assert k == k2 and torch.equal(v, v2), k
+    if opt_name == "sgd":
+        popt, ropt = SparseSGD(prod.get_parameters(), lr=0.3), torch.optim.SGD(ref.get_parameters(), lr=0.3)
+    else:
+        popt, ropt = SparseAdagrad(prod.get_parameters(), lr=0.05), torch.optim.Adagrad(ref.get_parameters(), lr=0.05)
+    prod.compile(popt, torch.nn.BCEWithLogitsLoss(), [LogLoss()], DEV)
+    ref.compile(ropt, torch.nn.BCEWithLogitsLoss())
+    for s in range(4):
+        batch = _ctr_batch(rows, nd, B, seed=100 + s, zipf=zipf)
+        pl, _ = prod.test_step(batch)
+        ref.eval()
+        with torch.no_grad():
+            rl, _ = ref({k: v for k, v in batch.items()})
+        np.testing.assert_allclose(pl.detach().cpu().numpy(), rl.numpy(), rtol=1e-5, atol=1e-6)
+        lp = prod.train_step(batch)["loss"].item()
+        lr_ = ref.train_step(batch)["loss"].item()
+        np.testing.assert_allclose(lp, lr_, rtol=1e-5)
+    for (k, v), (_, v2) in zip(prod.state_dict().items(), ref.state_dict().items()):
+        np.testing.assert_allclose(v.cpu().numpy(), v2.numpy(), rtol=2e-5, atol=2e-6, err_msg=k)
+    prod.embeddings.check_index_errors()
+
+
+def test_golden_ctr_regression_on_gpu(golden_ctr):
+    F, nd, D, B = (int(x) for x in golden_ctr["dims"])
+    rows = [int(r) for r in golden_ctr["rows"]]
+    scols = [Col(rows[f], f"C{f}") for f in range(F)]
+    dcols = [NumericColumn(f"I{j}", 0.0, 1.0, 0.5, 0.25) for j in range(nd)]
+    m = DeepFM(scols, dcols, Col(2, "label"), D, [16, 8], random_seed=2020)
+    m.compile(SparseAdagrad(m.get_parameters(), lr=0.1), torch.nn.BCEWithLogitsLoss(), [LogLoss()], DEV)
+    tag = "deepfm_adagrad"
+    for s in range(3):
+        b = batch_from(golden_ctr, f"{tag}/batch{s}")
+        pred, _ = m.test_step(b)
+        np.testing.assert_allclose(pred.detach().cpu().numpy(), golden_ctr[f"{tag}/pred{s}"], rtol=1e-5, atol=1e-6)
+        m.train_step(b)
+    final = state_from(golden_ctr, f"{tag}/final")
+    for k, v in m.state_dict().items():
+        np.testing.assert_allclose(v.cpu().numpy(), final[k].numpy(), rtol=2e-5, atol=2e-6, err_msg=k)
+
+
+def test_lazy_adam_and_rowwise_run_and_state_dict_roundtrip(tmp_path):
+    scols, dcols, lab, rows = _ctr_setup(F=4)
+    for Opt in (SparseAdam, SparseRowWiseAdagrad):
+        m = DeepFM(scols, dcols, lab, 8, [16], random_seed=3)
+        m.compile(Opt(m.get_parameters(), lr=0.01), torch.nn.BCEWithLogitsLoss(), [LogLoss()], DEV)
+        losses = [m.train_step(_ctr_batch(rows, len(dcols), 256, seed=5))["loss"].item() for _ in range(20)]
+        assert losses[-1] < losses[0], "training on a fixed batch must reduce the loss"
+        path = str(tmp_path / "w.pt")
+        m.save_weights(path)
+        m2 = DeepFM(scols, dcols, lab, 8, [16], random_seed=4)
+        m2.load_weights(path, DEV)
+        for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+            assert torch.equal(a, b), k
+        m.save_best_weights()
+        m.load_best_weights()
+        sd = m.compiled_optimizers.state_dict()
+        assert sd["step"] == 20
+
+
+def test_stock_sparse_optimizer_mode_gives_sparse_grads():
+    """Without a fused optimizer the tables still train: weight.grad is a coalesced sparse tensor equal
+    to the dense reference gradient."""
+    scols, dcols, lab, rows = _ctr_setup(F=3, nd=0)
+    m = FM(scols, [], lab, 8, random_seed=5).to(DEV)
+    ref = ref_models.FMRef(5, scols, [], lab, 8)
+    batch = _ctr_batch(rows, 0, 128, seed=1, zipf=True)
+    dbatch = {k: v.to(DEV) for k, v in batch.items()}
+    pl, t = m(dbatch)
+    torch.nn.functional.binary_cross_entropy_with_logits(pl, t).backward()
+    rl, rt = ref(batch)
+    torch.nn.functional.binary_cross_entropy_with_logits(rl, rt).backward()
+    for f in range(3):
+        g = m.embeddings[f].weight.grad
+        assert g.is_sparse and g.is_coalesced()
+        np.testing.assert_allclose(g.to_dense().cpu().numpy(), ref.embeddings[f].weight.grad.numpy(), rtol=1e-4, atol=1e-7)
+
+
+def test_out_of_range_id_is_reported():
+    scols, dcols, lab, rows = _ctr_setup(F=2, nd=0)
+    m = FM(scols, [], lab, 8, random_seed=5).to(DEV)
+    batch = {k: v.to(DEV) for k, v in _ctr_batch(rows, 0, 16, seed=1).items()}
+    batch["C0"][3] = rows[0] + 5
+    with torch.no_grad():
+        m(batch)
+    with pytest.raises(IndexError):
+        m.embeddings.check_index_errors()

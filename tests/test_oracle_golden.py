@@ -1,0 +1,149 @@
+"""The oracle is only as good as its pin: check every restatement against golden vectors produced by
+executing the unmodified reference (oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import batch_from, state_from
+from oracle import ref_models, ref_ops
+from pytorchrec_b200.feature_column import CategoricalColumnWithIdentity as Col
+from pytorchrec_b200.feature_column import CrossedColumn
+from pytorchrec_b200.optim import AdamW
+
+
+def _mf_setup(g):
+    n_u, n_i, D, B, L, steps = (int(x) for x in g["dims"])
+    cols = dict(uid=Col(n_u, "uid"), iid=Col(n_i, "iid"), iids=Col(n_i, "iids"), label=Col(2, "label"))
+    return cols, D, steps
+
+
+def _build(case, cols, D):
+    if case.startswith("svdpp"):
+        return ref_models.SVDPPRef(2020, cols["uid"], cols["iid"], cols["iids"], cols["label"], D)
+    return ref_models.FunkSVDRef(2020, cols["uid"], cols["iid"], cols["label"], D)
+
+
+def _optimizer(case, model):
+    if case.endswith("_sgd"):
+        return torch.optim.SGD(model.get_parameters(), lr=0.5)
+    if case.endswith("_adamw"):
+        return AdamW(model.get_parameters(), lr=0.01, weight_decay=0.1)
+    return torch.optim.Adam(model.get_parameters(), lr=0.01)
+
+
+def _loss(case):
+    from pytorchrec_b200.loss import BPRLoss
+    return BPRLoss() if "_pair_" in case else torch.nn.MSELoss()
+
+
+def test_golden_is_reference_pinned(golden_mf, golden_idioms):
+    assert int(golden_mf["pinned_by_reference"]) == 1
+    assert int(golden_idioms["pinned_by_reference"]) == 1
+
+
+@pytest.mark.parametrize("case", ["svdpp_point_sgd", "svdpp_pair_sgd", "svdpp_point_adam", "funksvd_point_sgd",
+                                  "funksvd_pair_adamw"])
+def test_restated_models_match_reference_run(golden_mf, case):
+    """Seeded init bit-exact; predictions / losses / stepped weights equal to the reference's own run."""
+    assert case in list(golden_mf["cases"])
+    cols, D, steps = _mf_setup(golden_mf)
+    model = _build(case, cols, D)
+    init = state_from(golden_mf, f"{case}/init")
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, init[k]), f"seed parity broken for {k}"
+    model.compile(_optimizer(case, model), _loss(case))
+    for s in range(steps):
+        batch = batch_from(golden_mf, f"{case}/batch{s}")
+        model.eval()
+        with torch.no_grad():
+            pred, target = model(batch)
+        np.testing.assert_allclose(pred.numpy(), golden_mf[f"{case}/pred{s}"], rtol=1e-6, atol=1e-8)
+        np.testing.assert_array_equal(target.numpy(), golden_mf[f"{case}/target{s}"])
+        loss = model.train_step(batch)["loss"].item()
+        np.testing.assert_allclose(loss, golden_mf[f"{case}/loss{s}"], rtol=1e-6)
+    final = state_from(golden_mf, f"{case}/final")
+    for k, v in model.state_dict().items():
+        np.testing.assert_allclose(v.numpy(), final[k].numpy(), rtol=1e-5, atol=1e-8, err_msg=k)
+
+
+def test_mask_and_mean_pool_idiom(golden_idioms):
+    his = torch.from_numpy(golden_idioms["his"])
+    valid = ref_ops.valid_mask(his, "pad_keep_first")
+    np.testing.assert_array_equal(valid.numpy().astype(np.uint8), golden_idioms["valid"])
+    w = torch.from_numpy(golden_idioms["weight"])
+    pooled = ref_ops.pooled_lookup_ref(w, his, "mean", "pad_keep_first")
+    np.testing.assert_allclose(pooled.numpy(), golden_idioms["pooled_mean"], rtol=1e-6, atol=1e-8)
+    ids, offsets = ref_ops.index_prep_ref(his, "pad_keep_first")
+    np.testing.assert_array_equal(np.diff(offsets.numpy()), golden_idioms["his_len"])
+    assert ids.numel() == int(offsets[-1])
+
+
+def test_sqrtn_pool_equals_svdpp_forward(golden_mf):
+    """pooled_lookup_ref('sqrtn','pad') is the pooling inside the reference SVD++ forward."""
+    case = "svdpp_point_sgd"
+    cols, D, _ = _mf_setup(golden_mf)
+    init = state_from(golden_mf, f"{case}/init")
+    b = batch_from(golden_mf, f"{case}/batch0")
+    pooled = ref_ops.pooled_lookup_ref(init["implicit_i_embeddings.weight"], b["iids"].long(), "sqrtn", "pad")
+    u = init["u_embeddings.weight"][b["uid"].long()] + pooled
+    i = init["i_embeddings.weight"][b["iid"].long()]
+    pred = (u * i).sum(-1) + init["u_bias.weight"][b["uid"].long(), 0] + init["i_bias.weight"][b["iid"].long(), 0] \
+        + init["global_bias"]
+    np.testing.assert_allclose(pred.numpy(), golden_mf[f"{case}/pred0"], rtol=1e-5, atol=1e-8)
+
+
+def test_fm2_is_the_funksvd_dot(golden_mf):
+    case = "funksvd_point_sgd"
+    init = state_from(golden_mf, f"{case}/init")
+    b = batch_from(golden_mf, f"{case}/batch0")
+    v = torch.stack([init["u_embeddings.weight"][b["uid"].long()], init["i_embeddings.weight"][b["iid"].long()]], 1)
+    np.testing.assert_allclose(ref_ops.fm2_ref(v).numpy(), golden_mf[f"{case}/pred0"], rtol=1e-5, atol=1e-9)
+
+
+def test_crossed_column(golden_idioms):
+    cols = [Col(5, "a"), Col(7, "b"), Col(3, "c")]
+    cross = CrossedColumn(cols)
+    batch = {n: torch.from_numpy(golden_idioms[f"cross/{n}"]) for n in "abc"}
+    assert cross.category_num == int(golden_idioms["cross/category_num"])
+    assert list(cross.coefficients) == list(golden_idioms["cross/coefficients"])
+    out = cross.get_feature_data(batch)
+    np.testing.assert_array_equal(out.numpy(), golden_idioms["cross/out"])
+    ref = ref_ops.crossed_ids_ref([golden_idioms[f"cross/{n}"] for n in "abc"], [5, 7, 3])
+    np.testing.assert_array_equal(ref, golden_idioms["cross/out"])
+
+
+def test_dense_embedding_grad_restatement():
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, 9, (40,), generator=g)
+    w = torch.randn(9, 4, generator=g, requires_grad=True)
+    up = torch.randn(40, 4, generator=g)
+    (torch.nn.functional.embedding(ids, w) * up).sum().backward()
+    np.testing.assert_allclose(ref_ops.dense_embedding_grad_ref(ids, up, 9).numpy(), w.grad.numpy(), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag", ["fm_sgd", "deepfm_adagrad"])
+def test_ctr_oracle_regression(golden_ctr, tag):
+    """FM / DeepFM do not exist in the reference (parity unpinned): this only freezes the oracle."""
+    assert int(golden_ctr["pinned_by_reference"]) == 0
+    from pytorchrec_b200.feature_column import NumericColumn
+    F, nd, D, B = (int(x) for x in golden_ctr["dims"])
+    rows = [int(r) for r in golden_ctr["rows"]]
+    scols = [Col(rows[f], f"C{f}") for f in range(F)]
+    dcols = [NumericColumn(f"I{j}", 0.0, 1.0, 0.5, 0.25) for j in range(nd)]
+    lab = Col(2, "label")
+    if tag.startswith("fm"):
+        model = ref_models.FMRef(2020, scols, dcols, lab, D)
+        opt = torch.optim.SGD(model.get_parameters(), lr=0.5)
+    else:
+        model = ref_models.DeepFMRef(2020, scols, dcols, lab, D, [16, 8])
+        opt = torch.optim.Adagrad(model.get_parameters(), lr=0.1)
+    model.compile(opt, torch.nn.BCEWithLogitsLoss())
+    for s in range(3):
+        b = batch_from(golden_ctr, f"{tag}/batch{s}")
+        with torch.no_grad():
+            pred, _ = model(b)
+        np.testing.assert_allclose(pred.numpy(), golden_ctr[f"{tag}/pred{s}"], rtol=1e-6, atol=1e-8)
+        model.train_step(b)
+    final = state_from(golden_ctr, f"{tag}/final")
+    for k, v in model.state_dict().items():
+        np.testing.assert_allclose(v.numpy(), final[k].numpy(), rtol=1e-5, atol=1e-8, err_msg=k)
