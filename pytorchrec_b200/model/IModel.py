@@ -82,7 +82,9 @@ class IModel(Module, ABC):
 
     # ------------------------------------------------------------------ weights
     def load_weights(self, filepath: str, device: torch.device):
-        state_dict = torch.load(filepath, map_location=device)
+        # written by save_weights with pickle.HIGHEST_PROTOCOL (as the reference does); torch>=2.6's
+        # weights-only unpickler rejects protocol 5, so load our own checkpoint with the full unpickler
+        state_dict = torch.load(filepath, map_location=device, weights_only=False)
         self.load_state_dict(state_dict)
         self.to(device)
 

@@ -85,8 +85,9 @@ class EmbeddingGroup:
         for t, table in enumerate(self.tables):
             sel = valid & (seg_table == t)
             idx = keys[sel].long() & 0xFFFFFFFF
-            grads.append(torch.sparse_coo_tensor(idx.unsqueeze(0), row_grad[:n][sel], size=table.weight.shape,
-                                                 is_coalesced=True))
+            g = torch.sparse_coo_tensor(idx.unsqueeze(0), row_grad[:n][sel], size=table.weight.shape,
+                                        check_invariants=False)
+            grads.append(g._coalesced_(True))  # segments are unique sorted rows by construction
         return grads
 
 

@@ -44,7 +44,10 @@ class _FusedSparseOptimizer(Optimizer):
                 g["params"] = dense_params
                 dense_groups.append(g)
                 self._dense_links.append((group, len(dense_groups) - 1))
-        self._dense = dense_cls(dense_groups, **dense_kwargs) if dense_groups else None
+        # The companion is built at the first step(): stock optimizers such as torch.optim.Adagrad allocate
+        # their state in __init__, i.e. before IModel.compile() moves the model to its device.
+        self._dense = None
+        self._dense_spec = (dense_cls, dense_groups, dense_kwargs) if dense_groups else None
         self._step_count_fused = 0
         self._ptr_cache: Dict[int, tuple] = {}
 
@@ -81,6 +84,7 @@ class _FusedSparseOptimizer(Optimizer):
             with torch.enable_grad():
                 loss = closure()
         self._step_count_fused += 1
+        self._ensure_dense()
         if self._dense is not None:
             for group, di in self._dense_links:
                 dg = self._dense.param_groups[di]
@@ -90,12 +94,19 @@ class _FusedSparseOptimizer(Optimizer):
             self._dense.step()
         return loss
 
+    def _ensure_dense(self):
+        if self._dense is None and self._dense_spec is not None:
+            cls, groups, kwargs = self._dense_spec
+            self._dense = cls(groups, **kwargs)
+
     def state_dict(self):
+        self._ensure_dense()
         return {"fused": super().state_dict(), "dense": self._dense.state_dict() if self._dense else None,
                 "step": self._step_count_fused}
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict["fused"])
+        self._ensure_dense()
         if self._dense is not None and state_dict.get("dense") is not None:
             self._dense.load_state_dict(state_dict["dense"])
         self._step_count_fused = int(state_dict.get("step", 0))

@@ -324,7 +324,7 @@ def test_fused_update_matches_dense_optimizers(opt_name, hp, D, hot):
             np.testing.assert_allclose(s1[t].cpu().numpy(), ropt.state[ref_w[t]]["sum"].numpy(), rtol=2e-5, atol=1e-7)
     if opt_name == "lazy_adam":
         for t in range(2):
-            np.testing.assert_allclose(s1[t].cpu().numpy(), ropt.state[ref_w[t]]["exp_avg"].numpy(), rtol=2e-5, atol=1e-7)
+            np.testing.assert_allclose(s1[t].cpu().numpy(), ropt.state[ref_w[t]]["exp_avg"].numpy(), rtol=2e-5, atol=2e-6)
             np.testing.assert_allclose(s2[t].cpu().numpy(), ropt.state[ref_w[t]]["exp_avg_sq"].numpy(), rtol=2e-5, atol=1e-9)
 
 

@@ -123,6 +123,7 @@ def test_param_groups_and_registries():
     opt = SparseAdagrad(m.get_parameters(), lr=0.1)
     assert len(opt._fused) == 4  # 2 embedding + 2 first-order tables
     fused_ids = {id(p) for p in opt._fused}
+    opt._ensure_dense()
     for g in opt._dense.param_groups:
         assert all(id(p) not in fused_ids for p in g["params"])
 
