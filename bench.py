@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--rows", type=int, default=CFG["rows"])
     ap.add_argument("--dim", type=int, default=CFG["dim"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager train_step instead of the whole-step CUDA graph")
     ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
 
@@ -43,7 +44,7 @@ def parse():
 def config_dict(a, world):
     return {"workload": "cfg2 DeepFM Criteo-shaped synthetic: 26 tables x %d rows x dim %d (+26 first-order dim 1), "
                         "13 dense, DNN 400-400-400, batch %d per GPU, fp32, sparse Adagrad" % (a.rows, a.dim, a.batch),
-            "global_batch": a.batch * world, "id_dist": a.id_dist,
+            "global_batch": a.batch * world, "id_dist": a.id_dist, "cuda_graph": (not a.no_graph) and world == 1,
             "parallelism": "single GPU" if world == 1 else f"row-wise sharded tables x{world} (all-to-all) + dense allreduce",
             "l2": "tables %.2f GB >> 126 MB L2; a different random id batch every step" %
                   (26 * a.rows * (a.dim + 1) * 4 / 1e9)}
@@ -171,6 +172,8 @@ def run_b200(a):
         model = ShardedDeepFM(sparse, dense, label, a.dim, CFG["layers"], random_seed=2020, table_device=dev)
     opt = SparseAdagrad(params=model.get_parameters(), lr=0.01)
     model.compile(opt, torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)
+    if not a.no_graph and world == 1:
+        model.enable_cuda_graph(True)
 
     n_pool = 8
     host = [criteo_batch(a.batch, CFG["n_sparse"], CFG["n_dense"], a.rows, seed=1000 * (rank + 1) + i,
@@ -205,9 +208,13 @@ def run_b200(a):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = lib.ptrec_launch_count()
+    def launch_total():
+        g = getattr(model, "_graphed", None)
+        return lib.ptrec_launch_count() + (g.replayed_launches if g is not None else 0)
+
+    l0 = launch_total()
     ms = timed(resident, a.steps, read_loss=False)
-    launches = lib.ptrec_launch_count() - l0
+    launches = launch_total() - l0
     for i in range(min(a.warmup, 3)):
         model.train_step(host[i % n_pool])
     ms_e2e = timed(host, a.steps, read_loss=True)

@@ -89,6 +89,10 @@ typedef struct ptrec_optim_args {
 int ptrec_abi_version(void);
 const char* ptrec_last_error(void); /* thread-local, valid until the next failing call */
 int64_t ptrec_launch_count(void);   /* kernels launched by this library since load (process-wide) */
+/* cudaLimitMaxL2FetchGranularity of the current device (32 / 64 / 128 bytes): random row reads narrower
+ * than the limit over-fetch from HBM.  Affects the whole device context; the caller decides. */
+int ptrec_set_l2_fetch_granularity(int32_t bytes);
+int ptrec_get_l2_fetch_granularity(void);
 
 /* ---------------------------------------------------------------------------------------------
  * a1/a6 index preparation.  Replaces the mask/len arithmetic of SVDPP.py:49,53 and

@@ -64,6 +64,8 @@ PROTOTYPES = {
     "ptrec_abi_version": (c_int, []),
     "ptrec_last_error": (c_char_p, []),
     "ptrec_launch_count": (c_int64, []),
+    "ptrec_set_l2_fetch_granularity": (c_int, [c_int32]),
+    "ptrec_get_l2_fetch_granularity": (c_int, []),
     "ptrec_index_prep_workspace_bytes": (c_size_t, [c_int64]),
     "ptrec_index_prep": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
                                  c_void_p, c_size_t, c_void_p]),

@@ -46,9 +46,30 @@ __device__ __forceinline__ float group_sum_sq(const RowVec<VEC>& g) {
   return s;
 }
 
+// Row state issued BEFORE the gradient gather so that the weight / state reads overlap it
+// (they depend only on the segment key, not on the gradient).
+template <int VEC, int OPT>
+struct RowState {
+  RowVec<VEC> w, a, b;  // weight, state1 slice, state2 slice
+  float r;              // row-wise state
+  __device__ __forceinline__ void clear() { w.zero(); a.zero(); b.zero(); r = 0.f; }
+  __device__ __forceinline__ void load(const float* wrow, const float* s1, const float* s2, int64_t row,
+                                       int D, int lane, bool lane_on) {
+    const int64_t off = row * (int64_t)D + lane * VEC;
+    clear();
+    if constexpr (OPT == kOptNone) return;
+    if (lane_on) w = load_row<VEC>(wrow + off);
+    if constexpr (OPT == PTREC_OPT_ADAGRAD) { if (lane_on) a = load_row<VEC>(s1 + off); }
+    if constexpr (OPT == PTREC_OPT_ROWWISE_ADAGRAD) { r = s1[row]; }
+    if constexpr (OPT == PTREC_OPT_LAZY_ADAM) {
+      if (lane_on) { a = load_row<VEC>(s1 + off); b = load_row<VEC>(s2 + off); }
+    }
+  }
+};
+
 // apply the optimizer to this lane's VEC-float slice of row `row`
 template <int VEC, int LPR, int OPT>
-__device__ __forceinline__ void apply_update(RowVec<VEC> g, float* __restrict__ wrow,
+__device__ __forceinline__ void apply_update(RowVec<VEC> g, const RowState<VEC, OPT>& st, float* __restrict__ wrow,
                                              float* __restrict__ s1, float* __restrict__ s2,
                                              int64_t row, int D, int lane, bool lane_on,
                                              const OptParams& op, float* row_grad_out) {
@@ -57,9 +78,7 @@ __device__ __forceinline__ void apply_update(RowVec<VEC> g, float* __restrict__ 
     if (lane_on) store_row<VEC>(row_grad_out + lane * VEC, g);
     return;
   }
-  RowVec<VEC> w;
-  w.zero();
-  if (lane_on) w = load_row<VEC>(wrow + off);
+  RowVec<VEC> w = st.w;
   if (op.weight_decay != 0.f) {
 #pragma unroll
     for (int k = 0; k < VEC; ++k) g.v[k] += op.weight_decay * w.v[k];
@@ -69,9 +88,7 @@ __device__ __forceinline__ void apply_update(RowVec<VEC> g, float* __restrict__ 
     for (int k = 0; k < VEC; ++k) w.v[k] -= op.lr * g.v[k];
   } else if constexpr (OPT == PTREC_OPT_ADAGRAD) {
     // torch.optim.Adagrad: state_sum.addcmul_(g, g); std = sqrt(state_sum) + eps; p.addcdiv_(g, std, -clr)
-    RowVec<VEC> s;
-    s.zero();
-    if (lane_on) s = load_row<VEC>(s1 + off);
+    RowVec<VEC> s = st.a;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       s.v[k] += g.v[k] * g.v[k];
@@ -82,21 +99,14 @@ __device__ __forceinline__ void apply_update(RowVec<VEC> g, float* __restrict__ 
     // one accumulator per row: state += mean_k(g_k^2)
     if (!lane_on) g.zero();
     const float ss = group_sum_sq<VEC, LPR>(g) * op.inv_D;
-    const float st = s1[row] + ss;
-    const float inv = op.lr / (sqrtf(st) + op.eps);
+    const float acc = st.r + ss;
+    const float inv = op.lr / (sqrtf(acc) + op.eps);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) w.v[k] -= inv * g.v[k];
-    __syncwarp(group_mask<LPR>());  // every lane has read s1[row] before lane 0 overwrites it
-    if (lane == 0) s1[row] = st;
+    if (lane == 0) s1[row] = acc;
   } else if constexpr (OPT == PTREC_OPT_LAZY_ADAM) {
     // torch.optim.SparseAdam (_functional.sparse_adam): moments move only on touched rows
-    RowVec<VEC> m, v;
-    m.zero();
-    v.zero();
-    if (lane_on) {
-      m = load_row<VEC>(s1 + off);
-      v = load_row<VEC>(s2 + off);
-    }
+    RowVec<VEC> m = st.a, v = st.b;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       m.v[k] += (g.v[k] - m.v[k]) * (1.f - op.beta1);
@@ -111,15 +121,42 @@ __device__ __forceinline__ void apply_update(RowVec<VEC> g, float* __restrict__ 
   if (lane_on) store_row<VEC>(wrow + off, w);
 }
 
-// gradient row of slot p, scaled by its bag's pooling factor
+// Per-CTA shared lookup: features of each table (contiguous range) and each feature's first slot.
+struct SlotMap {
+  ptrec_feature_desc feats[kMaxFeatures];
+  uint32_t base[kMaxFeatures];  // first slot of feature f = id_base * B (N < 2^31)
+  int16_t f0[kMaxTables];       // first feature of table t
+  int16_t nf[kMaxTables];       // number of features of table t
+};
+__device__ __forceinline__ void build_slot_map(SlotMap* m, const ptrec_feature_desc* g, int F, int T, int64_t B) {
+  load_feats(m->feats, g, F);
+  for (int t = threadIdx.x; t < T; t += blockDim.x) { m->f0[t] = 0; m->nf[t] = 0; }
+  __syncthreads();
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    m->base[f] = (uint32_t)(m->feats[f].id_base * B);
+    const int t = m->feats[f].table;
+    if (f == 0 || m->feats[f - 1].table != t) m->f0[t] = (int16_t)f;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    int n = 0;
+    for (int f = m->f0[t]; f < F && m->feats[f].table == t; ++f) ++n;
+    m->nf[t] = (int16_t)n;
+  }
+  __syncthreads();
+}
+
+// gradient row of slot p (which belongs to table t), scaled by its bag's pooling factor
 template <int VEC>
-__device__ __forceinline__ RowVec<VEC> slot_grad(const ptrec_feature_desc* s_feats, int F, int64_t B,
+__device__ __forceinline__ RowVec<VEC> slot_grad(const SlotMap* m, int t, int64_t B,
                                                  int32_t p, const float* __restrict__ grad_out,
                                                  int64_t stride, const float* __restrict__ bag_scale,
                                                  int lane, bool lane_on) {
-  const int f = find_feature(s_feats, F, B, p);
-  const ptrec_feature_desc& fd = s_feats[f];
-  const int64_t b = ((int64_t)p - fd.id_base * B) / fd.bag_len;
+  int f = m->f0[t];
+  for (int e = f + m->nf[t] - 1; f < e && m->base[f + 1] <= (uint32_t)p; ++f) {}
+  const ptrec_feature_desc& fd = m->feats[f];
+  const uint32_t rel = (uint32_t)p - m->base[f];
+  const int64_t b = fd.bag_len == 1 ? rel : rel / (uint32_t)fd.bag_len;
   RowVec<VEC> g;
   g.zero();
   if (lane_on) g = load_row_stream<VEC>(grad_out + b * stride + fd.out_col + lane * VEC);
@@ -133,7 +170,7 @@ __device__ __forceinline__ RowVec<VEC> slot_grad(const ptrec_feature_desc* s_fea
 template <int VEC, int LPR, int OPT>
 __global__ void __launch_bounds__(kUpdThreads)
 fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restrict__ state1_ptrs,
-                    void* const* __restrict__ state2_ptrs, int D,
+                    void* const* __restrict__ state2_ptrs, int T, int D,
                     const ptrec_feature_desc* __restrict__ feats, int F, int64_t B,
                     const uint32_t* __restrict__ sorted_keys, const int32_t* __restrict__ perm,
                     const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_table,
@@ -141,55 +178,59 @@ fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restric
                     int64_t stride, const float* __restrict__ bag_scale, OptParams op,
                     int* __restrict__ long_count, int32_t* __restrict__ long_list,
                     float* __restrict__ row_grad) {
-  __shared__ ptrec_feature_desc s_feats[kMaxFeatures];
-  load_feats(s_feats, feats, F);
-  __syncthreads();
+  __shared__ SlotMap s_map;
+  build_slot_map(&s_map, feats, F, T, B);
   constexpr int NSG = kUpdThreads / LPR;
   const int sg = threadIdx.x / LPR, lane = threadIdx.x % LPR;
   const bool lane_on = lane * VEC < D;
   const int n_seg = *n_seg_ptr;
-  // every sub-warp of a warp runs the same number of iterations (shuffles inside apply_update)
   const int n_round = (n_seg + NSG - 1) / NSG;
   for (int r = blockIdx.x; r < n_round; r += gridDim.x) {
     const int u = r * NSG + sg;
     const bool live = u < n_seg;
-    int start = 0, end = 0;
+    int start = 0, end = 0, t = 0;
     uint32_t key = kMaskedKey;
     if (live) {
       start = seg_start[u];
       end = seg_start[u + 1];
+      t = seg_table[u];
       key = sorted_keys[start];
     }
     const bool masked = key == kMaskedKey;
     const bool is_long = live && !masked && (end - start) > kLongSeg && OPT != kOptNone;
     if (is_long && lane == 0) long_list[atomicAdd(long_count, 1)] = u;
     const bool work = live && !masked && !is_long;
+    float* wrow = nullptr;
+    float* s1 = nullptr;
+    float* s2 = nullptr;
+    RowState<VEC, OPT> st;
+    st.clear();
+    if (OPT != kOptNone && work) {
+      wrow = reinterpret_cast<float*>(table_ptrs[t]);
+      if (state1_ptrs) s1 = reinterpret_cast<float*>(state1_ptrs[t]);
+      if (state2_ptrs) s2 = reinterpret_cast<float*>(state2_ptrs[t]);
+      st.load(wrow, s1, s2, (int64_t)key, D, lane, lane_on);
+    }
     RowVec<VEC> acc;
     acc.zero();
-    if (work) {
+    if (work || (OPT == kOptNone && live && !masked)) {
       for (int j0 = start; j0 < end; j0 += 4) {
         RowVec<VEC> g[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           g[q].zero();
           if (j0 + q < end)
-            g[q] = slot_grad<VEC>(s_feats, F, B, perm[j0 + q], grad_out, stride, bag_scale, lane, lane_on);
+            g[q] = slot_grad<VEC>(&s_map, t, B, perm[j0 + q], grad_out, stride, bag_scale, lane, lane_on);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc.add(g[q]);
       }
     }
     if constexpr (OPT == kOptNone) {
-      if (live) apply_update<VEC, LPR, OPT>(acc, nullptr, nullptr, nullptr, 0, D, lane, lane_on, op,
+      if (live) apply_update<VEC, LPR, OPT>(acc, st, nullptr, nullptr, nullptr, 0, D, lane, lane_on, op,
                                             row_grad + (int64_t)u * D);
     } else {
-      if (work) {
-        const int t = seg_table[u];
-        apply_update<VEC, LPR, OPT>(acc, reinterpret_cast<float*>(table_ptrs[t]),
-                                    state1_ptrs ? reinterpret_cast<float*>(state1_ptrs[t]) : nullptr,
-                                    state2_ptrs ? reinterpret_cast<float*>(state2_ptrs[t]) : nullptr,
-                                    (int64_t)key, D, lane, lane_on, op, nullptr);
-      }
+      if (work) apply_update<VEC, LPR, OPT>(acc, st, wrow, s1, s2, (int64_t)key, D, lane, lane_on, op, nullptr);
     }
   }
 }
@@ -198,32 +239,33 @@ fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restric
 template <int VEC, int LPR, int OPT>
 __global__ void __launch_bounds__(kLongThreads)
 fused_update_long_kernel(void* const* __restrict__ table_ptrs, void* const* __restrict__ state1_ptrs,
-                         void* const* __restrict__ state2_ptrs, int D,
+                         void* const* __restrict__ state2_ptrs, int T, int D,
                          const ptrec_feature_desc* __restrict__ feats, int F, int64_t B,
                          const uint32_t* __restrict__ sorted_keys, const int32_t* __restrict__ perm,
                          const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_table,
                          const float* __restrict__ grad_out, int64_t stride,
                          const float* __restrict__ bag_scale, OptParams op,
                          const int* __restrict__ long_count, const int32_t* __restrict__ long_list) {
-  __shared__ ptrec_feature_desc s_feats[kMaxFeatures];
+  const int n_long = *long_count;
+  if ((int)blockIdx.x >= n_long) return;  // the common case (no hot rows): exit before any setup
+  __shared__ SlotMap s_map;
   constexpr int NSG = kLongThreads / LPR;
   __shared__ float s_part[NSG * LPR * VEC];
-  load_feats(s_feats, feats, F);
-  __syncthreads();
+  build_slot_map(&s_map, feats, F, T, B);
   const int sg = threadIdx.x / LPR, lane = threadIdx.x % LPR;
   const bool lane_on = lane * VEC < D;
-  const int n_long = *long_count;
   for (int i = blockIdx.x; i < n_long; i += gridDim.x) {
     const int u = long_list[i];
     const int start = seg_start[u], end = seg_start[u + 1];
+    const int t = seg_table[u];
     RowVec<VEC> acc;
     acc.zero();
     for (int j0 = start + sg; j0 < end; j0 += NSG * 2) {
       RowVec<VEC> g0, g1;
-      g0 = slot_grad<VEC>(s_feats, F, B, perm[j0], grad_out, stride, bag_scale, lane, lane_on);
+      g0 = slot_grad<VEC>(&s_map, t, B, perm[j0], grad_out, stride, bag_scale, lane, lane_on);
       g1.zero();
       if (j0 + NSG < end)
-        g1 = slot_grad<VEC>(s_feats, F, B, perm[j0 + NSG], grad_out, stride, bag_scale, lane, lane_on);
+        g1 = slot_grad<VEC>(&s_map, t, B, perm[j0 + NSG], grad_out, stride, bag_scale, lane, lane_on);
       acc.add(g0);
       acc.add(g1);
     }
@@ -239,29 +281,24 @@ fused_update_long_kernel(void* const* __restrict__ table_ptrs, void* const* __re
       }
       __syncthreads();
     }
-    if (threadIdx.x < 32) {  // first warp converged: sub-warp 0 applies, its warp-mates idle
-      const bool doit = sg == 0;
+    if (sg == 0) {  // sub-warp 0 owns the row
       RowVec<VEC> tot;
-      tot.zero();
-      if (doit) {
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) tot.v[k] = mine[k];
-      }
-      const int t = seg_table[u];
+      for (int k = 0; k < VEC; ++k) tot.v[k] = mine[k];
       const uint32_t key = sorted_keys[start];
-      if (doit) {
-        apply_update<VEC, LPR, OPT>(tot, reinterpret_cast<float*>(table_ptrs[t]),
-                                    state1_ptrs ? reinterpret_cast<float*>(state1_ptrs[t]) : nullptr,
-                                    state2_ptrs ? reinterpret_cast<float*>(state2_ptrs[t]) : nullptr,
-                                    (int64_t)key, D, lane, lane_on, op, nullptr);
-      }
+      float* wrow = reinterpret_cast<float*>(table_ptrs[t]);
+      float* s1 = state1_ptrs ? reinterpret_cast<float*>(state1_ptrs[t]) : nullptr;
+      float* s2 = state2_ptrs ? reinterpret_cast<float*>(state2_ptrs[t]) : nullptr;
+      RowState<VEC, OPT> st;
+      st.load(wrow, s1, s2, (int64_t)key, D, lane, lane_on);
+      apply_update<VEC, LPR, OPT>(tot, st, wrow, s1, s2, (int64_t)key, D, lane, lane_on, op, nullptr);
     }
     __syncthreads();
   }
 }
 
 template <int VEC, int LPR, int OPT>
-static int launch_update(void* const* table_ptrs, void* const* s1, void* const* s2, int D,
+static int launch_update(void* const* table_ptrs, void* const* s1, void* const* s2, int T, int D,
                          const ptrec_feature_desc* feats, int F, int64_t B, int64_t N,
                          const uint32_t* sorted_keys, const int32_t* perm, const int32_t* seg_start,
                          const int32_t* seg_table, const int32_t* n_seg, const float* grad_out,
@@ -275,12 +312,12 @@ static int launch_update(void* const* table_ptrs, void* const* s1, void* const* 
   const unsigned grid = (unsigned)(rounds < (int64_t)sms * 16 ? (rounds > 0 ? rounds : 1) : (int64_t)sms * 16);
   if (OPT != kOptNone) PTREC_CUDA(cudaMemsetAsync(long_count, 0, sizeof(int), st));
   fused_update_kernel<VEC, LPR, OPT><<<grid, kUpdThreads, 0, st>>>(
-      table_ptrs, s1, s2, D, feats, F, B, sorted_keys, perm, seg_start, seg_table, n_seg, grad_out,
+      table_ptrs, s1, s2, T, D, feats, F, B, sorted_keys, perm, seg_start, seg_table, n_seg, grad_out,
       stride, bag_scale, op, long_count, long_list, row_grad);
   PTREC_LAUNCH_CHECK("fused_update_kernel");
   if (OPT != kOptNone) {
     fused_update_long_kernel<VEC, LPR, OPT><<<sms * 2, kLongThreads, 0, st>>>(
-        table_ptrs, s1, s2, D, feats, F, B, sorted_keys, perm, seg_start, seg_table, grad_out, stride,
+        table_ptrs, s1, s2, T, D, feats, F, B, sorted_keys, perm, seg_start, seg_table, grad_out, stride,
         bag_scale, op, long_count, long_list);
     PTREC_LAUNCH_CHECK("fused_update_long_kernel");
   }
@@ -288,14 +325,14 @@ static int launch_update(void* const* table_ptrs, void* const* s1, void* const* 
 }
 
 template <int OPT>
-static int dispatch_D(void* const* table_ptrs, void* const* s1, void* const* s2, int D,
+static int dispatch_D(void* const* table_ptrs, void* const* s1, void* const* s2, int T, int D,
                       const ptrec_feature_desc* feats, int F, int64_t B, int64_t N,
                       const uint32_t* sorted_keys, const int32_t* perm, const int32_t* seg_start,
                       const int32_t* seg_table, const int32_t* n_seg, const float* grad_out,
                       int64_t stride, const float* bag_scale, const OptParams& op, int* long_count,
                       int32_t* long_list, float* row_grad, cudaStream_t st) {
 #define PTREC_UPD(V, P) \
-  return launch_update<V, P, OPT>(table_ptrs, s1, s2, D, feats, F, B, N, sorted_keys, perm, seg_start, \
+  return launch_update<V, P, OPT>(table_ptrs, s1, s2, T, D, feats, F, B, N, sorted_keys, perm, seg_start, \
                                   seg_table, n_seg, grad_out, stride, bag_scale, op, long_count,        \
                                   long_list, row_grad, st)
   if (D == 1) PTREC_UPD(1, 1);
@@ -371,7 +408,7 @@ extern "C" int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* s
   int32_t* long_list = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(workspace) + 256);
   cudaStream_t st = (cudaStream_t)stream;
 #define PTREC_ARGS                                                                                      \
-  table_ptrs, state1_ptrs, state2_ptrs, D, feats, F, B, N, sorted_keys, perm, seg_start, seg_table, n_seg, \
+  table_ptrs, state1_ptrs, state2_ptrs, T, D, feats, F, B, N, sorted_keys, perm, seg_start, seg_table, n_seg, \
       grad_out, grad_row_stride, bag_scale, op, long_count, long_list, nullptr, st
   switch (opt_host->kind) {
     case PTREC_OPT_SGD:
@@ -429,7 +466,7 @@ extern "C" int ptrec_embedding_bwd_segment_sum(int32_t T, int32_t D, const ptrec
   const int64_t N = total_slots(feats_host, F, B);
   if (N == 0) return PTREC_OK;
   OptParams op{};
-  return dispatch_D<kOptNone>(nullptr, nullptr, nullptr, D, feats, F, B, N, sorted_keys, perm, seg_start,
+  return dispatch_D<kOptNone>(nullptr, nullptr, nullptr, T, D, feats, F, B, N, sorted_keys, perm, seg_start,
                               seg_table, n_seg, grad_out, grad_row_stride, bag_scale, op, nullptr,
                               nullptr, row_grad, (cudaStream_t)stream);
 }

@@ -41,26 +41,46 @@ __device__ __forceinline__ int table_of_slot(const TableLayout& lay, int64_t B, 
   return lo;
 }
 
-// key of slot p straight from the id matrices (first pass only)
+// key of slot p straight from the id matrices (first pass only).  A sort tile lies inside one table,
+// whose features are a contiguous descriptor range [f0, f0+nf): no search for single-feature tables,
+// no division for one-hot features, 32-bit arithmetic throughout (N < 2^31).
 struct KeyGen {
   const ptrec_feature_desc* feats;  // shared-memory copy
-  int F;
+  int f0, nf;
   const int64_t* ids;
   const int32_t* lens;
-  const int64_t* table_rows;
+  int64_t rows;  // rows of this tile's table
   int64_t B;
   __device__ __forceinline__ uint32_t operator()(int64_t p) const {
-    const int f = find_feature(feats, F, B, p);
+    int f = f0;
+    for (int e = f0 + nf - 1; f < e && feats[f + 1].id_base * B <= p; ++f) {}
     const ptrec_feature_desc& fd = feats[f];
-    const int64_t rel = p - fd.id_base * B;
-    const int64_t b = rel / fd.bag_len;
-    const int l = (int)(rel - b * fd.bag_len);
     const int64_t id = ids[p];
-    bool valid = slot_valid(fd.mask_mode, id, l, lens, fd.lens_col, B, b);
-    valid = valid && ((uint64_t)id < (uint64_t)table_rows[fd.table]);
+    bool valid = (uint64_t)id < (uint64_t)rows;
+    if (fd.mask_mode != PTREC_MASK_NONE) {
+      const uint32_t rel = (uint32_t)(p - fd.id_base * B);
+      const uint32_t b = rel / (uint32_t)fd.bag_len;
+      const int l = (int)(rel - b * (uint32_t)fd.bag_len);
+      valid = valid && slot_valid(fd.mask_mode, id, l, lens, fd.lens_col, B, b);
+    }
     return valid ? (uint32_t)id : kMaskedKey;
   }
 };
+
+// feature range of table t (thread 0 scans the <= 128 descriptors; result broadcast through smem)
+__device__ __forceinline__ void table_feature_range(const ptrec_feature_desc* s_feats, int F, int t, int* s_rng) {
+  if (threadIdx.x == 0) {
+    int f0 = 0, nf = 0;
+    for (int f = 0; f < F; ++f) {
+      if (s_feats[f].table == t) {
+        if (nf == 0) f0 = f;
+        ++nf;
+      }
+    }
+    s_rng[0] = f0;
+    s_rng[1] = nf;
+  }
+}
 
 template <bool FIRST>
 __global__ void __launch_bounds__(kSortThreads)
@@ -76,10 +96,15 @@ radix_hist_kernel(TableLayout lay, int64_t B, int shift, const uint32_t* __restr
   const int tiles_t = lay.tile_prefix[t + 1] - lay.tile_prefix[t];
   const int64_t beg = lay.Lstart[t] * B + (int64_t)k * kSortTile;
   const int64_t end = min(lay.Lstart[t + 1] * B, beg + kSortTile);
+  __shared__ int s_rng[2];
   s_hist[threadIdx.x] = 0;
-  if (FIRST) load_feats(s_feats, feats, F);
+  if (FIRST) {
+    load_feats(s_feats, feats, F);
+    __syncthreads();
+    table_feature_range(s_feats, F, t, s_rng);
+  }
   __syncthreads();
-  KeyGen gen{s_feats, F, ids, lens, table_rows, B};
+  KeyGen gen{s_feats, FIRST ? s_rng[0] : 0, FIRST ? s_rng[1] : 0, ids, lens, FIRST ? table_rows[t] : 0, B};
   for (int64_t j = beg + threadIdx.x; j < end; j += kSortThreads) {
     const uint32_t key = FIRST ? gen(j) : keys_in[j];
     atomicAdd(&s_hist[(key >> shift) & (kRadix - 1)], 1);
@@ -132,9 +157,14 @@ radix_scatter_kernel(TableLayout lay, int64_t B, int shift, const uint32_t* __re
 #pragma unroll
   for (int w = 0; w < NW; ++w) s_cnt[w][threadIdx.x] = 0;
   s_goff[threadIdx.x] = offsets[(int64_t)lay.tile_prefix[t] * kRadix + (int64_t)threadIdx.x * tiles_t + k];
-  if (FIRST) load_feats(s_feats, feats, F);
+  __shared__ int s_rng[2];
+  if (FIRST) {
+    load_feats(s_feats, feats, F);
+    __syncthreads();
+    table_feature_range(s_feats, F, t, s_rng);
+  }
   __syncthreads();
-  KeyGen gen{s_feats, F, ids, lens, table_rows, B};
+  KeyGen gen{s_feats, FIRST ? s_rng[0] : 0, FIRST ? s_rng[1] : 0, ids, lens, FIRST ? table_rows[t] : 0, B};
 
   uint32_t key[kSortItems];
   int32_t pay[kSortItems];

@@ -38,6 +38,68 @@ class History:
             self.history.setdefault(k, []).append(v)
 
 
+_LOOKUP_CACHE_KEY = "__ptrec_lookup_cache__"
+
+
+def _drop_lookup_cache(module, args):
+    """Forward pre-hook: the per-batch lookup cache (packed ids, shared sort) never outlives one forward."""
+    if args and isinstance(args[0], dict):
+        args[0].pop(_LOOKUP_CACHE_KEY, None)
+
+
+class _GraphedTrainStep:
+    """Whole-step CUDA graph (forward, loss, zero_grad, backward with the fused sparse update, dense
+    optimizer step) keyed by the batch signature.  The first ``warmup`` steps of a signature run eagerly —
+    they are real training steps and initialise every lazily-allocated buffer (optimizer state, pointer
+    arrays, workspaces) outside the capture.  Inputs are copied into static device tensors and the graph
+    is replayed; nothing is skipped or cached across steps."""
+
+    def __init__(self, model: "IModel", warmup: int = 2):
+        self.model = model
+        self.warmup = warmup
+        self.entries: Dict[tuple, dict] = {}
+        self.replayed_launches = 0  # libptrec kernel launches executed through graph replays
+
+    def step(self, data: Dict[str, torch.Tensor]):
+        m = self.model
+        sig = tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in data.items() if isinstance(v, torch.Tensor)))
+        e = self.entries.setdefault(sig, {"n": 0, "graph": None})
+        if e["n"] < self.warmup:
+            e["n"] += 1
+            return m._eager_train_step(data)
+        dev = m.compiled_device
+        opt = m.compiled_optimizers
+        if e["graph"] is None:
+            if not getattr(opt, "graph_safe", lambda: False)():
+                raise RuntimeError("CUDA-graph train steps need an optimizer whose update does not depend on the "
+                                   "host-side step count (SparseSGD, SparseAdagrad / SparseRowWiseAdagrad with lr_decay=0)")
+            e["static"] = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in data.items()
+                           if isinstance(v, torch.Tensor)}
+            for k, v in e["static"].items():
+                v.copy_(data[k])
+            torch.cuda.synchronize(dev)
+            m.train()
+            from .. import _lib
+            l0 = _lib.load().ptrec_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                prediction, target = m(dict(e["static"]))  # forward may add private entries to its dict
+                loss = m.compiled_loss(prediction, target)
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+            opt._step_count_fused -= 1  # capture records the step, it does not execute it
+            e["graph"], e["loss"] = g, loss
+            e["launches"] = int(_lib.load().ptrec_launch_count() - l0)  # recorded into the graph, not yet run
+        else:
+            for k, v in e["static"].items():
+                v.copy_(data[k], non_blocking=True)
+        e["graph"].replay()
+        self.replayed_launches += e["launches"]
+        opt._step_count_fused += 1
+        return {"loss": e["loss"]}
+
+
 class IModel(Module, ABC):
     """Model interface: subclasses implement ``_init_weights`` and ``forward(data) -> (prediction, target)``."""
 
@@ -60,6 +122,8 @@ class IModel(Module, ABC):
         self.compiled_loss: Optional[_Loss] = None
         self.compiled_metrics: Optional[MetricList] = None
         self.compiled_device: Optional[torch.device] = None
+        self._graphed: Optional[_GraphedTrainStep] = None
+        self.register_forward_pre_hook(_drop_lookup_cache)
         self._init_weights()
         self._reset_weights()
 
@@ -117,7 +181,16 @@ class IModel(Module, ABC):
         self.to(device)
         self._is_compiled = True
 
+    def enable_cuda_graph(self, enabled: bool = True, warmup: int = 2) -> None:
+        """Replay ``train_step`` as one CUDA graph per batch signature (CUDA devices only)."""
+        self._graphed = _GraphedTrainStep(self, warmup) if enabled else None
+
     def train_step(self, data: Dict):
+        if self._graphed is not None and self.compiled_device is not None and self.compiled_device.type == "cuda":
+            return self._graphed.step(data)
+        return self._eager_train_step(data)
+
+    def _eager_train_step(self, data: Dict):
         self.train()
         data = tensor_to_device(data, self.compiled_device)
         prediction, target = self(data)

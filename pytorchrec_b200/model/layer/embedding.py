@@ -22,6 +22,7 @@ from ... import ops
 from ...feature_column import CategoricalColumn
 
 _MASKED = -1  # 0xFFFFFFFF viewed as int32
+_CACHE_KEY = "__ptrec_lookup_cache__"  # private per-batch entry (never a tensor: tensor_to_device skips it)
 
 
 class EmbeddingGroup:
@@ -66,9 +67,14 @@ class EmbeddingGroup:
                 raise RuntimeError("some tables of this embedding group are not owned by the fused optimizer")
         return b
 
-    def apply_backward(self, layout, ids, lens, bag_scale, batch, grad_out):
+    def apply_backward(self, layout, ids, lens, bag_scale, batch, grad_out, shared=None):
         tables = self.table_set.refresh([w.data for w in self.weights()])
-        srt = ops.sort_dedup(tables, layout, ids, lens, batch)
+        # modules reading the same columns (e.g. FM's embedding and first-order tables) share one sort
+        srt = shared.get("sort") if shared is not None else None
+        if srt is None:
+            srt = ops.sort_dedup(tables, layout, ids, lens, batch)
+            if shared is not None:
+                shared["sort"] = srt
         bind = self.binding()
         if bind is not None:
             optimizer, group = bind
@@ -93,12 +99,12 @@ class EmbeddingGroup:
 
 class _FusedLookup(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, group: EmbeddingGroup, layout, ids, lens, batch, *weights):
+    def forward(ctx, group: EmbeddingGroup, layout, ids, lens, batch, shared, *weights):
         tables = group.table_set.refresh([w.detach() for w in weights])
         needs_scale = any(fd.pooling != 0 for fd in layout.host)
         out, bag_scale = ops.gather_pool_fwd(tables, layout, ids, lens, batch, want_scale=needs_scale,
                                              err_flag=group.err_flag(ids.device))
-        ctx.group, ctx.layout, ctx.batch = group, layout, batch
+        ctx.group, ctx.layout, ctx.batch, ctx.shared = group, layout, batch, shared
         ctx.save_for_backward(ids, lens, bag_scale)
         return out
 
@@ -107,8 +113,8 @@ class _FusedLookup(torch.autograd.Function):
         ids, lens, bag_scale = ctx.saved_tensors
         if not (grad_out.stride(1) == 1 and grad_out.data_ptr() % 16 == 0 and grad_out.stride(0) % 4 == 0):
             grad_out = grad_out.contiguous()
-        grads = ctx.group.apply_backward(ctx.layout, ids, lens, bag_scale, ctx.batch, grad_out)
-        return (None, None, None, None, None, *grads)
+        grads = ctx.group.apply_backward(ctx.layout, ids, lens, bag_scale, ctx.batch, grad_out, ctx.shared)
+        return (None, None, None, None, None, None, *grads)
 
 
 class EmbeddingTable(nn.Module):
@@ -143,7 +149,7 @@ class EmbeddingTable(nn.Module):
         if flat.dtype != torch.int64:
             flat = flat.long()
         flat = flat.contiguous()
-        out = _FusedLookup.apply(self._group, self._layout, flat, None, flat.numel(), self.weight)
+        out = _FusedLookup.apply(self._group, self._layout, flat, None, flat.numel(), None, self.weight)
         return out.view(*ids.shape, self.embedding_dim)
 
     def pooled(self, ids: Tensor, pooling: str = "sum", mask: str = "pad", lens: Optional[Tensor] = None) -> Tensor:
@@ -170,7 +176,7 @@ class EmbeddingTable(nn.Module):
             if lens is None:
                 raise ValueError("mask='lens' needs lens")
             lens32 = lens.reshape(1, B).to(torch.int32).contiguous()
-        return _FusedLookup.apply(self._group, lay, flat, lens32, B, self.weight)
+        return _FusedLookup.apply(self._group, lay, flat, lens32, B, None, self.weight)
 
     def extra_repr(self):
         return f"{self.num_embeddings}, {self.embedding_dim}"
@@ -265,15 +271,31 @@ class MultiTableEmbedding(nn.ModuleList):
         B = id_list[0].shape[0]
         bag_lens = tuple(1 if t.dim() == 1 else int(t.shape[1]) for t in id_list)
         layout = self._layout_for(bag_lens)
-        ids = torch.cat([id_list[i].reshape(-1) for i in self._order]) if len(id_list) > 1 \
-            else id_list[0].reshape(-1).contiguous()
-        lens = None
-        if layout.lens_names:
-            lens = torch.stack([self._lens_columns[n].get_feature_data(batch).reshape(-1)
-                                for n in layout.lens_names]).to(torch.int32).contiguous()
+        # Per-batch cache kept inside the batch dict: modules reading the same columns with the same
+        # masks and table heights share the packed id tensor and, in backward, ONE sort/dedup.
+        cache = batch.get(_CACHE_KEY) if isinstance(batch, dict) else None
+        if cache is None:
+            cache = {}
+            if isinstance(batch, dict):
+                batch[_CACHE_KEY] = cache
+        key = (tuple(self.feature_names[i] for i in self._order), bag_lens,
+               tuple(self._mask[self.feature_names[i]] for i in self._order),
+               tuple(t.num_embeddings for t in self.tables), tuple(self._table_of),
+               tuple((t.data_ptr(), t._version) for t in id_list))
+        shared = cache.get(key)
+        if shared is None:
+            ids = torch.cat([id_list[i].reshape(-1) for i in self._order]) if len(id_list) > 1 \
+                else id_list[0].reshape(-1).contiguous()
+            lens = None
+            if layout.lens_names:
+                lens = torch.stack([self._lens_columns[n].get_feature_data(batch).reshape(-1)
+                                    for n in layout.lens_names]).to(torch.int32).contiguous()
+            shared = {"ids": ids, "lens": lens}
+            cache[key] = shared
+        ids, lens = shared["ids"], shared["lens"]
         for t in self.tables:
             t._tag()
-        out = _FusedLookup.apply(self._group, layout, ids, lens, B, *[t.weight for t in self.tables])
+        out = _FusedLookup.apply(self._group, layout, ids, lens, B, shared, *[t.weight for t in self.tables])
         return out.view(B, len(self.columns), self.emb_size)
 
     def check_index_errors(self) -> None:

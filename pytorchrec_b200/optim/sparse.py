@@ -51,6 +51,10 @@ class _FusedSparseOptimizer(Optimizer):
         self._step_count_fused = 0
         self._ptr_cache: Dict[int, tuple] = {}
 
+    def graph_safe(self) -> bool:
+        """True when a captured step stays valid on replay (no host-side step count in the arithmetic)."""
+        return False
+
     # ---- called by EmbeddingGroup.apply_backward -------------------------------------------------
     def _state_tensors(self, p: torch.Tensor):
         """(state1, state2) for table ``p`` — allocated on first use on the table's device."""
@@ -124,6 +128,9 @@ class SparseSGD(_FusedSparseOptimizer):
         super().__init__(params, dict(lr=lr, weight_decay=weight_decay), torch.optim.SGD,
                          dict(lr=lr, weight_decay=weight_decay))
 
+    def graph_safe(self):
+        return True
+
     def _state_tensors(self, p):
         return None, None
 
@@ -144,6 +151,9 @@ class SparseAdagrad(_FusedSparseOptimizer):
         defaults = dict(lr=lr, lr_decay=lr_decay, weight_decay=weight_decay,
                         initial_accumulator_value=initial_accumulator_value, eps=eps)
         super().__init__(params, defaults, torch.optim.Adagrad, dict(defaults))
+
+    def graph_safe(self):
+        return all(g["lr_decay"] == 0 for g in self.param_groups)
 
     def _state_tensors(self, p):
         st = self.state[p]

@@ -177,3 +177,26 @@ def test_out_of_range_id_is_reported():
         m(batch)
     with pytest.raises(IndexError):
         m.embeddings.check_index_errors()
+
+
+def test_cuda_graph_train_step_equals_eager():
+    """The whole-step CUDA graph replays exactly the eager step (same kernels, same order)."""
+    scols, dcols, lab, rows = _ctr_setup()
+    models = []
+    for graphed in (False, True):
+        m = DeepFM(scols, dcols, lab, 16, [32, 16], random_seed=9)
+        m.compile(SparseAdagrad(m.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], DEV)
+        if graphed:
+            m.enable_cuda_graph(True, warmup=2)
+        losses = [m.train_step(_ctr_batch(rows, len(dcols), 256, seed=40 + s, zipf=True))["loss"].item() for s in range(6)]
+        models.append((m, losses))
+    (me, le), (mg, lg) = models
+    np.testing.assert_allclose(lg, le, rtol=1e-6)
+    for (k, a), (_, b) in zip(me.state_dict().items(), mg.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert mg.compiled_optimizers._step_count_fused == 6
+    with pytest.raises(RuntimeError):
+        m = DeepFM(scols, dcols, lab, 16, [32, 16], random_seed=9)
+        m.compile(SparseAdam(m.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], DEV)
+        m.enable_cuda_graph(True, warmup=0)
+        m.train_step(_ctr_batch(rows, len(dcols), 256, seed=1))
