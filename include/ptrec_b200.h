@@ -51,6 +51,9 @@ extern "C" {
 #define PTREC_MASK_PAD_KEEP_FIRST 2 /* id != 0 or slot 0    model/utils.py:5-10 (get_valid_his_index) */
 #define PTREC_MASK_LENS 3           /* slot < lens[b]       SASRec.py:109-110 / HistoryDataReader     */
 
+/* feature flags */
+#define PTREC_FEAT_NEG_IS_PAD 1 /* ids < 0 are empty slots (fixed-capacity all-to-all lists): skipped, no error */
+
 /* fused optimizers */
 #define PTREC_OPT_SGD 0
 #define PTREC_OPT_ADAGRAD 1
@@ -69,7 +72,7 @@ typedef struct ptrec_feature_desc {
   int32_t pooling;   /* PTREC_POOL_*                                                        */
   int32_t mask_mode; /* PTREC_MASK_*                                                        */
   int32_t lens_col;  /* row of `lens` ([n_cols, B] int32) used by PTREC_MASK_LENS, else -1  */
-  int32_t reserved;
+  int32_t flags;     /* PTREC_FEAT_* bits                                                  */
   int64_t id_base;   /* sum of bag_len over the features before this one                    */
   int64_t out_col;   /* float offset of this feature's pooled vector inside an output row   */
 } ptrec_feature_desc;
@@ -222,6 +225,25 @@ int ptrec_fm2_fwd(const float* v, int64_t v_row_stride, int64_t B, int32_t F, in
 int ptrec_fm2_bwd(const float* v, int64_t v_row_stride, const float* gy, const float* grad_in,
                   int64_t grad_in_row_stride, int64_t B, int32_t F, int32_t D, float* grad_v,
                   int64_t grad_v_row_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * C1 row-wise sharding: pack / unpack either side of the all-to-all (NCCL, issued by the host through
+ * torch.distributed).  owner(id) = id mod G, local_row = id div G.  No reference counterpart: the
+ * reference is single-device (torchrec/task/Task.py:187-190).
+ *   ids      [F, B] int64 one-hot lookups of this rank's batch (id < 0 = no lookup)
+ *   send_ids [G, F, C] int64: local rows for each (owner, field), in batch order, unused slots -1
+ *   ret_pos  [F, B] int32: (owner*F + f)*C + slot of each lookup, -1 if its list overflowed
+ *   overflow int32 word or NULL: max list length seen when some list exceeded C (lookups dropped)
+ * workspace: ptrec_a2a_pack_workspace_bytes(B, F, G).
+ */
+size_t ptrec_a2a_pack_workspace_bytes(int64_t B, int32_t F, int32_t G);
+int ptrec_a2a_pack_by_owner(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C,
+                            int64_t* send_ids, int32_t* ret_pos, int32_t* overflow, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* dst[ret_pos[f,b], :] = scale * src[b, f, :]  (gradient rows into the all-to-all send layout;
+ * src [B, F*D] with row stride src_row_stride, dst [G*F*C, D]) */
+int ptrec_a2a_scatter_rows(const float* src, int64_t src_row_stride, const int32_t* ret_pos, int64_t B,
+                           int32_t F, int32_t D, float scale, float* dst, void* stream);
 
 #ifdef __cplusplus
 }

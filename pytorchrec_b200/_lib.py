@@ -20,6 +20,7 @@ F32, BF16 = 0, 1
 POOL_SUM, POOL_MEAN, POOL_SQRTN = 0, 1, 2
 MASK_NONE, MASK_PAD, MASK_PAD_KEEP_FIRST, MASK_LENS = 0, 1, 2, 3
 OPT_SGD, OPT_ADAGRAD, OPT_ROWWISE_ADAGRAD, OPT_LAZY_ADAM = 0, 1, 2, 3
+FEAT_NEG_IS_PAD = 1
 
 POOLING_NAMES = {"sum": POOL_SUM, "mean": POOL_MEAN, "sqrtn": POOL_SQRTN}
 MASK_NAMES = {"none": MASK_NONE, "pad": MASK_PAD, "pad_keep_first": MASK_PAD_KEEP_FIRST, "lens": MASK_LENS}
@@ -32,7 +33,7 @@ class FeatureDesc(Structure):
         ("pooling", c_int32),
         ("mask_mode", c_int32),
         ("lens_col", c_int32),
-        ("reserved", c_int32),
+        ("flags", c_int32),
         ("id_base", c_int64),
         ("out_col", c_int64),
     ]
@@ -85,6 +86,11 @@ PROTOTYPES = {
     "ptrec_embedding_bwd_segment_sum": (c_int, [c_int32, c_int32, _FD, _FD, c_int32, c_int64, c_void_p,
                                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                                 c_void_p, c_void_p, c_void_p]),
+    "ptrec_a2a_pack_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "ptrec_a2a_pack_by_owner": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_size_t, c_void_p]),
+    "ptrec_a2a_scatter_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p,
+                                       c_void_p]),
     "ptrec_fm2_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "ptrec_fm2_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
                               c_void_p, c_int64, c_void_p]),

@@ -1,0 +1,184 @@
+// C1: pack / unpack kernels either side of the row-wise-sharding all-to-all.
+//
+// Tables are sharded row-wise: owner(id) = id mod G, local_row = id div G.  Every rank sends, for each
+// (destination, field), a FIXED-capacity list of local rows (capacity C >= expected B/G plus slack, unused
+// slots = -1) so that the collective has equal splits and needs no host synchronisation.  The same slot
+// numbering routes embedding rows back and row gradients forward:
+//     ret_pos[f, b] = (owner * F + f) * C + slot      (or -1 if the list overflowed; flagged)
+// Slots are assigned in batch order (stable), which keeps the owner's sort / segment sums bit-reproducible.
+// Bound: these move 8-16 B per lookup; they are launch-latency bound at the configs' sizes.
+#include "common.cuh"
+
+namespace ptrec {
+
+constexpr int kPackThreads = 256;
+constexpr int kPackItems = 8;
+constexpr int kPackTile = kPackThreads * kPackItems;  // 2048 lookups per CTA
+constexpr int kMaxRanks = 64;
+
+// counts[f][tile][dest]
+__global__ void __launch_bounds__(kPackThreads)
+pack_count_kernel(const int64_t* __restrict__ ids, int64_t B, int G, int tiles, int* __restrict__ counts) {
+  __shared__ int s_cnt[kMaxRanks];
+  const int f = blockIdx.y, tile = blockIdx.x;
+  if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t beg = (int64_t)tile * kPackTile, end = min(B, beg + kPackTile);
+  for (int64_t b = beg + threadIdx.x; b < end; b += kPackThreads) {
+    const int64_t id = ids[(int64_t)f * B + b];
+    if (id >= 0) atomicAdd(&s_cnt[(int)(id % G)], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < G) counts[((int64_t)f * tiles + tile) * G + threadIdx.x] = s_cnt[threadIdx.x];
+}
+
+// exclusive scan over tiles for each (f, dest); one CTA per field, one thread per destination
+__global__ void pack_scan_kernel(int* __restrict__ counts, int G, int tiles, int C, int32_t* __restrict__ overflow) {
+  const int f = blockIdx.x, d = threadIdx.x;
+  if (d >= G) return;
+  int run = 0;
+  for (int t = 0; t < tiles; ++t) {
+    int* p = counts + ((int64_t)f * tiles + t) * G + d;
+    const int c = *p;
+    *p = run;
+    run += c;
+  }
+  if (run > C && overflow != nullptr) atomicMax(overflow, run);
+}
+
+__global__ void __launch_bounds__(kPackThreads)
+pack_scatter_kernel(const int64_t* __restrict__ ids, int64_t B, int F, int G, int tiles, int C,
+                    const int* __restrict__ bases, int64_t* __restrict__ send_ids, int32_t* __restrict__ ret_pos) {
+  constexpr int NW = kPackThreads / 32;
+  __shared__ int s_cnt[NW][kMaxRanks];
+  __shared__ int s_base[kMaxRanks];
+  const int f = blockIdx.y, tile = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < NW * kMaxRanks; i += kPackThreads) (&s_cnt[0][0])[i] = 0;
+  if (threadIdx.x < G) s_base[threadIdx.x] = bases[((int64_t)f * tiles + tile) * G + threadIdx.x];
+  __syncthreads();
+  const int64_t beg = (int64_t)tile * kPackTile, end = min(B, beg + kPackTile);
+  int64_t id[kPackItems];
+  int rank[kPackItems], dest[kPackItems];
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < kPackItems; ++i) {
+    const int64_t b = beg + warp * (32 * kPackItems) + i * 32 + lane;
+    const bool in = b < end;
+    id[i] = in ? ids[(int64_t)f * B + b] : -1;
+    const bool ok = id[i] >= 0;
+    dest[i] = ok ? (int)(id[i] % G) : kMaxRanks;  // kMaxRanks = "nothing to send"
+    const unsigned m = __match_any_sync(0xffffffffu, dest[i]);
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (ok) base = s_cnt[warp][dest[i]];
+    __syncwarp();
+    if (ok && lane == leader) s_cnt[warp][dest[i]] = base + __popc(m);
+    __syncwarp();
+    rank[i] = base + __popc(m & lt);
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    int run = s_base[threadIdx.x];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const int c = s_cnt[w][threadIdx.x];
+      s_cnt[w][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kPackItems; ++i) {
+    const int64_t b = beg + warp * (32 * kPackItems) + i * 32 + lane;
+    if (b < end) {
+      int32_t pos = -1;
+      if (id[i] >= 0) {
+        const int slot = s_cnt[warp][dest[i]] + rank[i];
+        if (slot < C) {
+          pos = (int32_t)(((int64_t)dest[i] * F + f) * C + slot);
+          send_ids[pos] = id[i] / G;
+        }
+      }
+      ret_pos[(int64_t)f * B + b] = pos;
+    }
+  }
+}
+
+// dst[pos[f,b], :] = scale * src[b, f, :]   (one sub-warp per row)
+template <int VEC, int LPR>
+__global__ void __launch_bounds__(256)
+scatter_rows_kernel(const float* __restrict__ src, int64_t src_row_stride, const int32_t* __restrict__ pos,
+                    int64_t B, int F, int D, float scale, float* __restrict__ dst) {
+  const int64_t g = ((int64_t)blockIdx.x * 256 + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;
+  if (g >= B * F || lane * VEC >= D) return;
+  const int64_t b = g / F;
+  const int f = (int)(g - b * F);
+  const int32_t p = pos[(int64_t)f * B + b];
+  if (p < 0) return;
+  RowVec<VEC> r = load_row_stream<VEC>(src + b * src_row_stride + (int64_t)f * D + lane * VEC);
+  r.scale(scale);
+  store_row<VEC>(dst + (int64_t)p * D + lane * VEC, r);
+}
+
+}  // namespace ptrec
+
+using namespace ptrec;
+
+extern "C" size_t ptrec_a2a_pack_workspace_bytes(int64_t B, int32_t F, int32_t G) {
+  const int64_t tiles = ceil_div(B, kPackTile);
+  return align_up((size_t)(F * tiles * G) * sizeof(int) + 16, 256);
+}
+
+extern "C" int ptrec_a2a_pack_by_owner(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C,
+                                       int64_t* send_ids, int32_t* ret_pos, int32_t* overflow, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  PTREC_CHECK_ARG(ids && send_ids && ret_pos && workspace, PTREC_EINVAL, "a2a_pack: null pointer");
+  PTREC_CHECK_ARG(B >= 0 && F >= 1 && F <= 65535 && G >= 1 && G <= kMaxRanks && C >= 1, PTREC_EINVAL,
+                  "a2a_pack: bad sizes B=%lld F=%d G=%d C=%d", (long long)B, F, G, C);
+  PTREC_CHECK_ARG((int64_t)G * F * C < (int64_t)0x7fffffff, PTREC_EUNSUPPORTED, "a2a_pack: G*F*C must be < 2^31");
+  PTREC_CHECK_ARG(workspace_bytes >= ptrec_a2a_pack_workspace_bytes(B, F, G), PTREC_EWORKSPACE, "a2a_pack: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  PTREC_CUDA(cudaMemsetAsync(send_ids, 0xFF, (size_t)G * F * C * sizeof(int64_t), st));  // -1 = empty slot
+  if (B == 0) return PTREC_OK;
+  const int tiles = (int)ceil_div(B, kPackTile);
+  int* counts = reinterpret_cast<int*>(workspace);
+  dim3 grid(tiles, F);
+  pack_count_kernel<<<grid, kPackThreads, 0, st>>>(ids, B, G, tiles, counts);
+  PTREC_LAUNCH_CHECK("pack_count_kernel");
+  pack_scan_kernel<<<F, kMaxRanks, 0, st>>>(counts, G, tiles, C, overflow);
+  PTREC_LAUNCH_CHECK("pack_scan_kernel");
+  pack_scatter_kernel<<<grid, kPackThreads, 0, st>>>(ids, B, F, G, tiles, C, counts, send_ids, ret_pos);
+  PTREC_LAUNCH_CHECK("pack_scatter_kernel");
+  return PTREC_OK;
+}
+
+extern "C" int ptrec_a2a_scatter_rows(const float* src, int64_t src_row_stride, const int32_t* ret_pos, int64_t B,
+                                      int32_t F, int32_t D, float scale, float* dst, void* stream) {
+  PTREC_CHECK_ARG(src && ret_pos && dst, PTREC_EINVAL, "a2a_scatter_rows: null pointer");
+  const bool d_ok = D == 1 || D == 2 || (D >= 4 && D <= 128 && D % 4 == 0);
+  PTREC_CHECK_ARG(d_ok, PTREC_EUNSUPPORTED, "a2a_scatter_rows: D=%d unsupported", D);
+  const int vec = D >= 4 ? 4 : D;
+  PTREC_CHECK_ARG(((uintptr_t)src % (vec * 4)) == 0 && ((uintptr_t)dst % (vec * 4)) == 0 && src_row_stride % vec == 0,
+                  PTREC_EALIGN, "a2a_scatter_rows: misaligned");
+  if (B == 0) return PTREC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+#define PTREC_SC(V, P)                                                                                   \
+  {                                                                                                      \
+    const unsigned grid = (unsigned)ceil_div(B * F * P, 256);                                            \
+    scatter_rows_kernel<V, P><<<grid, 256, 0, st>>>(src, src_row_stride, ret_pos, B, F, D, scale, dst);  \
+    PTREC_LAUNCH_CHECK("scatter_rows_kernel");                                                           \
+    return PTREC_OK;                                                                                     \
+  }
+  if (D == 1) PTREC_SC(1, 1)
+  if (D == 2) PTREC_SC(2, 1)
+  const int lanes = D / 4;
+  if (lanes <= 1) PTREC_SC(4, 1)
+  if (lanes <= 2) PTREC_SC(4, 2)
+  if (lanes <= 4) PTREC_SC(4, 4)
+  if (lanes <= 8) PTREC_SC(4, 8)
+  if (lanes <= 16) PTREC_SC(4, 16)
+  PTREC_SC(4, 32)
+#undef PTREC_SC
+}

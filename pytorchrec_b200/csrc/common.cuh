@@ -43,7 +43,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-constexpr int kMaxFeatures = 128;  // descriptors are cached in shared memory
+constexpr int kMaxFeatures = 256;  // descriptors are cached in shared memory
 constexpr int kMaxTables = 128;
 constexpr uint32_t kMaskedKey = 0xFFFFFFFFu;
 

@@ -40,6 +40,7 @@ gather_onehot_kernel(const void* const* __restrict__ table_ptrs, const int64_t* 
   const float** s_tab = reinterpret_cast<const float**>(s_ids + (size_t)nsel * kOneHotTileB);
   int64_t* s_rows = reinterpret_cast<int64_t*>(s_tab + nsel);
   int64_t* s_col = s_rows + nsel;
+  int64_t* s_flag = s_col + nsel;
   __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x;
@@ -58,6 +59,7 @@ gather_onehot_kernel(const void* const* __restrict__ table_ptrs, const int64_t* 
     s_tab[s] = reinterpret_cast<const float*>(table_ptrs[fd.table]);
     s_rows[s] = table_rows[fd.table];
     s_col[s] = fd.out_col;
+    s_flag[s] = fd.flags;
     const int64_t* src = ids + fd.id_base * B + b0;
     if (use_bulk) {
       bulk_g2s(s_ids + (size_t)s * kOneHotTileB, src, (uint32_t)nb * 8u, &s_bar);
@@ -93,7 +95,7 @@ gather_onehot_kernel(const void* const* __restrict__ table_ptrs, const int64_t* 
         dst[u] = out + (b0 + bl) * out_row_stride + s_col[s] + lane * VEC;
         if ((uint64_t)id < (uint64_t)s_rows[s]) {
           if (lane_on) r[u] = load_row_stream<VEC>(s_tab[s] + id * (int64_t)D + lane * VEC);
-        } else if (err_flag != nullptr && lane == 0) {
+        } else if (err_flag != nullptr && lane == 0 && !(id < 0 && (s_flag[s] & PTREC_FEAT_NEG_IS_PAD))) {
           *err_flag = 1;
         }
       }
@@ -182,6 +184,7 @@ gather_bag_kernel(const void* const* __restrict__ table_ptrs, const int64_t* __r
           case PTREC_MASK_LENS: valid = l < len; break;
           default: valid = true;
         }
+        if (id < 0 && (fd.flags & PTREC_FEAT_NEG_IS_PAD)) valid = false;
         if (valid) {
           ++count;
           if ((uint64_t)id < (uint64_t)rows) {
@@ -220,7 +223,7 @@ static int launch_gather(const void* const* table_ptrs, const int64_t* table_row
   const int ids_al = aligned16(ids) ? 1 : 0;
   if (onehot.n > 0) {
     const int use_bulk = (ids_al && (B % 2 == 0)) ? 1 : 0;
-    const size_t smem = (size_t)onehot.n * (kOneHotTileB * 8 + 8 + 8 + 8);
+    const size_t smem = (size_t)onehot.n * (kOneHotTileB * 8 + 8 + 8 + 8 + 8);
     const unsigned grid = (unsigned)ceil_div(B, kOneHotTileB);
     gather_onehot_kernel<VEC, LPR><<<grid, kOneHotThreads, smem, st>>>(
         table_ptrs, table_rows, D, feats, onehot, ids, B, out, out_row_stride, err_flag, use_bulk);

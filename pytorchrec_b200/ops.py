@@ -44,8 +44,8 @@ class FeatureLayout:
         self.dim = int(dim)
         self.n_tables = int(n_tables)
         self.n_features = len(specs)
-        if self.n_features < 1 or self.n_features > 128 or self.n_tables > 128:
-            raise ValueError("between 1 and 128 features / tables per embedding group")
+        if self.n_features < 1 or self.n_features > 256 or self.n_tables > 128:
+            raise ValueError("1..256 features and 1..128 tables per embedding group")
         arr = (FeatureDesc * self.n_features)()
         id_base = 0
         prev_table = -1
@@ -58,13 +58,13 @@ class FeatureLayout:
             arr[f].pooling = _lib.POOLING_NAMES[s.get("pooling", "sum")]
             arr[f].mask_mode = _lib.MASK_NAMES[s.get("mask", "none")]
             arr[f].lens_col = int(s.get("lens_col", -1))
-            arr[f].reserved = 0
+            arr[f].flags = _lib.FEAT_NEG_IS_PAD if s.get("neg_is_pad") else 0
             arr[f].id_base = id_base
-            arr[f].out_col = f * self.dim
+            arr[f].out_col = int(s.get("out_col", f * self.dim))
             id_base += arr[f].bag_len
         self.host = arr
         self.total_bag_len = id_base
-        self.out_width = self.n_features * self.dim
+        self.out_width = int(max(arr[f].out_col for f in range(self.n_features))) + self.dim
         self._dev: Dict[torch.device, torch.Tensor] = {}
 
     def device_array(self, device: torch.device) -> torch.Tensor:
@@ -151,7 +151,8 @@ def make_ptr_array(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
 
 def gather_pool_fwd(tables: TableSet, layout: FeatureLayout, ids: torch.Tensor,
                     lens: Optional[torch.Tensor], batch: int, out: Optional[torch.Tensor] = None,
-                    want_scale: bool = False, err_flag: Optional[torch.Tensor] = None):
+                    want_scale: bool = False, err_flag: Optional[torch.Tensor] = None,
+                    out_row_stride: Optional[int] = None):
     lib = _lib.load()
     _require_cuda(ids, lens, out)
     dev = ids.device
@@ -159,17 +160,18 @@ def gather_pool_fwd(tables: TableSet, layout: FeatureLayout, ids: torch.Tensor,
     if out is None:
         out = torch.empty(batch, layout.out_width, dtype=torch.float32, device=dev)
     bag_scale = torch.empty(layout.n_features, batch, dtype=torch.float32, device=dev) if want_scale else None
-    _lib.check(_gather_call(lib, tables, layout, ids, lens, batch, out, bag_scale, err_flag, dev),
+    _lib.check(_gather_call(lib, tables, layout, ids, lens, batch, out, bag_scale, err_flag, dev,
+                            out.stride(0) if out_row_stride is None else out_row_stride),
                "ptrec_embedding_gather_pool_fwd")
     return out, bag_scale
 
 
-def _gather_call(lib, tables, layout, ids, lens, batch, out, bag_scale, err_flag, dev):
+def _gather_call(lib, tables, layout, ids, lens, batch, out, bag_scale, err_flag, dev, row_stride):
     feats_dev = layout.device_array(dev)
     return lib.ptrec_embedding_gather_pool_fwd(
         _ptr(tables.ptrs), _ptr(tables.rows), layout.n_tables, layout.dim, _lib.F32,
         ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)), layout.host,
-        layout.n_features, _ptr(ids), _ptr(lens), batch, _ptr(out), out.stride(0), _ptr(bag_scale),
+        layout.n_features, _ptr(ids), _ptr(lens), batch, _ptr(out), row_stride, _ptr(bag_scale),
         _ptr(err_flag), _stream(dev))
 
 
@@ -212,11 +214,14 @@ _BWD_FN = {
 
 def bwd_fused(tables: TableSet, state1_ptrs: Optional[torch.Tensor], state2_ptrs: Optional[torch.Tensor],
               layout: FeatureLayout, batch: int, srt: SortResult, grad_out: torch.Tensor,
-              bag_scale: Optional[torch.Tensor], opt: OptimArgs) -> None:
+              bag_scale: Optional[torch.Tensor], opt: OptimArgs, grad_row_stride: Optional[int] = None) -> None:
     lib = _lib.load()
     _require_cuda(grad_out, bag_scale)
     dev = grad_out.device
-    assert grad_out.dtype == torch.float32 and grad_out.dim() == 2 and grad_out.stride(1) == 1
+    assert grad_out.dtype == torch.float32 and grad_out.stride(-1) == 1
+    if grad_row_stride is None:
+        assert grad_out.dim() == 2
+        grad_row_stride = grad_out.stride(0)
     nbytes = lib.ptrec_embedding_bwd_workspace_bytes(srt.N, layout.dim)
     ws = _workspace("bwd_fused", nbytes, dev)
     feats_dev = layout.device_array(dev)
@@ -225,7 +230,7 @@ def bwd_fused(tables: TableSet, state1_ptrs: Optional[torch.Tensor], state2_ptrs
                   _lib.F32, ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)),
                   layout.host, layout.n_features, batch, _ptr(srt.sorted_keys), _ptr(srt.perm),
                   _ptr(srt.seg_start), _ptr(srt.seg_table), _ptr(srt.n_seg), _ptr(grad_out),
-                  grad_out.stride(0), _ptr(bag_scale), ctypes.byref(opt), _ptr(ws), ws.numel(),
+                  grad_row_stride, _ptr(bag_scale), ctypes.byref(opt), _ptr(ws), ws.numel(),
                   _stream(dev)), _BWD_FN[opt.kind])
 
 
@@ -291,3 +296,29 @@ def fm2(v: torch.Tensor) -> torch.Tensor:
     if not (v.stride(2) == 1 and v.stride(1) == v.shape[2]):
         v = v.contiguous()
     return _FM2.apply(v)
+
+
+# ----------------------------------------------------------------------------------------------
+# C1 all-to-all pack / unpack
+# ----------------------------------------------------------------------------------------------
+def a2a_pack_by_owner(ids: torch.Tensor, F: int, B: int, G: int, C: int, overflow: torch.Tensor):
+    """ids [F, B] int64 -> (send_ids [G, F, C] int64 with -1 padding, ret_pos [F, B] int32)."""
+    lib = _lib.load()
+    _require_cuda(ids, overflow)
+    dev = ids.device
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.numel() == F * B
+    send_ids = torch.empty(G, F, C, dtype=torch.int64, device=dev)
+    ret_pos = torch.empty(F, B, dtype=torch.int32, device=dev)
+    ws = _workspace("a2a_pack", lib.ptrec_a2a_pack_workspace_bytes(B, F, G), dev)
+    _lib.check(lib.ptrec_a2a_pack_by_owner(_ptr(ids), B, F, G, C, _ptr(send_ids), _ptr(ret_pos), _ptr(overflow),
+                                           _ptr(ws), ws.numel(), _stream(dev)), "ptrec_a2a_pack_by_owner")
+    return send_ids, ret_pos
+
+
+def a2a_scatter_rows(src: torch.Tensor, ret_pos: torch.Tensor, B: int, F: int, D: int, scale: float,
+                     dst: torch.Tensor) -> None:
+    lib = _lib.load()
+    _require_cuda(src, ret_pos, dst)
+    assert src.dtype == torch.float32 and src.stride(-1) == 1 and dst.is_contiguous()
+    _lib.check(lib.ptrec_a2a_scatter_rows(_ptr(src), src.stride(0), _ptr(ret_pos), B, F, D, float(scale), _ptr(dst),
+                                          _stream(src.device)), "ptrec_a2a_scatter_rows")

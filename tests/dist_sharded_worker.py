@@ -1,0 +1,81 @@
+"""torchrun worker (NCCL, >= 2 GPUs): ShardedDeepFM vs the unsharded fused DeepFM on the concatenated batch.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/dist_sharded_worker.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_sharding  # noqa: E402
+from pytorchrec_b200 import ops  # noqa: E402
+from pytorchrec_b200.distributed import ShardedDeepFM  # noqa: E402
+from pytorchrec_b200.distributed.sharded import list_capacity  # noqa: E402
+from pytorchrec_b200.feature_column import CategoricalColumnWithIdentity as Col, NumericColumn  # noqa: E402
+from pytorchrec_b200.metric import LogLoss  # noqa: E402
+from pytorchrec_b200.model import DeepFM  # noqa: E402
+from pytorchrec_b200.optim import SparseAdagrad  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    F, nd, D, B = 6, 3, 16, 256
+    rows = [103, 57, 1000, 64, 31, 5000]
+    scols = [Col(rows[f], f"C{f}") for f in range(F)]
+    dcols = [NumericColumn(f"I{j}", 0.0, 1.0, 0.5, 0.25) for j in range(nd)]
+    lab = Col(2, "label")
+
+    # the pack kernel against its CPU restatement (bit-exact)
+    ids = torch.stack([torch.randint(0, rows[f], (B,), generator=torch.Generator().manual_seed(f + 10 * rank)) for f in range(F)])
+    C = list_capacity(B, world)
+    ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+    send_ids, ret_pos = ops.a2a_pack_by_owner(ids.to(dev), F, B, world, C, ovf)
+    rs, rp, _ = ref_sharding.pack_by_owner_ref(ids, world, C)
+    assert torch.equal(send_ids.cpu(), rs) and torch.equal(ret_pos.cpu(), rp) and ovf.item() == 0
+
+    full = DeepFM(scols, dcols, lab, D, [32, 16], random_seed=3)
+    shard = ShardedDeepFM(scols, dcols, lab, D, [32, 16], random_seed=3)
+    sd = full.state_dict()
+    with torch.no_grad():
+        for name in ("embeddings", "first_order"):
+            for f in range(F):
+                getattr(shard, name)[f].weight.copy_(sd[f"{name}.{f}.weight"][rank::world])
+        for k, v in shard.state_dict().items():
+            if not k.startswith(("embeddings", "first_order")):
+                assert torch.equal(v, sd[k]), k
+    full.compile(SparseAdagrad(full.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)
+    shard.compile(SparseAdagrad(shard.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)
+
+    for step in range(4):
+        rng = np.random.default_rng(1000 + step)  # same global batch on every rank
+        gb = {f"C{f}": torch.from_numpy((rng.zipf(1.3, size=world * B) % rows[f]).astype(np.int64)) for f in range(F)}
+        gb.update({f"I{j}": torch.from_numpy(rng.random(world * B).astype(np.float32)) for j in range(nd)})
+        gb["label"] = torch.from_numpy(rng.integers(0, 2, size=world * B))
+        lb = {k: v[rank * B:(rank + 1) * B] for k, v in gb.items()}
+        pf, _ = full.test_step(gb)
+        ps, _ = shard.test_step(lb)
+        np.testing.assert_allclose(ps.detach().cpu().numpy(), pf.detach().cpu().numpy()[rank * B:(rank + 1) * B],
+                                   rtol=1e-5, atol=2e-5)
+        full.train_step(gb)
+        shard.train_step(lb)
+    shard.embeddings.check_errors()
+    fsd, ssd = full.state_dict(), shard.state_dict()
+    for k, v in ssd.items():
+        ref = fsd[k][rank::world] if k.startswith(("embeddings", "first_order")) else fsd[k]
+        a, b = v.cpu().numpy(), ref.cpu().numpy()
+        tight = np.abs(a - b) <= 1e-5 * np.abs(b) + 1.5e-5
+        assert tight.mean() >= 0.995, (k, tight.mean())
+        np.testing.assert_allclose(a, b, rtol=0, atol=3e-4, err_msg=k)
+    dist.barrier()
+    if rank == 0:
+        print("DIST_SHARDED_OK world=%d" % world, flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
