@@ -44,7 +44,7 @@ def parse():
 def config_dict(a, world):
     return {"workload": "cfg2 DeepFM Criteo-shaped synthetic: 26 tables x %d rows x dim %d (+26 first-order dim 1), "
                         "13 dense, DNN 400-400-400, batch %d per GPU, fp32, sparse Adagrad" % (a.rows, a.dim, a.batch),
-            "global_batch": a.batch * world, "id_dist": a.id_dist, "cuda_graph": (not a.no_graph) and world == 1,
+            "global_batch": a.batch * world, "id_dist": a.id_dist, "cuda_graph": not a.no_graph,
             "parallelism": "single GPU" if world == 1 else f"row-wise sharded tables x{world} (all-to-all) + dense allreduce",
             "l2": "tables %.2f GB >> 126 MB L2; a different random id batch every step" %
                   (26 * a.rows * (a.dim + 1) * 4 / 1e9)}
@@ -172,7 +172,7 @@ def run_b200(a):
         model = ShardedDeepFM(sparse, dense, label, a.dim, CFG["layers"], random_seed=2020, table_device=dev)
     opt = SparseAdagrad(params=model.get_parameters(), lr=0.01)
     model.compile(opt, torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)
-    if not a.no_graph and world == 1:
+    if not a.no_graph:
         model.enable_cuda_graph(True)
 
     n_pool = 8
@@ -245,8 +245,14 @@ def run_b200(a):
                                         "sample": f"failed: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # NCCL kernels captured in the step graph keep the communicator busy at teardown: drop the graphs,
+        # synchronise, and leave without the (hanging) communicator destructor.
         dist.barrier()
-        dist.destroy_process_group()
+        model.enable_cuda_graph(False)
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def kernel_roofline(a, model, resident, dev):
@@ -261,11 +267,12 @@ def kernel_roofline(a, model, resident, dev):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     emb = model.embeddings
-    tables = [t.weight.data for t in emb.tables]
+    tables = [t.weight.data for t in emb]
     F, D, B = len(tables), a.dim, a.batch
+    R = min(t.shape[0] for t in tables)
     lay = ops.FeatureLayout([dict(table=f, bag_len=1) for f in range(F)], D, F)
     ts = ops.TableSet().refresh(tables)
-    id_batches = [torch.cat([b[c.feature_name].reshape(-1) for c in emb.columns]).contiguous() for b in resident]
+    id_batches = [(torch.cat([b[c.feature_name].reshape(-1) for c in emb.columns]) % R).contiguous() for b in resident]
     state = [torch.zeros_like(t) for t in tables]
     p1 = ops.make_ptr_array(state)
     go = torch.randn(B, F * D, device=dev)

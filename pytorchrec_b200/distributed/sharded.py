@@ -62,13 +62,13 @@ class _ShardedLookup(torch.autograd.Function):
         own_ids = recv_ids.permute(1, 0, 2).contiguous().view(-1)              # [F, G_src, C]
         layout = mod.owner_layout(C)
         tables = mod.egroup.table_set.refresh([w.detach() for w in weights])
-        rows_out = torch.empty(G * F * C, D, dtype=torch.float32, device=dev)  # [G_src, F, C, D]
+        bufs = mod.buffers(C, dev)  # persistent: fixed addresses (pointer arrays built once, graph-capturable)
+        rows_out, recv_rows = bufs["rows_out"], bufs["recv_rows"]             # [G_src, F, C, D] / [G_owner, F, C, D]
         ops.gather_pool_fwd(tables, layout, own_ids, None, C, out=rows_out, err_flag=mod.egroup.err_flag(dev),
                             out_row_stride=D)
-        recv_rows = torch.empty_like(rows_out)
-        dist.all_to_all_single(recv_rows, rows_out, group=mod.group)           # [G_owner, F, C, D]
+        dist.all_to_all_single(recv_rows, rows_out, group=mod.group)
         # local gather by slot: out[b, f] = recv_rows[ret_pos[f, b]]
-        slot_tables = mod.slot_tables.refresh([recv_rows])
+        slot_tables = bufs["slot_tables"]
         out, _ = ops.gather_pool_fwd(slot_tables, mod.slot_layout(), ret_pos.view(-1).long(), None, B)
         ctx.mod, ctx.C, ctx.shape = mod, C, (F, B)
         ctx.save_for_backward(own_ids, ret_pos)
@@ -84,9 +84,9 @@ class _ShardedLookup(torch.autograd.Function):
         if not grad_out.is_contiguous():
             grad_out = grad_out.contiguous()
         # slots that carry no lookup are -1 on the owner (masked in the sort): no need to clear them
-        send_g = torch.empty(G * F * C, D, dtype=torch.float32, device=grad_out.device)
+        bufs = mod.buffers(C, grad_out.device)
+        send_g, recv_g = bufs["send_g"], bufs["recv_g"]
         ops.a2a_scatter_rows(grad_out, ret_pos, B, F, D, mod.grad_scale, send_g)
-        recv_g = torch.empty_like(send_g)
         dist.all_to_all_single(recv_g, send_g, group=mod.group)                # [G_src, F, C, D]
         layout = mod.owner_layout(C)
         tables = mod.egroup.table_set.refresh([t.weight.data for t in mod.egroup.tables])
@@ -127,10 +127,22 @@ class RowWiseShardedEmbedding(nn.ModuleList):
         self._owner_layouts: Dict[int, ops.FeatureLayout] = {}
         self._slot_layout: Optional[ops.FeatureLayout] = None
         self._overflow: Dict[torch.device, Tensor] = {}
+        self._bufs: Dict[tuple, dict] = {}
 
     @property
     def weight(self) -> Tensor:  # see MultiTableEmbedding.weight
         return torch.empty(0)
+
+    def buffers(self, C: int, device) -> dict:
+        key = (C, device)
+        b = self._bufs.get(key)
+        if b is None:
+            n = self.world * len(self.columns) * C
+            mk = lambda: torch.empty(n, self.emb_size, dtype=torch.float32, device=device)  # noqa: E731
+            b = {"rows_out": mk(), "recv_rows": mk(), "send_g": mk(), "recv_g": mk()}
+            b["slot_tables"] = ops.TableSet().refresh([b["recv_rows"]])
+            self._bufs[key] = b
+        return b
 
     def overflow_flag(self, device) -> Tensor:
         t = self._overflow.get(device)
@@ -165,6 +177,13 @@ class RowWiseShardedEmbedding(nn.ModuleList):
             t._tag()
         return _ShardedLookup.apply(self, ids, *[t.weight for t in self])
 
+    @property
+    def tables(self) -> List[EmbeddingTable]:
+        return [m for m in self]
+
+    def check_index_errors(self) -> None:
+        self.check_errors()
+
     def check_errors(self) -> None:
         """Synchronising check of the overflow / out-of-range flags."""
         for t in self._overflow.values():
@@ -179,24 +198,12 @@ class RowWiseShardedEmbedding(nn.ModuleList):
 class ShardedDeepFM(DeepFM):
     """DeepFM with both table groups row-wise sharded and the dense tower data-parallel."""
 
-    def _init_weights(self):
-        super()._init_weights()
-        dev = self.table_device
-        self.embeddings = RowWiseShardedEmbedding(self.sparse_columns, self.emb_size, device=dev)
-        self.first_order = RowWiseShardedEmbedding(self.sparse_columns, 1, device=dev)
+    def _make_embedding(self, emb_size: int):
+        return RowWiseShardedEmbedding(self.sparse_columns, emb_size, device=self.table_device)
 
     def _dense_params(self) -> List[Tensor]:
         table_ids = {id(t.weight) for m in (self.embeddings, self.first_order) for t in m}
         return [p for p in self.parameters() if id(p) not in table_ids]
 
-    def _eager_train_step(self, data: Dict):
-        from ..utils import tensor_to_device
-        self.train()
-        data = tensor_to_device(data, self.compiled_device)
-        prediction, target = self(data)
-        loss = self.compiled_loss(prediction, target)
-        self.compiled_optimizers.zero_grad()
-        loss.backward()
+    def _before_optimizer_step(self) -> None:
         allreduce_dense_grads(self._dense_params())
-        self.compiled_optimizers.step(closure=None)
-        return {"loss": loss}

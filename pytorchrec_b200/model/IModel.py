@@ -83,11 +83,7 @@ class _GraphedTrainStep:
             l0 = _lib.load().ptrec_launch_count()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                prediction, target = m(dict(e["static"]))  # forward may add private entries to its dict
-                loss = m.compiled_loss(prediction, target)
-                opt.zero_grad(set_to_none=True)
-                loss.backward()
-                opt.step()
+                loss = m._train_step_body(dict(e["static"]))  # forward may add private entries to its dict
             opt._step_count_fused -= 1  # capture records the step, it does not execute it
             e["graph"], e["loss"] = g, loss
             e["launches"] = int(_lib.load().ptrec_launch_count() - l0)  # recorded into the graph, not yet run
@@ -182,7 +178,9 @@ class IModel(Module, ABC):
         self._is_compiled = True
 
     def enable_cuda_graph(self, enabled: bool = True, warmup: int = 2) -> None:
-        """Replay ``train_step`` as one CUDA graph per batch signature (CUDA devices only)."""
+        """Replay ``train_step`` as one CUDA graph per batch signature (CUDA devices only).  Do not keep
+        outputs of a grad-enabled forward alive across the capturing step: their autograd graph pins the
+        parameters' AccumulateGrad nodes to the default stream, which cannot join a capture."""
         self._graphed = _GraphedTrainStep(self, warmup) if enabled else None
 
     def train_step(self, data: Dict):
@@ -193,12 +191,20 @@ class IModel(Module, ABC):
     def _eager_train_step(self, data: Dict):
         self.train()
         data = tensor_to_device(data, self.compiled_device)
+        return {"loss": self._train_step_body(data)}
+
+    def _train_step_body(self, data: Dict):
+        """forward, loss, zero_grad, backward, [gradient hook], step — IModel.py:120-124."""
         prediction, target = self(data)
         loss = self.compiled_loss(prediction, target)
         self.compiled_optimizers.zero_grad()
         loss.backward()
+        self._before_optimizer_step()
         self.compiled_optimizers.step(closure=None)
-        return {"loss": loss}
+        return loss
+
+    def _before_optimizer_step(self) -> None:
+        """Hook between backward and step (data-parallel models all-reduce dense gradients here)."""
 
     def test_step(self, data):
         self.eval()

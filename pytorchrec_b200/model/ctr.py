@@ -39,9 +39,13 @@ class FM(IModel):
         self.emb_size = emb_size
         super().__init__(**kwargs)
 
+    def _make_embedding(self, emb_size: int):
+        """Table-group factory (overridden by the row-wise sharded variant)."""
+        return MultiTableEmbedding(self.sparse_columns, emb_size, device=self.table_device)
+
     def _init_weights(self):
-        self.embeddings = MultiTableEmbedding(self.sparse_columns, self.emb_size, device=self.table_device)
-        self.first_order = MultiTableEmbedding(self.sparse_columns, 1, device=self.table_device)
+        self.embeddings = self._make_embedding(self.emb_size)
+        self.first_order = self._make_embedding(1)
         if self.dense_columns:
             self.dense_linear = Linear(len(self.dense_columns), 1, bias=False)
         self.global_bias = Parameter(torch.tensor(0.0))
