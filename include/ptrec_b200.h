@@ -227,6 +227,24 @@ int ptrec_fm2_bwd(const float* v, int64_t v_row_stride, const float* gy, const f
                   int64_t grad_v_row_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K5 DCN-v2 cross layer on tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM).
+ * Not in the reference; the layer is  x_{l+1} = x0 (.) (x_l W^T + b) + x_l  with W stored
+ * [d_out, d_in] row-major like nn.Linear.  All activations are bf16 [B, ld] row-major, d % 8 == 0 and
+ * ld % 8 == 0 (pad the concatenated input once); pointers 16-byte aligned.
+ *   fwd    out = x0 (.) u + x_l,  u = x_l W^T + bias;  u_out (may be NULL) receives u for the backward
+ *   dgrad  g_x = g_u W + g_out with g_u = g_out (.) x0 supplied by the caller; weight_t = W^T [d_in, d_out];
+ *          g_u_prev (may be NULL) receives g_x (.) x0, i.e. the g_u of the layer below
+ *   wgrad  grad_w [d_out, d_in] fp32 = g_u^T x_l   (workspace: ptrec_dcn_cross_wgrad_workspace_bytes)
+ */
+int ptrec_dcn_cross_fwd(const void* x_l, const void* x0, const void* weight, const float* bias, int64_t B,
+                        int32_t d, int64_t ld, void* out, void* u_out, void* stream);
+int ptrec_dcn_cross_dgrad(const void* g_u, const void* weight_t, const void* g_out, const void* x0, int64_t B,
+                          int32_t d, int64_t ld, void* g_x, void* g_u_prev, void* stream);
+size_t ptrec_dcn_cross_wgrad_workspace_bytes(int64_t B, int32_t d);
+int ptrec_dcn_cross_wgrad(const void* g_u, const void* x_l, int64_t B, int32_t d, int64_t ld, float* grad_w,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * C1 row-wise sharding: pack / unpack either side of the all-to-all (NCCL, issued by the host through
  * torch.distributed).  owner(id) = id mod G, local_row = id div G.  No reference counterpart: the
  * reference is single-device (torchrec/task/Task.py:187-190).

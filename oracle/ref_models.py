@@ -209,3 +209,43 @@ class DeepFMRef(FMRef):
         flat = v.reshape(v.shape[0], -1)
         deep_in = torch.cat([flat, x], dim=1) if x is not None else flat
         return logit + self.deep_out(self.mlp(deep_in)).squeeze(-1), self._target(data)
+
+
+class DCNRef(IModelRef):
+    """DCN-v2, parallel structure (NOT in the reference: parity unpinned).  Cross layer
+    ``x_{l+1} = x0 * (x_l W_l^T + b_l) + x_l`` with ``nn.Linear(d, d)`` per layer, fp32 throughout; head and
+    tower in the reference's idiom (MLP.py:8-23, ``Linear(..., 1, bias=False)`` as NCF.py:51)."""
+
+    def __init__(self, random_seed, sparse_columns, dense_columns, label_column, emb_size, cross_layers, layers, dropout=0.0):
+        self.sparse_columns, self.dense_columns = list(sparse_columns), list(dense_columns or [])
+        self.label_column, self.emb_size = label_column, emb_size
+        self.cross_layers, self.layers, self.dropout = cross_layers, list(layers), dropout
+        super().__init__(random_seed)
+
+    def _init_weights(self):
+        self.embeddings = nn.ModuleList([Embedding(c.category_num, self.emb_size) for c in self.sparse_columns])
+        d = len(self.sparse_columns) * self.emb_size + len(self.dense_columns)
+        self.cross = nn.Module()
+        self.cross.layers = nn.ModuleList([Linear(d, d) for _ in range(self.cross_layers)])
+        self.mlp = MLPRef(d, self.layers, self.dropout)
+        self.out = Linear(d + self.layers[-1], 1, bias=False)
+
+    def forward(self, data):
+        ids = [c.get_feature_data(data) for c in self.sparse_columns]
+        flat = torch.cat([e(i) for e, i in zip(self.embeddings, ids)], dim=1)
+        x0 = flat
+        if self.dense_columns:
+            x0 = torch.cat([flat, torch.stack([c.get_feature_data(data) for c in self.dense_columns], dim=1)], dim=1)
+        x = x0
+        for lin in self.cross.layers:
+            x = x0 * lin(x) + x
+        logit = self.out(torch.cat([x, self.mlp(x0)], dim=1)).squeeze(-1)
+        t = self.label_column.get_feature_data(data)
+        return logit, (t.float() if t is not None else None)
+
+
+def cross_net_ref(x0: Tensor, weights, biases) -> Tensor:
+    x = x0
+    for W, b in zip(weights, biases):
+        x = x0 * (x @ W.t() + b) + x
+    return x

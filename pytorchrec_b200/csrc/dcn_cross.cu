@@ -1,0 +1,374 @@
+// K5: DCN-v2 cross layer on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), bf16 in / fp32 acc.
+//
+//   forward   u = x_l W^T + b ;  out = x0 (.) u + x_l                       (W stored [d_out, d_in] like nn.Linear)
+//   dgrad     g_x = g_u W + g_out ,  g_u = g_out (.) x0 ;  also emits g_x (.) x0 (the next layer's g_u)
+//   wgrad     gW = g_u^T x_l  (K = batch): both operands transposed to K-major by a tiled transpose kernel,
+//             then the same GEMM with an fp32 epilogue.
+// Bound: bf16 tensor pipe.  FLOPs per launch = 2*B*d*d; the epilogue streams 3-4 [B, d] bf16 tiles, so the layer
+// sits near the ridge (AI ~ 300 FLOP/B) — the elementwise work is fused into the GEMM epilogue to stay on it.
+//
+// One CTA computes a 128 x 128 output tile: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// tcgen05.mma issuer (one elected lane), warps 2-5 = epilogue (tcgen05.ld 32x32b -> registers -> fused math ->
+// 16-byte global stores).  Operands are K-major 128B-swizzled tiles of 128 rows x 64 bf16 filled by
+// cp.async.bulk.tensor.2d and described to the MMA by shared-memory matrix descriptors; a 4-stage full/empty
+// mbarrier ring overlaps TMA with MMA; tcgen05.commit releases stages and publishes the accumulator.
+// Every mbarrier wait is bounded (trap instead of hang).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ptrec {
+
+constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 4, kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+constexpr uint32_t kStageBytesA = kBM * kBK * 2, kStageBytesB = kBN * kBK * 2;
+constexpr uint32_t kTmemCols = 128;
+constexpr size_t kGemmSmem = (size_t)kStages * (kStageBytesA + kStageBytesB) + 1024 /*align*/ + 256 /*barriers*/;
+
+enum EpiMode : int { EPI_F32 = 0, EPI_CROSS_FWD = 1, EPI_CROSS_DGRAD = 2 };
+
+struct EpiArgs {
+  int mode;
+  int64_t ld;                  // row pitch (elements) of the [M, N] bf16 operands / outputs below
+  const __nv_bfloat16* p0;     // CROSS_FWD: x0       CROSS_DGRAD: g_out
+  const __nv_bfloat16* p1;     // CROSS_FWD: x_l      CROSS_DGRAD: x0
+  const float* bias;           // CROSS_FWD: bias[N] (may be null)
+  __nv_bfloat16* o0;           // CROSS_FWD: out      CROSS_DGRAD: g_x
+  __nv_bfloat16* o1;           // CROSS_FWD: u (null = skip)   CROSS_DGRAD: g_x (.) x0 (null = skip)
+  float* of32;                 // EPI_F32: fp32 output [M, ldf]
+  int64_t ldf;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// K-major, 128B swizzle: 8-row atoms of 1024 B; LBO unused (1), SBO = 1024 B, descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_sw128_desc(const void* smem_tile) {
+  const uint32_t addr = smem_u32(smem_tile);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* p, float* f) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float* f) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+// ---- the GEMM: C[M, N] = A[M, K] * B[N, K]^T, fused epilogue ---------------------------------------------------
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                    int K, EpiArgs ep) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + (size_t)kStages * kStageBytesA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * (kStageBytesA + kStageBytesB));
+  uint64_t* full = bars;                 // [kStages]
+  uint64_t* empty = bars + kStages;      // [kStages]
+  uint64_t* acc_full = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+  const int num_kb = (K + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(&empty[s], ((kb / kStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], kStageBytesA + kStageBytesB);
+        tma_load_2d(sA + (size_t)s * kStageBytesA, &tmA, kb * kBK, m0, &full[s]);
+        tma_load_2d(sB + (size_t)s * kStageBytesB, &tmB, kb * kBK, n0, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(&full[s], (kb / kStages) & 1);
+        tcgen05_fence_after();
+        const uint64_t adesc = make_sw128_desc(sA + (size_t)s * kStageBytesA);
+        const uint64_t bdesc = make_sw128_desc(sB + (size_t)s * kStageBytesB);
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          // +32 bytes per K=16 slice inside the 128-byte swizzled row (start-address field is in 16-byte units)
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);  // frees the stage once the MMAs that read it retire
+      }
+      umma_commit(acc_full);     // accumulator complete
+    }
+  } else {
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
+    const int q = warp & 3;
+    mbar_wait(acc_full, 0);
+    tcgen05_fence_after();
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < M;
+#pragma unroll 1
+    for (int c = 0; c < kBN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      const int col0 = n0 + c * 32;
+      if (!row_ok || col0 >= N) continue;
+      if (ep.mode == EPI_F32) {
+        float* o = ep.of32 + (int64_t)row * ep.ldf + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (col0 + j < N) {
+            *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                             __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          }
+        }
+      } else {
+        const int64_t off = (int64_t)row * ep.ld + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (col0 + j >= N) break;
+          float a[8], b[8], r0[8], r1[8];
+          load_bf16x8(ep.p0 + off + j, a);
+          load_bf16x8(ep.p1 + off + j, b);
+          if (ep.mode == EPI_CROSS_FWD) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float u = __uint_as_float(v[j + i]) + (ep.bias ? ep.bias[col0 + j + i] : 0.f);
+              r1[i] = u;
+              r0[i] = a[i] * u + b[i];  // x0 * u + x_l
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float gx = __uint_as_float(v[j + i]) + a[i];  // g_u W + g_out
+              r0[i] = gx;
+              r1[i] = gx * b[i];                                  // next layer's g_u = g_x (.) x0
+            }
+          }
+          store_bf16x8(ep.o0 + off + j, r0);
+          if (ep.o1) store_bf16x8(ep.o1 + off + j, r1);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// [R, C] bf16 (pitch ld_in) -> [C, R] bf16 (pitch ld_out), 32x32 tiles through shared memory
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld_in, int R, int C,
+                                      __nv_bfloat16* __restrict__ out, int64_t ld_out) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[(int64_t)r * ld_in + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < R) out[(int64_t)c * ld_out + r] = tile[threadIdx.x][i];
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with pitch ld (elements); box = 64 cols x 128 rows, 128B swizzle
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn enc = get_encode();
+  PTREC_CHECK_ARG(enc != nullptr, PTREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PTREC_CHECK_ARG(r == CUDA_SUCCESS, PTREC_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return PTREC_OK;
+}
+
+static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, const EpiArgs& ep,
+                       cudaStream_t st) {
+  PTREC_CHECK_ARG(aligned16(A) && aligned16(B) && lda % 8 == 0 && ldb % 8 == 0, PTREC_EALIGN,
+                  "gemm: operands must be 16-byte aligned with pitches that are multiples of 8 elements");
+  PTREC_CHECK_ARG(M > 0 && N > 0 && K > 0 && N % 8 == 0, PTREC_EINVAL, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, A, M, K, lda);
+  if (rc != PTREC_OK) return rc;
+  rc = make_map(&tmB, B, N, K, ldb);
+  if (rc != PTREC_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div(N, kBN), (unsigned)ceil_div(M, kBM));
+  gemm_bf16_tn_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, M, N, K, ep);
+  PTREC_LAUNCH_CHECK("gemm_bf16_tn_kernel");
+  return PTREC_OK;
+}
+
+}  // namespace ptrec
+
+using namespace ptrec;
+
+static int check_cross(const void* a, const void* b, const void* c, int64_t B, int32_t d, int64_t ld) {
+  PTREC_CHECK_ARG(a && b && c, PTREC_EINVAL, "dcn_cross: null pointer");
+  PTREC_CHECK_ARG(B > 0 && B < (int64_t)0x7fffffff && d >= 8 && d % 8 == 0 && ld >= d && ld % 8 == 0, PTREC_EINVAL,
+                  "dcn_cross: need d %% 8 == 0 (pad the concat once), ld %% 8 == 0; got B=%lld d=%d ld=%lld",
+                  (long long)B, d, (long long)ld);
+  return PTREC_OK;
+}
+
+extern "C" int ptrec_dcn_cross_fwd(const void* x_l, const void* x0, const void* weight, const float* bias, int64_t B,
+                                   int32_t d, int64_t ld, void* out, void* u_out, void* stream) {
+  int rc = check_cross(x_l, x0, weight, B, d, ld);
+  if (rc != PTREC_OK) return rc;
+  PTREC_CHECK_ARG(out && aligned16(out) && aligned16(x0) && (!u_out || aligned16(u_out)), PTREC_EALIGN, "dcn_cross_fwd: alignment");
+  EpiArgs ep{};
+  ep.mode = EPI_CROSS_FWD;
+  ep.ld = ld;
+  ep.p0 = reinterpret_cast<const __nv_bfloat16*>(x0);
+  ep.p1 = reinterpret_cast<const __nv_bfloat16*>(x_l);
+  ep.bias = bias;
+  ep.o0 = reinterpret_cast<__nv_bfloat16*>(out);
+  ep.o1 = reinterpret_cast<__nv_bfloat16*>(u_out);
+  return launch_gemm(x_l, ld, weight, d, (int)B, d, d, ep, (cudaStream_t)stream);
+}
+
+extern "C" int ptrec_dcn_cross_dgrad(const void* g_u, const void* weight_t, const void* g_out, const void* x0, int64_t B,
+                                     int32_t d, int64_t ld, void* g_x, void* g_u_prev, void* stream) {
+  int rc = check_cross(g_u, weight_t, g_out, B, d, ld);
+  if (rc != PTREC_OK) return rc;
+  PTREC_CHECK_ARG(x0 && g_x && aligned16(g_x) && aligned16(x0) && aligned16(g_out) && (!g_u_prev || aligned16(g_u_prev)),
+                  PTREC_EALIGN, "dcn_cross_dgrad: alignment");
+  EpiArgs ep{};
+  ep.mode = EPI_CROSS_DGRAD;
+  ep.ld = ld;
+  ep.p0 = reinterpret_cast<const __nv_bfloat16*>(g_out);
+  ep.p1 = reinterpret_cast<const __nv_bfloat16*>(x0);
+  ep.o0 = reinterpret_cast<__nv_bfloat16*>(g_x);
+  ep.o1 = reinterpret_cast<__nv_bfloat16*>(g_u_prev);
+  return launch_gemm(g_u, ld, weight_t, d, (int)B, d, d, ep, (cudaStream_t)stream);
+}
+
+extern "C" size_t ptrec_dcn_cross_wgrad_workspace_bytes(int64_t B, int32_t d) {
+  const size_t ldt = align_up((size_t)B, 8);
+  return 2 * align_up((size_t)d * ldt * 2, 256) + 256;
+}
+
+extern "C" int ptrec_dcn_cross_wgrad(const void* g_u, const void* x_l, int64_t B, int32_t d, int64_t ld, float* grad_w,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_cross(g_u, x_l, grad_w, B, d, ld);
+  if (rc != PTREC_OK) return rc;
+  PTREC_CHECK_ARG(workspace && workspace_bytes >= ptrec_dcn_cross_wgrad_workspace_bytes(B, d), PTREC_EWORKSPACE,
+                  "dcn_cross_wgrad: workspace too small");
+  PTREC_CHECK_ARG(aligned16(grad_w) && d % 4 == 0, PTREC_EALIGN, "dcn_cross_wgrad: grad_w alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t ldt = (int64_t)align_up((size_t)B, 8);
+  __nv_bfloat16* gt = reinterpret_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* xt = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(workspace) +
+                                                       align_up((size_t)d * ldt * 2, 256));
+  dim3 tb(32, 8), tg((unsigned)ceil_div(d, 32), (unsigned)ceil_div(B, 32));
+  transpose_bf16_kernel<<<tg, tb, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g_u), ld, (int)B, d, gt, ldt);
+  PTREC_LAUNCH_CHECK("transpose_bf16_kernel");
+  transpose_bf16_kernel<<<tg, tb, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x_l), ld, (int)B, d, xt, ldt);
+  PTREC_LAUNCH_CHECK("transpose_bf16_kernel");
+  EpiArgs ep{};
+  ep.mode = EPI_F32;
+  ep.of32 = grad_w;
+  ep.ldf = d;
+  // gW[i, j] = sum_b g_u[b, i] * x_l[b, j]  ->  A = g_u^T [d, B], B = x_l^T [d, B], both K(=batch)-major
+  return launch_gemm(gt, ldt, xt, ldt, d, d, (int)B, ep, st);
+}

@@ -3,7 +3,7 @@ torchrec/model/models.py:8-30)."""
 from typing import Dict, Type
 
 from .IModel import History, IModel
-from .ctr import FM, DeepFM
+from .ctr import DCN, FM, DeepFM
 from .mf import SVDPP, FunkSVD
 
 _model_classes: Dict[str, Type[IModel]] = {
@@ -11,6 +11,7 @@ _model_classes: Dict[str, Type[IModel]] = {
     "svdpp": SVDPP,
     "fm": FM,
     "deepfm": DeepFM,
+    "dcn": DCN,
 }
 model_name_list = _model_classes.keys()
 
@@ -21,4 +22,4 @@ def get_model_type(model_name: str) -> Type[IModel]:
     return _model_classes[model_name]
 
 
-__all__ = ["IModel", "History", "FM", "DeepFM", "FunkSVD", "SVDPP", "get_model_type", "model_name_list"]
+__all__ = ["IModel", "History", "FM", "DeepFM", "DCN", "FunkSVD", "SVDPP", "get_model_type", "model_name_list"]

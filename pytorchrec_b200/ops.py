@@ -322,3 +322,110 @@ def a2a_scatter_rows(src: torch.Tensor, ret_pos: torch.Tensor, B: int, F: int, D
     assert src.dtype == torch.float32 and src.stride(-1) == 1 and dst.is_contiguous()
     _lib.check(lib.ptrec_a2a_scatter_rows(_ptr(src), src.stride(0), _ptr(ret_pos), B, F, D, float(scale), _ptr(dst),
                                           _stream(src.device)), "ptrec_a2a_scatter_rows")
+
+
+# ----------------------------------------------------------------------------------------------
+# K5 DCN-v2 cross layers (tcgen05)
+# ----------------------------------------------------------------------------------------------
+def _check_bf16_2d(*ts):
+    for t in ts:
+        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and t.data_ptr() % 16 == 0
+
+
+def dcn_cross_fwd(x_l: torch.Tensor, x0: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
+                  want_u: bool = True):
+    """out = x0 * (x_l @ weight.T + bias) + x_l  (bf16 [B, d]); returns (out, u or None)."""
+    lib = _lib.load()
+    _require_cuda(x_l, x0, weight, bias)
+    _check_bf16_2d(x_l, x0, weight)
+    B, d = x_l.shape
+    assert x0.shape == x_l.shape and x0.stride(0) == x_l.stride(0) and weight.shape == (d, d) and weight.is_contiguous()
+    out = torch.empty_strided((B, d), (x_l.stride(0), 1), dtype=torch.bfloat16, device=x_l.device)
+    u = torch.empty_strided((B, d), (x_l.stride(0), 1), dtype=torch.bfloat16, device=x_l.device) if want_u else None
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == d
+    _lib.check(lib.ptrec_dcn_cross_fwd(_ptr(x_l), _ptr(x0), _ptr(weight), _ptr(bias), B, d, x_l.stride(0), _ptr(out),
+                                       _ptr(u), _stream(x_l.device)), "ptrec_dcn_cross_fwd")
+    return out, u
+
+
+def dcn_cross_dgrad(g_u: torch.Tensor, weight_t: torch.Tensor, g_out: torch.Tensor, x0: torch.Tensor,
+                    want_prev: bool = True):
+    """g_x = g_u @ W + g_out ; optionally also g_x * x0 (next g_u).  weight_t = W.T contiguous."""
+    lib = _lib.load()
+    _require_cuda(g_u, weight_t, g_out, x0)
+    _check_bf16_2d(g_u, weight_t, g_out, x0)
+    B, d = g_u.shape
+    ld = g_u.stride(0)
+    assert g_out.stride(0) == ld and x0.stride(0) == ld and weight_t.is_contiguous()
+    g_x = torch.empty_strided((B, d), (ld, 1), dtype=torch.bfloat16, device=g_u.device)
+    prev = torch.empty_strided((B, d), (ld, 1), dtype=torch.bfloat16, device=g_u.device) if want_prev else None
+    _lib.check(lib.ptrec_dcn_cross_dgrad(_ptr(g_u), _ptr(weight_t), _ptr(g_out), _ptr(x0), B, d, ld, _ptr(g_x),
+                                         _ptr(prev), _stream(g_u.device)), "ptrec_dcn_cross_dgrad")
+    return g_x, prev
+
+
+def dcn_cross_wgrad(g_u: torch.Tensor, x_l: torch.Tensor) -> torch.Tensor:
+    """grad_W [d, d] fp32 = g_u.T @ x_l."""
+    lib = _lib.load()
+    _require_cuda(g_u, x_l)
+    _check_bf16_2d(g_u, x_l)
+    B, d = g_u.shape
+    assert x_l.stride(0) == g_u.stride(0)
+    gw = torch.empty(d, d, dtype=torch.float32, device=g_u.device)
+    ws = _workspace("dcn_wgrad", lib.ptrec_dcn_cross_wgrad_workspace_bytes(B, d), g_u.device)
+    _lib.check(lib.ptrec_dcn_cross_wgrad(_ptr(g_u), _ptr(x_l), B, d, g_u.stride(0), _ptr(gw), _ptr(ws), ws.numel(),
+                                         _stream(g_u.device)), "ptrec_dcn_cross_wgrad")
+    return gw
+
+
+class _CrossNet(torch.autograd.Function):
+    """All cross layers in one autograd node so that each dgrad epilogue can emit the g_u of the layer below."""
+
+    @staticmethod
+    def forward(ctx, x0f, n_layers, *params):
+        weights, biases = params[:n_layers], params[n_layers:]
+        B, d = x0f.shape
+        dp = (d + 7) // 8 * 8
+        x0 = torch.zeros(B, dp, dtype=torch.bfloat16, device=x0f.device)
+        x0[:, :d] = x0f
+        wb, xs, us = [], [x0], []
+        x = x0
+        for W, b in zip(weights, biases):
+            w16 = torch.zeros(dp, dp, dtype=torch.bfloat16, device=x0f.device)
+            w16[:d, :d] = W
+            bp = torch.zeros(dp, dtype=torch.float32, device=x0f.device)
+            bp[:d] = b
+            x, u = dcn_cross_fwd(x, x0, w16, bp, want_u=True)
+            wb.append(w16)
+            xs.append(x)
+            us.append(u)
+        ctx.d, ctx.n = d, n_layers
+        ctx.save_for_backward(*xs[:-1], *us, *wb)
+        return x[:, :d].to(x0f.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        n, d = ctx.n, ctx.d
+        saved = ctx.saved_tensors
+        xs, us, wb = saved[:n], saved[n:2 * n], saved[2 * n:]
+        x0 = xs[0]
+        B, dp = x0.shape
+        g_out = torch.zeros(B, dp, dtype=torch.bfloat16, device=g.device)
+        g_out[:, :d] = g
+        g_u = g_out * x0
+        g_x0 = torch.zeros(B, dp, dtype=torch.float32, device=g.device)
+        gws, gbs = [None] * n, [None] * n
+        for l in range(n - 1, -1, -1):
+            g_x0.addcmul_(g_out.float(), us[l].float())          # d out / d x0 = u
+            gws[l] = dcn_cross_wgrad(g_u, xs[l])[:d, :d]
+            gbs[l] = g_u.float().sum(0)[:d]
+            g_out, g_u = dcn_cross_dgrad(g_u, wb[l].t().contiguous(), g_out, x0, want_prev=l > 0)
+        g_x0 += g_out.float()                                      # x0 is also layer 0's x_l
+        return (g_x0[:, :d].to(g.dtype), None, *gws, *gbs)
+
+
+def cross_net(x0: torch.Tensor, weights, biases) -> torch.Tensor:
+    """L DCN-v2 cross layers ``x <- x0 * (x W_l^T + b_l) + x`` on tensor cores (bf16, fp32 accumulate)."""
+    _require_cuda(x0)
+    return _CrossNet.apply(x0.contiguous(), len(weights), *weights, *biases)

@@ -411,3 +411,67 @@ def test_full_size_properties_deepfm_config():
     ops.bwd_fused(tables, None, None, lay, B, srt, go, None, args)
     after = torch.stack([w.double().sum() for w in weights]).sum()
     np.testing.assert_allclose((before - after).item(), 0.5 * go.double().sum().item(), rtol=1e-3, atol=2.0)
+
+
+# ------------------------------------------------------------------------------------------ DCN cross (tcgen05)
+def _bf16(t):
+    return t.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,d", [(128, 128), (256, 64), (1000, 848), (4096, 896), (130, 72)])
+def test_dcn_cross_fwd_matches_fp32_reference(B, d):
+    """bf16 operands, fp32 accumulate: compare with the same bf16-rounded inputs multiplied in fp32 (tolerance 1e-2)."""
+    g = torch.Generator().manual_seed(B + d)
+    x0, xl = torch.randn(B, d, generator=g) * 0.5, torch.randn(B, d, generator=g) * 0.5
+    W, b = torch.randn(d, d, generator=g) / d ** 0.5, torch.randn(d, generator=g) * 0.1
+    x0b, xlb, Wb = _bf16(x0), _bf16(xl), _bf16(W)
+    out, u = ops.dcn_cross_fwd(xlb.to(DEV), x0b.to(DEV), Wb.to(DEV), b.to(DEV))
+    u_ref = xlb.float() @ Wb.float().t() + b
+    out_ref = x0b.float() * u_ref + xlb.float()
+    np.testing.assert_allclose(u.float().cpu().numpy(), u_ref.numpy(), rtol=1e-2, atol=1e-2)
+    np.testing.assert_allclose(out.float().cpu().numpy(), out_ref.numpy(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("B,d", [(256, 128), (1000, 848)])
+def test_dcn_cross_dgrad_wgrad(B, d):
+    g = torch.Generator().manual_seed(B * 3 + d)
+    x0, xl, go = (torch.randn(B, d, generator=g) * 0.5 for _ in range(3))
+    W = torch.randn(d, d, generator=g) / d ** 0.5
+    x0b, xlb, gob, Wb = _bf16(x0), _bf16(xl), _bf16(go), _bf16(W)
+    gub = _bf16(gob.float() * x0b.float())
+    gx, prev = ops.dcn_cross_dgrad(gub.to(DEV), Wb.t().contiguous().to(DEV), gob.to(DEV), x0b.to(DEV))
+    gx_ref = gub.float() @ Wb.float() + gob.float()
+    np.testing.assert_allclose(gx.float().cpu().numpy(), gx_ref.numpy(), rtol=1e-2, atol=1e-2)
+    np.testing.assert_allclose(prev.float().cpu().numpy(), (gx_ref * x0b.float()).numpy(), rtol=2e-2, atol=1e-2)
+    gw = ops.dcn_cross_wgrad(gub.to(DEV), xlb.to(DEV))
+    gw_ref = gub.float().t() @ xlb.float()
+    np.testing.assert_allclose(gw.cpu().numpy(), gw_ref.numpy(), rtol=1e-2, atol=1e-2 * B ** 0.5 * 0.25)
+
+
+def test_cross_net_autograd_matches_oracle():
+    from oracle import ref_models
+    B, d, L = 512, 845, 3
+    g = torch.Generator().manual_seed(1)
+    x0 = torch.randn(B, d, generator=g) * 0.3
+    Ws = [torch.randn(d, d, generator=g) / d ** 0.5 for _ in range(L)]
+    bs = [torch.randn(d, generator=g) * 0.1 for _ in range(L)]
+    go = torch.randn(B, d, generator=g)
+    x0r = x0.clone().requires_grad_(True)
+    Wr, br = [w.clone().requires_grad_(True) for w in Ws], [b.clone().requires_grad_(True) for b in bs]
+    yr = ref_models.cross_net_ref(x0r, Wr, br)
+    yr.backward(go)
+    x0d = x0.to(DEV).requires_grad_(True)
+    Wd, bd = [w.to(DEV).requires_grad_(True) for w in Ws], [b.to(DEV).requires_grad_(True) for b in bs]
+    y = ops.cross_net(x0d, Wd, bd)
+    y.backward(go.to(DEV))
+
+    def close(a, b, what):
+        a, b = a.detach().cpu().float(), b.detach().float()
+        err = (a - b).norm() / b.norm()
+        assert err < 1e-2, f"{what}: relative error {err:.4f}"
+
+    close(y, yr, "out")
+    close(x0d.grad, x0r.grad, "grad x0")
+    for l in range(L):
+        close(Wd[l].grad, Wr[l].grad, f"grad W{l}")
+        close(bd[l].grad, br[l].grad, f"grad b{l}")
