@@ -227,6 +227,31 @@ int ptrec_fm2_bwd(const float* v, int64_t v_row_stride, const float* gy, const f
                   int64_t grad_v_row_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K4 DIN attention pooling: activation unit + masked weighted sum, fused (nothing of shape [B, L, 4*DQ] or
+ * [B, L, H1] reaches HBM).  Not in the reference; the masking / history conventions are the reference's
+ * (length column clipped to >= 1, right-padded histories: HistoryDataReader.py:55-69, SASRec.py:83,109-110).
+ *   a_l = W3 relu(W2 relu(W1 [q, k_l, q-k_l, q*k_l] + b1) + b2) + b3 ;  pooled[b] = sum_{l < lens[b]} a_l k_l
+ *   q [B, DQ] (row stride q_stride), keys [B, L, DQ] (strides in floats), lens [B] int32 or NULL (= L)
+ *   W1 [H1, 4*DQ], b1 [H1], W2 [H2, H1], b2 [H2], W3 [1, H2], b3 [1]  (nn.Linear layouts), fp32
+ *   out [B, DQ];  scores [B, L] or NULL (a_l, 0 beyond the length)
+ * backward: g_q [B, DQ], g_keys [B, L, DQ] (zeros beyond the length), grad_params = flat
+ *   [gW1 | gb1 | gW2 | gb2 | gW3 | gb3] of ptrec_din_attn_pool_grad_floats() floats.
+ * Built for DQ in {16, 32} and (H1, H2) in {(80, 40), (64, 32)}.
+ */
+int ptrec_din_attn_pool_fwd(const float* q, int64_t q_stride, const float* keys, int64_t k_stride_b,
+                            int64_t k_stride_l, const int32_t* lens, int64_t B, int32_t L, int32_t DQ, int32_t H1,
+                            int32_t H2, const float* W1, const float* b1, const float* W2, const float* b2,
+                            const float* W3, const float* b3, float* out, float* scores, void* stream);
+int32_t ptrec_din_attn_pool_grad_floats(int32_t DQ, int32_t H1, int32_t H2);
+size_t ptrec_din_attn_pool_bwd_workspace_bytes(int32_t DQ, int32_t H1, int32_t H2);
+int ptrec_din_attn_pool_bwd(const float* q, int64_t q_stride, const float* keys, int64_t k_stride_b,
+                            int64_t k_stride_l, const int32_t* lens, int64_t B, int32_t L, int32_t DQ, int32_t H1,
+                            int32_t H2, const float* W1, const float* b1, const float* W2, const float* b2,
+                            const float* W3, const float* b3, const float* g_pooled, float* g_q, float* g_keys,
+                            int64_t gk_stride_b, int64_t gk_stride_l, float* grad_params, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K5 DCN-v2 cross layer on tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM).
  * Not in the reference; the layer is  x_{l+1} = x0 (.) (x_l W^T + b) + x_l  with W stored
  * [d_out, d_in] row-major like nn.Linear.  All activations are bf16 [B, ld] row-major, d % 8 == 0 and

@@ -249,3 +249,52 @@ def cross_net_ref(x0: Tensor, weights, biases) -> Tensor:
     for W, b in zip(weights, biases):
         x = x0 * (x @ W.t() + b) + x
     return x
+
+
+def din_attention_ref(q: Tensor, keys: Tensor, lens: Optional[Tensor], fc1, fc2, fc3) -> Tensor:
+    """DIN activation unit + masked weighted sum in plain torch: materialises [B, L, 4*DQ] and the hidden layers."""
+    B, L, DQ = keys.shape
+    qe = q.unsqueeze(1).expand(B, L, DQ)
+    z = torch.cat([qe, keys, qe - keys, qe * keys], dim=-1)
+    a = fc3(torch.relu(fc2(torch.relu(fc1(z))))).squeeze(-1)
+    if lens is not None:
+        a = a * (torch.arange(L).unsqueeze(0) < lens.reshape(B, 1)).to(a.dtype)
+    return (a.unsqueeze(-1) * keys).sum(dim=1)
+
+
+class _AttentionRef(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1, self.fc2, self.fc3 = Linear(4 * dim, hidden[0]), Linear(hidden[0], hidden[1]), Linear(hidden[1], 1)
+
+
+class DINRef(IModelRef):
+    """Deep Interest Network (NOT in the reference: parity unpinned).  History conventions are the reference's:
+    right-padded ``[B, L]`` ids with 0 = PAD and a length column (HistoryDataReader.py:55-69); shared item /
+    category tables as SASRec shares ``i_embeddings`` between candidates and history (SASRec.py:85-86)."""
+
+    def __init__(self, random_seed, uid_column, iid_column, cid_column, his_iid_column, his_cid_column, his_len_column,
+                 label_column, emb_size, layers, attention_hidden=(80, 40), dropout=0.0):
+        self.cols = (uid_column, iid_column, cid_column, his_iid_column, his_cid_column, his_len_column, label_column)
+        self.emb_size, self.layers, self.attention_hidden, self.dropout = emb_size, list(layers), attention_hidden, dropout
+        super().__init__(random_seed)
+
+    def _init_weights(self):
+        uid, iid, cid = self.cols[0], self.cols[1], self.cols[2]
+        D = self.emb_size
+        self.seq_emb = nn.ModuleList([Embedding(iid.category_num, D), Embedding(cid.category_num, D)])
+        self.user_emb = Embedding(uid.category_num, D)
+        self.attention = _AttentionRef(2 * D, self.attention_hidden)
+        self.mlp = MLPRef(5 * D, self.layers, self.dropout)
+        self.out = Linear(self.layers[-1], 1, bias=False)
+
+    def forward(self, data):
+        uid, iid, cid, hi, hc, hl, lab = self.cols
+        q = torch.cat([self.seq_emb[0](iid.get_feature_data(data)), self.seq_emb[1](cid.get_feature_data(data))], dim=-1)
+        keys = torch.cat([self.seq_emb[0](hi.get_feature_data(data)), self.seq_emb[1](hc.get_feature_data(data))], dim=-1)
+        pooled = din_attention_ref(q, keys, hl.get_feature_data(data), self.attention.fc1, self.attention.fc2,
+                                   self.attention.fc3)
+        user = self.user_emb(uid.get_feature_data(data))
+        logit = self.out(self.mlp(torch.cat([user, q, pooled], dim=1))).squeeze(-1)
+        t = lab.get_feature_data(data)
+        return logit, (t.float() if t is not None else None)

@@ -91,6 +91,15 @@ PROTOTYPES = {
                                         c_void_p, c_size_t, c_void_p]),
     "ptrec_a2a_scatter_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p,
                                        c_void_p]),
+    "ptrec_din_attn_pool_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int32,
+                                        c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ptrec_din_attn_pool_grad_floats": (c_int32, [c_int32, c_int32, c_int32]),
+    "ptrec_din_attn_pool_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "ptrec_din_attn_pool_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int32,
+                                        c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                                        c_size_t, c_void_p]),
     "ptrec_dcn_cross_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p,
                                     c_void_p, c_void_p]),
     "ptrec_dcn_cross_dgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p,

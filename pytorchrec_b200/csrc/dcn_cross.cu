@@ -20,7 +20,7 @@
 
 namespace ptrec {
 
-constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 4, kUmmaK = 16;
+constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 3, kUmmaK = 16;
 constexpr int kGemmThreads = 192;
 constexpr uint32_t kStageBytesA = kBM * kBK * 2, kStageBytesB = kBN * kBK * 2;
 constexpr uint32_t kTmemCols = 128;
@@ -106,7 +106,7 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float* f) {
 }
 
 // ---- the GEMM: C[M, N] = A[M, K] * B[N, K]^T, fused epilogue ---------------------------------------------------
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                     int K, EpiArgs ep) {
   extern __shared__ unsigned char smem_raw[];
@@ -178,7 +178,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tcgen05_fence_after();
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < M;
-#pragma unroll 1
+#pragma unroll 2
     for (int c = 0; c < kBN / 32; ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);

@@ -3,7 +3,7 @@ torchrec/model/models.py:8-30)."""
 from typing import Dict, Type
 
 from .IModel import History, IModel
-from .ctr import DCN, FM, DeepFM
+from .ctr import DCN, DIN, FM, DeepFM
 from .mf import SVDPP, FunkSVD
 
 _model_classes: Dict[str, Type[IModel]] = {
@@ -12,6 +12,7 @@ _model_classes: Dict[str, Type[IModel]] = {
     "fm": FM,
     "deepfm": DeepFM,
     "dcn": DCN,
+    "din": DIN,
 }
 model_name_list = _model_classes.keys()
 
@@ -22,4 +23,4 @@ def get_model_type(model_name: str) -> Type[IModel]:
     return _model_classes[model_name]
 
 
-__all__ = ["IModel", "History", "FM", "DeepFM", "DCN", "FunkSVD", "SVDPP", "get_model_type", "model_name_list"]
+__all__ = ["IModel", "History", "FM", "DeepFM", "DCN", "DIN", "FunkSVD", "SVDPP", "get_model_type", "model_name_list"]

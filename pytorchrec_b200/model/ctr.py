@@ -18,7 +18,7 @@ from torch.nn import Linear, Parameter
 
 from ..feature_column import CategoricalColumnWithIdentity, NumericColumn
 from .IModel import IModel
-from .layer import MLP, CrossNet, FMSecondOrder, MultiTableEmbedding
+from .layer import MLP, AttentionPooling, CrossNet, EmbeddingTable, FMSecondOrder, MultiTableEmbedding
 
 
 def _dense_matrix(dense_columns: List[NumericColumn], data: Dict[str, Tensor]) -> Optional[Tensor]:
@@ -121,5 +121,48 @@ class DCN(IModel):
         flat = v.reshape(v.shape[0], -1)
         x0 = torch.cat([flat, x], dim=1) if x is not None else flat
         logit = self.out(torch.cat([self.cross(x0), self.mlp(x0)], dim=1)).squeeze(-1)
+        target = self.label_column.get_feature_data(data)
+        return logit, (target.float() if target is not None else None)
+
+
+class DIN(IModel):
+    """Deep Interest Network on the fused path.  Inputs follow the reference's history wire format
+    (HistoryDataReader.py:55-69): a right-padded id matrix ``[B, L]`` (0 = PAD) plus a length column clipped to
+    >= 1.  Item and category tables are shared between the candidate and the history; candidate and history ids
+    go through ONE fused lookup per step (so each table sees one sort / dedup / update), the query is
+    ``[item(cand) || cate(cand)]`` and the keys ``[item(h_l) || cate(h_l)]``.
+        y = Linear(MLP([user || q || sum_{l<len} a_l k_l]))"""
+
+    def __init__(self, uid_column, iid_column, cid_column, his_iid_column, his_cid_column, his_len_column, label_column,
+                 emb_size: int, layers: List[int], attention_hidden=(80, 40), dropout: float = 0.0, table_device=None,
+                 **kwargs):
+        self.uid_column, self.iid_column, self.cid_column = uid_column, iid_column, cid_column
+        self.his_iid_column, self.his_cid_column, self.his_len_column = his_iid_column, his_cid_column, his_len_column
+        self.label_column = label_column
+        self.emb_size, self.layers, self.attention_hidden, self.dropout = emb_size, list(layers), tuple(attention_hidden), dropout
+        self.table_device = table_device
+        super().__init__(**kwargs)
+
+    def _init_weights(self):
+        D = self.emb_size
+        self.seq_emb = MultiTableEmbedding([self.iid_column, self.cid_column], D, device=self.table_device)
+        self.user_emb = EmbeddingTable(self.uid_column.category_num, D, device=self.table_device)
+        self.attention = AttentionPooling(2 * D, self.attention_hidden)
+        self.mlp = MLP(input_units=5 * D, hidden_units_list=self.layers, activation="relu", dropout=self.dropout)
+        self.out = Linear(self.layers[-1], 1, bias=False)
+
+    def forward(self, data: Dict[str, Tensor]):
+        D = self.emb_size
+        cand_i, cand_c = self.iid_column.get_feature_data(data), self.cid_column.get_feature_data(data)
+        his_i, his_c = self.his_iid_column.get_feature_data(data), self.his_cid_column.get_feature_data(data)
+        lens = self.his_len_column.get_feature_data(data)
+        B, L = his_i.shape
+        flat = {self.iid_column.feature_name: torch.cat([cand_i.unsqueeze(1), his_i], dim=1).reshape(-1),
+                self.cid_column.feature_name: torch.cat([cand_c.unsqueeze(1), his_c], dim=1).reshape(-1)}
+        seq = self.seq_emb(flat).view(B, 1 + L, 2 * D)      # [B, 1+L, item||cate]
+        q, keys = seq[:, 0], seq[:, 1:]
+        pooled = self.attention(q, keys, lens)
+        user = self.user_emb(self.uid_column.get_feature_data(data))
+        logit = self.out(self.mlp(torch.cat([user, q, pooled], dim=1))).squeeze(-1)
         target = self.label_column.get_feature_data(data)
         return logit, (target.float() if target is not None else None)

@@ -26,3 +26,21 @@ class CrossNet(nn.Module):
 
     def forward(self, x0: Tensor) -> Tensor:
         return ops.cross_net(x0, [m.weight for m in self.layers], [m.bias for m in self.layers])
+
+
+class AttentionPooling(nn.Module):
+    """DIN attention pooling: ``pooled = sum_{l < len} a_l k_l`` with the activation unit
+    ``a_l = fc3(relu(fc2(relu(fc1([q, k_l, q - k_l, q * k_l])))))`` (no softmax).  Parameters are three
+    ``nn.Linear`` modules (``fc1: 4*dim -> hidden[0]``, ``fc2``, ``fc3: hidden[1] -> 1``) so the reference's init
+    applies; forward and backward are one fused CUDA kernel each."""
+
+    def __init__(self, dim: int, hidden=(80, 40)):
+        super().__init__()
+        self.dim = dim
+        self.fc1 = nn.Linear(4 * dim, hidden[0])
+        self.fc2 = nn.Linear(hidden[0], hidden[1])
+        self.fc3 = nn.Linear(hidden[1], 1)
+
+    def forward(self, q: Tensor, keys: Tensor, lens: Tensor = None) -> Tensor:
+        return ops.din_attn_pool(q, keys, lens, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+                                 self.fc3.weight, self.fc3.bias)

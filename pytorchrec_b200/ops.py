@@ -429,3 +429,76 @@ def cross_net(x0: torch.Tensor, weights, biases) -> torch.Tensor:
     """L DCN-v2 cross layers ``x <- x0 * (x W_l^T + b_l) + x`` on tensor cores (bf16, fp32 accumulate)."""
     _require_cuda(x0)
     return _CrossNet.apply(x0.contiguous(), len(weights), *weights, *biases)
+
+
+# ----------------------------------------------------------------------------------------------
+# K4 DIN attention pooling
+# ----------------------------------------------------------------------------------------------
+def _din_args(q, keys, lens, params):
+    W1, b1, W2, b2, W3, b3 = params
+    B, L, DQ = keys.shape
+    H1, H2 = W1.shape[0], W2.shape[0]
+    assert q.shape == (B, DQ) and q.stride(1) == 1 and keys.stride(2) == 1
+    assert W1.shape == (H1, 4 * DQ) and W2.shape == (H2, H1) and W3.shape == (1, H2)
+    for p in params:
+        assert p.dtype == torch.float32 and p.is_contiguous()
+    if lens is not None:
+        lens = lens.to(torch.int32).contiguous()
+    return B, L, DQ, H1, H2, lens
+
+
+def din_attn_pool_fwd(q, keys, lens, params, want_scores: bool = False):
+    lib = _lib.load()
+    _require_cuda(q, keys, lens, *params)
+    B, L, DQ, H1, H2, lens = _din_args(q, keys, lens, params)
+    out = torch.empty(B, DQ, dtype=torch.float32, device=q.device)
+    scores = torch.empty(B, L, dtype=torch.float32, device=q.device) if want_scores else None
+    _lib.check(lib.ptrec_din_attn_pool_fwd(_ptr(q), q.stride(0), _ptr(keys), keys.stride(0), keys.stride(1), _ptr(lens),
+                                           B, L, DQ, H1, H2, *[_ptr(p) for p in params], _ptr(out), _ptr(scores),
+                                           _stream(q.device)), "ptrec_din_attn_pool_fwd")
+    return out, scores
+
+
+def din_attn_pool_bwd(q, keys, lens, params, g_pooled):
+    lib = _lib.load()
+    _require_cuda(q, keys, lens, g_pooled, *params)
+    B, L, DQ, H1, H2, lens = _din_args(q, keys, lens, params)
+    g_pooled = g_pooled.contiguous()
+    g_q = torch.empty(B, DQ, dtype=torch.float32, device=q.device)
+    g_keys = torch.empty(B, L, DQ, dtype=torch.float32, device=q.device)
+    n = lib.ptrec_din_attn_pool_grad_floats(DQ, H1, H2)
+    flat = torch.empty(n, dtype=torch.float32, device=q.device)
+    ws = _workspace("din_bwd", lib.ptrec_din_attn_pool_bwd_workspace_bytes(DQ, H1, H2), q.device)
+    _lib.check(lib.ptrec_din_attn_pool_bwd(_ptr(q), q.stride(0), _ptr(keys), keys.stride(0), keys.stride(1), _ptr(lens),
+                                           B, L, DQ, H1, H2, *[_ptr(p) for p in params], _ptr(g_pooled), _ptr(g_q),
+                                           _ptr(g_keys), g_keys.stride(0), g_keys.stride(1), _ptr(flat), _ptr(ws),
+                                           ws.numel(), _stream(q.device)), "ptrec_din_attn_pool_bwd")
+    sizes = [H1 * 4 * DQ, H1, H2 * H1, H2, H2, 1]
+    gW1, gb1, gW2, gb2, gW3, gb3 = torch.split(flat, sizes)
+    return g_q, g_keys, (gW1.view(H1, 4 * DQ), gb1, gW2.view(H2, H1), gb2, gW3.view(1, H2), gb3)
+
+
+class _DinAttnPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, keys, lens, W1, b1, W2, b2, W3, b3):
+        params = (W1, b1, W2, b2, W3, b3)
+        out, _ = din_attn_pool_fwd(q, keys, lens, params)
+        ctx.save_for_backward(q, keys, lens, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, keys, lens, *params = ctx.saved_tensors
+        g_q, g_keys, gp = din_attn_pool_bwd(q, keys, lens, tuple(params), g)
+        return (g_q, g_keys, None, *gp)
+
+
+def din_attn_pool(q, keys, lens, W1, b1, W2, b2, W3, b3):
+    """DIN attention pooling ``sum_{l<len} a_l k_l`` with the fused activation unit (CUDA forward + backward).
+    ``q [B, DQ]``, ``keys [B, L, DQ]`` (may be strided views), ``lens [B]`` or None."""
+    _require_cuda(q, keys)
+    if q.stride(-1) != 1 or q.data_ptr() % 16 or q.stride(0) % 4:
+        q = q.contiguous()
+    if keys.stride(-1) != 1 or keys.data_ptr() % 16 or keys.stride(0) % 4 or keys.stride(1) % 4:
+        keys = keys.contiguous()
+    return _DinAttnPool.apply(q, keys, lens, W1, b1, W2, b2, W3, b3)

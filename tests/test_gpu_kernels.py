@@ -475,3 +475,46 @@ def test_cross_net_autograd_matches_oracle():
     for l in range(L):
         close(Wd[l].grad, Wr[l].grad, f"grad W{l}")
         close(bd[l].grad, br[l].grad, f"grad b{l}")
+
+
+# ------------------------------------------------------------------------------------------ DIN attention pooling
+@pytest.mark.parametrize("B,L,DQ,hidden", [(3, 5, 32, (80, 40)), (64, 100, 32, (80, 40)), (33, 130, 16, (80, 40)),
+                                            (40, 50, 32, (64, 32)), (17, 100, 16, (64, 32))])
+def test_din_attention_pool_forward_backward(B, L, DQ, hidden):
+    from oracle import ref_models
+    g = torch.Generator().manual_seed(B + L + DQ)
+    H1, H2 = hidden
+    fc1, fc2, fc3 = torch.nn.Linear(4 * DQ, H1), torch.nn.Linear(H1, H2), torch.nn.Linear(H2, 1)
+    with torch.no_grad():
+        for m in (fc1, fc2, fc3):
+            m.weight.copy_(torch.randn(m.weight.shape, generator=g) * 0.2)
+            m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+    q = torch.randn(B, DQ, generator=g)
+    keys = torch.randn(B, L, DQ, generator=g)
+    lens = torch.randint(0, L + 1, (B,), generator=g)
+    lens[0] = L
+    go = torch.randn(B, DQ, generator=g)
+    qr, kr = q.clone().requires_grad_(True), keys.clone().requires_grad_(True)
+    out_ref = ref_models.din_attention_ref(qr, kr, lens, fc1, fc2, fc3)
+    out_ref.backward(go)
+    params = [p.detach().clone().to(DEV).requires_grad_(True) for p in (fc1.weight, fc1.bias, fc2.weight, fc2.bias, fc3.weight, fc3.bias)]
+    qd, kd = q.to(DEV).requires_grad_(True), keys.to(DEV).requires_grad_(True)
+    out = ops.din_attn_pool(qd, kd, lens.to(DEV), *params)
+    out.backward(go.to(DEV))
+
+    def close(a, b, what, rtol=1e-5):
+        a, b = a.detach().cpu(), b.detach()
+        tol = rtol * b.abs().max().clamp(min=1e-3) * 20 + 1e-6  # sums of ~L*H terms: scale by the tensor's magnitude
+        assert ((a - b).abs() <= tol).all(), f"{what}: max err {(a - b).abs().max():.3e} tol {tol:.3e}"
+
+    close(out, out_ref, "pooled")
+    close(qd.grad, qr.grad, "grad q")
+    close(kd.grad, kr.grad, "grad keys")
+    for p, r, n in zip(params, (fc1.weight, fc1.bias, fc2.weight, fc2.bias, fc3.weight, fc3.bias),
+                       ("W1", "b1", "W2", "b2", "W3", "b3")):
+        close(p.grad, r.grad, "grad " + n)
+    # strided q / keys views of one [B, 1+L, DQ] buffer (the layout the DIN model uses)
+    seq = torch.cat([q.unsqueeze(1), keys], dim=1).to(DEV)
+    out2, scores = ops.din_attn_pool_fwd(seq[:, 0], seq[:, 1:], lens.to(DEV), [p.detach() for p in params], want_scores=True)
+    assert torch.equal(out2, out.detach())
+    assert (scores.cpu()[torch.arange(L).unsqueeze(0) >= lens.unsqueeze(1)] == 0).all()
