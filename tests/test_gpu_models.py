@@ -292,7 +292,10 @@ def test_din_matches_oracle_twin(opt_name):
     if opt_name == "sgd":
         popt, ropt = SparseSGD(prod.get_parameters(), lr=0.2), torch.optim.SGD(ref.get_parameters(), lr=0.2)
     else:
-        popt, ropt = SparseAdagrad(prod.get_parameters(), lr=0.02), torch.optim.Adagrad(ref.get_parameters(), lr=0.02)
+        # eps well above the fp32 noise floor of the (cancelling) gradient sums: with the default 1e-10 an element
+        # whose true gradient is ~0 moves by lr * noise / (|noise| + eps), i.e. by an arbitrary fraction of lr
+        popt = SparseAdagrad(prod.get_parameters(), lr=0.02, eps=1e-6)
+        ropt = torch.optim.Adagrad(ref.get_parameters(), lr=0.02, eps=1e-6)
     prod.compile(popt, torch.nn.BCEWithLogitsLoss(), [LogLoss()], DEV)
     ref.compile(ropt, torch.nn.BCEWithLogitsLoss())
     for s in range(3):
