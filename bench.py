@@ -267,13 +267,15 @@ def kernel_roofline(a, model, resident, dev):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     emb = model.embeddings
-    tables = [t.weight.data for t in emb]
-    F, D, B = len(tables), a.dim, a.batch
-    R = min(t.shape[0] for t in tables)
+    F, D, B = len(emb), a.dim, a.batch
+    R = min(t.weight.shape[0] for t in emb)
+    # private copies in the layout the optimizer uses (weight | Adagrad sum interleaved in one 2*D-float row)
+    bufs = [torch.randn(t.weight.shape[0], 2 * D, device=dev) for t in emb]
+    tables = [b[:, :D] for b in bufs]
     lay = ops.FeatureLayout([dict(table=f, bag_len=1) for f in range(F)], D, F)
     ts = ops.TableSet().refresh(tables)
     id_batches = [(torch.cat([b[c.feature_name].reshape(-1) for c in emb.columns]) % R).contiguous() for b in resident]
-    state = [torch.zeros_like(t) for t in tables]
+    state = [b[:, D:].abs_() for b in bufs]
     p1 = ops.make_ptr_array(state)
     go = torch.randn(B, F * D, device=dev)
     args = _lib.OptimArgs(kind=_lib.OPT_ADAGRAD, step=1, lr=0.0, eps=1e-10, beta1=0, beta2=0, weight_decay=0, lr_decay=0)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 3
+#define PTREC_ABI_VERSION 4
 
 /* error codes */
 #define PTREC_OK 0
@@ -115,6 +115,8 @@ int ptrec_index_prep(const int64_t* ids_padded, const int32_t* lens, int64_t B, 
  * Replaces T x `nn.Embedding.forward` (FunkSVD.py:47-48, SVDPP.py:50,57-61, NCF.py:62-65) and the
  * masked pooling chains SVDPP.py:49-55 / SASRec.py:109-110 in ONE launch per bag class.
  *   table_ptrs [T] device array of table base pointers ([rows_t, D] row-major, 16-byte aligned)
+ *   row_stride floats between consecutive rows of every table (== D for plain tables; 2*D / 4*D when the
+ *              optimizer state is interleaved with the weights so that one 128-byte DRAM line holds both)
  *   table_rows [T] int64 (bounds check -> *err_flag = 1 on an out-of-range id, lookup skipped)
  *   ids        [sum_f B*bag_len_f] int64, feature-major, each feature [B, bag_len]
  *   lens       [n_cols, B] int32 or NULL
@@ -126,7 +128,7 @@ int ptrec_index_prep(const int64_t* ids_padded, const int32_t* lens, int64_t B, 
  *              (launch geometry is derived from it without touching the device).
  */
 int ptrec_embedding_gather_pool_fwd(const void* const* table_ptrs, const int64_t* table_rows,
-                                    int32_t T, int32_t D, int32_t dtype,
+                                    int32_t T, int32_t D, int64_t row_stride, int32_t dtype,
                                     const ptrec_feature_desc* feats,
                                     const ptrec_feature_desc* feats_host, int32_t F,
                                     const int64_t* ids, const int32_t* lens, int64_t B, float* out,
@@ -160,6 +162,8 @@ int ptrec_sort_dedup(const ptrec_feature_desc* feats, const ptrec_feature_desc* 
  * (IModel.py:122-124, optim/optimizers.py:7-11, torch.optim.SGD/Adagrad/SparseAdam arithmetic).
  * One pass per unique row: sum its gradient slots in sorted (= batch) order, read-modify-write
  * the weight row and its state.  No [rows, D] gradient tensor is ever materialised.
+ *   row_stride: floats between consecutive rows of the tables AND of the element-wise state arrays
+ *     (interleaved layout: state1_ptrs[t] = table_ptrs[t] + D, row_stride = 2*D).
  *   state1_ptrs / state2_ptrs [T] device arrays (NULL when the optimizer has no such state):
  *     ADAGRAD: state1 = sum of squares [rows, D];  ROWWISE_ADAGRAD: state1 = [rows];
  *     LAZY_ADAM: state1 = exp_avg, state2 = exp_avg_sq, both [rows, D].
@@ -169,7 +173,7 @@ int ptrec_sort_dedup(const ptrec_feature_desc* feats, const ptrec_feature_desc* 
  */
 size_t ptrec_embedding_bwd_workspace_bytes(int64_t N, int32_t D);
 int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* state1_ptrs,
-                              void* const* state2_ptrs, int32_t T, int32_t D, int32_t dtype,
+                              void* const* state2_ptrs, int32_t T, int32_t D, int64_t row_stride, int32_t dtype,
                               const ptrec_feature_desc* feats,
                               const ptrec_feature_desc* feats_host, int32_t F, int64_t B,
                               const uint32_t* sorted_keys, const int32_t* perm,
@@ -179,23 +183,23 @@ int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* state1_ptrs,
                               const ptrec_optim_args* opt_host, void* workspace,
                               size_t workspace_bytes, void* stream);
 /* the four named entry points of SURVEY.md §8b; each checks opt_host->kind and forwards */
-int ptrec_embedding_bwd_fused_sgd(void* const*, void* const*, void* const*, int32_t, int32_t,
+int ptrec_embedding_bwd_fused_sgd(void* const*, void* const*, void* const*, int32_t, int32_t, int64_t,
                                   int32_t, const ptrec_feature_desc*, const ptrec_feature_desc*, int32_t, int64_t,
                                   const uint32_t*, const int32_t*, const int32_t*, const int32_t*,
                                   const int32_t*, const float*, int64_t, const float*,
                                   const ptrec_optim_args*, void*, size_t, void*);
-int ptrec_embedding_bwd_fused_adagrad(void* const*, void* const*, void* const*, int32_t, int32_t,
+int ptrec_embedding_bwd_fused_adagrad(void* const*, void* const*, void* const*, int32_t, int32_t, int64_t,
                                       int32_t, const ptrec_feature_desc*, const ptrec_feature_desc*, int32_t, int64_t,
                                       const uint32_t*, const int32_t*, const int32_t*,
                                       const int32_t*, const int32_t*, const float*, int64_t,
                                       const float*, const ptrec_optim_args*, void*, size_t, void*);
 int ptrec_embedding_bwd_fused_rowwise_adagrad(void* const*, void* const*, void* const*, int32_t,
-                                              int32_t, int32_t, const ptrec_feature_desc*, const ptrec_feature_desc*, int32_t,
+                                              int32_t, int64_t, int32_t, const ptrec_feature_desc*, const ptrec_feature_desc*, int32_t,
                                               int64_t, const uint32_t*, const int32_t*,
                                               const int32_t*, const int32_t*, const int32_t*,
                                               const float*, int64_t, const float*,
                                               const ptrec_optim_args*, void*, size_t, void*);
-int ptrec_embedding_bwd_fused_lazy_adam(void* const*, void* const*, void* const*, int32_t, int32_t,
+int ptrec_embedding_bwd_fused_lazy_adam(void* const*, void* const*, void* const*, int32_t, int32_t, int64_t,
                                         int32_t, const ptrec_feature_desc*, const ptrec_feature_desc*, int32_t, int64_t,
                                         const uint32_t*, const int32_t*, const int32_t*,
                                         const int32_t*, const int32_t*, const float*, int64_t,

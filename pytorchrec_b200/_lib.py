@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libptrec_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # enums (mirror include/ptrec_b200.h)
 F32, BF16 = 0, 1
@@ -56,7 +56,7 @@ assert ctypes.sizeof(FeatureDesc) == 40
 assert ctypes.sizeof(OptimArgs) == 32
 
 _FD = POINTER(FeatureDesc)
-_BWD_ARGS = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, _FD, _FD, c_int32, c_int64,
+_BWD_ARGS = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int32, _FD, _FD, c_int32, c_int64,
              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
              POINTER(OptimArgs), c_void_p, c_size_t, c_void_p]
 
@@ -70,7 +70,7 @@ PROTOTYPES = {
     "ptrec_index_prep_workspace_bytes": (c_size_t, [c_int64]),
     "ptrec_index_prep": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
                                  c_void_p, c_size_t, c_void_p]),
-    "ptrec_embedding_gather_pool_fwd": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, _FD, _FD,
+    "ptrec_embedding_gather_pool_fwd": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int32, _FD, _FD,
                                                 c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                                 c_void_p, c_void_p, c_void_p]),
     "ptrec_sort_dedup_workspace_bytes": (c_size_t, [c_int64, c_int32]),

@@ -18,6 +18,7 @@ constexpr int kLongSeg = 32;
 constexpr int kOptNone = -1;  // segment-sum only
 
 struct OptParams {
+  int64_t row_stride;  // floats between consecutive rows of a table AND of its element-wise state
   float lr;         // already lr-decayed (Adagrad) / bias-corrected step size (Adam)
   float eps;
   float beta1;
@@ -54,8 +55,8 @@ struct RowState {
   float r;              // row-wise state
   __device__ __forceinline__ void clear() { w.zero(); a.zero(); b.zero(); r = 0.f; }
   __device__ __forceinline__ void load(const float* wrow, const float* s1, const float* s2, int64_t row,
-                                       int D, int lane, bool lane_on) {
-    const int64_t off = row * (int64_t)D + lane * VEC;
+                                       int64_t row_stride, int lane, bool lane_on) {
+    const int64_t off = row * row_stride + lane * VEC;
     clear();
     if constexpr (OPT == kOptNone) return;
     if (lane_on) w = load_row<VEC>(wrow + off);
@@ -73,7 +74,7 @@ __device__ __forceinline__ void apply_update(RowVec<VEC> g, const RowState<VEC, 
                                              float* __restrict__ s1, float* __restrict__ s2,
                                              int64_t row, int D, int lane, bool lane_on,
                                              const OptParams& op, float* row_grad_out) {
-  const int64_t off = row * (int64_t)D + lane * VEC;
+  const int64_t off = row * op.row_stride + lane * VEC;
   if constexpr (OPT == kOptNone) {
     if (lane_on) store_row<VEC>(row_grad_out + lane * VEC, g);
     return;
@@ -181,56 +182,91 @@ fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restric
   __shared__ SlotMap s_map;
   build_slot_map(&s_map, feats, F, T, B);
   constexpr int NSG = kUpdThreads / LPR;
+  constexpr int SEGS = 4;  // unique rows in flight per sub-warp: 4 x (weight + state + gradient) rows requested together
   const int sg = threadIdx.x / LPR, lane = threadIdx.x % LPR;
   const bool lane_on = lane * VEC < D;
   const int n_seg = *n_seg_ptr;
-  const int n_round = (n_seg + NSG - 1) / NSG;
+  const int n_round = (n_seg + NSG * SEGS - 1) / (NSG * SEGS);
   for (int r = blockIdx.x; r < n_round; r += gridDim.x) {
-    const int u = r * NSG + sg;
-    const bool live = u < n_seg;
-    int start = 0, end = 0, t = 0;
-    uint32_t key = kMaskedKey;
-    if (live) {
-      start = seg_start[u];
-      end = seg_start[u + 1];
-      t = seg_table[u];
-      key = sorted_keys[start];
-    }
-    const bool masked = key == kMaskedKey;
-    const bool is_long = live && !masked && (end - start) > kLongSeg && OPT != kOptNone;
-    if (is_long && lane == 0) long_list[atomicAdd(long_count, 1)] = u;
-    const bool work = live && !masked && !is_long;
-    float* wrow = nullptr;
-    float* s1 = nullptr;
-    float* s2 = nullptr;
-    RowState<VEC, OPT> st;
-    st.clear();
-    if (OPT != kOptNone && work) {
-      wrow = reinterpret_cast<float*>(table_ptrs[t]);
-      if (state1_ptrs) s1 = reinterpret_cast<float*>(state1_ptrs[t]);
-      if (state2_ptrs) s2 = reinterpret_cast<float*>(state2_ptrs[t]);
-      st.load(wrow, s1, s2, (int64_t)key, D, lane, lane_on);
-    }
-    RowVec<VEC> acc;
-    acc.zero();
-    if (work || (OPT == kOptNone && live && !masked)) {
-      for (int j0 = start; j0 < end; j0 += 4) {
-        RowVec<VEC> g[4];
+    int start[SEGS], end[SEGS], tab[SEGS];
+    uint32_t key[SEGS];
+    bool work[SEGS], live[SEGS];
+    // round 1: segment bounds + table (independent loads for all SEGS segments)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          g[q].zero();
-          if (j0 + q < end)
-            g[q] = slot_grad<VEC>(&s_map, t, B, perm[j0 + q], grad_out, stride, bag_scale, lane, lane_on);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc.add(g[q]);
+    for (int q = 0; q < SEGS; ++q) {
+      const int u = (r * SEGS + q) * NSG + sg;
+      live[q] = u < n_seg;
+      start[q] = end[q] = tab[q] = 0;
+      if (live[q]) {
+        start[q] = seg_start[u];
+        end[q] = seg_start[u + 1];
+        tab[q] = seg_table[u];
       }
     }
-    if constexpr (OPT == kOptNone) {
-      if (live) apply_update<VEC, LPR, OPT>(acc, st, nullptr, nullptr, nullptr, 0, D, lane, lane_on, op,
-                                            row_grad + (int64_t)u * D);
-    } else {
-      if (work) apply_update<VEC, LPR, OPT>(acc, st, wrow, s1, s2, (int64_t)key, D, lane, lane_on, op, nullptr);
+    // round 2: keys and first gradient slot
+    int32_t p0[SEGS];
+#pragma unroll
+    for (int q = 0; q < SEGS; ++q) {
+      key[q] = kMaskedKey;
+      p0[q] = 0;
+      if (live[q]) {
+        key[q] = sorted_keys[start[q]];
+        p0[q] = perm[start[q]];
+      }
+    }
+    // round 3: weight / state rows and the first gradient row of every segment
+    float* wrow[SEGS];
+    float* s1[SEGS];
+    float* s2[SEGS];
+    RowState<VEC, OPT> st[SEGS];
+    RowVec<VEC> acc[SEGS];
+#pragma unroll
+    for (int q = 0; q < SEGS; ++q) {
+      const int u = (r * SEGS + q) * NSG + sg;
+      const bool masked = key[q] == kMaskedKey;
+      const bool is_long = live[q] && !masked && (end[q] - start[q]) > kLongSeg && OPT != kOptNone;
+      if (is_long && lane == 0) long_list[atomicAdd(long_count, 1)] = u;
+      work[q] = live[q] && !masked && !is_long;
+      wrow[q] = s1[q] = s2[q] = nullptr;
+      st[q].clear();
+      acc[q].zero();
+      if (work[q]) {
+        if constexpr (OPT != kOptNone) {
+          wrow[q] = reinterpret_cast<float*>(table_ptrs[tab[q]]);
+          if (state1_ptrs) s1[q] = reinterpret_cast<float*>(state1_ptrs[tab[q]]);
+          if (state2_ptrs) s2[q] = reinterpret_cast<float*>(state2_ptrs[tab[q]]);
+          st[q].load(wrow[q], s1[q], s2[q], (int64_t)key[q], op.row_stride, lane, lane_on);
+        }
+        acc[q] = slot_grad<VEC>(&s_map, tab[q], B, p0[q], grad_out, stride, bag_scale, lane, lane_on);
+      }
+    }
+    // remaining gradient slots of longer segments (duplicates in the batch)
+#pragma unroll
+    for (int q = 0; q < SEGS; ++q) {
+      if (work[q]) {
+        for (int j0 = start[q] + 1; j0 < end[q]; j0 += 4) {
+          RowVec<VEC> g[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            g[x].zero();
+            if (j0 + x < end[q])
+              g[x] = slot_grad<VEC>(&s_map, tab[q], B, perm[j0 + x], grad_out, stride, bag_scale, lane, lane_on);
+          }
+#pragma unroll
+          for (int x = 0; x < 4; ++x) acc[q].add(g[x]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < SEGS; ++q) {
+      const int u = (r * SEGS + q) * NSG + sg;
+      if constexpr (OPT == kOptNone) {
+        if (live[q]) apply_update<VEC, LPR, OPT>(acc[q], st[q], nullptr, nullptr, nullptr, 0, D, lane, lane_on, op,
+                                                 row_grad + (int64_t)u * D);
+      } else {
+        if (work[q]) apply_update<VEC, LPR, OPT>(acc[q], st[q], wrow[q], s1[q], s2[q], (int64_t)key[q], D, lane, lane_on,
+                                                 op, nullptr);
+      }
     }
   }
 }
@@ -290,7 +326,7 @@ fused_update_long_kernel(void* const* __restrict__ table_ptrs, void* const* __re
       float* s1 = state1_ptrs ? reinterpret_cast<float*>(state1_ptrs[t]) : nullptr;
       float* s2 = state2_ptrs ? reinterpret_cast<float*>(state2_ptrs[t]) : nullptr;
       RowState<VEC, OPT> st;
-      st.load(wrow, s1, s2, (int64_t)key, D, lane, lane_on);
+      st.load(wrow, s1, s2, (int64_t)key, op.row_stride, lane, lane_on);
       apply_update<VEC, LPR, OPT>(tot, st, wrow, s1, s2, (int64_t)key, D, lane, lane_on, op, nullptr);
     }
     __syncthreads();
@@ -308,7 +344,7 @@ static int launch_update(void* const* table_ptrs, void* const* s1, void* const* 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t rounds = ceil_div(N, NSG);
+  const int64_t rounds = ceil_div(N, NSG * 4);
   const unsigned grid = (unsigned)(rounds < (int64_t)sms * 16 ? (rounds > 0 ? rounds : 1) : (int64_t)sms * 16);
   if (OPT != kOptNone) PTREC_CUDA(cudaMemsetAsync(long_count, 0, sizeof(int), st));
   fused_update_kernel<VEC, LPR, OPT><<<grid, kUpdThreads, 0, st>>>(
@@ -375,8 +411,8 @@ static int check_common(int32_t T, int32_t D, int32_t dtype, int32_t F, const vo
 }
 
 extern "C" int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* state1_ptrs,
-                                         void* const* state2_ptrs, int32_t T, int32_t D, int32_t dtype,
-                                         const ptrec_feature_desc* feats,
+                                         void* const* state2_ptrs, int32_t T, int32_t D, int64_t row_stride,
+                                         int32_t dtype, const ptrec_feature_desc* feats,
                                          const ptrec_feature_desc* feats_host, int32_t F, int64_t B,
                                          const uint32_t* sorted_keys, const int32_t* perm,
                                          const int32_t* seg_start, const int32_t* seg_table,
@@ -397,6 +433,8 @@ extern "C" int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* s
     PTREC_CHECK_ARG(feats_host[f].out_col % vec == 0, PTREC_EALIGN, "bwd_fused: feature %d out_col misaligned", f);
   }
   OptParams op;
+  PTREC_CHECK_ARG(row_stride >= D && row_stride % (D >= 4 ? 4 : D) == 0, PTREC_EALIGN, "bwd_fused: bad table row_stride");
+  op.row_stride = row_stride;
   op.eps = opt_host->eps;
   op.beta1 = opt_host->beta1;
   op.beta2 = opt_host->beta2;
@@ -436,13 +474,13 @@ extern "C" int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* s
 }
 
 #define PTREC_NAMED(NAME, KIND)                                                                          \
-  extern "C" int NAME(void* const* a, void* const* b, void* const* c, int32_t T, int32_t D, int32_t dt,  \
+  extern "C" int NAME(void* const* a, void* const* b, void* const* c, int32_t T, int32_t D, int64_t rs, int32_t dt, \
                       const ptrec_feature_desc* f, const ptrec_feature_desc* fh, int32_t F, int64_t B,   \
                       const uint32_t* k, const int32_t* p, const int32_t* s, const int32_t* st,          \
                       const int32_t* n, const float* g, int64_t gs, const float* bs,                     \
                       const ptrec_optim_args* o, void* ws, size_t wsb, void* stream) {                   \
     PTREC_CHECK_ARG(o && o->kind == KIND, PTREC_EINVAL, #NAME ": opt_host->kind must be " #KIND);        \
-    return ptrec_embedding_bwd_fused(a, b, c, T, D, dt, f, fh, F, B, k, p, s, st, n, g, gs, bs, o, ws,   \
+    return ptrec_embedding_bwd_fused(a, b, c, T, D, rs, dt, f, fh, F, B, k, p, s, st, n, g, gs, bs, o, ws, \
                                      wsb, stream);                                                        \
   }
 PTREC_NAMED(ptrec_embedding_bwd_fused_sgd, PTREC_OPT_SGD)

@@ -30,7 +30,7 @@ constexpr int kUnroll = 4;
 template <int VEC, int LPR>
 __global__ void __launch_bounds__(kOneHotThreads)
 gather_onehot_kernel(const void* const* __restrict__ table_ptrs, const int64_t* __restrict__ table_rows,
-                     int D, const ptrec_feature_desc* __restrict__ feats, FeatSel sel,
+                     int D, int64_t row_stride, const ptrec_feature_desc* __restrict__ feats, FeatSel sel,
                      const int64_t* __restrict__ ids, int64_t B, float* __restrict__ out,
                      int64_t out_row_stride, int32_t* err_flag, int use_bulk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -94,7 +94,7 @@ gather_onehot_kernel(const void* const* __restrict__ table_ptrs, const int64_t* 
         const int64_t id = s_ids[(size_t)s * kOneHotTileB + bl];
         dst[u] = out + (b0 + bl) * out_row_stride + s_col[s] + lane * VEC;
         if ((uint64_t)id < (uint64_t)s_rows[s]) {
-          if (lane_on) r[u] = load_row_stream<VEC>(s_tab[s] + id * (int64_t)D + lane * VEC);
+          if (lane_on) r[u] = load_row_stream<VEC>(s_tab[s] + id * row_stride + lane * VEC);
         } else if (err_flag != nullptr && lane == 0 && !(id < 0 && (s_flag[s] & PTREC_FEAT_NEG_IS_PAD))) {
           *err_flag = 1;
         }
@@ -115,7 +115,7 @@ constexpr int kBagStageMaxL = 2048;  // 4 * 2048 * 8 B = 64 KB of shared memory 
 template <int VEC, int LPR>
 __global__ void __launch_bounds__(kBagThreads)
 gather_bag_kernel(const void* const* __restrict__ table_ptrs, const int64_t* __restrict__ table_rows,
-                  int D, const ptrec_feature_desc* __restrict__ feats, FeatSel sel,
+                  int D, int64_t row_stride, const ptrec_feature_desc* __restrict__ feats, FeatSel sel,
                   const int64_t* __restrict__ ids, const int32_t* __restrict__ lens, int64_t B,
                   float* __restrict__ out, int64_t out_row_stride, float* __restrict__ bag_scale,
                   int32_t* err_flag, int ids_aligned16, int stage_cap_ids) {
@@ -188,7 +188,7 @@ gather_bag_kernel(const void* const* __restrict__ table_ptrs, const int64_t* __r
         if (valid) {
           ++count;
           if ((uint64_t)id < (uint64_t)rows) {
-            if (lane_on) r[u] = load_row_stream<VEC>(tab + id * (int64_t)D + lane * VEC);
+            if (lane_on) r[u] = load_row_stream<VEC>(tab + id * row_stride + lane * VEC);
           } else if (err_flag != nullptr && lane == 0) {
             *err_flag = 1;
           }
@@ -215,7 +215,7 @@ gather_bag_kernel(const void* const* __restrict__ table_ptrs, const int64_t* __r
 
 // ------------------------------------------------------------------------------------ dispatch
 template <int VEC, int LPR>
-static int launch_gather(const void* const* table_ptrs, const int64_t* table_rows, int D,
+static int launch_gather(const void* const* table_ptrs, const int64_t* table_rows, int D, int64_t row_stride,
                          const ptrec_feature_desc* feats, const FeatSel& onehot, const FeatSel& bags,
                          int max_bag_len, const int64_t* ids, const int32_t* lens, int64_t B,
                          float* out, int64_t out_row_stride, float* bag_scale, int32_t* err_flag,
@@ -226,7 +226,7 @@ static int launch_gather(const void* const* table_ptrs, const int64_t* table_row
     const size_t smem = (size_t)onehot.n * (kOneHotTileB * 8 + 8 + 8 + 8 + 8);
     const unsigned grid = (unsigned)ceil_div(B, kOneHotTileB);
     gather_onehot_kernel<VEC, LPR><<<grid, kOneHotThreads, smem, st>>>(
-        table_ptrs, table_rows, D, feats, onehot, ids, B, out, out_row_stride, err_flag, use_bulk);
+        table_ptrs, table_rows, D, row_stride, feats, onehot, ids, B, out, out_row_stride, err_flag, use_bulk);
     PTREC_LAUNCH_CHECK("gather_onehot_kernel");
   }
   if (bags.n > 0) {
@@ -238,7 +238,7 @@ static int launch_gather(const void* const* table_ptrs, const int64_t* table_row
     }
     dim3 grid((unsigned)ceil_div(B, kBagsPerCta), (unsigned)bags.n);
     gather_bag_kernel<VEC, LPR><<<grid, kBagThreads, smem, st>>>(
-        table_ptrs, table_rows, D, feats, bags, ids, lens, B, out, out_row_stride, bag_scale,
+        table_ptrs, table_rows, D, row_stride, feats, bags, ids, lens, B, out, out_row_stride, bag_scale,
         err_flag, ids_al, stage_L * kBagsPerCta);
     PTREC_LAUNCH_CHECK("gather_bag_kernel");
   }
@@ -334,7 +334,7 @@ extern "C" int ptrec_index_prep(const int64_t* ids_padded, const int32_t* lens, 
 }
 
 extern "C" int ptrec_embedding_gather_pool_fwd(const void* const* table_ptrs, const int64_t* table_rows,
-                                               int32_t T, int32_t D, int32_t dtype,
+                                               int32_t T, int32_t D, int64_t row_stride, int32_t dtype,
                                                const ptrec_feature_desc* feats,
                                                const ptrec_feature_desc* feats_host, int32_t F,
                                                const int64_t* ids, const int32_t* lens, int64_t B,
@@ -348,6 +348,8 @@ extern "C" int ptrec_embedding_gather_pool_fwd(const void* const* table_ptrs, co
   const bool d_ok = D == 1 || D == 2 || (D >= 4 && D <= 128 && D % 4 == 0);
   PTREC_CHECK_ARG(d_ok, PTREC_EUNSUPPORTED, "gather: D=%d unsupported (1, 2, or a multiple of 4 up to 128)", D);
   const int vec = D >= 4 ? 4 : D;
+  PTREC_CHECK_ARG(row_stride >= D && row_stride % vec == 0, PTREC_EALIGN, "gather: table row_stride %lld invalid for D=%d",
+                  (long long)row_stride, D);
   PTREC_CHECK_ARG(((uintptr_t)out % (vec * 4)) == 0 && (out_row_stride % vec) == 0, PTREC_EALIGN,
                   "gather: out / out_row_stride not aligned to %d bytes", vec * 4);
   if (B == 0) return PTREC_OK;
@@ -376,7 +378,7 @@ extern "C" int ptrec_embedding_gather_pool_fwd(const void* const* table_ptrs, co
   cudaStream_t st = (cudaStream_t)stream;
 
 #define PTREC_GATHER(V, P) \
-  return launch_gather<V, P>(table_ptrs, table_rows, D, feats, onehot, bags, max_bag_len, ids, lens, B, \
+  return launch_gather<V, P>(table_ptrs, table_rows, D, row_stride, feats, onehot, bags, max_bag_len, ids, lens, B, \
                              out, out_row_stride, bag_scale, err_flag, st)
   if (D == 1) PTREC_GATHER(1, 1);
   if (D == 2) PTREC_GATHER(2, 1);

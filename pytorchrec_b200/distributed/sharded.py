@@ -89,13 +89,13 @@ class _ShardedLookup(torch.autograd.Function):
         ops.a2a_scatter_rows(grad_out, ret_pos, B, F, D, mod.grad_scale, send_g)
         dist.all_to_all_single(recv_g, send_g, group=mod.group)                # [G_src, F, C, D]
         layout = mod.owner_layout(C)
-        tables = mod.egroup.table_set.refresh([t.weight.data for t in mod.egroup.tables])
-        srt = ops.sort_dedup(tables, layout, own_ids, None, C)
         bind = mod.egroup.binding()
         if bind is None:
             raise RuntimeError("row-wise sharded tables need a pytorchrec_b200.optim sparse optimizer")
         optimizer, group = bind
-        s1, s2, args = optimizer._fused_prepare(mod.egroup, group)
+        s1, s2, args = optimizer._fused_prepare(mod.egroup, group)  # may interleave weight | state: before pointers
+        tables = mod.egroup.table_set.refresh([t.weight.data for t in mod.egroup.tables])
+        srt = ops.sort_dedup(tables, layout, own_ids, None, C)
         ops.bwd_fused(tables, s1, s2, layout, C, srt, recv_g, None, args, grad_row_stride=D)
         return (None, None) + (None,) * len(mod.egroup.tables)
 

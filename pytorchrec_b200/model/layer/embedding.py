@@ -68,6 +68,11 @@ class EmbeddingGroup:
         return b
 
     def apply_backward(self, layout, ids, lens, bag_scale, batch, grad_out, shared=None):
+        bind = self.binding()
+        prepared = None
+        if bind is not None:
+            # may re-house the tables (weight | state interleaving) on first use: do it before taking pointers
+            prepared = bind[0]._fused_prepare(self, bind[1])
         tables = self.table_set.refresh([w.data for w in self.weights()])
         # modules reading the same columns (e.g. FM's embedding and first-order tables) share one sort
         srt = shared.get("sort") if shared is not None else None
@@ -75,10 +80,8 @@ class EmbeddingGroup:
             srt = ops.sort_dedup(tables, layout, ids, lens, batch)
             if shared is not None:
                 shared["sort"] = srt
-        bind = self.binding()
         if bind is not None:
-            optimizer, group = bind
-            s1, s2, args = optimizer._fused_prepare(self, group)
+            s1, s2, args = prepared
             ops.bwd_fused(tables, s1, s2, layout, batch, srt, grad_out, bag_scale, args)
             return [None] * len(self.tables)
         # stock-optimizer mode: coalesced sparse gradients (one host sync for the segment count)

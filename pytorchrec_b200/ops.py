@@ -126,18 +126,25 @@ class TableSet:
         self.ptrs = None
         self.rows = None
         self.max_rows = 0
+        self.row_stride = 0
 
     def refresh(self, weights: Sequence[torch.Tensor]):
-        key = tuple(w.data_ptr() for w in weights)
+        key = tuple((w.data_ptr(), w.stride(0)) for w in weights)
         if key != self._key:
             dev = weights[0].device
+            stride = weights[0].stride(0) if weights[0].shape[0] > 1 else weights[0].shape[1]
             for w in weights:
                 _require_cuda(w)
-                if w.dtype != torch.float32 or not w.is_contiguous() or w.device != dev:
-                    raise RuntimeError("embedding tables must be contiguous fp32 CUDA tensors on one device")
-                if w.data_ptr() % 16 != 0:
-                    raise RuntimeError("embedding table base pointer must be 16-byte aligned")
-            self.ptrs = torch.tensor(list(key), dtype=torch.int64).to(dev)
+                if w.dtype != torch.float32 or w.dim() != 2 or w.stride(1) != 1 or w.device != dev:
+                    raise RuntimeError("embedding tables must be fp32 [rows, D] CUDA tensors with unit inner stride on one device")
+                if w.shape[0] > 1 and w.stride(0) != stride:
+                    raise RuntimeError("all tables of one embedding group must share the same row stride "
+                                       "(all plain, or all interleaved with their optimizer state)")
+                align = 16 if w.shape[1] >= 4 else 4 * w.shape[1]
+                if w.data_ptr() % align != 0:
+                    raise RuntimeError("embedding table base pointer is misaligned")
+            self.row_stride = int(stride)
+            self.ptrs = torch.tensor([w.data_ptr() for w in weights], dtype=torch.int64).to(dev)
             self.rows = torch.tensor([w.shape[0] for w in weights], dtype=torch.int64).to(dev)
             self.max_rows = max(w.shape[0] for w in weights)
             self._key = key
@@ -169,7 +176,7 @@ def gather_pool_fwd(tables: TableSet, layout: FeatureLayout, ids: torch.Tensor,
 def _gather_call(lib, tables, layout, ids, lens, batch, out, bag_scale, err_flag, dev, row_stride):
     feats_dev = layout.device_array(dev)
     return lib.ptrec_embedding_gather_pool_fwd(
-        _ptr(tables.ptrs), _ptr(tables.rows), layout.n_tables, layout.dim, _lib.F32,
+        _ptr(tables.ptrs), _ptr(tables.rows), layout.n_tables, layout.dim, tables.row_stride or layout.dim, _lib.F32,
         ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)), layout.host,
         layout.n_features, _ptr(ids), _ptr(lens), batch, _ptr(out), row_stride, _ptr(bag_scale),
         _ptr(err_flag), _stream(dev))
@@ -227,7 +234,7 @@ def bwd_fused(tables: TableSet, state1_ptrs: Optional[torch.Tensor], state2_ptrs
     feats_dev = layout.device_array(dev)
     fn = getattr(lib, _BWD_FN[opt.kind])
     _lib.check(fn(_ptr(tables.ptrs), _ptr(state1_ptrs), _ptr(state2_ptrs), layout.n_tables, layout.dim,
-                  _lib.F32, ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)),
+                  tables.row_stride or layout.dim, _lib.F32, ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)),
                   layout.host, layout.n_features, batch, _ptr(srt.sorted_keys), _ptr(srt.perm),
                   _ptr(srt.seg_start), _ptr(srt.seg_table), _ptr(srt.n_seg), _ptr(grad_out),
                   grad_row_stride, _ptr(bag_scale), ctypes.byref(opt), _ptr(ws), ws.numel(),

@@ -50,10 +50,39 @@ class _FusedSparseOptimizer(Optimizer):
         self._dense_spec = (dense_cls, dense_groups, dense_kwargs) if dense_groups else None
         self._step_count_fused = 0
         self._ptr_cache: Dict[int, tuple] = {}
+        self._interleaved: Dict[int, torch.Tensor] = {}  # id(param) -> [rows, stride] buffer holding weight | state
 
     def graph_safe(self) -> bool:
         """True when a captured step stays valid on replay (no host-side step count in the arithmetic)."""
         return False
+
+    def _interleave(self, p: torch.Tensor, names, fills, slots: int) -> None:
+        """Re-house table ``p`` and its element-wise state in ONE ``[rows, slots*D]`` buffer (weight in columns
+        [0, D), state k in [k*D, (k+1)*D)).  On B200 a random row access costs a full 128-byte DRAM line whatever the
+        row size (profiles/r1_ubench_dram_granularity.csv), so keeping a 64-byte weight row and its 64-byte state row
+        in the same line halves the row traffic of the fused update.  ``p.data`` becomes a strided view of the
+        buffer; ``state[p][name]`` are views too, so state_dict / load_state_dict keep working."""
+        st = self.state[p]
+        D = p.shape[1]
+        buf = self._interleaved.get(id(p))
+        ok = (buf is not None and buf.device == p.device and p.data.data_ptr() == buf.data_ptr()
+              and all(n in st and st[n].data_ptr() == buf.data_ptr() + 4 * D * (k + 1) for k, n in enumerate(names)))
+        if ok:
+            return
+        new = torch.empty(p.shape[0], slots * D, dtype=torch.float32, device=p.device)
+        new[:, :D].copy_(p.data)
+        for k, (n, fill) in enumerate(zip(names, fills)):
+            view = new[:, (k + 1) * D:(k + 2) * D]
+            if n in st and st[n].shape == view.shape:
+                view.copy_(st[n].to(p.device))
+            else:
+                view.fill_(fill)
+            st[n] = view
+        if slots > len(names) + 1:
+            new[:, (len(names) + 1) * D:].zero_()
+        p.data = new[:, :D]
+        self._interleaved[id(p)] = new
+        self._ptr_cache.clear()
 
     # ---- called by EmbeddingGroup.apply_backward -------------------------------------------------
     def _state_tensors(self, p: torch.Tensor):
@@ -74,6 +103,7 @@ class _FusedSparseOptimizer(Optimizer):
                 s1.append(a)
                 s2.append(b)
             dev = weights[0].device
+            key = tuple(w.data_ptr() for w in weights)  # _state_tensors may have re-housed the tables
             p1 = torch.tensor([t.data_ptr() for t in s1], dtype=torch.int64).to(dev) if self.N_STATE >= 1 else None
             p2 = torch.tensor([t.data_ptr() for t in s2], dtype=torch.int64).to(dev) if self.N_STATE >= 2 else None
             cached = (key, p1, p2)
@@ -145,24 +175,30 @@ class SparseAdagrad(_FusedSparseOptimizer):
     KIND = _lib.OPT_ADAGRAD
     N_STATE = 1
 
-    def __init__(self, params, lr=1e-2, lr_decay=0.0, weight_decay=0.0, initial_accumulator_value=0.0, eps=1e-10):
+    def __init__(self, params, lr=1e-2, lr_decay=0.0, weight_decay=0.0, initial_accumulator_value=0.0, eps=1e-10,
+                 interleave: bool = True):
         if lr < 0.0:
             raise ValueError(f"Invalid learning rate: {lr}")
         defaults = dict(lr=lr, lr_decay=lr_decay, weight_decay=weight_decay,
                         initial_accumulator_value=initial_accumulator_value, eps=eps)
+        self.interleave = interleave
         super().__init__(params, defaults, torch.optim.Adagrad, dict(defaults))
 
     def graph_safe(self):
         return all(g["lr_decay"] == 0 for g in self.param_groups)
 
+    def _init_acc(self, p):
+        for g in self.param_groups:
+            if any(q is p for q in g["params"]):
+                return g["initial_accumulator_value"]
+        return 0.0
+
     def _state_tensors(self, p):
         st = self.state[p]
-        if "sum" not in st or st["sum"].device != p.device:
-            init = 0.0
-            for g in self.param_groups:
-                if any(q is p for q in g["params"]):
-                    init = g["initial_accumulator_value"]
-            st["sum"] = torch.full_like(p.data, init) if "sum" not in st else st["sum"].to(p.device)
+        if self.interleave and type(self) is SparseAdagrad:
+            self._interleave(p, ["sum"], [self._init_acc(p)], slots=2)
+        elif "sum" not in st or st["sum"].device != p.device:
+            st["sum"] = torch.full_like(p.data, self._init_acc(p)) if "sum" not in st else st["sum"].to(p.device)
         return st["sum"], None
 
     def _optim_args(self, group):
@@ -193,16 +229,20 @@ class SparseAdam(_FusedSparseOptimizer):
     KIND = _lib.OPT_LAZY_ADAM
     N_STATE = 2
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, interleave: bool = True):
         if lr < 0.0:
             raise ValueError(f"Invalid learning rate: {lr}")
         if not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0:
             raise ValueError(f"Invalid betas: {betas}")
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self.interleave = interleave
         super().__init__(params, defaults, torch.optim.Adam, dict(defaults))
 
     def _state_tensors(self, p):
         st = self.state[p]
+        if self.interleave:
+            self._interleave(p, ["exp_avg", "exp_avg_sq"], [0.0, 0.0], slots=4)  # w | m | v | pad: 2 lines at D=16
+            return st["exp_avg"], st["exp_avg_sq"]
         for k in ("exp_avg", "exp_avg_sq"):
             if k not in st:
                 st[k] = torch.zeros_like(p.data)
