@@ -7,11 +7,16 @@
 // Bound: bf16 tensor pipe.  FLOPs per launch = 2*B*d*d; the epilogue streams 3-4 [B, d] bf16 tiles, so the layer
 // sits near the ridge (AI ~ 300 FLOP/B) — the elementwise work is fused into the GEMM epilogue to stay on it.
 //
-// One CTA computes a 128 x 128 output tile: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
-// tcgen05.mma issuer (one elected lane), warps 2-5 = epilogue (tcgen05.ld 32x32b -> registers -> fused math ->
-// 16-byte global stores).  Operands are K-major 128B-swizzled tiles of 128 rows x 64 bf16 filled by
-// cp.async.bulk.tensor.2d and described to the MMA by shared-memory matrix descriptors; a 4-stage full/empty
-// mbarrier ring overlaps TMA with MMA; tcgen05.commit releases stages and publishes the accumulator.
+// Persistent kernel, one CTA per SM walking 128 x 128 output tiles (n fastest, so concurrently running CTAs share
+// the A row-panel in L2).  Warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + tcgen05.mma issuer
+// (one elected lane), warps 2-5 = epilogue.  Three pipelines:
+//   * operand ring: 4 stages of K-major 128B-swizzled tiles (128 rows x 64 bf16 for A and for B) filled by
+//     cp.async.bulk.tensor.2d, described to the MMA by shared-memory matrix descriptors, released by tcgen05.commit;
+//   * accumulator double buffer: 2 x 128 TMEM columns, so the MMAs of tile i+1 run while tile i is drained;
+//   * epilogue staging: the two [128 x 128] bf16 epilogue operands (x0 / x_l, or g_out / x0) are TMA-loaded into
+//     shared memory while the MMAs run; the epilogue warps tcgen05.ld the accumulator, read the operands from the
+//     swizzled tiles (conflict-free), write both results back in place and one thread TMA-stores them
+//     (cp.async.bulk.tensor.2d.global.shared), so every global access of the epilogue is a full coalesced tile.
 // Every mbarrier wait is bounded (trap instead of hang).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -20,11 +25,14 @@
 
 namespace ptrec {
 
-constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 3, kUmmaK = 16;
+constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 4, kUmmaK = 16;
 constexpr int kGemmThreads = 192;
 constexpr uint32_t kStageBytesA = kBM * kBK * 2, kStageBytesB = kBN * kBK * 2;
-constexpr uint32_t kTmemCols = 128;
-constexpr size_t kGemmSmem = (size_t)kStages * (kStageBytesA + kStageBytesB) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kTmemCols = 256;                      // two 128-column accumulators
+constexpr uint32_t kEpiSubTile = kBM * 64 * 2;           // 128 rows x 64 bf16, one 128B-swizzled box (16 KB)
+constexpr uint32_t kEpiOperand = 2 * kEpiSubTile;        // [128 x 128] bf16
+constexpr size_t kGemmSmem = (size_t)kStages * (kStageBytesA + kStageBytesB) + 2 * kEpiOperand + 1024 /*align*/ +
+                             256 /*barriers*/;
 
 enum EpiMode : int { EPI_F32 = 0, EPI_CROSS_FWD = 1, EPI_CROSS_DGRAD = 2 };
 
@@ -106,29 +114,52 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float* f) {
 }
 
 // ---- the GEMM: C[M, N] = A[M, K] * B[N, K]^T, fused epilogue ---------------------------------------------------
-__global__ void __launch_bounds__(kGemmThreads, 2)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                    int K, EpiArgs ep) {
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+struct GemmMaps {
+  CUtensorMap a, b;        // mainloop operands
+  CUtensorMap p0, p1;      // epilogue operands (loaded)
+  CUtensorMap o0, o1;      // epilogue results (stored)
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, EpiArgs ep) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;
   unsigned char* sB = smem + (size_t)kStages * kStageBytesA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * (kStageBytesA + kStageBytesB));
-  uint64_t* full = bars;                 // [kStages]
-  uint64_t* empty = bars + kStages;      // [kStages]
-  uint64_t* acc_full = bars + 2 * kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  unsigned char* sE0 = smem + (size_t)kStages * (kStageBytesA + kStageBytesB);  // operand 0 / result 0
+  unsigned char* sE1 = sE0 + kEpiOperand;                                       // operand 1 / result 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sE1 + kEpiOperand);
+  uint64_t* full = bars;                      // [kStages]
+  uint64_t* empty = bars + kStages;           // [kStages]
+  uint64_t* acc_full = bars + 2 * kStages;    // [2]
+  uint64_t* acc_empty = acc_full + 2;         // [2]
+  uint64_t* epi_full = acc_empty + 2;         // [1]
+  uint64_t* epi_empty = epi_full + 1;         // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+  const int tiles_n = (N + kBN - 1) / kBN, tiles_m = (M + kBM - 1) / kBM;
+  const int n_tiles = tiles_n * tiles_m;
   const int num_kb = (K + kBK - 1) / kBK;
+  const bool staged_epi = ep.mode != EPI_F32;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(acc_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+    }
+    mbar_init(epi_full, 1);
+    mbar_init(epi_empty, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -144,80 +175,131 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        mbar_wait(&empty[s], ((kb / kStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[s], kStageBytesA + kStageBytesB);
-        tma_load_2d(sA + (size_t)s * kStageBytesA, &tmA, kb * kBK, m0, &full[s]);
-        tma_load_2d(sB + (size_t)s * kStageBytesB, &tmB, kb * kBK, n0, &full[s]);
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b) : "memory");
+      int kbg = 0;  // global k-block counter (ring position)
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * kBN;
+        const int epi_at = num_kb / 2;  // epilogue operands are requested half-way through the K loop
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const int s = kbg % kStages;
+          mbar_wait(&empty[s], ((kbg / kStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[s], kStageBytesA + kStageBytesB);
+          tma_load_2d(sA + (size_t)s * kStageBytesA, &maps.a, kb * kBK, m0, &full[s]);
+          tma_load_2d(sB + (size_t)s * kStageBytesB, &maps.b, kb * kBK, n0, &full[s]);
+          if (staged_epi && kb == epi_at) {
+            mbar_wait(epi_empty, (it & 1) ^ 1);  // previous tile's results have left shared memory
+            mbar_arrive_expect_tx(epi_full, 2 * kEpiOperand);
+            tma_load_2d(sE0, &maps.p0, n0, m0, epi_full);
+            tma_load_2d(sE0 + kEpiSubTile, &maps.p0, n0 + 64, m0, epi_full);
+            tma_load_2d(sE1, &maps.p1, n0, m0, epi_full);
+            tma_load_2d(sE1 + kEpiSubTile, &maps.p1, n0 + 64, m0, epi_full);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        mbar_wait(&full[s], (kb / kStages) & 1);
+      int kbg = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint64_t adesc = make_sw128_desc(sA + (size_t)s * kStageBytesA);
-        const uint64_t bdesc = make_sw128_desc(sB + (size_t)s * kStageBytesB);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kBN);
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const int s = kbg % kStages;
+          mbar_wait(&full[s], (kbg / kStages) & 1);
+          tcgen05_fence_after();
+          const uint64_t adesc = make_sw128_desc(sA + (size_t)s * kStageBytesA);
+          const uint64_t bdesc = make_sw128_desc(sB + (size_t)s * kStageBytesB);
 #pragma unroll
-        for (int k = 0; k < kBK / kUmmaK; ++k) {
-          // +32 bytes per K=16 slice inside the 128-byte swizzled row (start-address field is in 16-byte units)
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            // +32 bytes per K=16 slice inside the 128-byte swizzled row (start-address field is in 16-byte units)
+            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);      // frees the stage once the MMAs that read it retire
         }
-        umma_commit(&empty[s]);  // frees the stage once the MMAs that read it retire
+        umma_commit(&acc_full[buf]);   // accumulator complete
       }
-      umma_commit(acc_full);     // accumulator complete
     }
   } else {
     // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
     const int q = warp & 3;
-    mbar_wait(acc_full, 0);
-    tcgen05_fence_after();
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < M;
-#pragma unroll 2
-    for (int c = 0; c < kBN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      const int col0 = n0 + c * 32;
-      if (!row_ok || col0 >= N) continue;
-      if (ep.mode == EPI_F32) {
-        float* o = ep.of32 + (int64_t)row * ep.ldf + col0;
+    const int r = q * 32 + lane;  // row inside the tile
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * kBN;
+      const int buf = it & 1;
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tcgen05_fence_after();
+      if (staged_epi) mbar_wait(epi_full, it & 1);
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kBN);
+      const int row = m0 + r;
+#pragma unroll 1
+      for (int c = 0; c < kBN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tacc + (uint32_t)(c * 32), v);
+        const int col0 = n0 + c * 32;
+        if (!staged_epi) {
+          if (row < M && col0 < N) {
+            float* o = ep.of32 + (int64_t)row * ep.ldf + col0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (col0 + j < N) {
-            *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                             __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            for (int j = 0; j < 32; j += 4) {
+              if (col0 + j < N) {
+                *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                 __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const int g = c * 4 + (j >> 3);  // 8-column group inside the 128-wide tile
+            const uint32_t off = (uint32_t)(g >> 3) * kEpiSubTile + (uint32_t)r * 128u + (uint32_t)(((g & 7) ^ (r & 7)) << 4);
+            float a[8], b[8], r0[8], r1[8];
+            load_bf16x8(reinterpret_cast<const __nv_bfloat16*>(sE0 + off), a);
+            load_bf16x8(reinterpret_cast<const __nv_bfloat16*>(sE1 + off), b);
+            if (ep.mode == EPI_CROSS_FWD) {
+              float bias8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bias8[i] = (ep.bias && col0 + j + i < N) ? ep.bias[col0 + j + i] : 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float u = __uint_as_float(v[j + i]) + bias8[i];
+                r1[i] = u;                 // u          -> result 1
+                r0[i] = a[i] * u + b[i];   // x0*u + x_l -> result 0
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float gx = __uint_as_float(v[j + i]) + a[i];  // g_u W + g_out -> result 0
+                r0[i] = gx;
+                r1[i] = gx * b[i];                                  // g_x (.) x0    -> result 1
+              }
+            }
+            store_bf16x8(reinterpret_cast<__nv_bfloat16*>(sE0 + off), r0);
+            store_bf16x8(reinterpret_cast<__nv_bfloat16*>(sE1 + off), r1);
           }
         }
-      } else {
-        const int64_t off = (int64_t)row * ep.ld + col0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          if (col0 + j >= N) break;
-          float a[8], b[8], r0[8], r1[8];
-          load_bf16x8(ep.p0 + off + j, a);
-          load_bf16x8(ep.p1 + off + j, b);
-          if (ep.mode == EPI_CROSS_FWD) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float u = __uint_as_float(v[j + i]) + (ep.bias ? ep.bias[col0 + j + i] : 0.f);
-              r1[i] = u;
-              r0[i] = a[i] * u + b[i];  // x0 * u + x_l
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float gx = __uint_as_float(v[j + i]) + a[i];  // g_u W + g_out
-              r0[i] = gx;
-              r1[i] = gx * b[i];                                  // next layer's g_u = g_x (.) x0
-            }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (staged_epi) {
+        fence_proxy_async();                                  // generic-proxy writes -> visible to the TMA store
+        asm volatile("bar.sync 1, 128;" ::: "memory");        // the 4 epilogue warps
+        if (threadIdx.x == 64) {
+          tma_store_2d(&maps.o0, sE0, n0, m0);
+          if (n0 + 64 < N) tma_store_2d(&maps.o0, sE0 + kEpiSubTile, n0 + 64, m0);
+          if (ep.o1) {
+            tma_store_2d(&maps.o1, sE1, n0, m0);
+            if (n0 + 64 < N) tma_store_2d(&maps.o1, sE1 + kEpiSubTile, n0 + 64, m0);
           }
-          store_bf16x8(ep.o0 + off + j, r0);
-          if (ep.o1) store_bf16x8(ep.o1 + off + j, r1);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may be overwritten
+          mbar_arrive(epi_empty);
         }
       }
     }
@@ -283,18 +365,30 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, i
   PTREC_CHECK_ARG(aligned16(A) && aligned16(B) && lda % 8 == 0 && ldb % 8 == 0, PTREC_EALIGN,
                   "gemm: operands must be 16-byte aligned with pitches that are multiples of 8 elements");
   PTREC_CHECK_ARG(M > 0 && N > 0 && K > 0 && N % 8 == 0, PTREC_EINVAL, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
-  CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, A, M, K, lda);
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc = make_map(&maps.a, A, M, K, lda);
   if (rc != PTREC_OK) return rc;
-  rc = make_map(&tmB, B, N, K, ldb);
+  rc = make_map(&maps.b, B, N, K, ldb);
   if (rc != PTREC_OK) return rc;
+  if (ep.mode != EPI_F32) {
+    // epilogue operands / results are [M, N] bf16 with pitch ep.ld; box = 64 columns x 128 rows, 128B swizzle
+    if ((rc = make_map(&maps.p0, ep.p0, M, N, ep.ld)) != PTREC_OK) return rc;
+    if ((rc = make_map(&maps.p1, ep.p1, M, N, ep.ld)) != PTREC_OK) return rc;
+    if ((rc = make_map(&maps.o0, ep.o0, M, N, ep.ld)) != PTREC_OK) return rc;
+    if ((rc = make_map(&maps.o1, ep.o1 ? ep.o1 : ep.o0, M, N, ep.ld)) != PTREC_OK) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     PTREC_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     attr_set = true;
   }
-  dim3 grid((unsigned)ceil_div(N, kBN), (unsigned)ceil_div(M, kBM));
-  gemm_bf16_tn_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, M, N, K, ep);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = ceil_div(N, kBN) * ceil_div(M, kBM);
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  gemm_bf16_tn_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(maps, M, N, K, ep);
   PTREC_LAUNCH_CHECK("gemm_bf16_tn_kernel");
   return PTREC_OK;
 }
