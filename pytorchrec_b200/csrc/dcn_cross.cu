@@ -26,13 +26,14 @@
 namespace ptrec {
 
 constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 4, kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;                              // 2 per TMEM lane quadrant (column halves)
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kStageBytesA = kBM * kBK * 2, kStageBytesB = kBN * kBK * 2;
 constexpr uint32_t kTmemCols = 256;                      // two 128-column accumulators
 constexpr uint32_t kEpiSubTile = kBM * 64 * 2;           // 128 rows x 64 bf16, one 128B-swizzled box (16 KB)
 constexpr uint32_t kEpiOperand = 2 * kEpiSubTile;        // [128 x 128] bf16
 constexpr size_t kGemmSmem = (size_t)kStages * (kStageBytesA + kStageBytesB) + 2 * kEpiOperand + 1024 /*align*/ +
-                             256 /*barriers*/;
+                             1024 /*barriers + bias slice*/;
 
 enum EpiMode : int { EPI_F32 = 0, EPI_CROSS_FWD = 1, EPI_CROSS_DGRAD = 2 };
 
@@ -142,6 +143,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, 
   uint64_t* epi_full = acc_empty + 2;         // [1]
   uint64_t* epi_empty = epi_full + 1;         // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_empty + 1);
+  float* s_bias = reinterpret_cast<float*>(bars + 16);       // [kBN] bias slice of the current tile (16-byte aligned)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (N + kBN - 1) / kBN, tiles_m = (M + kBM - 1) / kBM;
@@ -156,7 +158,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+      mbar_init(&acc_empty[b], kEpiWarps);  // one arrival per epilogue warp
     }
     mbar_init(epi_full, 1);
     mbar_init(epi_empty, 1);
@@ -224,73 +226,77 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, 
       }
     }
   } else {
-    // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32); two warps share a quadrant and split the columns
+    const int e = warp - 2;            // 0 .. kEpiWarps-1
     const int q = warp & 3;
-    const int r = q * 32 + lane;  // row inside the tile
+    const int half = e >> 2;           // which 64-column half of the tile this warp drains
+    const int r = q * 32 + lane;       // row inside the tile
+    const int et = threadIdx.x - 64;   // 0 .. 32*kEpiWarps-1
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * kBN;
       const int buf = it & 1;
+      if (ep.mode == EPI_CROSS_FWD) {
+        if (et < kBN) s_bias[et] = (ep.bias && n0 + et < N) ? ep.bias[n0 + et] : 0.f;
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      }
       mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tcgen05_fence_after();
       if (staged_epi) mbar_wait(epi_full, it & 1);
-      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kBN);
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kBN + half * 64);
       const int row = m0 + r;
-#pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tacc + (uint32_t)(c * 32), v);
-        const int col0 = n0 + c * 32;
-        if (!staged_epi) {
-          if (row < M && col0 < N) {
-            float* o = ep.of32 + (int64_t)row * ep.ldf + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < N) {
-                *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                 __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const int g = c * 4 + (j >> 3);  // 8-column group inside the 128-wide tile
-            const uint32_t off = (uint32_t)(g >> 3) * kEpiSubTile + (uint32_t)r * 128u + (uint32_t)(((g & 7) ^ (r & 7)) << 4);
-            float a[8], b[8], r0[8], r1[8];
-            load_bf16x8(reinterpret_cast<const __nv_bfloat16*>(sE0 + off), a);
-            load_bf16x8(reinterpret_cast<const __nv_bfloat16*>(sE1 + off), b);
-            if (ep.mode == EPI_CROSS_FWD) {
-              float bias8[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) bias8[i] = (ep.bias && col0 + j + i < N) ? ep.bias[col0 + j + i] : 0.f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float u = __uint_as_float(v[j + i]) + bias8[i];
-                r1[i] = u;                 // u          -> result 1
-                r0[i] = a[i] * u + b[i];   // x0*u + x_l -> result 0
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float gx = __uint_as_float(v[j + i]) + a[i];  // g_u W + g_out -> result 0
-                r0[i] = gx;
-                r1[i] = gx * b[i];                                  // g_x (.) x0    -> result 1
-              }
-            }
-            store_bf16x8(reinterpret_cast<__nv_bfloat16*>(sE0 + off), r0);
-            store_bf16x8(reinterpret_cast<__nv_bfloat16*>(sE1 + off), r1);
-          }
-        }
-      }
-      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      uint32_t v[64];
+      tmem_ld32(tacc, v);
+      tmem_ld32(tacc + 32, v + 32);
+      // accumulator columns are in registers: hand the TMEM buffer back to the MMA warp right away
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      if (staged_epi) {
-        fence_proxy_async();                                  // generic-proxy writes -> visible to the TMA store
-        asm volatile("bar.sync 1, 128;" ::: "memory");        // the 4 epilogue warps
-        if (threadIdx.x == 64) {
+      if (!staged_epi) {
+        const int col0 = n0 + half * 64;
+        if (row < M && col0 < N) {
+          float* o = ep.of32 + (int64_t)row * ep.ldf + col0;
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            if (col0 + j < N) {
+              *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            }
+          }
+        }
+      } else {
+        unsigned char* e0 = sE0 + (size_t)half * kEpiSubTile + (size_t)r * 128u;
+        unsigned char* e1 = sE1 + (size_t)half * kEpiSubTile + (size_t)r * 128u;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {  // 8-column groups of this warp's 64-column half
+          const uint32_t off = (uint32_t)((g ^ (r & 7)) << 4);
+          float a[8], b[8], r0[8], r1[8];
+          load_bf16x8(reinterpret_cast<const __nv_bfloat16*>(e0 + off), a);
+          load_bf16x8(reinterpret_cast<const __nv_bfloat16*>(e1 + off), b);
+          if (ep.mode == EPI_CROSS_FWD) {
+            const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[half * 64 + g * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[half * 64 + g * 8 + 4]);
+            const float bias8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float u = __uint_as_float(v[g * 8 + i]) + bias8[i];
+              r1[i] = u;                 // u          -> result 1
+              r0[i] = a[i] * u + b[i];   // x0*u + x_l -> result 0
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float gx = __uint_as_float(v[g * 8 + i]) + a[i];  // g_u W + g_out -> result 0
+              r0[i] = gx;
+              r1[i] = gx * b[i];                                      // g_x (.) x0    -> result 1
+            }
+          }
+          store_bf16x8(reinterpret_cast<__nv_bfloat16*>(e0 + off), r0);
+          store_bf16x8(reinterpret_cast<__nv_bfloat16*>(e1 + off), r1);
+        }
+        fence_proxy_async();                                              // generic-proxy writes -> visible to the TMA store
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");  // all epilogue warps
+        if (et == 0) {
           tma_store_2d(&maps.o0, sE0, n0, m0);
           if (n0 + 64 < N) tma_store_2d(&maps.o0, sE0 + kEpiSubTile, n0 + 64, m0);
           if (ep.o1) {
