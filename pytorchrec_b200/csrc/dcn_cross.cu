@@ -45,8 +45,9 @@ struct EpiArgs {
   const float* bias;           // CROSS_FWD: bias[N] (may be null)
   __nv_bfloat16* o0;           // CROSS_FWD: out      CROSS_DGRAD: g_x
   __nv_bfloat16* o1;           // CROSS_FWD: u (null = skip)   CROSS_DGRAD: g_x (.) x0 (null = skip)
-  float* of32;                 // EPI_F32: fp32 output [M, ldf]
+  float* of32;                 // EPI_F32: fp32 output [splits][M, ldf] (split-K partials)
   int64_t ldf;
+  int splits;                  // EPI_F32 only: K is cut into `splits` ranges, one output slab each (>= 1)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -147,8 +148,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (N + kBN - 1) / kBN, tiles_m = (M + kBM - 1) / kBM;
-  const int n_tiles = tiles_n * tiles_m;
-  const int num_kb = (K + kBK - 1) / kBK;
+  const int splits = ep.mode == EPI_F32 ? max(ep.splits, 1) : 1;
+  const int mn_tiles = tiles_n * tiles_m;
+  const int n_tiles = mn_tiles * splits;
+  const int total_kb = (K + kBK - 1) / kBK;
+  const int kb_per_split = (total_kb + splits - 1) / splits;
   const bool staged_epi = ep.mode != EPI_F32;
 
   if (threadIdx.x == 0) {
@@ -182,14 +186,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, 
       int kbg = 0;  // global k-block counter (ring position)
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * kBN;
+        const int mn = tile % mn_tiles, split = tile / mn_tiles;
+        const int m0 = (mn / tiles_n) * kBM, n0 = (mn % tiles_n) * kBN;
+        const int kb0 = split * kb_per_split, num_kb = max(0, min(total_kb - kb0, kb_per_split));
         const int epi_at = num_kb / 2;  // epilogue operands are requested half-way through the K loop
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const int s = kbg % kStages;
           mbar_wait(&empty[s], ((kbg / kStages) & 1) ^ 1);
           mbar_arrive_expect_tx(&full[s], kStageBytesA + kStageBytesB);
-          tma_load_2d(sA + (size_t)s * kStageBytesA, &maps.a, kb * kBK, m0, &full[s]);
-          tma_load_2d(sB + (size_t)s * kStageBytesB, &maps.b, kb * kBK, n0, &full[s]);
+          tma_load_2d(sA + (size_t)s * kStageBytesA, &maps.a, (kb0 + kb) * kBK, m0, &full[s]);
+          tma_load_2d(sB + (size_t)s * kStageBytesB, &maps.b, (kb0 + kb) * kBK, n0, &full[s]);
           if (staged_epi && kb == epi_at) {
             mbar_wait(epi_empty, (it & 1) ^ 1);  // previous tile's results have left shared memory
             mbar_arrive_expect_tx(epi_full, 2 * kEpiOperand);
@@ -209,6 +215,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, 
         mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kBN);
+        const int kb0 = (tile / mn_tiles) * kb_per_split, num_kb = max(0, min(total_kb - kb0, kb_per_split));
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const int s = kbg % kStages;
           mbar_wait(&full[s], (kbg / kStages) & 1);
@@ -234,7 +241,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, 
     const int et = threadIdx.x - 64;   // 0 .. 32*kEpiWarps-1
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * kBN;
+      const int mn = tile % mn_tiles, split = tile / mn_tiles;
+      const int m0 = (mn / tiles_n) * kBM, n0 = (mn % tiles_n) * kBN;
       const int buf = it & 1;
       if (ep.mode == EPI_CROSS_FWD) {
         if (et < kBN) s_bias[et] = (ep.bias && n0 + et < N) ? ep.bias[n0 + et] : 0.f;
@@ -255,7 +263,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, 
       if (!staged_epi) {
         const int col0 = n0 + half * 64;
         if (row < M && col0 < N) {
-          float* o = ep.of32 + (int64_t)row * ep.ldf + col0;
+          float* o = ep.of32 + ((int64_t)split * M + row) * ep.ldf + col0;
 #pragma unroll
           for (int j = 0; j < 64; j += 4) {
             if (col0 + j < N) {
@@ -333,6 +341,18 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int6
   }
 }
 
+// out[e] = sum_s partial[s][e]  (fixed order: deterministic split-K)
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t n, float* __restrict__ out) {
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (e >= n) return;
+  float4 acc = *reinterpret_cast<const float4*>(partial + e);
+  for (int s = 1; s < splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(partial + (int64_t)s * n + e);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + e) = acc;
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -392,7 +412,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, i
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t tiles = ceil_div(N, kBN) * ceil_div(M, kBM);
+  const int64_t tiles = ceil_div(N, kBN) * ceil_div(M, kBM) * (ep.mode == EPI_F32 && ep.splits > 1 ? ep.splits : 1);
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
   gemm_bf16_tn_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(maps, M, N, K, ep);
   PTREC_LAUNCH_CHECK("gemm_bf16_tn_kernel");
@@ -443,9 +463,18 @@ extern "C" int ptrec_dcn_cross_dgrad(const void* g_u, const void* weight_t, cons
   return launch_gemm(g_u, ld, weight_t, d, (int)B, d, d, ep, (cudaStream_t)stream);
 }
 
+static int wgrad_splits(int32_t d) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t mn = ceil_div(d, kBN) * ceil_div(d, kBM);
+  int s = (int)(sms / mn);
+  return s < 1 ? 1 : (s > 16 ? 16 : s);
+}
+
 extern "C" size_t ptrec_dcn_cross_wgrad_workspace_bytes(int64_t B, int32_t d) {
   const size_t ldt = align_up((size_t)B, 8);
-  return 2 * align_up((size_t)d * ldt * 2, 256) + 256;
+  return 2 * align_up((size_t)d * ldt * 2, 256) + align_up((size_t)16 * d * d * 4, 256) + 256;
 }
 
 extern "C" int ptrec_dcn_cross_wgrad(const void* g_u, const void* x_l, int64_t B, int32_t d, int64_t ld, float* grad_w,
@@ -465,10 +494,26 @@ extern "C" int ptrec_dcn_cross_wgrad(const void* g_u, const void* x_l, int64_t B
   PTREC_LAUNCH_CHECK("transpose_bf16_kernel");
   transpose_bf16_kernel<<<tg, tb, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x_l), ld, (int)B, d, xt, ldt);
   PTREC_LAUNCH_CHECK("transpose_bf16_kernel");
+  float* partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) +
+                                            2 * align_up((size_t)d * ldt * 2, 256));
+  int splits = wgrad_splits(d);
+  {  // every split must own at least one 64-wide K block (an empty split would publish a stale accumulator)
+    const int total_kb = (int)ceil_div(B, kBK);
+    if (splits > total_kb) splits = total_kb;
+    const int per = (int)ceil_div(total_kb, splits);
+    splits = (int)ceil_div(total_kb, per);
+  }
   EpiArgs ep{};
   ep.mode = EPI_F32;
-  ep.of32 = grad_w;
+  ep.of32 = splits > 1 ? partial : grad_w;
   ep.ldf = d;
-  // gW[i, j] = sum_b g_u[b, i] * x_l[b, j]  ->  A = g_u^T [d, B], B = x_l^T [d, B], both K(=batch)-major
-  return launch_gemm(gt, ldt, xt, ldt, d, d, (int)B, ep, st);
+  ep.splits = splits;
+  // gW[i, j] = sum_b g_u[b, i] * x_l[b, j]  ->  A = g_u^T [d, B], B = x_l^T [d, B], both K(=batch)-major;
+  // the batch (K) is cut into `splits` ranges so that all SMs have a tile; partials are summed in a fixed order
+  int rc2 = launch_gemm(gt, ldt, xt, ldt, d, d, (int)B, ep, st);
+  if (rc2 != PTREC_OK || splits == 1) return rc2;
+  const int64_t n = (int64_t)d * d;
+  splitk_reduce_kernel<<<(unsigned)ceil_div(n / 4, 256), 256, 0, st>>>(partial, splits, n, grad_w);
+  PTREC_LAUNCH_CHECK("splitk_reduce_kernel");
+  return PTREC_OK;
 }
