@@ -37,13 +37,16 @@ def parse():
     ap.add_argument("--dim", type=int, default=CFG["dim"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager train_step instead of the whole-step CUDA graph")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
+                    help="cfg2 (default, the bench line): 26x1e6xD16, B 16384/GPU.  cfg5: 26 x (5e7*G/8) rows x D64, "
+                         "B 65536/GPU, row-wise sharded (weak-scaling series of SURVEY 8d)")
     ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
 
 
 def config_dict(a, world):
-    return {"workload": "cfg2 DeepFM Criteo-shaped synthetic: 26 tables x %d rows x dim %d (+26 first-order dim 1), "
-                        "13 dense, DNN 400-400-400, batch %d per GPU, fp32, sparse Adagrad" % (a.rows, a.dim, a.batch),
+    return {"workload": "%s DeepFM Criteo-shaped synthetic: 26 tables x %d rows x dim %d (+26 first-order dim 1), "
+                        "13 dense, DNN 400-400-400, batch %d per GPU, fp32, sparse Adagrad" % (a.workload, a.rows, a.dim, a.batch),
             "global_batch": a.batch * world, "id_dist": a.id_dist, "cuda_graph": not a.no_graph,
             "parallelism": "single GPU" if world == 1 else f"row-wise sharded tables x{world} (all-to-all) + dense allreduce",
             "l2": "tables %.2f GB >> 126 MB L2; a different random id batch every step" %
@@ -330,6 +333,9 @@ def kernel_roofline(a, model, resident, dev):
 
 if __name__ == "__main__":
     args = parse()
+    if args.workload == "cfg5":
+        args.rows = int(5e7 * max(args.gpus, 1) / 8)
+        args.dim, args.batch = 64, 65536
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -69,14 +69,21 @@ class _GraphedTrainStep:
             return m._eager_train_step(data)
         dev = m.compiled_device
         opt = m.compiled_optimizers
+        on_host = all(v.device.type == "cpu" for v in data.values() if isinstance(v, torch.Tensor))
         if e["graph"] is None:
             if not getattr(opt, "graph_safe", lambda: False)():
                 raise RuntimeError("CUDA-graph train steps need an optimizer whose update does not depend on the "
                                    "host-side step count (SparseSGD, SparseAdagrad / SparseRowWiseAdagrad with lr_decay=0)")
-            e["static"] = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in data.items()
-                           if isinstance(v, torch.Tensor)}
-            for k, v in e["static"].items():
-                v.copy_(data[k])
+            # static inputs are typed views of ONE device buffer: host batches arrive with a single pinned,
+            # packed, asynchronous copy (N1), device batches are copied key by key
+            from ..utils.ingest import BatchPacker
+            e["packer"] = BatchPacker(data, dev)
+            e["static"] = e["packer"].views
+            if on_host:
+                e["packer"].load(data)
+            else:
+                for k, v in e["static"].items():
+                    v.copy_(data[k])
             torch.cuda.synchronize(dev)
             m.train()
             from .. import _lib
@@ -87,6 +94,8 @@ class _GraphedTrainStep:
             opt._step_count_fused -= 1  # capture records the step, it does not execute it
             e["graph"], e["loss"] = g, loss
             e["launches"] = int(_lib.load().ptrec_launch_count() - l0)  # recorded into the graph, not yet run
+        elif on_host:
+            e["packer"].load(data)
         else:
             for k, v in e["static"].items():
                 v.copy_(data[k], non_blocking=True)
@@ -119,6 +128,8 @@ class IModel(Module, ABC):
         self.compiled_metrics: Optional[MetricList] = None
         self.compiled_device: Optional[torch.device] = None
         self._graphed: Optional[_GraphedTrainStep] = None
+        self._packers: Dict[tuple, Any] = {}
+        self.packed_ingest = True  # N1: host batches move with one pinned packed copy instead of one copy per key
         self.register_forward_pre_hook(_drop_lookup_cache)
         self._init_weights()
         self._reset_weights()
@@ -188,9 +199,23 @@ class IModel(Module, ABC):
             return self._graphed.step(data)
         return self._eager_train_step(data)
 
+    def _to_device(self, data: Dict):
+        """Host -> device move of one batch.  CUDA target + host tensors: one packed pinned transfer (N1);
+        otherwise the reference's per-key ``tensor_to_device`` (IModel.py:119)."""
+        dev = self.compiled_device
+        if (self.packed_ingest and dev is not None and dev.type == "cuda" and isinstance(data, dict) and data
+                and all(isinstance(v, torch.Tensor) and v.device.type == "cpu" for v in data.values())):
+            sig = tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in data.items()))
+            packer = self._packers.get(sig)
+            if packer is None:
+                from ..utils.ingest import BatchPacker
+                packer = self._packers[sig] = BatchPacker(data, dev)
+            return packer.load(data)
+        return tensor_to_device(data, dev)
+
     def _eager_train_step(self, data: Dict):
         self.train()
-        data = tensor_to_device(data, self.compiled_device)
+        data = self._to_device(data)
         return {"loss": self._train_step_body(data)}
 
     def _train_step_body(self, data: Dict):
@@ -208,7 +233,7 @@ class IModel(Module, ABC):
 
     def test_step(self, data):
         self.eval()
-        data = tensor_to_device(data, self.compiled_device)
+        data = self._to_device(data)
         prediction, target = self(data)
         return prediction, target
 

@@ -315,3 +315,46 @@ def test_din_matches_oracle_twin(opt_name):
         # their summation-order noise into O(1e-3 * lr) differences on a few percent of the elements
         assert tight.mean() >= (0.95 if opt_name == "adagrad" else 0.995), (k, tight.mean())
         np.testing.assert_allclose(a, b, rtol=0, atol=1e-3 * 3 * 0.2, err_msg=k)
+
+
+def test_fm_cfg1_full_size_matches_cpu_oracle():
+    """BASELINE cfg1 at full size: FM, 26 tables x 1e5 rows x D16 (+26 first-order), 13 dense, batch 4096 —
+    two SGD train steps on the GPU vs the CPU oracle twin (identical seeded init)."""
+    from pytorchrec_b200.data import criteo_batch, criteo_columns
+    sparse, dense, label = criteo_columns(26, 13, 100_000)
+    prod = FM(sparse, dense, label, 16, random_seed=2020)
+    ref = ref_models.FMRef(2020, sparse, dense, label, 16)
+    prod.compile(SparseSGD(prod.get_parameters(), lr=0.1), torch.nn.BCEWithLogitsLoss(), [LogLoss()], DEV)
+    ref.compile(torch.optim.SGD(ref.get_parameters(), lr=0.1), torch.nn.BCEWithLogitsLoss())
+    for s in range(2):
+        batch = criteo_batch(4096, 26, 13, 100_000, seed=77 + s, dist="zipf" if s else "uniform")
+        lp = prod.train_step(batch)["loss"].item()
+        lr_ = ref.train_step(batch)["loss"].item()
+        np.testing.assert_allclose(lp, lr_, rtol=1e-5)
+    for (k, v), (_, v2) in zip(prod.state_dict().items(), ref.state_dict().items()):
+        np.testing.assert_allclose(v.cpu().numpy(), v2.numpy(), rtol=1e-5, atol=2e-7, err_msg=k)
+    prod.embeddings.check_index_errors()
+
+
+def test_packed_ingest_equals_per_key_transfer():
+    """N1: the single pinned packed H2D copy presents the same Dict[str, Tensor] as the reference's per-key .to()."""
+    from pytorchrec_b200.utils.ingest import BatchPacker
+    scols, dcols, lab, rows = _ctr_setup()
+    batches = [_ctr_batch(rows, len(dcols), 300, seed=s) for s in range(5)]
+    packer = BatchPacker(batches[0], DEV)
+    for b in batches:  # more batches than staging buffers: exercises the event guard
+        dev = packer.load(b)
+        assert set(dev) == set(b)
+        for k, v in b.items():
+            assert dev[k].dtype == v.dtype and dev[k].shape == v.shape and torch.equal(dev[k].cpu(), v)
+    assert packer.h2d_bytes >= sum(v.numel() * v.element_size() for v in batches[0].values())
+    # model level: identical training with and without the packer
+    res = []
+    for packed in (True, False):
+        m = DeepFM(scols, dcols, lab, 16, [32, 16], random_seed=9)
+        m.packed_ingest = packed
+        m.compile(SparseAdagrad(m.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], DEV)
+        res.append(([m.train_step(b)["loss"].item() for b in batches], m.state_dict()))
+    assert res[0][0] == res[1][0]
+    for (k, a), (_, b2) in zip(res[0][1].items(), res[1][1].items()):
+        assert torch.equal(a, b2), k
