@@ -21,6 +21,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: everything libraries print (NCCL banner, warnings) is sent to stderr by
+# pointing fd 1 at fd 2 for the whole run; the result line is written to the saved descriptor at the end.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 CFG = dict(n_sparse=26, n_dense=13, rows=1_000_000, dim=16, batch=16384, layers=[400, 400, 400])
 
@@ -96,7 +105,7 @@ def run_reference(a):
                              "sample": f"{steps_run} full-size train steps (batch {a.batch}) after {warm_run} warm-up, "
                                        "oracle port of the reference idiom on host cores"},
             "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -246,7 +255,7 @@ def run_b200(a):
             except Exception as e:  # noqa
                 line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # NCCL kernels captured in the step graph keep the communicator busy at teardown: drop the graphs,
         # synchronise, and leave without the (hanging) communicator destructor.
@@ -270,10 +279,11 @@ def kernel_roofline(a, model, resident, dev):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     emb = model.embeddings
-    F, D, B = len(emb), a.dim, a.batch
-    R = min(t.weight.shape[0] for t in emb)
+    emb_tables = [t for t in emb.groups[0]] if hasattr(emb, "groups") else [t for t in emb]
+    F, D, B = len(emb_tables), a.dim, a.batch
+    R = min(t.weight.shape[0] for t in emb_tables)
     # private copies in the layout the optimizer uses (weight | Adagrad sum interleaved in one 2*D-float row)
-    bufs = [torch.randn(t.weight.shape[0], 2 * D, device=dev) for t in emb]
+    bufs = [torch.randn(t.weight.shape[0], 2 * D, device=dev) for t in emb_tables]
     tables = [b[:, :D] for b in bufs]
     lay = ops.FeatureLayout([dict(table=f, bag_len=1) for f in range(F)], D, F)
     ts = ops.TableSet().refresh(tables)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 4
+#define PTREC_ABI_VERSION 5
 
 /* error codes */
 #define PTREC_OK 0
@@ -287,10 +287,11 @@ size_t ptrec_a2a_pack_workspace_bytes(int64_t B, int32_t F, int32_t G);
 int ptrec_a2a_pack_by_owner(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C,
                             int64_t* send_ids, int32_t* ret_pos, int32_t* overflow, void* workspace,
                             size_t workspace_bytes, void* stream);
-/* dst[ret_pos[f,b], :] = scale * src[b, f, :]  (gradient rows into the all-to-all send layout;
- * src [B, F*D] with row stride src_row_stride, dst [G*F*C, D]) */
+/* dst[ret_pos[f,b] * dst_row_stride + 0..D) = scale * src[b, f, :]  (gradient rows into the all-to-all send
+ * layout; src [B, F*D] with row stride src_row_stride; dst rows may be wider than D so that several embedding
+ * widths of the same fields travel in one collective) */
 int ptrec_a2a_scatter_rows(const float* src, int64_t src_row_stride, const int32_t* ret_pos, int64_t B,
-                           int32_t F, int32_t D, float scale, float* dst, void* stream);
+                           int32_t F, int32_t D, float scale, float* dst, int64_t dst_row_stride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libptrec_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # enums (mirror include/ptrec_b200.h)
 F32, BF16 = 0, 1
@@ -90,7 +90,7 @@ PROTOTYPES = {
     "ptrec_a2a_pack_by_owner": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_size_t, c_void_p]),
     "ptrec_a2a_scatter_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p,
-                                       c_void_p]),
+                                       c_int64, c_void_p]),
     "ptrec_din_attn_pool_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int32,
                                         c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -109,7 +109,7 @@ pack_scatter_kernel(const int64_t* __restrict__ ids, int64_t B, int F, int G, in
 template <int VEC, int LPR>
 __global__ void __launch_bounds__(256)
 scatter_rows_kernel(const float* __restrict__ src, int64_t src_row_stride, const int32_t* __restrict__ pos,
-                    int64_t B, int F, int D, float scale, float* __restrict__ dst) {
+                    int64_t B, int F, int D, float scale, float* __restrict__ dst, int64_t dst_row_stride) {
   const int64_t g = ((int64_t)blockIdx.x * 256 + threadIdx.x) / LPR;
   const int lane = threadIdx.x % LPR;
   if (g >= B * F || lane * VEC >= D) return;
@@ -119,7 +119,7 @@ scatter_rows_kernel(const float* __restrict__ src, int64_t src_row_stride, const
   if (p < 0) return;
   RowVec<VEC> r = load_row_stream<VEC>(src + b * src_row_stride + (int64_t)f * D + lane * VEC);
   r.scale(scale);
-  store_row<VEC>(dst + (int64_t)p * D + lane * VEC, r);
+  store_row<VEC>(dst + (int64_t)p * dst_row_stride + lane * VEC, r);
 }
 
 }  // namespace ptrec
@@ -155,19 +155,22 @@ extern "C" int ptrec_a2a_pack_by_owner(const int64_t* ids, int64_t B, int32_t F,
 }
 
 extern "C" int ptrec_a2a_scatter_rows(const float* src, int64_t src_row_stride, const int32_t* ret_pos, int64_t B,
-                                      int32_t F, int32_t D, float scale, float* dst, void* stream) {
+                                      int32_t F, int32_t D, float scale, float* dst, int64_t dst_row_stride,
+                                      void* stream) {
   PTREC_CHECK_ARG(src && ret_pos && dst, PTREC_EINVAL, "a2a_scatter_rows: null pointer");
   const bool d_ok = D == 1 || D == 2 || (D >= 4 && D <= 128 && D % 4 == 0);
   PTREC_CHECK_ARG(d_ok, PTREC_EUNSUPPORTED, "a2a_scatter_rows: D=%d unsupported", D);
   const int vec = D >= 4 ? 4 : D;
-  PTREC_CHECK_ARG(((uintptr_t)src % (vec * 4)) == 0 && ((uintptr_t)dst % (vec * 4)) == 0 && src_row_stride % vec == 0,
+  PTREC_CHECK_ARG(((uintptr_t)src % (vec * 4)) == 0 && ((uintptr_t)dst % (vec * 4)) == 0 && src_row_stride % vec == 0 &&
+                      dst_row_stride >= D && dst_row_stride % vec == 0,
                   PTREC_EALIGN, "a2a_scatter_rows: misaligned");
   if (B == 0) return PTREC_OK;
   cudaStream_t st = (cudaStream_t)stream;
 #define PTREC_SC(V, P)                                                                                   \
   {                                                                                                      \
     const unsigned grid = (unsigned)ceil_div(B * F * P, 256);                                            \
-    scatter_rows_kernel<V, P><<<grid, 256, 0, st>>>(src, src_row_stride, ret_pos, B, F, D, scale, dst);  \
+    scatter_rows_kernel<V, P><<<grid, 256, 0, st>>>(src, src_row_stride, ret_pos, B, F, D, scale, dst,   \
+                                                    dst_row_stride);                                     \
     PTREC_LAUNCH_CHECK("scatter_rows_kernel");                                                           \
     return PTREC_OK;                                                                                     \
   }

@@ -324,11 +324,12 @@ def a2a_pack_by_owner(ids: torch.Tensor, F: int, B: int, G: int, C: int, overflo
 
 def a2a_scatter_rows(src: torch.Tensor, ret_pos: torch.Tensor, B: int, F: int, D: int, scale: float,
                      dst: torch.Tensor) -> None:
+    """dst is a [n_slots, D] view (possibly a column slice of a wider buffer: its row stride is honoured)."""
     lib = _lib.load()
     _require_cuda(src, ret_pos, dst)
-    assert src.dtype == torch.float32 and src.stride(-1) == 1 and dst.is_contiguous()
+    assert src.dtype == torch.float32 and src.stride(-1) == 1 and dst.dim() == 2 and dst.stride(1) == 1
     _lib.check(lib.ptrec_a2a_scatter_rows(_ptr(src), src.stride(0), _ptr(ret_pos), B, F, D, float(scale), _ptr(dst),
-                                          _stream(src.device)), "ptrec_a2a_scatter_rows")
+                                          dst.stride(0), _stream(src.device)), "ptrec_a2a_scatter_rows")
 
 
 # ----------------------------------------------------------------------------------------------

@@ -41,12 +41,13 @@ def main():
     full = DeepFM(scols, dcols, lab, D, [32, 16], random_seed=3)
     shard = ShardedDeepFM(scols, dcols, lab, D, [32, 16], random_seed=3)
     sd = full.state_dict()
+    names = {"embeddings": 0, "first_order": 1}  # unsharded module name -> width group of the sharded model
     with torch.no_grad():
-        for name in ("embeddings", "first_order"):
+        for name, k in names.items():
             for f in range(F):
-                getattr(shard, name)[f].weight.copy_(sd[f"{name}.{f}.weight"][rank::world])
+                shard.sharded.groups[k][f].weight.copy_(sd[f"{name}.{f}.weight"][rank::world])
         for k, v in shard.state_dict().items():
-            if not k.startswith(("embeddings", "first_order")):
+            if not k.startswith("sharded."):
                 v.copy_(sd[k])
     full.compile(SparseAdagrad(full.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)
     shard.compile(SparseAdagrad(shard.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)
@@ -66,10 +67,15 @@ def main():
                                    rtol=1e-5, atol=2e-5)
         full.train_step(gb)
         shard.train_step(lb)
-    shard.embeddings.check_errors()
+    shard.sharded.check_errors()
     fsd, ssd = full.state_dict(), shard.state_dict()
+    inv = {0: "embeddings", 1: "first_order"}
     for k, v in ssd.items():
-        ref = fsd[k][rank::world] if k.startswith(("embeddings", "first_order")) else fsd[k]
+        if k.startswith("sharded.groups."):
+            _, _, gk, f, _ = k.split(".")
+            ref = fsd[f"{inv[int(gk)]}.{f}.weight"][rank::world]
+        else:
+            ref = fsd[k]
         a, b = v.cpu().numpy(), ref.cpu().numpy()
         tight = np.abs(a - b) <= 1e-5 * np.abs(b) + 1.5e-5
         assert tight.mean() >= 0.995, (k, tight.mean())
