@@ -259,6 +259,41 @@ class ShardedDeepFM(DeepFM):
         logit = logit + self.deep_out(self.mlp(deep_in)).squeeze(-1)
         return logit, self._target(data)
 
+    # ---- N4: checkpoints interchangeable with the unsharded model -------------------------------------------------
+    _GROUP_NAMES = ("embeddings", "first_order")
+
+    @torch.no_grad()
+    def full_state_dict(self) -> Dict[str, Tensor]:
+        """Gather the row-wise shards (collective: call on every rank) into the ``state_dict`` of the UNSHARDED
+        ``DeepFM`` (``embeddings.{f}.weight`` / ``first_order.{f}.weight`` with rows interleaved back as
+        ``row = local_row * G + rank``), on the CPU; dense parameters are taken from this rank."""
+        G = self.sharded.world
+        out = {k: v.detach().cpu() for k, v in self.state_dict().items() if not k.startswith("sharded.")}
+        for k, name in enumerate(self._GROUP_NAMES):
+            for f, (col, table) in enumerate(zip(self.sparse_columns, self.sharded.groups[k])):
+                local = table.weight.detach().contiguous()
+                cap = (col.category_num + G - 1) // G
+                padded = torch.zeros(cap, local.shape[1], dtype=local.dtype, device=local.device)
+                padded[:local.shape[0]] = local
+                parts = [torch.empty_like(padded) for _ in range(G)]
+                dist.all_gather(parts, padded, group=self.sharded.group)
+                full = torch.stack(parts, dim=1).reshape(cap * G, local.shape[1])[:col.category_num]
+                out[f"{name}.{f}.weight"] = full.cpu()
+        return out
+
+    @torch.no_grad()
+    def load_full_state_dict(self, state_dict: Dict[str, Tensor]) -> None:
+        """Inverse of ``full_state_dict``: take an unsharded ``DeepFM`` checkpoint and keep rows ``rank::G``."""
+        G, rank = self.sharded.world, self.sharded.rank
+        own = self.state_dict()
+        for k, name in enumerate(self._GROUP_NAMES):
+            for f, table in enumerate(self.sharded.groups[k]):
+                shard = state_dict[f"{name}.{f}.weight"][rank::G]
+                table.weight[:shard.shape[0]].copy_(shard)
+        for key, v in own.items():
+            if not key.startswith("sharded."):
+                v.copy_(state_dict[key])
+
     def _dense_params(self) -> List[Tensor]:
         table_ids = {id(t.weight) for t in self.sharded.tables}
         return [p for p in self.parameters() if id(p) not in table_ids]

@@ -14,6 +14,13 @@ def get_pos_rank(prediction: np.ndarray, user_sample_n: int) -> np.ndarray:
     return np.argmax(order == 0, axis=1) + 1
 
 
+def get_pos_rank_torch(prediction, user_sample_n: int):
+    """Device-side rank of column 0 (N3): 1 + number of candidates scoring strictly higher — the same answer as
+    the stable argsort above, without moving the score matrix to the host."""
+    scores = prediction.reshape(-1, user_sample_n)
+    return 1 + (scores[:, 1:] > scores[:, :1]).sum(dim=1)
+
+
 class IMetric:
     name = "metric"
 
@@ -68,13 +75,20 @@ class MetricList:
         assert len(metrics) > 0
         self.metrics = metrics
 
-    def __call__(self, prediction: np.ndarray, target: np.ndarray) -> Dict[str, float]:
+    def rank_only(self) -> bool:
+        return all(isinstance(m, _RankMetric) for m in self.metrics)
+
+    def __call__(self, prediction, target) -> Dict[str, float]:
         ranks: Dict[int, np.ndarray] = {}
         out = {}
+        on_device = not isinstance(prediction, np.ndarray)
         for m in self.metrics:
             if isinstance(m, _RankMetric):
                 if m.user_sample_n not in ranks:
-                    ranks[m.user_sample_n] = get_pos_rank(prediction, m.user_sample_n)
+                    if on_device:  # torch tensor (any device): rank there, move only the [users] rank vector
+                        ranks[m.user_sample_n] = get_pos_rank_torch(prediction, m.user_sample_n).cpu().numpy()
+                    else:
+                        ranks[m.user_sample_n] = get_pos_rank(prediction, m.user_sample_n)
                 out[m.name] = m.from_rank(ranks[m.user_sample_n])
             else:
                 out[m.name] = m(prediction, target)

@@ -275,10 +275,18 @@ class IModel(Module, ABC):
         self._assert_compile_was_called()
         loader = DataLoader(dataset=dataset, batch_size=batch_size, num_workers=workers)
         predictions, targets = [], []
+        # N3: with ranking metrics only, scores stay on the device and ranks are computed there — one
+        # synchronisation per evaluate() instead of the reference's .cpu().numpy() per batch (IModel.py:250-251)
+        keep_on_device = self.compiled_metrics.rank_only() and self.compiled_device.type == "cuda"
         for data in loader:
             prediction, target = self.test_step(data)
-            predictions.append(prediction.detach().cpu().numpy())
-            targets.append(target.detach().cpu().numpy())
+            if keep_on_device:
+                predictions.append(prediction.detach())
+            else:
+                predictions.append(prediction.detach().cpu().numpy())
+                targets.append(target.detach().cpu().numpy())
+        if keep_on_device:
+            return self.compiled_metrics(torch.cat(predictions), None)
         return self.compiled_metrics(np.concatenate(predictions), np.concatenate(targets))
 
     @torch.no_grad()

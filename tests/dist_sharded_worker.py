@@ -41,14 +41,7 @@ def main():
     full = DeepFM(scols, dcols, lab, D, [32, 16], random_seed=3)
     shard = ShardedDeepFM(scols, dcols, lab, D, [32, 16], random_seed=3)
     sd = full.state_dict()
-    names = {"embeddings": 0, "first_order": 1}  # unsharded module name -> width group of the sharded model
-    with torch.no_grad():
-        for name, k in names.items():
-            for f in range(F):
-                shard.sharded.groups[k][f].weight.copy_(sd[f"{name}.{f}.weight"][rank::world])
-        for k, v in shard.state_dict().items():
-            if not k.startswith("sharded."):
-                v.copy_(sd[k])
+    shard.load_full_state_dict(sd)  # N4: an unsharded checkpoint loads into the sharded model (rows rank::G)
     full.compile(SparseAdagrad(full.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)
     shard.compile(SparseAdagrad(shard.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)
     if os.environ.get("PTREC_TEST_GRAPH", "1") == "1":
@@ -80,6 +73,14 @@ def main():
         tight = np.abs(a - b) <= 1e-5 * np.abs(b) + 1.5e-5
         assert tight.mean() >= 0.995, (k, tight.mean())
         np.testing.assert_allclose(a, b, rtol=0, atol=3e-4, err_msg=k)
+    # N4: the gathered checkpoint is the unsharded model's state_dict (keys, shapes, values)
+    gathered = shard.full_state_dict()
+    assert set(gathered) == set(fsd), set(gathered) ^ set(fsd)
+    for k, v in gathered.items():
+        assert v.shape == fsd[k].shape, k
+        np.testing.assert_allclose(v.numpy(), fsd[k].cpu().numpy(), rtol=0, atol=3e-4, err_msg=k)
+    probe = DeepFM(scols, dcols, lab, D, [32, 16], random_seed=99)
+    probe.load_state_dict(gathered)
     dist.barrier()
     if rank == 0:
         print("DIST_SHARDED_OK world=%d" % world, flush=True)

@@ -358,3 +358,31 @@ def test_packed_ingest_equals_per_key_transfer():
     assert res[0][0] == res[1][0]
     for (k, a), (_, b2) in zip(res[0][1].items(), res[1][1].items()):
         assert torch.equal(a, b2), k
+
+
+def test_evaluate_with_device_side_ranks():
+    """N3: evaluate() on [B, 1+neg] candidate lists (FunkSVD.py:56-65 shape) keeps scores on the GPU."""
+    from pytorchrec_b200.metric import Hit, NDCG
+
+    class Candidates(torch.utils.data.Dataset):
+        def __init__(self, n, neg):
+            g = torch.Generator().manual_seed(3)
+            self.uid = torch.randint(1, 50, (n,), generator=g)
+            self.iid = torch.randint(1, 80, (n, 1 + neg), generator=g)
+
+        def __len__(self):
+            return len(self.uid)
+
+        def __getitem__(self, i):
+            return {"uid": self.uid[i], "iid": self.iid[i], "label": torch.tensor(1)}
+
+    m = FunkSVD(Col(50, "uid"), Col(80, "iid"), Col(2, "label"), 8, random_seed=4)
+    m.compile(SparseSGD(m.get_parameters(), lr=0.1), torch.nn.MSELoss(), [Hit(10, 3), NDCG(10, 3)], DEV)
+    ds = Candidates(300, 9)
+    logs = m.evaluate(ds, batch_size=64)
+    # host recomputation from the same scores
+    with torch.no_grad():
+        pred, _ = m.test_step({"uid": ds.uid, "iid": ds.iid, "label": torch.ones(300)})
+    from pytorchrec_b200.metric import MetricList
+    want = MetricList([Hit(10, 3), NDCG(10, 3)])(pred.cpu().numpy(), None)
+    assert logs.keys() == want.keys() and all(abs(logs[k] - want[k]) < 1e-9 for k in logs)

@@ -180,3 +180,14 @@ def test_metrics_and_losses():
     np.testing.assert_allclose(BPRLoss()(x, None).item(), torch.nn.functional.softplus(torch.tensor([-1.0, 3.0])).mean().item())
     assert Top1Loss(reduction="none")(x, None).shape == (2,)
     assert get_loss("bce") is torch.nn.BCEWithLogitsLoss
+
+
+def test_device_rank_equals_host_rank():
+    """N3: the torch rank (usable on the GPU) agrees with the numpy argsort rank, ties included."""
+    from pytorchrec_b200.metric import Hit, MetricList, NDCG, get_pos_rank, get_pos_rank_torch
+    g = torch.Generator().manual_seed(0)
+    pred = torch.randint(0, 6, (400, 100), generator=g).float()  # many ties
+    np.testing.assert_array_equal(get_pos_rank_torch(pred, 100).numpy(), get_pos_rank(pred.numpy(), 100))
+    ml = MetricList([Hit(100, 10), NDCG(100, 10)])
+    a, b = ml(pred, None), ml(pred.numpy(), None)
+    assert a.keys() == b.keys() and all(abs(a[k] - b[k]) < 1e-12 for k in a)
