@@ -3,10 +3,11 @@
 // Integer-only, bit-exact against torch.sort(stable=True) / torch.unique(sorted=True) per table.
 // Bound: launch latency at the configs' sizes (N = 4e5..2e6 keys move ~16 B each per pass);
 // the design goal is therefore few, wide, spin-free launches:
-//   per 8-bit pass: histogram (tile x digit counts) -> per-table scan -> stable scatter (warp
-//   match-any ranking, no atomics on the output path); then head flags -> scan -> segment list.
-// Tables are sorted independently (a tile never straddles two tables), so only ceil(log2(rows)/8)
-// passes are needed instead of covering a global (table, id) key.
+//   per pass (8- or 10-bit digits): histogram (tile x digit counts) -> per-table scan -> stable scatter
+//   (warp match-any ranking, no atomics on the output path); then head flags -> scan -> segment list.
+// Tables are sorted independently (a tile never straddles two tables), so only ceil(log2(rows)/RB)
+// passes are needed instead of covering a global (table, id) key: 2 passes of 10 bits for 1e5..1e6-row
+// tables (3 with 8-bit digits), 3 for 5e7 rows.
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -15,7 +16,7 @@ namespace ptrec {
 constexpr int kSortThreads = 256;
 constexpr int kSortItems = 8;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 2048
-constexpr int kRadix = 256;
+constexpr int kMaxRadix = 1024;
 
 struct TableLayout {
   int32_t T;
@@ -82,12 +83,13 @@ __device__ __forceinline__ void table_feature_range(const ptrec_feature_desc* s_
   }
 }
 
-template <bool FIRST>
+template <bool FIRST, int RB>
 __global__ void __launch_bounds__(kSortThreads)
 radix_hist_kernel(TableLayout lay, int64_t B, int shift, const uint32_t* __restrict__ keys_in,
                   const ptrec_feature_desc* __restrict__ feats, int F, const int64_t* __restrict__ ids,
                   const int32_t* __restrict__ lens, const int64_t* __restrict__ table_rows,
                   int* __restrict__ hist) {
+  constexpr int kRadix = 1 << RB;
   __shared__ int s_hist[kRadix];
   __shared__ ptrec_feature_desc s_feats[FIRST ? kMaxFeatures : 1];
   const int tile = blockIdx.x;
@@ -97,7 +99,7 @@ radix_hist_kernel(TableLayout lay, int64_t B, int shift, const uint32_t* __restr
   const int64_t beg = lay.Lstart[t] * B + (int64_t)k * kSortTile;
   const int64_t end = min(lay.Lstart[t + 1] * B, beg + kSortTile);
   __shared__ int s_rng[2];
-  s_hist[threadIdx.x] = 0;
+  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) s_hist[d] = 0;
   if (FIRST) {
     load_feats(s_feats, feats, F);
     __syncthreads();
@@ -110,11 +112,12 @@ radix_hist_kernel(TableLayout lay, int64_t B, int shift, const uint32_t* __restr
     atomicAdd(&s_hist[(key >> shift) & (kRadix - 1)], 1);
   }
   __syncthreads();
-  hist[(int64_t)lay.tile_prefix[t] * kRadix + (int64_t)threadIdx.x * tiles_t + k] = s_hist[threadIdx.x];
+  for (int d = threadIdx.x; d < kRadix; d += kSortThreads)
+    hist[(int64_t)lay.tile_prefix[t] * kRadix + (int64_t)d * tiles_t + k] = s_hist[d];
 }
 
 // one CTA per table: exclusive scan of its [256][tiles_t] counts, seeded with the table's first slot
-__global__ void __launch_bounds__(1024) radix_scan_kernel(TableLayout lay, int64_t B, int* __restrict__ hist) {
+__global__ void __launch_bounds__(1024) radix_scan_kernel(TableLayout lay, int64_t B, int kRadix, int* __restrict__ hist) {
   __shared__ int s_warp[33];
   __shared__ int s_carry;
   const int t = blockIdx.x;
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(TableLayout lay, int64
   }
 }
 
-template <bool FIRST>
+template <bool FIRST, int RB>
 __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(TableLayout lay, int64_t B, int shift, const uint32_t* __restrict__ keys_in,
                      const int32_t* __restrict__ perm_in, const ptrec_feature_desc* __restrict__ feats,
@@ -144,6 +147,7 @@ radix_scatter_kernel(TableLayout lay, int64_t B, int shift, const uint32_t* __re
                      const int64_t* __restrict__ table_rows, const int* __restrict__ offsets,
                      uint32_t* __restrict__ keys_out, int32_t* __restrict__ perm_out) {
   constexpr int NW = kSortThreads / 32;
+  constexpr int kRadix = 1 << RB;
   __shared__ int s_cnt[NW][kRadix];
   __shared__ int s_goff[kRadix];
   __shared__ ptrec_feature_desc s_feats[FIRST ? kMaxFeatures : 1];
@@ -154,9 +158,11 @@ radix_scatter_kernel(TableLayout lay, int64_t B, int shift, const uint32_t* __re
   const int64_t beg = lay.Lstart[t] * B + (int64_t)k * kSortTile;
   const int64_t end = min(lay.Lstart[t + 1] * B, beg + kSortTile);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) {
 #pragma unroll
-  for (int w = 0; w < NW; ++w) s_cnt[w][threadIdx.x] = 0;
-  s_goff[threadIdx.x] = offsets[(int64_t)lay.tile_prefix[t] * kRadix + (int64_t)threadIdx.x * tiles_t + k];
+    for (int w = 0; w < NW; ++w) s_cnt[w][d] = 0;
+    s_goff[d] = offsets[(int64_t)lay.tile_prefix[t] * kRadix + (int64_t)d * tiles_t + k];
+  }
   __shared__ int s_rng[2];
   if (FIRST) {
     load_feats(s_feats, feats, F);
@@ -191,12 +197,12 @@ radix_scatter_kernel(TableLayout lay, int64_t B, int shift, const uint32_t* __re
     rank[i] = base + __popc(m & lt);
   }
   __syncthreads();
-  {  // exclusive prefix over warps for digit d = threadIdx.x
+  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) {  // exclusive prefix over warps for digit d
     int run = 0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
-      const int c = s_cnt[w][threadIdx.x];
-      s_cnt[w][threadIdx.x] = run;
+      const int c = s_cnt[w][d];
+      s_cnt[w][d] = run;
       run += c;
     }
   }
@@ -279,7 +285,7 @@ extern "C" size_t ptrec_sort_dedup_workspace_bytes(int64_t N, int32_t T) {
   size_t bytes = 0;
   bytes += align_up((size_t)N * 4, 256);                       // keys_tmp
   bytes += align_up((size_t)N * 4, 256);                       // perm_tmp
-  bytes += align_up(tiles * kRadix * 4, 256);                  // hist
+  bytes += align_up(tiles * kMaxRadix * 4, 256);               // hist
   bytes += align_up(((size_t)scan_num_tiles(N) + 1) * 4, 256); // head scan tile sums
   return bytes + 256;
 }
@@ -307,15 +313,19 @@ extern "C" int ptrec_sort_dedup(const ptrec_feature_desc* feats, const ptrec_fea
     PTREC_CUDA(cudaMemsetAsync(seg_start, 0, sizeof(int32_t), st));
     return PTREC_OK;
   }
-  // passes: smallest P with 2^(8P) - 1 >= max_rows (so the masked key sorts strictly last)
-  int P = 1;
-  while (P < 4 && ((1ull << (8 * P)) - 1ull) < (unsigned long long)max_rows_host) ++P;
+  // key bits: smallest b with 2^b - 1 >= max_rows (so the masked key 0xFFFFFFFF sorts strictly last);
+  // 10-bit digits when they save a pass over 8-bit digits
+  int bits = 1;
+  while (bits < 32 && ((1ull << bits) - 1ull) < (unsigned long long)max_rows_host) ++bits;
+  const int p8 = (bits + 7) / 8, p10 = (bits + 9) / 10;
+  const int RB = p10 < p8 ? 10 : 8;
+  const int P = RB == 10 ? p10 : p8;
 
   unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
   uint32_t* keys_tmp = reinterpret_cast<uint32_t*>(w); w += align_up((size_t)N * 4, 256);
   int32_t* perm_tmp = reinterpret_cast<int32_t*>(w);   w += align_up((size_t)N * 4, 256);
   int* hist = reinterpret_cast<int*>(w);
-  w += align_up(((size_t)ceil_div(N, kSortTile) + (size_t)T + 1) * kRadix * 4, 256);
+  w += align_up(((size_t)ceil_div(N, kSortTile) + (size_t)T + 1) * kMaxRadix * 4, 256);
   int* tile_sums = reinterpret_cast<int*>(w);
 
   const uint32_t* kin = nullptr;
@@ -324,25 +334,21 @@ extern "C" int ptrec_sort_dedup(const ptrec_feature_desc* feats, const ptrec_fea
     const bool to_out = ((P - 1 - p) % 2) == 0;
     uint32_t* kout = to_out ? sorted_keys : keys_tmp;
     int32_t* pout = to_out ? perm : perm_tmp;
-    const int shift = 8 * p;
-    if (p == 0) {
-      radix_hist_kernel<true><<<lay.total_tiles, kSortThreads, 0, st>>>(lay, B, shift, nullptr, feats, F, ids,
-                                                                        lens, table_rows, hist);
-    } else {
-      radix_hist_kernel<false><<<lay.total_tiles, kSortThreads, 0, st>>>(lay, B, shift, kin, feats, F, ids,
-                                                                         lens, table_rows, hist);
-    }
+    const int shift = RB * p;
+#define PTREC_HIST(FIRST_, RB_) \
+  radix_hist_kernel<FIRST_, RB_><<<lay.total_tiles, kSortThreads, 0, st>>>(lay, B, shift, kin, feats, F, ids, lens, table_rows, hist)
+#define PTREC_SCAT(FIRST_, RB_) \
+  radix_scatter_kernel<FIRST_, RB_><<<lay.total_tiles, kSortThreads, 0, st>>>(lay, B, shift, kin, pin, feats, F, ids, lens, table_rows, hist, kout, pout)
+    if (p == 0) { if (RB == 10) PTREC_HIST(true, 10); else PTREC_HIST(true, 8); }
+    else        { if (RB == 10) PTREC_HIST(false, 10); else PTREC_HIST(false, 8); }
     PTREC_LAUNCH_CHECK("radix_hist_kernel");
-    radix_scan_kernel<<<T, 1024, 0, st>>>(lay, B, hist);
+    radix_scan_kernel<<<T, 1024, 0, st>>>(lay, B, 1 << RB, hist);
     PTREC_LAUNCH_CHECK("radix_scan_kernel");
-    if (p == 0) {
-      radix_scatter_kernel<true><<<lay.total_tiles, kSortThreads, 0, st>>>(
-          lay, B, shift, nullptr, nullptr, feats, F, ids, lens, table_rows, hist, kout, pout);
-    } else {
-      radix_scatter_kernel<false><<<lay.total_tiles, kSortThreads, 0, st>>>(
-          lay, B, shift, kin, pin, feats, F, ids, lens, table_rows, hist, kout, pout);
-    }
+    if (p == 0) { if (RB == 10) PTREC_SCAT(true, 10); else PTREC_SCAT(true, 8); }
+    else        { if (RB == 10) PTREC_SCAT(false, 10); else PTREC_SCAT(false, 8); }
     PTREC_LAUNCH_CHECK("radix_scatter_kernel");
+#undef PTREC_HIST
+#undef PTREC_SCAT
     kin = kout;
     pin = pout;
   }
