@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 5
+#define PTREC_ABI_VERSION 6
 
 /* error codes */
 #define PTREC_OK 0
@@ -76,6 +76,15 @@ typedef struct ptrec_feature_desc {
   int64_t id_base;   /* sum of bag_len over the features before this one                    */
   int64_t out_col;   /* float offset of this feature's pooled vector inside an output row   */
 } ptrec_feature_desc;
+
+/* One segment (= one unique (table, row) touched by the batch) as emitted by ptrec_sort_dedup: everything the
+ * fused update needs about the segment in one 16-byte record (one 128-bit load). */
+typedef struct ptrec_segment_meta {
+  uint32_t key;       /* row id (0xFFFFFFFF = the table's run of masked slots)   */
+  int32_t first_slot; /* perm[seg_start[u]]: slot of the segment's first lookup   */
+  int32_t table;      /* table index                                              */
+  int32_t reserved;
+} ptrec_segment_meta;
 
 /* hyper-parameters of the fused row update; passed by value (host memory) */
 typedef struct ptrec_optim_args {
@@ -144,7 +153,7 @@ int ptrec_embedding_gather_pool_fwd(const void* const* table_ptrs, const int64_t
  *   sorted_keys [N] uint32   id of the slot at sorted position j (0xFFFFFFFF = masked)
  *   perm        [N] int32    slot p at sorted position j
  *   seg_start   [N+1] int32  sorted position where segment u starts; seg_start[n_seg] = N
- *   seg_table   [N] int32    table of segment u
+ *   seg_meta    [N] ptrec_segment_meta   key / first slot / table of segment u
  *   n_seg       [1] int32    number of segments (masked runs included, one per table at most)
  * workspace: ptrec_sort_dedup_workspace_bytes(N, T).  max_rows_host = max_t rows_t (bounds key bits);
  * table_rows [T] device int64: ids outside [0, rows_t) are treated as masked.
@@ -153,7 +162,7 @@ size_t ptrec_sort_dedup_workspace_bytes(int64_t N, int32_t T);
 int ptrec_sort_dedup(const ptrec_feature_desc* feats, const ptrec_feature_desc* feats_host, int32_t F,
                      int32_t T, const int64_t* table_rows, int64_t max_rows_host,
                      const int64_t* ids, const int32_t* lens, int64_t B, uint32_t* sorted_keys,
-                     int32_t* perm, int32_t* seg_start, int32_t* seg_table, int32_t* n_seg,
+                     int32_t* perm, int32_t* seg_start, ptrec_segment_meta* seg_meta, int32_t* n_seg,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -177,34 +186,24 @@ int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* state1_ptrs,
                               const ptrec_feature_desc* feats,
                               const ptrec_feature_desc* feats_host, int32_t F, int64_t B,
                               const uint32_t* sorted_keys, const int32_t* perm,
-                              const int32_t* seg_start, const int32_t* seg_table,
+                              const int32_t* seg_start, const ptrec_segment_meta* seg_meta,
                               const int32_t* n_seg, const float* grad_out,
                               int64_t grad_row_stride, const float* bag_scale,
                               const ptrec_optim_args* opt_host, void* workspace,
                               size_t workspace_bytes, void* stream);
-/* the four named entry points of SURVEY.md §8b; each checks opt_host->kind and forwards */
-int ptrec_embedding_bwd_fused_sgd(void* const*, void* const*, void* const*, int32_t, int32_t, int64_t,
-                                  int32_t, const ptrec_feature_desc*, const ptrec_feature_desc*, int32_t, int64_t,
-                                  const uint32_t*, const int32_t*, const int32_t*, const int32_t*,
-                                  const int32_t*, const float*, int64_t, const float*,
-                                  const ptrec_optim_args*, void*, size_t, void*);
-int ptrec_embedding_bwd_fused_adagrad(void* const*, void* const*, void* const*, int32_t, int32_t, int64_t,
-                                      int32_t, const ptrec_feature_desc*, const ptrec_feature_desc*, int32_t, int64_t,
-                                      const uint32_t*, const int32_t*, const int32_t*,
-                                      const int32_t*, const int32_t*, const float*, int64_t,
-                                      const float*, const ptrec_optim_args*, void*, size_t, void*);
-int ptrec_embedding_bwd_fused_rowwise_adagrad(void* const*, void* const*, void* const*, int32_t,
-                                              int32_t, int64_t, int32_t, const ptrec_feature_desc*, const ptrec_feature_desc*, int32_t,
-                                              int64_t, const uint32_t*, const int32_t*,
-                                              const int32_t*, const int32_t*, const int32_t*,
-                                              const float*, int64_t, const float*,
-                                              const ptrec_optim_args*, void*, size_t, void*);
-int ptrec_embedding_bwd_fused_lazy_adam(void* const*, void* const*, void* const*, int32_t, int32_t, int64_t,
-                                        int32_t, const ptrec_feature_desc*, const ptrec_feature_desc*, int32_t, int64_t,
-                                        const uint32_t*, const int32_t*, const int32_t*,
-                                        const int32_t*, const int32_t*, const float*, int64_t,
-                                        const float*, const ptrec_optim_args*, void*, size_t,
-                                        void*);
+/* the four named entry points of SURVEY.md §8b: same arguments as ptrec_embedding_bwd_fused; each checks
+ * opt_host->kind and forwards */
+#define PTREC_BWD_FUSED_ARGS                                                                                   \
+  void* const* table_ptrs, void* const* state1_ptrs, void* const* state2_ptrs, int32_t T, int32_t D,           \
+      int64_t row_stride, int32_t dtype, const ptrec_feature_desc* feats, const ptrec_feature_desc* feats_host, \
+      int32_t F, int64_t B, const uint32_t* sorted_keys, const int32_t* perm, const int32_t* seg_start,        \
+      const ptrec_segment_meta* seg_meta, const int32_t* n_seg, const float* grad_out, int64_t grad_row_stride, \
+      const float* bag_scale, const ptrec_optim_args* opt_host, void* workspace, size_t workspace_bytes,       \
+      void* stream
+int ptrec_embedding_bwd_fused_sgd(PTREC_BWD_FUSED_ARGS);
+int ptrec_embedding_bwd_fused_adagrad(PTREC_BWD_FUSED_ARGS);
+int ptrec_embedding_bwd_fused_rowwise_adagrad(PTREC_BWD_FUSED_ARGS);
+int ptrec_embedding_bwd_fused_lazy_adam(PTREC_BWD_FUSED_ARGS);
 
 /* Segment-reduce only (no update): writes the per-unique-row gradient sums so that a stock sparse
  * optimizer (torch.optim.SparseAdam / SGD) can consume them.  row_grad [N, D] float32 (first
@@ -212,7 +211,7 @@ int ptrec_embedding_bwd_fused_lazy_adam(void* const*, void* const*, void* const*
 int ptrec_embedding_bwd_segment_sum(int32_t T, int32_t D, const ptrec_feature_desc* feats,
                                     const ptrec_feature_desc* feats_host, int32_t F, int64_t B,
                                     const uint32_t* sorted_keys, const int32_t* perm,
-                                    const int32_t* seg_start, const int32_t* seg_table,
+                                    const int32_t* seg_start, const ptrec_segment_meta* seg_meta,
                                     const int32_t* n_seg, const float* grad_out,
                                     int64_t grad_row_stride, const float* bag_scale,
                                     float* row_grad, void* stream);

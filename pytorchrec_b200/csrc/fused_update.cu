@@ -174,7 +174,7 @@ fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restric
                     void* const* __restrict__ state2_ptrs, int T, int D,
                     const ptrec_feature_desc* __restrict__ feats, int F, int64_t B,
                     const uint32_t* __restrict__ sorted_keys, const int32_t* __restrict__ perm,
-                    const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_table,
+                    const int32_t* __restrict__ seg_start, const ptrec_segment_meta* __restrict__ seg_meta,
                     const int32_t* __restrict__ n_seg_ptr, const float* __restrict__ grad_out,
                     int64_t stride, const float* __restrict__ bag_scale, OptParams op,
                     int* __restrict__ long_count, int32_t* __restrict__ long_list,
@@ -187,33 +187,40 @@ fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restric
   const bool lane_on = lane * VEC < D;
   const int n_seg = *n_seg_ptr;
   const int n_round = (n_seg + NSG * SEGS - 1) / (NSG * SEGS);
+  // Segment metadata is ONE round of independent loads (bounds + a 16-byte record), and the metadata of the next
+  // round is requested before this round's rows: the only exposed dependency per iteration is the row fetch.
+  int nstart[SEGS], nend[SEGS];
+  int4 nmeta[SEGS];
+  auto fetch_meta = [&](int r) {
+#pragma unroll
+    for (int q = 0; q < SEGS; ++q) {
+      const int u = (r * SEGS + q) * NSG + sg;
+      nstart[q] = nend[q] = 0;
+      nmeta[q] = make_int4((int)kMaskedKey, 0, 0, 0);
+      if (r < n_round && u < n_seg) {
+        nstart[q] = seg_start[u];
+        nend[q] = seg_start[u + 1];
+        nmeta[q] = *reinterpret_cast<const int4*>(seg_meta + u);
+      }
+    }
+  };
+  fetch_meta(blockIdx.x);
   for (int r = blockIdx.x; r < n_round; r += gridDim.x) {
     int start[SEGS], end[SEGS], tab[SEGS];
     uint32_t key[SEGS];
+    int32_t p0[SEGS];
     bool work[SEGS], live[SEGS];
-    // round 1: segment bounds + table (independent loads for all SEGS segments)
 #pragma unroll
     for (int q = 0; q < SEGS; ++q) {
       const int u = (r * SEGS + q) * NSG + sg;
       live[q] = u < n_seg;
-      start[q] = end[q] = tab[q] = 0;
-      if (live[q]) {
-        start[q] = seg_start[u];
-        end[q] = seg_start[u + 1];
-        tab[q] = seg_table[u];
-      }
+      start[q] = nstart[q];
+      end[q] = nend[q];
+      key[q] = (uint32_t)nmeta[q].x;
+      p0[q] = nmeta[q].y;
+      tab[q] = nmeta[q].z;
     }
-    // round 2: keys and first gradient slot
-    int32_t p0[SEGS];
-#pragma unroll
-    for (int q = 0; q < SEGS; ++q) {
-      key[q] = kMaskedKey;
-      p0[q] = 0;
-      if (live[q]) {
-        key[q] = sorted_keys[start[q]];
-        p0[q] = perm[start[q]];
-      }
-    }
+    fetch_meta(r + gridDim.x);
     // round 3: weight / state rows and the first gradient row of every segment
     float* wrow[SEGS];
     float* s1[SEGS];
@@ -278,7 +285,7 @@ fused_update_long_kernel(void* const* __restrict__ table_ptrs, void* const* __re
                          void* const* __restrict__ state2_ptrs, int T, int D,
                          const ptrec_feature_desc* __restrict__ feats, int F, int64_t B,
                          const uint32_t* __restrict__ sorted_keys, const int32_t* __restrict__ perm,
-                         const int32_t* __restrict__ seg_start, const int32_t* __restrict__ seg_table,
+                         const int32_t* __restrict__ seg_start, const ptrec_segment_meta* __restrict__ seg_meta,
                          const float* __restrict__ grad_out, int64_t stride,
                          const float* __restrict__ bag_scale, OptParams op,
                          const int* __restrict__ long_count, const int32_t* __restrict__ long_list) {
@@ -293,7 +300,7 @@ fused_update_long_kernel(void* const* __restrict__ table_ptrs, void* const* __re
   for (int i = blockIdx.x; i < n_long; i += gridDim.x) {
     const int u = long_list[i];
     const int start = seg_start[u], end = seg_start[u + 1];
-    const int t = seg_table[u];
+    const int t = seg_meta[u].table;
     RowVec<VEC> acc;
     acc.zero();
     for (int j0 = start + sg; j0 < end; j0 += NSG * 2) {
@@ -337,7 +344,7 @@ template <int VEC, int LPR, int OPT>
 static int launch_update(void* const* table_ptrs, void* const* s1, void* const* s2, int T, int D,
                          const ptrec_feature_desc* feats, int F, int64_t B, int64_t N,
                          const uint32_t* sorted_keys, const int32_t* perm, const int32_t* seg_start,
-                         const int32_t* seg_table, const int32_t* n_seg, const float* grad_out,
+                         const ptrec_segment_meta* seg_meta, const int32_t* n_seg, const float* grad_out,
                          int64_t stride, const float* bag_scale, const OptParams& op, int* long_count,
                          int32_t* long_list, float* row_grad, cudaStream_t st) {
   constexpr int NSG = kUpdThreads / LPR;
@@ -345,15 +352,16 @@ static int launch_update(void* const* table_ptrs, void* const* s1, void* const* 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t rounds = ceil_div(N, NSG * 4);
-  const unsigned grid = (unsigned)(rounds < (int64_t)sms * 16 ? (rounds > 0 ? rounds : 1) : (int64_t)sms * 16);
+  // 4 CTAs per SM (register-limited): one wave, several rounds per CTA so that the metadata prefetch has a next round
+  const unsigned grid = (unsigned)(rounds < (int64_t)sms * 4 ? (rounds > 0 ? rounds : 1) : (int64_t)sms * 4);
   if (OPT != kOptNone) PTREC_CUDA(cudaMemsetAsync(long_count, 0, sizeof(int), st));
   fused_update_kernel<VEC, LPR, OPT><<<grid, kUpdThreads, 0, st>>>(
-      table_ptrs, s1, s2, T, D, feats, F, B, sorted_keys, perm, seg_start, seg_table, n_seg, grad_out,
+      table_ptrs, s1, s2, T, D, feats, F, B, sorted_keys, perm, seg_start, seg_meta, n_seg, grad_out,
       stride, bag_scale, op, long_count, long_list, row_grad);
   PTREC_LAUNCH_CHECK("fused_update_kernel");
   if (OPT != kOptNone) {
     fused_update_long_kernel<VEC, LPR, OPT><<<sms * 2, kLongThreads, 0, st>>>(
-        table_ptrs, s1, s2, T, D, feats, F, B, sorted_keys, perm, seg_start, seg_table, grad_out, stride,
+        table_ptrs, s1, s2, T, D, feats, F, B, sorted_keys, perm, seg_start, seg_meta, grad_out, stride,
         bag_scale, op, long_count, long_list);
     PTREC_LAUNCH_CHECK("fused_update_long_kernel");
   }
@@ -364,12 +372,12 @@ template <int OPT>
 static int dispatch_D(void* const* table_ptrs, void* const* s1, void* const* s2, int T, int D,
                       const ptrec_feature_desc* feats, int F, int64_t B, int64_t N,
                       const uint32_t* sorted_keys, const int32_t* perm, const int32_t* seg_start,
-                      const int32_t* seg_table, const int32_t* n_seg, const float* grad_out,
+                      const ptrec_segment_meta* seg_meta, const int32_t* n_seg, const float* grad_out,
                       int64_t stride, const float* bag_scale, const OptParams& op, int* long_count,
                       int32_t* long_list, float* row_grad, cudaStream_t st) {
 #define PTREC_UPD(V, P) \
   return launch_update<V, P, OPT>(table_ptrs, s1, s2, T, D, feats, F, B, N, sorted_keys, perm, seg_start, \
-                                  seg_table, n_seg, grad_out, stride, bag_scale, op, long_count,        \
+                                  seg_meta, n_seg, grad_out, stride, bag_scale, op, long_count,        \
                                   long_list, row_grad, st)
   if (D == 1) PTREC_UPD(1, 1);
   if (D == 2) PTREC_UPD(2, 1);
@@ -415,14 +423,14 @@ extern "C" int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* s
                                          int32_t dtype, const ptrec_feature_desc* feats,
                                          const ptrec_feature_desc* feats_host, int32_t F, int64_t B,
                                          const uint32_t* sorted_keys, const int32_t* perm,
-                                         const int32_t* seg_start, const int32_t* seg_table,
+                                         const int32_t* seg_start, const ptrec_segment_meta* seg_meta,
                                          const int32_t* n_seg, const float* grad_out,
                                          int64_t grad_row_stride, const float* bag_scale,
                                          const ptrec_optim_args* opt_host, void* workspace,
                                          size_t workspace_bytes, void* stream) {
   int rc = check_common(T, D, dtype, F, grad_out, grad_row_stride);
   if (rc != PTREC_OK) return rc;
-  PTREC_CHECK_ARG(table_ptrs && feats && feats_host && sorted_keys && perm && seg_start && seg_table && n_seg &&
+  PTREC_CHECK_ARG(table_ptrs && feats && feats_host && sorted_keys && perm && seg_start && seg_meta && n_seg &&
                       grad_out && opt_host, PTREC_EINVAL, "bwd_fused: null pointer");
   const int64_t N = total_slots(feats_host, F, B);
   PTREC_CHECK_ARG(workspace && workspace_bytes >= ptrec_embedding_bwd_workspace_bytes(N, D), PTREC_EWORKSPACE,
@@ -446,7 +454,7 @@ extern "C" int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* s
   int32_t* long_list = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(workspace) + 256);
   cudaStream_t st = (cudaStream_t)stream;
 #define PTREC_ARGS                                                                                      \
-  table_ptrs, state1_ptrs, state2_ptrs, T, D, feats, F, B, N, sorted_keys, perm, seg_start, seg_table, n_seg, \
+  table_ptrs, state1_ptrs, state2_ptrs, T, D, feats, F, B, N, sorted_keys, perm, seg_start, seg_meta, n_seg, \
       grad_out, grad_row_stride, bag_scale, op, long_count, long_list, nullptr, st
   switch (opt_host->kind) {
     case PTREC_OPT_SGD:
@@ -476,7 +484,7 @@ extern "C" int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* s
 #define PTREC_NAMED(NAME, KIND)                                                                          \
   extern "C" int NAME(void* const* a, void* const* b, void* const* c, int32_t T, int32_t D, int64_t rs, int32_t dt, \
                       const ptrec_feature_desc* f, const ptrec_feature_desc* fh, int32_t F, int64_t B,   \
-                      const uint32_t* k, const int32_t* p, const int32_t* s, const int32_t* st,          \
+                      const uint32_t* k, const int32_t* p, const int32_t* s, const ptrec_segment_meta* st,          \
                       const int32_t* n, const float* g, int64_t gs, const float* bs,                     \
                       const ptrec_optim_args* o, void* ws, size_t wsb, void* stream) {                   \
     PTREC_CHECK_ARG(o && o->kind == KIND, PTREC_EINVAL, #NAME ": opt_host->kind must be " #KIND);        \
@@ -493,18 +501,18 @@ extern "C" int ptrec_embedding_bwd_segment_sum(int32_t T, int32_t D, const ptrec
                                                const ptrec_feature_desc* feats_host, int32_t F,
                                                int64_t B, const uint32_t* sorted_keys,
                                                const int32_t* perm, const int32_t* seg_start,
-                                               const int32_t* seg_table, const int32_t* n_seg,
+                                               const ptrec_segment_meta* seg_meta, const int32_t* n_seg,
                                                const float* grad_out, int64_t grad_row_stride,
                                                const float* bag_scale, float* row_grad, void* stream) {
   int rc = check_common(T, D, PTREC_F32, F, grad_out, grad_row_stride);
   if (rc != PTREC_OK) return rc;
-  PTREC_CHECK_ARG(feats && feats_host && sorted_keys && perm && seg_start && seg_table && n_seg && row_grad,
+  PTREC_CHECK_ARG(feats && feats_host && sorted_keys && perm && seg_start && seg_meta && n_seg && row_grad,
                   PTREC_EINVAL, "segment_sum: null pointer");
   PTREC_CHECK_ARG(aligned16(row_grad), PTREC_EALIGN, "segment_sum: row_grad must be 16-byte aligned");
   const int64_t N = total_slots(feats_host, F, B);
   if (N == 0) return PTREC_OK;
   OptParams op{};
   return dispatch_D<kOptNone>(nullptr, nullptr, nullptr, T, D, feats, F, B, N, sorted_keys, perm, seg_start,
-                              seg_table, n_seg, grad_out, grad_row_stride, bag_scale, op, nullptr,
+                              seg_meta, n_seg, grad_out, grad_row_stride, bag_scale, op, nullptr,
                               nullptr, row_grad, (cudaStream_t)stream);
 }

@@ -236,11 +236,18 @@ struct SegOut {
   int64_t B;
   int64_t N;
   int32_t* seg_start;
-  int32_t* seg_table;
+  ptrec_segment_meta* seg_meta;
+  const uint32_t* keys;
+  const int32_t* perm;
   __device__ void operator()(int64_t j, int prefix, int v) const {
     if (v) {
       seg_start[prefix] = (int32_t)j;
-      seg_table[prefix] = table_of_slot(lay, B, j);
+      int4 m;
+      m.x = (int)keys[j];
+      m.y = perm[j];
+      m.z = table_of_slot(lay, B, j);
+      m.w = 0;
+      *reinterpret_cast<int4*>(seg_meta + prefix) = m;  // one 16-byte record per segment
     }
     if (j == N - 1) seg_start[prefix + v] = (int32_t)N;
   }
@@ -294,9 +301,9 @@ extern "C" int ptrec_sort_dedup(const ptrec_feature_desc* feats, const ptrec_fea
                                 int32_t F, int32_t T, const int64_t* table_rows, int64_t max_rows_host,
                                 const int64_t* ids, const int32_t* lens, int64_t B,
                                 uint32_t* sorted_keys, int32_t* perm, int32_t* seg_start,
-                                int32_t* seg_table, int32_t* n_seg, void* workspace,
+                                ptrec_segment_meta* seg_meta, int32_t* n_seg, void* workspace,
                                 size_t workspace_bytes, void* stream) {
-  PTREC_CHECK_ARG(feats && feats_host && table_rows && ids && sorted_keys && perm && seg_start && seg_table && n_seg,
+  PTREC_CHECK_ARG(feats && feats_host && table_rows && ids && sorted_keys && perm && seg_start && seg_meta && n_seg,
                   PTREC_EINVAL, "sort_dedup: null pointer");
   PTREC_CHECK_ARG(max_rows_host >= 1 && max_rows_host < (int64_t)0xFFFFFFFFLL, PTREC_EUNSUPPORTED,
                   "sort_dedup: tables must have < 2^32-1 rows");
@@ -355,7 +362,7 @@ extern "C" int ptrec_sort_dedup(const ptrec_feature_desc* feats, const ptrec_fea
 
   const int stiles = scan_num_tiles(N);
   HeadIn hin{lay, B, sorted_keys};
-  SegOut sout{lay, B, N, seg_start, seg_table};
+  SegOut sout{lay, B, N, seg_start, seg_meta, sorted_keys, perm};
   scan_tile_sums_kernel<<<stiles, kScanThreads, 0, st>>>(hin, N, tile_sums);
   PTREC_LAUNCH_CHECK("scan_tile_sums_kernel(heads)");
   scan_top_kernel<<<1, 1024, 0, st>>>(tile_sums, stiles, n_seg);

@@ -183,7 +183,12 @@ def _gather_call(lib, tables, layout, ids, lens, batch, out, bag_scale, err_flag
 
 
 class SortResult:
-    __slots__ = ("sorted_keys", "perm", "seg_start", "seg_table", "n_seg", "N")
+    __slots__ = ("sorted_keys", "perm", "seg_start", "seg_meta", "n_seg", "N")
+
+    @property
+    def seg_table(self):
+        """table index of each segment (column 2 of the 16-byte ptrec_segment_meta records)"""
+        return self.seg_meta[:, 2]
 
 
 def sort_dedup(tables: TableSet, layout: FeatureLayout, ids: torch.Tensor,
@@ -198,7 +203,7 @@ def sort_dedup(tables: TableSet, layout: FeatureLayout, ids: torch.Tensor,
     r.sorted_keys = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
     r.perm = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
     r.seg_start = torch.empty(N + 1, dtype=torch.int32, device=dev)
-    r.seg_table = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    r.seg_meta = torch.empty(max(N, 1), 4, dtype=torch.int32, device=dev)  # ptrec_segment_meta[N]
     r.n_seg = torch.empty(1, dtype=torch.int32, device=dev)
     nbytes = lib.ptrec_sort_dedup_workspace_bytes(N, layout.n_tables)
     ws = _workspace("sort_dedup", nbytes, dev)
@@ -206,7 +211,7 @@ def sort_dedup(tables: TableSet, layout: FeatureLayout, ids: torch.Tensor,
     _lib.check(lib.ptrec_sort_dedup(
         ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)), layout.host,
         layout.n_features, layout.n_tables, _ptr(tables.rows), tables.max_rows, _ptr(ids), _ptr(lens),
-        batch, _ptr(r.sorted_keys), _ptr(r.perm), _ptr(r.seg_start), _ptr(r.seg_table), _ptr(r.n_seg),
+        batch, _ptr(r.sorted_keys), _ptr(r.perm), _ptr(r.seg_start), _ptr(r.seg_meta), _ptr(r.n_seg),
         _ptr(ws), ws.numel(), _stream(dev)), "ptrec_sort_dedup")
     return r
 
@@ -236,7 +241,7 @@ def bwd_fused(tables: TableSet, state1_ptrs: Optional[torch.Tensor], state2_ptrs
     _lib.check(fn(_ptr(tables.ptrs), _ptr(state1_ptrs), _ptr(state2_ptrs), layout.n_tables, layout.dim,
                   tables.row_stride or layout.dim, _lib.F32, ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)),
                   layout.host, layout.n_features, batch, _ptr(srt.sorted_keys), _ptr(srt.perm),
-                  _ptr(srt.seg_start), _ptr(srt.seg_table), _ptr(srt.n_seg), _ptr(grad_out),
+                  _ptr(srt.seg_start), _ptr(srt.seg_meta), _ptr(srt.n_seg), _ptr(grad_out),
                   grad_row_stride, _ptr(bag_scale), ctypes.byref(opt), _ptr(ws), ws.numel(),
                   _stream(dev)), _BWD_FN[opt.kind])
 
@@ -253,7 +258,7 @@ def segment_sum(layout: FeatureLayout, batch: int, srt: SortResult, grad_out: to
         layout.n_tables, layout.dim,
         ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)), layout.host,
         layout.n_features, batch, _ptr(srt.sorted_keys), _ptr(srt.perm), _ptr(srt.seg_start),
-        _ptr(srt.seg_table), _ptr(srt.n_seg), _ptr(grad_out), grad_out.stride(0), _ptr(bag_scale),
+        _ptr(srt.seg_meta), _ptr(srt.n_seg), _ptr(grad_out), grad_out.stride(0), _ptr(bag_scale),
         _ptr(row_grad), _stream(dev)), "ptrec_embedding_bwd_segment_sum")
     return row_grad
 

@@ -150,6 +150,9 @@ def _check_sort(layout, tables, ids_dev, lens_dev, B, specs, id_list, lens_list,
     n_seg = int(srt.n_seg.item())
     seg_start = srt.seg_start.cpu()[: n_seg + 1].long()
     seg_table = srt.seg_table.cpu()[:n_seg].long()
+    meta = srt.seg_meta.cpu()[:n_seg]
+    assert torch.equal(_u32(meta[:, 0]), keys[seg_start[:n_seg]]), "segment record key"
+    assert torch.equal(meta[:, 1].long(), perm[seg_start[:n_seg]]), "segment record first slot"
     # oracle: per table, concatenate its features' slots in layout order
     T = len(rows)
     per_ids, per_valid, base = [], [], []
