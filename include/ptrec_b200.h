@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 6
+#define PTREC_ABI_VERSION 7
 
 /* error codes */
 #define PTREC_OK 0
@@ -143,6 +143,20 @@ int ptrec_embedding_gather_pool_fwd(const void* const* table_ptrs, const int64_t
                                     const int64_t* ids, const int32_t* lens, int64_t B, float* out,
                                     int64_t out_row_stride, float* bag_scale, int32_t* err_flag,
                                     void* stream);
+
+/* K1 over ROW-WISE SHARDS in peer memory (C1, forward): table t is split over G GPUs of one NVLink domain,
+ * owner(id) = id mod G, local row = id div G; shard_ptrs [T][G] holds the base pointer of every shard as seen from
+ * THIS device (its own shard plus the peers' through symmetric / IPC mappings), so the row loads travel over
+ * NVLink / NVSwitch inside the gather kernel and the forward needs no collective.  table_rows [T] = GLOBAL row
+ * counts.  One-hot fields only (bag_len 1, PTREC_MASK_NONE).  The caller orders the owners' updates before these
+ * reads (one collective per step, see pytorchrec_b200/distributed/sharded.py).  No reference counterpart
+ * (single-device reference, torchrec/task/Task.py:187-190). */
+int ptrec_embedding_gather_pool_fwd_sharded(const void* const* shard_ptrs, const int64_t* table_rows,
+                                            int32_t T, int32_t G, int32_t D, int64_t row_stride, int32_t dtype,
+                                            const ptrec_feature_desc* feats,
+                                            const ptrec_feature_desc* feats_host, int32_t F,
+                                            const int64_t* ids, int64_t B, float* out, int64_t out_row_stride,
+                                            int32_t* err_flag, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K2a segmented sort + dedup of the lookups of one batch (the integer half of the backward).
@@ -291,6 +305,22 @@ int ptrec_a2a_pack_by_owner(const int64_t* ids, int64_t B, int32_t F, int32_t G,
  * widths of the same fields travel in one collective) */
 int ptrec_a2a_scatter_rows(const float* src, int64_t src_row_stride, const int32_t* ret_pos, int64_t B,
                            int32_t F, int32_t D, float scale, float* dst, int64_t dst_row_stride, void* stream);
+
+
+/* Peer-memory dispatch (no all-to-all): the same lists and gradient rows are STORED straight into the owners'
+ * receive buffers over NVLink, in the layout the owner-side ptrec_sort_dedup / ptrec_embedding_bwd_fused read:
+ *   peer_ids [G] device array; peer_ids[o] = rank o's id buffer [F, G_src, C] int64 (the owner keeps unused slots
+ *            at -1: it resets its buffer after consuming it); this rank writes peer_ids[o][(f*G + my_rank)*C + slot]
+ *   peer_dst [G] device array; peer_dst[o] = rank o's gradient buffer [G_src*F*C, dst_row_stride] float32; this rank
+ *            writes row my_rank*F*C + (ret_pos mod F*C), columns [dst_col, dst_col + D)
+ * ret_pos keeps the meaning above.  The caller fences (one small collective) between these stores and the owners'
+ * reads, and between the owners' reads and the next step's stores. */
+int ptrec_a2a_pack_by_owner_peer(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C, int32_t my_rank,
+                                 int64_t* const* peer_ids, int32_t* ret_pos, int32_t* overflow, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+int ptrec_a2a_scatter_rows_peer(const float* src, int64_t src_row_stride, const int32_t* ret_pos, int64_t B,
+                                int32_t F, int32_t D, float scale, float* const* peer_dst, int64_t dst_row_stride,
+                                int64_t dst_col, int32_t C, int32_t G, int32_t my_rank, void* stream);
 
 #ifdef __cplusplus
 }

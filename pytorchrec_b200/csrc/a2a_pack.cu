@@ -7,6 +7,12 @@
 //     ret_pos[f, b] = (owner * F + f) * C + slot      (or -1 if the list overflowed; flagged)
 // Slots are assigned in batch order (stable), which keeps the owner's sort / segment sums bit-reproducible.
 // Bound: these move 8-16 B per lookup; they are launch-latency bound at the configs' sizes.
+//
+// Peer mode (ptrec_a2a_*_peer): the lists and the gradient rows are stored DIRECTLY into the owner's receive buffers
+// through peer pointers (NVLink / NVSwitch stores), in the layout the owner-side sort and fused update read:
+//     owner_ids [f, src, slot]          owner_grads [(src*F + f)*C + slot, :]
+// so the dispatch needs no all-to-all; the caller orders "all pushes done" before the owner consumes them with one
+// small collective (a fence), and the owner resets its own id lists to -1 after consuming them.
 #include "common.cuh"
 
 namespace ptrec {
@@ -48,10 +54,13 @@ __global__ void pack_scan_kernel(int* __restrict__ counts, int G, int tiles, int
 
 __global__ void __launch_bounds__(kPackThreads)
 pack_scatter_kernel(const int64_t* __restrict__ ids, int64_t B, int F, int G, int tiles, int C,
-                    const int* __restrict__ bases, int64_t* __restrict__ send_ids, int32_t* __restrict__ ret_pos) {
+                    const int* __restrict__ bases, int64_t* __restrict__ send_ids, int32_t* __restrict__ ret_pos,
+                    int64_t* const* __restrict__ peer_ids, int my_rank) {
   constexpr int NW = kPackThreads / 32;
   __shared__ int s_cnt[NW][kMaxRanks];
   __shared__ int s_base[kMaxRanks];
+  __shared__ int64_t* s_peer[kMaxRanks];
+  if (peer_ids != nullptr && threadIdx.x < G) s_peer[threadIdx.x] = peer_ids[threadIdx.x];
   const int f = blockIdx.y, tile = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < NW * kMaxRanks; i += kPackThreads) (&s_cnt[0][0])[i] = 0;
@@ -97,7 +106,10 @@ pack_scatter_kernel(const int64_t* __restrict__ ids, int64_t B, int F, int G, in
         const int slot = s_cnt[warp][dest[i]] + rank[i];
         if (slot < C) {
           pos = (int32_t)(((int64_t)dest[i] * F + f) * C + slot);
-          send_ids[pos] = id[i] / G;
+          if (peer_ids != nullptr)
+            s_peer[dest[i]][((int64_t)f * G + my_rank) * C + slot] = id[i] / G;
+          else
+            send_ids[pos] = id[i] / G;
         }
       }
       ret_pos[(int64_t)f * B + b] = pos;
@@ -122,6 +134,26 @@ scatter_rows_kernel(const float* __restrict__ src, int64_t src_row_stride, const
   store_row<VEC>(dst + (int64_t)p * dst_row_stride + lane * VEC, r);
 }
 
+// peer_dst[owner][(my_rank*F*C + (pos mod F*C)) * stride + col : +D] = scale * src[b, f, :]
+template <int VEC, int LPR>
+__global__ void __launch_bounds__(256)
+scatter_rows_peer_kernel(const float* __restrict__ src, int64_t src_row_stride, const int32_t* __restrict__ pos,
+                         int64_t B, int F, int D, float scale, float* const* __restrict__ peer_dst,
+                         int64_t dst_row_stride, int64_t dst_col, int FC, int my_rank) {
+  const int64_t g = ((int64_t)blockIdx.x * 256 + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;
+  if (g >= B * F || lane * VEC >= D) return;
+  const int64_t b = g / F;
+  const int f = (int)(g - b * F);
+  const int32_t p = pos[(int64_t)f * B + b];
+  if (p < 0) return;
+  const int owner = p / FC;
+  const int64_t row = (int64_t)my_rank * FC + (p - owner * FC);
+  RowVec<VEC> r = load_row_stream<VEC>(src + b * src_row_stride + (int64_t)f * D + lane * VEC);
+  r.scale(scale);
+  store_row<VEC>(peer_dst[owner] + row * dst_row_stride + dst_col + lane * VEC, r);
+}
+
 }  // namespace ptrec
 
 using namespace ptrec;
@@ -131,16 +163,18 @@ extern "C" size_t ptrec_a2a_pack_workspace_bytes(int64_t B, int32_t F, int32_t G
   return align_up((size_t)(F * tiles * G) * sizeof(int) + 16, 256);
 }
 
-extern "C" int ptrec_a2a_pack_by_owner(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C,
-                                       int64_t* send_ids, int32_t* ret_pos, int32_t* overflow, void* workspace,
-                                       size_t workspace_bytes, void* stream) {
-  PTREC_CHECK_ARG(ids && send_ids && ret_pos && workspace, PTREC_EINVAL, "a2a_pack: null pointer");
+static int pack_impl(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C, int64_t* send_ids,
+                     int64_t* const* peer_ids, int32_t my_rank, int32_t* ret_pos, int32_t* overflow, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  PTREC_CHECK_ARG(ids && (send_ids || peer_ids) && ret_pos && workspace, PTREC_EINVAL, "a2a_pack: null pointer");
+  PTREC_CHECK_ARG(my_rank >= 0 && my_rank < G, PTREC_EINVAL, "a2a_pack: rank %d outside [0, %d)", my_rank, G);
   PTREC_CHECK_ARG(B >= 0 && F >= 1 && F <= 65535 && G >= 1 && G <= kMaxRanks && C >= 1, PTREC_EINVAL,
                   "a2a_pack: bad sizes B=%lld F=%d G=%d C=%d", (long long)B, F, G, C);
   PTREC_CHECK_ARG((int64_t)G * F * C < (int64_t)0x7fffffff, PTREC_EUNSUPPORTED, "a2a_pack: G*F*C must be < 2^31");
   PTREC_CHECK_ARG(workspace_bytes >= ptrec_a2a_pack_workspace_bytes(B, F, G), PTREC_EWORKSPACE, "a2a_pack: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  PTREC_CUDA(cudaMemsetAsync(send_ids, 0xFF, (size_t)G * F * C * sizeof(int64_t), st));  // -1 = empty slot
+  if (send_ids != nullptr)
+    PTREC_CUDA(cudaMemsetAsync(send_ids, 0xFF, (size_t)G * F * C * sizeof(int64_t), st));  // -1 = empty slot
   if (B == 0) return PTREC_OK;
   const int tiles = (int)ceil_div(B, kPackTile);
   int* counts = reinterpret_cast<int*>(workspace);
@@ -149,9 +183,25 @@ extern "C" int ptrec_a2a_pack_by_owner(const int64_t* ids, int64_t B, int32_t F,
   PTREC_LAUNCH_CHECK("pack_count_kernel");
   pack_scan_kernel<<<F, kMaxRanks, 0, st>>>(counts, G, tiles, C, overflow);
   PTREC_LAUNCH_CHECK("pack_scan_kernel");
-  pack_scatter_kernel<<<grid, kPackThreads, 0, st>>>(ids, B, F, G, tiles, C, counts, send_ids, ret_pos);
+  pack_scatter_kernel<<<grid, kPackThreads, 0, st>>>(ids, B, F, G, tiles, C, counts, send_ids, ret_pos, peer_ids,
+                                                     my_rank);
   PTREC_LAUNCH_CHECK("pack_scatter_kernel");
   return PTREC_OK;
+}
+
+extern "C" int ptrec_a2a_pack_by_owner(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C,
+                                       int64_t* send_ids, int32_t* ret_pos, int32_t* overflow, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  PTREC_CHECK_ARG(send_ids, PTREC_EINVAL, "a2a_pack: null send_ids");
+  return pack_impl(ids, B, F, G, C, send_ids, nullptr, 0, ret_pos, overflow, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ptrec_a2a_pack_by_owner_peer(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C,
+                                            int32_t my_rank, int64_t* const* peer_ids, int32_t* ret_pos,
+                                            int32_t* overflow, void* workspace, size_t workspace_bytes,
+                                            void* stream) {
+  PTREC_CHECK_ARG(peer_ids, PTREC_EINVAL, "a2a_pack_peer: null peer pointer array");
+  return pack_impl(ids, B, F, G, C, nullptr, peer_ids, my_rank, ret_pos, overflow, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ptrec_a2a_scatter_rows(const float* src, int64_t src_row_stride, const int32_t* ret_pos, int64_t B,
@@ -173,6 +223,42 @@ extern "C" int ptrec_a2a_scatter_rows(const float* src, int64_t src_row_stride, 
                                                     dst_row_stride);                                     \
     PTREC_LAUNCH_CHECK("scatter_rows_kernel");                                                           \
     return PTREC_OK;                                                                                     \
+  }
+  if (D == 1) PTREC_SC(1, 1)
+  if (D == 2) PTREC_SC(2, 1)
+  const int lanes = D / 4;
+  if (lanes <= 1) PTREC_SC(4, 1)
+  if (lanes <= 2) PTREC_SC(4, 2)
+  if (lanes <= 4) PTREC_SC(4, 4)
+  if (lanes <= 8) PTREC_SC(4, 8)
+  if (lanes <= 16) PTREC_SC(4, 16)
+  PTREC_SC(4, 32)
+#undef PTREC_SC
+}
+
+extern "C" int ptrec_a2a_scatter_rows_peer(const float* src, int64_t src_row_stride, const int32_t* ret_pos,
+                                           int64_t B, int32_t F, int32_t D, float scale, float* const* peer_dst,
+                                           int64_t dst_row_stride, int64_t dst_col, int32_t C, int32_t G,
+                                           int32_t my_rank, void* stream) {
+  PTREC_CHECK_ARG(src && ret_pos && peer_dst, PTREC_EINVAL, "a2a_scatter_rows_peer: null pointer");
+  PTREC_CHECK_ARG(G >= 1 && G <= kMaxRanks && my_rank >= 0 && my_rank < G && C >= 1, PTREC_EINVAL,
+                  "a2a_scatter_rows_peer: bad G=%d rank=%d C=%d", G, my_rank, C);
+  const bool d_ok = D == 1 || D == 2 || (D >= 4 && D <= 128 && D % 4 == 0);
+  PTREC_CHECK_ARG(d_ok, PTREC_EUNSUPPORTED, "a2a_scatter_rows_peer: D=%d unsupported", D);
+  const int vec = D >= 4 ? 4 : D;
+  PTREC_CHECK_ARG(((uintptr_t)src % (vec * 4)) == 0 && src_row_stride % vec == 0 && dst_row_stride >= D &&
+                      dst_row_stride % vec == 0 && dst_col % vec == 0,
+                  PTREC_EALIGN, "a2a_scatter_rows_peer: misaligned");
+  if (B == 0) return PTREC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int FC = F * C;
+#define PTREC_SC(V, P)                                                                                         \
+  {                                                                                                            \
+    const unsigned grid = (unsigned)ceil_div(B * F * P, 256);                                                  \
+    scatter_rows_peer_kernel<V, P><<<grid, 256, 0, st>>>(src, src_row_stride, ret_pos, B, F, D, scale,         \
+                                                         peer_dst, dst_row_stride, dst_col, FC, my_rank);      \
+    PTREC_LAUNCH_CHECK("scatter_rows_peer_kernel");                                                            \
+    return PTREC_OK;                                                                                           \
   }
   if (D == 1) PTREC_SC(1, 1)
   if (D == 2) PTREC_SC(2, 1)

@@ -27,18 +27,22 @@ constexpr int kOneHotThreads = 128;  // 4 warps
 constexpr int kUnroll = 4;
 
 // ------------------------------------------------------------------------------------ one-hot
-template <int VEC, int LPR>
+// SHARDED: the tables are row-wise shards owned by `shards` GPUs of one NVLink domain (owner = id mod shards,
+// local row = id div shards); table_ptrs is [T][shards] and may hold PEER pointers, so the same 128-bit row loads
+// travel over NVLink / NVSwitch and the lookup needs no collective.  table_rows stays the GLOBAL row count.
+template <int VEC, int LPR, bool SHARDED>
 __global__ void __launch_bounds__(kOneHotThreads)
 gather_onehot_kernel(const void* const* __restrict__ table_ptrs, const int64_t* __restrict__ table_rows,
                      int D, int64_t row_stride, const ptrec_feature_desc* __restrict__ feats, FeatSel sel,
                      const int64_t* __restrict__ ids, int64_t B, float* __restrict__ out,
-                     int64_t out_row_stride, int32_t* err_flag, int use_bulk) {
+                     int64_t out_row_stride, int32_t* err_flag, int use_bulk, int shards) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: ids tile [n_sel][kOneHotTileB] int64 | per-selected-feature {table ptr, rows, out_col, id_base}
+  // layout: ids tile [n_sel][kOneHotTileB] int64 | per-selected-feature {table ptr x shards, rows, out_col, flags}
   int64_t* s_ids = reinterpret_cast<int64_t*>(smem_raw);
   const int nsel = sel.n;
+  const int nsh = SHARDED ? shards : 1;
   const float** s_tab = reinterpret_cast<const float**>(s_ids + (size_t)nsel * kOneHotTileB);
-  int64_t* s_rows = reinterpret_cast<int64_t*>(s_tab + nsel);
+  int64_t* s_rows = reinterpret_cast<int64_t*>(s_tab + (size_t)nsel * nsh);
   int64_t* s_col = s_rows + nsel;
   int64_t* s_flag = s_col + nsel;
   __shared__ __align__(8) uint64_t s_bar;
@@ -56,7 +60,8 @@ gather_onehot_kernel(const void* const* __restrict__ table_ptrs, const int64_t* 
   }
   for (int s = tid; s < nsel; s += blockDim.x) {
     const ptrec_feature_desc fd = feats[sel.idx[s]];
-    s_tab[s] = reinterpret_cast<const float*>(table_ptrs[fd.table]);
+    for (int g = 0; g < nsh; ++g)
+      s_tab[(size_t)s * nsh + g] = reinterpret_cast<const float*>(table_ptrs[(size_t)fd.table * nsh + g]);
     s_rows[s] = table_rows[fd.table];
     s_col[s] = fd.out_col;
     s_flag[s] = fd.flags;
@@ -94,7 +99,24 @@ gather_onehot_kernel(const void* const* __restrict__ table_ptrs, const int64_t* 
         const int64_t id = s_ids[(size_t)s * kOneHotTileB + bl];
         dst[u] = out + (b0 + bl) * out_row_stride + s_col[s] + lane * VEC;
         if ((uint64_t)id < (uint64_t)s_rows[s]) {
-          if (lane_on) r[u] = load_row_stream<VEC>(s_tab[s] + id * row_stride + lane * VEC);
+          const float* tab;
+          int64_t row;
+          if (SHARDED) {
+            int own;
+            if ((uint64_t)id >> 32) {
+              row = id / nsh;
+              own = (int)(id - row * nsh);
+            } else {  // 32-bit divide: the common case
+              const uint32_t q = (uint32_t)id / (uint32_t)nsh;
+              own = (int)((uint32_t)id - q * (uint32_t)nsh);
+              row = q;
+            }
+            tab = s_tab[(size_t)s * nsh + own];
+          } else {
+            tab = s_tab[s];
+            row = id;
+          }
+          if (lane_on) r[u] = load_row_stream<VEC>(tab + row * row_stride + lane * VEC);
         } else if (err_flag != nullptr && lane == 0 && !(id < 0 && (s_flag[s] & PTREC_FEAT_NEG_IS_PAD))) {
           *err_flag = 1;
         }
@@ -219,14 +241,23 @@ static int launch_gather(const void* const* table_ptrs, const int64_t* table_row
                          const ptrec_feature_desc* feats, const FeatSel& onehot, const FeatSel& bags,
                          int max_bag_len, const int64_t* ids, const int32_t* lens, int64_t B,
                          float* out, int64_t out_row_stride, float* bag_scale, int32_t* err_flag,
-                         cudaStream_t st) {
+                         int shards, cudaStream_t st) {
   const int ids_al = aligned16(ids) ? 1 : 0;
   if (onehot.n > 0) {
     const int use_bulk = (ids_al && (B % 2 == 0)) ? 1 : 0;
-    const size_t smem = (size_t)onehot.n * (kOneHotTileB * 8 + 8 + 8 + 8 + 8);
+    const size_t smem = (size_t)onehot.n * (kOneHotTileB * 8 + 8 * (shards > 1 ? shards : 1) + 8 + 8 + 8);
     const unsigned grid = (unsigned)ceil_div(B, kOneHotTileB);
-    gather_onehot_kernel<VEC, LPR><<<grid, kOneHotThreads, smem, st>>>(
-        table_ptrs, table_rows, D, row_stride, feats, onehot, ids, B, out, out_row_stride, err_flag, use_bulk);
+    if (shards > 1) {
+      if (smem > 48 * 1024)
+        PTREC_CUDA(cudaFuncSetAttribute(gather_onehot_kernel<VEC, LPR, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gather_onehot_kernel<VEC, LPR, true><<<grid, kOneHotThreads, smem, st>>>(
+          table_ptrs, table_rows, D, row_stride, feats, onehot, ids, B, out, out_row_stride, err_flag, use_bulk,
+          shards);
+    } else {
+      gather_onehot_kernel<VEC, LPR, false><<<grid, kOneHotThreads, smem, st>>>(
+          table_ptrs, table_rows, D, row_stride, feats, onehot, ids, B, out, out_row_stride, err_flag, use_bulk, 1);
+    }
     PTREC_LAUNCH_CHECK("gather_onehot_kernel");
   }
   if (bags.n > 0) {
@@ -333,13 +364,11 @@ extern "C" int ptrec_index_prep(const int64_t* ids_padded, const int32_t* lens, 
   return PTREC_OK;
 }
 
-extern "C" int ptrec_embedding_gather_pool_fwd(const void* const* table_ptrs, const int64_t* table_rows,
-                                               int32_t T, int32_t D, int64_t row_stride, int32_t dtype,
-                                               const ptrec_feature_desc* feats,
-                                               const ptrec_feature_desc* feats_host, int32_t F,
-                                               const int64_t* ids, const int32_t* lens, int64_t B,
-                                               float* out, int64_t out_row_stride, float* bag_scale,
-                                               int32_t* err_flag, void* stream) {
+static int gather_pool_fwd_impl(const void* const* table_ptrs, const int64_t* table_rows, int32_t T, int32_t shards,
+                                int32_t D, int64_t row_stride, int32_t dtype, const ptrec_feature_desc* feats,
+                                const ptrec_feature_desc* feats_host, int32_t F, const int64_t* ids,
+                                const int32_t* lens, int64_t B, float* out, int64_t out_row_stride,
+                                float* bag_scale, int32_t* err_flag, void* stream) {
   PTREC_CHECK_ARG(dtype == PTREC_F32, PTREC_EUNSUPPORTED, "gather: only fp32 tables are built (dtype=%d)", dtype);
   PTREC_CHECK_ARG(T >= 1 && T <= kMaxTables && F >= 1 && F <= kMaxFeatures, PTREC_EINVAL,
                   "gather: T=%d F=%d out of range (max %d)", T, F, kMaxFeatures);
@@ -375,11 +404,13 @@ extern "C" int ptrec_embedding_gather_pool_fwd(const void* const* table_ptrs, co
     }
   }
   PTREC_CHECK_ARG(!need_lens || lens, PTREC_EINVAL, "gather: lens required by a PTREC_MASK_LENS feature");
+  PTREC_CHECK_ARG(shards == 1 || bags.n == 0, PTREC_EUNSUPPORTED,
+                  "gather: row-wise sharded tables serve one-hot fields only (pooled bags stay unsharded)");
   cudaStream_t st = (cudaStream_t)stream;
 
 #define PTREC_GATHER(V, P) \
   return launch_gather<V, P>(table_ptrs, table_rows, D, row_stride, feats, onehot, bags, max_bag_len, ids, lens, B, \
-                             out, out_row_stride, bag_scale, err_flag, st)
+                             out, out_row_stride, bag_scale, err_flag, shards, st)
   if (D == 1) PTREC_GATHER(1, 1);
   if (D == 2) PTREC_GATHER(2, 1);
   const int lanes = D / 4;
@@ -390,4 +421,26 @@ extern "C" int ptrec_embedding_gather_pool_fwd(const void* const* table_ptrs, co
   if (lanes <= 16) PTREC_GATHER(4, 16);
   PTREC_GATHER(4, 32);
 #undef PTREC_GATHER
+}
+
+extern "C" int ptrec_embedding_gather_pool_fwd(const void* const* table_ptrs, const int64_t* table_rows,
+                                               int32_t T, int32_t D, int64_t row_stride, int32_t dtype,
+                                               const ptrec_feature_desc* feats,
+                                               const ptrec_feature_desc* feats_host, int32_t F,
+                                               const int64_t* ids, const int32_t* lens, int64_t B,
+                                               float* out, int64_t out_row_stride, float* bag_scale,
+                                               int32_t* err_flag, void* stream) {
+  return gather_pool_fwd_impl(table_ptrs, table_rows, T, 1, D, row_stride, dtype, feats, feats_host, F, ids, lens, B,
+                              out, out_row_stride, bag_scale, err_flag, stream);
+}
+
+extern "C" int ptrec_embedding_gather_pool_fwd_sharded(const void* const* shard_ptrs, const int64_t* table_rows,
+                                                       int32_t T, int32_t G, int32_t D, int64_t row_stride,
+                                                       int32_t dtype, const ptrec_feature_desc* feats,
+                                                       const ptrec_feature_desc* feats_host, int32_t F,
+                                                       const int64_t* ids, int64_t B, float* out,
+                                                       int64_t out_row_stride, int32_t* err_flag, void* stream) {
+  PTREC_CHECK_ARG(G >= 1 && G <= 64, PTREC_EINVAL, "gather_sharded: G=%d out of range (1..64)", G);
+  return gather_pool_fwd_impl(shard_ptrs, table_rows, T, G, D, row_stride, dtype, feats, feats_host, F, ids, nullptr,
+                              B, out, out_row_stride, nullptr, err_flag, stream);
 }

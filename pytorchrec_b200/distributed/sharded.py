@@ -4,14 +4,28 @@ allreduce (C2).  One process per GPU (torchrun); NCCL over NVLink / NVSwitch thr
 has a reference counterpart, it widens the same hot path to the 8 x B200 box.
 
 Plan:  owner(id) = id mod G,  local_row = id div G.
+
+Peer-memory path (default on NCCL process groups; ``peer=False`` or PTREC_PEER_GATHER=0 selects the other one):
+the shards and the owners' receive buffers live in symmetric memory, every rank holds the peers' pointers, and
+the exchange happens INSIDE the kernels over NVLink / NVSwitch:
+  forward   ONE gather launch per width; its 128-bit row loads go to whichever GPU owns the row  (no collective)
+  backward  pack ids by owner + scatter gradient rows, both stored straight into the owners' buffers
+            -> fence (1-element all_reduce: "every push has landed")
+            -> owner-side sort / dedup / segment-sum / fused optimizer update; owner resets its id lists
+  dense     one flat all_reduce(SUM) / G of the dense-tower gradients — also the fence that orders this step's table
+            updates and buffer reuse before the next step's peer reads and pushes.
+No kernel waits on another rank: cross-rank ordering comes only from stream order + those two collectives.
+
+All-to-all path (NCCL only; any backend that offers all_to_all_single):
   forward   pack ids by owner (fixed-capacity lists, no host sync)  -> all_to_all(ids)
             -> owner-side fused gather straight into the return layout -> all_to_all(rows)
             -> local gather by slot  -> [B, F, D]
   backward  scatter gradient rows into the send layout -> all_to_all(grads)
             -> owner-side sort / dedup / segment-sum / fused optimizer update (no gradient returns)
-  dense     one flat all_reduce(SUM) / G of the dense-tower gradients.
 """
 import math
+import os
+import weakref
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -35,6 +49,17 @@ def list_capacity(batch: int, world: int, factor: float = 1.25) -> int:
     return min((c + 15) // 16 * 16, (batch + 15) // 16 * 16)
 
 
+_PEER_MODULES: "weakref.WeakSet" = weakref.WeakSet()  # RowWiseShardedEmbedding instances on the peer-memory path
+
+
+def _mark_fenced(group) -> None:
+    """A collective over ``group`` was just enqueued on the current stream: everything the ranks enqueued before
+    it (table updates, receive-buffer resets) is ordered before whatever any rank enqueues after it."""
+    for m in _PEER_MODULES:
+        if (m.group or dist.group.WORLD) is (group or dist.group.WORLD):
+            m._dirty = False
+
+
 def allreduce_dense_grads(params: Sequence[Tensor], group=None) -> None:
     """Average ``.grad`` of the replicated dense parameters over the ranks with ONE flat all_reduce."""
     grads = [p.grad for p in params if p.grad is not None and not p.grad.is_sparse]
@@ -42,6 +67,7 @@ def allreduce_dense_grads(params: Sequence[Tensor], group=None) -> None:
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    _mark_fenced(group)
     flat.div_(dist.get_world_size(group))
     off = 0
     for g in grads:
@@ -117,6 +143,63 @@ class _ShardedLookup(torch.autograd.Function):
         return (None, None) + (None,) * (len(mod.dims) * len(mod.columns))
 
 
+class _PeerLookup(torch.autograd.Function):
+    """The same lookup with the exchange inside the kernels (peer loads / stores over NVLink), see module docstring."""
+
+    @staticmethod
+    def forward(ctx, mod: "RowWiseShardedEmbedding", ids: Tensor, *weights):
+        F, B = ids.shape
+        dev = ids.device
+        if mod._dirty:
+            mod.fence(dev)
+        flat = ids.reshape(-1)
+        outs = []
+        for k, D in enumerate(mod.dims):
+            out = ops.gather_fwd_sharded(mod._shard_ptrs[k], mod._rows_global, mod.world, mod._row_stride[k],
+                                         mod.plain_layout(k), flat, B, err_flag=mod.egroups[k].err_flag(dev))
+            outs.append(out.view(B, F, D))
+        ctx.mod, ctx.shape = mod, (F, B)
+        ctx.save_for_backward(ids)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        mod = ctx.mod
+        F, B = ctx.shape
+        G, S = mod.world, mod.slot_width
+        (ids,) = ctx.saved_tensors
+        dev = ids.device
+        C = list_capacity(B, G, mod.capacity_factor)
+        pb = mod.peer_buffers(C, dev)
+        if mod._dirty:  # the owners may still be consuming / resetting their buffers from an earlier backward
+            mod.fence(dev)
+        ret_pos = ops.a2a_pack_by_owner_peer(ids, F, B, G, C, mod.rank, pb["peer_ids"], mod.overflow_flag(dev))
+        for k, D in enumerate(mod.dims):
+            g = grads[k]
+            g = torch.zeros(B, F * D, device=dev) if g is None else g.reshape(B, F * D)
+            if not g.is_contiguous():
+                g = g.contiguous()
+            ops.a2a_scatter_rows_peer(g, ret_pos, B, F, D, mod.grad_scale, pb["peer_g"], S, mod.col_of[k], C, G,
+                                      mod.rank)
+        mod.fence(dev)  # every rank's pushes have landed in every owner's buffers
+        recv_ids, recv_g = pb["recv_ids"], pb["recv_g"]
+        srt = None
+        for k, D in enumerate(mod.dims):
+            eg = mod.egroups[k]
+            bind = eg.binding()
+            if bind is None:
+                raise RuntimeError("row-wise sharded tables need a pytorchrec_b200.optim sparse optimizer")
+            s1, s2, args = bind[0]._fused_prepare(eg, bind[1])  # may interleave weight | state: before taking pointers
+            tables = eg.table_set.refresh([t.weight.data for t in eg.tables])
+            layout = mod.owner_layout(C, k)
+            if srt is None:
+                srt = ops.sort_dedup(tables, layout, recv_ids, None, C)
+            ops.bwd_fused(tables, s1, s2, layout, C, srt, recv_g, None, args, grad_row_stride=S)
+        recv_ids.fill_(-1)  # slots nobody writes next step must read "no lookup"
+        mod._dirty = True   # tables changed, buffers recycled: a fence must precede the next peer access
+        return (None, None) + (None,) * (len(mod.dims) * len(mod.columns))
+
+
 class RowWiseShardedEmbedding(nn.Module):
     """``MultiTableEmbedding`` whose tables are sharded row-wise over the process group.  ``emb_size`` may be a list
     (e.g. ``[16, 1]`` for DeepFM's embedding and first-order tables): every width gets its own table per column
@@ -125,7 +208,7 @@ class RowWiseShardedEmbedding(nn.Module):
     column) — the Criteo-shaped configs; pooled bags stay on ``MultiTableEmbedding``."""
 
     def __init__(self, columns: Sequence[CategoricalColumn], emb_size, group=None,
-                 capacity_factor: float = 1.25, device=None):
+                 capacity_factor: float = 1.25, device=None, peer: Optional[bool] = None):
         super().__init__()
         if not dist.is_initialized():
             raise RuntimeError("RowWiseShardedEmbedding needs an initialised torch.distributed process group")
@@ -152,6 +235,117 @@ class RowWiseShardedEmbedding(nn.Module):
         self._slot_layouts: Dict[int, ops.FeatureLayout] = {}
         self._overflow: Dict[torch.device, Tensor] = {}
         self._bufs: Dict[tuple, dict] = {}
+        # ---- peer-memory path state ----
+        if peer is None:
+            peer = dist.get_backend(group) == "nccl" and os.environ.get("PTREC_PEER_GATHER", "1") != "0"
+        self.peer = bool(peer)
+        self._dirty = False                        # a table update / buffer reset not yet ordered by a collective
+        self._peer_key = None                      # (data_ptr, row stride) of every table when pointers were exchanged
+        self._symm: Dict[int, Tensor] = {}         # data_ptr -> symmetric-memory allocation that backs a table
+        self._symm_handles: list = []
+        self._shard_ptrs: List[Tensor] = []        # per width: int64 [T, G] shard base addresses seen from this GPU
+        self._row_stride: List[int] = []
+        self._rows_global: Optional[Tensor] = None
+        self._plain_layouts: Dict[int, ops.FeatureLayout] = {}
+        self._peer_bufs: Dict[tuple, dict] = {}
+        self._fence_buf: Optional[Tensor] = None
+        if self.peer:
+            _PEER_MODULES.add(self)
+
+    # ---- peer-memory path --------------------------------------------------------------------------------------
+    def fence(self, device) -> None:
+        """1-element all_reduce on the current stream: orders everything every rank enqueued before it ahead of
+        everything any rank enqueues after it (no kernel of ours ever waits on another rank)."""
+        if self._fence_buf is None:
+            self._fence_buf = torch.zeros(1, dtype=torch.float32, device=device)
+        dist.all_reduce(self._fence_buf, group=self.group)
+        _mark_fenced(self.group)
+
+    def sync_peers(self) -> None:
+        """Host-synchronising fence: call (on every rank) after writing table rows outside the training step."""
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self._dirty = False
+
+    def _symm_alloc(self, cap_rows: int):
+        import torch.distributed._symmetric_memory as symm
+
+        def alloc(rows: int, width: int) -> Tensor:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            buf = symm.empty(max(cap_rows, rows), width, dtype=torch.float32, device=dev)  # same size on all ranks
+            self._symm[buf.data_ptr()] = buf
+            return buf[:rows]
+        return alloc
+
+    def _ensure_peer(self, device) -> None:
+        """(Re)exchange the shard pointers when a table's storage moved (first use; the optimizer interleaving
+        weight | state at its first step; a loaded optimizer state).  Collective, and identical on every rank
+        because the same events move the same tables everywhere."""
+        key = tuple((t.weight.data_ptr(), t.weight.stride(0)) for t in self.tables)
+        if key == self._peer_key:
+            return
+        import torch.distributed._symmetric_memory as symm
+        group = self.group or dist.group.WORLD
+        G = self.world
+        self._shard_ptrs, self._row_stride, handles = [], [], []
+        for g, D in zip(self.groups, self.dims):
+            ptrs = []
+            strides = set()
+            for col, t in zip(self.columns, g):
+                w = t.weight
+                buf = self._symm.get(w.data_ptr())
+                if buf is None:  # plain allocation: move the rows into symmetric memory
+                    if w.stride(0) != w.shape[1]:
+                        raise RuntimeError("a sharded table was interleaved outside symmetric memory")
+                    view = w._ptrec_alloc(w.shape[0], w.shape[1])
+                    view.copy_(w.data)
+                    w.data = view
+                    buf = self._symm[w.data_ptr()]
+                hdl = symm.rendezvous(buf, group)
+                handles.append(hdl)
+                ptrs.append([int(p) for p in hdl.buffer_ptrs])
+                strides.add(int(w.stride(0)))
+            if len(strides) != 1:
+                raise RuntimeError(f"tables of one width must share a row stride, got {sorted(strides)}")
+            self._shard_ptrs.append(torch.tensor(ptrs, dtype=torch.int64).to(device))
+            self._row_stride.append(strides.pop())
+        live = {t.weight.data_ptr() for t in self.tables}
+        self._symm = {p: b for p, b in self._symm.items() if p in live}
+        self._symm_handles = handles
+        self._rows_global = torch.tensor([c.category_num for c in self.columns], dtype=torch.int64).to(device)
+        self._peer_key = tuple((t.weight.data_ptr(), t.weight.stride(0)) for t in self.tables)
+        for eg in self.egroups:  # pointer arrays cached on the local tables are stale too
+            eg.table_set.refresh([t.weight.data for t in eg.tables])
+        self.sync_peers()  # the copies above are complete on every rank before anyone reads a peer
+
+    def plain_layout(self, k: int) -> ops.FeatureLayout:
+        lay = self._plain_layouts.get(k)
+        if lay is None:
+            F = len(self.columns)
+            lay = ops.FeatureLayout([dict(table=f, bag_len=1, neg_is_pad=True) for f in range(F)], self.dims[k], F)
+            self._plain_layouts[k] = lay
+        return lay
+
+    def peer_buffers(self, C: int, device) -> dict:
+        """Owner-side receive buffers in symmetric memory + the peers' addresses of theirs (collective on first use
+        of a capacity)."""
+        key = (C, device)
+        b = self._peer_bufs.get(key)
+        if b is None:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group or dist.group.WORLD
+            F, G = len(self.columns), self.world
+            recv_ids = symm.empty(F * G * C, dtype=torch.int64, device=device)
+            recv_g = symm.empty(G * F * C, self.slot_width, dtype=torch.float32, device=device)
+            recv_ids.fill_(-1)
+            recv_g.zero_()
+            h_ids, h_g = symm.rendezvous(recv_ids, group), symm.rendezvous(recv_g, group)
+            b = {"recv_ids": recv_ids, "recv_g": recv_g, "handles": (h_ids, h_g),
+                 "peer_ids": torch.tensor([int(p) for p in h_ids.buffer_ptrs], dtype=torch.int64).to(device),
+                 "peer_g": torch.tensor([int(p) for p in h_g.buffer_ptrs], dtype=torch.int64).to(device)}
+            self._peer_bufs[key] = b
+            self.sync_peers()
+        return b
 
     @property
     def emb_size(self) -> int:
@@ -208,10 +402,16 @@ class RowWiseShardedEmbedding(nn.Module):
         ids = torch.stack([c.get_feature_data(batch).reshape(-1) for c in self.columns])  # [F, B]
         weights = []
         for g in self.groups:
-            for t in g:
+            for col, t in zip(self.columns, g):
                 t._tag()
+                if self.peer and getattr(t.weight, "_ptrec_alloc", None) is None:
+                    t.weight._ptrec_alloc = self._symm_alloc((col.category_num + self.world - 1) // self.world)
                 weights.append(t.weight)
-        outs = _ShardedLookup.apply(self, ids, *weights)
+        if self.peer:
+            self._ensure_peer(ids.device)
+            outs = _PeerLookup.apply(self, ids, *weights)
+        else:
+            outs = _ShardedLookup.apply(self, ids, *weights)
         return outs[0] if self.single else list(outs)
 
     def check_index_errors(self) -> None:
@@ -293,6 +493,8 @@ class ShardedDeepFM(DeepFM):
         for key, v in own.items():
             if not key.startswith("sharded."):
                 v.copy_(state_dict[key])
+        if self.sharded.peer:
+            self.sharded.sync_peers()  # peers read these rows directly
 
     def _dense_params(self) -> List[Tensor]:
         table_ids = {id(t.weight) for t in self.sharded.tables}

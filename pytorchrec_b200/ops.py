@@ -182,6 +182,27 @@ def _gather_call(lib, tables, layout, ids, lens, batch, out, bag_scale, err_flag
         _ptr(err_flag), _stream(dev))
 
 
+def gather_fwd_sharded(shard_ptrs: torch.Tensor, table_rows: torch.Tensor, G: int, row_stride: int,
+                       layout: FeatureLayout, ids: torch.Tensor, batch: int, out: Optional[torch.Tensor] = None,
+                       err_flag: Optional[torch.Tensor] = None):
+    """One-hot lookups over row-wise shards reached through (peer) pointers: ``shard_ptrs`` int64 [T, G] device
+    tensor of shard base addresses as seen from this device, ``table_rows`` int64 [T] GLOBAL row counts."""
+    lib = _lib.load()
+    _require_cuda(ids, out, shard_ptrs, table_rows)
+    dev = ids.device
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.numel() == layout.slots(batch)
+    assert shard_ptrs.dtype == torch.int64 and shard_ptrs.numel() == layout.n_tables * G
+    if out is None:
+        out = torch.empty(batch, layout.out_width, dtype=torch.float32, device=dev)
+    feats_dev = layout.device_array(dev)
+    _lib.check(lib.ptrec_embedding_gather_pool_fwd_sharded(
+        _ptr(shard_ptrs), _ptr(table_rows), layout.n_tables, G, layout.dim, row_stride, _lib.F32,
+        ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)), layout.host,
+        layout.n_features, _ptr(ids), batch, _ptr(out), out.stride(0), _ptr(err_flag), _stream(dev)),
+        "ptrec_embedding_gather_pool_fwd_sharded")
+    return out
+
+
 class SortResult:
     __slots__ = ("sorted_keys", "perm", "seg_start", "seg_meta", "n_seg", "N")
 
@@ -335,6 +356,33 @@ def a2a_scatter_rows(src: torch.Tensor, ret_pos: torch.Tensor, B: int, F: int, D
     assert src.dtype == torch.float32 and src.stride(-1) == 1 and dst.dim() == 2 and dst.stride(1) == 1
     _lib.check(lib.ptrec_a2a_scatter_rows(_ptr(src), src.stride(0), _ptr(ret_pos), B, F, D, float(scale), _ptr(dst),
                                           dst.stride(0), _stream(src.device)), "ptrec_a2a_scatter_rows")
+
+
+def a2a_pack_by_owner_peer(ids: torch.Tensor, F: int, B: int, G: int, C: int, rank: int, peer_ids: torch.Tensor,
+                           overflow: torch.Tensor) -> torch.Tensor:
+    """ids [F, B] -> ret_pos [F, B]; the lists are stored into the owners' id buffers (``peer_ids`` int64 [G] device
+    tensor of their addresses, each [F, G, C] int64)."""
+    lib = _lib.load()
+    _require_cuda(ids, overflow, peer_ids)
+    dev = ids.device
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.numel() == F * B and peer_ids.numel() == G
+    ret_pos = torch.empty(F, B, dtype=torch.int32, device=dev)
+    ws = _workspace("a2a_pack", lib.ptrec_a2a_pack_workspace_bytes(B, F, G), dev)
+    _lib.check(lib.ptrec_a2a_pack_by_owner_peer(_ptr(ids), B, F, G, C, rank, _ptr(peer_ids), _ptr(ret_pos),
+                                                _ptr(overflow), _ptr(ws), ws.numel(), _stream(dev)),
+               "ptrec_a2a_pack_by_owner_peer")
+    return ret_pos
+
+
+def a2a_scatter_rows_peer(src: torch.Tensor, ret_pos: torch.Tensor, B: int, F: int, D: int, scale: float,
+                          peer_dst: torch.Tensor, dst_row_stride: int, dst_col: int, C: int, G: int,
+                          rank: int) -> None:
+    lib = _lib.load()
+    _require_cuda(src, ret_pos, peer_dst)
+    assert src.dtype == torch.float32 and src.stride(-1) == 1 and peer_dst.numel() == G
+    _lib.check(lib.ptrec_a2a_scatter_rows_peer(_ptr(src), src.stride(0), _ptr(ret_pos), B, F, D, float(scale),
+                                               _ptr(peer_dst), dst_row_stride, dst_col, C, G, rank,
+                                               _stream(src.device)), "ptrec_a2a_scatter_rows_peer")
 
 
 # ----------------------------------------------------------------------------------------------

@@ -69,7 +69,9 @@ class _FusedSparseOptimizer(Optimizer):
               and all(n in st and st[n].data_ptr() == buf.data_ptr() + 4 * D * (k + 1) for k, n in enumerate(names)))
         if ok:
             return
-        new = torch.empty(p.shape[0], slots * D, dtype=torch.float32, device=p.device)
+        alloc = getattr(p, "_ptrec_alloc", None)  # e.g. symmetric memory for tables that peers read over NVLink
+        new = (alloc(p.shape[0], slots * D) if alloc is not None
+               else torch.empty(p.shape[0], slots * D, dtype=torch.float32, device=p.device))
         new[:, :D].copy_(p.data)
         for k, (n, fill) in enumerate(zip(names, fills)):
             view = new[:, (k + 1) * D:(k + 2) * D]

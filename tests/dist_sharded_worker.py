@@ -61,6 +61,7 @@ def main():
         full.train_step(gb)
         shard.train_step(lb)
     shard.sharded.check_errors()
+    assert shard.sharded.peer == (os.environ.get("PTREC_PEER_GATHER", "1") != "0")
     fsd, ssd = full.state_dict(), shard.state_dict()
     inv = {0: "embeddings", 1: "first_order"}
     for k, v in ssd.items():
@@ -83,7 +84,7 @@ def main():
     probe.load_state_dict(gathered)
     dist.barrier()
     if rank == 0:
-        print("DIST_SHARDED_OK world=%d" % world, flush=True)
+        print("DIST_SHARDED_OK world=%d peer=%s" % (world, shard.sharded.peer), flush=True)
     torch.cuda.synchronize()
     sys.stdout.flush()
     os._exit(0)  # graphs that captured NCCL kernels make destroy_process_group() hang

@@ -202,8 +202,10 @@ def test_cuda_graph_train_step_equals_eager():
         m.train_step(_ctr_batch(rows, len(dcols), 256, seed=1))
 
 
-def test_sharded_deepfm_matches_unsharded_on_two_gpus():
-    """Row-wise sharded tables + all-to-all + dense allreduce == single-GPU model on the concatenated batch."""
+@pytest.mark.parametrize("peer", ["1", "0"], ids=["peer_memory", "all_to_all"])
+def test_sharded_deepfm_matches_unsharded_on_two_gpus(peer):
+    """Row-wise sharded tables (exchange inside the kernels over NVLink peer memory, or NCCL all-to-all) + dense
+    allreduce == single-GPU model on the concatenated batch."""
     import subprocess
     import sys
     if torch.cuda.device_count() < 2:
@@ -211,8 +213,9 @@ def test_sharded_deepfm_matches_unsharded_on_two_gpus():
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "dist_sharded_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "127.0.0.1", "--master-port", "29533" if peer == "1" else "29534",
+           os.path.join(root, "tests", "dist_sharded_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PTREC_PEER_GATHER=peer))
     assert "DIST_SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
@@ -237,6 +240,72 @@ def test_a2a_pack_kernels_match_cpu_plan():
             ok = rp[f] >= 0
             want[rp[f][ok].long()] = 0.5 * src.view(B, F, D)[ok, f]
         assert torch.equal(dst.cpu(), want)
+
+
+def test_peer_dispatch_kernels_equal_all_to_all_plan():
+    """The peer-memory pack / scatter (stores straight into the owners' buffers) leave exactly what the all-to-all of
+    the CPU plan would deliver; G virtual ranks on one device, bit-exact."""
+    from oracle import ref_sharding
+    from pytorchrec_b200 import ops
+    for (F, B, G, D) in ((3, 100, 2, 16), (26, 1031, 8, 16), (5, 2048, 4, 1)):
+        rows, S = 997, 20
+        C = max(16, B // G + 40)
+        own_ids = [torch.full((F * G * C,), -1, dtype=torch.int64, device=DEV) for _ in range(G)]
+        own_g = [torch.zeros(G * F * C, S, device=DEV) for _ in range(G)]
+        peer_ids = torch.tensor([t.data_ptr() for t in own_ids], dtype=torch.int64).to(DEV)
+        peer_g = torch.tensor([t.data_ptr() for t in own_g], dtype=torch.int64).to(DEV)
+        want_ids = torch.full((G, F, G, C), -1, dtype=torch.int64)      # [owner][f, src, c]
+        want_g = torch.zeros(G, G * F * C, S)                            # [owner][(src*F + f)*C + c]
+        for r in range(G):
+            gen = torch.Generator().manual_seed(100 + r)
+            ids = torch.stack([torch.randint(-1, rows, (B,), generator=gen) for _ in range(F)])
+            src = torch.randn(B, F * D, generator=gen)
+            ovf = torch.zeros(1, dtype=torch.int32, device=DEV)
+            ret_pos = ops.a2a_pack_by_owner_peer(ids.to(DEV), F, B, G, C, r, peer_ids, ovf)
+            ops.a2a_scatter_rows_peer(src.to(DEV), ret_pos, B, F, D, 0.25, peer_g, S, 4, C, G, r)
+            rs, rp, longest = ref_sharding.pack_by_owner_ref(ids, G, C)
+            assert torch.equal(ret_pos.cpu(), rp) and ovf.item() == (longest if longest > C else 0)
+            want_ids[:, :, r, :] = rs                                   # all-to-all: owner o receives rs[o] from r
+            for f in range(F):
+                ok = rp[f] >= 0
+                pos = rp[f][ok].long()
+                o, rem = pos // (F * C), pos % (F * C)
+                want_g[o, r * F * C + rem, 4:4 + D] = 0.25 * src.view(B, F, D)[ok, f]
+        for o in range(G):
+            assert torch.equal(own_ids[o].cpu().view(F, G, C), want_ids[o])
+            assert torch.equal(own_g[o].cpu(), want_g[o])
+
+
+@pytest.mark.parametrize("G,D,stride_mult", [(2, 16, 1), (8, 16, 2), (4, 1, 1), (3, 64, 2)])
+def test_sharded_gather_reads_row_wise_shards_bit_exact(G, D, stride_mult):
+    from pytorchrec_b200 import ops
+    rows = [1000, 7, 4099, 1]
+    B, T = 777, 4
+    gen = torch.Generator().manual_seed(G * 100 + D)
+    full = [torch.randn(r, D, generator=gen) for r in rows]
+    keep, ptrs = [], []
+    for t in range(T):
+        row_ptrs = []
+        for g in range(G):
+            part = full[t][g::G]
+            buf = torch.zeros(max(part.shape[0], 1), stride_mult * D, device=DEV)  # weight | (state) interleaved
+            buf[:part.shape[0], :D] = part.to(DEV)
+            keep.append(buf)
+            row_ptrs.append(buf.data_ptr())
+        ptrs.append(row_ptrs)
+    shard_ptrs = torch.tensor(ptrs, dtype=torch.int64).to(DEV)
+    rows_t = torch.tensor(rows, dtype=torch.int64).to(DEV)
+    lay = ops.FeatureLayout([dict(table=t, bag_len=1, neg_is_pad=True) for t in range(T)], D, T)
+    ids = torch.stack([torch.randint(0, rows[t], (B,), generator=gen) for t in range(T)])
+    ids[0, 5] = -1                                  # "no lookup": zero row, no error
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out = ops.gather_fwd_sharded(shard_ptrs, rows_t, G, stride_mult * D, lay, ids.to(DEV).view(-1), B, err_flag=err)
+    want = torch.stack([full[t][ids[t].clamp(min=0)] for t in range(T)], dim=1)
+    want[5, 0] = 0
+    assert torch.equal(out.cpu().view(B, T, D), want) and err.item() == 0
+    ids[2, 9] = rows[2]                             # out of range against the GLOBAL height
+    ops.gather_fwd_sharded(shard_ptrs, rows_t, G, stride_mult * D, lay, ids.to(DEV).view(-1), B, err_flag=err)
+    assert err.item() == 1
 
 
 def test_dcn_matches_oracle_twin_within_bf16_tolerance():
