@@ -57,7 +57,10 @@ def config_dict(a, world):
     return {"workload": "%s DeepFM Criteo-shaped synthetic: 26 tables x %d rows x dim %d (+26 first-order dim 1), "
                         "13 dense, DNN 400-400-400, batch %d per GPU, fp32, sparse Adagrad" % (a.workload, a.rows, a.dim, a.batch),
             "global_batch": a.batch * world, "id_dist": a.id_dist, "cuda_graph": not a.no_graph,
-            "parallelism": "single GPU" if world == 1 else f"row-wise sharded tables x{world} (all-to-all) + dense allreduce",
+            "parallelism": "single GPU" if world == 1 else (
+                f"row-wise sharded tables x{world} ("
+                + ("NVLink peer-memory gather / push inside the kernels" if os.environ.get("PTREC_PEER_GATHER", "1") != "0"
+                   else "NCCL all-to-all") + ") + dense allreduce"),
             "l2": "tables %.2f GB >> 126 MB L2; a different random id batch every step" %
                   (26 * a.rows * (a.dim + 1) * 4 / 1e9)}
 

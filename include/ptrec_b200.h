@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 7
+#define PTREC_ABI_VERSION 8
 
 /* error codes */
 #define PTREC_OK 0
@@ -285,6 +285,38 @@ int ptrec_dcn_cross_dgrad(const void* g_u, const void* weight_t, const void* g_o
 size_t ptrec_dcn_cross_wgrad_workspace_bytes(int64_t B, int32_t d);
 int ptrec_dcn_cross_wgrad(const void* g_u, const void* x_l, int64_t B, int32_t d, int64_t ld, float* grad_w,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K6 fp32-faithful Linear layers of the DNN tower on tcgen05 (replaces the fp32 cuBLAS sgemm behind nn.Linear in
+ * torchrec/model/layer/Dense.py:9-17 / MLP.py:13-21 and its backward).  Operands are fp32 matrices split exactly
+ * into three bf16 planes (x = x0 + x1 + x2); products use the six plane pairs of weight >= 2^-16 with fp32
+ * accumulation, i.e. fp32-level error (the north star's 1e-5) at tensor-core speed.
+ *
+ * ptrec_tc_split3: src fp32 [R, C] (pitch ld) ->
+ *   planes    [3][R][pl_ld] bf16 (or NULL)   row-major planes: the A operand of  y = x W^T  and of  dx = g W
+ *   planes_t  [3][C][pt_ld] bf16 (or NULL)   transposed planes: both operands of dW = g^T x (K = batch)
+ *   relu_ref  fp32 [R, C] (pitch ld_ref) or NULL: src is zeroed where relu_ref <= 0 (ReLU backward fused)
+ *   colsum    fp32 [C] or NULL: column sums of the (masked) src = bias gradient, fixed summation order;
+ *             needs workspace ptrec_tc_split3_workspace_bytes(R, C)
+ * Plane pitches are multiples of 8 elements; pad columns are written as zero.
+ *
+ * ptrec_tc_gemm_split3: out[M, N] (pitch ldo, multiple of 4, >= N rounded up to 4) =
+ *   A[M, K] B[N, K]^T (+ bias[N]) (ReLU)   with A, B given as planes [3][M][lda], [3][N][ldb].
+ *   splits > 1 cuts K into ranges accumulated through fp32 partials in the workspace
+ *   (ptrec_tc_gemm_split3_workspace_bytes) and summed in a fixed order; no bias / ReLU then.
+ *   y  = x W^T + b : A = planes(x) [B, K],      B = planes(W) [N, K]
+ *   dx = g W       : A = planes(g) [B, N],      B = planes_t(W) [K, N]
+ *   dW = g^T x     : A = planes_t(g) [N, B],    B = planes_t(x) [K, B],  splits = ..._default_splits()
+ */
+size_t ptrec_tc_split3_workspace_bytes(int64_t R, int64_t C);
+int ptrec_tc_split3(const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref, int64_t ld_ref,
+                    void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld, float* colsum, void* workspace,
+                    size_t workspace_bytes, void* stream);
+size_t ptrec_tc_gemm_split3_workspace_bytes(int64_t M, int64_t ldo, int32_t splits);
+int32_t ptrec_tc_gemm_split3_default_splits(int64_t M, int64_t N, int64_t K);
+int ptrec_tc_gemm_split3(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N, int64_t ldb,
+                         int64_t K, const float* bias, int32_t relu, float* out, int64_t ldo, int32_t splits,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * C1 row-wise sharding: pack / unpack either side of the all-to-all (NCCL, issued by the host through

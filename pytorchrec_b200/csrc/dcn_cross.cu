@@ -18,10 +18,7 @@
 //     swizzled tiles (conflict-free), write both results back in place and one thread TMA-stores them
 //     (cp.async.bulk.tensor.2d.global.shared), so every global access of the epilogue is a full coalesced tile.
 // Every mbarrier wait is bounded (trap instead of hang).
-#include <cuda.h>
-#include <cuda_bf16.h>
-
-#include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace ptrec {
 
@@ -50,52 +47,8 @@ struct EpiArgs {
   int splits;                  // EPI_F32 only: K is cut into `splits` ranges, one output slab each (>= 1)
 };
 
-// ---- PTX wrappers -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// K-major, 128B swizzle: 8-row atoms of 1024 B; LBO unused (1), SBO = 1024 B, descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t make_sw128_desc(const void* smem_tile) {
-  const uint32_t addr = smem_u32(smem_tile);
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
-      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 __device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* p, float* f) {
   const uint4 r = *reinterpret_cast<const uint4*>(p);
@@ -116,12 +69,6 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float* f) {
 }
 
 // ---- the GEMM: C[M, N] = A[M, K] * B[N, K]^T, fused epilogue ---------------------------------------------------
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1)
-               : "memory");
-}
-
 struct GemmMaps {
   CUtensorMap a, b;        // mainloop operands
   CUtensorMap p0, p1;      // epilogue operands (loaded)
@@ -354,23 +301,6 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess) {
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-  }
-  return fn;
-}
-
 // 2-D bf16 row-major [rows, cols] with pitch ld (elements); box = 64 cols x 128 rows, 128B swizzle
 static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
   EncodeTiledFn enc = get_encode();

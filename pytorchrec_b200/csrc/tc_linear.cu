@@ -1,0 +1,468 @@
+// K6: fp32-faithful Linear layers of the DNN tower on the tcgen05 tensor cores (reference: torchrec/model/layer/
+// Dense.py:4-24, MLP.py:8-23 — nn.Linear -> ReLU).  The reference computes these GEMMs in fp32; the north star
+// asks for 1e-5 relative agreement, which rules out TF32 / plain bf16.  Every fp32 operand is therefore split
+// EXACTLY into three bf16 planes
+//        x = x0 + x1 + x2,   x0 = bf16(x), x1 = bf16(x - x0), x2 = bf16(x - x0 - x1)      (3 x 8 = 24 mantissa bits)
+// and the product is accumulated in fp32 (TMEM) from the six plane pairs whose weight is >= 2^-16 relative:
+//        A B^T ~= A0B2 + A2B0 + A1B1 + A0B1 + A1B0 + A0B0          (dropped pairs are <= 2^-24 relative)
+// so the result carries fp32-level error (measured against fp64 in tests) at 6 bf16 MMAs per product instead of the
+// fp32 SIMT pipe: ~10x the arithmetic rate of the cuBLAS sgemm the stock nn.Linear falls back to.
+//
+//   split3_kernel        fp32 [R, C] -> planes [3, R, Cp] and/or transposed planes [3, C, Rp]; optional ReLU-backward
+//                        mask (g * (y > 0)) and column sums (bias gradient) fused in the same pass.       bound: HBM
+//   gemm_split3_kernel   C[M, N] = sum over the 6 pairs of A_i[M, K] B_j[N, K]^T, persistent 128 x 128 tiles;
+//                        warp 0 TMA producer (3-D maps: k, row, plane; 6 tiles = 96 KB per stage, 2 stages),
+//                        warp 1 TMEM alloc + tcgen05.mma issuer (24 MMAs per stage: every plane tile is reused by 2-3
+//                        MMAs, halving the shared-memory fill per FLOP of a plain bf16 GEMM), 8 epilogue warps drain
+//                        the double-buffered accumulator: + bias, ReLU, fp32 store; or split-K partials (wgrad).
+//                        bound: bf16 tensor pipe.  FLOPs per launch = 12 * M * N * K.
+#include "tcgen05.cuh"
+
+namespace ptrec {
+
+// ------------------------------------------------------------------------------------------------ split into planes
+constexpr int kSpTile = 64;
+constexpr int kSpThreads = 256;
+constexpr int kSpPitch = kSpTile + 8;  // bf16 elements: rows stay 16-byte aligned
+
+__device__ __forceinline__ void split3(float v, __nv_bfloat16& p0, __nv_bfloat16& p1, __nv_bfloat16& p2) {
+  p0 = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(p0);
+  p1 = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(p1);
+  p2 = __float2bfloat16_rn(r2);
+}
+
+struct Split3Args {
+  const float* src;
+  int64_t ld;
+  int R, C;
+  const float* ref;  // ReLU output (or any tensor whose sign gates src); null = no mask
+  int64_t ld_ref;
+  __nv_bfloat16* planes;  // [3][R][pl_ld], columns [C, Cp) written as zero; null = skip
+  int64_t pl_ld, pl_plane;
+  int Cp;
+  __nv_bfloat16* planes_t;  // [3][C][pt_ld], columns [R, Rp) written as zero; null = skip
+  int64_t pt_ld, pt_plane;
+  int Rp;
+  float* colsum_part;  // [gridDim.y][C] per-row-tile column sums of the masked src; null = skip
+};
+
+__global__ void __launch_bounds__(kSpThreads) split3_kernel(const Split3Args a) {
+  __shared__ __align__(16) __nv_bfloat16 s_t[3][kSpTile][kSpPitch];
+  __shared__ float s_cs[16][kSpTile];
+  const int c0 = blockIdx.x * kSpTile, r0 = blockIdx.y * kSpTile;
+  const int cg = threadIdx.x & 15, rr = threadIdx.x >> 4;  // 4 columns x (rows rr, rr+16, rr+32, rr+48)
+  const int c = c0 + cg * 4;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool vec_in = (a.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.src) & 15) == 0) && (c + 3 < a.C);
+  const bool vec_ref = a.ref != nullptr && (a.ld_ref % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.ref) & 15) == 0) &&
+                       (c + 3 < a.C);
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int rl = rr + pass * 16, r = r0 + rl;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < a.R) {
+      const float* p = a.src + (int64_t)r * a.ld + c;
+      if (vec_in) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (c + i < a.C) v[i] = p[i];
+      }
+      if (a.ref != nullptr) {
+        const float* q = a.ref + (int64_t)r * a.ld_ref + c;
+        float m[4] = {1.f, 1.f, 1.f, 1.f};
+        if (vec_ref) {
+          const float4 t = *reinterpret_cast<const float4*>(q);
+          m[0] = t.x; m[1] = t.y; m[2] = t.z; m[3] = t.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (c + i < a.C) m[i] = q[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (!(m[i] > 0.f)) v[i] = 0.f;
+      }
+    }
+    __nv_bfloat16 p0[4], p1[4], p2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      split3(v[i], p0[i], p1[i], p2[i]);
+      cs[i] += v[i];
+    }
+    if (a.planes != nullptr && r < a.R && c < a.Cp) {  // Cp % 8 == 0, c % 4 == 0: the group of 4 is inside the pitch
+      __nv_bfloat16* o = a.planes + (int64_t)r * a.pl_ld + c;
+      *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(p0);
+      *reinterpret_cast<uint2*>(o + a.pl_plane) = *reinterpret_cast<const uint2*>(p1);
+      *reinterpret_cast<uint2*>(o + 2 * a.pl_plane) = *reinterpret_cast<const uint2*>(p2);
+    }
+    if (a.planes_t != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        s_t[0][cg * 4 + i][rl] = p0[i];
+        s_t[1][cg * 4 + i][rl] = p1[i];
+        s_t[2][cg * 4 + i][rl] = p2[i];
+      }
+    }
+  }
+  if (a.colsum_part != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s_cs[rr][cg * 4 + i] = cs[i];
+  }
+  __syncthreads();
+  if (a.colsum_part != nullptr && threadIdx.x < kSpTile && c0 + (int)threadIdx.x < a.C) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += s_cs[k][threadIdx.x];  // fixed order
+    a.colsum_part[(int64_t)blockIdx.y * a.C + c0 + threadIdx.x] = s;
+  }
+  if (a.planes_t != nullptr) {
+    const int seg = threadIdx.x & 7;  // 8 rows (16 bytes) of the transposed row
+    const int r = r0 + seg * 8;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int cl = (threadIdx.x >> 3) + pass * 32;
+      const int cc = c0 + cl;
+      if (cc < a.C && r < a.Rp) {  // Rp % 8 == 0: the group of 8 is inside the pitch; rows >= R hold zeros
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          *reinterpret_cast<uint4*>(a.planes_t + (int64_t)p * a.pt_plane + (int64_t)cc * a.pt_ld + r) =
+              *reinterpret_cast<const uint4*>(&s_t[p][cl][seg * 8]);
+        }
+      }
+    }
+  }
+}
+
+// out[c] = sum over row tiles of part[t][c], fixed order (deterministic bias gradient)
+__global__ void colsum_reduce_kernel(const float* __restrict__ part, int tiles, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int t = 0; t < tiles; ++t) s += part[(int64_t)t * C + c];
+  out[c] = s;
+}
+
+// out[e] = sum_s partial[s][e], fixed order (deterministic split-K)
+__global__ void partial_reduce_kernel(const float* __restrict__ partial, int splits, int64_t n, float* __restrict__ out) {
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (e >= n) return;
+  float4 acc = *reinterpret_cast<const float4*>(partial + e);
+  for (int s = 1; s < splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(partial + (int64_t)s * n + e);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + e) = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ the GEMM
+constexpr int kLBM = 128, kLBN = 128, kLBK = 64, kLStages = 2, kLUmmaK = 16;
+constexpr int kLEpiWarps = 8;
+constexpr int kLThreads = 64 + 32 * kLEpiWarps;
+constexpr uint32_t kLTile = kLBM * kLBK * 2;          // one plane tile: 128 rows x 64 bf16, 128B-swizzled (16 KB)
+constexpr uint32_t kLStageBytes = 6 * kLTile;         // A0 A1 A2 B0 B1 B2
+constexpr uint32_t kLTmemCols = 512;  // 2 buffers x {main, correction} x 128 columns: all of TMEM
+constexpr size_t kLSmem = (size_t)kLStages * kLStageBytes + 1024 /*align*/ + 1024 /*barriers + bias slice*/;
+
+struct LinEpi {
+  const float* bias;  // [N] or null
+  int relu;
+  float* out;         // [splits][M, ldo] fp32
+  int64_t ldo;
+  int splits;         // K cut into `splits` ranges (>= 1), one output slab each
+};
+
+struct LinMaps {
+  CUtensorMap a, b;  // 3-D: (k, row, plane)
+};
+
+__global__ void __launch_bounds__(kLThreads, 1)
+gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, LinEpi ep) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kLStages * kLStageBytes);
+  uint64_t* full = bars;                    // [kLStages]
+  uint64_t* empty = bars + kLStages;        // [kLStages]
+  uint64_t* acc_full = bars + 2 * kLStages; // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(bars + 16);  // [kLBN], 16-byte aligned
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (N + kLBN - 1) / kLBN, tiles_m = (M + kLBM - 1) / kLBM;
+  const int splits = max(ep.splits, 1);
+  const int mn_tiles = tiles_n * tiles_m;
+  const int n_tiles = mn_tiles * splits;
+  const int total_kb = (K + kLBK - 1) / kLBK;
+  const int kb_per_split = (total_kb + splits - 1) / splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kLStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], kLEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kLTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b) : "memory");
+      int kbg = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int mn = tile % mn_tiles, split = tile / mn_tiles;
+        const int m0 = (mn / tiles_n) * kLBM, n0 = (mn % tiles_n) * kLBN;
+        const int kb0 = split * kb_per_split, num_kb = max(0, min(total_kb - kb0, kb_per_split));
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const int s = kbg % kLStages;
+          mbar_wait(&empty[s], ((kbg / kLStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[s], kLStageBytes);
+          unsigned char* st = smem + (size_t)s * kLStageBytes;
+          const int k0 = (kb0 + kb) * kLBK;
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            tma_load_3d(st + (size_t)p * kLTile, &maps.a, k0, m0, p, &full[s]);
+            tma_load_3d(st + (size_t)(3 + p) * kLTile, &maps.b, k0, n0, p, &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int kbg = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        // Two accumulators per tile.  The tensor core truncates (does not round) when it aligns an MMA result with
+        // the running sum, a bias that grows with the number of accumulations; keeping the five small pairs in their
+        // own accumulator makes their truncation relative to a 2^-8 smaller magnitude and leaves the main one with
+        // the K/16 accumulations of a plain bf16 GEMM.  The epilogue adds the two in fp32.
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 2 * kLBN);
+        const uint32_t tmem_c = tmem_d + (uint32_t)kLBN;
+        const int mn = tile % mn_tiles;
+        const int n0 = (mn % tiles_n) * kLBN;
+        const int n_eff = min(kLBN, (N - n0 + 15) & ~15);  // the last column tile issues narrower MMAs
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_eff >> 3) << 17) |
+                               ((uint32_t)(kLBM >> 4) << 24);
+        const int kb0 = (tile / mn_tiles) * kb_per_split, num_kb = max(0, min(total_kb - kb0, kb_per_split));
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const int s = kbg % kLStages;
+          mbar_wait(&full[s], (kbg / kLStages) & 1);
+          tcgen05_fence_after();
+          unsigned char* st = smem + (size_t)s * kLStageBytes;
+          uint64_t ad[3], bd[3];
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            ad[p] = make_sw128_desc(st + (size_t)p * kLTile);
+            bd[p] = make_sw128_desc(st + (size_t)(3 + p) * kLTile);
+          }
+#pragma unroll
+          for (int k = 0; k < kLBK / kLUmmaK; ++k) {
+            const uint64_t o = (uint64_t)(k * 2);  // +32 bytes per K=16 slice inside the swizzled row
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_bf16(tmem_c, ad[0] + o, bd[2] + o, idesc, acc);  // smallest pairs first
+            umma_bf16(tmem_c, ad[2] + o, bd[0] + o, idesc, 1u);
+            umma_bf16(tmem_c, ad[1] + o, bd[1] + o, idesc, 1u);
+            umma_bf16(tmem_c, ad[0] + o, bd[1] + o, idesc, 1u);
+            umma_bf16(tmem_c, ad[1] + o, bd[0] + o, idesc, 1u);
+            umma_bf16(tmem_d, ad[0] + o, bd[0] + o, idesc, acc);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int e = warp - 2;
+    const int q = warp & 3;   // TMEM lane quadrant this warp may access
+    const int half = e >> 2;  // 64-column half of the tile
+    const int r = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int mn = tile % mn_tiles, split = tile / mn_tiles;
+      const int m0 = (mn / tiles_n) * kLBM, n0 = (mn % tiles_n) * kLBN;
+      const int buf = it & 1;
+      if (ep.bias != nullptr) {
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kLEpiWarps) : "memory");  // previous tile's readers are done
+        if (et < kLBN) s_bias[et] = (n0 + et < N) ? ep.bias[n0 + et] : 0.f;
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kLEpiWarps) : "memory");
+      }
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * kLBN + half * 64);
+      uint32_t v[64];
+      tmem_ld32(tacc, v);
+      tmem_ld32(tacc + 32, v + 32);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // + correction accumulator
+        uint32_t w[32];
+        tmem_ld32(tacc + kLBN + h * 32, w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[h * 32 + j] = __float_as_uint(__uint_as_float(v[h * 32 + j]) + __uint_as_float(w[j]));
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      const int row = m0 + r, col0 = n0 + half * 64;
+      if (row < M && col0 < N) {
+        float* o = ep.out + ((int64_t)split * M + row) * ep.ldo + col0;
+        const bool has_bias = ep.bias != nullptr;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          if (col0 + j < N) {  // ldo % 4 == 0 and ldo >= round_up(N, 4): the whole group is inside the pitch
+            float4 t = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                   __uint_as_float(v[j + 3]));
+            if (has_bias) {
+              const float4 b = *reinterpret_cast<const float4*>(&s_bias[half * 64 + j]);
+              t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+            }
+            if (ep.relu) {
+              t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(o + j) = t;
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kLTmemCols) : "memory");
+  }
+}
+
+// 3-D bf16 map over planes [3][rows][ld]: dims (cols, rows, 3), box 64 x 128 x 1, 128B swizzle, OOB -> zero
+static int make_map3(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int64_t plane) {
+  EncodeTiledFn enc = get_encode();
+  PTREC_CHECK_ARG(enc != nullptr, PTREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 3};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kLBK, (cuuint32_t)kLBM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PTREC_CHECK_ARG(r == CUDA_SUCCESS, PTREC_ECUDA, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
+  return PTREC_OK;
+}
+
+}  // namespace ptrec
+
+using namespace ptrec;
+
+extern "C" size_t ptrec_tc_split3_workspace_bytes(int64_t R, int64_t C) {
+  return align_up((size_t)(ceil_div(R, kSpTile) * C) * sizeof(float) + 16, 256);
+}
+
+extern "C" int ptrec_tc_split3(const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref,
+                               int64_t ld_ref, void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld,
+                               float* colsum, void* workspace, size_t workspace_bytes, void* stream) {
+  PTREC_CHECK_ARG(src != nullptr && (planes || planes_t || colsum), PTREC_EINVAL, "tc_split3: null pointer");
+  PTREC_CHECK_ARG(R >= 1 && C >= 1 && R < (1ll << 31) && C < (1ll << 31) && ld >= C, PTREC_EINVAL,
+                  "tc_split3: bad shape R=%lld C=%lld ld=%lld", (long long)R, (long long)C, (long long)ld);
+  PTREC_CHECK_ARG(!planes || (pl_ld % 8 == 0 && pl_ld >= C && aligned16(planes)), PTREC_EALIGN,
+                  "tc_split3: plane pitch must be a multiple of 8 elements >= C, base 16-byte aligned");
+  PTREC_CHECK_ARG(!planes_t || (pt_ld % 8 == 0 && pt_ld >= R && aligned16(planes_t)), PTREC_EALIGN,
+                  "tc_split3: transposed plane pitch must be a multiple of 8 elements >= R, base 16-byte aligned");
+  PTREC_CHECK_ARG(!relu_ref || ld_ref >= C, PTREC_EINVAL, "tc_split3: bad ld_ref");
+  PTREC_CHECK_ARG(!colsum || (workspace && workspace_bytes >= ptrec_tc_split3_workspace_bytes(R, C)), PTREC_EWORKSPACE,
+                  "tc_split3: workspace too small for the column sums");
+  cudaStream_t st = (cudaStream_t)stream;
+  Split3Args a;
+  a.src = src; a.ld = ld; a.R = (int)R; a.C = (int)C; a.ref = relu_ref; a.ld_ref = ld_ref;
+  a.planes = reinterpret_cast<__nv_bfloat16*>(planes); a.pl_ld = pl_ld; a.pl_plane = R * pl_ld;
+  a.Cp = (int)std::min<int64_t>(pl_ld, (C + 7) / 8 * 8);
+  a.planes_t = reinterpret_cast<__nv_bfloat16*>(planes_t); a.pt_ld = pt_ld; a.pt_plane = C * pt_ld;
+  a.Rp = (int)std::min<int64_t>(pt_ld, (R + 7) / 8 * 8);
+  a.colsum_part = colsum ? reinterpret_cast<float*>(workspace) : nullptr;
+  dim3 grid((unsigned)ceil_div(C, kSpTile), (unsigned)ceil_div(R, kSpTile));
+  split3_kernel<<<grid, kSpThreads, 0, st>>>(a);
+  PTREC_LAUNCH_CHECK("split3_kernel");
+  if (colsum) {
+    colsum_reduce_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(a.colsum_part, (int)grid.y, (int)C, colsum);
+    PTREC_LAUNCH_CHECK("colsum_reduce_kernel");
+  }
+  return PTREC_OK;
+}
+
+extern "C" size_t ptrec_tc_gemm_split3_workspace_bytes(int64_t M, int64_t ldo, int32_t splits) {
+  return splits > 1 ? align_up((size_t)splits * M * ldo * sizeof(float), 256) : 0;
+}
+
+// default split count for a K-heavy product (weight gradients): fill the SMs without starving a split of k-blocks
+extern "C" int32_t ptrec_tc_gemm_split3_default_splits(int64_t M, int64_t N, int64_t K) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = ceil_div(M, kLBM) * ceil_div(N, kLBN), kbs = ceil_div(K, kLBK);
+  int64_t s = tiles >= sms ? 1 : sms / tiles;
+  s = std::max<int64_t>(1, std::min<int64_t>(s, kbs / 4 > 0 ? kbs / 4 : 1));
+  return (int32_t)std::min<int64_t>(s, 64);
+}
+
+extern "C" int ptrec_tc_gemm_split3(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N,
+                                    int64_t ldb, int64_t K, const float* bias, int32_t relu, float* out, int64_t ldo,
+                                    int32_t splits, void* workspace, size_t workspace_bytes, void* stream) {
+  PTREC_CHECK_ARG(a_planes && b_planes && out, PTREC_EINVAL, "tc_gemm_split3: null pointer");
+  PTREC_CHECK_ARG(M >= 1 && N >= 1 && K >= 1 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), PTREC_EINVAL,
+                  "tc_gemm_split3: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  PTREC_CHECK_ARG(aligned16(a_planes) && aligned16(b_planes) && aligned16(out) && lda % 8 == 0 && ldb % 8 == 0 &&
+                      lda >= K && ldb >= K && ldo % 4 == 0 && ldo >= (N + 3) / 4 * 4,
+                  PTREC_EALIGN, "tc_gemm_split3: pitches must be multiples of 8 (planes) / 4 (out) elements");
+  if (splits < 1) splits = 1;
+  const int total_kb = (int)ceil_div(K, kLBK);
+  if (splits > total_kb) splits = total_kb;
+  while (splits > 1 && (int64_t)(splits - 1) * ceil_div(total_kb, splits) >= total_kb) --splits;  // no empty split
+  PTREC_CHECK_ARG(splits == 1 || (!bias && !relu), PTREC_EINVAL, "tc_gemm_split3: split-K has no bias / ReLU epilogue");
+  PTREC_CHECK_ARG(splits == 1 || (workspace && workspace_bytes >= ptrec_tc_gemm_split3_workspace_bytes(M, ldo, splits)),
+                  PTREC_EWORKSPACE, "tc_gemm_split3: workspace too small for %d split-K partials", splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  LinMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc = make_map3(&maps.a, a_planes, M, K, lda, M * lda);
+  if (rc != PTREC_OK) return rc;
+  rc = make_map3(&maps.b, b_planes, N, K, ldb, N * ldb);
+  if (rc != PTREC_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  LinEpi ep;
+  ep.bias = bias; ep.relu = relu; ep.ldo = ldo; ep.splits = splits;
+  ep.out = splits > 1 ? reinterpret_cast<float*>(workspace) : out;
+  const int64_t tiles = ceil_div(N, kLBN) * ceil_div(M, kLBM) * splits;
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  gemm_split3_kernel<<<grid, kLThreads, kLSmem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+  PTREC_LAUNCH_CHECK("gemm_split3_kernel");
+  if (splits > 1) {
+    const int64_t n = M * ldo;
+    partial_reduce_kernel<<<(unsigned)ceil_div(n / 4, 256), 256, 0, st>>>(ep.out, splits, n, out);
+    PTREC_LAUNCH_CHECK("partial_reduce_kernel");
+  }
+  return PTREC_OK;
+}

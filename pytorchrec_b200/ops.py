@@ -386,6 +386,61 @@ def a2a_scatter_rows_peer(src: torch.Tensor, ret_pos: torch.Tensor, B: int, F: i
 
 
 # ----------------------------------------------------------------------------------------------
+# K6 fp32-faithful Linear on tcgen05 (bf16 x 3 split operands)
+# ----------------------------------------------------------------------------------------------
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def tc_split3(src: torch.Tensor, relu_ref: Optional[torch.Tensor] = None, want_planes: bool = True,
+              want_t: bool = False, want_colsum: bool = False):
+    """fp32 [R, C] -> (planes [3, R, pad8(C)] bf16, planes_t [3, C, pad8(R)] bf16, colsum [C]); each None unless asked.
+    ``relu_ref`` zeroes src where relu_ref <= 0 first (ReLU backward)."""
+    lib = _lib.load()
+    _require_cuda(src, relu_ref)
+    assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1
+    R, C = src.shape
+    dev = src.device
+    if relu_ref is not None:
+        assert relu_ref.shape == src.shape and relu_ref.dtype == torch.float32 and relu_ref.stride(1) == 1
+    planes = torch.empty(3, R, _pad8(C), dtype=torch.bfloat16, device=dev) if want_planes else None
+    planes_t = torch.empty(3, C, _pad8(R), dtype=torch.bfloat16, device=dev) if want_t else None
+    colsum = torch.empty(C, dtype=torch.float32, device=dev) if want_colsum else None
+    ws = _workspace("tc_split3", lib.ptrec_tc_split3_workspace_bytes(R, C), dev) if want_colsum else None
+    _lib.check(lib.ptrec_tc_split3(_ptr(src), src.stride(0), R, C, _ptr(relu_ref),
+                                   relu_ref.stride(0) if relu_ref is not None else 0, _ptr(planes), _pad8(C),
+                                   _ptr(planes_t), _pad8(R), _ptr(colsum), _ptr(ws), ws.numel() if ws is not None else 0,
+                                   _stream(dev)), "ptrec_tc_split3")
+    return planes, planes_t, colsum
+
+
+def tc_gemm_split3(a_planes: torch.Tensor, b_planes: torch.Tensor, K: int, bias: Optional[torch.Tensor] = None,
+                   relu: bool = False, splits: int = 1) -> torch.Tensor:
+    """out [M, N] fp32 = A[M, K] B[N, K]^T (+ bias) (ReLU) from bf16 planes [3, M, lda], [3, N, ldb].  The result is a
+    [:, :N] view of a buffer whose pitch is N rounded up to 4.  ``splits=0`` picks the split-K count for a K-heavy
+    product."""
+    lib = _lib.load()
+    _require_cuda(a_planes, b_planes, bias)
+    assert a_planes.dtype == torch.bfloat16 and b_planes.dtype == torch.bfloat16
+    assert a_planes.dim() == 3 and b_planes.dim() == 3 and a_planes.is_contiguous() and b_planes.is_contiguous()
+    M, lda = a_planes.shape[1], a_planes.shape[2]
+    N, ldb = b_planes.shape[1], b_planes.shape[2]
+    dev = a_planes.device
+    if splits == 0:
+        splits = lib.ptrec_tc_gemm_split3_default_splits(M, N, K)
+    ldo = (N + 3) // 4 * 4
+    out = torch.empty(M, ldo, dtype=torch.float32, device=dev)
+    nbytes = lib.ptrec_tc_gemm_split3_workspace_bytes(M, ldo, splits)
+    ws = _workspace("tc_gemm_split3", nbytes, dev) if nbytes else None
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
+    _lib.check(lib.ptrec_tc_gemm_split3(_ptr(a_planes), M, lda, _ptr(b_planes), N, ldb, K, _ptr(bias), int(relu),
+                                        _ptr(out), ldo, splits, _ptr(ws), ws.numel() if ws is not None else 0,
+                                        _stream(dev)), "ptrec_tc_gemm_split3")
+    return out[:, :N] if ldo != N else out
+
+
+# ----------------------------------------------------------------------------------------------
 # K5 DCN-v2 cross layers (tcgen05)
 # ----------------------------------------------------------------------------------------------
 def _check_bf16_2d(*ts):

@@ -521,3 +521,73 @@ def test_din_attention_pool_forward_backward(B, L, DQ, hidden):
     out2, scores = ops.din_attn_pool_fwd(seq[:, 0], seq[:, 1:], lens.to(DEV), [p.detach() for p in params], want_scores=True)
     assert torch.equal(out2, out.detach())
     assert (scores.cpu()[torch.arange(L).unsqueeze(0) >= lens.unsqueeze(1)] == 0).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K6 fp32-faithful Linear on tcgen05 (bf16 x 3 split operands)
+# ---------------------------------------------------------------------------------------------------------------
+def _planes_sum(pl, rows, cols):
+    return (pl[2, :rows, :cols].float() + pl[1, :rows, :cols].float()) + pl[0, :rows, :cols].float()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,C", [(64, 64), (200, 429), (1031, 13), (4096, 400)])
+def test_tc_split3_planes_are_an_exact_decomposition(R, C):
+    gen = torch.Generator().manual_seed(R + C)
+    x = (torch.randn(R, C, generator=gen) * torch.exp(3 * torch.randn(R, C, generator=gen))).to(DEV)
+    y = torch.randn(R, C, generator=gen).to(DEV)
+    pl, plt, cs = ops.tc_split3(x, want_planes=True, want_t=True, want_colsum=True)
+    assert torch.equal(_planes_sum(pl, R, C), x)                      # x0 + x1 + x2 == x bit for bit
+    assert torch.equal(_planes_sum(plt, C, R), x.t())
+    assert (pl[:, :, C:] == 0).all() and (plt[:, :, R:] == 0).all()   # pad columns are zero
+    ref = x.double().sum(0)
+    assert torch.allclose(cs.double(), ref, rtol=1e-5, atol=1e-5 * x.abs().sum(0).max().item())
+    # fused ReLU backward: g * (y > 0)
+    pl2, _, cs2 = ops.tc_split3(x, relu_ref=y, want_colsum=True)
+    masked = x * (y > 0)
+    assert torch.equal(_planes_sum(pl2, R, C), masked)
+    assert torch.allclose(cs2.double(), masked.double().sum(0), rtol=1e-5, atol=1e-5 * x.abs().sum(0).max().item())
+    # strided source (a column slice)
+    wide = torch.randn(R, C + 5, generator=gen).to(DEV)
+    pl3, _, _ = ops.tc_split3(wide[:, 3:3 + C])
+    assert torch.equal(_planes_sum(pl3, R, C), wide[:, 3:3 + C])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 400, 429), (1000, 16, 40), (2048, 429, 400), (130, 1, 700)])
+def test_tc_gemm_split3_has_fp32_level_error(M, N, K):
+    """|C - C_fp64| is at the level of an fp32 GEMM (<= 2e-6 of sum|a||b|), far from bf16 / tf32 error."""
+    gen = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=gen).to(DEV)
+    b = torch.randn(N, K, generator=gen).to(DEV)
+    bias = torch.randn(N, generator=gen).to(DEV)
+    pa, _, _ = ops.tc_split3(a)
+    pb, _, _ = ops.tc_split3(b)
+    ref = a.double() @ b.double().t()
+    scale = (a.double().abs() @ b.double().abs().t())
+    out = ops.tc_gemm_split3(pa, pb, K)
+    assert out.shape == (M, N)
+    err = ((out.double() - ref).abs() / scale).max().item()
+    fp32_err = ((a @ b.t()).double() - ref).abs().div(scale).max().item()
+    assert err <= max(2e-7, 2 * fp32_err), (err, fp32_err)
+    out2 = ops.tc_gemm_split3(pa, pb, K, bias=bias, relu=True)
+    ref2 = torch.relu(ref + bias.double())
+    assert ((out2.double() - ref2).abs() / (scale + bias.abs().double())).max().item() <= max(2e-7, 2 * fp32_err)
+    # split-K (the weight-gradient shape): same answer up to summation order
+    out3 = ops.tc_gemm_split3(pa, pb, K, splits=3)
+    assert ((out3.double() - ref).abs() / scale).max().item() <= max(3e-7, 2 * fp32_err)
+
+
+@pytest.mark.gpu
+def test_tc_gemm_split3_weight_gradient_shape_with_transposed_planes():
+    B, N, K = 4096, 400, 429
+    gen = torch.Generator().manual_seed(5)
+    g = torch.randn(B, N, generator=gen).to(DEV)
+    x = torch.randn(B, K, generator=gen).to(DEV)
+    _, gt, _ = ops.tc_split3(g, want_planes=False, want_t=True)
+    _, xt, _ = ops.tc_split3(x, want_planes=False, want_t=True)
+    dw = ops.tc_gemm_split3(gt, xt, B, splits=0)
+    ref = g.double().t() @ x.double()
+    scale = g.double().abs().t() @ x.double().abs()
+    assert dw.shape == (N, K)
+    assert ((dw.double() - ref).abs() / scale).max().item() <= 3e-7
