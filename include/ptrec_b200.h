@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 8
+#define PTREC_ABI_VERSION 9
 
 /* error codes */
 #define PTREC_OK 0
@@ -285,6 +285,26 @@ int ptrec_dcn_cross_dgrad(const void* g_u, const void* weight_t, const void* g_o
 size_t ptrec_dcn_cross_wgrad_workspace_bytes(int64_t B, int32_t d);
 int ptrec_dcn_cross_wgrad(const void* g_u, const void* x_l, int64_t B, int32_t d, int64_t ld, float* grad_w,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K7 dense-parameter update in one launch (the dense half of optimizer.step(), IModel.py:124 ->
+ * torchrec/optim/optimizers.py:7-11 -> torch.optim.SGD / Adagrad / Adam arithmetic, same operation order).
+ *   tensors     [n_tensors] device array of {param, grad, state1, state2, numel} (contiguous fp32 tensors;
+ *               state1 = Adagrad sum | Adam exp_avg, state2 = Adam exp_avg_sq, NULL where unused)
+ *   chunk_start [n_tensors + 1] int32 device array: first CTA of each tensor, ptrec_dense_optim_chunk() elements per
+ *               CTA; n_chunks = chunk_start[n_tensors]
+ *   args        host; kind PTREC_OPT_SGD | PTREC_OPT_ADAGRAD | PTREC_OPT_LAZY_ADAM (= dense Adam here); step >= 1
+ */
+typedef struct ptrec_dense_tensor {
+  void* param;
+  const void* grad;
+  void* state1;
+  void* state2;
+  int64_t numel;
+} ptrec_dense_tensor;
+int32_t ptrec_dense_optim_chunk(void);
+int ptrec_dense_optim_step(const ptrec_dense_tensor* tensors, const int32_t* chunk_start, int32_t n_tensors,
+                           int32_t n_chunks, const ptrec_optim_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K6 fp32-faithful Linear layers of the DNN tower on tcgen05 (replaces the fp32 cuBLAS sgemm behind nn.Linear in

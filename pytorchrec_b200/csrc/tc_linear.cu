@@ -138,13 +138,24 @@ __global__ void __launch_bounds__(kSpThreads) split3_kernel(const Split3Args a) 
   }
 }
 
-// out[c] = sum over row tiles of part[t][c], fixed order (deterministic bias gradient)
-__global__ void colsum_reduce_kernel(const float* __restrict__ part, int tiles, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s = 0.f;
-  for (int t = 0; t < tiles; ++t) s += part[(int64_t)t * C + c];
-  out[c] = s;
+// out[c] = sum over row tiles of part[t][c]: 8 lanes per column stride over the tiles, then a fixed xor tree
+// (deterministic bias gradient)
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ part, int tiles, int C,
+                                                            float* __restrict__ out) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int sub = threadIdx.x >> 5;  // 8 warps: warp w sums tiles w, w+8, ... (coalesced across the 32 columns)
+  __shared__ float s[8][33];
+  float acc = 0.f;
+  if (c < C)
+    for (int t = sub; t < tiles; t += 8) acc += part[(int64_t)t * C + c];
+  s[sub][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (sub == 0 && c < C) {
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += s[k][threadIdx.x];
+    out[c] = r;
+  }
 }
 
 // out[e] = sum_s partial[s][e], fixed order (deterministic split-K)
@@ -400,7 +411,7 @@ extern "C" int ptrec_tc_split3(const float* src, int64_t ld, int64_t R, int64_t 
   split3_kernel<<<grid, kSpThreads, 0, st>>>(a);
   PTREC_LAUNCH_CHECK("split3_kernel");
   if (colsum) {
-    colsum_reduce_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(a.colsum_part, (int)grid.y, (int)C, colsum);
+    colsum_reduce_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>(a.colsum_part, (int)grid.y, (int)C, colsum);
     PTREC_LAUNCH_CHECK("colsum_reduce_kernel");
   }
   return PTREC_OK;

@@ -51,6 +51,7 @@ class _FusedSparseOptimizer(Optimizer):
         self._step_count_fused = 0
         self._ptr_cache: Dict[int, tuple] = {}
         self._interleaved: Dict[int, torch.Tensor] = {}  # id(param) -> [rows, stride] buffer holding weight | state
+        self._dense_plan: Dict[tuple, tuple] = {}        # (dense group, step bucket) -> (pointer key, descriptors, chunk starts, n)
 
     def graph_safe(self) -> bool:
         """True when a captured step stays valid on replay (no host-side step count in the arithmetic)."""
@@ -127,8 +128,100 @@ class _FusedSparseOptimizer(Optimizer):
                 for k in dg:
                     if k != "params" and k in group:
                         dg[k] = group[k]
-            self._dense.step()
+            if not self._fused_dense_step():
+                self._dense.step()
         return loss
+
+    # ---- K7: the dense companion's arithmetic in one launch per parameter group ------------------------
+    _DENSE_KIND = {torch.optim.SGD: _lib.OPT_SGD, torch.optim.Adagrad: _lib.OPT_ADAGRAD,
+                   torch.optim.Adam: _lib.OPT_LAZY_ADAM}
+
+    def _fused_dense_step(self) -> bool:
+        """Step the dense parameters with ``ptrec_dense_optim_step`` (state lives in the torch optimizer object, so
+        ``state_dict`` / ``load_state_dict`` are unchanged).  False = not applicable (CPU tensors, sparse or missing
+        layouts): the caller runs the stock ``torch.optim`` step instead."""
+        import os
+        kind = self._DENSE_KIND.get(type(self._dense))
+        if kind is None or os.environ.get("PTREC_FUSED_DENSE_OPTIM", "1") == "0":
+            return False
+        plans = []
+        for gi, dg in enumerate(self._dense.param_groups):
+            if dg.get("maximize") or dg.get("amsgrad") or dg.get("momentum") or dg.get("nesterov") \
+                    or dg.get("differentiable") or dg.get("capturable"):
+                return False
+            ps = [p for p in dg["params"] if p.grad is not None]
+            for p in ps:
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and not p.grad.is_sparse
+                        and p.grad.is_contiguous() and p.grad.dtype == torch.float32):
+                    return False
+            plans.append((gi, dg, ps))
+        lib = _lib.load()
+        chunk = lib.ptrec_dense_optim_chunk()
+        for gi, dg, ps in plans:
+            if not ps:
+                continue
+            states = []
+            for p in ps:
+                if kind == _lib.OPT_SGD:  # no state; do not create empty entries in the defaultdict
+                    states.append(None)
+                    continue
+                st = self._dense.state[p]
+                if kind == _lib.OPT_LAZY_ADAM and "exp_avg" not in st:  # torch.optim.Adam initialises lazily
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                if kind != _lib.OPT_SGD:
+                    if not torch.is_tensor(st.get("step")):
+                        return False
+                    for k in (("sum",) if kind == _lib.OPT_ADAGRAD else ("exp_avg", "exp_avg_sq")):
+                        t = st[k]
+                        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+                            return False
+                states.append(st)
+            # torch.optim keeps one step counter per parameter (a parameter that skipped a step lags behind):
+            # one launch per distinct counter value — a single launch in the usual case
+            buckets: Dict[int, list] = {}
+            for i, st in enumerate(states):
+                step = 1
+                if kind != _lib.OPT_SGD:
+                    st["step"] += 1
+                    step = int(st["step"].item())
+                buckets.setdefault(step, []).append(i)
+            for bi, (step, idx) in enumerate(sorted(buckets.items())):
+                bps = [ps[i] for i in idx]
+                if kind == _lib.OPT_ADAGRAD:
+                    s1, s2 = [states[i]["sum"] for i in idx], [None] * len(idx)
+                elif kind == _lib.OPT_LAZY_ADAM:
+                    s1, s2 = [states[i]["exp_avg"] for i in idx], [states[i]["exp_avg_sq"] for i in idx]
+                else:
+                    s1 = s2 = [None] * len(idx)
+                key = tuple((p.data_ptr(), p.grad.data_ptr(), a.data_ptr() if a is not None else 0,
+                             b.data_ptr() if b is not None else 0) for p, a, b in zip(bps, s1, s2))
+                cached = self._dense_plan.get((gi, bi))
+                if cached is None or cached[0] != key:
+                    import numpy as np
+                    rec = np.zeros((len(bps), 5), dtype=np.int64)
+                    starts = np.zeros(len(bps) + 1, dtype=np.int32)
+                    for i, (p, k4) in enumerate(zip(bps, key)):
+                        rec[i, :4] = k4
+                        rec[i, 4] = p.numel()
+                        starts[i + 1] = starts[i] + (p.numel() + chunk - 1) // chunk
+                    dev = bps[0].device
+                    # pinned staging: this may run inside a CUDA-graph capture (the captured copy node re-reads the
+                    # pinned buffers on replay, so they are kept alive with the plan)
+                    h_rec, h_starts = torch.from_numpy(rec).pin_memory(), torch.from_numpy(starts).pin_memory()
+                    cached = (key, h_rec.to(dev, non_blocking=True), h_starts.to(dev, non_blocking=True),
+                              int(starts[-1]), h_rec, h_starts)
+                    self._dense_plan[(gi, bi)] = cached
+                betas = dg.get("betas", (0.0, 0.0))
+                args = OptimArgs(kind=kind, step=step, lr=dg["lr"], eps=dg.get("eps", 0.0), beta1=betas[0],
+                                 beta2=betas[1], weight_decay=dg.get("weight_decay", 0.0),
+                                 lr_decay=dg.get("lr_decay", 0.0))
+                stream = ctypes.c_void_p(torch.cuda.current_stream(bps[0].device).cuda_stream)
+                _lib.check(lib.ptrec_dense_optim_step(ctypes.c_void_p(cached[1].data_ptr()),
+                                                      ctypes.c_void_p(cached[2].data_ptr()), len(bps), cached[3],
+                                                      ctypes.byref(args), stream), "ptrec_dense_optim_step")
+        return True
 
     def _ensure_dense(self):
         if self._dense is None and self._dense_spec is not None:

@@ -455,3 +455,45 @@ def test_evaluate_with_device_side_ranks():
     from pytorchrec_b200.metric import MetricList
     want = MetricList([Hit(10, 3), NDCG(10, 3)])(pred.cpu().numpy(), None)
     assert logs.keys() == want.keys() and all(abs(logs[k] - want[k]) < 1e-9 for k in logs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kw", [("sgd", dict(lr=0.05, weight_decay=0.01)),
+                                     ("adagrad", dict(lr=0.05, lr_decay=0.01, weight_decay=0.01, eps=1e-10,
+                                                      initial_accumulator_value=0.1)),
+                                     ("adam", dict(lr=0.01, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.01))])
+def test_fused_dense_parameter_step_equals_torch_optim(name, kw):
+    """K7: the one-launch dense update has torch.optim's arithmetic (same operation order, same state layout)."""
+    from pytorchrec_b200.optim import SparseAdagrad, SparseAdam, SparseSGD
+    ours_cls = {"sgd": SparseSGD, "adagrad": SparseAdagrad, "adam": SparseAdam}[name]
+    ref_cls = {"sgd": torch.optim.SGD, "adagrad": torch.optim.Adagrad, "adam": torch.optim.Adam}[name]
+    gen = torch.Generator().manual_seed(7)
+    shapes = [(400, 429), (400,), (1,), (3, 5, 7), (2049,)]
+    a = [torch.nn.Parameter(torch.randn(*s, generator=gen).to(DEV)) for s in shapes]
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    ours, ref = ours_cls(a, **kw), ref_cls(b, **kw)
+    for step in range(4):
+        for i, (p, q) in enumerate(zip(a, b)):
+            if step == 2 and i == 3:
+                p.grad = q.grad = None          # a parameter without a gradient is skipped
+                continue
+            g = torch.randn(*p.shape, generator=gen).to(DEV)
+            p.grad, q.grad = g.clone(), g.clone()
+        launches = _lib_launches()
+        ours.step()
+        # one launch, not the stock multi-tensor cascade (two once a parameter's own step counter lags behind)
+        assert _lib_launches() == launches + (2 if step == 3 and name != "sgd" else 1)
+        ref.step()
+        for p, q in zip(a, b):
+            np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=2e-6, atol=1e-7)
+    sd = ours.state_dict()["dense"]["state"]
+    rsd = ref.state_dict()["state"]
+    assert set(sd) == set(rsd)
+    for k in rsd:
+        for n, v in rsd[k].items():
+            np.testing.assert_allclose(sd[k][n].cpu().numpy(), v.cpu().numpy(), rtol=2e-6, atol=1e-7)
+
+
+def _lib_launches():
+    from pytorchrec_b200 import _lib
+    return _lib.load().ptrec_launch_count()
