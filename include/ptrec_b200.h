@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 9
+#define PTREC_ABI_VERSION 10
 
 /* error codes */
 #define PTREC_OK 0
@@ -327,6 +327,11 @@ int ptrec_dense_optim_step(const ptrec_dense_tensor* tensors, const int32_t* chu
  *   y  = x W^T + b : A = planes(x) [B, K],      B = planes(W) [N, K]
  *   dx = g W       : A = planes(g) [B, N],      B = planes_t(W) [K, N]
  *   dW = g^T x     : A = planes_t(g) [N, B],    B = planes_t(x) [K, B],  splits = ..._default_splits()
+ *
+ * ptrec_tc_gemm_split3_tn: out[M, N] = A^T B with A given as planes [3][K][lda] (M contiguous) and B as planes
+ *   [3][K][ldb] (N contiguous): the MN-major operand form of tcgen05, i.e. the reduction runs over the ROWS of the
+ *   stored matrices.   dW = g^T x : A = planes(g) [B, N], B = planes(x) [B, K] — the row-major planes the forward
+ *   and the input-gradient GEMMs already use, so the weight gradient needs no transposed copies.
  */
 size_t ptrec_tc_split3_workspace_bytes(int64_t R, int64_t C);
 int ptrec_tc_split3(const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref, int64_t ld_ref,
@@ -337,6 +342,9 @@ int32_t ptrec_tc_gemm_split3_default_splits(int64_t M, int64_t N, int64_t K);
 int ptrec_tc_gemm_split3(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N, int64_t ldb,
                          int64_t K, const float* bias, int32_t relu, float* out, int64_t ldo, int32_t splits,
                          void* workspace, size_t workspace_bytes, void* stream);
+int ptrec_tc_gemm_split3_tn(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N, int64_t ldb,
+                            int64_t K, float* out, int64_t ldo, int32_t splits, void* workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * C1 row-wise sharding: pack / unpack either side of the all-to-all (NCCL, issued by the host through

@@ -191,6 +191,11 @@ struct LinMaps {
   CUtensorMap a, b;  // 3-D: (k, row, plane)
 };
 
+// MN_MAJOR = false: operands are K-major planes [3][M or N][K]            (y = x W^T, dx = g W^T^T)
+// MN_MAJOR = true : operands are MN-major planes [3][K][M or N] — the reduction dimension is the ROW of the stored
+//                   matrices, which is how activations and gradients already lie for dW = g^T x (K = batch): the
+//                   tensor core reads them transposed straight from shared memory, no transpose pass.
+template <bool MN_MAJOR>
 __global__ void __launch_bounds__(kLThreads, 1)
 gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, LinEpi ep) {
   extern __shared__ unsigned char smem_raw[];
@@ -250,8 +255,15 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
           const int k0 = (kb0 + kb) * kLBK;
 #pragma unroll
           for (int p = 0; p < 3; ++p) {
-            tma_load_3d(st + (size_t)p * kLTile, &maps.a, k0, m0, p, &full[s]);
-            tma_load_3d(st + (size_t)(3 + p) * kLTile, &maps.b, k0, n0, p, &full[s]);
+            if (MN_MAJOR) {  // two boxes of 64 (mn) x 64 (k rows) per 128-wide tile, 8 KB each
+              tma_load_3d(st + (size_t)p * kLTile, &maps.a, m0, k0, p, &full[s]);
+              tma_load_3d(st + (size_t)p * kLTile + kLTile / 2, &maps.a, m0 + 64, k0, p, &full[s]);
+              tma_load_3d(st + (size_t)(3 + p) * kLTile, &maps.b, n0, k0, p, &full[s]);
+              tma_load_3d(st + (size_t)(3 + p) * kLTile + kLTile / 2, &maps.b, n0 + 64, k0, p, &full[s]);
+            } else {
+              tma_load_3d(st + (size_t)p * kLTile, &maps.a, k0, m0, p, &full[s]);
+              tma_load_3d(st + (size_t)(3 + p) * kLTile, &maps.b, k0, n0, p, &full[s]);
+            }
           }
         }
       }
@@ -273,7 +285,7 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
         const int n0 = (mn % tiles_n) * kLBN;
         const int n_eff = min(kLBN, (N - n0 + 15) & ~15);  // the last column tile issues narrower MMAs
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_eff >> 3) << 17) |
-                               ((uint32_t)(kLBM >> 4) << 24);
+                               ((uint32_t)(kLBM >> 4) << 24) | (MN_MAJOR ? ((1u << 15) | (1u << 16)) : 0u);
         const int kb0 = (tile / mn_tiles) * kb_per_split, num_kb = max(0, min(total_kb - kb0, kb_per_split));
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const int s = kbg % kLStages;
@@ -283,12 +295,14 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
           uint64_t ad[3], bd[3];
 #pragma unroll
           for (int p = 0; p < 3; ++p) {
-            ad[p] = make_sw128_desc(st + (size_t)p * kLTile);
-            bd[p] = make_sw128_desc(st + (size_t)(3 + p) * kLTile);
+            ad[p] = MN_MAJOR ? make_sw128_mn_desc(st + (size_t)p * kLTile) : make_sw128_desc(st + (size_t)p * kLTile);
+            bd[p] = MN_MAJOR ? make_sw128_mn_desc(st + (size_t)(3 + p) * kLTile)
+                             : make_sw128_desc(st + (size_t)(3 + p) * kLTile);
           }
 #pragma unroll
           for (int k = 0; k < kLBK / kLUmmaK; ++k) {
-            const uint64_t o = (uint64_t)(k * 2);  // +32 bytes per K=16 slice inside the swizzled row
+            // K-major: +32 bytes per K=16 slice inside the swizzled row; MN-major: 16 k-rows of 128 bytes = +2048 bytes
+            const uint64_t o = MN_MAJOR ? (uint64_t)(k * 128) : (uint64_t)(k * 2);
             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
             umma_bf16(tmem_c, ad[0] + o, bd[2] + o, idesc, acc);  // smallest pairs first
             umma_bf16(tmem_c, ad[2] + o, bd[0] + o, idesc, 1u);
@@ -378,6 +392,21 @@ static int make_map3(CUtensorMap* map, const void* base, int64_t rows, int64_t c
   return PTREC_OK;
 }
 
+// MN-major operand: planes [3][k_rows][ld] with the M/N dimension contiguous; box 64 (mn) x 64 (k rows) x 1
+static int make_map3_mn(CUtensorMap* map, const void* base, int64_t k_rows, int64_t mn, int64_t ld, int64_t plane) {
+  EncodeTiledFn enc = get_encode();
+  PTREC_CHECK_ARG(enc != nullptr, PTREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)mn, (cuuint64_t)k_rows, 3};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)kLBK, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PTREC_CHECK_ARG(r == CUDA_SUCCESS, PTREC_ECUDA, "cuTensorMapEncodeTiled(3d, mn-major) failed (%d)", (int)r);
+  return PTREC_OK;
+}
+
 }  // namespace ptrec
 
 using namespace ptrec;
@@ -432,14 +461,14 @@ extern "C" int32_t ptrec_tc_gemm_split3_default_splits(int64_t M, int64_t N, int
   return (int32_t)std::min<int64_t>(s, 64);
 }
 
-extern "C" int ptrec_tc_gemm_split3(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N,
-                                    int64_t ldb, int64_t K, const float* bias, int32_t relu, float* out, int64_t ldo,
-                                    int32_t splits, void* workspace, size_t workspace_bytes, void* stream) {
+static int gemm_split3_impl(bool mn_major, const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N,
+                            int64_t ldb, int64_t K, const float* bias, int32_t relu, float* out, int64_t ldo,
+                            int32_t splits, void* workspace, size_t workspace_bytes, void* stream) {
   PTREC_CHECK_ARG(a_planes && b_planes && out, PTREC_EINVAL, "tc_gemm_split3: null pointer");
   PTREC_CHECK_ARG(M >= 1 && N >= 1 && K >= 1 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), PTREC_EINVAL,
                   "tc_gemm_split3: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   PTREC_CHECK_ARG(aligned16(a_planes) && aligned16(b_planes) && aligned16(out) && lda % 8 == 0 && ldb % 8 == 0 &&
-                      lda >= K && ldb >= K && ldo % 4 == 0 && ldo >= (N + 3) / 4 * 4,
+                      lda >= (mn_major ? M : K) && ldb >= (mn_major ? N : K) && ldo % 4 == 0 && ldo >= (N + 3) / 4 * 4,
                   PTREC_EALIGN, "tc_gemm_split3: pitches must be multiples of 8 (planes) / 4 (out) elements");
   if (splits < 1) splits = 1;
   const int total_kb = (int)ceil_div(K, kLBK);
@@ -451,13 +480,14 @@ extern "C" int ptrec_tc_gemm_split3(const void* a_planes, int64_t M, int64_t lda
   cudaStream_t st = (cudaStream_t)stream;
   LinMaps maps;
   memset(&maps, 0, sizeof(maps));
-  int rc = make_map3(&maps.a, a_planes, M, K, lda, M * lda);
+  int rc = mn_major ? make_map3_mn(&maps.a, a_planes, K, M, lda, K * lda) : make_map3(&maps.a, a_planes, M, K, lda, M * lda);
   if (rc != PTREC_OK) return rc;
-  rc = make_map3(&maps.b, b_planes, N, K, ldb, N * ldb);
+  rc = mn_major ? make_map3_mn(&maps.b, b_planes, K, N, ldb, K * ldb) : make_map3(&maps.b, b_planes, N, K, ldb, N * ldb);
   if (rc != PTREC_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem));
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem));
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem));
     attr_set = true;
   }
   int dev = 0, sms = 148;
@@ -468,7 +498,10 @@ extern "C" int ptrec_tc_gemm_split3(const void* a_planes, int64_t M, int64_t lda
   ep.out = splits > 1 ? reinterpret_cast<float*>(workspace) : out;
   const int64_t tiles = ceil_div(N, kLBN) * ceil_div(M, kLBM) * splits;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  gemm_split3_kernel<<<grid, kLThreads, kLSmem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+  if (mn_major)
+    gemm_split3_kernel<true><<<grid, kLThreads, kLSmem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+  else
+    gemm_split3_kernel<false><<<grid, kLThreads, kLSmem, st>>>(maps, (int)M, (int)N, (int)K, ep);
   PTREC_LAUNCH_CHECK("gemm_split3_kernel");
   if (splits > 1) {
     const int64_t n = M * ldo;
@@ -476,4 +509,18 @@ extern "C" int ptrec_tc_gemm_split3(const void* a_planes, int64_t M, int64_t lda
     PTREC_LAUNCH_CHECK("partial_reduce_kernel");
   }
   return PTREC_OK;
+}
+
+extern "C" int ptrec_tc_gemm_split3(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N,
+                                    int64_t ldb, int64_t K, const float* bias, int32_t relu, float* out, int64_t ldo,
+                                    int32_t splits, void* workspace, size_t workspace_bytes, void* stream) {
+  return gemm_split3_impl(false, a_planes, M, lda, b_planes, N, ldb, K, bias, relu, out, ldo, splits, workspace,
+                          workspace_bytes, stream);
+}
+
+extern "C" int ptrec_tc_gemm_split3_tn(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N,
+                                       int64_t ldb, int64_t K, float* out, int64_t ldo, int32_t splits, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  return gemm_split3_impl(true, a_planes, M, lda, b_planes, N, ldb, K, nullptr, 0, out, ldo, splits, workspace,
+                          workspace_bytes, stream);
 }

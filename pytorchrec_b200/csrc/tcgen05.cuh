@@ -46,6 +46,19 @@ __device__ __forceinline__ uint64_t make_sw128_desc(const void* smem_tile) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major, 128B swizzle (operand stored with the M/N dimension contiguous, e.g. a TMA box of 64 mn-elements x R k-rows):
+// rows of 128 bytes along M/N, 8 k-rows form the 1024-byte swizzle atom; SBO = stride between groups of 8 k-rows
+// (1024 B, dense), LBO = stride between blocks of 64 mn-elements (the next TMA box, 64 k-rows x 128 B = 8192 B).
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(const void* smem_tile) {
+  const uint32_t addr = smem_u32(smem_tile);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"

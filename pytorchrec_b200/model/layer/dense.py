@@ -19,33 +19,33 @@ from ... import ops
 
 
 class _TcLinearReLU(torch.autograd.Function):
-    """y = relu(x W^T + b) on K6.  Saves y (ReLU mask), the transposed planes of x (weight gradient) and the
-    transposed planes of W (input gradient)."""
+    """y = relu(x W^T + b) on K6.  Saves y (ReLU mask), the planes of x (weight gradient: read MN-major, i.e.
+    transposed by the tensor core itself) and the transposed planes of W (input gradient)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         N, K = weight.shape
-        px, pxt, _ = ops.tc_split3(x, want_planes=True, want_t=need_dw)
+        px, _, _ = ops.tc_split3(x)
         pw, pwt, _ = ops.tc_split3(weight, want_planes=True, want_t=need_dx)
         y = ops.tc_gemm_split3(px, pw, K, bias=bias, relu=True)
-        ctx.save_for_backward(y, pxt, pwt)
+        ctx.save_for_backward(y, px if need_dw else None, pwt)
         ctx.dims = (x.shape[0], N, K)
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        y, pxt, pwt = ctx.saved_tensors
+        y, px, pwt = ctx.saved_tensors
         B, N, K = ctx.dims
         need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
         if gy.stride(-1) != 1:
             gy = gy.contiguous()
-        pg, pgt, db = ops.tc_split3(gy, relu_ref=y, want_planes=need_dx, want_t=need_dw, want_colsum=need_db)
+        pg, _, db = ops.tc_split3(gy, relu_ref=y, want_planes=need_dx or need_dw, want_colsum=need_db)
         dx = ops.tc_gemm_split3(pg, pwt, N) if need_dx else None                  # g W        [B, K]
         dw = None
         if need_dw:
-            dw = ops.tc_gemm_split3(pgt, pxt, B, splits=0)                          # g^T x      [N, K]
+            dw = ops.tc_gemm_split3_tn(pg, N, px, K)                                # g^T x      [N, K]
             if not dw.is_contiguous():
                 dw = dw.contiguous()
         return dx, dw, db

@@ -440,6 +440,29 @@ def tc_gemm_split3(a_planes: torch.Tensor, b_planes: torch.Tensor, K: int, bias:
     return out[:, :N] if ldo != N else out
 
 
+def tc_gemm_split3_tn(a_planes: torch.Tensor, M: int, b_planes: torch.Tensor, N: int, splits: int = 0) -> torch.Tensor:
+    """out [M, N] fp32 = A^T B from row-major planes A [3, K, pad8(M)], B [3, K, pad8(N)] (reduction over the rows:
+    the weight-gradient form dW = g^T x with K = batch).  ``splits=0`` picks the split-K count."""
+    lib = _lib.load()
+    _require_cuda(a_planes, b_planes)
+    assert a_planes.dtype == torch.bfloat16 and b_planes.dtype == torch.bfloat16
+    assert a_planes.dim() == 3 and b_planes.dim() == 3 and a_planes.is_contiguous() and b_planes.is_contiguous()
+    K, lda = a_planes.shape[1], a_planes.shape[2]
+    assert b_planes.shape[1] == K and lda >= M and b_planes.shape[2] >= N
+    ldb = b_planes.shape[2]
+    dev = a_planes.device
+    if splits == 0:
+        splits = lib.ptrec_tc_gemm_split3_default_splits(M, N, K)
+    ldo = (N + 3) // 4 * 4
+    out = torch.empty(M, ldo, dtype=torch.float32, device=dev)
+    nbytes = lib.ptrec_tc_gemm_split3_workspace_bytes(M, ldo, splits)
+    ws = _workspace("tc_gemm_split3", nbytes, dev) if nbytes else None
+    _lib.check(lib.ptrec_tc_gemm_split3_tn(_ptr(a_planes), M, lda, _ptr(b_planes), N, ldb, K, _ptr(out), ldo, splits,
+                                           _ptr(ws), ws.numel() if ws is not None else 0, _stream(dev)),
+               "ptrec_tc_gemm_split3_tn")
+    return out[:, :N] if ldo != N else out
+
+
 # ----------------------------------------------------------------------------------------------
 # K5 DCN-v2 cross layers (tcgen05)
 # ----------------------------------------------------------------------------------------------

@@ -591,3 +591,21 @@ def test_tc_gemm_split3_weight_gradient_shape_with_transposed_planes():
     scale = g.double().abs().t() @ x.double().abs()
     assert dw.shape == (N, K)
     assert ((dw.double() - ref).abs() / scale).max().item() <= 3e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,K", [(4096, 400, 429), (1000, 128, 64), (777, 16, 1030), (64, 200, 13)])
+def test_tc_gemm_split3_tn_weight_gradient_from_row_major_planes(B, N, K):
+    """dW = g^T x straight from the row-major planes (MN-major tcgen05 operands): no transposed copies."""
+    gen = torch.Generator().manual_seed(B + N)
+    g = torch.randn(B, N, generator=gen).to(DEV)
+    x = torch.randn(B, K, generator=gen).to(DEV)
+    pg, _, _ = ops.tc_split3(g)
+    px, _, _ = ops.tc_split3(x)
+    ref = g.double().t() @ x.double()
+    scale = g.double().abs().t() @ x.double().abs()
+    fp32_err = ((g.t() @ x).double() - ref).abs().div(scale).max().item()
+    for splits, tol in ((0, max(3e-7, 2 * fp32_err)), (1, 1e-6)):  # one split = one long chain of truncating adds
+        dw = ops.tc_gemm_split3_tn(pg, N, px, K, splits=splits)
+        assert dw.shape == (N, K)
+        assert ((dw.double() - ref).abs() / scale).max().item() <= tol, (splits, fp32_err)
