@@ -247,7 +247,10 @@ def run_b200(a):
             "gpu_launches": int(launches), "clocks": clocks}
 
     if rank == 0:
-        line["roofline"], line["kernels"] = kernel_roofline(a, model, resident, dev)
+        roof, line["kernels"], roof2 = kernel_roofline(a, model, resident, dev)
+        line["roofline"] = roof
+        if roof2 is not None:
+            line["roofline_hbm"] = roof2  # the dominant HBM-bound kernel of the embedding path
         if world == 1 and not a.no_cpu_baseline:
             try:
                 sps, cms, cores = time_cpu(a, a.cpu_steps, 1)
@@ -333,15 +336,47 @@ def kernel_roofline(a, model, resident, dev):
     }
     hbm = {k: v for k, v in kernels.items() if k in ("gather_pool_fwd", "fused_update_adagrad")}
     dom = max(hbm, key=lambda k: hbm[k]["seconds"])
-    traffic = None
+    traffic_all = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom)
-    roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
-            "frac": kernels[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
-            "frac_of_spec_8000": kernels[dom]["GBps"] / 8000.0,
-            "algorithmic_bytes_per_launch": kernels[dom]["bytes"], "seconds_per_launch": kernels[dom]["seconds"]}
-    return roof, kernels
+        traffic_all = json.load(open(tpath))
+    roof_hbm = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["GBps"] / peak, "traffic": traffic_all.get(dom), "peak_source": peak_src,
+                "frac_of_spec_8000": kernels[dom]["GBps"] / 8000.0,
+                "algorithmic_bytes_per_launch": kernels[dom]["bytes"], "seconds_per_launch": kernels[dom]["seconds"]}
+
+    # K6: the DNN-tower GEMMs (9 launches per step: the largest share of the step).  Tensor-bound: each fp32 product
+    # is 6 bf16 plane-pair MMAs, so a launch issues 12*M*N*K bf16 FLOPs.  Operands rotate over 4
+    # buffer sets (260 MB > L2).
+    from pytorchrec_b200.model.layer.dense import tc_linear_enabled
+    mlp = getattr(model, "mlp", None)
+    if not (tc_linear_enabled() and mlp is not None):
+        return roof_hbm, kernels, None
+    lin = mlp.mlp[0].linear
+    N, K = lin.weight.shape
+    xs = [torch.randn(B, K, device=dev) for _ in range(4)]
+    pxs = [ops.tc_split3(x)[0] for x in xs]
+    pw = ops.tc_split3(lin.weight.detach())[0]
+    bias = lin.bias.detach()
+    t_gemm = time_it(lambda i: ops.tc_gemm_split3(pxs[i % 4], pw, K, bias=bias, relu=True), 40)
+    t_wgrad = time_it(lambda i: ops.tc_gemm_split3_tn(pxs[i % 4], K, pxs[(i + 1) % 4], K), 20)
+    t_split = time_it(lambda i: ops.tc_split3(xs[i % 4]), 40)
+    flops = 12.0 * B * N * K
+    kernels["tc_linear_fwd(gemm_split3)"] = {"seconds": t_gemm, "flops_bf16_issued": flops, "TFLOPs_bf16": flops / t_gemm / 1e12,
+                                             "TFLOPs_fp32_equivalent": flops / 6 / t_gemm / 1e12, "M": B, "N": N, "K": K}
+    kernels["tc_linear_wgrad(gemm_split3_tn)"] = {"seconds": t_wgrad, "M": K, "N": K, "K": B,
+                                                  "TFLOPs_bf16": 12.0 * B * K * K / t_wgrad / 1e12}
+    sp_bytes = B * K * 4 + 3 * B * ((K + 7) // 8 * 8) * 2
+    kernels["tc_split3"] = {"seconds": t_split, "bytes": sp_bytes, "GBps": sp_bytes / t_split / 1e9}
+    pk = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    tpeak = pk.get("bf16_tflops", 2250.0)
+    roof = {"kernel": "gemm_split3 (K6, DNN tower Linear fwd)", "bound": "tensor", "achieved": flops / t_gemm / 1e12,
+            "peak": tpeak, "unit": "TFLOP/s", "frac": flops / t_gemm / 1e12 / tpeak,
+            "traffic": traffic_all.get("gemm_split3"),
+            "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)" if pk else "nominal",
+            "algorithmic_flops_per_launch": flops, "seconds_per_launch": t_gemm,
+            "note": "bf16 FLOPs issued = 6 plane pairs x 2*M*N*K; fp32-equivalent rate = achieved / 6"}
+    return roof, kernels, roof_hbm
 
 
 if __name__ == "__main__":

@@ -171,13 +171,18 @@ __global__ void partial_reduce_kernel(const float* __restrict__ partial, int spl
 }
 
 // ------------------------------------------------------------------------------------------------ the GEMM
-constexpr int kLBM = 128, kLBN = 128, kLBK = 64, kLStages = 2, kLUmmaK = 16;
+// Operand delivery from L2 is what bounds this kernel (ncu: ~38 B/clk/SM, the LTS cap), so the CTA tile is as wide as
+// TMEM allows: 128 x 256 with K blocks of 32 -> 72 KB per stage for 12 MMAs of N = 256 (0.75x the bytes per FLOP of
+// 128 x 128 tiles).  The two fp32 accumulators (main + correction, below) take all 512 TMEM columns, so the
+// accumulator is single-buffered: the MMA warp waits for the epilogue to pull a tile into registers (~5 % of a tile).
+constexpr int kLBM = 128, kLBN = 256, kLBK = 32, kLStages = 3, kLUmmaK = 16;
 constexpr int kLEpiWarps = 8;
 constexpr int kLThreads = 64 + 32 * kLEpiWarps;
-constexpr uint32_t kLTile = kLBM * kLBK * 2;          // one plane tile: 128 rows x 64 bf16, 128B-swizzled (16 KB)
-constexpr uint32_t kLStageBytes = 6 * kLTile;         // A0 A1 A2 B0 B1 B2
-constexpr uint32_t kLTmemCols = 512;  // 2 buffers x {main, correction} x 128 columns: all of TMEM
-constexpr size_t kLSmem = (size_t)kLStages * kLStageBytes + 1024 /*align*/ + 1024 /*barriers + bias slice*/;
+constexpr uint32_t kLTileA = kLBM * kLBK * 2;          // one A plane tile:  128 rows x 32 bf16 (8 KB)
+constexpr uint32_t kLTileB = kLBN * kLBK * 2;          // one B plane tile:  256 rows x 32 bf16 (16 KB)
+constexpr uint32_t kLStageBytes = 3 * (kLTileA + kLTileB);  // A0 A1 A2 B0 B1 B2 = 72 KB
+constexpr uint32_t kLTmemCols = 512;                   // main [0, 256) + correction [256, 512)
+constexpr size_t kLSmem = (size_t)kLStages * kLStageBytes + 1024 /*align*/ + 2048 /*barriers + bias slice*/;
 
 struct LinEpi {
   const float* bias;  // [N] or null
@@ -188,8 +193,32 @@ struct LinEpi {
 };
 
 struct LinMaps {
-  CUtensorMap a, b;  // 3-D: (k, row, plane)
+  CUtensorMap a, b;  // 3-D: K-major (k, row, plane) or MN-major (mn, k row, plane)
 };
+
+// K-major, 64B swizzle (rows of 32 bf16): 8-row atoms of 512 B; LBO unused (1), SBO = 512 B
+__device__ __forceinline__ uint64_t make_sw64_desc(const void* smem_tile) {
+  const uint32_t addr = smem_u32(smem_tile);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// MN-major, 128B swizzle, boxes of 64 mn-elements x 32 k-rows (4 KB): SBO = 1024 B between groups of 8 k-rows,
+// LBO = 4096 B between blocks of 64 mn-elements
+__device__ __forceinline__ uint64_t make_sw128_mn32_desc(const void* smem_tile) {
+  const uint32_t addr = smem_u32(smem_tile);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(4096 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 
 // MN_MAJOR = false: operands are K-major planes [3][M or N][K]            (y = x W^T, dx = g W^T^T)
 // MN_MAJOR = true : operands are MN-major planes [3][K][M or N] — the reduction dimension is the ROW of the stored
@@ -203,9 +232,9 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kLStages * kLStageBytes);
   uint64_t* full = bars;                    // [kLStages]
   uint64_t* empty = bars + kLStages;        // [kLStages]
-  uint64_t* acc_full = bars + 2 * kLStages; // [2]
-  uint64_t* acc_empty = acc_full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_full = bars + 2 * kLStages; // [1]
+  uint64_t* acc_empty = acc_full + 1;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
   float* s_bias = reinterpret_cast<float*>(bars + 16);  // [kLBN], 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -215,16 +244,16 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
   const int n_tiles = mn_tiles * splits;
   const int total_kb = (K + kLBK - 1) / kLBK;
   const int kb_per_split = (total_kb + splits - 1) / splits;
+  // tile order: n slowest, so that the widest column tiles come first and the narrow remainder tiles fill the tail
+  // of the round-robin (longest-processing-time-first for the two tile widths a Linear layer produces)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kLStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], kLEpiWarps);
-    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, kLEpiWarps);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -245,24 +274,27 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
       int kbg = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int mn = tile % mn_tiles, split = tile / mn_tiles;
-        const int m0 = (mn / tiles_n) * kLBM, n0 = (mn % tiles_n) * kLBN;
+        const int m0 = (mn % tiles_m) * kLBM, n0 = (mn / tiles_m) * kLBN;
         const int kb0 = split * kb_per_split, num_kb = max(0, min(total_kb - kb0, kb_per_split));
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const int s = kbg % kLStages;
           mbar_wait(&empty[s], ((kbg / kLStages) & 1) ^ 1);
           mbar_arrive_expect_tx(&full[s], kLStageBytes);
-          unsigned char* st = smem + (size_t)s * kLStageBytes;
+          unsigned char* sa = smem + (size_t)s * kLStageBytes;
+          unsigned char* sb = sa + 3 * kLTileA;
           const int k0 = (kb0 + kb) * kLBK;
 #pragma unroll
           for (int p = 0; p < 3; ++p) {
-            if (MN_MAJOR) {  // two boxes of 64 (mn) x 64 (k rows) per 128-wide tile, 8 KB each
-              tma_load_3d(st + (size_t)p * kLTile, &maps.a, m0, k0, p, &full[s]);
-              tma_load_3d(st + (size_t)p * kLTile + kLTile / 2, &maps.a, m0 + 64, k0, p, &full[s]);
-              tma_load_3d(st + (size_t)(3 + p) * kLTile, &maps.b, n0, k0, p, &full[s]);
-              tma_load_3d(st + (size_t)(3 + p) * kLTile + kLTile / 2, &maps.b, n0 + 64, k0, p, &full[s]);
+            if (MN_MAJOR) {  // boxes of 64 (mn) x 32 (k rows), 4 KB each: 2 per A tile, 4 per B tile
+#pragma unroll
+              for (int j = 0; j < kLBM / 64; ++j)
+                tma_load_3d(sa + (size_t)p * kLTileA + (size_t)j * 4096, &maps.a, m0 + 64 * j, k0, p, &full[s]);
+#pragma unroll
+              for (int j = 0; j < kLBN / 64; ++j)
+                tma_load_3d(sb + (size_t)p * kLTileB + (size_t)j * 4096, &maps.b, n0 + 64 * j, k0, p, &full[s]);
             } else {
-              tma_load_3d(st + (size_t)p * kLTile, &maps.a, k0, m0, p, &full[s]);
-              tma_load_3d(st + (size_t)(3 + p) * kLTile, &maps.b, k0, n0, p, &full[s]);
+              tma_load_3d(sa + (size_t)p * kLTileA, &maps.a, k0, m0, p, &full[s]);
+              tma_load_3d(sb + (size_t)p * kLTileB, &maps.b, k0, n0, p, &full[s]);
             }
           }
         }
@@ -272,17 +304,16 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
     if (lane == 0) {
       int kbg = 0, it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        mbar_wait(acc_empty, (it & 1) ^ 1);  // the epilogue holds the previous tile in registers
         tcgen05_fence_after();
         // Two accumulators per tile.  The tensor core truncates (does not round) when it aligns an MMA result with
         // the running sum, a bias that grows with the number of accumulations; keeping the five small pairs in their
         // own accumulator makes their truncation relative to a 2^-8 smaller magnitude and leaves the main one with
         // the K/16 accumulations of a plain bf16 GEMM.  The epilogue adds the two in fp32.
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 2 * kLBN);
-        const uint32_t tmem_c = tmem_d + (uint32_t)kLBN;
+        const uint32_t tmem_d = tmem_base;
+        const uint32_t tmem_c = tmem_base + (uint32_t)kLBN;
         const int mn = tile % mn_tiles;
-        const int n0 = (mn % tiles_n) * kLBN;
+        const int n0 = (mn / tiles_m) * kLBN;
         const int n_eff = min(kLBN, (N - n0 + 15) & ~15);  // the last column tile issues narrower MMAs
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_eff >> 3) << 17) |
                                ((uint32_t)(kLBM >> 4) << 24) | (MN_MAJOR ? ((1u << 15) | (1u << 16)) : 0u);
@@ -291,13 +322,13 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
           const int s = kbg % kLStages;
           mbar_wait(&full[s], (kbg / kLStages) & 1);
           tcgen05_fence_after();
-          unsigned char* st = smem + (size_t)s * kLStageBytes;
+          unsigned char* sa = smem + (size_t)s * kLStageBytes;
+          unsigned char* sb = sa + 3 * kLTileA;
           uint64_t ad[3], bd[3];
 #pragma unroll
           for (int p = 0; p < 3; ++p) {
-            ad[p] = MN_MAJOR ? make_sw128_mn_desc(st + (size_t)p * kLTile) : make_sw128_desc(st + (size_t)p * kLTile);
-            bd[p] = MN_MAJOR ? make_sw128_mn_desc(st + (size_t)(3 + p) * kLTile)
-                             : make_sw128_desc(st + (size_t)(3 + p) * kLTile);
+            ad[p] = MN_MAJOR ? make_sw128_mn32_desc(sa + (size_t)p * kLTileA) : make_sw64_desc(sa + (size_t)p * kLTileA);
+            bd[p] = MN_MAJOR ? make_sw128_mn32_desc(sb + (size_t)p * kLTileB) : make_sw64_desc(sb + (size_t)p * kLTileB);
           }
 #pragma unroll
           for (int k = 0; k < kLBK / kLUmmaK; ++k) {
@@ -313,52 +344,54 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
           }
           umma_commit(&empty[s]);
         }
-        umma_commit(&acc_full[buf]);
+        umma_commit(acc_full);
       }
     }
   } else {
     const int e = warp - 2;
     const int q = warp & 3;   // TMEM lane quadrant this warp may access
-    const int half = e >> 2;  // 64-column half of the tile
+    const int half = e >> 2;  // 128-column half of the tile
     const int r = q * 32 + lane;
     const int et = threadIdx.x - 64;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int mn = tile % mn_tiles, split = tile / mn_tiles;
-      const int m0 = (mn / tiles_n) * kLBM, n0 = (mn % tiles_n) * kLBN;
-      const int buf = it & 1;
+      const int m0 = (mn % tiles_m) * kLBM, n0 = (mn / tiles_m) * kLBN;
       if (ep.bias != nullptr) {
         asm volatile("bar.sync 2, %0;" ::"n"(32 * kLEpiWarps) : "memory");  // previous tile's readers are done
         if (et < kLBN) s_bias[et] = (n0 + et < N) ? ep.bias[n0 + et] : 0.f;
         asm volatile("bar.sync 2, %0;" ::"n"(32 * kLEpiWarps) : "memory");
       }
-      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      mbar_wait(acc_full, it & 1);
       tcgen05_fence_after();
-      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * kLBN + half * 64);
-      uint32_t v[64];
-      tmem_ld32(tacc, v);
-      tmem_ld32(tacc + 32, v + 32);
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+      const int row = m0 + r, col0 = n0 + half * 128;
+      const bool live = col0 < N;  // warp-uniform: a narrow remainder tile leaves the second half empty
+      uint32_t v[128];
+      if (live) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {  // + correction accumulator
-        uint32_t w[32];
-        tmem_ld32(tacc + kLBN + h * 32, w);
+        for (int h = 0; h < 4; ++h) {
+          uint32_t w[32];
+          tmem_ld32(tacc + h * 32, v + h * 32);
+          tmem_ld32(tacc + kLBN + h * 32, w);  // + correction accumulator
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[h * 32 + j] = __float_as_uint(__uint_as_float(v[h * 32 + j]) + __uint_as_float(w[j]));
+          for (int j = 0; j < 32; ++j)
+            v[h * 32 + j] = __float_as_uint(__uint_as_float(v[h * 32 + j]) + __uint_as_float(w[j]));
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      const int row = m0 + r, col0 = n0 + half * 64;
-      if (row < M && col0 < N) {
+      if (lane == 0) mbar_arrive(acc_empty);
+      if (live && row < M) {
         float* o = ep.out + ((int64_t)split * M + row) * ep.ldo + col0;
         const bool has_bias = ep.bias != nullptr;
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
+        for (int j = 0; j < 128; j += 4) {
           if (col0 + j < N) {  // ldo % 4 == 0 and ldo >= round_up(N, 4): the whole group is inside the pitch
             float4 t = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                    __uint_as_float(v[j + 3]));
             if (has_bias) {
-              const float4 b = *reinterpret_cast<const float4*>(&s_bias[half * 64 + j]);
+              const float4 b = *reinterpret_cast<const float4*>(&s_bias[half * 128 + j]);
               t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
             }
             if (ep.relu) {
@@ -377,22 +410,23 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
   }
 }
 
-// 3-D bf16 map over planes [3][rows][ld]: dims (cols, rows, 3), box 64 x 128 x 1, 128B swizzle, OOB -> zero
-static int make_map3(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int64_t plane) {
+// K-major operand: 3-D bf16 map over planes [3][rows][ld]: dims (cols, rows, 3), box 32 x box_rows x 1, 64B swizzle
+static int make_map3(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int64_t plane,
+                     int box_rows) {
   EncodeTiledFn enc = get_encode();
   PTREC_CHECK_ARG(enc != nullptr, PTREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 3};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
-  cuuint32_t box[3] = {(cuuint32_t)kLBK, (cuuint32_t)kLBM, 1};
+  cuuint32_t box[3] = {(cuuint32_t)kLBK, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PTREC_CHECK_ARG(r == CUDA_SUCCESS, PTREC_ECUDA, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
   return PTREC_OK;
 }
 
-// MN-major operand: planes [3][k_rows][ld] with the M/N dimension contiguous; box 64 (mn) x 64 (k rows) x 1
+// MN-major operand: planes [3][k_rows][ld] with the M/N dimension contiguous; box 64 (mn) x 32 (k rows) x 1
 static int make_map3_mn(CUtensorMap* map, const void* base, int64_t k_rows, int64_t mn, int64_t ld, int64_t plane) {
   EncodeTiledFn enc = get_encode();
   PTREC_CHECK_ARG(enc != nullptr, PTREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
@@ -480,9 +514,11 @@ static int gemm_split3_impl(bool mn_major, const void* a_planes, int64_t M, int6
   cudaStream_t st = (cudaStream_t)stream;
   LinMaps maps;
   memset(&maps, 0, sizeof(maps));
-  int rc = mn_major ? make_map3_mn(&maps.a, a_planes, K, M, lda, K * lda) : make_map3(&maps.a, a_planes, M, K, lda, M * lda);
+  int rc = mn_major ? make_map3_mn(&maps.a, a_planes, K, M, lda, K * lda)
+                    : make_map3(&maps.a, a_planes, M, K, lda, M * lda, kLBM);
   if (rc != PTREC_OK) return rc;
-  rc = mn_major ? make_map3_mn(&maps.b, b_planes, K, N, ldb, K * ldb) : make_map3(&maps.b, b_planes, N, K, ldb, N * ldb);
+  rc = mn_major ? make_map3_mn(&maps.b, b_planes, K, N, ldb, K * ldb)
+                : make_map3(&maps.b, b_planes, N, K, ldb, N * ldb, kLBN);
   if (rc != PTREC_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
