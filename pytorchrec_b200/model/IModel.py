@@ -95,8 +95,15 @@ class _GraphedTrainStep:
             e["graph"], e["loss"] = g, loss
             e["launches"] = int(_lib.load().ptrec_launch_count() - l0)  # recorded into the graph, not yet run
         elif on_host:
-            e["packer"].load(data)
-        else:
+            pre = m._take_prefetched(data) if m._prefetched else None
+            if pre is not None:   # already on the device (copy stream): one D2D copy into the graph's static inputs
+                e["packer"].dev.copy_(pre[1].dev, non_blocking=True)
+                pre[2]()
+            else:
+                e["packer"].load(data)
+        elif getattr(data, "buffer", None) is not None and data.signature == e["packer"].signature():
+            e["packer"].dev.copy_(data.buffer, non_blocking=True)  # IModel.stage(): one D2D copy for the whole batch
+        else:  # loose device tensors: one copy per key
             for k, v in e["static"].items():
                 v.copy_(data[k], non_blocking=True)
         e["graph"].replay()
@@ -130,6 +137,8 @@ class IModel(Module, ABC):
         self._graphed: Optional[_GraphedTrainStep] = None
         self._packers: Dict[tuple, Any] = {}
         self.packed_ingest = True  # N1: host batches move with one pinned packed copy instead of one copy per key
+        self._prefetch: Dict[tuple, dict] = {}   # batch signature -> {"packers": [2], "i", "stream"}
+        self._prefetched: list = []              # [(batch dict, device views, ready event, packer)], at most 2
         self.register_forward_pre_hook(_drop_lookup_cache)
         self._init_weights()
         self._reset_weights()
@@ -199,10 +208,71 @@ class IModel(Module, ABC):
             return self._graphed.step(data)
         return self._eager_train_step(data)
 
+    def prefetch(self, data: Dict) -> Dict:
+        """N1: start the host -> device transfer of a batch that a later ``train_step`` / ``test_step`` call will
+        consume, on a copy stream, so that it overlaps the step that is running (the data-loader pattern: call it
+        for batch k+1 right after ``train_step(batch k)``).  Double-buffered; passing the same dict object to the
+        step picks the transfer up.  Returns ``data``; a no-op for device batches or CPU models."""
+        dev = self.compiled_device
+        if not (self.packed_ingest and dev is not None and dev.type == "cuda" and isinstance(data, dict) and data
+                and all(isinstance(v, torch.Tensor) and v.device.type == "cpu" for v in data.values())):
+            return data
+        from ..utils.ingest import BatchPacker
+        sig = tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in data.items()))
+        pf = self._prefetch.get(sig)
+        if pf is None:
+            pf = self._prefetch[sig] = {"packers": [BatchPacker(data, dev), BatchPacker(data, dev)], "i": 0,
+                                        "stream": torch.cuda.Stream(dev), "consumed": [None, None]}
+        i = pf["i"]
+        pf["i"] ^= 1
+        packer, stream = pf["packers"][i], pf["stream"]
+        if pf["consumed"][i] is not None:
+            stream.wait_event(pf["consumed"][i])  # the step that read this buffer two prefetches ago is done with it
+        with torch.cuda.stream(stream):
+            views = packer.load(data)
+            ready = torch.cuda.Event()
+            ready.record(stream)
+        self._prefetched = [r for r in self._prefetched if r[0] is not data][-1:] + [(data, views, ready, packer, pf, i)]
+        return data
+
+    def stage(self, data: Dict) -> Dict:
+        """A device-resident, packed copy of a batch (N1): ``train_step`` / ``test_step`` accept it like any batch
+        dict; the CUDA-graph step moves it into its static inputs with one copy instead of one per key."""
+        dev = self.compiled_device
+        if dev is None or dev.type != "cuda":
+            return tensor_to_device(data, dev)
+        from ..utils.ingest import BatchPacker
+        sig = tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in data.items()))
+        packer = self._packers.get(sig)
+        if packer is None:
+            packer = self._packers[sig] = BatchPacker(data, dev)
+        return packer.stage(data)
+
+    def _take_prefetched(self, data: Dict):
+        """(device views, packer, release) of a batch handed to ``prefetch`` earlier, or None.  The current stream is
+        made to wait for the transfer; ``release()`` must be called once the step's reads of the views are enqueued."""
+        for n, rec in enumerate(self._prefetched):
+            if rec[0] is data:
+                del self._prefetched[n]
+                _, views, ready, packer, pf, i = rec
+                cur = torch.cuda.current_stream(self.compiled_device)
+                cur.wait_event(ready)
+
+                def release():
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    pf["consumed"][i] = ev
+                return views, packer, release
+        return None
+
     def _to_device(self, data: Dict):
         """Host -> device move of one batch.  CUDA target + host tensors: one packed pinned transfer (N1);
         otherwise the reference's per-key ``tensor_to_device`` (IModel.py:119)."""
         dev = self.compiled_device
+        pre = self._take_prefetched(data) if self._prefetched else None
+        if pre is not None:
+            self._release_after_step = pre[2]
+            return pre[0]
         if (self.packed_ingest and dev is not None and dev.type == "cuda" and isinstance(data, dict) and data
                 and all(isinstance(v, torch.Tensor) and v.device.type == "cpu" for v in data.values())):
             sig = tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in data.items()))
@@ -216,7 +286,14 @@ class IModel(Module, ABC):
     def _eager_train_step(self, data: Dict):
         self.train()
         data = self._to_device(data)
-        return {"loss": self._train_step_body(data)}
+        # detached: a loss that keeps its autograd graph alive would pin AccumulateGrad nodes to the stream of this
+        # eager step and break a later CUDA-graph capture of the same parameters
+        logs = {"loss": self._train_step_body(data).detach()}
+        rel = getattr(self, "_release_after_step", None)
+        if rel is not None:  # the prefetch buffer may be refilled once this step's kernels have read it
+            self._release_after_step = None
+            rel()
+        return logs
 
     def _train_step_body(self, data: Dict):
         """forward, loss, zero_grad, backward, [gradient hook], step — IModel.py:120-124."""
@@ -235,6 +312,10 @@ class IModel(Module, ABC):
         self.eval()
         data = self._to_device(data)
         prediction, target = self(data)
+        rel = getattr(self, "_release_after_step", None)
+        if rel is not None:
+            self._release_after_step = None
+            rel()
         return prediction, target
 
     def predict_step(self, data):
@@ -257,8 +338,15 @@ class IModel(Module, ABC):
                 dataset.train_neg_sample()
             loader = DataLoader(dataset=dataset, batch_size=batch_size, shuffle=shuffle, num_workers=workers,
                                 drop_last=drop_last)
-            for data in loader:
+            it = iter(loader)
+            data = next(it, None)
+            if data is not None:
+                self.prefetch(data)
+            while data is not None:
                 logs = self.train_step(data)
+                data = next(it, None)       # the loader builds batch k+1 and its transfer starts while step k runs
+                if data is not None:
+                    self.prefetch(data)
             epoch_logs = copy.copy(logs)
             if dev_dataset is not None and (epoch + 1) % dev_freq == 0:
                 epoch_logs.update(self.evaluate(dev_dataset, dev_batch_size or batch_size, workers=workers))

@@ -15,6 +15,13 @@ from torch import Tensor
 _ALIGN = 256
 
 
+class PackedBatch(dict):
+    """A batch whose tensors are typed views of ONE device buffer (``buffer``): still the reference's
+    ``Dict[str, Tensor]`` wire format for ``forward``, but movable with a single copy."""
+    buffer: Tensor = None
+    signature: tuple = ()
+
+
 class BatchPacker:
     def __init__(self, example: Dict[str, Tensor], device: torch.device, n_staging: int = 2):
         self.device = device
@@ -39,6 +46,15 @@ class BatchPacker:
 
     def signature(self):
         return tuple((k, str(dt), shp) for k, dt, shp, _, _ in self.layout)
+
+    def stage(self, batch: Dict[str, Tensor]) -> PackedBatch:
+        """A device-resident copy of ``batch`` (host or device tensors) in its own packed buffer."""
+        buf = torch.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+        out = PackedBatch({k: self._view(buf, dt, shp, o, n) for k, dt, shp, o, n in self.layout})
+        for k in out:
+            out[k].copy_(batch[k])
+        out.buffer, out.signature = buf, self.signature()
+        return out
 
     def load(self, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
         """Pack ``batch`` (host tensors of the example's shapes / dtypes) and enqueue the single H2D copy on the

@@ -497,3 +497,53 @@ def test_fused_dense_parameter_step_equals_torch_optim(name, kw):
 def _lib_launches():
     from pytorchrec_b200 import _lib
     return _lib.load().ptrec_launch_count()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True])
+def test_prefetched_batches_train_exactly_like_direct_ones(graph):
+    """N1: prefetch(batch k+1) during step k (copy stream, double-buffered) gives bit-identical training."""
+    scols, dcols, lab, rows = _ctr_setup(F=5, nd=2)
+    models = []
+    for _ in range(2):
+        m = DeepFM(scols, dcols, lab, 8, [16, 8], random_seed=11)
+        m.compile(SparseAdagrad(m.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], DEV)
+        if graph:
+            m.enable_cuda_graph(True, warmup=2)
+        models.append(m)
+    direct, pre = models
+    batches = [_ctr_batch(rows, len(dcols), 128, seed=40 + s) for s in range(7)]
+    pre.prefetch(batches[0])
+    for i, b in enumerate(batches):
+        la = direct.train_step({k: v.clone() for k, v in b.items()})["loss"]
+        lb = pre.train_step(b)["loss"]
+        if i + 1 < len(batches):
+            pre.prefetch(batches[i + 1])
+        assert torch.equal(la, lb), i
+    with torch.no_grad():
+        pre.prefetch(batches[0])
+        pa, _ = direct.test_step(batches[0])
+        pb, _ = pre.test_step(batches[0])
+    assert torch.equal(pa, pb)
+    for (k, v), (_, w) in zip(direct.state_dict().items(), pre.state_dict().items()):
+        assert torch.equal(v, w), k
+
+
+@pytest.mark.gpu
+def test_staged_device_batches_train_exactly_like_host_ones():
+    """N1: IModel.stage() keeps a batch resident in one packed device buffer; graph and eager steps accept it."""
+    scols, dcols, lab, rows = _ctr_setup(F=5, nd=2)
+    models = []
+    for _ in range(2):
+        m = DeepFM(scols, dcols, lab, 8, [16, 8], random_seed=12)
+        m.compile(SparseAdagrad(m.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], DEV)
+        m.enable_cuda_graph(True, warmup=2)
+        models.append(m)
+    a, b = models
+    batches = [_ctr_batch(rows, len(dcols), 128, seed=60 + s) for s in range(5)]
+    staged = [b.stage(x) for x in batches]
+    assert all(v.is_cuda for v in staged[0].values()) and staged[0].buffer is not None
+    for x, y in zip(batches, staged):
+        assert torch.equal(a.train_step(x)["loss"], b.train_step(y)["loss"])
+    for (k, v), (_, w) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(v, w), k
