@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 10
+#define PTREC_ABI_VERSION 11
 
 /* error codes */
 #define PTREC_OK 0
@@ -157,6 +157,12 @@ int ptrec_embedding_gather_pool_fwd_sharded(const void* const* shard_ptrs, const
                                             const ptrec_feature_desc* feats_host, int32_t F,
                                             const int64_t* ids, int64_t B, float* out, int64_t out_row_stride,
                                             int32_t* err_flag, void* stream);
+
+/* K2a has two code paths with identical outputs: one CTA per table entirely in shared memory (2 launches), and
+ * the multi-launch global radix sort.  mode 0 = global only, 1 = automatic (shared memory for small batches, where
+ * launch latency dominates; default), 2 = shared memory whenever a table's batch fits (<= 22528 slots). */
+void ptrec_set_smem_sort(int32_t mode);
+int32_t ptrec_smem_sort_enabled(void);
 
 /* ---------------------------------------------------------------------------------------------
  * K2a segmented sort + dedup of the lookups of one batch (the integer half of the backward).

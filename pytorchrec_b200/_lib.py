@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libptrec_b200.so")
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # enums (mirror include/ptrec_b200.h)
 F32, BF16 = 0, 1
@@ -76,6 +76,8 @@ PROTOTYPES = {
     "ptrec_embedding_gather_pool_fwd_sharded": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64,
                                                         c_int32, _FD, _FD, c_int32, c_void_p, c_int64, c_void_p,
                                                         c_int64, c_void_p, c_void_p]),
+    "ptrec_set_smem_sort": (None, [c_int32]),
+    "ptrec_smem_sort_enabled": (c_int32, []),
     "ptrec_sort_dedup_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "ptrec_sort_dedup": (c_int, [_FD, _FD, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p,
                                  c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -189,9 +189,18 @@ def _check_sort(layout, tables, ids_dev, lens_dev, B, specs, id_list, lens_list,
     return srt
 
 
-@pytest.mark.parametrize("B", [1, 100, 2048, 5000])
+@pytest.fixture(params=["smem_sort", "global_sort"])
+def sort_path(request):
+    """K2a has a one-CTA-per-table shared-memory path and a multi-launch global path: same outputs from both."""
+    lib = _lib.load()
+    lib.ptrec_set_smem_sort(2 if request.param == "smem_sort" else 0)
+    yield request.param
+    lib.ptrec_set_smem_sort(1)
+
+
+@pytest.mark.parametrize("B", [1, 100, 2048, 5000, 22528, 30000])
 @pytest.mark.parametrize("rows", [[3, 70000, 257], [1 << 20, 9, 300]])
-def test_sort_dedup_bit_exact_onehot(B, rows):
+def test_sort_dedup_bit_exact_onehot(B, rows, sort_path):
     D = 4
     weights = _tables([min(r, 64) for r in rows], D, seed=1)  # contents irrelevant: only row counts matter
     id_list = [_ids((B,), rows[t], seed=B + t, zipf=(t == 1)) for t in range(3)]
@@ -206,7 +215,7 @@ def test_sort_dedup_bit_exact_onehot(B, rows):
 
 
 @pytest.mark.parametrize("mask", ["pad", "pad_keep_first", "lens"])
-def test_sort_dedup_bags_masks_and_shared_table(mask):
+def test_sort_dedup_bags_masks_and_shared_table(mask, sort_path):
     B, L, D = 257, 19, 8
     rows = [40, 1000]
     id_list = [_ids((B,), rows[0], seed=1), _ids((B, L), rows[0], seed=2, pad_frac=0.5), _ids((B, 3), rows[1], seed=3)]
@@ -223,7 +232,7 @@ def test_sort_dedup_bags_masks_and_shared_table(mask):
     _check_sort(layout, tables, ids, lens_dev, B, specs, id_list, [None, lens, None], rows)
 
 
-def test_sort_dedup_out_of_range_ids_are_masked():
+def test_sort_dedup_out_of_range_ids_are_masked(sort_path):
     rows = [10]
     ids = torch.tensor([3, 10, -4, 3, 0, 9], dtype=torch.int64)
     layout = ops.FeatureLayout([dict(table=0, bag_len=1)], 4, 1)
