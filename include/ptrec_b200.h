@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 11
+#define PTREC_ABI_VERSION 12
 
 /* error codes */
 #define PTREC_OK 0
@@ -339,6 +339,11 @@ int ptrec_dense_optim_step(const ptrec_dense_tensor* tensors, const int32_t* chu
  *   stored matrices.   dW = g^T x : A = planes(g) [B, N], B = planes(x) [B, K] — the row-major planes the forward
  *   and the input-gradient GEMMs already use, so the weight gradient needs no transposed copies.
  */
+/* The GEMM has a CTA-pair (cta_group::2, 256 x 256 tiles; default) and a single-CTA (128 x 256) kernel with
+ * identical results; tests run both. */
+void ptrec_tc_set_2sm(int32_t enabled);
+void ptrec_tc_set_bk(int32_t bk); /* CTA-pair kernel: K elements per stage, 32 (4 stages) or 64 (2 stages) */
+int32_t ptrec_tc_2sm_enabled(void);
 size_t ptrec_tc_split3_workspace_bytes(int64_t R, int64_t C);
 int ptrec_tc_split3(const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref, int64_t ld_ref,
                     void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld, float* colsum, void* workspace,

@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libptrec_b200.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # enums (mirror include/ptrec_b200.h)
 F32, BF16 = 0, 1
@@ -93,6 +93,9 @@ PROTOTYPES = {
                                                 c_void_p, c_void_p, c_void_p]),
     "ptrec_dense_optim_chunk": (c_int32, []),
     "ptrec_dense_optim_step": (c_int, [c_void_p, c_void_p, c_int32, c_int32, POINTER(OptimArgs), c_void_p]),
+    "ptrec_tc_set_2sm": (None, [c_int32]),
+    "ptrec_tc_set_bk": (None, [c_int32]),
+    "ptrec_tc_2sm_enabled": (c_int32, []),
     "ptrec_tc_split3_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "ptrec_tc_split3": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                 c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),

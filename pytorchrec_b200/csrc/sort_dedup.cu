@@ -280,7 +280,6 @@ smem_sort_kernel(TableLayout lay, int64_t B, int passes, const ptrec_feature_des
   uint16_t* s_idx1 = s_idx0 + n_cap;                                    // [n_cap]
   uint16_t* s_cnt = s_idx1 + n_cap;                                     // [32][256]
   __shared__ ptrec_feature_desc s_feats[kSmemSortMaxFeat];
-  __shared__ int s_tot[256];
   __shared__ int s_dbase[256];
   __shared__ int s_wt[8];
   __shared__ int s_red[32];
@@ -334,7 +333,6 @@ smem_sort_kernel(TableLayout lay, int64_t B, int passes, const ptrec_feature_des
         s_cnt[w * 256 + d] = (uint16_t)run;
         run += c;
       }
-      s_tot[d] = run;
       int v = run;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {

@@ -410,29 +410,269 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
   }
 }
 
+// ------------------------------------------------------------------------------------------------ 2-SM variant
+// The same GEMM with CTA pairs (cta_group::2): a pair owns a 256 x 256 tile — each CTA holds 128 rows of A, its own
+// 128 accumulator rows in TMEM, and HALF of the B tile; the pair's tensor cores share the B halves.  Per CTA and K
+// block that is 48 KB from L2 (72 KB in the 1-SM kernel) and two thirds of the shared-memory operand reads, the two
+// limits the 1-SM kernel runs into.  Both CTAs run a TMA producer (completing on the leader's barrier), only the
+// leader issues MMAs; tcgen05.commit multicasts the stage release / accumulator-ready arrivals to both CTAs, and both
+// CTAs' epilogue warps arrive remotely on the leader's accumulator-free barrier.
+constexpr size_t k2Smem = (size_t)192 * 1024 + 1024 /*align*/ + 2048 /*barriers + bias slice*/;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;         // clears the CTA-pair bit of a shared::cluster address -> leader
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {  // arrives on `bar` in BOTH CTAs of the pair
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // remote arrive on the leader CTA's barrier
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
+// BK = K elements per stage: 32 (64-byte swizzle, 4 stages of 48 KB) or 64 (128-byte swizzle, 2 stages of 96 KB)
+template <bool MN_MAJOR, int BK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
+gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, LinEpi ep) {
+  constexpr int k2Stages = BK == 64 ? 2 : 4;
+  constexpr uint32_t k2Tile = 128 * BK * 2;     // any plane tile: 128 rows (or 2 boxes of 64 mn) x BK bf16
+  constexpr uint32_t k2StageBytes = 6 * k2Tile; // A0 A1 A2 B0 B1 B2 (B = this CTA's half)
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)k2Stages * k2StageBytes);
+  uint64_t* full = bars;                    // [k2Stages]  (the leader's are the ones in use)
+  uint64_t* empty = bars + k2Stages;        // [k2Stages]
+  uint64_t* acc_full = bars + 2 * k2Stages; // [1]
+  uint64_t* acc_empty = acc_full + 1;       // [1]  (leader's)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  float* s_bias = reinterpret_cast<float*>(bars + 16);  // [256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int tiles_n = (N + 255) / 256, tiles_m = (M + 255) / 256;
+  const int splits = max(ep.splits, 1);
+  const int mn_tiles = tiles_n * tiles_m;
+  const int n_tiles = mn_tiles * splits;
+  const int total_kb = (K + BK - 1) / BK;
+  const int kb_per_split = (total_kb + splits - 1) / splits;
+  const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < k2Stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 2 * kLEpiWarps);  // the epilogue warps of both CTAs
+    fence_mbar_init();
+  }
+  cluster_sync_all();  // the peer's barriers exist before anything arrives on them
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kLTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b) : "memory");
+      int kbg = 0;
+      for (int tile = cid; tile < n_tiles; tile += n_clusters) {
+        const int mn = tile % mn_tiles, split = tile / mn_tiles;
+        const int m0 = (mn % tiles_m) * 256 + rank * 128, n0 = (mn / tiles_m) * 256;
+        const int n_eff = min(256, (N - n0 + 15) & ~15);
+        const int nb0 = n0 + rank * (n_eff >> 1);  // this CTA's half of the B tile
+        const int kb0 = split * kb_per_split, num_kb = max(0, min(total_kb - kb0, kb_per_split));
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const int s = kbg % k2Stages;
+          mbar_wait(&empty[s], ((kbg / k2Stages) & 1) ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * k2StageBytes);  // both CTAs' bytes land on the leader
+          unsigned char* sa = smem + (size_t)s * k2StageBytes;
+          unsigned char* sb = sa + 3 * k2Tile;
+          const int k0 = (kb0 + kb) * BK;
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            if (MN_MAJOR) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                tma_load_3d_2sm(sa + (size_t)p * k2Tile + (size_t)j * (k2Tile / 2), &maps.a, m0 + 64 * j, k0, p, &full[s]);
+                tma_load_3d_2sm(sb + (size_t)p * k2Tile + (size_t)j * (k2Tile / 2), &maps.b, nb0 + 64 * j, k0, p, &full[s]);
+              }
+            } else {
+              tma_load_3d_2sm(sa + (size_t)p * k2Tile, &maps.a, k0, m0, p, &full[s]);
+              tma_load_3d_2sm(sb + (size_t)p * k2Tile, &maps.b, k0, nb0, p, &full[s]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int kbg = 0, it = 0;
+      for (int tile = cid; tile < n_tiles; tile += n_clusters, ++it) {
+        mbar_wait(acc_empty, (it & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base;
+        const uint32_t tmem_c = tmem_base + 256u;
+        const int mn = tile % mn_tiles;
+        const int n0 = (mn / tiles_m) * 256;
+        const int n_eff = min(256, (N - n0 + 15) & ~15);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_eff >> 3) << 17) |
+                               ((uint32_t)(256 >> 4) << 24) | (MN_MAJOR ? ((1u << 15) | (1u << 16)) : 0u);
+        const int kb0 = (tile / mn_tiles) * kb_per_split, num_kb = max(0, min(total_kb - kb0, kb_per_split));
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const int s = kbg % k2Stages;
+          mbar_wait(&full[s], (kbg / k2Stages) & 1);
+          tcgen05_fence_after();
+          unsigned char* sa = smem + (size_t)s * k2StageBytes;
+          unsigned char* sb = sa + 3 * k2Tile;
+          uint64_t ad[3], bd[3];
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            const void* pa = sa + (size_t)p * k2Tile;
+            const void* pb = sb + (size_t)p * k2Tile;
+            if (BK == 64) {
+              ad[p] = MN_MAJOR ? make_sw128_mn_desc(pa) : make_sw128_desc(pa);
+              bd[p] = MN_MAJOR ? make_sw128_mn_desc(pb) : make_sw128_desc(pb);
+            } else {
+              ad[p] = MN_MAJOR ? make_sw128_mn32_desc(pa) : make_sw64_desc(pa);
+              bd[p] = MN_MAJOR ? make_sw128_mn32_desc(pb) : make_sw64_desc(pb);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < BK / kLUmmaK; ++k) {
+            const uint64_t o = MN_MAJOR ? (uint64_t)(k * 128) : (uint64_t)(k * 2);
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_bf16_2sm(tmem_c, ad[0] + o, bd[2] + o, idesc, acc);
+            umma_bf16_2sm(tmem_c, ad[2] + o, bd[0] + o, idesc, 1u);
+            umma_bf16_2sm(tmem_c, ad[1] + o, bd[1] + o, idesc, 1u);
+            umma_bf16_2sm(tmem_c, ad[0] + o, bd[1] + o, idesc, 1u);
+            umma_bf16_2sm(tmem_c, ad[1] + o, bd[0] + o, idesc, 1u);
+            umma_bf16_2sm(tmem_d, ad[0] + o, bd[0] + o, idesc, acc);
+          }
+          umma_commit_2sm(&empty[s]);
+        }
+        umma_commit_2sm(acc_full);
+      }
+    }
+  } else {
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int half = e >> 2;
+    const int r = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    int it = 0;
+    for (int tile = cid; tile < n_tiles; tile += n_clusters, ++it) {
+      const int mn = tile % mn_tiles, split = tile / mn_tiles;
+      const int m0 = (mn % tiles_m) * 256 + rank * 128, n0 = (mn / tiles_m) * 256;
+      if (ep.bias != nullptr) {
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kLEpiWarps) : "memory");
+        if (et < 256) s_bias[et] = (n0 + et < N) ? ep.bias[n0 + et] : 0.f;
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kLEpiWarps) : "memory");
+      }
+      mbar_wait(acc_full, it & 1);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+      const int row = m0 + r, col0 = n0 + half * 128;
+      const bool live = col0 < N;
+      uint32_t v[128];
+      if (live) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          uint32_t w[32];
+          tmem_ld32(tacc + h * 32, v + h * 32);
+          tmem_ld32(tacc + 256 + h * 32, w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[h * 32 + j] = __float_as_uint(__uint_as_float(v[h * 32 + j]) + __uint_as_float(w[j]));
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(acc_empty);
+      if (live && row < M) {
+        float* o = ep.out + ((int64_t)split * M + row) * ep.ldo + col0;
+        const bool has_bias = ep.bias != nullptr;
+#pragma unroll
+        for (int j = 0; j < 128; j += 4) {
+          if (col0 + j < N) {
+            float4 t = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                   __uint_as_float(v[j + 3]));
+            if (has_bias) {
+              const float4 b = *reinterpret_cast<const float4*>(&s_bias[half * 128 + j]);
+              t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+            }
+            if (ep.relu) {
+              t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(o + j) = t;
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // both CTAs are done with TMEM and with each other's barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kLTmemCols) : "memory");
+  }
+}
+
 // K-major operand: 3-D bf16 map over planes [3][rows][ld]: dims (cols, rows, 3), box 32 x box_rows x 1, 64B swizzle
 static int make_map3(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int64_t plane,
-                     int box_rows) {
+                     int box_rows, int bk = kLBK) {
   EncodeTiledFn enc = get_encode();
   PTREC_CHECK_ARG(enc != nullptr, PTREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 3};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
-  cuuint32_t box[3] = {(cuuint32_t)kLBK, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PTREC_CHECK_ARG(r == CUDA_SUCCESS, PTREC_ECUDA, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
   return PTREC_OK;
 }
 
 // MN-major operand: planes [3][k_rows][ld] with the M/N dimension contiguous; box 64 (mn) x 32 (k rows) x 1
-static int make_map3_mn(CUtensorMap* map, const void* base, int64_t k_rows, int64_t mn, int64_t ld, int64_t plane) {
+static int make_map3_mn(CUtensorMap* map, const void* base, int64_t k_rows, int64_t mn, int64_t ld, int64_t plane,
+                        int bk = kLBK) {
   EncodeTiledFn enc = get_encode();
   PTREC_CHECK_ARG(enc != nullptr, PTREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[3] = {(cuuint64_t)mn, (cuuint64_t)k_rows, 3};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)kLBK, 1};
+  cuuint32_t box[3] = {64, (cuuint32_t)bk, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -480,6 +720,12 @@ extern "C" int ptrec_tc_split3(const float* src, int64_t ld, int64_t R, int64_t 
   return PTREC_OK;
 }
 
+static int g_tc_bk = 32;
+extern "C" void ptrec_tc_set_bk(int32_t bk) { g_tc_bk = bk == 64 ? 64 : 32; }
+static int g_tc_2sm = 1;
+extern "C" void ptrec_tc_set_2sm(int32_t enabled) { g_tc_2sm = enabled ? 1 : 0; }
+extern "C" int32_t ptrec_tc_2sm_enabled(void) { return g_tc_2sm; }
+
 extern "C" size_t ptrec_tc_gemm_split3_workspace_bytes(int64_t M, int64_t ldo, int32_t splits) {
   return splits > 1 ? align_up((size_t)splits * M * ldo * sizeof(float), 256) : 0;
 }
@@ -489,7 +735,9 @@ extern "C" int32_t ptrec_tc_gemm_split3_default_splits(int64_t M, int64_t N, int
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t tiles = ceil_div(M, kLBM) * ceil_div(N, kLBN), kbs = ceil_div(K, kLBK);
+  const int64_t tiles = g_tc_2sm ? ceil_div(M, 256) * ceil_div(N, 256) : ceil_div(M, kLBM) * ceil_div(N, kLBN);
+  const int64_t kbs = ceil_div(K, kLBK);
+  if (g_tc_2sm) sms /= 2;  // work items are CTA pairs
   int64_t s = tiles >= sms ? 1 : sms / tiles;
   s = std::max<int64_t>(1, std::min<int64_t>(s, kbs / 4 > 0 ? kbs / 4 : 1));
   return (int32_t)std::min<int64_t>(s, 64);
@@ -505,7 +753,7 @@ static int gemm_split3_impl(bool mn_major, const void* a_planes, int64_t M, int6
                       lda >= (mn_major ? M : K) && ldb >= (mn_major ? N : K) && ldo % 4 == 0 && ldo >= (N + 3) / 4 * 4,
                   PTREC_EALIGN, "tc_gemm_split3: pitches must be multiples of 8 (planes) / 4 (out) elements");
   if (splits < 1) splits = 1;
-  const int total_kb = (int)ceil_div(K, kLBK);
+  const int total_kb = (int)ceil_div(K, (g_tc_2sm ? g_tc_bk : kLBK));
   if (splits > total_kb) splits = total_kb;
   while (splits > 1 && (int64_t)(splits - 1) * ceil_div(total_kb, splits) >= total_kb) --splits;  // no empty split
   PTREC_CHECK_ARG(splits == 1 || (!bias && !relu), PTREC_EINVAL, "tc_gemm_split3: split-K has no bias / ReLU epilogue");
@@ -514,24 +762,50 @@ static int gemm_split3_impl(bool mn_major, const void* a_planes, int64_t M, int6
   cudaStream_t st = (cudaStream_t)stream;
   LinMaps maps;
   memset(&maps, 0, sizeof(maps));
-  int rc = mn_major ? make_map3_mn(&maps.a, a_planes, K, M, lda, K * lda)
-                    : make_map3(&maps.a, a_planes, M, K, lda, M * lda, kLBM);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool two_sm = g_tc_2sm != 0 && sms >= 2;
+  const int bk = two_sm ? g_tc_bk : kLBK;
+  int rc = mn_major ? make_map3_mn(&maps.a, a_planes, K, M, lda, K * lda, bk)
+                    : make_map3(&maps.a, a_planes, M, K, lda, M * lda, kLBM, bk);
   if (rc != PTREC_OK) return rc;
-  rc = mn_major ? make_map3_mn(&maps.b, b_planes, K, N, ldb, K * ldb)
-                : make_map3(&maps.b, b_planes, N, K, ldb, N * ldb, kLBN);
+  rc = mn_major ? make_map3_mn(&maps.b, b_planes, K, N, ldb, K * ldb, bk)
+                : make_map3(&maps.b, b_planes, N, K, ldb, N * ldb, two_sm ? 128 : kLBN, bk);
   if (rc != PTREC_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem));
     PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem));
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
     attr_set = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   LinEpi ep;
   ep.bias = bias; ep.relu = relu; ep.ldo = ldo; ep.splits = splits;
   ep.out = splits > 1 ? reinterpret_cast<float*>(workspace) : out;
+  if (two_sm) {
+    const int64_t pair_tiles = ceil_div(N, 256) * ceil_div(M, 256) * splits;
+    const int64_t clusters = std::min<int64_t>(pair_tiles, sms / 2);
+    const unsigned grid2 = (unsigned)(2 * clusters);
+    if (mn_major && bk == 64)
+      gemm_split3_2sm_kernel<true, 64><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+    else if (mn_major)
+      gemm_split3_2sm_kernel<true, 32><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+    else if (bk == 64)
+      gemm_split3_2sm_kernel<false, 64><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+    else
+      gemm_split3_2sm_kernel<false, 32><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+    PTREC_LAUNCH_CHECK("gemm_split3_2sm_kernel");
+    if (splits > 1) {
+      const int64_t n = M * ldo;
+      partial_reduce_kernel<<<(unsigned)ceil_div(n / 4, 256), 256, 0, st>>>(ep.out, splits, n, out);
+      PTREC_LAUNCH_CHECK("partial_reduce_kernel");
+    }
+    return PTREC_OK;
+  }
   const int64_t tiles = ceil_div(N, kLBN) * ceil_div(M, kLBM) * splits;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
   if (mn_major)

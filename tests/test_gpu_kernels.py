@@ -535,6 +535,15 @@ def test_din_attention_pool_forward_backward(B, L, DQ, hidden):
 # ---------------------------------------------------------------------------------------------------------------
 # K6 fp32-faithful Linear on tcgen05 (bf16 x 3 split operands)
 # ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(params=["2sm", "1sm"])
+def tc_mode(request):
+    """K6 GEMM: CTA-pair (cta_group::2) and single-CTA kernels must agree with fp64 alike."""
+    lib = _lib.load()
+    lib.ptrec_tc_set_2sm(1 if request.param == "2sm" else 0)
+    yield request.param
+    lib.ptrec_tc_set_2sm(1)
+
+
 def _planes_sum(pl, rows, cols):
     return (pl[2, :rows, :cols].float() + pl[1, :rows, :cols].float()) + pl[0, :rows, :cols].float()
 
@@ -564,7 +573,7 @@ def test_tc_split3_planes_are_an_exact_decomposition(R, C):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 400, 429), (1000, 16, 40), (2048, 429, 400), (130, 1, 700)])
-def test_tc_gemm_split3_has_fp32_level_error(M, N, K):
+def test_tc_gemm_split3_has_fp32_level_error(M, N, K, tc_mode):
     """|C - C_fp64| is at the level of an fp32 GEMM (<= 2e-6 of sum|a||b|), far from bf16 / tf32 error."""
     gen = torch.Generator().manual_seed(M + N + K)
     a = torch.randn(M, K, generator=gen).to(DEV)
@@ -588,7 +597,7 @@ def test_tc_gemm_split3_has_fp32_level_error(M, N, K):
 
 
 @pytest.mark.gpu
-def test_tc_gemm_split3_weight_gradient_shape_with_transposed_planes():
+def test_tc_gemm_split3_weight_gradient_shape_with_transposed_planes(tc_mode):
     B, N, K = 4096, 400, 429
     gen = torch.Generator().manual_seed(5)
     g = torch.randn(B, N, generator=gen).to(DEV)
@@ -604,7 +613,7 @@ def test_tc_gemm_split3_weight_gradient_shape_with_transposed_planes():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,N,K", [(4096, 400, 429), (1000, 128, 64), (777, 16, 1030), (64, 200, 13)])
-def test_tc_gemm_split3_tn_weight_gradient_from_row_major_planes(B, N, K):
+def test_tc_gemm_split3_tn_weight_gradient_from_row_major_planes(B, N, K, tc_mode):
     """dW = g^T x straight from the row-major planes (MN-major tcgen05 operands): no transposed copies."""
     gen = torch.Generator().manual_seed(B + N)
     g = torch.randn(B, N, generator=gen).to(DEV)

@@ -13,6 +13,9 @@ def timeit(fn, n=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
 B = int(os.environ.get("B", 16384))
+from pytorchrec_b200 import _lib
+_lib.load().ptrec_tc_set_2sm(int(os.environ.get("TWO_SM", "1")))
+_lib.load().ptrec_tc_set_bk(int(os.environ.get("BK", "32")))
 for K, N in ((429, 400), (400, 400), (1024, 1024)):
     x = torch.randn(B, K, device=dev); w = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev)
     g = torch.randn(B, N, device=dev)
