@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 12
+#define PTREC_ABI_VERSION 13
 
 /* error codes */
 #define PTREC_OK 0
@@ -392,6 +392,13 @@ int ptrec_a2a_pack_by_owner_peer(const int64_t* ids, int64_t B, int32_t F, int32
 int ptrec_a2a_scatter_rows_peer(const float* src, int64_t src_row_stride, const int32_t* ret_pos, int64_t B,
                                 int32_t F, int32_t D, float scale, float* const* peer_dst, int64_t dst_row_stride,
                                 int64_t dst_col, int32_t C, int32_t G, int32_t my_rank, void* stream);
+
+/* Same, every embedding width of the fields in one launch (srcs / strides / dims / dst_cols: HOST arrays of n_widths
+ * entries, n_widths <= 4): the stores of one slot to its owner are adjacent. */
+int ptrec_a2a_scatter_rows_peer_multi(const float* const* srcs, const int64_t* src_row_strides, const int32_t* dims,
+                                      const int64_t* dst_cols, int32_t n_widths, const int32_t* ret_pos, int64_t B,
+                                      int32_t F, float scale, float* const* peer_dst, int64_t dst_row_stride,
+                                      int32_t C, int32_t G, int32_t my_rank, void* stream);
 
 #ifdef __cplusplus
 }

@@ -154,6 +154,46 @@ scatter_rows_peer_kernel(const float* __restrict__ src, int64_t src_row_stride, 
   store_row<VEC>(peer_dst[owner] + row * dst_row_stride + dst_col + lane * VEC, r);
 }
 
+// every width of a slot in ONE launch: the slot's lanes cover the float4 chunks of [width 0 | width 1 | ...], so the
+// stores of one slot to its owner are adjacent (e.g. DeepFM: 64 B embedding gradient + 4 B first-order gradient)
+constexpr int kMaxWidths = 4;
+struct PeerWidths {
+  const float* src[kMaxWidths];
+  int64_t stride[kMaxWidths];
+  int32_t dim[kMaxWidths];
+  int32_t col[kMaxWidths];
+  int32_t chunk0[kMaxWidths + 1];  // first float4 chunk of each width
+  int32_t n;
+};
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+scatter_rows_peer_multi_kernel(PeerWidths w, const int32_t* __restrict__ pos, int64_t B, int F, float scale,
+                               float* const* __restrict__ peer_dst, int64_t dst_row_stride, int FC, int my_rank) {
+  const int64_t g = ((int64_t)blockIdx.x * 256 + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;
+  if (g >= B * F || lane >= w.chunk0[w.n]) return;
+  const int64_t b = g / F;
+  const int f = (int)(g - b * F);
+  const int32_t p = pos[(int64_t)f * B + b];
+  if (p < 0) return;
+  int k = 0;
+  while (k + 1 < w.n && lane >= w.chunk0[k + 1]) ++k;
+  const int c = (lane - w.chunk0[k]) * 4;           // first element of this lane's chunk inside width k
+  const int D = w.dim[k];
+  const int owner = p / FC;
+  const int64_t row = (int64_t)my_rank * FC + (p - owner * FC);
+  const float* s = w.src[k] + b * w.stride[k] + (int64_t)f * D + c;
+  float* d = peer_dst[owner] + row * dst_row_stride + w.col[k] + c;
+  if (c + 3 < D && (D & 3) == 0) {
+    float4 v = *reinterpret_cast<const float4*>(s);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    *reinterpret_cast<float4*>(d) = v;
+  } else {
+    for (int i = 0; i < 4 && c + i < D; ++i) d[i] = s[i] * scale;
+  }
+}
+
 }  // namespace ptrec
 
 using namespace ptrec;
@@ -270,4 +310,55 @@ extern "C" int ptrec_a2a_scatter_rows_peer(const float* src, int64_t src_row_str
   if (lanes <= 16) PTREC_SC(4, 16)
   PTREC_SC(4, 32)
 #undef PTREC_SC
+}
+
+extern "C" int ptrec_a2a_scatter_rows_peer_multi(const float* const* srcs, const int64_t* src_row_strides,
+                                                 const int32_t* dims, const int64_t* dst_cols, int32_t n_widths,
+                                                 const int32_t* ret_pos, int64_t B, int32_t F, float scale,
+                                                 float* const* peer_dst, int64_t dst_row_stride, int32_t C, int32_t G,
+                                                 int32_t my_rank, void* stream) {
+  PTREC_CHECK_ARG(srcs && src_row_strides && dims && dst_cols && ret_pos && peer_dst, PTREC_EINVAL,
+                  "a2a_scatter_rows_peer_multi: null pointer");
+  PTREC_CHECK_ARG(n_widths >= 1 && n_widths <= kMaxWidths, PTREC_EINVAL, "a2a_scatter_rows_peer_multi: 1..%d widths",
+                  kMaxWidths);
+  PTREC_CHECK_ARG(G >= 1 && G <= kMaxRanks && my_rank >= 0 && my_rank < G && C >= 1, PTREC_EINVAL,
+                  "a2a_scatter_rows_peer_multi: bad G=%d rank=%d C=%d", G, my_rank, C);
+  PeerWidths w;
+  w.n = n_widths;
+  int chunks = 0;
+  for (int k = 0; k < n_widths; ++k) {
+    PTREC_CHECK_ARG(srcs[k] && dims[k] >= 1 && dims[k] <= 128, PTREC_EINVAL, "a2a_scatter_rows_peer_multi: width %d", k);
+    const bool vec = (dims[k] & 3) == 0;
+    PTREC_CHECK_ARG(!vec || (((uintptr_t)srcs[k] & 15) == 0 && src_row_strides[k] % 4 == 0 && dst_cols[k] % 4 == 0 &&
+                             dst_row_stride % 4 == 0),
+                    PTREC_EALIGN, "a2a_scatter_rows_peer_multi: width %d misaligned", k);
+    w.src[k] = srcs[k];
+    w.stride[k] = src_row_strides[k];
+    w.dim[k] = dims[k];
+    w.col[k] = (int32_t)dst_cols[k];
+    w.chunk0[k] = chunks;
+    chunks += (dims[k] + 3) / 4;
+  }
+  w.chunk0[n_widths] = chunks;
+  for (int k = n_widths; k < kMaxWidths; ++k) { w.src[k] = nullptr; w.stride[k] = 0; w.dim[k] = 0; w.col[k] = 0; }
+  for (int k = n_widths + 1; k <= kMaxWidths; ++k) w.chunk0[k] = chunks;
+  PTREC_CHECK_ARG(chunks <= 32, PTREC_EUNSUPPORTED, "a2a_scatter_rows_peer_multi: slot wider than 128 floats");
+  if (B == 0) return PTREC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int FC = F * C;
+#define PTREC_SCM(P)                                                                                            \
+  {                                                                                                             \
+    const unsigned grid = (unsigned)ceil_div(B * F * P, 256);                                                   \
+    scatter_rows_peer_multi_kernel<P><<<grid, 256, 0, st>>>(w, ret_pos, B, F, scale, peer_dst, dst_row_stride,  \
+                                                            FC, my_rank);                                      \
+    PTREC_LAUNCH_CHECK("scatter_rows_peer_multi_kernel");                                                       \
+    return PTREC_OK;                                                                                            \
+  }
+  if (chunks <= 1) PTREC_SCM(1)
+  if (chunks <= 2) PTREC_SCM(2)
+  if (chunks <= 4) PTREC_SCM(4)
+  if (chunks <= 8) PTREC_SCM(8)
+  if (chunks <= 16) PTREC_SCM(16)
+  PTREC_SCM(32)
+#undef PTREC_SCM
 }

@@ -174,13 +174,13 @@ class _PeerLookup(torch.autograd.Function):
         if mod._dirty:  # the owners may still be consuming / resetting their buffers from an earlier backward
             mod.fence(dev)
         ret_pos = ops.a2a_pack_by_owner_peer(ids, F, B, G, C, mod.rank, pb["peer_ids"], mod.overflow_flag(dev))
+        gs = []
         for k, D in enumerate(mod.dims):
             g = grads[k]
             g = torch.zeros(B, F * D, device=dev) if g is None else g.reshape(B, F * D)
-            if not g.is_contiguous():
-                g = g.contiguous()
-            ops.a2a_scatter_rows_peer(g, ret_pos, B, F, D, mod.grad_scale, pb["peer_g"], S, mod.col_of[k], C, G,
-                                      mod.rank)
+            gs.append(g if g.is_contiguous() else g.contiguous())
+        ops.a2a_scatter_rows_peer_multi(gs, mod.dims, mod.col_of, ret_pos, B, F, mod.grad_scale, pb["peer_g"], S, C, G,
+                                        mod.rank)
         mod.fence(dev)  # every rank's pushes have landed in every owner's buffers
         recv_ids, recv_g = pb["recv_ids"], pb["recv_g"]
         srt = None

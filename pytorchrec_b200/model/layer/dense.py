@@ -55,6 +55,12 @@ def tc_linear_enabled() -> bool:
     return os.environ.get("PTREC_TC_LINEAR", "1") != "0"
 
 
+# Below this many multiply-accumulates (batch * in * out) the three launches of the K6 path (split x, split W, GEMM)
+# cost more than the fp32 cuBLAS sgemm they replace (measured: DIN's 8192 x ~100 x 200 layers), so small layers stay
+# on nn.Linear.  Tests set it to 0 to push small models through K6.
+TC_MIN_MACS = int(os.environ.get("PTREC_TC_LINEAR_MIN_MACS", str(1 << 28)))
+
+
 class Dense(Module):
     def __init__(self, input_units: int, output_units: int, activation: str, dropout: float):
         super().__init__()
@@ -65,7 +71,7 @@ class Dense(Module):
     def forward(self, x):
         w = self.linear.weight
         if x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and tc_linear_enabled() \
-                and not torch.is_autocast_enabled():
+                and not torch.is_autocast_enabled() and x.numel() * w.shape[0] >= TC_MIN_MACS:
             lead = x.shape[:-1]
             x2 = x.reshape(-1, x.shape[-1])
             if x2.stride(-1) != 1:

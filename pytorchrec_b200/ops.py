@@ -385,6 +385,22 @@ def a2a_scatter_rows_peer(src: torch.Tensor, ret_pos: torch.Tensor, B: int, F: i
                                                _stream(src.device)), "ptrec_a2a_scatter_rows_peer")
 
 
+def a2a_scatter_rows_peer_multi(srcs, dims, cols, ret_pos: torch.Tensor, B: int, F: int, scale: float,
+                                peer_dst: torch.Tensor, dst_row_stride: int, C: int, G: int, rank: int) -> None:
+    """Every width in one launch: srcs[k] [B, F*dims[k]] fp32 -> columns [cols[k], cols[k]+dims[k]) of the owners' slots."""
+    lib = _lib.load()
+    _require_cuda(ret_pos, peer_dst, *srcs)
+    n = len(srcs)
+    assert n == len(dims) == len(cols) and all(s.dtype == torch.float32 and s.stride(-1) == 1 for s in srcs)
+    a_src = (ctypes.c_void_p * n)(*[s.data_ptr() for s in srcs])
+    a_str = (ctypes.c_int64 * n)(*[s.stride(0) for s in srcs])
+    a_dim = (ctypes.c_int32 * n)(*dims)
+    a_col = (ctypes.c_int64 * n)(*cols)
+    _lib.check(lib.ptrec_a2a_scatter_rows_peer_multi(a_src, a_str, a_dim, a_col, n, _ptr(ret_pos), B, F, float(scale),
+                                                     _ptr(peer_dst), dst_row_stride, C, G, rank,
+                                                     _stream(ret_pos.device)), "ptrec_a2a_scatter_rows_peer_multi")
+
+
 # ----------------------------------------------------------------------------------------------
 # K6 fp32-faithful Linear on tcgen05 (bf16 x 3 split operands)
 # ----------------------------------------------------------------------------------------------

@@ -50,6 +50,16 @@ def test_reference_models_on_fused_tables_match_reference_run(golden_mf, case):
         np.testing.assert_allclose(v.cpu().numpy(), final[k].numpy(), rtol=1e-5, atol=1e-7, err_msg=k)
 
 
+@pytest.fixture(autouse=True)
+def _small_layers_on_k6():
+    """The test models are tiny; push their Dense layers through the tensor-core path (K6) anyway — the size
+    heuristic would leave them on cuBLAS (covered by test_dense_layer_size_heuristic)."""
+    from pytorchrec_b200.model.layer import dense
+    old, dense.TC_MIN_MACS = dense.TC_MIN_MACS, 0
+    yield
+    dense.TC_MIN_MACS = old
+
+
 def _ctr_setup(F=6, nd=3, D=16, rows=None, seed=11):
     rows = rows or [50 + 13 * f for f in range(F)]
     scols = [Col(rows[f], f"C{f}") for f in range(F)]
@@ -274,6 +284,22 @@ def test_peer_dispatch_kernels_equal_all_to_all_plan():
         for o in range(G):
             assert torch.equal(own_ids[o].cpu().view(F, G, C), want_ids[o])
             assert torch.equal(own_g[o].cpu(), want_g[o])
+        # every width in one launch (DeepFM: D and 1) leaves the same bytes as one launch per width
+        multi = [torch.zeros(G * F * C, S, device=DEV) for _ in range(G)]
+        single = [torch.zeros(G * F * C, S, device=DEV) for _ in range(G)]
+        pm = torch.tensor([t.data_ptr() for t in multi], dtype=torch.int64).to(DEV)
+        ps = torch.tensor([t.data_ptr() for t in single], dtype=torch.int64).to(DEV)
+        for r in range(G):
+            gen = torch.Generator().manual_seed(200 + r)
+            ids = torch.stack([torch.randint(-1, rows, (B,), generator=gen) for _ in range(F)]).to(DEV)
+            g0, g1 = torch.randn(B, F * D, generator=gen).to(DEV), torch.randn(B, F, generator=gen).to(DEV)
+            scratch = torch.tensor([t.data_ptr() for t in own_ids], dtype=torch.int64).to(DEV)
+            ret_pos = ops.a2a_pack_by_owner_peer(ids, F, B, G, C, r, scratch, torch.zeros(1, dtype=torch.int32, device=DEV))
+            ops.a2a_scatter_rows_peer_multi([g0, g1], [D, 1], [0, 16], ret_pos, B, F, 0.5, pm, S, C, G, r)
+            ops.a2a_scatter_rows_peer(g0, ret_pos, B, F, D, 0.5, ps, S, 0, C, G, r)
+            ops.a2a_scatter_rows_peer(g1, ret_pos, B, F, 1, 0.5, ps, S, 16, C, G, r)
+        for o in range(G):
+            assert torch.equal(multi[o], single[o])
 
 
 @pytest.mark.parametrize("G,D,stride_mult", [(2, 16, 1), (8, 16, 2), (4, 1, 1), (3, 64, 2)])
@@ -547,3 +573,29 @@ def test_staged_device_batches_train_exactly_like_host_ones():
         assert torch.equal(a.train_step(x)["loss"], b.train_step(y)["loss"])
     for (k, v), (_, w) in zip(a.state_dict().items(), b.state_dict().items()):
         assert torch.equal(v, w), k
+
+
+@pytest.mark.gpu
+def test_dense_layer_size_heuristic_and_parity_of_both_paths():
+    """Dense = nn.Linear -> ReLU on cuBLAS below TC_MIN_MACS, on K6 above; both give the same forward / gradients."""
+    from pytorchrec_b200 import _lib
+    from pytorchrec_b200.model.layer import dense
+    torch.manual_seed(3)
+    layer = dense.Dense(429, 400, "relu", 0.0).to(DEV)
+    x = torch.randn(2048, 429, device=DEV, requires_grad=True)
+    outs = []
+    for min_macs in (1 << 62, 0):          # cuBLAS, then K6
+        dense.TC_MIN_MACS = min_macs
+        before = _lib.load().ptrec_launch_count()
+        y = layer(x)
+        (y * torch.linspace(-1, 1, 400, device=DEV)).sum().backward()
+        used_k6 = _lib.load().ptrec_launch_count() > before
+        assert used_k6 == (min_macs == 0)
+        outs.append((y.detach().clone(), x.grad.clone(), layer.linear.weight.grad.clone(), layer.linear.bias.grad.clone()))
+        x.grad = None
+        layer.zero_grad()
+    for a, b in zip(*outs):
+        scale = b.abs().max().item()
+        assert (a - b).abs().max().item() <= 2e-6 * max(1.0, scale) * 30, (a - b).abs().max().item()
+    dense.TC_MIN_MACS = 1 << 28
+    assert 2048 * 429 * 400 >= dense.TC_MIN_MACS and 8192 * 96 * 200 < dense.TC_MIN_MACS
