@@ -76,6 +76,8 @@ class EmbeddingGroup:
         tables = self.table_set.refresh([w.data for w in self.weights()])
         # modules reading the same columns (e.g. FM's embedding and first-order tables) share one sort
         srt = shared.get("sort") if shared is not None else None
+        if srt is not None and shared.get("sort_event") is not None:
+            torch.cuda.current_stream(ids.device).wait_event(shared.pop("sort_event"))  # join the early sort
         if srt is None:
             srt = ops.sort_dedup(tables, layout, ids, lens, batch)
             if shared is not None:
@@ -100,11 +102,40 @@ class EmbeddingGroup:
         return grads
 
 
+_SIDE_STREAMS: Dict[torch.device, "torch.cuda.Stream"] = {}
+
+
+def _early_sort_enabled() -> bool:
+    import os
+    return os.environ.get("PTREC_EARLY_SORT", "1") != "0"
+
+
+def _start_early_sort(tables, layout, ids, lens, batch, shared) -> None:
+    """K2a depends on the ids only, so it is started during the FORWARD on a side stream and overlaps the dense
+    tower (its kernels are latency-bound and co-reside with the persistent GEMM CTAs); the backward joins it with
+    an event.  Under CUDA-graph capture the fork / join becomes part of the graph."""
+    dev = ids.device
+    main = torch.cuda.current_stream(dev)
+    side = _SIDE_STREAMS.get(dev)
+    if side is None:
+        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        srt = ops.sort_dedup(tables, layout, ids, lens, batch)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    for t in (srt.sorted_keys, srt.perm, srt.seg_start, srt.seg_meta, srt.n_seg):
+        t.record_stream(main)  # consumed on the main stream in backward
+    shared["sort"], shared["sort_event"] = srt, ev
+
+
 class _FusedLookup(torch.autograd.Function):
     @staticmethod
     def forward(ctx, group: EmbeddingGroup, layout, ids, lens, batch, shared, *weights):
         tables = group.table_set.refresh([w.detach() for w in weights])
         needs_scale = any(fd.pooling != 0 for fd in layout.host)
+        if (shared is not None and "sort" not in shared and any(ctx.needs_input_grad[6:]) and _early_sort_enabled()):
+            _start_early_sort(tables, layout, ids, lens, batch, shared)
         out, bag_scale = ops.gather_pool_fwd(tables, layout, ids, lens, batch, want_scale=needs_scale,
                                              err_flag=group.err_flag(ids.device))
         ctx.group, ctx.layout, ctx.batch, ctx.shared = group, layout, batch, shared
