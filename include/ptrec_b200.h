@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 13
+#define PTREC_ABI_VERSION 14
 
 /* error codes */
 #define PTREC_OK 0
@@ -291,6 +291,38 @@ int ptrec_dcn_cross_dgrad(const void* g_u, const void* weight_t, const void* g_o
 size_t ptrec_dcn_cross_wgrad_workspace_bytes(int64_t B, int32_t d);
 int ptrec_dcn_cross_wgrad(const void* g_u, const void* x_l, int64_t B, int32_t d, int64_t ld, float* grad_w,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K8 the FM head: first-order sum + second-order interaction + dense-feature linear term + bias in one pass, and
+ * (DeepFM) the tower input [v | x] written by the same pass; the Linear(H, 1) that closes the tower as a row dot.
+ * Written in the reference's idiom these are  biases + dot (SVDPP.py:65-66),  concat -> MLP -> Linear(., 1)
+ * (NCF.py:68-74);  here they replace ~20 latency-bound torch launches per step.
+ *   v [B, F*D] (row stride given), w1 [B, F] first-order values or NULL, x [B, nd] dense features or NULL,
+ *   wd [nd] or NULL, bias [1] or NULL;  logit [B];  deep_in [B, >= F*D+nd] or NULL.
+ * Backward: g [B] = d loss / d logit, g_deep_in = gradient of the tower input or NULL (added on the fly);
+ *   grad_v [B, F*D], grad_w1 [B, F] or NULL, grad_x [B, nd] or NULL, grad_wd [nd] / grad_bias [1] or NULL
+ *   (two-level fixed-order sums; workspace ptrec_fm_head_bwd_workspace_bytes).
+ * Needs D a power of two in [4, 128], F*D <= 2048, nd <= 128 (ptrec_fm_head_supported); callers fall back to K3 +
+ * library ops otherwise.
+ */
+int ptrec_fm_head_supported(int32_t F, int32_t D, int32_t nd);
+int ptrec_fm_head_fwd(const float* v, int64_t v_row_stride, const float* w1, int64_t w1_row_stride, const float* x,
+                      int64_t x_row_stride, const float* wd, const float* bias, int64_t B, int32_t F, int32_t D,
+                      int32_t nd, float* logit, float* deep_in, int64_t deep_in_row_stride, void* stream);
+size_t ptrec_fm_head_bwd_workspace_bytes(int32_t nd);
+int ptrec_fm_head_bwd(const float* v, int64_t v_row_stride, const float* x, int64_t x_row_stride, const float* wd,
+                      const float* g, const float* g_deep_in, int64_t g_deep_in_row_stride, int64_t B, int32_t F,
+                      int32_t D, int32_t nd, float* grad_v, int64_t grad_v_row_stride, float* grad_w1, float* grad_x,
+                      int64_t grad_x_row_stride, float* grad_wd, float* grad_bias, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* y[b] = h[b, :] . w  (h [B, H], w [H]);  backward: grad_h = g (x) w (or NULL), grad_w = h^T g (or NULL) */
+int ptrec_rowdot_supported(int32_t H);
+int ptrec_rowdot_fwd(const float* h, int64_t h_row_stride, const float* w, int64_t B, int32_t H, float* y,
+                     void* stream);
+size_t ptrec_rowdot_bwd_workspace_bytes(int32_t H);
+int ptrec_rowdot_bwd(const float* h, int64_t h_row_stride, const float* w, const float* g, int64_t B, int32_t H,
+                     float* grad_h, int64_t grad_h_row_stride, float* grad_w, void* workspace, size_t workspace_bytes,
+                     void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K7 dense-parameter update in one launch (the dense half of optimizer.step(), IModel.py:124 ->

@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libptrec_b200.so")
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 # enums (mirror include/ptrec_b200.h)
 F32, BF16 = 0, 1
@@ -91,6 +91,18 @@ PROTOTYPES = {
     "ptrec_embedding_bwd_segment_sum": (c_int, [c_int32, c_int32, _FD, _FD, c_int32, c_int64, c_void_p,
                                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                                 c_void_p, c_void_p, c_void_p]),
+    "ptrec_fm_head_supported": (c_int, [c_int32, c_int32, c_int32]),
+    "ptrec_fm_head_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                  c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
+    "ptrec_fm_head_bwd_workspace_bytes": (c_size_t, [c_int32]),
+    "ptrec_fm_head_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                  c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                  c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ptrec_rowdot_supported": (c_int, [c_int32]),
+    "ptrec_rowdot_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "ptrec_rowdot_bwd_workspace_bytes": (c_size_t, [c_int32]),
+    "ptrec_rowdot_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p,
+                                 c_void_p, c_size_t, c_void_p]),
     "ptrec_dense_optim_chunk": (c_int32, []),
     "ptrec_dense_optim_step": (c_int, [c_void_p, c_void_p, c_int32, c_int32, POINTER(OptimArgs), c_void_p]),
     "ptrec_tc_set_2sm": (None, [c_int32]),

@@ -417,7 +417,10 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
 // limits the 1-SM kernel runs into.  Both CTAs run a TMA producer (completing on the leader's barrier), only the
 // leader issues MMAs; tcgen05.commit multicasts the stage release / accumulator-ready arrivals to both CTAs, and both
 // CTAs' epilogue warps arrive remotely on the leader's accumulator-free barrier.
-constexpr size_t k2Smem = (size_t)192 * 1024 + 1024 /*align*/ + 2048 /*barriers + bias slice*/;
+#ifndef K2_STAGES
+#define K2_STAGES 4
+#endif
+constexpr size_t k2Smem = (size_t)(K2_STAGES == 3 ? 144 : 192) * 1024 + 1024 /*align*/ + 2048 /*barriers + bias slice*/;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;         // clears the CTA-pair bit of a shared::cluster address -> leader
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -458,7 +461,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // remote a
 template <bool MN_MAJOR, int BK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
 gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, LinEpi ep) {
-  constexpr int k2Stages = BK == 64 ? 2 : 4;
+  constexpr int k2Stages = BK == 64 ? 2 : K2_STAGES;
   constexpr uint32_t k2Tile = 128 * BK * 2;     // any plane tile: 128 rows (or 2 boxes of 64 mn) x BK bf16
   constexpr uint32_t k2StageBytes = 6 * k2Tile; // A0 A1 A2 B0 B1 B2 (B = this CTA's half)
   extern __shared__ unsigned char smem_raw[];

@@ -451,13 +451,8 @@ class ShardedDeepFM(DeepFM):
         from ..model.ctr import _dense_matrix
         v, w = self.sharded(data)                       # [B, F, D], [B, F, 1]
         x = _dense_matrix(self.dense_columns, data)
-        logit = w.sum(dim=(1, 2)) + self.fm2(v) + self.global_bias
-        if x is not None:
-            logit = logit + self.dense_linear(x).squeeze(-1)
-        flat = v.reshape(v.shape[0], -1)
-        deep_in = torch.cat([flat, x], dim=1) if x is not None else flat
-        logit = logit + self.deep_out(self.mlp(deep_in)).squeeze(-1)
-        return logit, self._target(data)
+        logit, deep_in = self._head(data, v, w, x, True)
+        return logit + self._deep_logit(deep_in), self._target(data)
 
     # ---- N4: checkpoints interchangeable with the unsharded model -------------------------------------------------
     _GROUP_NAMES = ("embeddings", "first_order")

@@ -51,21 +51,30 @@ class FM(IModel):
         self.global_bias = Parameter(torch.tensor(0.0))
         self.fm2 = FMSecondOrder()
 
-    def _fm_logit(self, data, v: Tensor, x: Optional[Tensor]) -> Tensor:
-        w = self.first_order(data)  # [B, F, 1]
-        logit = w.sum(dim=(1, 2)) + self.fm2(v) + self.global_bias
-        if x is not None:
-            logit = logit + self.dense_linear(x).squeeze(-1)
-        return logit
-
     def _target(self, data):
         target = self.label_column.get_feature_data(data)
         return target.float() if target is not None else None
 
+    def _head(self, data, v: Tensor, w: Tensor, x: Optional[Tensor], want_deep_in: bool):
+        """(FM logit, tower input or None): one fused pass (K8) where the shape allows, K3 + library ops otherwise."""
+        from .layer.interaction import fm_head
+        fused = fm_head(v, w, x, self.dense_linear.weight if x is not None else None, self.global_bias, want_deep_in)
+        if fused is not None:
+            return fused
+        logit = w.sum(dim=(1, 2)) + self.fm2(v) + self.global_bias
+        if x is not None:
+            logit = logit + self.dense_linear(x).squeeze(-1)
+        deep_in = None
+        if want_deep_in:
+            flat = v.reshape(v.shape[0], -1)
+            deep_in = torch.cat([flat, x], dim=1) if x is not None else flat
+        return logit, deep_in
+
     def forward(self, data: Dict[str, Tensor]):
         v = self.embeddings(data)  # [B, F, D]
         x = _dense_matrix(self.dense_columns, data)
-        return self._fm_logit(data, v, x), self._target(data)
+        logit, _ = self._head(data, v, self.first_order(data), x, False)
+        return logit, self._target(data)
 
 
 class DeepFM(FM):
@@ -81,13 +90,17 @@ class DeepFM(FM):
         self.mlp = MLP(input_units=in_units, hidden_units_list=self.layers, activation="relu", dropout=self.dropout)
         self.deep_out = Linear(self.layers[-1], 1, bias=False)
 
+    def _deep_logit(self, deep_in: Tensor) -> Tensor:
+        from .layer.interaction import row_dot
+        h = self.mlp(deep_in)
+        y = row_dot(h, self.deep_out.weight)
+        return y if y is not None else self.deep_out(h).squeeze(-1)
+
     def forward(self, data: Dict[str, Tensor]):
         v = self.embeddings(data)
         x = _dense_matrix(self.dense_columns, data)
-        flat = v.reshape(v.shape[0], -1)
-        deep_in = torch.cat([flat, x], dim=1) if x is not None else flat
-        logit = self._fm_logit(data, v, x) + self.deep_out(self.mlp(deep_in)).squeeze(-1)
-        return logit, self._target(data)
+        logit, deep_in = self._head(data, v, self.first_order(data), x, True)
+        return logit + self._deep_logit(deep_in), self._target(data)
 
 
 class DCN(IModel):

@@ -14,6 +14,85 @@ class FMSecondOrder(nn.Module):
         return ops.fm2(v)
 
 
+class _FMHead(torch.autograd.Function):
+    """K8: first-order sum + FM second order + dense linear term + bias -> logit, and the tower input [v | x]."""
+
+    @staticmethod
+    def forward(ctx, v2d, w1, x, wd, bias, F, D, want_deep_in):
+        logit, deep_in = ops.fm_head_fwd(v2d, w1, x, wd, bias, F, D, want_deep_in)
+        ctx.save_for_backward(v2d, x, wd)
+        ctx.meta = (F, D)
+        if deep_in is None:
+            deep_in = v2d.new_empty(0)
+            ctx.mark_non_differentiable(deep_in)
+        return logit, deep_in
+
+    @staticmethod
+    def backward(ctx, g_logit, g_deep_in):
+        v2d, x, wd = ctx.saved_tensors
+        F, D = ctx.meta
+        need = ctx.needs_input_grad
+        if g_deep_in is not None and g_deep_in.numel() == 0:
+            g_deep_in = None
+        if g_deep_in is not None and not (g_deep_in.stride(1) == 1 and g_deep_in.stride(0) % 4 == 0
+                                          and g_deep_in.data_ptr() % 16 == 0):
+            g_deep_in = g_deep_in.contiguous()
+            if g_deep_in.stride(0) % 4 != 0:  # odd width: re-pitch
+                buf = g_deep_in.new_empty(g_deep_in.shape[0], (g_deep_in.shape[1] + 3) // 4 * 4)
+                buf[:, :g_deep_in.shape[1]] = g_deep_in
+                g_deep_in = buf[:, :g_deep_in.shape[1]]
+        gv, gw1, gwd, gb = ops.fm_head_bwd(v2d, x, wd, g_logit.contiguous(), g_deep_in, F, D, want_w1=need[1],
+                                           want_wd=need[3] and wd is not None, want_bias=need[4])
+        return gv if need[0] else None, gw1, None, gwd, gb, None, None, None
+
+
+class _RowDot(torch.autograd.Function):
+    """K8: y[b] = h[b, :] . w — the Linear(H, 1, bias=False) closing a tower."""
+
+    @staticmethod
+    def forward(ctx, h, w):
+        ctx.save_for_backward(h, w)
+        return ops.rowdot_fwd(h, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w = ctx.saved_tensors
+        gh, gw = ops.rowdot_bwd(h, w, g.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return gh, gw
+
+
+def fm_head_enabled() -> bool:
+    import os
+    return os.environ.get("PTREC_FM_HEAD", "1") != "0"
+
+
+def fm_head(v: Tensor, w1, x, wd, bias, want_deep_in: bool):
+    """``v [B, F, D]``, ``w1 [B, F, 1]`` or None, ``x [B, nd]`` or None, ``wd`` = Linear(nd, 1).weight or None,
+    ``bias`` scalar parameter or None -> ``(logit [B], deep_in [B, F*D + nd] or None)``; None if K8 does not cover
+    the shape (the caller composes K3 + library ops instead)."""
+    B, F, D = v.shape
+    nd = 0 if x is None else x.shape[1]
+    if not (v.is_cuda and v.dtype == torch.float32 and fm_head_enabled() and ops.fm_head_supported(F, D, nd)):
+        return None
+    v2d = v.reshape(B, F * D)
+    if not (v2d.stride(1) == 1 and v2d.stride(0) % 4 == 0 and v2d.data_ptr() % 16 == 0):
+        v2d = v2d.contiguous()
+    logit, deep_in = _FMHead.apply(v2d, w1.reshape(B, F).contiguous() if w1 is not None else None,
+                                   x.contiguous() if x is not None else None,
+                                   wd.reshape(-1) if (wd is not None and x is not None) else None,
+                                   bias.reshape(1) if bias is not None else None, F, D, want_deep_in)
+    return logit, (deep_in if want_deep_in else None)
+
+
+def row_dot(h: Tensor, weight: Tensor):
+    """``Linear(H, 1, bias=False)(h).squeeze(-1)`` as one pass; None if the shape is not covered."""
+    if not (h.is_cuda and h.dtype == torch.float32 and h.dim() == 2 and fm_head_enabled()
+            and ops.rowdot_supported(h.shape[1]) and h.stride(1) == 1 and h.stride(0) % 4 == 0
+            and h.data_ptr() % 16 == 0):
+        return None
+    return _RowDot.apply(h, weight.reshape(-1))
+
+
 class CrossNet(nn.Module):
     """DCN-v2 cross network: ``x_{l+1} = x0 * (x_l W_l^T + b_l) + x_l`` for ``l < num_layers``.
     Parameters are ``layers.{l}.weight [d, d]`` / ``layers.{l}.bias [d]`` (``nn.Linear`` modules, so the

@@ -334,6 +334,80 @@ def fm2(v: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 # C1 all-to-all pack / unpack
 # ----------------------------------------------------------------------------------------------
+# ----------------------------------------------------------------------------------------------
+# K8 FM head + row dot
+# ----------------------------------------------------------------------------------------------
+def fm_head_supported(F: int, D: int, nd: int) -> bool:
+    return bool(_lib.load().ptrec_fm_head_supported(F, D, nd))
+
+
+def fm_head_fwd(v: torch.Tensor, w1: Optional[torch.Tensor], x: Optional[torch.Tensor], wd: Optional[torch.Tensor],
+                bias: Optional[torch.Tensor], F: int, D: int, want_deep_in: bool):
+    """v [B, F*D] (row stride % 4 == 0), w1 [B, F], x [B, nd], wd [nd], bias [1] -> (logit [B], deep_in or None);
+    deep_in is a [B, F*D+nd] view of a buffer whose pitch is rounded up to 4 floats."""
+    lib = _lib.load()
+    _require_cuda(v, w1, x, wd, bias)
+    B = v.shape[0]
+    nd = 0 if x is None else x.shape[1]
+    dev = v.device
+    logit = torch.empty(B, dtype=torch.float32, device=dev)
+    deep_buf = None
+    if want_deep_in:
+        pitch = (F * D + nd + 3) // 4 * 4
+        deep_buf = torch.empty(B, pitch, dtype=torch.float32, device=dev)
+    _lib.check(lib.ptrec_fm_head_fwd(_ptr(v), v.stride(0), _ptr(w1), w1.stride(0) if w1 is not None else 0, _ptr(x),
+                                     x.stride(0) if x is not None else 0, _ptr(wd), _ptr(bias), B, F, D, nd,
+                                     _ptr(logit), _ptr(deep_buf), deep_buf.stride(0) if deep_buf is not None else 0,
+                                     _stream(dev)), "ptrec_fm_head_fwd")
+    return logit, (deep_buf[:, :F * D + nd] if deep_buf is not None else None)
+
+
+def fm_head_bwd(v: torch.Tensor, x: Optional[torch.Tensor], wd: Optional[torch.Tensor], g: torch.Tensor,
+                g_deep_in: Optional[torch.Tensor], F: int, D: int, want_w1: bool, want_wd: bool, want_bias: bool):
+    """-> (grad_v [B, F*D], grad_w1 [B, F] or None, grad_wd [nd] or None, grad_bias [1] or None)"""
+    lib = _lib.load()
+    _require_cuda(v, x, wd, g, g_deep_in)
+    B = v.shape[0]
+    nd = 0 if x is None else x.shape[1]
+    dev = v.device
+    gv = torch.empty(B, F * D, dtype=torch.float32, device=dev)
+    gw1 = torch.empty(B, F, dtype=torch.float32, device=dev) if want_w1 else None
+    gwd = torch.empty(nd, dtype=torch.float32, device=dev) if (want_wd and nd) else None
+    gb = torch.empty(1, dtype=torch.float32, device=dev) if want_bias else None
+    ws = _workspace("fm_head", lib.ptrec_fm_head_bwd_workspace_bytes(nd), dev)
+    _lib.check(lib.ptrec_fm_head_bwd(_ptr(v), v.stride(0), _ptr(x), x.stride(0) if x is not None else 0, _ptr(wd),
+                                     _ptr(g), _ptr(g_deep_in), g_deep_in.stride(0) if g_deep_in is not None else 0, B,
+                                     F, D, nd, _ptr(gv), gv.stride(0), _ptr(gw1), None, 0, _ptr(gwd), _ptr(gb),
+                                     _ptr(ws), ws.numel(), _stream(dev)), "ptrec_fm_head_bwd")
+    return gv, gw1, gwd, gb
+
+
+def rowdot_supported(H: int) -> bool:
+    return bool(_lib.load().ptrec_rowdot_supported(H))
+
+
+def rowdot_fwd(h: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _require_cuda(h, w)
+    B, H = h.shape
+    y = torch.empty(B, dtype=torch.float32, device=h.device)
+    _lib.check(lib.ptrec_rowdot_fwd(_ptr(h), h.stride(0), _ptr(w), B, H, _ptr(y), _stream(h.device)), "ptrec_rowdot_fwd")
+    return y
+
+
+def rowdot_bwd(h: torch.Tensor, w: torch.Tensor, g: torch.Tensor, want_h: bool, want_w: bool):
+    lib = _lib.load()
+    _require_cuda(h, w, g)
+    B, H = h.shape
+    dev = h.device
+    gh = torch.empty(B, H, dtype=torch.float32, device=dev) if want_h else None
+    gw = torch.empty(H, dtype=torch.float32, device=dev) if want_w else None
+    ws = _workspace("rowdot", lib.ptrec_rowdot_bwd_workspace_bytes(H), dev)
+    _lib.check(lib.ptrec_rowdot_bwd(_ptr(h), h.stride(0), _ptr(w), _ptr(g), B, H, _ptr(gh), gh.stride(0) if want_h else 0,
+                                    _ptr(gw), _ptr(ws), ws.numel(), _stream(dev)), "ptrec_rowdot_bwd")
+    return gh, gw
+
+
 def a2a_pack_by_owner(ids: torch.Tensor, F: int, B: int, G: int, C: int, overflow: torch.Tensor):
     """ids [F, B] int64 -> (send_ids [G, F, C] int64 with -1 padding, ret_pos [F, B] int32)."""
     lib = _lib.load()

@@ -627,3 +627,63 @@ def test_tc_gemm_split3_tn_weight_gradient_from_row_major_planes(B, N, K, tc_mod
         dw = ops.tc_gemm_split3_tn(pg, N, px, K, splits=splits)
         assert dw.shape == (N, K)
         assert ((dw.double() - ref).abs() / scale).max().item() <= tol, (splits, fp32_err)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K8 FM head + row dot
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,F,D,nd", [(257, 26, 16, 13), (64, 3, 4, 0), (1000, 26, 64, 13), (33, 5, 8, 1)])
+def test_fm_head_forward_backward_match_torch(B, F, D, nd):
+    from pytorchrec_b200.model.layer.interaction import fm_head
+    gen = torch.Generator().manual_seed(B + F)
+    v = torch.randn(B, F, D, generator=gen).to(DEV).requires_grad_(True)
+    w1 = torch.randn(B, F, 1, generator=gen).to(DEV).requires_grad_(True)
+    x = torch.randn(B, nd, generator=gen).to(DEV) if nd else None
+    wd = torch.randn(1, nd, generator=gen).to(DEV).requires_grad_(True) if nd else None
+    bias = torch.randn((), generator=gen).to(DEV).requires_grad_(True)
+    gl = torch.randn(B, generator=gen).to(DEV)
+    gd = torch.randn(B, F * D + nd, generator=gen).to(DEV)
+
+    def ref():
+        s = v.sum(1)
+        logit = w1.sum(dim=(1, 2)) + 0.5 * (s * s - (v * v).sum(1)).sum(1) + bias
+        if nd:
+            logit = logit + (x @ wd.t()).squeeze(-1)
+        flat = v.reshape(B, -1)
+        return logit, (torch.cat([flat, x], 1) if nd else flat)
+
+    outs = []
+    for fn in (ref, lambda: fm_head(v, w1, x, wd, bias, True)):
+        logit, deep_in = fn()
+        torch.autograd.backward([logit, deep_in], [gl, gd])
+        outs.append([logit.detach(), deep_in.detach(), v.grad, w1.grad, bias.grad] + ([wd.grad] if nd else []))
+        v.grad = w1.grad = bias.grad = None
+        if nd:
+            wd.grad = None
+    names = ["logit", "deep_in", "gv", "gw1", "gbias", "gwd"]
+    for n, a, b in zip(names, outs[0], outs[1]):
+        assert a.shape == b.shape, n
+        scale = max(1.0, a.abs().max().item())
+        tol = (2e-5 if n in ("gbias", "gwd") else 3e-6) * scale * (D if n == "logit" else 1)
+        assert (a - b).abs().max().item() <= tol, (n, (a - b).abs().max().item(), tol)
+    assert torch.equal(outs[0][1], outs[1][1])  # the tower input is a copy: bit-exact
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H", [(1000, 400), (64, 1024), (257, 32)])
+def test_row_dot_matches_linear(B, H):
+    from pytorchrec_b200.model.layer.interaction import row_dot
+    gen = torch.Generator().manual_seed(H)
+    h = torch.randn(B, H, generator=gen).to(DEV).requires_grad_(True)
+    w = torch.randn(1, H, generator=gen).to(DEV).requires_grad_(True)
+    g = torch.randn(B, generator=gen).to(DEV)
+    res = []
+    for fn in (lambda: torch.nn.functional.linear(h, w).squeeze(-1), lambda: row_dot(h, w)):
+        y = fn()
+        y.backward(g)
+        res.append((y.detach(), h.grad, w.grad))
+        h.grad = w.grad = None
+    for a, b in zip(*res):
+        assert a.shape == b.shape
+        assert (a - b).abs().max().item() <= 2e-5 * max(1.0, a.abs().max().item())
