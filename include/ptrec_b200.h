@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 14
+#define PTREC_ABI_VERSION 15
 
 /* error codes */
 #define PTREC_OK 0
@@ -298,7 +298,8 @@ int ptrec_dcn_cross_wgrad(const void* g_u, const void* x_l, int64_t B, int32_t d
  * Written in the reference's idiom these are  biases + dot (SVDPP.py:65-66),  concat -> MLP -> Linear(., 1)
  * (NCF.py:68-74);  here they replace ~20 latency-bound torch launches per step.
  *   v [B, F*D] (row stride given), w1 [B, F] first-order values or NULL, x [B, nd] dense features or NULL,
- *   wd [nd] or NULL, bias [1] or NULL;  logit [B];  deep_in [B, >= F*D+nd] or NULL.
+ *   wd [nd] or NULL, bias [1] or NULL;  logit [B];  deep_in [B, >= F*D+nd] or NULL;  deep_in_planes (or NULL): the
+ *   tower input again as the exact bf16 planes [3][B][ld] K6 consumes (ld a multiple of 8 >= F*D+nd, pad = 0).
  * Backward: g [B] = d loss / d logit, g_deep_in = gradient of the tower input or NULL (added on the fly);
  *   grad_v [B, F*D], grad_w1 [B, F] or NULL, grad_x [B, nd] or NULL, grad_wd [nd] / grad_bias [1] or NULL
  *   (two-level fixed-order sums; workspace ptrec_fm_head_bwd_workspace_bytes).
@@ -308,7 +309,8 @@ int ptrec_dcn_cross_wgrad(const void* g_u, const void* x_l, int64_t B, int32_t d
 int ptrec_fm_head_supported(int32_t F, int32_t D, int32_t nd);
 int ptrec_fm_head_fwd(const float* v, int64_t v_row_stride, const float* w1, int64_t w1_row_stride, const float* x,
                       int64_t x_row_stride, const float* wd, const float* bias, int64_t B, int32_t F, int32_t D,
-                      int32_t nd, float* logit, float* deep_in, int64_t deep_in_row_stride, void* stream);
+                      int32_t nd, float* logit, float* deep_in, int64_t deep_in_row_stride, void* deep_in_planes,
+                      int64_t deep_in_planes_ld, void* stream);
 size_t ptrec_fm_head_bwd_workspace_bytes(int32_t nd);
 int ptrec_fm_head_bwd(const float* v, int64_t v_row_stride, const float* x, int64_t x_row_stride, const float* wd,
                       const float* g, const float* g_deep_in, int64_t g_deep_in_row_stride, int64_t B, int32_t F,
@@ -360,6 +362,8 @@ int ptrec_dense_optim_step(const ptrec_dense_tensor* tensors, const int32_t* chu
  *
  * ptrec_tc_gemm_split3: out[M, N] (pitch ldo, multiple of 4, >= N rounded up to 4) =
  *   A[M, K] B[N, K]^T (+ bias[N]) (ReLU)   with A, B given as planes [3][M][lda], [3][N][ldb].
+ *   out_planes (or NULL): the result written a second time as bf16 planes [3][M][out_planes_ld] — the next
+ *   layer's A operand, so that layer needs no split pass (out_planes_ld a multiple of 8 >= N; splits == 1 only).
  *   splits > 1 cuts K into ranges accumulated through fp32 partials in the workspace
  *   (ptrec_tc_gemm_split3_workspace_bytes) and summed in a fixed order; no bias / ReLU then.
  *   y  = x W^T + b : A = planes(x) [B, K],      B = planes(W) [N, K]
@@ -383,8 +387,8 @@ int ptrec_tc_split3(const float* src, int64_t ld, int64_t R, int64_t C, const fl
 size_t ptrec_tc_gemm_split3_workspace_bytes(int64_t M, int64_t ldo, int32_t splits);
 int32_t ptrec_tc_gemm_split3_default_splits(int64_t M, int64_t N, int64_t K);
 int ptrec_tc_gemm_split3(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N, int64_t ldb,
-                         int64_t K, const float* bias, int32_t relu, float* out, int64_t ldo, int32_t splits,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         int64_t K, const float* bias, int32_t relu, float* out, int64_t ldo, void* out_planes,
+                         int64_t out_planes_ld, int32_t splits, void* workspace, size_t workspace_bytes, void* stream);
 int ptrec_tc_gemm_split3_tn(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N, int64_t ldb,
                             int64_t K, float* out, int64_t ldo, int32_t splits, void* workspace,
                             size_t workspace_bytes, void* stream);

@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libptrec_b200.so")
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 # enums (mirror include/ptrec_b200.h)
 F32, BF16 = 0, 1
@@ -93,7 +93,8 @@ PROTOTYPES = {
                                                 c_void_p, c_void_p, c_void_p]),
     "ptrec_fm_head_supported": (c_int, [c_int32, c_int32, c_int32]),
     "ptrec_fm_head_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
-                                  c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
+                                  c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                  c_void_p]),
     "ptrec_fm_head_bwd_workspace_bytes": (c_size_t, [c_int32]),
     "ptrec_fm_head_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
@@ -114,7 +115,8 @@ PROTOTYPES = {
     "ptrec_tc_gemm_split3_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "ptrec_tc_gemm_split3_default_splits": (c_int32, [c_int64, c_int64, c_int64]),
     "ptrec_tc_gemm_split3": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p,
-                                     c_int32, c_void_p, c_int64, c_int32, c_void_p, c_size_t, c_void_p]),
+                                     c_int32, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_size_t,
+                                     c_void_p]),
     "ptrec_tc_gemm_split3_tn": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                         c_int64, c_int32, c_void_p, c_size_t, c_void_p]),
     "ptrec_a2a_pack_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),

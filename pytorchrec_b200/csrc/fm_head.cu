@@ -8,6 +8,7 @@
 // NCF.py:68-74: concat -> MLP -> Linear(., 1)) — ~20 latency-bound torch launches per step at cfg2.
 // Bound: HBM (each pass streams [B, F*D] once or twice).  Reductions over the batch are two-level with a fixed order.
 #include "common.cuh"
+#include "split3.cuh"
 
 namespace ptrec {
 
@@ -31,12 +32,14 @@ __global__ void __launch_bounds__(kHdWarps * 32)
 fm_head_fwd_kernel(const float* __restrict__ v, int64_t vs, const float* __restrict__ w1, int64_t w1s,
                    const float* __restrict__ x, int64_t xs, const float* __restrict__ wd,
                    const float* __restrict__ bias, int64_t B, int F, int n_chunks, int lanes_per_row, int nd,
-                   float* __restrict__ logit, float* __restrict__ deep_in, int64_t ds) {
+                   float* __restrict__ logit, float* __restrict__ deep_in, int64_t ds,
+                   __nv_bfloat16* __restrict__ planes, int64_t pl_ld, int64_t pl_plane) {
   const int64_t b = (int64_t)blockIdx.x * kHdWarps + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31;
   const float* row = v + b * vs;
   float* drow = deep_in ? deep_in + b * ds : nullptr;
+  __nv_bfloat16* prow = planes ? planes + b * pl_ld : nullptr;
   float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
   float Q = 0.f;
   for (int q0 = lane; q0 < n_chunks; q0 += 32 * 4) {
@@ -52,6 +55,10 @@ fm_head_fwd_kernel(const float* __restrict__ v, int64_t vs, const float* __restr
       S = hd_add(S, t[u]);
       Q += t[u].x * t[u].x + t[u].y * t[u].y + t[u].z * t[u].z + t[u].w * t[u].w;
       if (drow && q < n_chunks) st_f4(drow + q * 4, t[u]);
+      if (prow && q < n_chunks) {
+        const float tv[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+        split3_store4(tv, prow + q * 4, pl_plane);
+      }
     }
   }
   S = hd_reduce_S(S, lanes_per_row);
@@ -66,12 +73,25 @@ fm_head_fwd_kernel(const float* __restrict__ v, int64_t vs, const float* __restr
       if (drow) drow[n_chunks * 4 + j] = xv;
     }
   }
+  if (prow) {  // dense columns and the zero pad up to the plane pitch
+    for (int j = lane; n_chunks * 4 + j < pl_ld; j += 32) {
+      const float xv = (x != nullptr && j < nd) ? x[b * xs + j] : 0.f;
+      __nv_bfloat16 p0, p1, p2;
+      split3(xv, p0, p1, p2);
+      __nv_bfloat16* o = prow + n_chunks * 4 + j;
+      o[0] = p0;
+      o[pl_plane] = p1;
+      o[2 * pl_plane] = p2;
+    }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) logit[b] = acc + (bias ? bias[0] : 0.f);
 }
 
 // grid-stride over samples; per-CTA partial sums of g*x[.,j] (j < nd) and of g (column nd) -> part[blockIdx][nd+1]
+// MAXC = float4 chunks of a row cached per lane (n_chunks <= 32*MAXC): v and the tower gradient are requested together
+template <int MAXC>
 __global__ void __launch_bounds__(kHdWarps * 32)
 fm_head_bwd_kernel(const float* __restrict__ v, int64_t vs, const float* __restrict__ x, int64_t xs,
                    const float* __restrict__ wd, const float* __restrict__ g, const float* __restrict__ gdi,
@@ -84,26 +104,35 @@ fm_head_bwd_kernel(const float* __restrict__ v, int64_t vs, const float* __restr
   float pb = 0.f;
   for (int64_t b = (int64_t)blockIdx.x * kHdWarps + warp; b < B; b += (int64_t)gridDim.x * kHdWarps) {
     const float* row = v + b * vs;
-    float4 c[kHdMaxChunks];
+    const float* irow = gdi ? gdi + b * gds : nullptr;
+    float4 c[MAXC], d[MAXC];
+#pragma unroll
+    for (int u = 0; u < MAXC; ++u) {
+      const int q = lane + u * 32;
+      const bool in = q < n_chunks;
+      c[u] = in ? ldg_stream_f4(row + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      d[u] = (in && irow) ? ldg_stream_f4(irow + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float gb = g[b];
+    float xv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (x != nullptr) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = lane + u * 32;
+        if (j < nd) xv[u] = x[b * xs + j];
+      }
+    }
     float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int u = 0; u < kHdMaxChunks; ++u) {
-      const int q = lane + u * 32;
-      c[u] = q < n_chunks ? ldg_stream_f4(row + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < kHdMaxChunks; ++u) S = hd_add(S, c[u]);
+    for (int u = 0; u < MAXC; ++u) S = hd_add(S, c[u]);
     S = hd_reduce_S(S, lanes_per_row);
-    const float gb = g[b];
     float* orow = gv + b * gvs;
-    const float* irow = gdi ? gdi + b * gds : nullptr;
 #pragma unroll
-    for (int u = 0; u < kHdMaxChunks; ++u) {
+    for (int u = 0; u < MAXC; ++u) {
       const int q = lane + u * 32;
       if (q < n_chunks) {
-        float4 o = make_float4(gb * (S.x - c[u].x), gb * (S.y - c[u].y), gb * (S.z - c[u].z), gb * (S.w - c[u].w));
-        if (irow) o = hd_add(o, ldg_stream_f4(irow + q * 4));
-        st_f4(orow + q * 4, o);
+        st_f4(orow + q * 4, make_float4(gb * (S.x - c[u].x) + d[u].x, gb * (S.y - c[u].y) + d[u].y,
+                                        gb * (S.z - c[u].z) + d[u].z, gb * (S.w - c[u].w) + d[u].w));
       }
     }
     if (gw1 != nullptr)
@@ -113,7 +142,7 @@ fm_head_bwd_kernel(const float* __restrict__ v, int64_t vs, const float* __restr
       for (int u = 0; u < 4; ++u) {
         const int j = lane + u * 32;
         if (j < nd) {
-          pw[u] += gb * x[b * xs + j];
+          pw[u] += gb * xv[u];
           if (gx != nullptr) gx[b * gxs + j] = (wd ? gb * wd[j] : 0.f) + (irow ? irow[n_chunks * 4 + j] : 0.f);
         }
       }
@@ -136,22 +165,22 @@ fm_head_bwd_kernel(const float* __restrict__ v, int64_t vs, const float* __restr
   }
 }
 
-// out[c] = sum_t part[t][c], c < C: warps stride over the partials, then a fixed-order sum over the 8 warps
-__global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restrict__ part, int tiles, int C,
-                                                          float* __restrict__ out0, int C0,
-                                                          float* __restrict__ out1) {
+// out[c] = sum_t part[t][c], c < C: 32 warps stride over the partials, then a fixed-order sum over the warps
+__global__ void __launch_bounds__(1024) head_reduce_kernel(const float* __restrict__ part, int tiles, int C,
+                                                           float* __restrict__ out0, int C0,
+                                                           float* __restrict__ out1) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int sub = threadIdx.x >> 5;
-  __shared__ float s[8][33];
+  __shared__ float s[32][33];
   float acc = 0.f;
   if (c < C)
-    for (int t = sub; t < tiles; t += 8) acc += part[(int64_t)t * C + c];
+    for (int t = sub; t < tiles; t += 32) acc += part[(int64_t)t * C + c];
   s[sub][threadIdx.x & 31] = acc;
   __syncthreads();
   if (sub == 0 && c < C) {
     float r = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r += s[k][threadIdx.x];
+    for (int k = 0; k < 32; ++k) r += s[k][threadIdx.x];
     if (c < C0) {
       if (out0) out0[c] = r;
     } else if (out1) {
@@ -183,17 +212,17 @@ rowdot_fwd_kernel(const float* __restrict__ h, int64_t hs, const float* __restri
   if (lane == 0) y[b] = acc;
 }
 
-// g_h[b,k] = g[b]*w[k];  per-CTA partials of g_w[k] = sum_b g[b]*h[b,k]  (H % 4 == 0, H <= 1024, aligned)
+// g_h[b,k] = g[b]*w[k];  per-CTA partials of g_w[k] = sum_b g[b]*h[b,k]  (H % 4 == 0, H <= 128*MAXC, aligned)
+template <int MAXC>
 __global__ void __launch_bounds__(kHdWarps * 32)
 rowdot_bwd_kernel(const float* __restrict__ h, int64_t hs, const float* __restrict__ w, const float* __restrict__ g,
                   int64_t B, int H, float* __restrict__ gh, int64_t ghs, float* __restrict__ part) {
   extern __shared__ float s_acc[];  // [kHdWarps][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = H / 4;
-  float4 a[kHdMaxH / 128];
-  float4 wv[kHdMaxH / 128];
+  float4 a[MAXC], wv[MAXC];
 #pragma unroll
-  for (int u = 0; u < kHdMaxH / 128; ++u) {
+  for (int u = 0; u < MAXC; ++u) {
     a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int q = lane + u * 32;
     wv[u] = q < nq ? *reinterpret_cast<const float4*>(w + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -202,19 +231,22 @@ rowdot_bwd_kernel(const float* __restrict__ h, int64_t hs, const float* __restri
     const float gb = g[b];
     const float* row = h + b * hs;
     float* orow = gh ? gh + b * ghs : nullptr;
+    float4 t[MAXC];
 #pragma unroll
-    for (int u = 0; u < kHdMaxH / 128; ++u) {
+    for (int u = 0; u < MAXC; ++u) {
       const int q = lane + u * 32;
-      if (q < nq) {
-        const float4 t = ldg_stream_f4(row + q * 4);
-        a[u].x += gb * t.x; a[u].y += gb * t.y; a[u].z += gb * t.z; a[u].w += gb * t.w;
-        if (orow) st_f4(orow + q * 4, make_float4(gb * wv[u].x, gb * wv[u].y, gb * wv[u].z, gb * wv[u].w));
-      }
+      t[u] = q < nq ? ldg_stream_f4(row + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < MAXC; ++u) {
+      const int q = lane + u * 32;
+      a[u].x += gb * t[u].x; a[u].y += gb * t[u].y; a[u].z += gb * t[u].z; a[u].w += gb * t[u].w;
+      if (orow && q < nq) st_f4(orow + q * 4, make_float4(gb * wv[u].x, gb * wv[u].y, gb * wv[u].z, gb * wv[u].w));
     }
   }
   if (part == nullptr) return;
 #pragma unroll
-  for (int u = 0; u < kHdMaxH / 128; ++u) {
+  for (int u = 0; u < MAXC; ++u) {
     const int q = lane + u * 32;
     if (q < nq) *reinterpret_cast<float4*>(&s_acc[(size_t)warp * H + q * 4]) = a[u];
   }
@@ -231,7 +263,7 @@ static int head_grid() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return sms * 4;
+  return sms * 6;
 }
 
 }  // namespace ptrec
@@ -249,7 +281,8 @@ extern "C" int ptrec_fm_head_supported(int32_t F, int32_t D, int32_t nd) {
 extern "C" int ptrec_fm_head_fwd(const float* v, int64_t v_row_stride, const float* w1, int64_t w1_row_stride,
                                  const float* x, int64_t x_row_stride, const float* wd, const float* bias, int64_t B,
                                  int32_t F, int32_t D, int32_t nd, float* logit, float* deep_in,
-                                 int64_t deep_in_row_stride, void* stream) {
+                                 int64_t deep_in_row_stride, void* deep_in_planes, int64_t deep_in_planes_ld,
+                                 void* stream) {
   PTREC_CHECK_ARG(v && logit && B >= 0 && F >= 1, PTREC_EINVAL, "fm_head_fwd: bad argument");
   PTREC_CHECK_ARG(ptrec_fm_head_supported(F, D, nd), PTREC_EUNSUPPORTED,
                   "fm_head_fwd: needs D a power of two in [4, 128], F*D <= 2048, <= %d dense features", kHdMaxDense);
@@ -259,10 +292,14 @@ extern "C" int ptrec_fm_head_fwd(const float* v, int64_t v_row_stride, const flo
                                deep_in_row_stride >= (int64_t)F * D + nd),
                   PTREC_EALIGN, "fm_head_fwd: deep_in misaligned");
   PTREC_CHECK_ARG(nd == 0 || x != nullptr, PTREC_EINVAL, "fm_head_fwd: dense features without x");
+  PTREC_CHECK_ARG(!deep_in_planes || (aligned16(deep_in_planes) && deep_in_planes_ld % 8 == 0 &&
+                                      deep_in_planes_ld >= (int64_t)F * D + nd),
+                  PTREC_EALIGN, "fm_head_fwd: plane pitch must be a multiple of 8 >= F*D + nd");
   if (B == 0) return PTREC_OK;
   fm_head_fwd_kernel<<<(unsigned)ceil_div(B, kHdWarps), kHdWarps * 32, 0, (cudaStream_t)stream>>>(
       v, v_row_stride, w1, w1_row_stride, nd ? x : nullptr, x_row_stride, wd, bias, B, F, F * D / 4, D / 4, nd, logit,
-      deep_in, deep_in_row_stride);
+      deep_in, deep_in_row_stride, reinterpret_cast<__nv_bfloat16*>(deep_in_planes), deep_in_planes_ld,
+      B * deep_in_planes_ld);
   PTREC_LAUNCH_CHECK("fm_head_fwd_kernel");
   return PTREC_OK;
 }
@@ -288,12 +325,18 @@ extern "C" int ptrec_fm_head_bwd(const float* v, int64_t v_row_stride, const flo
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = (int)std::min<int64_t>(head_grid(), ceil_div(B, kHdWarps));
   float* part = need_part ? reinterpret_cast<float*>(workspace) : nullptr;
-  fm_head_bwd_kernel<<<grid, kHdWarps * 32, 0, st>>>(v, v_row_stride, nd ? x : nullptr, x_row_stride, wd, g, g_deep_in,
-                                                     g_deep_in_row_stride, B, F, F * D / 4, D / 4, nd, grad_v,
-                                                     grad_v_row_stride, grad_w1, grad_x, grad_x_row_stride, part);
+#define PTREC_HEAD_BWD(MC)                                                                                          \
+  fm_head_bwd_kernel<MC><<<grid, kHdWarps * 32, 0, st>>>(v, v_row_stride, nd ? x : nullptr, x_row_stride, wd, g,     \
+                                                         g_deep_in, g_deep_in_row_stride, B, F, F * D / 4, D / 4, nd, \
+                                                         grad_v, grad_v_row_stride, grad_w1, grad_x, grad_x_row_stride, part)
+  const int n_chunks = F * D / 4;
+  if (n_chunks <= 128) PTREC_HEAD_BWD(4);
+  else if (n_chunks <= 256) PTREC_HEAD_BWD(8);
+  else PTREC_HEAD_BWD(16);
+#undef PTREC_HEAD_BWD
   PTREC_LAUNCH_CHECK("fm_head_bwd_kernel");
   if (need_part) {
-    head_reduce_kernel<<<(unsigned)ceil_div(nd + 1, 32), 256, 0, st>>>(part, grid, nd + 1, grad_wd, nd, grad_bias);
+    head_reduce_kernel<<<(unsigned)ceil_div(nd + 1, 32), 1024, 0, st>>>(part, grid, nd + 1, grad_wd, nd, grad_bias);
     PTREC_LAUNCH_CHECK("head_reduce_kernel");
   }
   return PTREC_OK;
@@ -331,10 +374,13 @@ extern "C" int ptrec_rowdot_bwd(const float* h, int64_t h_row_stride, const floa
   const int grid = (int)std::min<int64_t>(head_grid(), ceil_div(B, kHdWarps));
   const size_t smem = (size_t)kHdWarps * H * sizeof(float);
   float* part = grad_w ? reinterpret_cast<float*>(workspace) : nullptr;
-  rowdot_bwd_kernel<<<grid, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, grad_h, grad_h_row_stride, part);
+  if (H <= 512)
+    rowdot_bwd_kernel<4><<<grid, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, grad_h, grad_h_row_stride, part);
+  else
+    rowdot_bwd_kernel<8><<<grid, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, grad_h, grad_h_row_stride, part);
   PTREC_LAUNCH_CHECK("rowdot_bwd_kernel");
   if (grad_w) {
-    head_reduce_kernel<<<(unsigned)ceil_div(H, 32), 256, 0, st>>>(part, grid, H, grad_w, H, nullptr);
+    head_reduce_kernel<<<(unsigned)ceil_div(H, 32), 1024, 0, st>>>(part, grid, H, grad_w, H, nullptr);
     PTREC_LAUNCH_CHECK("head_reduce_kernel");
   }
   return PTREC_OK;

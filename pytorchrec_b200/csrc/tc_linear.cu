@@ -17,6 +17,7 @@
 //                        the double-buffered accumulator: + bias, ReLU, fp32 store; or split-K partials (wgrad).
 //                        bound: bf16 tensor pipe.  FLOPs per launch = 12 * M * N * K.
 #include "tcgen05.cuh"
+#include "split3.cuh"
 
 namespace ptrec {
 
@@ -24,14 +25,6 @@ namespace ptrec {
 constexpr int kSpTile = 64;
 constexpr int kSpThreads = 256;
 constexpr int kSpPitch = kSpTile + 8;  // bf16 elements: rows stay 16-byte aligned
-
-__device__ __forceinline__ void split3(float v, __nv_bfloat16& p0, __nv_bfloat16& p1, __nv_bfloat16& p2) {
-  p0 = __float2bfloat16_rn(v);
-  const float r1 = v - __bfloat162float(p0);
-  p1 = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(p1);
-  p2 = __float2bfloat16_rn(r2);
-}
 
 struct Split3Args {
   const float* src;
@@ -190,6 +183,8 @@ struct LinEpi {
   float* out;         // [splits][M, ldo] fp32
   int64_t ldo;
   int splits;         // K cut into `splits` ranges (>= 1), one output slab each
+  __nv_bfloat16* planes;  // optional: the result again as bf16 planes [3][M][pl_ld] (the next layer's operand)
+  int64_t pl_ld, pl_plane;
 };
 
 struct LinMaps {
@@ -398,6 +393,10 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
               t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
             }
             *reinterpret_cast<float4*>(o + j) = t;
+            if (ep.planes != nullptr) {  // pl_ld >= N rounded up to 8: the group of 4 is inside the pitch
+              const float tv[4] = {t.x, t.y, t.z, t.w};
+              split3_store4(tv, ep.planes + (int64_t)row * ep.pl_ld + col0 + j, ep.pl_plane);
+            }
           }
         }
       }
@@ -639,6 +638,10 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
               t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
             }
             *reinterpret_cast<float4*>(o + j) = t;
+            if (ep.planes != nullptr) {  // pl_ld >= N rounded up to 8: the group of 4 is inside the pitch
+              const float tv[4] = {t.x, t.y, t.z, t.w};
+              split3_store4(tv, ep.planes + (int64_t)row * ep.pl_ld + col0 + j, ep.pl_plane);
+            }
           }
         }
       }
@@ -748,7 +751,8 @@ extern "C" int32_t ptrec_tc_gemm_split3_default_splits(int64_t M, int64_t N, int
 
 static int gemm_split3_impl(bool mn_major, const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N,
                             int64_t ldb, int64_t K, const float* bias, int32_t relu, float* out, int64_t ldo,
-                            int32_t splits, void* workspace, size_t workspace_bytes, void* stream) {
+                            void* out_planes, int64_t out_planes_ld, int32_t splits, void* workspace,
+                            size_t workspace_bytes, void* stream) {
   PTREC_CHECK_ARG(a_planes && b_planes && out, PTREC_EINVAL, "tc_gemm_split3: null pointer");
   PTREC_CHECK_ARG(M >= 1 && N >= 1 && K >= 1 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), PTREC_EINVAL,
                   "tc_gemm_split3: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
@@ -759,7 +763,10 @@ static int gemm_split3_impl(bool mn_major, const void* a_planes, int64_t M, int6
   const int total_kb = (int)ceil_div(K, (g_tc_2sm ? g_tc_bk : kLBK));
   if (splits > total_kb) splits = total_kb;
   while (splits > 1 && (int64_t)(splits - 1) * ceil_div(total_kb, splits) >= total_kb) --splits;  // no empty split
-  PTREC_CHECK_ARG(splits == 1 || (!bias && !relu), PTREC_EINVAL, "tc_gemm_split3: split-K has no bias / ReLU epilogue");
+  PTREC_CHECK_ARG(splits == 1 || (!bias && !relu && !out_planes), PTREC_EINVAL,
+                  "tc_gemm_split3: split-K has no bias / ReLU / planes epilogue");
+  PTREC_CHECK_ARG(!out_planes || (aligned16(out_planes) && out_planes_ld % 8 == 0 && out_planes_ld >= (N + 3) / 4 * 4),
+                  PTREC_EALIGN, "tc_gemm_split3: output plane pitch must be a multiple of 8 >= N");
   PTREC_CHECK_ARG(splits == 1 || (workspace && workspace_bytes >= ptrec_tc_gemm_split3_workspace_bytes(M, ldo, splits)),
                   PTREC_EWORKSPACE, "tc_gemm_split3: workspace too small for %d split-K partials", splits);
   cudaStream_t st = (cudaStream_t)stream;
@@ -788,6 +795,7 @@ static int gemm_split3_impl(bool mn_major, const void* a_planes, int64_t M, int6
   }
   LinEpi ep;
   ep.bias = bias; ep.relu = relu; ep.ldo = ldo; ep.splits = splits;
+  ep.planes = reinterpret_cast<__nv_bfloat16*>(out_planes); ep.pl_ld = out_planes_ld; ep.pl_plane = M * out_planes_ld;
   ep.out = splits > 1 ? reinterpret_cast<float*>(workspace) : out;
   if (two_sm) {
     const int64_t pair_tiles = ceil_div(N, 256) * ceil_div(M, 256) * splits;
@@ -826,14 +834,15 @@ static int gemm_split3_impl(bool mn_major, const void* a_planes, int64_t M, int6
 
 extern "C" int ptrec_tc_gemm_split3(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N,
                                     int64_t ldb, int64_t K, const float* bias, int32_t relu, float* out, int64_t ldo,
-                                    int32_t splits, void* workspace, size_t workspace_bytes, void* stream) {
-  return gemm_split3_impl(false, a_planes, M, lda, b_planes, N, ldb, K, bias, relu, out, ldo, splits, workspace,
-                          workspace_bytes, stream);
+                                    void* out_planes, int64_t out_planes_ld, int32_t splits, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  return gemm_split3_impl(false, a_planes, M, lda, b_planes, N, ldb, K, bias, relu, out, ldo, out_planes, out_planes_ld,
+                          splits, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ptrec_tc_gemm_split3_tn(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N,
                                        int64_t ldb, int64_t K, float* out, int64_t ldo, int32_t splits, void* workspace,
                                        size_t workspace_bytes, void* stream) {
-  return gemm_split3_impl(true, a_planes, M, lda, b_planes, N, ldb, K, nullptr, 0, out, ldo, splits, workspace,
-                          workspace_bytes, stream);
+  return gemm_split3_impl(true, a_planes, M, lda, b_planes, N, ldb, K, nullptr, 0, out, ldo, nullptr, 0, splits,
+                          workspace, workspace_bytes, stream);
 }

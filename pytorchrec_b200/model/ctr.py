@@ -58,7 +58,10 @@ class FM(IModel):
     def _head(self, data, v: Tensor, w: Tensor, x: Optional[Tensor], want_deep_in: bool):
         """(FM logit, tower input or None): one fused pass (K8) where the shape allows, K3 + library ops otherwise."""
         from .layer.interaction import fm_head
-        fused = fm_head(v, w, x, self.dense_linear.weight if x is not None else None, self.global_bias, want_deep_in)
+        mlp = getattr(self, "mlp", None)
+        units = mlp.mlp[0].linear.out_features if (want_deep_in and mlp is not None) else 0
+        fused = fm_head(v, w, x, self.dense_linear.weight if x is not None else None, self.global_bias, want_deep_in,
+                        tower_units=units)
         if fused is not None:
             return fused
         logit = w.sum(dim=(1, 2)) + self.fm2(v) + self.global_bias

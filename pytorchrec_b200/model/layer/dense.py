@@ -20,22 +20,29 @@ from ... import ops
 
 class _TcLinearReLU(torch.autograd.Function):
     """y = relu(x W^T + b) on K6.  Saves y (ReLU mask), the planes of x (weight gradient: read MN-major, i.e.
-    transposed by the tensor core itself) and the transposed planes of W (input gradient)."""
+    transposed by the tensor core itself) and the transposed planes of W (input gradient).  ``px``: the planes of x if
+    the producer already wrote them (K8 head, previous layer's epilogue); ``emit_planes``: have the epilogue write
+    the planes of y for the next layer.  Returns (y, planes of y or an empty tensor)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, px, emit_planes):
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         N, K = weight.shape
-        px, _, _ = ops.tc_split3(x)
+        if px is None:
+            px, _, _ = ops.tc_split3(x)
         pw, pwt, _ = ops.tc_split3(weight, want_planes=True, want_t=need_dx)
-        y = ops.tc_gemm_split3(px, pw, K, bias=bias, relu=True)
+        if emit_planes:
+            y, py = ops.tc_gemm_split3(px, pw, K, bias=bias, relu=True, want_planes=True)
+        else:
+            y, py = ops.tc_gemm_split3(px, pw, K, bias=bias, relu=True), x.new_empty(0, dtype=torch.bfloat16)
         ctx.save_for_backward(y, px if need_dw else None, pwt)
         ctx.dims = (x.shape[0], N, K)
         ctx.has_bias = bias is not None
-        return y
+        ctx.mark_non_differentiable(py)
+        return y, py
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, _gpy):
         y, px, pwt = ctx.saved_tensors
         B, N, K = ctx.dims
         need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
@@ -48,7 +55,7 @@ class _TcLinearReLU(torch.autograd.Function):
             dw = ops.tc_gemm_split3_tn(pg, N, px, K)                                # g^T x      [N, K]
             if not dw.is_contiguous():
                 dw = dw.contiguous()
-        return dx, dw, db
+        return dx, dw, db, None, None
 
 
 def tc_linear_enabled() -> bool:
@@ -67,6 +74,7 @@ class Dense(Module):
         self.linear = Linear(input_units, output_units)
         self.activation = ReLU()
         self.dropout = Dropout(dropout)
+        self.emit_planes = False  # set by MLP: the next Dense consumes this layer's output planes (no split pass)
 
     def forward(self, x):
         w = self.linear.weight
@@ -76,8 +84,16 @@ class Dense(Module):
             x2 = x.reshape(-1, x.shape[-1])
             if x2.stride(-1) != 1:
                 x2 = x2.contiguous()
-            y = _TcLinearReLU.apply(x2, w, self.linear.bias)
-            return self.dropout(y.reshape(*lead, w.shape[0]))
+            px = getattr(x, "_ptrec_planes", None)  # written by the producer of x (K8 head / previous layer)
+            if px is not None and not (x.dim() == 2 and tuple(px.shape) == (3, x2.shape[0], (x2.shape[1] + 7) // 8 * 8)
+                                       and px.device == x2.device):
+                px = None
+            y, py = _TcLinearReLU.apply(x2, w, self.linear.bias, px, self.emit_planes and x.dim() == 2)
+            if self.training and self.dropout.p > 0:
+                return self.dropout(y.reshape(*lead, w.shape[0]))
+            if py.numel():
+                y._ptrec_planes = py
+            return y.reshape(*lead, w.shape[0]) if x.dim() != 2 else y
         return self.dropout(self.activation(self.linear(x)))
 
 
@@ -89,6 +105,9 @@ class MLP(Module):
         for index, hidden_units in enumerate(hidden_units_list):
             self.mlp.add_module(f"dense_{index}", Dense(units, hidden_units, activation, dropout))
             units = hidden_units
+        # Dense.emit_planes (the GEMM epilogue writes the next layer's planes) stays off: the epilogue stores are
+        # per-thread rows (8-byte pieces, uncoalesced) and measured slower than the separate split pass
+        # (cfg2 step 0.72 -> 0.85 ms); it needs a shared-memory-staged epilogue first.
 
     def forward(self, x):
         return self.mlp(x)

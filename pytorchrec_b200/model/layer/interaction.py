@@ -18,17 +18,24 @@ class _FMHead(torch.autograd.Function):
     """K8: first-order sum + FM second order + dense linear term + bias -> logit, and the tower input [v | x]."""
 
     @staticmethod
-    def forward(ctx, v2d, w1, x, wd, bias, F, D, want_deep_in):
-        logit, deep_in = ops.fm_head_fwd(v2d, w1, x, wd, bias, F, D, want_deep_in)
+    def forward(ctx, v2d, w1, x, wd, bias, F, D, want_deep_in, want_planes):
+        planes = None
+        if want_deep_in and want_planes:
+            logit, deep_in, planes = ops.fm_head_fwd(v2d, w1, x, wd, bias, F, D, True, True)
+        else:
+            logit, deep_in = ops.fm_head_fwd(v2d, w1, x, wd, bias, F, D, want_deep_in)
         ctx.save_for_backward(v2d, x, wd)
         ctx.meta = (F, D)
         if deep_in is None:
             deep_in = v2d.new_empty(0)
             ctx.mark_non_differentiable(deep_in)
-        return logit, deep_in
+        if planes is None:
+            planes = v2d.new_empty(0, dtype=torch.bfloat16)
+        ctx.mark_non_differentiable(planes)
+        return logit, deep_in, planes
 
     @staticmethod
-    def backward(ctx, g_logit, g_deep_in):
+    def backward(ctx, g_logit, g_deep_in, _g_planes):
         v2d, x, wd = ctx.saved_tensors
         F, D = ctx.meta
         need = ctx.needs_input_grad
@@ -43,7 +50,7 @@ class _FMHead(torch.autograd.Function):
                 g_deep_in = buf[:, :g_deep_in.shape[1]]
         gv, gw1, gwd, gb = ops.fm_head_bwd(v2d, x, wd, g_logit.contiguous(), g_deep_in, F, D, want_w1=need[1],
                                            want_wd=need[3] and wd is not None, want_bias=need[4])
-        return gv if need[0] else None, gw1, None, gwd, gb, None, None, None
+        return gv if need[0] else None, gw1, None, gwd, gb, None, None, None, None
 
 
 class _RowDot(torch.autograd.Function):
@@ -66,10 +73,12 @@ def fm_head_enabled() -> bool:
     return os.environ.get("PTREC_FM_HEAD", "1") != "0"
 
 
-def fm_head(v: Tensor, w1, x, wd, bias, want_deep_in: bool):
+def fm_head(v: Tensor, w1, x, wd, bias, want_deep_in: bool, tower_units: int = 0):
     """``v [B, F, D]``, ``w1 [B, F, 1]`` or None, ``x [B, nd]`` or None, ``wd`` = Linear(nd, 1).weight or None,
     ``bias`` scalar parameter or None -> ``(logit [B], deep_in [B, F*D + nd] or None)``; None if K8 does not cover
-    the shape (the caller composes K3 + library ops instead)."""
+    the shape (the caller composes K3 + library ops instead).  ``tower_units``: width of the Dense layer that will
+    consume ``deep_in``; when that layer runs on K6 the head also writes its bf16 operand planes
+    (``deep_in._ptrec_planes``), sparing the layer its split pass."""
     B, F, D = v.shape
     nd = 0 if x is None else x.shape[1]
     if not (v.is_cuda and v.dtype == torch.float32 and fm_head_enabled() and ops.fm_head_supported(F, D, nd)):
@@ -77,11 +86,19 @@ def fm_head(v: Tensor, w1, x, wd, bias, want_deep_in: bool):
     v2d = v.reshape(B, F * D)
     if not (v2d.stride(1) == 1 and v2d.stride(0) % 4 == 0 and v2d.data_ptr() % 16 == 0):
         v2d = v2d.contiguous()
-    logit, deep_in = _FMHead.apply(v2d, w1.reshape(B, F).contiguous() if w1 is not None else None,
-                                   x.contiguous() if x is not None else None,
-                                   wd.reshape(-1) if (wd is not None and x is not None) else None,
-                                   bias.reshape(1) if bias is not None else None, F, D, want_deep_in)
-    return logit, (deep_in if want_deep_in else None)
+    from . import dense
+    want_planes = (want_deep_in and tower_units > 0 and dense.tc_linear_enabled()
+                   and B * (F * D + nd) * tower_units >= dense.TC_MIN_MACS)
+    logit, deep_in, planes = _FMHead.apply(v2d, w1.reshape(B, F).contiguous() if w1 is not None else None,
+                                           x.contiguous() if x is not None else None,
+                                           wd.reshape(-1) if (wd is not None and x is not None) else None,
+                                           bias.reshape(1) if bias is not None else None, F, D, want_deep_in,
+                                           want_planes)
+    if not want_deep_in:
+        return logit, None
+    if planes.numel():
+        deep_in._ptrec_planes = planes
+    return logit, deep_in
 
 
 def row_dot(h: Tensor, weight: Tensor):

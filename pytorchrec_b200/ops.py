@@ -342,7 +342,7 @@ def fm_head_supported(F: int, D: int, nd: int) -> bool:
 
 
 def fm_head_fwd(v: torch.Tensor, w1: Optional[torch.Tensor], x: Optional[torch.Tensor], wd: Optional[torch.Tensor],
-                bias: Optional[torch.Tensor], F: int, D: int, want_deep_in: bool):
+                bias: Optional[torch.Tensor], F: int, D: int, want_deep_in: bool, want_planes: bool = False):
     """v [B, F*D] (row stride % 4 == 0), w1 [B, F], x [B, nd], wd [nd], bias [1] -> (logit [B], deep_in or None);
     deep_in is a [B, F*D+nd] view of a buffer whose pitch is rounded up to 4 floats."""
     lib = _lib.load()
@@ -355,11 +355,13 @@ def fm_head_fwd(v: torch.Tensor, w1: Optional[torch.Tensor], x: Optional[torch.T
     if want_deep_in:
         pitch = (F * D + nd + 3) // 4 * 4
         deep_buf = torch.empty(B, pitch, dtype=torch.float32, device=dev)
+    planes = torch.empty(3, B, _pad8(F * D + nd), dtype=torch.bfloat16, device=dev) if want_planes else None
     _lib.check(lib.ptrec_fm_head_fwd(_ptr(v), v.stride(0), _ptr(w1), w1.stride(0) if w1 is not None else 0, _ptr(x),
                                      x.stride(0) if x is not None else 0, _ptr(wd), _ptr(bias), B, F, D, nd,
                                      _ptr(logit), _ptr(deep_buf), deep_buf.stride(0) if deep_buf is not None else 0,
-                                     _stream(dev)), "ptrec_fm_head_fwd")
-    return logit, (deep_buf[:, :F * D + nd] if deep_buf is not None else None)
+                                     _ptr(planes), _pad8(F * D + nd), _stream(dev)), "ptrec_fm_head_fwd")
+    deep_in = deep_buf[:, :F * D + nd] if deep_buf is not None else None
+    return (logit, deep_in, planes) if want_planes else (logit, deep_in)
 
 
 def fm_head_bwd(v: torch.Tensor, x: Optional[torch.Tensor], wd: Optional[torch.Tensor], g: torch.Tensor,
@@ -505,10 +507,10 @@ def tc_split3(src: torch.Tensor, relu_ref: Optional[torch.Tensor] = None, want_p
 
 
 def tc_gemm_split3(a_planes: torch.Tensor, b_planes: torch.Tensor, K: int, bias: Optional[torch.Tensor] = None,
-                   relu: bool = False, splits: int = 1) -> torch.Tensor:
+                   relu: bool = False, splits: int = 1, want_planes: bool = False):
     """out [M, N] fp32 = A[M, K] B[N, K]^T (+ bias) (ReLU) from bf16 planes [3, M, lda], [3, N, ldb].  The result is a
     [:, :N] view of a buffer whose pitch is N rounded up to 4.  ``splits=0`` picks the split-K count for a K-heavy
-    product."""
+    product.  ``want_planes``: also return the result as planes [3, M, pad8(N)] (written by the same epilogue)."""
     lib = _lib.load()
     _require_cuda(a_planes, b_planes, bias)
     assert a_planes.dtype == torch.bfloat16 and b_planes.dtype == torch.bfloat16
@@ -524,10 +526,14 @@ def tc_gemm_split3(a_planes: torch.Tensor, b_planes: torch.Tensor, K: int, bias:
     ws = _workspace("tc_gemm_split3", nbytes, dev) if nbytes else None
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
+    planes = torch.empty(3, M, _pad8(N), dtype=torch.bfloat16, device=dev) if want_planes else None
+    if want_planes and _pad8(N) != ldo:
+        planes[:, :, N:].zero_()  # the epilogue writes columns < ldo only
     _lib.check(lib.ptrec_tc_gemm_split3(_ptr(a_planes), M, lda, _ptr(b_planes), N, ldb, K, _ptr(bias), int(relu),
-                                        _ptr(out), ldo, splits, _ptr(ws), ws.numel() if ws is not None else 0,
-                                        _stream(dev)), "ptrec_tc_gemm_split3")
-    return out[:, :N] if ldo != N else out
+                                        _ptr(out), ldo, _ptr(planes), _pad8(N), splits, _ptr(ws),
+                                        ws.numel() if ws is not None else 0, _stream(dev)), "ptrec_tc_gemm_split3")
+    y = out[:, :N] if ldo != N else out
+    return (y, planes) if want_planes else y
 
 
 def tc_gemm_split3_tn(a_planes: torch.Tensor, M: int, b_planes: torch.Tensor, N: int, splits: int = 0) -> torch.Tensor:

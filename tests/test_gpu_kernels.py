@@ -687,3 +687,23 @@ def test_row_dot_matches_linear(B, H):
     for a, b in zip(*res):
         assert a.shape == b.shape
         assert (a - b).abs().max().item() <= 2e-5 * max(1.0, a.abs().max().item())
+
+
+@pytest.mark.gpu
+def test_producer_written_planes_are_the_exact_split_of_the_fp32_result(tc_mode):
+    """GEMM epilogue and FM head write the next layer's bf16 planes themselves: same bits as a split pass."""
+    gen = torch.Generator().manual_seed(9)
+    a = torch.randn(700, 429, generator=gen).to(DEV)
+    w = torch.randn(400, 429, generator=gen).to(DEV)
+    b = torch.randn(400, generator=gen).to(DEV)
+    pa, pw = ops.tc_split3(a)[0], ops.tc_split3(w)[0]
+    y, py = ops.tc_gemm_split3(pa, pw, 429, bias=b, relu=True, want_planes=True)
+    assert torch.equal(y, ops.tc_gemm_split3(pa, pw, 429, bias=b, relu=True))
+    assert torch.equal(py, ops.tc_split3(y)[0])
+    w2 = torch.randn(52, 429, generator=gen).to(DEV)      # N = 52: pitch 52 (fp32) vs 56 (planes), pad must be 0
+    y2, py2 = ops.tc_gemm_split3(pa, ops.tc_split3(w2)[0], 429, want_planes=True)
+    assert torch.equal(py2, ops.tc_split3(y2)[0])
+    v = torch.randn(300, 26 * 16, generator=gen).to(DEV)
+    x = torch.randn(300, 13, generator=gen).to(DEV)
+    logit, deep_in, planes = ops.fm_head_fwd(v, None, x, None, None, 26, 16, True, True)
+    assert torch.equal(deep_in, torch.cat([v, x], 1)) and torch.equal(planes, ops.tc_split3(deep_in)[0])
