@@ -59,7 +59,7 @@ def config_dict(a, world):
             "global_batch": a.batch * world, "id_dist": a.id_dist, "cuda_graph": not a.no_graph,
             "parallelism": "single GPU" if world == 1 else (
                 f"row-wise sharded tables x{world} ("
-                + ("NVLink peer-memory gather / push inside the kernels" if os.environ.get("PTREC_PEER_GATHER", "1") != "0"
+                + ("NVLink peer-memory gather / push inside the kernels" if getattr(a, "peer_path", True)
                    else "NCCL all-to-all") + ") + dense allreduce"),
             "l2": "tables %.2f GB >> 126 MB L2; a different random id batch every step" %
                   (26 * a.rows * (a.dim + 1) * 4 / 1e9)}
@@ -185,6 +185,7 @@ def run_b200(a):
     else:
         from pytorchrec_b200.distributed import ShardedDeepFM
         model = ShardedDeepFM(sparse, dense, label, a.dim, CFG["layers"], random_seed=2020, table_device=dev)
+    a.peer_path = bool(getattr(getattr(model, "sharded", None), "peer", False))
     opt = SparseAdagrad(params=model.get_parameters(), lr=0.01)
     model.compile(opt, torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)
     if not a.no_graph:

@@ -5,7 +5,8 @@ has a reference counterpart, it widens the same hot path to the 8 x B200 box.
 
 Plan:  owner(id) = id mod G,  local_row = id div G.
 
-Peer-memory path (default on NCCL process groups; ``peer=False`` or PTREC_PEER_GATHER=0 selects the other one):
+Peer-memory path (default on NCCL process groups while the shards stay below PTREC_PEER_MAX_GB = 16 GB per GPU;
+``peer=True/False`` or PTREC_PEER_GATHER=1/0 force one or the other):
 the shards and the owners' receive buffers live in symmetric memory, every rank holds the peers' pointers, and
 the exchange happens INSIDE the kernels over NVLink / NVSwitch:
   forward   ONE gather launch per width; its 128-bit row loads go to whichever GPU owns the row  (no collective)
@@ -237,7 +238,15 @@ class RowWiseShardedEmbedding(nn.Module):
         self._bufs: Dict[tuple, dict] = {}
         # ---- peer-memory path state ----
         if peer is None:
-            peer = dist.get_backend(group) == "nccl" and os.environ.get("PTREC_PEER_GATHER", "1") != "0"
+            # Peer-memory exchange where the shards are small, NCCL all-to-all where they are huge: with 83 GB of
+            # weight|state per GPU (cfg5) random rows across 7 x 83 GB of peer mappings ran 10.1 ms/step against
+            # 6.8 ms for the all-to-all path (which touches remote memory only through contiguous buffers), while at
+            # cfg2 (< 2 GB per GPU) the peer path wins (profiles/r1_bench_cfg5_n8_{peer,a2a}.json).  The estimate uses
+            # the rank-independent shard height so that every rank takes the same decision.
+            env = os.environ.get("PTREC_PEER_GATHER", "auto")
+            cap_gb = float(os.environ.get("PTREC_PEER_MAX_GB", "16"))
+            per_gpu = sum((c.category_num + self.world - 1) // self.world for c in self.columns) * sum(self.dims) * 8
+            peer = dist.get_backend(group) == "nccl" and (env == "1" or (env != "0" and per_gpu <= cap_gb * 2 ** 30))
         self.peer = bool(peer)
         self._dirty = False                        # a table update / buffer reset not yet ordered by a collective
         self._peer_key = None                      # (data_ptr, row stride) of every table when pointers were exchanged
