@@ -323,6 +323,16 @@ class IModel(Module, ABC):
         return prediction
 
     # ------------------------------------------------------------------ fit / evaluate
+    @staticmethod
+    def _loader(dataset, batch_size: int, shuffle: bool, workers: int, drop_last: bool):
+        """Batches of ``dataset`` in ``DataLoader`` order.  A tensor-native split (``data.SplitDataset``, N2) assembles
+        whole batches by index — same samples, same order under the same seed; any other ``Dataset`` goes through
+        ``torch.utils.data.DataLoader`` exactly as in the reference (IModel.py:183-186,242,294)."""
+        if hasattr(dataset, "batches"):
+            return dataset.batches(batch_size, shuffle=shuffle, drop_last=drop_last)
+        return DataLoader(dataset=dataset, batch_size=batch_size, shuffle=shuffle, num_workers=workers,
+                          drop_last=drop_last)
+
     def fit(self, dataset: Dataset, batch_size: int, epochs: int, dev_dataset: Optional[Dataset] = None,
             train_mode=None, verbose: int = 0, callbacks: Optional[list] = None, shuffle: bool = True,
             workers: int = 0, drop_last: bool = False, dev_batch_size: Optional[int] = None,
@@ -336,9 +346,7 @@ class IModel(Module, ABC):
             if train_mode is not None and getattr(train_mode, "value", train_mode) == "pair_wise" \
                     and hasattr(dataset, "train_neg_sample"):
                 dataset.train_neg_sample()
-            loader = DataLoader(dataset=dataset, batch_size=batch_size, shuffle=shuffle, num_workers=workers,
-                                drop_last=drop_last)
-            it = iter(loader)
+            it = iter(self._loader(dataset, batch_size, shuffle, workers, drop_last))
             data = next(it, None)
             if data is not None:
                 self.prefetch(data)
@@ -361,7 +369,7 @@ class IModel(Module, ABC):
     @torch.no_grad()
     def evaluate(self, dataset: Dataset, batch_size: int, verbose: int = 0, callbacks=None, workers: int = 0):
         self._assert_compile_was_called()
-        loader = DataLoader(dataset=dataset, batch_size=batch_size, num_workers=workers)
+        loader = self._loader(dataset, batch_size, False, workers, False)
         predictions, targets = [], []
         # N3: with ranking metrics only, scores stay on the device and ranks are computed there — one
         # synchronisation per evaluate() instead of the reference's .cpu().numpy() per batch (IModel.py:250-251)
@@ -379,7 +387,7 @@ class IModel(Module, ABC):
 
     @torch.no_grad()
     def predict(self, dataset: Dataset, batch_size: int, verbose: int = 0, callbacks=None, workers: int = 0):
-        loader = DataLoader(dataset=dataset, batch_size=batch_size, num_workers=workers)
+        loader = self._loader(dataset, batch_size, False, workers, False)
         return np.concatenate([self.predict_step(d).detach().cpu().numpy() for d in loader])
 
     def _assert_compile_was_called(self):
