@@ -54,7 +54,9 @@ def parse():
 
 
 def config_dict(a, world):
-    return {"workload": "%s DeepFM Criteo-shaped synthetic: 26 tables x %d rows x dim %d (+26 first-order dim 1), "
+    from pytorchrec_b200 import ops
+    return {"dnn_gemm_operands": ops.tc_mode(),  # K6: fp32 Linear operands as bf16x3 or fp16x2 planes
+            "workload": "%s DeepFM Criteo-shaped synthetic: 26 tables x %d rows x dim %d (+26 first-order dim 1), "
                         "13 dense, DNN 400-400-400, batch %d per GPU, fp32, sparse Adagrad" % (a.workload, a.rows, a.dim, a.batch),
             "global_batch": a.batch * world, "id_dist": a.id_dist, "cuda_graph": not a.no_graph,
             "parallelism": "single GPU" if world == 1 else (
@@ -364,27 +366,38 @@ def kernel_roofline(a, model, resident, dev):
     lin = mlp.mlp[0].linear
     N, K = lin.weight.shape
     xs = [torch.randn(B, K, device=dev) for _ in range(4)]
-    pxs = [ops.tc_split3(x)[0] for x in xs]
-    pw = ops.tc_split3(lin.weight.detach())[0]
     bias = lin.bias.detach()
-    t_gemm = time_it(lambda i: ops.tc_gemm_split3(pxs[i % 4], pw, K, bias=bias, relu=True), 40)
-    t_wgrad = time_it(lambda i: ops.tc_gemm_split3_tn(pxs[i % 4], K, pxs[(i + 1) % 4], K), 20)
-    t_split = time_it(lambda i: ops.tc_split3(xs[i % 4]), 40)
-    flops = 12.0 * B * N * K
-    kernels["tc_linear_fwd(gemm_split3)"] = {"seconds": t_gemm, "flops_bf16_issued": flops, "TFLOPs_bf16": flops / t_gemm / 1e12,
-                                             "TFLOPs_fp32_equivalent": flops / 6 / t_gemm / 1e12, "M": B, "N": N, "K": K}
-    kernels["tc_linear_wgrad(gemm_split3_tn)"] = {"seconds": t_wgrad, "M": K, "N": K, "K": B,
-                                                  "TFLOPs_bf16": 12.0 * B * K * K / t_wgrad / 1e12}
-    sp_bytes = B * K * 4 + 3 * B * ((K + 7) // 8 * 8) * 2
-    kernels["tc_split3"] = {"seconds": t_split, "bytes": sp_bytes, "GBps": sp_bytes / t_split / 1e9}
+    h2 = ops.tc_mode() == "fp16x2"
+    if h2:   # fp16 x 2 operands: 3 MMAs per product, two planes, an |x|-maximum pass inside the split call
+        hxs = [ops.tc_split2h(x) for x in xs]
+        hw = ops.tc_split2h(lin.weight.detach())
+        t_gemm = time_it(lambda i: ops.tc_gemm_split2h(hxs[i % 4][0], hxs[i % 4][3], hw[0], hw[3], K, bias=bias, relu=True), 40)
+        t_wgrad = time_it(lambda i: ops.tc_gemm_split2h_tn(hxs[i % 4][0], hxs[i % 4][3], K, hxs[(i + 1) % 4][0],
+                                                           hxs[(i + 1) % 4][3], K), 20)
+        t_split = time_it(lambda i: ops.tc_split2h(xs[i % 4]), 40)
+        pairs, planes, fmt, kname = 3, 2, "fp16", "gemm_split2h"
+    else:
+        pxs = [ops.tc_split3(x)[0] for x in xs]
+        pw = ops.tc_split3(lin.weight.detach())[0]
+        t_gemm = time_it(lambda i: ops.tc_gemm_split3(pxs[i % 4], pw, K, bias=bias, relu=True), 40)
+        t_wgrad = time_it(lambda i: ops.tc_gemm_split3_tn(pxs[i % 4], K, pxs[(i + 1) % 4], K), 20)
+        t_split = time_it(lambda i: ops.tc_split3(xs[i % 4]), 40)
+        pairs, planes, fmt, kname = 6, 3, "bf16", "gemm_split3"
+    flops = 2.0 * pairs * B * N * K
+    kernels[f"tc_linear_fwd({kname})"] = {"seconds": t_gemm, f"flops_{fmt}_issued": flops, f"TFLOPs_{fmt}": flops / t_gemm / 1e12,
+                                          "TFLOPs_fp32_equivalent": flops / pairs / t_gemm / 1e12, "M": B, "N": N, "K": K}
+    kernels[f"tc_linear_wgrad({kname}_tn)"] = {"seconds": t_wgrad, "M": K, "N": K, "K": B,
+                                               f"TFLOPs_{fmt}": 2.0 * pairs * B * K * K / t_wgrad / 1e12}
+    sp_bytes = B * K * 4 * (2 if h2 else 1) + planes * B * ((K + 7) // 8 * 8) * 2
+    kernels["tc_split2h" if h2 else "tc_split3"] = {"seconds": t_split, "bytes": sp_bytes, "GBps": sp_bytes / t_split / 1e9}
     pk = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
     tpeak = pk.get("bf16_tflops", 2250.0)
-    roof = {"kernel": "gemm_split3 (K6, DNN tower Linear fwd)", "bound": "tensor", "achieved": flops / t_gemm / 1e12,
+    roof = {"kernel": f"{kname} (K6, DNN tower Linear fwd)", "bound": "tensor", "achieved": flops / t_gemm / 1e12,
             "peak": tpeak, "unit": "TFLOP/s", "frac": flops / t_gemm / 1e12 / tpeak,
-            "traffic": traffic_all.get("gemm_split3"),
+            "traffic": traffic_all.get(kname),
             "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)" if pk else "nominal",
             "algorithmic_flops_per_launch": flops, "seconds_per_launch": t_gemm,
-            "note": "bf16 FLOPs issued = 6 plane pairs x 2*M*N*K; fp32-equivalent rate = achieved / 6"}
+            "note": f"{fmt} FLOPs issued = {pairs} plane pairs x 2*M*N*K; fp32-equivalent rate = achieved / {pairs}"}
     return roof, kernels, roof_hbm
 
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 15
+#define PTREC_ABI_VERSION 16
 
 /* error codes */
 #define PTREC_OK 0
@@ -392,6 +392,31 @@ int ptrec_tc_gemm_split3(const void* a_planes, int64_t M, int64_t lda, const voi
 int ptrec_tc_gemm_split3_tn(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N, int64_t ldb,
                             int64_t K, float* out, int64_t ldo, int32_t splits, void* workspace,
                             size_t workspace_bytes, void* stream);
+
+/* K6, fp16 x 2 operand format (same GEMM kernels, 3 MMAs per product instead of 6, two operand planes instead of three).
+ * fp16 has 5 exponent bits, so every tensor is first multiplied by a power of two s that puts its largest magnitude in
+ * [2^13, 2^14) (exact); then  x s = h0 + h1 / 2^11,  h0 = fp16(x s),  h1 = fp16((x s - h0) 2^11)  — 2 x 11 = 22 mantissa
+ * bits, and h1 is a normal fp16 number whenever h0 is.  The product uses A0 B0 (main accumulator) and A0 B1 + A1 B0
+ * (correction accumulator, carrying 2^11); the fp32 epilogue forms (main + 2^-11 corr) / (s_a s_b).  Dropped: A1 B1,
+ * 2^-22 relative.
+ *
+ * ptrec_tc_split2h: as ptrec_tc_split3 with fp16 planes [2][R][pl_ld] / [2][C][pt_ld]; scale_out receives s (one fp32
+ *   device word, read by the GEMMs on the device: no host synchronisation).  s comes from the absolute maximum of src
+ *   (before the relu_ref mask), found by a first kernel of the same call.  workspace: ptrec_tc_split2h_workspace_bytes
+ *   (always needed).
+ * ptrec_tc_gemm_split2h / _tn: as ptrec_tc_gemm_split3 / _tn on fp16 planes; scale_a / scale_b are the device words the
+ *   two split calls wrote.  No output planes. */
+size_t ptrec_tc_split2h_workspace_bytes(int64_t R, int64_t C);
+int ptrec_tc_split2h(const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref, int64_t ld_ref,
+                     void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld, float* colsum, float* scale_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int ptrec_tc_gemm_split2h(const void* a_planes, const float* scale_a, int64_t M, int64_t lda, const void* b_planes,
+                          const float* scale_b, int64_t N, int64_t ldb, int64_t K, const float* bias, int32_t relu,
+                          float* out, int64_t ldo, int32_t splits, void* workspace, size_t workspace_bytes,
+                          void* stream);
+int ptrec_tc_gemm_split2h_tn(const void* a_planes, const float* scale_a, int64_t M, int64_t lda, const void* b_planes,
+                             const float* scale_b, int64_t N, int64_t ldb, int64_t K, float* out, int64_t ldo,
+                             int32_t splits, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * C1 row-wise sharding: pack / unpack either side of the all-to-all (NCCL, issued by the host through

@@ -120,3 +120,40 @@ def crossed_ids_ref(id_list: Sequence[np.ndarray], category_nums: Sequence[int])
     for ids, n in zip(id_list, category_nums):
         out = out * n + ids.astype(np.int64)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K6 fp16 x 2 operand format (no reference counterpart: the reference multiplies in fp32, torchrec/model/layer/
+# Dense.py:9-17; this restates include/ptrec_b200.h's definition so the device planes can be checked bit for bit)
+# ---------------------------------------------------------------------------------------------------------------
+def h2_scale_ref(absmax: float) -> float:
+    """Power of two that puts ``absmax`` in [2^13, 2^14); 1 for 0 / inf / nan (split3.cuh::h2_scale)."""
+    import math
+    if not (absmax > 0.0) or math.isinf(absmax):
+        return 1.0
+    e = math.frexp(absmax)[1] - 1          # floor(log2(absmax))
+    e = max(e, -127)                        # fp32 subnormals report the exponent field 0
+    return 2.0 ** max(-126, min(13 - e, 126))
+
+
+def split2h_ref(x: torch.Tensor, mask_ref: torch.Tensor = None):
+    """(h0, h1, scale): x * scale = h0 + h1 / 2048 with h0 = fp16(x * scale), h1 = fp16((x * scale - h0) * 2048);
+    ``scale`` from the absolute maximum of x BEFORE the ReLU mask ``mask_ref > 0`` is applied."""
+    x = x.float()
+    scale = h2_scale_ref(float(x.abs().max())) if x.numel() else 1.0
+    if mask_ref is not None:
+        x = x * (mask_ref > 0)
+    xs = x * scale
+    h0 = xs.half()
+    h1 = ((xs - h0.float()) * 2048.0).half()
+    return h0, h1, scale
+
+
+def gemm_split2h_ref(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """A B^T through the fp16 x 2 format with fp32 accumulation (CPU emulation of the K6 arithmetic: plane products
+    are exact in fp32, the accumulation order differs from the tensor core's)."""
+    a0, a1, sa = split2h_ref(a)
+    b0, b1, sb = split2h_ref(b)
+    main = a0.float() @ b0.float().t()
+    corr = a0.float() @ b1.float().t() + a1.float() @ b0.float().t()
+    return ((main + corr * (1.0 / 2048.0)) * (1.0 / sa)) * (1.0 / sb)

@@ -23,3 +23,35 @@ __device__ __forceinline__ void split3_store4(const float* v, __nv_bfloat16* o, 
 }
 
 }  // namespace ptrec
+
+// ---- fp16 x 2 ("h2") split ---------------------------------------------------------------------------------------
+// x * s == h0 + h1 / 2048 up to 2^-23 relative, where s is a power of two that puts the tensor's largest magnitude in
+// [2^13, 2^14) (fp16 has 5 exponent bits: without s, gradients of ~1e-8 would fall below its subnormals).  The second
+// plane is stored multiplied by 2^11 so that it is a normal fp16 number whenever the first one is (Ootomo & Yokota's
+// error-corrected tensor-core GEMM); the GEMM accumulates the two cross terms in their own accumulator and applies
+// 2^-11 and 1 / (s_a s_b) in its fp32 epilogue.  2 x 11 = 22 mantissa bits, 3 MMAs per product.
+#include <cuda_fp16.h>
+
+namespace ptrec {
+
+constexpr float kH2Second = 2048.f;          // 2^11
+constexpr float kH2SecondInv = 1.f / 2048.f;
+
+// power-of-two scale for a tensor whose largest magnitude is m: m * s in [2^13, 2^14) (exponent clamped to the normal
+// fp32 range; the epilogue undoes the two operand scales with two separate exact multiplications); 0 / inf / nan -> 1.
+__device__ __forceinline__ float h2_scale(float m) {
+  if (!(m > 0.f) || m > 3.0e38f) return 1.f;
+  const int e = (int)((__float_as_uint(m) >> 23) & 0xFFu) - 127;  // floor(log2 m) (-127 for fp32 subnormals)
+  int se = 13 - e;
+  se = se < -126 ? -126 : (se > 126 ? 126 : se);
+  return __uint_as_float((uint32_t)(se + 127) << 23);
+}
+
+__device__ __forceinline__ void split2h(float v, float scale, __half& h0, __half& h1) {
+  const float xs = v * scale;  // exact (power of two)
+  h0 = __float2half_rn(xs);
+  const float r = xs - __half2float(h0);  // exact in fp32
+  h1 = __float2half_rn(r * kH2Second);
+}
+
+}  // namespace ptrec

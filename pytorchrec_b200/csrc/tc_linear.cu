@@ -32,18 +32,72 @@ struct Split3Args {
   int R, C;
   const float* ref;  // ReLU output (or any tensor whose sign gates src); null = no mask
   int64_t ld_ref;
-  __nv_bfloat16* planes;  // [3][R][pl_ld], columns [C, Cp) written as zero; null = skip
+  unsigned short* planes;  // [NP][R][pl_ld] bf16 / fp16 bits, columns [C, Cp) written as zero; null = skip
   int64_t pl_ld, pl_plane;
   int Cp;
-  __nv_bfloat16* planes_t;  // [3][C][pt_ld], columns [R, Rp) written as zero; null = skip
+  unsigned short* planes_t;  // [NP][C][pt_ld], columns [R, Rp) written as zero; null = skip
   int64_t pt_ld, pt_plane;
   int Rp;
   float* colsum_part;  // [gridDim.y][C] per-row-tile column sums of the masked src; null = skip
+  // NP == 2 (fp16 x 2) only: per-CTA maxima of |src| written by absmax_kernel, and where the scale goes
+  const float* absmax_part;
+  int n_part;
+  float* scale_out;
 };
 
-__global__ void __launch_bounds__(kSpThreads) split3_kernel(const Split3Args a) {
-  __shared__ __align__(16) __nv_bfloat16 s_t[3][kSpTile][kSpPitch];
+// |src| maxima, one per CTA (no atomics: the split kernel reduces the few hundred partials itself)
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ src, int64_t ld, int R, int C,
+                                                     float* __restrict__ part) {
+  float m = 0.f;
+  const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  const int c4 = vec ? C / 4 : 0;
+  const int64_t n4 = (int64_t)R * c4;
+  const int64_t step = (int64_t)gridDim.x * 256;
+#pragma unroll 4
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += step) {
+    const int64_t r = i / c4;
+    const int c = (int)(i - r * c4);
+    const float4 t = *reinterpret_cast<const float4*>(src + r * ld + 4 * c);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+  }
+  const int tail = C - 4 * c4;  // the whole row when the source is not 16-byte addressable
+  const int64_t nt = (int64_t)R * tail;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nt; i += step) {
+    const int64_t r = i / tail;
+    m = fmaxf(m, fabsf(src[r * ld + 4 * c4 + (int)(i - r * tail)]));
+  }
+  __shared__ float s_m[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_m[w]);
+    part[blockIdx.x] = m;
+  }
+}
+
+// NP = 3: exact bf16 x 3 split.  NP = 2: fp16 x 2 split of src * scale (split3.cuh), scale from the |src| maxima.
+template <int NP>
+__global__ void __launch_bounds__(kSpThreads) split_kernel(const Split3Args a) {
+  __shared__ __align__(16) unsigned short s_t[NP][kSpTile][kSpPitch];
   __shared__ float s_cs[16][kSpTile];
+  __shared__ float s_red[kSpThreads / 32];
+  float scale = 1.f;
+  if (NP == 2) {
+    float m = 0.f;
+    for (int i = threadIdx.x; i < a.n_part; i += kSpThreads) m = fmaxf(m, a.absmax_part[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = s_red[0];
+#pragma unroll
+    for (int w = 1; w < kSpThreads / 32; ++w) m = fmaxf(m, s_red[w]);
+    scale = h2_scale(m);  // every thread of every CTA derives the same value
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.scale_out = scale;
+  }
   const int c0 = blockIdx.x * kSpTile, r0 = blockIdx.y * kSpTile;
   const int cg = threadIdx.x & 15, rr = threadIdx.x >> 4;  // 4 columns x (rows rr, rr+16, rr+32, rr+48)
   const int c = c0 + cg * 4;
@@ -81,24 +135,33 @@ __global__ void __launch_bounds__(kSpThreads) split3_kernel(const Split3Args a) 
           if (!(m[i] > 0.f)) v[i] = 0.f;
       }
     }
-    __nv_bfloat16 p0[4], p1[4], p2[4];
+    unsigned short pl[NP][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      split3(v[i], p0[i], p1[i], p2[i]);
+      if (NP == 3) {
+        __nv_bfloat16 b0, b1, b2;
+        split3(v[i], b0, b1, b2);
+        pl[0][i] = __bfloat16_as_ushort(b0);
+        pl[1][i] = __bfloat16_as_ushort(b1);
+        pl[NP - 1][i] = __bfloat16_as_ushort(b2);
+      } else {
+        __half h0, h1;
+        split2h(v[i], scale, h0, h1);
+        pl[0][i] = __half_as_ushort(h0);
+        pl[1][i] = __half_as_ushort(h1);
+      }
       cs[i] += v[i];
     }
     if (a.planes != nullptr && r < a.R && c < a.Cp) {  // Cp % 8 == 0, c % 4 == 0: the group of 4 is inside the pitch
-      __nv_bfloat16* o = a.planes + (int64_t)r * a.pl_ld + c;
-      *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(p0);
-      *reinterpret_cast<uint2*>(o + a.pl_plane) = *reinterpret_cast<const uint2*>(p1);
-      *reinterpret_cast<uint2*>(o + 2 * a.pl_plane) = *reinterpret_cast<const uint2*>(p2);
+      unsigned short* o = a.planes + (int64_t)r * a.pl_ld + c;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) *reinterpret_cast<uint2*>(o + p * a.pl_plane) = *reinterpret_cast<const uint2*>(pl[p]);
     }
     if (a.planes_t != nullptr) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        s_t[0][cg * 4 + i][rl] = p0[i];
-        s_t[1][cg * 4 + i][rl] = p1[i];
-        s_t[2][cg * 4 + i][rl] = p2[i];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) s_t[p][cg * 4 + i][rl] = pl[p][i];
       }
     }
   }
@@ -122,7 +185,7 @@ __global__ void __launch_bounds__(kSpThreads) split3_kernel(const Split3Args a) 
       const int cc = c0 + cl;
       if (cc < a.C && r < a.Rp) {  // Rp % 8 == 0: the group of 8 is inside the pitch; rows >= R hold zeros
 #pragma unroll
-        for (int p = 0; p < 3; ++p) {
+        for (int p = 0; p < NP; ++p) {
           *reinterpret_cast<uint4*>(a.planes_t + (int64_t)p * a.pt_plane + (int64_t)cc * a.pt_ld + r) =
               *reinterpret_cast<const uint4*>(&s_t[p][cl][seg * 8]);
         }
@@ -168,14 +231,22 @@ __global__ void partial_reduce_kernel(const float* __restrict__ partial, int spl
 // TMEM allows: 128 x 256 with K blocks of 32 -> 72 KB per stage for 12 MMAs of N = 256 (0.75x the bytes per FLOP of
 // 128 x 128 tiles).  The two fp32 accumulators (main + correction, below) take all 512 TMEM columns, so the
 // accumulator is single-buffered: the MMA warp waits for the epilogue to pull a tile into registers (~5 % of a tile).
-constexpr int kLBM = 128, kLBN = 256, kLBK = 32, kLStages = 3, kLUmmaK = 16;
+constexpr int kLBM = 128, kLBN = 256, kLBK = 32, kLUmmaK = 16;
 constexpr int kLEpiWarps = 8;
 constexpr int kLThreads = 64 + 32 * kLEpiWarps;
 constexpr uint32_t kLTileA = kLBM * kLBK * 2;          // one A plane tile:  128 rows x 32 bf16 (8 KB)
 constexpr uint32_t kLTileB = kLBN * kLBK * 2;          // one B plane tile:  256 rows x 32 bf16 (16 KB)
-constexpr uint32_t kLStageBytes = 3 * (kLTileA + kLTileB);  // A0 A1 A2 B0 B1 B2 = 72 KB
+// NP planes per operand: 3 (bf16 x 3: A0 A1 A2 B0 B1 B2 = 72 KB per stage, 3 stages) or 2 (fp16 x 2: 48 KB, 4 stages)
+template <int NP> struct LinCfg {
+  static constexpr int kStages = NP == 3 ? 3 : 4;
+  static constexpr uint32_t kStageBytes = NP * (kLTileA + kLTileB);
+  // instruction descriptor: D = fp32 (bit 4); A / B format bf16 (1 at bits 7 / 10) or fp16 (0)
+  static constexpr uint32_t kIdescFmt = NP == 3 ? ((1u << 4) | (1u << 7) | (1u << 10)) : (1u << 4);
+};
 constexpr uint32_t kLTmemCols = 512;                   // main [0, 256) + correction [256, 512)
-constexpr size_t kLSmem = (size_t)kLStages * kLStageBytes + 1024 /*align*/ + 2048 /*barriers + bias slice*/;
+constexpr size_t kLSmem = (size_t)3 * 72 * 1024 + 1024 /*align*/ + 2048 /*barriers + bias slice*/;
+static_assert((size_t)LinCfg<3>::kStages * LinCfg<3>::kStageBytes + 3072 <= kLSmem, "bf16 x 3 stages exceed the budget");
+static_assert((size_t)LinCfg<2>::kStages * LinCfg<2>::kStageBytes + 3072 <= kLSmem, "fp16 x 2 stages exceed the budget");
 
 struct LinEpi {
   const float* bias;  // [N] or null
@@ -183,9 +254,19 @@ struct LinEpi {
   float* out;         // [splits][M, ldo] fp32
   int64_t ldo;
   int splits;         // K cut into `splits` ranges (>= 1), one output slab each
-  __nv_bfloat16* planes;  // optional: the result again as bf16 planes [3][M][pl_ld] (the next layer's operand)
+  __nv_bfloat16* planes;  // optional (bf16 x 3 only): the result again as planes [3][M][pl_ld] (next layer's operand)
   int64_t pl_ld, pl_plane;
+  const float* scale_a;   // fp16 x 2 only: the power-of-two scales the operands were split with (device words)
+  const float* scale_b;
 };
+
+// acc = main + correction.  bf16 x 3: plain sum.  fp16 x 2: the correction accumulator holds 2^11 (A0 B1 + A1 B0) of
+// the SCALED operands; inv_a / inv_b (exact powers of two) undo the operand scales.
+template <int NP>
+__device__ __forceinline__ float lin_combine(float main_acc, float corr_acc, float inv_a, float inv_b) {
+  if (NP == 3) return main_acc + corr_acc;
+  return (fmaf(corr_acc, kH2SecondInv, main_acc) * inv_a) * inv_b;
+}
 
 struct LinMaps {
   CUtensorMap a, b;  // 3-D: K-major (k, row, plane) or MN-major (mn, k row, plane)
@@ -219,9 +300,11 @@ __device__ __forceinline__ uint64_t make_sw128_mn32_desc(const void* smem_tile) 
 // MN_MAJOR = true : operands are MN-major planes [3][K][M or N] — the reduction dimension is the ROW of the stored
 //                   matrices, which is how activations and gradients already lie for dW = g^T x (K = batch): the
 //                   tensor core reads them transposed straight from shared memory, no transpose pass.
-template <bool MN_MAJOR>
+template <bool MN_MAJOR, int NP>
 __global__ void __launch_bounds__(kLThreads, 1)
 gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, LinEpi ep) {
+  constexpr int kLStages = LinCfg<NP>::kStages;
+  constexpr uint32_t kLStageBytes = LinCfg<NP>::kStageBytes;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kLStages * kLStageBytes);
@@ -276,10 +359,10 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
           mbar_wait(&empty[s], ((kbg / kLStages) & 1) ^ 1);
           mbar_arrive_expect_tx(&full[s], kLStageBytes);
           unsigned char* sa = smem + (size_t)s * kLStageBytes;
-          unsigned char* sb = sa + 3 * kLTileA;
+          unsigned char* sb = sa + NP * kLTileA;
           const int k0 = (kb0 + kb) * kLBK;
 #pragma unroll
-          for (int p = 0; p < 3; ++p) {
+          for (int p = 0; p < NP; ++p) {
             if (MN_MAJOR) {  // boxes of 64 (mn) x 32 (k rows), 4 KB each: 2 per A tile, 4 per B tile
 #pragma unroll
               for (int j = 0; j < kLBM / 64; ++j)
@@ -310,7 +393,7 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
         const int mn = tile % mn_tiles;
         const int n0 = (mn / tiles_m) * kLBN;
         const int n_eff = min(kLBN, (N - n0 + 15) & ~15);  // the last column tile issues narrower MMAs
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_eff >> 3) << 17) |
+        const uint32_t idesc = LinCfg<NP>::kIdescFmt | ((uint32_t)(n_eff >> 3) << 17) |
                                ((uint32_t)(kLBM >> 4) << 24) | (MN_MAJOR ? ((1u << 15) | (1u << 16)) : 0u);
         const int kb0 = (tile / mn_tiles) * kb_per_split, num_kb = max(0, min(total_kb - kb0, kb_per_split));
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
@@ -318,10 +401,10 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
           mbar_wait(&full[s], (kbg / kLStages) & 1);
           tcgen05_fence_after();
           unsigned char* sa = smem + (size_t)s * kLStageBytes;
-          unsigned char* sb = sa + 3 * kLTileA;
-          uint64_t ad[3], bd[3];
+          unsigned char* sb = sa + NP * kLTileA;
+          uint64_t ad[NP], bd[NP];
 #pragma unroll
-          for (int p = 0; p < 3; ++p) {
+          for (int p = 0; p < NP; ++p) {
             ad[p] = MN_MAJOR ? make_sw128_mn32_desc(sa + (size_t)p * kLTileA) : make_sw64_desc(sa + (size_t)p * kLTileA);
             bd[p] = MN_MAJOR ? make_sw128_mn32_desc(sb + (size_t)p * kLTileB) : make_sw64_desc(sb + (size_t)p * kLTileB);
           }
@@ -330,11 +413,16 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
             // K-major: +32 bytes per K=16 slice inside the swizzled row; MN-major: 16 k-rows of 128 bytes = +2048 bytes
             const uint64_t o = MN_MAJOR ? (uint64_t)(k * 128) : (uint64_t)(k * 2);
             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            umma_bf16(tmem_c, ad[0] + o, bd[2] + o, idesc, acc);  // smallest pairs first
-            umma_bf16(tmem_c, ad[2] + o, bd[0] + o, idesc, 1u);
-            umma_bf16(tmem_c, ad[1] + o, bd[1] + o, idesc, 1u);
-            umma_bf16(tmem_c, ad[0] + o, bd[1] + o, idesc, 1u);
-            umma_bf16(tmem_c, ad[1] + o, bd[0] + o, idesc, 1u);
+            if (NP == 3) {
+              umma_bf16(tmem_c, ad[0] + o, bd[NP - 1] + o, idesc, acc);  // smallest pairs first
+              umma_bf16(tmem_c, ad[NP - 1] + o, bd[0] + o, idesc, 1u);
+              umma_bf16(tmem_c, ad[1] + o, bd[1] + o, idesc, 1u);
+              umma_bf16(tmem_c, ad[0] + o, bd[1] + o, idesc, 1u);
+              umma_bf16(tmem_c, ad[1] + o, bd[0] + o, idesc, 1u);
+            } else {  // fp16 x 2: the two cross terms (second planes carry 2^11) go to the correction accumulator
+              umma_bf16(tmem_c, ad[0] + o, bd[1] + o, idesc, acc);
+              umma_bf16(tmem_c, ad[1] + o, bd[0] + o, idesc, 1u);
+            }
             umma_bf16(tmem_d, ad[0] + o, bd[0] + o, idesc, acc);
           }
           umma_commit(&empty[s]);
@@ -348,6 +436,8 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
     const int half = e >> 2;  // 128-column half of the tile
     const int r = q * 32 + lane;
     const int et = threadIdx.x - 64;
+    const float inv_a = (NP == 2) ? 1.f / ep.scale_a[0] : 1.f;  // exact: the scales are powers of two
+    const float inv_b = (NP == 2) ? 1.f / ep.scale_b[0] : 1.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int mn = tile % mn_tiles, split = tile / mn_tiles;
@@ -371,7 +461,8 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
           tmem_ld32(tacc + kLBN + h * 32, w);  // + correction accumulator
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            v[h * 32 + j] = __float_as_uint(__uint_as_float(v[h * 32 + j]) + __uint_as_float(w[j]));
+            v[h * 32 + j] = __float_as_uint(lin_combine<NP>(__uint_as_float(v[h * 32 + j]), __uint_as_float(w[j]),
+                                                            inv_a, inv_b));
         }
       }
       tcgen05_fence_before();
@@ -393,7 +484,7 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
               t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
             }
             *reinterpret_cast<float4*>(o + j) = t;
-            if (ep.planes != nullptr) {  // pl_ld >= N rounded up to 8: the group of 4 is inside the pitch
+            if (NP == 3 && ep.planes != nullptr) {  // pl_ld >= N rounded up to 8: the group of 4 is inside the pitch
               const float tv[4] = {t.x, t.y, t.z, t.w};
               split3_store4(tv, ep.planes + (int64_t)row * ep.pl_ld + col0 + j, ep.pl_plane);
             }
@@ -457,12 +548,14 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // remote a
 }
 
 // BK = K elements per stage: 32 (64-byte swizzle, 4 stages of 48 KB) or 64 (128-byte swizzle, 2 stages of 96 KB)
-template <bool MN_MAJOR, int BK>
+template <bool MN_MAJOR, int BK, int NP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
 gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, LinEpi ep) {
-  constexpr int k2Stages = BK == 64 ? 2 : K2_STAGES;
-  constexpr uint32_t k2Tile = 128 * BK * 2;     // any plane tile: 128 rows (or 2 boxes of 64 mn) x BK bf16
-  constexpr uint32_t k2StageBytes = 6 * k2Tile; // A0 A1 A2 B0 B1 B2 (B = this CTA's half)
+  // bf16 x 3: 6 tiles per stage (48 / 96 KB) -> 4 / 2 stages; fp16 x 2: 4 tiles (32 / 64 KB) -> 6 / 3 stages
+  constexpr int k2Stages = NP == 3 ? (BK == 64 ? 2 : K2_STAGES) : (BK == 64 ? 3 : 6);
+  constexpr uint32_t k2Tile = 128 * BK * 2;     // any plane tile: 128 rows (or 2 boxes of 64 mn) x BK 16-bit elements
+  constexpr uint32_t k2StageBytes = 2 * NP * k2Tile; // A planes, then B planes (B = this CTA's half)
+  static_assert((size_t)k2Stages * k2StageBytes + 3072 <= k2Smem, "stages exceed the shared-memory budget");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)k2Stages * k2StageBytes);
@@ -520,10 +613,10 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
           mbar_wait(&empty[s], ((kbg / k2Stages) & 1) ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * k2StageBytes);  // both CTAs' bytes land on the leader
           unsigned char* sa = smem + (size_t)s * k2StageBytes;
-          unsigned char* sb = sa + 3 * k2Tile;
+          unsigned char* sb = sa + NP * k2Tile;
           const int k0 = (kb0 + kb) * BK;
 #pragma unroll
-          for (int p = 0; p < 3; ++p) {
+          for (int p = 0; p < NP; ++p) {
             if (MN_MAJOR) {
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
@@ -549,7 +642,7 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
         const int mn = tile % mn_tiles;
         const int n0 = (mn / tiles_m) * 256;
         const int n_eff = min(256, (N - n0 + 15) & ~15);
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_eff >> 3) << 17) |
+        const uint32_t idesc = LinCfg<NP>::kIdescFmt | ((uint32_t)(n_eff >> 3) << 17) |
                                ((uint32_t)(256 >> 4) << 24) | (MN_MAJOR ? ((1u << 15) | (1u << 16)) : 0u);
         const int kb0 = (tile / mn_tiles) * kb_per_split, num_kb = max(0, min(total_kb - kb0, kb_per_split));
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
@@ -557,10 +650,10 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
           mbar_wait(&full[s], (kbg / k2Stages) & 1);
           tcgen05_fence_after();
           unsigned char* sa = smem + (size_t)s * k2StageBytes;
-          unsigned char* sb = sa + 3 * k2Tile;
-          uint64_t ad[3], bd[3];
+          unsigned char* sb = sa + NP * k2Tile;
+          uint64_t ad[NP], bd[NP];
 #pragma unroll
-          for (int p = 0; p < 3; ++p) {
+          for (int p = 0; p < NP; ++p) {
             const void* pa = sa + (size_t)p * k2Tile;
             const void* pb = sb + (size_t)p * k2Tile;
             if (BK == 64) {
@@ -575,11 +668,16 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
           for (int k = 0; k < BK / kLUmmaK; ++k) {
             const uint64_t o = MN_MAJOR ? (uint64_t)(k * 128) : (uint64_t)(k * 2);
             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            umma_bf16_2sm(tmem_c, ad[0] + o, bd[2] + o, idesc, acc);
-            umma_bf16_2sm(tmem_c, ad[2] + o, bd[0] + o, idesc, 1u);
-            umma_bf16_2sm(tmem_c, ad[1] + o, bd[1] + o, idesc, 1u);
-            umma_bf16_2sm(tmem_c, ad[0] + o, bd[1] + o, idesc, 1u);
-            umma_bf16_2sm(tmem_c, ad[1] + o, bd[0] + o, idesc, 1u);
+            if (NP == 3) {
+              umma_bf16_2sm(tmem_c, ad[0] + o, bd[NP - 1] + o, idesc, acc);
+              umma_bf16_2sm(tmem_c, ad[NP - 1] + o, bd[0] + o, idesc, 1u);
+              umma_bf16_2sm(tmem_c, ad[1] + o, bd[1] + o, idesc, 1u);
+              umma_bf16_2sm(tmem_c, ad[0] + o, bd[1] + o, idesc, 1u);
+              umma_bf16_2sm(tmem_c, ad[1] + o, bd[0] + o, idesc, 1u);
+            } else {
+              umma_bf16_2sm(tmem_c, ad[0] + o, bd[1] + o, idesc, acc);
+              umma_bf16_2sm(tmem_c, ad[1] + o, bd[0] + o, idesc, 1u);
+            }
             umma_bf16_2sm(tmem_d, ad[0] + o, bd[0] + o, idesc, acc);
           }
           umma_commit_2sm(&empty[s]);
@@ -593,6 +691,8 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
     const int half = e >> 2;
     const int r = q * 32 + lane;
     const int et = threadIdx.x - 64;
+    const float inv_a = (NP == 2) ? 1.f / ep.scale_a[0] : 1.f;
+    const float inv_b = (NP == 2) ? 1.f / ep.scale_b[0] : 1.f;
     int it = 0;
     for (int tile = cid; tile < n_tiles; tile += n_clusters, ++it) {
       const int mn = tile % mn_tiles, split = tile / mn_tiles;
@@ -616,7 +716,8 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
           tmem_ld32(tacc + 256 + h * 32, w);
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            v[h * 32 + j] = __float_as_uint(__uint_as_float(v[h * 32 + j]) + __uint_as_float(w[j]));
+            v[h * 32 + j] = __float_as_uint(lin_combine<NP>(__uint_as_float(v[h * 32 + j]), __uint_as_float(w[j]),
+                                                            inv_a, inv_b));
         }
       }
       tcgen05_fence_before();
@@ -638,7 +739,7 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
               t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
             }
             *reinterpret_cast<float4*>(o + j) = t;
-            if (ep.planes != nullptr) {  // pl_ld >= N rounded up to 8: the group of 4 is inside the pitch
+            if (NP == 3 && ep.planes != nullptr) {  // pl_ld >= N rounded up to 8: the group of 4 is inside the pitch
               const float tv[4] = {t.x, t.y, t.z, t.w};
               split3_store4(tv, ep.planes + (int64_t)row * ep.pl_ld + col0 + j, ep.pl_plane);
             }
@@ -656,14 +757,15 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
 
 // K-major operand: 3-D bf16 map over planes [3][rows][ld]: dims (cols, rows, 3), box 32 x box_rows x 1, 64B swizzle
 static int make_map3(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int64_t plane,
-                     int box_rows, int bk = kLBK) {
+                     int box_rows, int bk, int np) {
   EncodeTiledFn enc = get_encode();
   PTREC_CHECK_ARG(enc != nullptr, PTREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 3};
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)np};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
   cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, np == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                   const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -673,14 +775,15 @@ static int make_map3(CUtensorMap* map, const void* base, int64_t rows, int64_t c
 
 // MN-major operand: planes [3][k_rows][ld] with the M/N dimension contiguous; box 64 (mn) x 32 (k rows) x 1
 static int make_map3_mn(CUtensorMap* map, const void* base, int64_t k_rows, int64_t mn, int64_t ld, int64_t plane,
-                        int bk = kLBK) {
+                        int bk, int np) {
   EncodeTiledFn enc = get_encode();
   PTREC_CHECK_ARG(enc != nullptr, PTREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[3] = {(cuuint64_t)mn, (cuuint64_t)k_rows, 3};
+  cuuint64_t dims[3] = {(cuuint64_t)mn, (cuuint64_t)k_rows, (cuuint64_t)np};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
   cuuint32_t box[3] = {64, (cuuint32_t)bk, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, np == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                   const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PTREC_CHECK_ARG(r == CUDA_SUCCESS, PTREC_ECUDA, "cuTensorMapEncodeTiled(3d, mn-major) failed (%d)", (int)r);
@@ -691,39 +794,75 @@ static int make_map3_mn(CUtensorMap* map, const void* base, int64_t k_rows, int6
 
 using namespace ptrec;
 
+constexpr int kAbsmaxMaxParts = 1024;  // CTAs of absmax_kernel (one partial maximum each)
+
 extern "C" size_t ptrec_tc_split3_workspace_bytes(int64_t R, int64_t C) {
   return align_up((size_t)(ceil_div(R, kSpTile) * C) * sizeof(float) + 16, 256);
 }
+extern "C" size_t ptrec_tc_split2h_workspace_bytes(int64_t R, int64_t C) {
+  return ptrec_tc_split3_workspace_bytes(R, C) + kAbsmaxMaxParts * sizeof(float);
+}
 
-extern "C" int ptrec_tc_split3(const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref,
-                               int64_t ld_ref, void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld,
-                               float* colsum, void* workspace, size_t workspace_bytes, void* stream) {
-  PTREC_CHECK_ARG(src != nullptr && (planes || planes_t || colsum), PTREC_EINVAL, "tc_split3: null pointer");
+// np = 3: bf16 x 3 planes; np = 2: fp16 x 2 planes of src * scale (scale_out receives the power-of-two scale)
+static int split_impl(int np, const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref, int64_t ld_ref,
+                      void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld, float* colsum, float* scale_out,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  PTREC_CHECK_ARG(src != nullptr && (planes || planes_t || colsum), PTREC_EINVAL, "tc_split: null pointer");
   PTREC_CHECK_ARG(R >= 1 && C >= 1 && R < (1ll << 31) && C < (1ll << 31) && ld >= C, PTREC_EINVAL,
-                  "tc_split3: bad shape R=%lld C=%lld ld=%lld", (long long)R, (long long)C, (long long)ld);
+                  "tc_split: bad shape R=%lld C=%lld ld=%lld", (long long)R, (long long)C, (long long)ld);
   PTREC_CHECK_ARG(!planes || (pl_ld % 8 == 0 && pl_ld >= C && aligned16(planes)), PTREC_EALIGN,
-                  "tc_split3: plane pitch must be a multiple of 8 elements >= C, base 16-byte aligned");
+                  "tc_split: plane pitch must be a multiple of 8 elements >= C, base 16-byte aligned");
   PTREC_CHECK_ARG(!planes_t || (pt_ld % 8 == 0 && pt_ld >= R && aligned16(planes_t)), PTREC_EALIGN,
-                  "tc_split3: transposed plane pitch must be a multiple of 8 elements >= R, base 16-byte aligned");
-  PTREC_CHECK_ARG(!relu_ref || ld_ref >= C, PTREC_EINVAL, "tc_split3: bad ld_ref");
-  PTREC_CHECK_ARG(!colsum || (workspace && workspace_bytes >= ptrec_tc_split3_workspace_bytes(R, C)), PTREC_EWORKSPACE,
-                  "tc_split3: workspace too small for the column sums");
+                  "tc_split: transposed plane pitch must be a multiple of 8 elements >= R, base 16-byte aligned");
+  PTREC_CHECK_ARG(!relu_ref || ld_ref >= C, PTREC_EINVAL, "tc_split: bad ld_ref");
+  const size_t need = np == 2 ? ptrec_tc_split2h_workspace_bytes(R, C) : ptrec_tc_split3_workspace_bytes(R, C);
+  PTREC_CHECK_ARG(!(colsum || np == 2) || (workspace && workspace_bytes >= need), PTREC_EWORKSPACE,
+                  "tc_split: workspace too small (%zu < %zu)", workspace_bytes, need);
+  PTREC_CHECK_ARG(np == 3 || scale_out != nullptr, PTREC_EINVAL, "tc_split2h: scale_out is null");
   cudaStream_t st = (cudaStream_t)stream;
   Split3Args a;
   a.src = src; a.ld = ld; a.R = (int)R; a.C = (int)C; a.ref = relu_ref; a.ld_ref = ld_ref;
-  a.planes = reinterpret_cast<__nv_bfloat16*>(planes); a.pl_ld = pl_ld; a.pl_plane = R * pl_ld;
+  a.planes = reinterpret_cast<unsigned short*>(planes); a.pl_ld = pl_ld; a.pl_plane = R * pl_ld;
   a.Cp = (int)std::min<int64_t>(pl_ld, (C + 7) / 8 * 8);
-  a.planes_t = reinterpret_cast<__nv_bfloat16*>(planes_t); a.pt_ld = pt_ld; a.pt_plane = C * pt_ld;
+  a.planes_t = reinterpret_cast<unsigned short*>(planes_t); a.pt_ld = pt_ld; a.pt_plane = C * pt_ld;
   a.Rp = (int)std::min<int64_t>(pt_ld, (R + 7) / 8 * 8);
   a.colsum_part = colsum ? reinterpret_cast<float*>(workspace) : nullptr;
+  a.absmax_part = nullptr; a.n_part = 0; a.scale_out = scale_out;
   dim3 grid((unsigned)ceil_div(C, kSpTile), (unsigned)ceil_div(R, kSpTile));
-  split3_kernel<<<grid, kSpThreads, 0, st>>>(a);
-  PTREC_LAUNCH_CHECK("split3_kernel");
+  if (np == 2) {
+    float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) +
+                                           ptrec_tc_split3_workspace_bytes(R, C));
+    // 16 float4 per thread keeps ~8 loads in flight per thread; at most kAbsmaxMaxParts CTAs
+    const int64_t want = ceil_div(R * ceil_div(C, (int64_t)4), (int64_t)256 * 16);
+    const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(want, kAbsmaxMaxParts));
+    absmax_kernel<<<parts, 256, 0, st>>>(src, ld, (int)R, (int)C, part);
+    PTREC_LAUNCH_CHECK("absmax_kernel");
+    a.absmax_part = part; a.n_part = parts;
+    split_kernel<2><<<grid, kSpThreads, 0, st>>>(a);
+  } else {
+    split_kernel<3><<<grid, kSpThreads, 0, st>>>(a);
+  }
+  PTREC_LAUNCH_CHECK("split_kernel");
   if (colsum) {
     colsum_reduce_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>(a.colsum_part, (int)grid.y, (int)C, colsum);
     PTREC_LAUNCH_CHECK("colsum_reduce_kernel");
   }
   return PTREC_OK;
+}
+
+extern "C" int ptrec_tc_split3(const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref,
+                               int64_t ld_ref, void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld,
+                               float* colsum, void* workspace, size_t workspace_bytes, void* stream) {
+  return split_impl(3, src, ld, R, C, relu_ref, ld_ref, planes, pl_ld, planes_t, pt_ld, colsum, nullptr, workspace,
+                    workspace_bytes, stream);
+}
+
+extern "C" int ptrec_tc_split2h(const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref,
+                                int64_t ld_ref, void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld,
+                                float* colsum, float* scale_out, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  return split_impl(2, src, ld, R, C, relu_ref, ld_ref, planes, pl_ld, planes_t, pt_ld, colsum, scale_out, workspace,
+                    workspace_bytes, stream);
 }
 
 static int g_tc_bk = 32;
@@ -749,26 +888,73 @@ extern "C" int32_t ptrec_tc_gemm_split3_default_splits(int64_t M, int64_t N, int
   return (int32_t)std::min<int64_t>(s, 64);
 }
 
-static int gemm_split3_impl(bool mn_major, const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N,
-                            int64_t ldb, int64_t K, const float* bias, int32_t relu, float* out, int64_t ldo,
-                            void* out_planes, int64_t out_planes_ld, int32_t splits, void* workspace,
-                            size_t workspace_bytes, void* stream) {
-  PTREC_CHECK_ARG(a_planes && b_planes && out, PTREC_EINVAL, "tc_gemm_split3: null pointer");
+template <int NP>
+static int gemm_launch(bool mn_major, bool two_sm, int bk, int sms, const LinMaps& maps, int64_t M, int64_t N, int64_t K,
+                       const LinEpi& ep, float* out, cudaStream_t st) {
+  static bool attr_set = false;  // one flag per plane count
+  if (!attr_set) {
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_kernel<false, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem));
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_kernel<true, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem));
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<false, 32, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<true, 32, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<false, 64, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<true, 64, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
+    attr_set = true;
+  }
+  const int splits = ep.splits;
+  if (two_sm) {
+    const int64_t pair_tiles = ceil_div(N, 256) * ceil_div(M, 256) * splits;
+    const int64_t clusters = std::min<int64_t>(pair_tiles, sms / 2);
+    const unsigned grid2 = (unsigned)(2 * clusters);
+    if (mn_major && bk == 64)
+      gemm_split3_2sm_kernel<true, 64, NP><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+    else if (mn_major)
+      gemm_split3_2sm_kernel<true, 32, NP><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+    else if (bk == 64)
+      gemm_split3_2sm_kernel<false, 64, NP><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+    else
+      gemm_split3_2sm_kernel<false, 32, NP><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+    PTREC_LAUNCH_CHECK("gemm_split3_2sm_kernel");
+  } else {
+    const int64_t tiles = ceil_div(N, kLBN) * ceil_div(M, kLBM) * splits;
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    if (mn_major)
+      gemm_split3_kernel<true, NP><<<grid, kLThreads, kLSmem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+    else
+      gemm_split3_kernel<false, NP><<<grid, kLThreads, kLSmem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+    PTREC_LAUNCH_CHECK("gemm_split3_kernel");
+  }
+  if (splits > 1) {
+    const int64_t n = M * ep.ldo;
+    partial_reduce_kernel<<<(unsigned)ceil_div(n / 4, 256), 256, 0, st>>>(ep.out, splits, n, out);
+    PTREC_LAUNCH_CHECK("partial_reduce_kernel");
+  }
+  return PTREC_OK;
+}
+
+static int gemm_split_impl(int np, bool mn_major, const void* a_planes, const float* scale_a, int64_t M, int64_t lda,
+                           const void* b_planes, const float* scale_b, int64_t N, int64_t ldb, int64_t K,
+                           const float* bias, int32_t relu, float* out, int64_t ldo, void* out_planes,
+                           int64_t out_planes_ld, int32_t splits, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  PTREC_CHECK_ARG(a_planes && b_planes && out, PTREC_EINVAL, "tc_gemm_split: null pointer");
+  PTREC_CHECK_ARG(np == 3 || (scale_a && scale_b), PTREC_EINVAL, "tc_gemm_split2h: null operand scale");
   PTREC_CHECK_ARG(M >= 1 && N >= 1 && K >= 1 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), PTREC_EINVAL,
-                  "tc_gemm_split3: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+                  "tc_gemm_split: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   PTREC_CHECK_ARG(aligned16(a_planes) && aligned16(b_planes) && aligned16(out) && lda % 8 == 0 && ldb % 8 == 0 &&
                       lda >= (mn_major ? M : K) && ldb >= (mn_major ? N : K) && ldo % 4 == 0 && ldo >= (N + 3) / 4 * 4,
-                  PTREC_EALIGN, "tc_gemm_split3: pitches must be multiples of 8 (planes) / 4 (out) elements");
+                  PTREC_EALIGN, "tc_gemm_split: pitches must be multiples of 8 (planes) / 4 (out) elements");
   if (splits < 1) splits = 1;
   const int total_kb = (int)ceil_div(K, (g_tc_2sm ? g_tc_bk : kLBK));
   if (splits > total_kb) splits = total_kb;
   while (splits > 1 && (int64_t)(splits - 1) * ceil_div(total_kb, splits) >= total_kb) --splits;  // no empty split
   PTREC_CHECK_ARG(splits == 1 || (!bias && !relu && !out_planes), PTREC_EINVAL,
-                  "tc_gemm_split3: split-K has no bias / ReLU / planes epilogue");
-  PTREC_CHECK_ARG(!out_planes || (aligned16(out_planes) && out_planes_ld % 8 == 0 && out_planes_ld >= (N + 3) / 4 * 4),
-                  PTREC_EALIGN, "tc_gemm_split3: output plane pitch must be a multiple of 8 >= N");
+                  "tc_gemm_split: split-K has no bias / ReLU / planes epilogue");
+  PTREC_CHECK_ARG(!out_planes || (np == 3 && aligned16(out_planes) && out_planes_ld % 8 == 0 &&
+                                  out_planes_ld >= (N + 3) / 4 * 4),
+                  PTREC_EALIGN, "tc_gemm_split: output planes need bf16 x 3 and a pitch that is a multiple of 8 >= N");
   PTREC_CHECK_ARG(splits == 1 || (workspace && workspace_bytes >= ptrec_tc_gemm_split3_workspace_bytes(M, ldo, splits)),
-                  PTREC_EWORKSPACE, "tc_gemm_split3: workspace too small for %d split-K partials", splits);
+                  PTREC_EWORKSPACE, "tc_gemm_split: workspace too small for %d split-K partials", splits);
   cudaStream_t st = (cudaStream_t)stream;
   LinMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -777,72 +963,48 @@ static int gemm_split3_impl(bool mn_major, const void* a_planes, int64_t M, int6
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const bool two_sm = g_tc_2sm != 0 && sms >= 2;
   const int bk = two_sm ? g_tc_bk : kLBK;
-  int rc = mn_major ? make_map3_mn(&maps.a, a_planes, K, M, lda, K * lda, bk)
-                    : make_map3(&maps.a, a_planes, M, K, lda, M * lda, kLBM, bk);
+  int rc = mn_major ? make_map3_mn(&maps.a, a_planes, K, M, lda, K * lda, bk, np)
+                    : make_map3(&maps.a, a_planes, M, K, lda, M * lda, kLBM, bk, np);
   if (rc != PTREC_OK) return rc;
-  rc = mn_major ? make_map3_mn(&maps.b, b_planes, K, N, ldb, K * ldb, bk)
-                : make_map3(&maps.b, b_planes, N, K, ldb, N * ldb, two_sm ? 128 : kLBN, bk);
+  rc = mn_major ? make_map3_mn(&maps.b, b_planes, K, N, ldb, K * ldb, bk, np)
+                : make_map3(&maps.b, b_planes, N, K, ldb, N * ldb, two_sm ? 128 : kLBN, bk, np);
   if (rc != PTREC_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem));
-    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem));
-    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
-    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
-    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
-    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
-    attr_set = true;
-  }
   LinEpi ep;
   ep.bias = bias; ep.relu = relu; ep.ldo = ldo; ep.splits = splits;
   ep.planes = reinterpret_cast<__nv_bfloat16*>(out_planes); ep.pl_ld = out_planes_ld; ep.pl_plane = M * out_planes_ld;
   ep.out = splits > 1 ? reinterpret_cast<float*>(workspace) : out;
-  if (two_sm) {
-    const int64_t pair_tiles = ceil_div(N, 256) * ceil_div(M, 256) * splits;
-    const int64_t clusters = std::min<int64_t>(pair_tiles, sms / 2);
-    const unsigned grid2 = (unsigned)(2 * clusters);
-    if (mn_major && bk == 64)
-      gemm_split3_2sm_kernel<true, 64><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
-    else if (mn_major)
-      gemm_split3_2sm_kernel<true, 32><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
-    else if (bk == 64)
-      gemm_split3_2sm_kernel<false, 64><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
-    else
-      gemm_split3_2sm_kernel<false, 32><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
-    PTREC_LAUNCH_CHECK("gemm_split3_2sm_kernel");
-    if (splits > 1) {
-      const int64_t n = M * ldo;
-      partial_reduce_kernel<<<(unsigned)ceil_div(n / 4, 256), 256, 0, st>>>(ep.out, splits, n, out);
-      PTREC_LAUNCH_CHECK("partial_reduce_kernel");
-    }
-    return PTREC_OK;
-  }
-  const int64_t tiles = ceil_div(N, kLBN) * ceil_div(M, kLBM) * splits;
-  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  if (mn_major)
-    gemm_split3_kernel<true><<<grid, kLThreads, kLSmem, st>>>(maps, (int)M, (int)N, (int)K, ep);
-  else
-    gemm_split3_kernel<false><<<grid, kLThreads, kLSmem, st>>>(maps, (int)M, (int)N, (int)K, ep);
-  PTREC_LAUNCH_CHECK("gemm_split3_kernel");
-  if (splits > 1) {
-    const int64_t n = M * ldo;
-    partial_reduce_kernel<<<(unsigned)ceil_div(n / 4, 256), 256, 0, st>>>(ep.out, splits, n, out);
-    PTREC_LAUNCH_CHECK("partial_reduce_kernel");
-  }
-  return PTREC_OK;
+  ep.scale_a = scale_a; ep.scale_b = scale_b;
+  return np == 3 ? gemm_launch<3>(mn_major, two_sm, bk, sms, maps, M, N, K, ep, out, st)
+                 : gemm_launch<2>(mn_major, two_sm, bk, sms, maps, M, N, K, ep, out, st);
 }
 
 extern "C" int ptrec_tc_gemm_split3(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N,
                                     int64_t ldb, int64_t K, const float* bias, int32_t relu, float* out, int64_t ldo,
                                     void* out_planes, int64_t out_planes_ld, int32_t splits, void* workspace,
                                     size_t workspace_bytes, void* stream) {
-  return gemm_split3_impl(false, a_planes, M, lda, b_planes, N, ldb, K, bias, relu, out, ldo, out_planes, out_planes_ld,
-                          splits, workspace, workspace_bytes, stream);
+  return gemm_split_impl(3, false, a_planes, nullptr, M, lda, b_planes, nullptr, N, ldb, K, bias, relu, out, ldo,
+                         out_planes, out_planes_ld, splits, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ptrec_tc_gemm_split3_tn(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N,
                                        int64_t ldb, int64_t K, float* out, int64_t ldo, int32_t splits, void* workspace,
                                        size_t workspace_bytes, void* stream) {
-  return gemm_split3_impl(true, a_planes, M, lda, b_planes, N, ldb, K, nullptr, 0, out, ldo, nullptr, 0, splits,
-                          workspace, workspace_bytes, stream);
+  return gemm_split_impl(3, true, a_planes, nullptr, M, lda, b_planes, nullptr, N, ldb, K, nullptr, 0, out, ldo, nullptr,
+                         0, splits, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ptrec_tc_gemm_split2h(const void* a_planes, const float* scale_a, int64_t M, int64_t lda,
+                                     const void* b_planes, const float* scale_b, int64_t N, int64_t ldb, int64_t K,
+                                     const float* bias, int32_t relu, float* out, int64_t ldo, int32_t splits,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  return gemm_split_impl(2, false, a_planes, scale_a, M, lda, b_planes, scale_b, N, ldb, K, bias, relu, out, ldo,
+                         nullptr, 0, splits, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ptrec_tc_gemm_split2h_tn(const void* a_planes, const float* scale_a, int64_t M, int64_t lda,
+                                        const void* b_planes, const float* scale_b, int64_t N, int64_t ldb, int64_t K,
+                                        float* out, int64_t ldo, int32_t splits, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  return gemm_split_impl(2, true, a_planes, scale_a, M, lda, b_planes, scale_b, N, ldb, K, nullptr, 0, out, ldo,
+                         nullptr, 0, splits, workspace, workspace_bytes, stream);
 }

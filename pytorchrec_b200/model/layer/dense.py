@@ -6,7 +6,9 @@
 On a CUDA device the Linear -> ReLU pair and its backward run on the tcgen05 tensor cores through K6
 (csrc/tc_linear.cu): every fp32 operand is split exactly into three bf16 planes and the product is accumulated in
 fp32 from the six significant plane pairs, which keeps fp32-level error (the reference computes these GEMMs in
-fp32 and the north star asks for 1e-5) at 3-5x the speed of the fp32 SIMT sgemm behind ``nn.Linear``.  The ReLU
+fp32 and the north star asks for 1e-5) at 3-5x the speed of the fp32 SIMT sgemm behind ``nn.Linear``.
+``PTREC_TC_MODE=fp16x2`` (``ops.set_tc_mode``) selects the two-plane fp16 operand format instead: a per-tensor
+power-of-two scale, 22 mantissa bits, half the MMAs and two thirds of the operand bytes (include/ptrec_b200.h).  The ReLU
 mask and the bias gradient are fused into the pass that splits the incoming gradient.  ``PTREC_TC_LINEAR=0`` selects
 the stock ``nn.Linear`` path (cuBLAS fp32) for A/B measurements."""
 import os
@@ -28,14 +30,21 @@ class _TcLinearReLU(torch.autograd.Function):
     def forward(ctx, x, weight, bias, px, emit_planes):
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         N, K = weight.shape
-        if px is None:
-            px, _, _ = ops.tc_split3(x)
-        pw, pwt, _ = ops.tc_split3(weight, want_planes=True, want_t=need_dx)
-        if emit_planes:
-            y, py = ops.tc_gemm_split3(px, pw, K, bias=bias, relu=True, want_planes=True)
+        ctx.h2 = ops.tc_mode() == "fp16x2"
+        if ctx.h2:  # two fp16 planes of the scaled operand + the device-side scale word (ops.tc_split2h)
+            px, _, _, sx = ops.tc_split2h(x)
+            pw, pwt, _, sw = ops.tc_split2h(weight, want_planes=True, want_t=need_dx)
+            y, py = ops.tc_gemm_split2h(px, sx, pw, sw, K, bias=bias, relu=True), x.new_empty(0, dtype=torch.bfloat16)
+            ctx.save_for_backward(y, px if need_dw else None, pwt, sx, sw)
         else:
-            y, py = ops.tc_gemm_split3(px, pw, K, bias=bias, relu=True), x.new_empty(0, dtype=torch.bfloat16)
-        ctx.save_for_backward(y, px if need_dw else None, pwt)
+            if px is None:
+                px, _, _ = ops.tc_split3(x)
+            pw, pwt, _ = ops.tc_split3(weight, want_planes=True, want_t=need_dx)
+            if emit_planes:
+                y, py = ops.tc_gemm_split3(px, pw, K, bias=bias, relu=True, want_planes=True)
+            else:
+                y, py = ops.tc_gemm_split3(px, pw, K, bias=bias, relu=True), x.new_empty(0, dtype=torch.bfloat16)
+            ctx.save_for_backward(y, px if need_dw else None, pwt)
         ctx.dims = (x.shape[0], N, K)
         ctx.has_bias = bias is not None
         ctx.mark_non_differentiable(py)
@@ -43,18 +52,25 @@ class _TcLinearReLU(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy, _gpy):
-        y, px, pwt = ctx.saved_tensors
         B, N, K = ctx.dims
         need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
         if gy.stride(-1) != 1:
             gy = gy.contiguous()
-        pg, _, db = ops.tc_split3(gy, relu_ref=y, want_planes=need_dx or need_dw, want_colsum=need_db)
-        dx = ops.tc_gemm_split3(pg, pwt, N) if need_dx else None                  # g W        [B, K]
         dw = None
-        if need_dw:
-            dw = ops.tc_gemm_split3_tn(pg, N, px, K)                                # g^T x      [N, K]
-            if not dw.is_contiguous():
-                dw = dw.contiguous()
+        if ctx.h2:
+            y, px, pwt, sx, sw = ctx.saved_tensors
+            pg, _, db, sg = ops.tc_split2h(gy, relu_ref=y, want_planes=need_dx or need_dw, want_colsum=need_db)
+            dx = ops.tc_gemm_split2h(pg, sg, pwt, sw, N) if need_dx else None      # g W        [B, K]
+            if need_dw:
+                dw = ops.tc_gemm_split2h_tn(pg, sg, N, px, sx, K)                   # g^T x      [N, K]
+        else:
+            y, px, pwt = ctx.saved_tensors
+            pg, _, db = ops.tc_split3(gy, relu_ref=y, want_planes=need_dx or need_dw, want_colsum=need_db)
+            dx = ops.tc_gemm_split3(pg, pwt, N) if need_dx else None                # g W        [B, K]
+            if need_dw:
+                dw = ops.tc_gemm_split3_tn(pg, N, px, K)                            # g^T x      [N, K]
+        if dw is not None and not dw.is_contiguous():
+            dw = dw.contiguous()
         return dx, dw, db, None, None
 
 
@@ -86,7 +102,8 @@ class Dense(Module):
                 x2 = x2.contiguous()
             px = getattr(x, "_ptrec_planes", None)  # written by the producer of x (K8 head / previous layer)
             if px is not None and not (x.dim() == 2 and tuple(px.shape) == (3, x2.shape[0], (x2.shape[1] + 7) // 8 * 8)
-                                       and px.device == x2.device):
+                                       and px.device == x2.device and px.dtype == torch.bfloat16
+                                       and ops.tc_mode() == "bf16x3"):
                 px = None
             y, py = _TcLinearReLU.apply(x2, w, self.linear.bias, px, self.emit_planes and x.dim() == 2)
             if self.training and self.dropout.p > 0:

@@ -87,7 +87,7 @@ def fm_head(v: Tensor, w1, x, wd, bias, want_deep_in: bool, tower_units: int = 0
     if not (v2d.stride(1) == 1 and v2d.stride(0) % 4 == 0 and v2d.data_ptr() % 16 == 0):
         v2d = v2d.contiguous()
     from . import dense
-    want_planes = (want_deep_in and tower_units > 0 and dense.tc_linear_enabled()
+    want_planes = (want_deep_in and tower_units > 0 and dense.tc_linear_enabled() and ops.tc_mode() == "bf16x3"
                    and B * (F * D + nd) * tower_units >= dense.TC_MIN_MACS)
     logit, deep_in, planes = _FMHead.apply(v2d, w1.reshape(B, F).contiguous() if w1 is not None else None,
                                            x.contiguous() if x is not None else None,

@@ -5,6 +5,7 @@ synchronises with the host.  There is no CPU path: the CPU implementation of thi
 the reference (torchrec/model/IModel.py:116-125 + nn.Embedding + torch.optim).
 """
 import ctypes
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -556,6 +557,101 @@ def tc_gemm_split3_tn(a_planes: torch.Tensor, M: int, b_planes: torch.Tensor, N:
     _lib.check(lib.ptrec_tc_gemm_split3_tn(_ptr(a_planes), M, lda, _ptr(b_planes), N, ldb, K, _ptr(out), ldo, splits,
                                            _ptr(ws), ws.numel() if ws is not None else 0, _stream(dev)),
                "ptrec_tc_gemm_split3_tn")
+    return out[:, :N] if ldo != N else out
+
+
+# ---- fp16 x 2 operand mode of K6 ("h2"): x * s = h0 + h1 / 2^11 with a per-tensor power-of-two scale s --------------
+_TC_MODES = ("bf16x3", "fp16x2")
+_tc_mode = os.environ.get("PTREC_TC_MODE", "bf16x3")
+if _tc_mode not in _TC_MODES:
+    raise ValueError(f"PTREC_TC_MODE must be one of {_TC_MODES}, got {_tc_mode!r}")
+
+
+def tc_mode() -> str:
+    """Operand format of the K6 Linear GEMMs: ``bf16x3`` (three exact bf16 planes, 6 MMAs per product) or ``fp16x2``
+    (two fp16 planes of the power-of-two-scaled operand, 3 MMAs per product; 22 mantissa bits)."""
+    return _tc_mode
+
+
+def set_tc_mode(mode: str) -> None:
+    global _tc_mode
+    if mode not in _TC_MODES:
+        raise ValueError(f"invalid K6 operand mode {mode!r}; one of {_TC_MODES}")
+    _tc_mode = mode
+
+
+def tc_split2h(src: torch.Tensor, relu_ref: Optional[torch.Tensor] = None, want_planes: bool = True,
+               want_t: bool = False, want_colsum: bool = False):
+    """fp32 [R, C] -> (planes [2, R, pad8(C)] fp16, planes_t [2, C, pad8(R)] fp16, colsum [C], scale [1] fp32).
+    ``scale`` is the power of two the tensor was multiplied by before the split (largest magnitude -> [2^13, 2^14)),
+    computed on the device from the tensor's absolute maximum; the GEMM divides it out again."""
+    lib = _lib.load()
+    _require_cuda(src, relu_ref)
+    assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1
+    R, C = src.shape
+    dev = src.device
+    if relu_ref is not None:
+        assert relu_ref.shape == src.shape and relu_ref.dtype == torch.float32 and relu_ref.stride(1) == 1
+    planes = torch.empty(2, R, _pad8(C), dtype=torch.float16, device=dev) if want_planes else None
+    planes_t = torch.empty(2, C, _pad8(R), dtype=torch.float16, device=dev) if want_t else None
+    colsum = torch.empty(C, dtype=torch.float32, device=dev) if want_colsum else None
+    scale = torch.empty(1, dtype=torch.float32, device=dev)
+    ws = _workspace("tc_split2h", lib.ptrec_tc_split2h_workspace_bytes(R, C), dev)
+    _lib.check(lib.ptrec_tc_split2h(_ptr(src), src.stride(0), R, C, _ptr(relu_ref),
+                                    relu_ref.stride(0) if relu_ref is not None else 0, _ptr(planes), _pad8(C),
+                                    _ptr(planes_t), _pad8(R), _ptr(colsum), _ptr(scale), _ptr(ws), ws.numel(),
+                                    _stream(dev)), "ptrec_tc_split2h")
+    return planes, planes_t, colsum, scale
+
+
+def _check_h2(a_planes, scale_a, b_planes, scale_b):
+    _require_cuda(a_planes, b_planes, scale_a, scale_b)
+    assert a_planes.dtype == torch.float16 and b_planes.dtype == torch.float16
+    assert a_planes.dim() == 3 and b_planes.dim() == 3 and a_planes.shape[0] == 2 and b_planes.shape[0] == 2
+    assert a_planes.is_contiguous() and b_planes.is_contiguous()
+    assert scale_a.dtype == torch.float32 and scale_b.dtype == torch.float32 and scale_a.numel() == 1 == scale_b.numel()
+
+
+def tc_gemm_split2h(a_planes: torch.Tensor, scale_a: torch.Tensor, b_planes: torch.Tensor, scale_b: torch.Tensor,
+                    K: int, bias: Optional[torch.Tensor] = None, relu: bool = False, splits: int = 1) -> torch.Tensor:
+    """out [M, N] fp32 = A[M, K] B[N, K]^T (+ bias) (ReLU) from fp16 planes [2, M, lda], [2, N, ldb] and their scales."""
+    lib = _lib.load()
+    _check_h2(a_planes, scale_a, b_planes, scale_b)
+    M, lda = a_planes.shape[1], a_planes.shape[2]
+    N, ldb = b_planes.shape[1], b_planes.shape[2]
+    dev = a_planes.device
+    if splits == 0:
+        splits = lib.ptrec_tc_gemm_split3_default_splits(M, N, K)
+    ldo = (N + 3) // 4 * 4
+    out = torch.empty(M, ldo, dtype=torch.float32, device=dev)
+    nbytes = lib.ptrec_tc_gemm_split3_workspace_bytes(M, ldo, splits)
+    ws = _workspace("tc_gemm_split3", nbytes, dev) if nbytes else None
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
+    _lib.check(lib.ptrec_tc_gemm_split2h(_ptr(a_planes), _ptr(scale_a), M, lda, _ptr(b_planes), _ptr(scale_b), N, ldb, K,
+                                         _ptr(bias), int(relu), _ptr(out), ldo, splits, _ptr(ws),
+                                         ws.numel() if ws is not None else 0, _stream(dev)), "ptrec_tc_gemm_split2h")
+    return out[:, :N] if ldo != N else out
+
+
+def tc_gemm_split2h_tn(a_planes: torch.Tensor, scale_a: torch.Tensor, M: int, b_planes: torch.Tensor,
+                       scale_b: torch.Tensor, N: int, splits: int = 0) -> torch.Tensor:
+    """out [M, N] fp32 = A^T B from row-major fp16 planes A [2, K, pad8(M)], B [2, K, pad8(N)] (dW = g^T x)."""
+    lib = _lib.load()
+    _check_h2(a_planes, scale_a, b_planes, scale_b)
+    K, lda = a_planes.shape[1], a_planes.shape[2]
+    assert b_planes.shape[1] == K and lda >= M and b_planes.shape[2] >= N
+    ldb = b_planes.shape[2]
+    dev = a_planes.device
+    if splits == 0:
+        splits = lib.ptrec_tc_gemm_split3_default_splits(M, N, K)
+    ldo = (N + 3) // 4 * 4
+    out = torch.empty(M, ldo, dtype=torch.float32, device=dev)
+    nbytes = lib.ptrec_tc_gemm_split3_workspace_bytes(M, ldo, splits)
+    ws = _workspace("tc_gemm_split3", nbytes, dev) if nbytes else None
+    _lib.check(lib.ptrec_tc_gemm_split2h_tn(_ptr(a_planes), _ptr(scale_a), M, lda, _ptr(b_planes), _ptr(scale_b), N, ldb,
+                                            K, _ptr(out), ldo, splits, _ptr(ws), ws.numel() if ws is not None else 0,
+                                            _stream(dev)), "ptrec_tc_gemm_split2h_tn")
     return out[:, :N] if ldo != N else out
 
 

@@ -32,7 +32,23 @@ for K, N in ((429, 400), (400, 400), (1024, 1024)):
     t["dgrad cublas fp32"] = timeit(lambda: g @ w)
     t["wgrad tc"] = timeit(lambda: ops.tc_gemm_split3(pgt, pxt, B, splits=0))
     t["wgrad cublas fp32"] = timeit(lambda: g.t() @ x)
-    print(f"B={B} K={K} N={N}  ({fl / 1e9:.1f} GFLOP fp32-equivalent per GEMM)")
+    # fp16 x 2 operand format (3 MMAs per product, two planes)
+    hx, _, _, sx = ops.tc_split2h(x)
+    hw, hwt, _, sw = ops.tc_split2h(w, want_t=True)
+    hg, _, _, sg = ops.tc_split2h(g)
+    t["split2h(x) absmax+rm"] = timeit(lambda: ops.tc_split2h(x))
+    t["split2h(g) relu+colsum rm"] = timeit(lambda: ops.tc_split2h(g, relu_ref=g, want_colsum=True))
+    t["fwd  tc h2"] = timeit(lambda: ops.tc_gemm_split2h(hx, sx, hw, sw, K, bias=b, relu=True))
+    t["dgrad tc h2"] = timeit(lambda: ops.tc_gemm_split2h(hg, sg, hwt, sw, N))
+    t["wgrad tc h2 (tn)"] = timeit(lambda: ops.tc_gemm_split2h_tn(hg, sg, N, hx, sx, K))
+    t["wgrad tc (tn)"] = timeit(lambda: ops.tc_gemm_split3_tn(pg, N, px, K))
+    ref = torch.relu(x.double() @ w.double().t() + b.double())
+    den = x.double().abs() @ w.double().abs().t() + b.double().abs()
+    e3 = ((ops.tc_gemm_split3(px, pw, K, bias=b, relu=True).double() - ref).abs() / den).max().item()
+    e2 = ((ops.tc_gemm_split2h(hx, sx, hw, sw, K, bias=b, relu=True).double() - ref).abs() / den).max().item()
+    ef = ((torch.relu(torch.nn.functional.linear(x, w, b)).double() - ref).abs() / den).max().item()
+    print(f"B={B} K={K} N={N}  ({fl / 1e9:.1f} GFLOP fp32-equivalent per GEMM)  max err / sum|a||b|: "
+          f"bf16x3 {e3:.2e}  fp16x2 {e2:.2e}  cublas fp32 {ef:.2e}")
     for k, v in t.items():
-        extra = f"  {fl / v / 1e6:7.1f} TFLOP/s fp32-equiv ({6 * fl / v / 1e6:7.1f} bf16)" if "tc" in k or "cublas" in k else ""
+        extra = f"  {fl / v / 1e6:7.1f} TFLOP/s fp32-equiv" if "tc" in k or "cublas" in k else ""
         print(f"  {k:34s} {v:8.1f} us{extra}")
