@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 16
+#define PTREC_ABI_VERSION 17
 
 /* error codes */
 #define PTREC_OK 0
@@ -404,16 +404,20 @@ int ptrec_tc_gemm_split3_tn(const void* a_planes, int64_t M, int64_t lda, const 
  *   device word, read by the GEMMs on the device: no host synchronisation).  s comes from the absolute maximum of src
  *   (before the relu_ref mask), found by a first kernel of the same call.  workspace: ptrec_tc_split2h_workspace_bytes
  *   (always needed).
+ *   absmax_in (or NULL): one device word holding max |src| already (written by the GEMM that produced src, below);
+ *   the call then skips its own pass over src.
  * ptrec_tc_gemm_split2h / _tn: as ptrec_tc_gemm_split3 / _tn on fp16 planes; scale_a / scale_b are the device words the
- *   two split calls wrote.  No output planes. */
+ *   two split calls wrote.  No output planes.  absmax_out (or NULL; splits == 1 only): one fp32 device word, ZERO on
+ *   entry, that the epilogue raises to max |out| (atomicMax on the bit pattern) — pass it as absmax_in when out is
+ *   split for the next GEMM. */
 size_t ptrec_tc_split2h_workspace_bytes(int64_t R, int64_t C);
 int ptrec_tc_split2h(const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref, int64_t ld_ref,
                      void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld, float* colsum, float* scale_out,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     const float* absmax_in, void* workspace, size_t workspace_bytes, void* stream);
 int ptrec_tc_gemm_split2h(const void* a_planes, const float* scale_a, int64_t M, int64_t lda, const void* b_planes,
                           const float* scale_b, int64_t N, int64_t ldb, int64_t K, const float* bias, int32_t relu,
-                          float* out, int64_t ldo, int32_t splits, void* workspace, size_t workspace_bytes,
-                          void* stream);
+                          float* out, int64_t ldo, float* absmax_out, int32_t splits, void* workspace,
+                          size_t workspace_bytes, void* stream);
 int ptrec_tc_gemm_split2h_tn(const void* a_planes, const float* scale_a, int64_t M, int64_t lda, const void* b_planes,
                              const float* scale_b, int64_t N, int64_t ldb, int64_t K, float* out, int64_t ldo,
                              int32_t splits, void* workspace, size_t workspace_bytes, void* stream);

@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libptrec_b200.so")
 
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 # enums (mirror include/ptrec_b200.h)
 F32, BF16 = 0, 1
@@ -121,10 +121,10 @@ PROTOTYPES = {
                                         c_int64, c_int32, c_void_p, c_size_t, c_void_p]),
     "ptrec_tc_split2h_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "ptrec_tc_split2h": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
-                                 c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                 c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ptrec_tc_gemm_split2h": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64,
-                                      c_int64, c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_size_t,
-                                      c_void_p]),
+                                      c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_int32, c_void_p,
+                                      c_size_t, c_void_p]),
     "ptrec_tc_gemm_split2h_tn": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64,
                                          c_int64, c_void_p, c_int64, c_int32, c_void_p, c_size_t, c_void_p]),
     "ptrec_a2a_pack_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),

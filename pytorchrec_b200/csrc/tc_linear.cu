@@ -45,31 +45,27 @@ struct Split3Args {
   float* scale_out;
 };
 
-// |src| maxima, one per CTA (no atomics: the split kernel reduces the few hundred partials itself)
+// |src| maxima, one per CTA (no atomics: the split kernel reduces the partials itself).  Warp per row, lanes stride
+// over the row's 16-byte chunks: coalesced, no index arithmetic beyond adds.
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ src, int64_t ld, int R, int C,
                                                      float* __restrict__ part) {
-  float m = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-  const int c4 = vec ? C / 4 : 0;
-  const int64_t n4 = (int64_t)R * c4;
-  const int64_t step = (int64_t)gridDim.x * 256;
+  const int c4 = vec ? (C >> 2) : 0;
+  float m = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < R; r += (int64_t)gridDim.x * 8) {
+    const float* p = src + r * ld;
 #pragma unroll 4
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += step) {
-    const int64_t r = i / c4;
-    const int c = (int)(i - r * c4);
-    const float4 t = *reinterpret_cast<const float4*>(src + r * ld + 4 * c);
-    m = fmaxf(m, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
-  }
-  const int tail = C - 4 * c4;  // the whole row when the source is not 16-byte addressable
-  const int64_t nt = (int64_t)R * tail;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nt; i += step) {
-    const int64_t r = i / tail;
-    m = fmaxf(m, fabsf(src[r * ld + 4 * c4 + (int)(i - r * tail)]));
+    for (int c = lane; c < c4; c += 32) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p) + c);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+    }
+    for (int c = 4 * c4 + lane; c < C; c += 32) m = fmaxf(m, fabsf(__ldg(p + c)));
   }
   __shared__ float s_m[8];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  if (lane == 0) s_m[warp] = m;
   __syncthreads();
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -258,6 +254,8 @@ struct LinEpi {
   int64_t pl_ld, pl_plane;
   const float* scale_a;   // fp16 x 2 only: the power-of-two scales the operands were split with (device words)
   const float* scale_b;
+  uint32_t* absmax_out;   // optional: max |out| as fp32 bits, combined with atomicMax (the caller zeroes the word); lets the
+                          // next split of `out` skip its own pass over the tensor
 };
 
 // acc = main + correction.  bf16 x 3: plain sum.  fp16 x 2: the correction accumulator holds 2^11 (A0 B1 + A1 B0) of
@@ -468,6 +466,7 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
+      float amax = 0.f;
       if (live && row < M) {
         float* o = ep.out + ((int64_t)split * M + row) * ep.ldo + col0;
         const bool has_bias = ep.bias != nullptr;
@@ -484,12 +483,18 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
               t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
             }
             *reinterpret_cast<float4*>(o + j) = t;
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
             if (NP == 3 && ep.planes != nullptr) {  // pl_ld >= N rounded up to 8: the group of 4 is inside the pitch
               const float tv[4] = {t.x, t.y, t.z, t.w};
               split3_store4(tv, ep.planes + (int64_t)row * ep.pl_ld + col0 + j, ep.pl_plane);
             }
           }
         }
+      }
+      if (ep.absmax_out != nullptr) {  // warp-uniform branch; one combining atomic per warp and tile
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if (lane == 0 && amax > 0.f) atomicMax(ep.absmax_out, __float_as_uint(amax));  // non-negative floats order as uints
       }
     }
   }
@@ -723,6 +728,7 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(acc_empty);
+      float amax = 0.f;
       if (live && row < M) {
         float* o = ep.out + ((int64_t)split * M + row) * ep.ldo + col0;
         const bool has_bias = ep.bias != nullptr;
@@ -739,12 +745,18 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
               t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
             }
             *reinterpret_cast<float4*>(o + j) = t;
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
             if (NP == 3 && ep.planes != nullptr) {  // pl_ld >= N rounded up to 8: the group of 4 is inside the pitch
               const float tv[4] = {t.x, t.y, t.z, t.w};
               split3_store4(tv, ep.planes + (int64_t)row * ep.pl_ld + col0 + j, ep.pl_plane);
             }
           }
         }
+      }
+      if (ep.absmax_out != nullptr) {  // warp-uniform branch; one combining atomic per warp and tile
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if (lane == 0 && amax > 0.f) atomicMax(ep.absmax_out, __float_as_uint(amax));  // non-negative floats order as uints
       }
     }
   }
@@ -806,7 +818,7 @@ extern "C" size_t ptrec_tc_split2h_workspace_bytes(int64_t R, int64_t C) {
 // np = 3: bf16 x 3 planes; np = 2: fp16 x 2 planes of src * scale (scale_out receives the power-of-two scale)
 static int split_impl(int np, const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref, int64_t ld_ref,
                       void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld, float* colsum, float* scale_out,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+                      const float* absmax_in, void* workspace, size_t workspace_bytes, void* stream) {
   PTREC_CHECK_ARG(src != nullptr && (planes || planes_t || colsum), PTREC_EINVAL, "tc_split: null pointer");
   PTREC_CHECK_ARG(R >= 1 && C >= 1 && R < (1ll << 31) && C < (1ll << 31) && ld >= C, PTREC_EINVAL,
                   "tc_split: bad shape R=%lld C=%lld ld=%lld", (long long)R, (long long)C, (long long)ld);
@@ -830,14 +842,16 @@ static int split_impl(int np, const float* src, int64_t ld, int64_t R, int64_t C
   a.absmax_part = nullptr; a.n_part = 0; a.scale_out = scale_out;
   dim3 grid((unsigned)ceil_div(C, kSpTile), (unsigned)ceil_div(R, kSpTile));
   if (np == 2) {
-    float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) +
-                                           ptrec_tc_split3_workspace_bytes(R, C));
-    // 16 float4 per thread keeps ~8 loads in flight per thread; at most kAbsmaxMaxParts CTAs
-    const int64_t want = ceil_div(R * ceil_div(C, (int64_t)4), (int64_t)256 * 16);
-    const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(want, kAbsmaxMaxParts));
-    absmax_kernel<<<parts, 256, 0, st>>>(src, ld, (int)R, (int)C, part);
-    PTREC_LAUNCH_CHECK("absmax_kernel");
-    a.absmax_part = part; a.n_part = parts;
+    if (absmax_in != nullptr) {  // the producer of src already reduced max |src| into one word (GEMM epilogue)
+      a.absmax_part = absmax_in; a.n_part = 1;
+    } else {
+      float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) +
+                                             ptrec_tc_split3_workspace_bytes(R, C));
+      const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(R, (int64_t)8), kAbsmaxMaxParts));
+      absmax_kernel<<<parts, 256, 0, st>>>(src, ld, (int)R, (int)C, part);  // a warp per row, <= 8192 warps
+      PTREC_LAUNCH_CHECK("absmax_kernel");
+      a.absmax_part = part; a.n_part = parts;
+    }
     split_kernel<2><<<grid, kSpThreads, 0, st>>>(a);
   } else {
     split_kernel<3><<<grid, kSpThreads, 0, st>>>(a);
@@ -853,16 +867,16 @@ static int split_impl(int np, const float* src, int64_t ld, int64_t R, int64_t C
 extern "C" int ptrec_tc_split3(const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref,
                                int64_t ld_ref, void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld,
                                float* colsum, void* workspace, size_t workspace_bytes, void* stream) {
-  return split_impl(3, src, ld, R, C, relu_ref, ld_ref, planes, pl_ld, planes_t, pt_ld, colsum, nullptr, workspace,
-                    workspace_bytes, stream);
+  return split_impl(3, src, ld, R, C, relu_ref, ld_ref, planes, pl_ld, planes_t, pt_ld, colsum, nullptr, nullptr,
+                    workspace, workspace_bytes, stream);
 }
 
 extern "C" int ptrec_tc_split2h(const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref,
                                 int64_t ld_ref, void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld,
-                                float* colsum, float* scale_out, void* workspace, size_t workspace_bytes,
-                                void* stream) {
-  return split_impl(2, src, ld, R, C, relu_ref, ld_ref, planes, pl_ld, planes_t, pt_ld, colsum, scale_out, workspace,
-                    workspace_bytes, stream);
+                                float* colsum, float* scale_out, const float* absmax_in, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  return split_impl(2, src, ld, R, C, relu_ref, ld_ref, planes, pl_ld, planes_t, pt_ld, colsum, scale_out, absmax_in,
+                    workspace, workspace_bytes, stream);
 }
 
 static int g_tc_bk = 32;
@@ -935,8 +949,8 @@ static int gemm_launch(bool mn_major, bool two_sm, int bk, int sms, const LinMap
 static int gemm_split_impl(int np, bool mn_major, const void* a_planes, const float* scale_a, int64_t M, int64_t lda,
                            const void* b_planes, const float* scale_b, int64_t N, int64_t ldb, int64_t K,
                            const float* bias, int32_t relu, float* out, int64_t ldo, void* out_planes,
-                           int64_t out_planes_ld, int32_t splits, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+                           int64_t out_planes_ld, float* absmax_out, int32_t splits, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   PTREC_CHECK_ARG(a_planes && b_planes && out, PTREC_EINVAL, "tc_gemm_split: null pointer");
   PTREC_CHECK_ARG(np == 3 || (scale_a && scale_b), PTREC_EINVAL, "tc_gemm_split2h: null operand scale");
   PTREC_CHECK_ARG(M >= 1 && N >= 1 && K >= 1 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), PTREC_EINVAL,
@@ -948,8 +962,8 @@ static int gemm_split_impl(int np, bool mn_major, const void* a_planes, const fl
   const int total_kb = (int)ceil_div(K, (g_tc_2sm ? g_tc_bk : kLBK));
   if (splits > total_kb) splits = total_kb;
   while (splits > 1 && (int64_t)(splits - 1) * ceil_div(total_kb, splits) >= total_kb) --splits;  // no empty split
-  PTREC_CHECK_ARG(splits == 1 || (!bias && !relu && !out_planes), PTREC_EINVAL,
-                  "tc_gemm_split: split-K has no bias / ReLU / planes epilogue");
+  PTREC_CHECK_ARG(splits == 1 || (!bias && !relu && !out_planes && !absmax_out), PTREC_EINVAL,
+                  "tc_gemm_split: split-K has no bias / ReLU / planes / absmax epilogue");
   PTREC_CHECK_ARG(!out_planes || (np == 3 && aligned16(out_planes) && out_planes_ld % 8 == 0 &&
                                   out_planes_ld >= (N + 3) / 4 * 4),
                   PTREC_EALIGN, "tc_gemm_split: output planes need bf16 x 3 and a pitch that is a multiple of 8 >= N");
@@ -974,6 +988,7 @@ static int gemm_split_impl(int np, bool mn_major, const void* a_planes, const fl
   ep.planes = reinterpret_cast<__nv_bfloat16*>(out_planes); ep.pl_ld = out_planes_ld; ep.pl_plane = M * out_planes_ld;
   ep.out = splits > 1 ? reinterpret_cast<float*>(workspace) : out;
   ep.scale_a = scale_a; ep.scale_b = scale_b;
+  ep.absmax_out = reinterpret_cast<uint32_t*>(absmax_out);
   return np == 3 ? gemm_launch<3>(mn_major, two_sm, bk, sms, maps, M, N, K, ep, out, st)
                  : gemm_launch<2>(mn_major, two_sm, bk, sms, maps, M, N, K, ep, out, st);
 }
@@ -983,22 +998,22 @@ extern "C" int ptrec_tc_gemm_split3(const void* a_planes, int64_t M, int64_t lda
                                     void* out_planes, int64_t out_planes_ld, int32_t splits, void* workspace,
                                     size_t workspace_bytes, void* stream) {
   return gemm_split_impl(3, false, a_planes, nullptr, M, lda, b_planes, nullptr, N, ldb, K, bias, relu, out, ldo,
-                         out_planes, out_planes_ld, splits, workspace, workspace_bytes, stream);
+                         out_planes, out_planes_ld, nullptr, splits, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ptrec_tc_gemm_split3_tn(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N,
                                        int64_t ldb, int64_t K, float* out, int64_t ldo, int32_t splits, void* workspace,
                                        size_t workspace_bytes, void* stream) {
   return gemm_split_impl(3, true, a_planes, nullptr, M, lda, b_planes, nullptr, N, ldb, K, nullptr, 0, out, ldo, nullptr,
-                         0, splits, workspace, workspace_bytes, stream);
+                         0, nullptr, splits, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ptrec_tc_gemm_split2h(const void* a_planes, const float* scale_a, int64_t M, int64_t lda,
                                      const void* b_planes, const float* scale_b, int64_t N, int64_t ldb, int64_t K,
-                                     const float* bias, int32_t relu, float* out, int64_t ldo, int32_t splits,
-                                     void* workspace, size_t workspace_bytes, void* stream) {
+                                     const float* bias, int32_t relu, float* out, int64_t ldo, float* absmax_out,
+                                     int32_t splits, void* workspace, size_t workspace_bytes, void* stream) {
   return gemm_split_impl(2, false, a_planes, scale_a, M, lda, b_planes, scale_b, N, ldb, K, bias, relu, out, ldo,
-                         nullptr, 0, splits, workspace, workspace_bytes, stream);
+                         nullptr, 0, absmax_out, splits, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ptrec_tc_gemm_split2h_tn(const void* a_planes, const float* scale_a, int64_t M, int64_t lda,
@@ -1006,5 +1021,5 @@ extern "C" int ptrec_tc_gemm_split2h_tn(const void* a_planes, const float* scale
                                         float* out, int64_t ldo, int32_t splits, void* workspace,
                                         size_t workspace_bytes, void* stream) {
   return gemm_split_impl(2, true, a_planes, scale_a, M, lda, b_planes, scale_b, N, ldb, K, nullptr, 0, out, ldo,
-                         nullptr, 0, splits, workspace, workspace_bytes, stream);
+                         nullptr, 0, nullptr, splits, workspace, workspace_bytes, stream);
 }

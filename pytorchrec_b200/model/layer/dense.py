@@ -24,7 +24,10 @@ class _TcLinearReLU(torch.autograd.Function):
     """y = relu(x W^T + b) on K6.  Saves y (ReLU mask), the planes of x (weight gradient: read MN-major, i.e.
     transposed by the tensor core itself) and the transposed planes of W (input gradient).  ``px``: the planes of x if
     the producer already wrote them (K8 head, previous layer's epilogue); ``emit_planes``: have the epilogue write
-    the planes of y for the next layer.  Returns (y, planes of y or an empty tensor)."""
+    the planes of y for the next layer.  Returns (y, planes of y or an empty tensor).  In the fp16 x 2 operand mode
+    ``px`` is instead the device word holding max |x| when the producer of x left one, and the second output is the
+    word holding max |y| (reduced by the GEMM epilogue), so that only the first layer's input and the gradient
+    entering the last layer need a pass of their own to find their scale."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, px, emit_planes):
@@ -32,9 +35,10 @@ class _TcLinearReLU(torch.autograd.Function):
         N, K = weight.shape
         ctx.h2 = ops.tc_mode() == "fp16x2"
         if ctx.h2:  # two fp16 planes of the scaled operand + the device-side scale word (ops.tc_split2h)
-            px, _, _, sx = ops.tc_split2h(x)
+            # px here = the word holding max |x| if the producer of x (the previous layer's epilogue) left one
+            px, _, _, sx = ops.tc_split2h(x, absmax_in=px)
             pw, pwt, _, sw = ops.tc_split2h(weight, want_planes=True, want_t=need_dx)
-            y, py = ops.tc_gemm_split2h(px, sx, pw, sw, K, bias=bias, relu=True), x.new_empty(0, dtype=torch.bfloat16)
+            y, py = ops.tc_gemm_split2h(px, sx, pw, sw, K, bias=bias, relu=True, want_absmax=True)  # py: max |y|
             ctx.save_for_backward(y, px if need_dw else None, pwt, sx, sw)
         else:
             if px is None:
@@ -59,8 +63,12 @@ class _TcLinearReLU(torch.autograd.Function):
         dw = None
         if ctx.h2:
             y, px, pwt, sx, sw = ctx.saved_tensors
-            pg, _, db, sg = ops.tc_split2h(gy, relu_ref=y, want_planes=need_dx or need_dw, want_colsum=need_db)
-            dx = ops.tc_gemm_split2h(pg, sg, pwt, sw, N) if need_dx else None      # g W        [B, K]
+            pg, _, db, sg = ops.tc_split2h(gy, relu_ref=y, want_planes=need_dx or need_dw, want_colsum=need_db,
+                                           absmax_in=_carried_absmax(gy))
+            dx = None
+            if need_dx:                                                             # g W        [B, K]
+                dx, am = ops.tc_gemm_split2h(pg, sg, pwt, sw, N, want_absmax=True)
+                _carry_absmax(dx, am)   # the layer below splits dx next: it finds max |dx| already reduced
             if need_dw:
                 dw = ops.tc_gemm_split2h_tn(pg, sg, N, px, sx, K)                   # g^T x      [N, K]
         else:
@@ -72,6 +80,21 @@ class _TcLinearReLU(torch.autograd.Function):
         if dw is not None and not dw.is_contiguous():
             dw = dw.contiguous()
         return dx, dw, db, None, None
+
+
+def _carry_absmax(t: torch.Tensor, word: torch.Tensor) -> None:
+    """Attach the device word holding max |t| (written by the GEMM epilogue that produced ``t``) to the tensor object,
+    with the storage address and version it describes."""
+    t._ptrec_absmax = (word, t.data_ptr(), t._version, tuple(t.shape))
+
+
+def _carried_absmax(t: torch.Tensor):
+    """The word attached by ``_carry_absmax`` if it still describes ``t`` (same storage, not modified since); else None
+    — the split then finds the maximum itself."""
+    rec = getattr(t, "_ptrec_absmax", None)
+    if rec is None or rec[1] != t.data_ptr() or rec[2] != t._version or rec[3] != tuple(t.shape):
+        return None
+    return rec[0]
 
 
 def tc_linear_enabled() -> bool:
@@ -97,18 +120,23 @@ class Dense(Module):
         if x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and tc_linear_enabled() \
                 and not torch.is_autocast_enabled() and x.numel() * w.shape[0] >= TC_MIN_MACS:
             lead = x.shape[:-1]
-            x2 = x.reshape(-1, x.shape[-1])
+            x2 = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
             if x2.stride(-1) != 1:
                 x2 = x2.contiguous()
-            px = getattr(x, "_ptrec_planes", None)  # written by the producer of x (K8 head / previous layer)
-            if px is not None and not (x.dim() == 2 and tuple(px.shape) == (3, x2.shape[0], (x2.shape[1] + 7) // 8 * 8)
-                                       and px.device == x2.device and px.dtype == torch.bfloat16
-                                       and ops.tc_mode() == "bf16x3"):
-                px = None
-            y, py = _TcLinearReLU.apply(x2, w, self.linear.bias, px, self.emit_planes and x.dim() == 2)
+            h2 = ops.tc_mode() == "fp16x2"
+            if h2:   # fp16 x 2: what travels with a tensor is the word holding its absolute maximum
+                px = _carried_absmax(x2)
+            else:
+                px = getattr(x, "_ptrec_planes", None)  # written by the producer of x (K8 head / previous layer)
+                if px is not None and not (x.dim() == 2 and px.dtype == torch.bfloat16 and px.device == x2.device
+                                           and tuple(px.shape) == (3, x2.shape[0], (x2.shape[1] + 7) // 8 * 8)):
+                    px = None
+            y, py = _TcLinearReLU.apply(x2, w, self.linear.bias, px, self.emit_planes and x.dim() == 2 and not h2)
             if self.training and self.dropout.p > 0:
                 return self.dropout(y.reshape(*lead, w.shape[0]))
-            if py.numel():
+            if h2:
+                _carry_absmax(y, py)
+            elif py.numel():
                 y._ptrec_planes = py
             return y.reshape(*lead, w.shape[0]) if x.dim() != 2 else y
         return self.dropout(self.activation(self.linear(x)))

@@ -562,14 +562,14 @@ def tc_gemm_split3_tn(a_planes: torch.Tensor, M: int, b_planes: torch.Tensor, N:
 
 # ---- fp16 x 2 operand mode of K6 ("h2"): x * s = h0 + h1 / 2^11 with a per-tensor power-of-two scale s --------------
 _TC_MODES = ("bf16x3", "fp16x2")
-_tc_mode = os.environ.get("PTREC_TC_MODE", "bf16x3")
+_tc_mode = os.environ.get("PTREC_TC_MODE", "fp16x2")
 if _tc_mode not in _TC_MODES:
     raise ValueError(f"PTREC_TC_MODE must be one of {_TC_MODES}, got {_tc_mode!r}")
 
 
 def tc_mode() -> str:
-    """Operand format of the K6 Linear GEMMs: ``bf16x3`` (three exact bf16 planes, 6 MMAs per product) or ``fp16x2``
-    (two fp16 planes of the power-of-two-scaled operand, 3 MMAs per product; 22 mantissa bits)."""
+    """Operand format of the K6 Linear GEMMs: ``fp16x2`` (default: two fp16 planes of the power-of-two-scaled operand,
+    3 MMAs per product, 22 mantissa bits) or ``bf16x3`` (three exact bf16 planes, 6 MMAs per product)."""
     return _tc_mode
 
 
@@ -581,10 +581,12 @@ def set_tc_mode(mode: str) -> None:
 
 
 def tc_split2h(src: torch.Tensor, relu_ref: Optional[torch.Tensor] = None, want_planes: bool = True,
-               want_t: bool = False, want_colsum: bool = False):
+               want_t: bool = False, want_colsum: bool = False, absmax_in: Optional[torch.Tensor] = None):
     """fp32 [R, C] -> (planes [2, R, pad8(C)] fp16, planes_t [2, C, pad8(R)] fp16, colsum [C], scale [1] fp32).
     ``scale`` is the power of two the tensor was multiplied by before the split (largest magnitude -> [2^13, 2^14)),
-    computed on the device from the tensor's absolute maximum; the GEMM divides it out again."""
+    computed on the device from the tensor's absolute maximum; the GEMM divides it out again.  ``absmax_in``: a
+    one-element fp32 tensor that already holds max |src| (``tc_gemm_split2h(..., want_absmax=True)``): skips the
+    pass that finds it."""
     lib = _lib.load()
     _require_cuda(src, relu_ref)
     assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1
@@ -597,10 +599,13 @@ def tc_split2h(src: torch.Tensor, relu_ref: Optional[torch.Tensor] = None, want_
     colsum = torch.empty(C, dtype=torch.float32, device=dev) if want_colsum else None
     scale = torch.empty(1, dtype=torch.float32, device=dev)
     ws = _workspace("tc_split2h", lib.ptrec_tc_split2h_workspace_bytes(R, C), dev)
+    if absmax_in is not None:
+        _require_cuda(absmax_in)
+        assert absmax_in.dtype == torch.float32 and absmax_in.numel() == 1
     _lib.check(lib.ptrec_tc_split2h(_ptr(src), src.stride(0), R, C, _ptr(relu_ref),
                                     relu_ref.stride(0) if relu_ref is not None else 0, _ptr(planes), _pad8(C),
-                                    _ptr(planes_t), _pad8(R), _ptr(colsum), _ptr(scale), _ptr(ws), ws.numel(),
-                                    _stream(dev)), "ptrec_tc_split2h")
+                                    _ptr(planes_t), _pad8(R), _ptr(colsum), _ptr(scale), _ptr(absmax_in), _ptr(ws),
+                                    ws.numel(), _stream(dev)), "ptrec_tc_split2h")
     return planes, planes_t, colsum, scale
 
 
@@ -613,8 +618,10 @@ def _check_h2(a_planes, scale_a, b_planes, scale_b):
 
 
 def tc_gemm_split2h(a_planes: torch.Tensor, scale_a: torch.Tensor, b_planes: torch.Tensor, scale_b: torch.Tensor,
-                    K: int, bias: Optional[torch.Tensor] = None, relu: bool = False, splits: int = 1) -> torch.Tensor:
-    """out [M, N] fp32 = A[M, K] B[N, K]^T (+ bias) (ReLU) from fp16 planes [2, M, lda], [2, N, ldb] and their scales."""
+                    K: int, bias: Optional[torch.Tensor] = None, relu: bool = False, splits: int = 1,
+                    want_absmax: bool = False):
+    """out [M, N] fp32 = A[M, K] B[N, K]^T (+ bias) (ReLU) from fp16 planes [2, M, lda], [2, N, ldb] and their scales.
+    ``want_absmax`` (splits == 1): also return a one-element fp32 tensor that the epilogue raises to max |out|."""
     lib = _lib.load()
     _check_h2(a_planes, scale_a, b_planes, scale_b)
     M, lda = a_planes.shape[1], a_planes.shape[2]
@@ -628,10 +635,12 @@ def tc_gemm_split2h(a_planes: torch.Tensor, scale_a: torch.Tensor, b_planes: tor
     ws = _workspace("tc_gemm_split3", nbytes, dev) if nbytes else None
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
+    absmax = torch.zeros(1, dtype=torch.float32, device=dev) if want_absmax else None
     _lib.check(lib.ptrec_tc_gemm_split2h(_ptr(a_planes), _ptr(scale_a), M, lda, _ptr(b_planes), _ptr(scale_b), N, ldb, K,
-                                         _ptr(bias), int(relu), _ptr(out), ldo, splits, _ptr(ws),
+                                         _ptr(bias), int(relu), _ptr(out), ldo, _ptr(absmax), splits, _ptr(ws),
                                          ws.numel() if ws is not None else 0, _stream(dev)), "ptrec_tc_gemm_split2h")
-    return out[:, :N] if ldo != N else out
+    y = out[:, :N] if ldo != N else out
+    return (y, absmax) if want_absmax else y
 
 
 def tc_gemm_split2h_tn(a_planes: torch.Tensor, scale_a: torch.Tensor, M: int, b_planes: torch.Tensor,

@@ -1,10 +1,8 @@
 """K6 in its fp16 x 2 operand format (``PTREC_TC_MODE=fp16x2``, include/ptrec_b200.h): device planes bit for bit against
 the restatement in oracle/ref_ops.py, GEMM error against fp64 at the level of an fp32 GEMM, and a Dense layer against
-``nn.Linear``.  The format is opt-in, so these tests run when the suite itself runs in that mode:
-
-    PTREC_TC_MODE=fp16x2 python -m pytest tests -m gpu
-
-(the model parity tests of tests/test_gpu_models.py then exercise the same format end to end)."""
+``nn.Linear``.  fp16x2 is the default operand format (``PTREC_TC_MODE=bf16x3`` selects the three-plane one, whose kernel tests in
+tests/test_gpu_kernels.py call it directly and run either way); the model parity tests of tests/test_gpu_models.py
+exercise the default format end to end."""
 import pytest
 import torch
 
@@ -12,8 +10,15 @@ from oracle import ref_ops
 from pytorchrec_b200 import _lib, ops
 
 DEV = torch.device("cuda:0")
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(ops.tc_mode() != "fp16x2", reason="opt-in format: run with PTREC_TC_MODE=fp16x2")]
+pytestmark = [pytest.mark.gpu]
+
+
+@pytest.fixture(autouse=True)
+def _fp16x2_operands():
+    old = ops.tc_mode()
+    ops.set_tc_mode("fp16x2")
+    yield
+    ops.set_tc_mode(old)
 
 
 @pytest.fixture(params=["2sm", "1sm"])
@@ -62,6 +67,14 @@ def _err(out, ref, scale):
     return ((out.double() - ref).abs() / scale).max().item()
 
 
+def _chain(k_steps):
+    """The tensor core aligns each MMA's products with the running fp32 sum and TRUNCATES: a chain of
+    ``k_steps`` accumulations of 16 products carries up to half an ulp of bias per step relative to the running sum.
+    Invisible when the sum cancels (|sum| << sum |a||b|, the usual case), visible on heavy-tailed operands whose sum is
+    dominated by a few terms (measured: 7.1e-7 at K = 700 against 1.3e-7 for the CPU emulation of the same format)."""
+    return k_steps * 2.0 ** -25
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 400, 429), (1000, 16, 40), (2048, 429, 400), (130, 1, 700),
                                    (4096, 400, 1677)])
 @pytest.mark.parametrize("kind", ["unit", "tower", "tiny"])
@@ -82,15 +95,24 @@ def test_gemm_split2h_has_fp32_level_error(M, N, K, kind, tc_kernel):
     fp32_err = _err(a @ b.t(), ref, scale)
     out = ops.tc_gemm_split2h(pa, sa, pb, sb, K)
     assert out.shape == (M, N)
-    assert _err(out, ref, scale) <= max(3e-7, 2 * fp32_err), (_err(out, ref, scale), fp32_err)
+    tol = max(3e-7, 2 * fp32_err) + (_chain(K / 16) if kind == "tiny" else 0.0)
+    assert _err(out, ref, scale) <= tol, (_err(out, ref, scale), fp32_err)
     # the device result equals the CPU emulation of the same arithmetic up to accumulation order
     emu = ref_ops.gemm_split2h_ref(a.cpu(), b.cpu())
-    assert _err(out.cpu(), emu.double(), scale.cpu()) <= 3e-7
+    assert _err(out.cpu(), emu.double(), scale.cpu()) <= 2 * tol   # two fp32 accumulations
     out2 = ops.tc_gemm_split2h(pa, sa, pb, sb, K, bias=bias, relu=True)
     ref2 = torch.relu(ref + bias.double())
-    assert _err(out2, ref2, scale + bias.abs().double()) <= max(3e-7, 2 * fp32_err)
+    assert _err(out2, ref2, scale + bias.abs().double()) <= tol
     out3 = ops.tc_gemm_split2h(pa, sa, pb, sb, K, splits=3)
-    assert _err(out3, ref, scale) <= max(4e-7, 2 * fp32_err)
+    assert _err(out3, ref, scale) <= tol + 1e-7
+    # the epilogue's max |out| word: exact, and a split that takes it produces the same planes as one that looks itself
+    for kw in (dict(), dict(bias=bias, relu=True)):
+        o, am = ops.tc_gemm_split2h(pa, sa, pb, sb, K, want_absmax=True, **kw)
+        assert torch.equal(o, ops.tc_gemm_split2h(pa, sa, pb, sb, K, **kw))
+        assert am.item() == o.abs().max().item()
+        p1, _, _, s1 = ops.tc_split2h(o)
+        p2, _, _, s2 = ops.tc_split2h(o, absmax_in=am)
+        assert torch.equal(s1, s2) and torch.equal(p1, p2)
 
 
 @pytest.mark.parametrize("B,N,K", [(4096, 400, 429), (1000, 128, 64), (777, 16, 1030), (64, 200, 13)])
@@ -103,10 +125,42 @@ def test_gemm_split2h_tn_weight_gradient_from_row_major_planes(B, N, K, tc_kerne
     ref = g.double().t() @ x.double()
     scale = g.double().abs().t() @ x.double().abs()
     fp32_err = _err(g.t() @ x, ref, scale)
-    for splits, tol in ((0, max(4e-7, 2 * fp32_err)), (1, 1e-6)):
+    auto = _lib.load().ptrec_tc_gemm_split3_default_splits(N, K, B)
+    for splits, tol in ((0, max(4e-7, 2 * fp32_err) + _chain(B / 16 / auto)), (1, 1e-6 + _chain(B / 16))):
         dw = ops.tc_gemm_split2h_tn(pg, sg, N, px, sx, K, splits=splits)
         assert dw.shape == (N, K)
         assert _err(dw, ref, scale) <= tol, (splits, _err(dw, ref, scale), fp32_err)
+
+
+def test_mlp_carries_absmax_words_between_layers_and_matches_fp64():
+    """Three Dense layers: outputs / input gradients travel with the word holding their maximum (no extra pass), and
+    the whole tower agrees with an fp64 evaluation."""
+    from pytorchrec_b200.model.layer import dense
+    old, dense.TC_MIN_MACS = dense.TC_MIN_MACS, 0
+    try:
+        torch.manual_seed(5)
+        mlp = dense.MLP(429, [400, 400, 200], "relu", 0.0).to(DEV)
+        x = torch.rand(1024, 429, device=DEV).requires_grad_(True)
+        h = mlp.mlp[0](x)
+        assert dense._carried_absmax(h) is not None and dense._carried_absmax(h).item() == h.abs().max().item()
+        assert dense._carried_absmax(h + 0) is None
+        lib = _lib.load()
+        n0 = lib.ptrec_launch_count()
+        y = mlp(x)
+        fwd_launches = lib.ptrec_launch_count() - n0
+        # per layer: split(x) [+ absmax for layer 0 only], absmax(W) + split(W), GEMM  ->  3 * 4 + 1
+        assert fwd_launches == 13, fwd_launches
+        gy = 1e-5 * torch.randn_like(y)
+        y.backward(gy)
+        xd = x.detach().double().requires_grad_(True)
+        hd = xd
+        for layer in mlp.mlp:
+            hd = torch.relu(hd @ layer.linear.weight.detach().double().t() + layer.linear.bias.detach().double())
+        hd.backward(gy.double())
+        assert (y.double() - hd).abs().max().item() <= 3e-6 * hd.abs().max().item()
+        assert (x.grad.double() - xd.grad).abs().max().item() <= 3e-6 * xd.grad.abs().max().item()
+    finally:
+        dense.TC_MIN_MACS = old
 
 
 def test_dense_layer_matches_nn_linear_forward_and_backward():
