@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 17
+#define PTREC_ABI_VERSION 18
 
 /* error codes */
 #define PTREC_OK 0
@@ -410,6 +410,11 @@ int ptrec_tc_gemm_split3_tn(const void* a_planes, int64_t M, int64_t lda, const 
  *   two split calls wrote.  No output planes.  absmax_out (or NULL; splits == 1 only): one fp32 device word, ZERO on
  *   entry, that the epilogue raises to max |out| (atomicMax on the bit pattern) — pass it as absmax_in when out is
  *   split for the next GEMM. */
+/* fp16 x 2 GEMMs on CTA pairs: pair tiles of 256 x 256 (one accumulator pair in TMEM) or 256 x 128 (two accumulator
+ * pairs: the MMAs of the next tile overlap the epilogue of the current one).  Identical results up to summation order
+ * of nothing — both accumulate a tile's K range in the same order — so tests require bit equality. */
+void ptrec_tc_set_bn(int32_t bn); /* 128 or 256 */
+int32_t ptrec_tc_get_bn(void);
 size_t ptrec_tc_split2h_workspace_bytes(int64_t R, int64_t C);
 int ptrec_tc_split2h(const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref, int64_t ld_ref,
                      void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld, float* colsum, float* scale_out,

@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libptrec_b200.so")
 
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 # enums (mirror include/ptrec_b200.h)
 F32, BF16 = 0, 1
@@ -119,6 +119,8 @@ PROTOTYPES = {
                                      c_void_p]),
     "ptrec_tc_gemm_split3_tn": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                         c_int64, c_int32, c_void_p, c_size_t, c_void_p]),
+    "ptrec_tc_set_bn": (None, [c_int32]),
+    "ptrec_tc_get_bn": (c_int32, []),
     "ptrec_tc_split2h_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "ptrec_tc_split2h": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                  c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -185,6 +187,8 @@ def load():
     ver = lib.ptrec_abi_version()
     if ver != ABI_VERSION:
         raise RuntimeError(f"libptrec_b200.so ABI {ver} != binding ABI {ABI_VERSION}: rebuild")
+    if os.environ.get("PTREC_TC_BN"):  # K6 fp16 x 2 pair-tile width, 128 or 256 (A/B measurements)
+        lib.ptrec_tc_set_bn(int(os.environ["PTREC_TC_BN"]))
     _lib = lib
     return lib
 

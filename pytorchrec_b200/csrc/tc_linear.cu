@@ -767,6 +767,212 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
   }
 }
 
+// ------------------------------------------------------------------------------- fp16 x 2, double-buffered accumulators
+// With two operand planes the accumulator pair (main + correction) of a 128-column tile takes 256 TMEM columns, so TWO
+// tiles fit: the MMAs of tile i+1 run while the epilogue warps drain tile i (the 256-column kernels above hold one tile
+// and stall the tensor core for every epilogue — ~1/3 of the time at the DNN-tower shapes, K ~ 400).  CTA pairs own
+// 256 x 128 tiles: per CTA and K block 128 rows of A (2 planes x 8 KB) and its 64-row half of B (2 x 4 KB) = 24 KB,
+// 8 stages.  Shared-memory operand reads: 6 KB per MMA of 64 tensor-core cycles = 96 B/clk of the 128 available.
+constexpr int kDbBN = 128, kDbBK = 32, kDbStages = 8;
+constexpr uint32_t kDbTileA = 128 * kDbBK * 2;                  // 8 KB
+constexpr uint32_t kDbTileB = 64 * kDbBK * 2;                   // 4 KB
+constexpr uint32_t kDbStageBytes = 2 * (kDbTileA + kDbTileB);   // A0 A1 B0 B1 = 24 KB
+static_assert((size_t)kDbStages * kDbStageBytes + 3072 <= k2Smem, "stages exceed the shared-memory budget");
+
+template <bool MN_MAJOR>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
+gemm_split2h_2sm_db_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, LinEpi ep) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kDbStages * kDbStageBytes);
+  uint64_t* full = bars;                       // [kDbStages]  (the leader's are the ones in use)
+  uint64_t* empty = bars + kDbStages;          // [kDbStages]
+  uint64_t* acc_full = bars + 2 * kDbStages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]  (leader's)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(bars + 32);  // [kDbBN], 256 bytes into the barrier block
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int tiles_n = (N + kDbBN - 1) / kDbBN, tiles_m = (M + 255) / 256;
+  const int splits = max(ep.splits, 1);
+  const int mn_tiles = tiles_n * tiles_m;
+  const int n_tiles = mn_tiles * splits;
+  const int total_kb = (K + kDbBK - 1) / kDbBK;
+  const int kb_per_split = (total_kb + splits - 1) / splits;
+  const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDbStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 2 * kLEpiWarps);  // the epilogue warps of both CTAs
+    }
+    fence_mbar_init();
+  }
+  cluster_sync_all();  // the peer's barriers exist before anything arrives on them
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kLTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b) : "memory");
+      int kbg = 0;
+      for (int tile = cid; tile < n_tiles; tile += n_clusters) {
+        const int mn = tile % mn_tiles, split = tile / mn_tiles;
+        const int m0 = (mn % tiles_m) * 256 + rank * 128, n0 = (mn / tiles_m) * kDbBN;
+        const int n_eff = min(kDbBN, (N - n0 + 15) & ~15);
+        const int nb0 = n0 + rank * (n_eff >> 1);  // this CTA's half of the B tile
+        const int kb0 = split * kb_per_split, num_kb = max(0, min(total_kb - kb0, kb_per_split));
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const int s = kbg % kDbStages;
+          mbar_wait(&empty[s], ((kbg / kDbStages) & 1) ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kDbStageBytes);  // both CTAs' bytes land on the leader
+          unsigned char* sa = smem + (size_t)s * kDbStageBytes;
+          unsigned char* sb = sa + 2 * kDbTileA;
+          const int k0 = (kb0 + kb) * kDbBK;
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            if (MN_MAJOR) {  // boxes of 64 (mn) x 32 (k rows), 4 KB: two for the 128 rows of A, one for the B half
+              tma_load_3d_2sm(sa + (size_t)p * kDbTileA, &maps.a, m0, k0, p, &full[s]);
+              tma_load_3d_2sm(sa + (size_t)p * kDbTileA + 4096, &maps.a, m0 + 64, k0, p, &full[s]);
+              tma_load_3d_2sm(sb + (size_t)p * kDbTileB, &maps.b, nb0, k0, p, &full[s]);
+            } else {
+              tma_load_3d_2sm(sa + (size_t)p * kDbTileA, &maps.a, k0, m0, p, &full[s]);
+              tma_load_3d_2sm(sb + (size_t)p * kDbTileB, &maps.b, k0, nb0, p, &full[s]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int kbg = 0, it = 0;
+      for (int tile = cid; tile < n_tiles; tile += n_clusters, ++it) {
+        const int buf = it & 1, use = it >> 1;
+        mbar_wait(&acc_empty[buf], (use & 1) ^ 1);  // the epilogue has drained this buffer's previous tile
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 2 * kDbBN);   // main accumulator
+        const uint32_t tmem_c = tmem_d + (uint32_t)kDbBN;                  // correction accumulator
+        const int mn = tile % mn_tiles;
+        const int n0 = (mn / tiles_m) * kDbBN;
+        const int n_eff = min(kDbBN, (N - n0 + 15) & ~15);
+        const uint32_t idesc = LinCfg<2>::kIdescFmt | ((uint32_t)(n_eff >> 3) << 17) | ((uint32_t)(256 >> 4) << 24) |
+                               (MN_MAJOR ? ((1u << 15) | (1u << 16)) : 0u);
+        const int kb0 = (tile / mn_tiles) * kb_per_split, num_kb = max(0, min(total_kb - kb0, kb_per_split));
+        for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+          const int s = kbg % kDbStages;
+          mbar_wait(&full[s], (kbg / kDbStages) & 1);
+          tcgen05_fence_after();
+          unsigned char* sa = smem + (size_t)s * kDbStageBytes;
+          unsigned char* sb = sa + 2 * kDbTileA;
+          uint64_t ad[2], bd[2];
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const void* pa = sa + (size_t)p * kDbTileA;
+            const void* pb = sb + (size_t)p * kDbTileB;
+            ad[p] = MN_MAJOR ? make_sw128_mn32_desc(pa) : make_sw64_desc(pa);
+            bd[p] = MN_MAJOR ? make_sw128_mn32_desc(pb) : make_sw64_desc(pb);
+          }
+#pragma unroll
+          for (int k = 0; k < kDbBK / kLUmmaK; ++k) {
+            const uint64_t o = MN_MAJOR ? (uint64_t)(k * 128) : (uint64_t)(k * 2);
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_bf16_2sm(tmem_c, ad[0] + o, bd[1] + o, idesc, acc);
+            umma_bf16_2sm(tmem_c, ad[1] + o, bd[0] + o, idesc, 1u);
+            umma_bf16_2sm(tmem_d, ad[0] + o, bd[0] + o, idesc, acc);
+          }
+          umma_commit_2sm(&empty[s]);
+        }
+        umma_commit_2sm(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int e = warp - 2;
+    const int q = warp & 3;   // TMEM lane quadrant this warp may access
+    const int half = e >> 2;  // 64-column half of the tile
+    const int r = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const float inv_a = 1.f / ep.scale_a[0];  // exact: the scales are powers of two
+    const float inv_b = 1.f / ep.scale_b[0];
+    int it = 0;
+    for (int tile = cid; tile < n_tiles; tile += n_clusters, ++it) {
+      const int buf = it & 1, use = it >> 1;
+      const int mn = tile % mn_tiles, split = tile / mn_tiles;
+      const int m0 = (mn % tiles_m) * 256 + rank * 128, n0 = (mn / tiles_m) * kDbBN;
+      if (ep.bias != nullptr) {
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kLEpiWarps) : "memory");  // previous tile's readers are done
+        if (et < kDbBN) s_bias[et] = (n0 + et < N) ? ep.bias[n0 + et] : 0.f;
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kLEpiWarps) : "memory");
+      }
+      mbar_wait(&acc_full[buf], use & 1);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * 2 * kDbBN) + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+      const int row = m0 + r, col0 = n0 + half * 64;
+      const bool live = col0 < N;  // warp-uniform: a narrow remainder tile leaves the second half empty
+      uint32_t v[64];
+      if (live) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t w[32];
+          tmem_ld32(tacc + h * 32, v + h * 32);
+          tmem_ld32(tacc + kDbBN + h * 32, w);  // correction accumulator
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[h * 32 + j] = __float_as_uint(lin_combine<2>(__uint_as_float(v[h * 32 + j]), __uint_as_float(w[j]),
+                                                           inv_a, inv_b));
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&acc_empty[buf]);  // the tensor core may reuse this buffer for tile it + 2
+      float amax = 0.f;
+      if (live && row < M) {
+        float* o = ep.out + ((int64_t)split * M + row) * ep.ldo + col0;
+        const bool has_bias = ep.bias != nullptr;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          if (col0 + j < N) {  // ldo % 4 == 0 and ldo >= round_up(N, 4): the whole group is inside the pitch
+            float4 t = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                   __uint_as_float(v[j + 3]));
+            if (has_bias) {
+              const float4 b = *reinterpret_cast<const float4*>(&s_bias[half * 64 + j]);
+              t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+            }
+            if (ep.relu) {
+              t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(o + j) = t;
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+          }
+        }
+      }
+      if (ep.absmax_out != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if (lane == 0 && amax > 0.f) atomicMax(ep.absmax_out, __float_as_uint(amax));
+      }
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // both CTAs are done with TMEM and with each other's barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kLTmemCols) : "memory");
+  }
+}
+
 // K-major operand: 3-D bf16 map over planes [3][rows][ld]: dims (cols, rows, 3), box 32 x box_rows x 1, 64B swizzle
 static int make_map3(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int64_t plane,
                      int box_rows, int bk, int np) {
@@ -883,6 +1089,10 @@ static int g_tc_bk = 32;
 extern "C" void ptrec_tc_set_bk(int32_t bk) { g_tc_bk = bk == 64 ? 64 : 32; }
 static int g_tc_2sm = 1;
 extern "C" void ptrec_tc_set_2sm(int32_t enabled) { g_tc_2sm = enabled ? 1 : 0; }
+// fp16 x 2, CTA pairs: tile width 256 (one accumulator pair in TMEM) or 128 (two: MMAs overlap the epilogue)
+static int g_tc_bn = 256;
+extern "C" void ptrec_tc_set_bn(int32_t bn) { g_tc_bn = bn == 128 ? 128 : 256; }
+extern "C" int32_t ptrec_tc_get_bn(void) { return g_tc_bn; }
 extern "C" int32_t ptrec_tc_2sm_enabled(void) { return g_tc_2sm; }
 
 extern "C" size_t ptrec_tc_gemm_split3_workspace_bytes(int64_t M, int64_t ldo, int32_t splits) {
@@ -903,8 +1113,8 @@ extern "C" int32_t ptrec_tc_gemm_split3_default_splits(int64_t M, int64_t N, int
 }
 
 template <int NP>
-static int gemm_launch(bool mn_major, bool two_sm, int bk, int sms, const LinMaps& maps, int64_t M, int64_t N, int64_t K,
-                       const LinEpi& ep, float* out, cudaStream_t st) {
+static int gemm_launch(bool mn_major, bool two_sm, bool db, int bk, int sms, const LinMaps& maps, int64_t M, int64_t N,
+                       int64_t K, const LinEpi& ep, float* out, cudaStream_t st) {
   static bool attr_set = false;  // one flag per plane count
   if (!attr_set) {
     PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_kernel<false, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmem));
@@ -913,10 +1123,22 @@ static int gemm_launch(bool mn_major, bool two_sm, int bk, int sms, const LinMap
     PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<true, 32, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
     PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<false, 64, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
     PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<true, 64, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
+    if (NP == 2) {
+      PTREC_CUDA(cudaFuncSetAttribute(gemm_split2h_2sm_db_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
+      PTREC_CUDA(cudaFuncSetAttribute(gemm_split2h_2sm_db_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
+    }
     attr_set = true;
   }
   const int splits = ep.splits;
-  if (two_sm) {
+  if (NP == 2 && db) {
+    const int64_t pair_tiles = ceil_div(N, kDbBN) * ceil_div(M, 256) * splits;
+    const unsigned grid2 = (unsigned)(2 * std::min<int64_t>(pair_tiles, sms / 2));
+    if (mn_major)
+      gemm_split2h_2sm_db_kernel<true><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+    else
+      gemm_split2h_2sm_db_kernel<false><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+    PTREC_LAUNCH_CHECK("gemm_split2h_2sm_db_kernel");
+  } else if (two_sm) {
     const int64_t pair_tiles = ceil_div(N, 256) * ceil_div(M, 256) * splits;
     const int64_t clusters = std::min<int64_t>(pair_tiles, sms / 2);
     const unsigned grid2 = (unsigned)(2 * clusters);
@@ -959,7 +1181,13 @@ static int gemm_split_impl(int np, bool mn_major, const void* a_planes, const fl
                       lda >= (mn_major ? M : K) && ldb >= (mn_major ? N : K) && ldo % 4 == 0 && ldo >= (N + 3) / 4 * 4,
                   PTREC_EALIGN, "tc_gemm_split: pitches must be multiples of 8 (planes) / 4 (out) elements");
   if (splits < 1) splits = 1;
-  const int total_kb = (int)ceil_div(K, (g_tc_2sm ? g_tc_bk : kLBK));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool two_sm = g_tc_2sm != 0 && sms >= 2;
+  const bool db = np == 2 && two_sm && g_tc_bn == 128;  // double-buffered 256 x 128 pair tiles (K blocks of 32)
+  const int bk = db ? kDbBK : (two_sm ? g_tc_bk : kLBK);
+  const int total_kb = (int)ceil_div(K, (int64_t)bk);
   if (splits > total_kb) splits = total_kb;
   while (splits > 1 && (int64_t)(splits - 1) * ceil_div(total_kb, splits) >= total_kb) --splits;  // no empty split
   PTREC_CHECK_ARG(splits == 1 || (!bias && !relu && !out_planes && !absmax_out), PTREC_EINVAL,
@@ -972,16 +1200,11 @@ static int gemm_split_impl(int np, bool mn_major, const void* a_planes, const fl
   cudaStream_t st = (cudaStream_t)stream;
   LinMaps maps;
   memset(&maps, 0, sizeof(maps));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const bool two_sm = g_tc_2sm != 0 && sms >= 2;
-  const int bk = two_sm ? g_tc_bk : kLBK;
   int rc = mn_major ? make_map3_mn(&maps.a, a_planes, K, M, lda, K * lda, bk, np)
                     : make_map3(&maps.a, a_planes, M, K, lda, M * lda, kLBM, bk, np);
   if (rc != PTREC_OK) return rc;
   rc = mn_major ? make_map3_mn(&maps.b, b_planes, K, N, ldb, K * ldb, bk, np)
-                : make_map3(&maps.b, b_planes, N, K, ldb, N * ldb, two_sm ? 128 : kLBN, bk, np);
+                : make_map3(&maps.b, b_planes, N, K, ldb, N * ldb, db ? 64 : (two_sm ? 128 : kLBN), bk, np);
   if (rc != PTREC_OK) return rc;
   LinEpi ep;
   ep.bias = bias; ep.relu = relu; ep.ldo = ldo; ep.splits = splits;
@@ -989,8 +1212,8 @@ static int gemm_split_impl(int np, bool mn_major, const void* a_planes, const fl
   ep.out = splits > 1 ? reinterpret_cast<float*>(workspace) : out;
   ep.scale_a = scale_a; ep.scale_b = scale_b;
   ep.absmax_out = reinterpret_cast<uint32_t*>(absmax_out);
-  return np == 3 ? gemm_launch<3>(mn_major, two_sm, bk, sms, maps, M, N, K, ep, out, st)
-                 : gemm_launch<2>(mn_major, two_sm, bk, sms, maps, M, N, K, ep, out, st);
+  return np == 3 ? gemm_launch<3>(mn_major, two_sm, false, bk, sms, maps, M, N, K, ep, out, st)
+                 : gemm_launch<2>(mn_major, two_sm, db, bk, sms, maps, M, N, K, ep, out, st);
 }
 
 extern "C" int ptrec_tc_gemm_split3(const void* a_planes, int64_t M, int64_t lda, const void* b_planes, int64_t N,

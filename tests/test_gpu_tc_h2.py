@@ -21,12 +21,16 @@ def _fp16x2_operands():
     ops.set_tc_mode(old)
 
 
-@pytest.fixture(params=["2sm", "1sm"])
+@pytest.fixture(params=["2sm", "2sm_db", "1sm"])
 def tc_kernel(request):
+    """CTA-pair kernel with one 256-column accumulator pair, with two 128-column pairs (double-buffered), single CTA."""
     lib = _lib.load()
-    lib.ptrec_tc_set_2sm(1 if request.param == "2sm" else 0)
+    bn = lib.ptrec_tc_get_bn()
+    lib.ptrec_tc_set_2sm(0 if request.param == "1sm" else 1)
+    lib.ptrec_tc_set_bn(128 if request.param == "2sm_db" else 256)
     yield request.param
     lib.ptrec_tc_set_2sm(1)
+    lib.ptrec_tc_set_bn(bn)
 
 
 @pytest.mark.parametrize("R,C", [(64, 64), (200, 429), (1031, 13), (4096, 400)])
@@ -186,3 +190,25 @@ def test_dense_layer_matches_nn_linear_forward_and_backward():
             assert (a.double() - r).abs().max().item() <= tol, (name, (a.double() - r).abs().max().item(), tol)
     finally:
         dense.TC_MIN_MACS = old
+
+
+def test_both_pair_tile_widths_give_identical_results():
+    lib = _lib.load()
+    bn = lib.ptrec_tc_get_bn()
+    gen = torch.Generator().manual_seed(21)
+    a = torch.randn(1000, 429, generator=gen).to(DEV)
+    b = torch.randn(400, 429, generator=gen).to(DEV)
+    g = torch.randn(1000, 400, generator=gen).to(DEV)
+    bias = torch.randn(400, generator=gen).to(DEV)
+    pa, _, _, sa = ops.tc_split2h(a)
+    pb, _, _, sb = ops.tc_split2h(b)
+    pg, _, _, sg = ops.tc_split2h(g)
+    outs = []
+    try:
+        for width in (256, 128):
+            lib.ptrec_tc_set_bn(width)
+            outs.append((ops.tc_gemm_split2h(pa, sa, pb, sb, 429, bias=bias, relu=True),
+                         ops.tc_gemm_split2h_tn(pg, sg, 400, pa, sa, 429, splits=4)))
+    finally:
+        lib.ptrec_tc_set_bn(bn)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
