@@ -51,6 +51,25 @@ def test_argument_errors_come_back_as_codes_not_crashes():
     assert rc == -1 and b"fm2_fwd" in lib.ptrec_last_error()
     rc = lib.ptrec_index_prep(None, None, 4, 0, 0, None, None, None, 0, None)
     assert rc < 0
+    # K6, fp16 x 2 format: null operands / missing scale words / missing workspace are refused before any launch
+    assert lib.ptrec_tc_split2h(None, 8, 4, 8, None, 0, None, 8, None, 8, None, None, None, None, 0, None) < 0
+    assert b"tc_split" in lib.ptrec_last_error()
+    assert lib.ptrec_tc_gemm_split2h(None, None, 4, 8, None, None, 4, 8, 8, None, 0, None, 4, None, 1, None, 0, None) < 0
+    assert lib.ptrec_tc_split2h_workspace_bytes(16384, 400) >= lib.ptrec_tc_split3_workspace_bytes(16384, 400) + 4096
+    lib.ptrec_tc_set_bn(128)
+    assert lib.ptrec_tc_get_bn() == 128
+    lib.ptrec_tc_set_bn(7)          # anything but 128 selects the 256-wide tiles
+    assert lib.ptrec_tc_get_bn() == 256
+
+
+def test_k6_operand_mode_switch():
+    assert ops.tc_mode() in ("fp16x2", "bf16x3")
+    old = ops.tc_mode()
+    ops.set_tc_mode("bf16x3")
+    assert ops.tc_mode() == "bf16x3"
+    with pytest.raises(ValueError):
+        ops.set_tc_mode("tf32")
+    ops.set_tc_mode(old)
 
 
 def test_no_cpu_fallback():
