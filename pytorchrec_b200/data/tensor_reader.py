@@ -155,8 +155,10 @@ class SplitDataset:
     def train_neg_sample(self) -> None:
         self.reader.train_neg_sample()
 
-    def batches(self, batch_size: int, shuffle: bool = False, drop_last: bool = False) -> Iterator[Dict[str, Tensor]]:
-        return self.reader.batches(self.split, batch_size, shuffle=shuffle, drop_last=drop_last)
+    def batches(self, batch_size: int, shuffle: bool = False, drop_last: bool = False, rank: int = 0,
+                world_size: int = 1) -> Iterator[Dict[str, Tensor]]:
+        return self.reader.batches(self.split, batch_size, shuffle=shuffle, drop_last=drop_last, rank=rank,
+                                   world_size=world_size)
 
 
 class TensorDataReader:
@@ -366,12 +368,21 @@ class TensorDataReader:
         return batch
 
     def batches(self, split: str, batch_size: int, shuffle: bool = False, drop_last: bool = False,
-                generator: Optional[torch.Generator] = None) -> Iterator[Dict[str, Tensor]]:
+                generator: Optional[torch.Generator] = None, rank: int = 0, world_size: int = 1
+                ) -> Iterator[Dict[str, Tensor]]:
         """Iterate ``split`` in the order of ``DataLoader(dataset, batch_size, shuffle=shuffle, drop_last=drop_last)``:
         the loader's iterator draws its base seed from the global CPU generator, ``RandomSampler`` then draws the
         seed of a private generator and takes ``randperm(n)`` from it — the same draws are made here, so the same
-        torch seed gives the same batches (and leaves the global generator in the same state)."""
+        torch seed gives the same batches (and leaves the global generator in the same state).
+
+        ``world_size > 1`` (data-parallel ranks of the row-wise-sharded models, one process per GPU): every rank makes
+        the same draws (same seed on every rank, as ``set_torch_seed`` arranges) and takes the strided slice
+        ``order[rank::world_size]`` of the epoch's order, trimmed so that all ranks see the same number of samples —
+        the union over ranks of step k's batches is the reference loader's batch k of size ``world_size * batch_size``,
+        so a sharded run consumes the reference's sample stream."""
         n = self.size(split)
+        if not (0 <= rank < world_size):
+            raise ValueError(f"rank {rank} outside world of {world_size}")
         torch.empty((), dtype=torch.int64).random_(generator=generator)  # _BaseDataLoaderIter's base seed
         if shuffle:
             g = torch.Generator()
@@ -379,6 +390,9 @@ class TensorDataReader:
             order = torch.randperm(n, generator=g)
         else:
             order = torch.arange(n)
+        if world_size > 1:
+            order = order[:n - n % world_size][rank::world_size]
+            n = order.numel()
         order = order.to(self.device)
         stop = n - n % batch_size if drop_last else n
         for s in range(0, stop, batch_size):

@@ -323,13 +323,20 @@ class IModel(Module, ABC):
         return prediction
 
     # ------------------------------------------------------------------ fit / evaluate
-    @staticmethod
-    def _loader(dataset, batch_size: int, shuffle: bool, workers: int, drop_last: bool):
+    def _data_parallel_rank(self):
+        """(rank, world_size) of this replica among the data-parallel ranks; (0, 1) for single-device models.  Row-wise
+        sharded models (``distributed.sharded``) train one batch slice per rank."""
+        sh = getattr(self, "sharded", None)
+        return (int(sh.rank), int(sh.world)) if sh is not None and hasattr(sh, "world") else (0, 1)
+
+    def _loader(self, dataset, batch_size: int, shuffle: bool, workers: int, drop_last: bool):
         """Batches of ``dataset`` in ``DataLoader`` order.  A tensor-native split (``data.SplitDataset``, N2) assembles
-        whole batches by index — same samples, same order under the same seed; any other ``Dataset`` goes through
-        ``torch.utils.data.DataLoader`` exactly as in the reference (IModel.py:183-186,242,294)."""
+        whole batches by index — same samples, same order under the same seed, and for data-parallel models this
+        rank's strided slice of that order; any other ``Dataset`` goes through ``torch.utils.data.DataLoader`` exactly
+        as in the reference (IModel.py:183-186,242,294)."""
         if hasattr(dataset, "batches"):
-            return dataset.batches(batch_size, shuffle=shuffle, drop_last=drop_last)
+            rank, world = self._data_parallel_rank()
+            return dataset.batches(batch_size, shuffle=shuffle, drop_last=drop_last, rank=rank, world_size=world)
         return DataLoader(dataset=dataset, batch_size=batch_size, shuffle=shuffle, num_workers=workers,
                           drop_last=drop_last)
 

@@ -203,6 +203,29 @@ def test_batches_equal_rowwise_assembly_at_scale():
         assert torch.equal(got[key], want[key]), key
 
 
+def test_data_parallel_ranks_partition_the_reference_stream(G):
+    """world_size ranks x batch b: the union of the ranks' step-k batches is the reference loader's batch k of size
+    world_size * b (same epoch order on every rank, strided slices)."""
+    r = pair_reader(G)
+    r.train_neg_sample()
+    world, b = 2, 8
+    torch.manual_seed(100)
+    whole = list(r.batches("train", world * b, shuffle=True, drop_last=True))
+    per_rank = []
+    for rank in range(world):
+        torch.manual_seed(100)
+        per_rank.append(list(r.batches("train", b, shuffle=True, drop_last=True, rank=rank, world_size=world)))
+    assert len(per_rank[0]) == len(per_rank[1]) == len(whole)
+    for k, ref in enumerate(whole):
+        for key in ref:
+            merged = torch.stack([per_rank[rank][k][key] for rank in range(world)], dim=1).reshape(ref[key].shape)
+            assert torch.equal(merged, ref[key]), (k, key)
+    seen = torch.cat([x["index"] for rank in range(world) for x in r.batches("train", b, rank=rank, world_size=world)])
+    assert seen.numel() == len(set(seen.tolist())) == r.size("train") - r.size("train") % world
+    with pytest.raises(ValueError):
+        next(r.batches("train", b, rank=2, world_size=2))
+
+
 class _FakeFrame:
     def __init__(self, cols):
         self._c = cols
