@@ -329,13 +329,14 @@ class IModel(Module, ABC):
         sh = getattr(self, "sharded", None)
         return (int(sh.rank), int(sh.world)) if sh is not None and hasattr(sh, "world") else (0, 1)
 
-    def _loader(self, dataset, batch_size: int, shuffle: bool, workers: int, drop_last: bool):
+    def _loader(self, dataset, batch_size: int, shuffle: bool, workers: int, drop_last: bool, train: bool = False):
         """Batches of ``dataset`` in ``DataLoader`` order.  A tensor-native split (``data.SplitDataset``, N2) assembles
-        whole batches by index — same samples, same order under the same seed, and for data-parallel models this
-        rank's strided slice of that order; any other ``Dataset`` goes through ``torch.utils.data.DataLoader`` exactly
-        as in the reference (IModel.py:183-186,242,294)."""
+        whole batches by index — same samples, same order under the same seed; when TRAINING a data-parallel model it
+        yields this rank's strided slice of that order (evaluation runs the whole split on every rank, so metrics need
+        no reduction).  Any other ``Dataset`` goes through ``torch.utils.data.DataLoader`` exactly as in the reference
+        (IModel.py:183-186,242,294)."""
         if hasattr(dataset, "batches"):
-            rank, world = self._data_parallel_rank()
+            rank, world = self._data_parallel_rank() if train else (0, 1)
             return dataset.batches(batch_size, shuffle=shuffle, drop_last=drop_last, rank=rank, world_size=world)
         return DataLoader(dataset=dataset, batch_size=batch_size, shuffle=shuffle, num_workers=workers,
                           drop_last=drop_last)
@@ -353,7 +354,7 @@ class IModel(Module, ABC):
             if train_mode is not None and getattr(train_mode, "value", train_mode) == "pair_wise" \
                     and hasattr(dataset, "train_neg_sample"):
                 dataset.train_neg_sample()
-            it = iter(self._loader(dataset, batch_size, shuffle, workers, drop_last))
+            it = iter(self._loader(dataset, batch_size, shuffle, workers, drop_last, train=True))
             data = next(it, None)
             if data is not None:
                 self.prefetch(data)
