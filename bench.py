@@ -105,7 +105,7 @@ def run_reference(a):
     line = {"impl": "reference", "metric": "train_samples_per_sec", "value": sps, "unit": "samples/s",
             "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(a, 1),
+            "config": config_dict(a, max(a.gpus, 1)),
             "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": f"{steps_run} full-size train steps (batch {a.batch}) after {warm_run} warm-up, "
                                        "oracle port of the reference idiom on host cores"},
