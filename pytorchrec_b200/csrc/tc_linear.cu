@@ -8,14 +8,21 @@
 // so the result carries fp32-level error (measured against fp64 in tests) at 6 bf16 MMAs per product instead of the
 // fp32 SIMT pipe: ~10x the arithmetic rate of the cuBLAS sgemm the stock nn.Linear falls back to.
 //
-//   split3_kernel        fp32 [R, C] -> planes [3, R, Cp] and/or transposed planes [3, C, Rp]; optional ReLU-backward
+//   split_kernel<NP>     fp32 [R, C] -> planes [NP, R, Cp] and/or transposed planes [NP, C, Rp]; optional ReLU-backward
 //                        mask (g * (y > 0)) and column sums (bias gradient) fused in the same pass.       bound: HBM
-//   gemm_split3_kernel   C[M, N] = sum over the 6 pairs of A_i[M, K] B_j[N, K]^T, persistent 128 x 128 tiles;
-//                        warp 0 TMA producer (3-D maps: k, row, plane; 6 tiles = 96 KB per stage, 2 stages),
-//                        warp 1 TMEM alloc + tcgen05.mma issuer (24 MMAs per stage: every plane tile is reused by 2-3
-//                        MMAs, halving the shared-memory fill per FLOP of a plain bf16 GEMM), 8 epilogue warps drain
-//                        the double-buffered accumulator: + bias, ReLU, fp32 store; or split-K partials (wgrad).
-//                        bound: bf16 tensor pipe.  FLOPs per launch = 12 * M * N * K.
+//   gemm_split3_kernel   C[M, N] = sum over the plane pairs of A_i[M, K] B_j[N, K]^T, persistent 128 x 256 tiles;
+//   gemm_split3_2sm_...  warp 0 TMA producer (3-D maps: k, row, plane), warp 1 TMEM alloc + tcgen05.mma issuer (every
+//                        plane tile is reused by 2-3 MMAs), 8 epilogue warps drain the accumulator pair: + bias, ReLU,
+//                        fp32 store; or split-K partials (wgrad).  bound: tensor pipe fed through shared memory.
+//
+// The kernels are templates on the number of operand planes NP:
+//   NP = 3  bf16 x 3 (above): exact split, 6 MMAs per product, FLOPs per launch = 12 * M * N * K.
+//   NP = 2  fp16 x 2 (default, split3.cuh): x * s = h0 + h1 / 2^11 with a per-tensor power-of-two scale s from the
+//           tensor's absolute maximum (absmax_kernel, or a word the producing GEMM's epilogue reduced), 22 mantissa
+//           bits; A0 B0 -> main accumulator, A0 B1 + A1 B0 -> correction accumulator (carries 2^11), epilogue
+//           (main + 2^-11 corr) / (s_a s_b); 3 MMAs per product, FLOPs per launch = 6 * M * N * K.
+//   gemm_split2h_2sm_db_kernel: NP = 2 with 256 x 128 pair tiles and two accumulator pairs in TMEM (MMAs overlap the
+//           epilogue); correct, measured slower than the 256-wide tiles, selectable with ptrec_tc_set_bn.
 #include "tcgen05.cuh"
 #include "split3.cuh"
 
