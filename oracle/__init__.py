@@ -7,7 +7,9 @@ read-only at /root/reference when golden vectors are generated) computes on this
 function cites the reference file:line it follows.
 
 Pinning status
-  * PINNED by executing the unmodified reference here (``oracle/make_golden.py`` -> ``tests/golden/*.npz``):
+  * PINNED by executing the unmodified reference here (``oracle/make_golden.py``, ``make_golden_ncf.py``,
+    ``make_golden_reader.py`` -> ``tests/golden/*.npz``): the NCF model with its MLP / Dense tower, the data readers'
+    batch assembly and pair-wise negative sampler (``ref_reader.py``), and
     the lifecycle / init / param groups / train_step restatement (``IModelRef``), ``nn.Embedding`` gather,
     the SVD++ masked ``sum / sqrt(count)`` pooling, the SASRec masked-mean idiom, the FunkSVD / SVD++ /
     NCF-style interactions, dense SGD / Adam / AdamW steps, ``CrossedColumn`` arithmetic.

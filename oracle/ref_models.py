@@ -211,6 +211,38 @@ class DeepFMRef(FMRef):
         return logit + self.deep_out(self.mlp(deep_in)).squeeze(-1), self._target(data)
 
 
+class NCFRef(IModelRef):
+    """torchrec/model/NCF.py:38-79 restated: GMF (element-wise product of one table pair) beside an MLP over the
+    concatenation of a second table pair, ``Linear(emb + layers[-1], 1, bias=False)`` on their concatenation; the user
+    is repeated over the ``[B, N]`` candidate items; target = one-hot on candidate 0.  Pinned by
+    tests/golden/reference_ncf.npz (reference run) — which also pins ``MLPRef`` / ``DenseRef``."""
+
+    def __init__(self, random_seed, uid_column, iid_column, label_column, emb_size, layers, dropout=0.0):
+        self.uid_column, self.iid_column, self.label_column = uid_column, iid_column, label_column
+        self.emb_size, self.layers, self.dropout = emb_size, list(layers), dropout
+        super().__init__(random_seed)
+
+    def _init_weights(self):
+        n_u, n_i = self.uid_column.category_num, self.iid_column.category_num
+        self.mf_u_embeddings = Embedding(n_u, self.emb_size)
+        self.mf_i_embeddings = Embedding(n_i, self.emb_size)
+        self.mlp_u_embeddings = Embedding(n_u, self.emb_size)
+        self.mlp_i_embeddings = Embedding(n_i, self.emb_size)
+        self.mlp = MLPRef(2 * self.emb_size, self.layers, self.dropout)
+        self.prediction = Linear(self.emb_size + self.layers[-1], 1, bias=False)
+
+    def forward(self, data):
+        u_ids = self.uid_column.get_feature_data(data)
+        i_ids = self.iid_column.get_feature_data(data)
+        n = i_ids.shape[1]
+        u_ids = u_ids.unsqueeze(-1).repeat(1, n).reshape(-1)
+        i_ids = i_ids.reshape(-1)
+        mf = self.mf_u_embeddings(u_ids) * self.mf_i_embeddings(i_ids)
+        deep = self.mlp(torch.cat([self.mlp_u_embeddings(u_ids), self.mlp_i_embeddings(i_ids)], dim=-1))
+        pred = self.prediction(torch.cat([mf, deep], dim=-1)).reshape(-1, n)
+        return pred, _one_hot_target(pred)
+
+
 class DCNRef(IModelRef):
     """DCN-v2, parallel structure (NOT in the reference: parity unpinned).  Cross layer
     ``x_{l+1} = x0 * (x_l W_l^T + b_l) + x_l`` with ``nn.Linear(d, d)`` per layer, fp32 throughout; head and

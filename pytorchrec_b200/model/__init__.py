@@ -4,11 +4,12 @@ from typing import Dict, Type
 
 from .IModel import History, IModel
 from .ctr import DCN, DIN, FM, DeepFM
-from .mf import SVDPP, FunkSVD
+from .mf import NCF, SVDPP, FunkSVD
 
 _model_classes: Dict[str, Type[IModel]] = {
     "funksvd": FunkSVD,
     "svdpp": SVDPP,
+    "ncf": NCF,
     "fm": FM,
     "deepfm": DeepFM,
     "dcn": DCN,
@@ -23,4 +24,4 @@ def get_model_type(model_name: str) -> Type[IModel]:
     return _model_classes[model_name]
 
 
-__all__ = ["IModel", "History", "FM", "DeepFM", "DCN", "DIN", "FunkSVD", "SVDPP", "get_model_type", "model_name_list"]
+__all__ = ["IModel", "History", "FM", "DeepFM", "DCN", "DIN", "FunkSVD", "SVDPP", "NCF", "get_model_type", "model_name_list"]

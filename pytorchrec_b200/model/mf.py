@@ -1,8 +1,9 @@
-"""The reference's own embedding models re-hosted on the fused tables: FunkSVD and SVD++.
+"""The reference's own embedding models re-hosted on the fused tables: FunkSVD, SVD++ and NCF.
 
 Constructor arguments, attribute names (hence ``state_dict`` keys), forward shapes and outputs follow
-torchrec/model/FunkSVD.py:12-67 and SVDPP.py:12-91; only the embedding modules differ
-(``EmbeddingTable`` / ``MultiTableEmbedding`` instead of ``nn.Embedding``).  They exist so that the
+torchrec/model/FunkSVD.py:12-67, SVDPP.py:12-91 and NCF.py:13-79; only the embedding modules differ
+(``EmbeddingTable`` / ``MultiTableEmbedding`` instead of ``nn.Embedding``) and, for NCF, the tower's Linear layers
+run on K6 when they are large enough (``model/layer/dense.py``).  They exist so that the
 CUDA path can be checked against the UNMODIFIED reference models on identical weights and batches.
 """
 from typing import Dict
@@ -13,7 +14,7 @@ from torch.nn import Parameter
 
 from ..feature_column import CategoricalColumnWithIdentity
 from .IModel import IModel
-from .layer import EmbeddingTable
+from .layer import MLP, EmbeddingTable
 
 
 def _candidate_target(prediction: Tensor) -> Tensor:
@@ -88,3 +89,41 @@ class SVDPP(IModel):
             prediction = (u.unsqueeze(1) * i).sum(dim=-1) + u_bias.unsqueeze(1) + i_bias + self.global_bias
             target = _candidate_target(prediction)
         return prediction, target
+
+
+class NCF(IModel):
+    """Neural collaborative filtering (torchrec/model/NCF.py:38-79): GMF branch ``mf_u * mf_i`` beside
+    ``MLP([mlp_u, mlp_i])``, ``Linear(emb + layers[-1], 1, bias=False)`` on their concatenation.  ``iid`` is
+    ``[B, N]`` (candidates; N = 2 for pair-wise training) and the user is repeated over the candidates."""
+
+    def __init__(self, random_seed: int, uid_column: CategoricalColumnWithIdentity,
+                 iid_column: CategoricalColumnWithIdentity, label_column: CategoricalColumnWithIdentity,
+                 emb_size: int, layers, dropout: float):
+        self.uid_column = uid_column
+        self.iid_column = iid_column
+        self.label_column = label_column
+        self.emb_size = emb_size
+        self.layers = list(layers)
+        self.dropout = dropout
+        super().__init__(random_seed)
+
+    def _init_weights(self):
+        n_u, n_i = self.uid_column.category_num, self.iid_column.category_num
+        self.mf_u_embeddings = EmbeddingTable(n_u, self.emb_size)
+        self.mf_i_embeddings = EmbeddingTable(n_i, self.emb_size)
+        self.mlp_u_embeddings = EmbeddingTable(n_u, self.emb_size)
+        self.mlp_i_embeddings = EmbeddingTable(n_i, self.emb_size)
+        self.mlp = MLP(input_units=2 * self.emb_size, hidden_units_list=self.layers, activation="relu",
+                       dropout=self.dropout)
+        self.prediction = torch.nn.Linear(self.emb_size + self.layers[-1], 1, bias=False)
+
+    def forward(self, data: Dict[str, Tensor]):
+        u_ids = self.uid_column.get_feature_data(data)            # [B]
+        i_ids = self.iid_column.get_feature_data(data)            # [B, N]
+        n = i_ids.shape[1]
+        u_ids = u_ids.unsqueeze(-1).repeat(1, n).reshape(-1)      # [B * N]
+        i_ids = i_ids.reshape(-1)
+        mf = self.mf_u_embeddings(u_ids) * self.mf_i_embeddings(i_ids)
+        deep = self.mlp(torch.cat([self.mlp_u_embeddings(u_ids), self.mlp_i_embeddings(i_ids)], dim=-1))
+        prediction = self.prediction(torch.cat([mf, deep], dim=-1)).reshape(-1, n)
+        return prediction, _candidate_target(prediction)

@@ -36,6 +36,11 @@ def golden_idioms():
 
 
 @pytest.fixture(scope="session")
+def golden_ncf():
+    return np.load(os.path.join(GOLDEN, "reference_ncf.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_ctr():
     return np.load(os.path.join(GOLDEN, "oracle_ctr.npz"))
 

@@ -113,6 +113,23 @@ def test_seed_parity_with_reference_models(golden_mf):
     m.load_state_dict(state_from(golden_mf, "svdpp_point_sgd/final"))
 
 
+def test_ncf_seed_parity_and_checkpoint_keys_with_reference_run(golden_ncf):
+    """The product NCF (fused tables + K6-capable tower) has the reference NCF's ``state_dict`` keys and, under the same
+    seed, its initial weights bit for bit — a reference checkpoint loads unchanged."""
+    from conftest import state_from
+    from pytorchrec_b200.model import NCF, get_model_type
+    n_u, n_i, D, B, steps, *layers = (int(x) for x in golden_ncf["dims"])
+    model = NCF(2020, Col(n_u, "uid"), Col(n_i, "iid"), Col(2, "label"), D, layers, 0.0)
+    init = state_from(golden_ncf, "ncf_n2_sgd/init")
+    assert list(model.state_dict().keys()) == list(init.keys())
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, init[k]), k
+    model.load_state_dict(state_from(golden_ncf, "ncf_n2_sgd/final"))
+    assert get_model_type("ncf") is NCF
+    groups = model.get_parameters()
+    assert sum(p.numel() for p in groups[1]["params"]) == sum(layers)   # the tower's biases, undecayed
+
+
 def test_deepfm_seed_parity_with_oracle_twin(golden_ctr):
     F, nd, D, B = (int(x) for x in golden_ctr["dims"])
     rows = [int(r) for r in golden_ctr["rows"]]

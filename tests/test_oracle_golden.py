@@ -68,6 +68,34 @@ def test_restated_models_match_reference_run(golden_mf, case):
         np.testing.assert_allclose(v.numpy(), final[k].numpy(), rtol=1e-5, atol=1e-7, err_msg=k)
 
 
+@pytest.mark.parametrize("case", ["ncf_n2_sgd", "ncf_n2_adam", "ncf_n5_sgd"])
+def test_ncf_restatement_matches_reference_run(golden_ncf, case):
+    """NCF (torchrec/model/NCF.py) runs the MLP / Dense tower and the concat -> Linear(., 1) head: the reference's
+    own run pins ``NCFRef`` and with it ``MLPRef`` / ``DenseRef``, the tower every CTR oracle twin is built from."""
+    assert int(golden_ncf["pinned_by_reference"]) == 1 and case in list(golden_ncf["cases"])
+    n_u, n_i, D, B, steps, *layers = (int(x) for x in golden_ncf["dims"])
+    model = ref_models.NCFRef(2020, Col(n_u, "uid"), Col(n_i, "iid"), Col(2, "label"), D, layers, 0.0)
+    init = state_from(golden_ncf, f"{case}/init")
+    assert list(model.state_dict().keys()) == list(init.keys())
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, init[k]), f"seed parity broken for {k}"
+    from pytorchrec_b200.loss import BPRLoss
+    opt = (torch.optim.SGD(model.get_parameters(), lr=0.5) if case.endswith("sgd")
+           else torch.optim.Adam(model.get_parameters(), lr=0.01))
+    model.compile(opt, BPRLoss() if "_n2_" in case else torch.nn.BCEWithLogitsLoss())
+    for s in range(steps):
+        batch = batch_from(golden_ncf, f"{case}/batch{s}")
+        model.eval()
+        with torch.no_grad():
+            pred, target = model(batch)
+        np.testing.assert_allclose(pred.numpy(), golden_ncf[f"{case}/pred{s}"], rtol=1e-5, atol=1e-8)
+        np.testing.assert_array_equal(target.numpy(), golden_ncf[f"{case}/target{s}"])
+        np.testing.assert_allclose(model.train_step(batch)["loss"].item(), golden_ncf[f"{case}/loss{s}"], rtol=1e-6)
+    final = state_from(golden_ncf, f"{case}/final")
+    for k, v in model.state_dict().items():
+        np.testing.assert_allclose(v.numpy(), final[k].numpy(), rtol=1e-5, atol=1e-7, err_msg=k)
+
+
 def test_mask_and_mean_pool_idiom(golden_idioms):
     his = torch.from_numpy(golden_idioms["his"])
     valid = ref_ops.valid_mask(his, "pad_keep_first")
