@@ -50,6 +50,8 @@ def parse():
                     help="cfg2 (default, the bench line): 26x1e6xD16, B 16384/GPU.  cfg5: 26 x (5e7*G/8) rows x D64, "
                          "B 65536/GPU, row-wise sharded (weak-scaling series of SURVEY 8d)")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--pipelined-loss", action="store_true",
+                    help="e2e: read step k's loss from a pinned buffer after step k+1 is enqueued (experimental)")
     return ap.parse_args()
 
 
@@ -210,6 +212,25 @@ def run_b200(a):
         ev0.record()
         if read_loss:  # end to end: the data-loader pattern of IModel.fit (prefetch batch k+1 while step k runs)
             model.prefetch(batches[0])
+        if read_loss and a.pipelined_loss:
+            # experimental (off by default, not yet measured): every step's loss still reaches the host inside the
+            # timed region, but through a pinned buffer read AFTER the next step has been enqueued, so the device
+            # does not idle while the host issues the next prefetch + graph launch
+            pin = torch.empty(2, dtype=torch.float32).pin_memory()
+            evs = [None, None]
+            for i in range(steps):
+                logs = model.train_step(batches[i % len(batches)])
+                pin[i & 1:(i & 1) + 1].copy_(logs["loss"].detach().reshape(1), non_blocking=True)
+                evs[i & 1] = torch.cuda.Event()
+                evs[i & 1].record()
+                if i + 1 < steps:
+                    model.prefetch(batches[(i + 1) % len(batches)])
+                if i > 0:
+                    evs[(i - 1) & 1].synchronize()
+                    float(pin[(i - 1) & 1])
+            evs[(steps - 1) & 1].synchronize()
+            float(pin[(steps - 1) & 1])
+            steps = 0  # the loop below is skipped
         for i in range(steps):
             logs = model.train_step(batches[i % len(batches)])
             if read_loss:
