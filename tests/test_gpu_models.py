@@ -52,9 +52,6 @@ def test_reference_models_on_fused_tables_match_reference_run(golden_mf, case):
         np.testing.assert_allclose(v.cpu().numpy(), final[k].numpy(), rtol=1e-5, atol=1e-7, err_msg=k)
 
 
-@pytest.mark.skipif(os.environ.get("PTREC_TEST_UNVALIDATED") != "1",
-                    reason="written after the round's GPU budget was spent: not yet run on hardware "
-                           "(PTREC_TEST_UNVALIDATED=1 runs it)")
 @pytest.mark.parametrize("case", ["ncf_n2_sgd", "ncf_n5_sgd"])
 def test_reference_ncf_on_fused_tables_and_k6_tower_matches_reference_run(golden_ncf, case):
     """NCF on EmbeddingTable + SparseSGD with its MLP on the tensor-core Linear path reproduces the reference's own
