@@ -24,6 +24,7 @@ All-to-all path (NCCL only; any backend that offers all_to_all_single):
   backward  scatter gradient rows into the send layout -> all_to_all(grads)
             -> owner-side sort / dedup / segment-sum / fused optimizer update (no gradient returns)
 """
+import copy
 import math
 import os
 import weakref
@@ -44,9 +45,25 @@ def shard_rows(total_rows: int, world: int, rank: int) -> int:
     return (total_rows - rank + world - 1) // world if total_rows > rank else 0
 
 
-def list_capacity(batch: int, world: int, factor: float = 1.25) -> int:
-    """Slots per (owner, field) list: expected batch/world plus slack, multiple of 16."""
-    c = int(math.ceil(batch / world * factor)) + 64
+def owner_share(category_nums: Sequence[int], world: int) -> float:
+    """Largest fraction of one field's lookups that a single owner can expect under ``owner = id mod G`` with ids
+    uniform over the field's categories: ``max_f ceil(R_f / G) / R_f``.  ``1 / G`` for tall tables; a field with
+    fewer categories than ranks sends ``1 / R_f`` of the batch to each of its ``R_f`` owners (Criteo has fields with
+    3-10 categories)."""
+    share = 1.0 / world
+    for r in category_nums:
+        r = max(int(r), 1)
+        share = max(share, ((r + world - 1) // world) / r)
+    return share
+
+
+def list_capacity(batch: int, world: int, factor: float = 1.25, share: Optional[float] = None) -> int:
+    """Slots per (owner, field) list: the expected ``batch * share`` (``share`` = ``owner_share`` of the columns,
+    ``1 / world`` when not given) plus slack, a multiple of 16, never more than the batch (which cannot overflow).
+    Hot ids can still exceed it (every duplicate of an id lands on the same owner): the pack kernels then raise the
+    overflow word, which ``RowWiseShardedEmbedding`` turns into a RuntimeError (``poll_errors`` / ``check_errors``)."""
+    share = 1.0 / world if share is None else share
+    c = int(math.ceil(batch * share * factor)) + 64
     return min((c + 15) // 16 * 16, (batch + 15) // 16 * 16)
 
 
@@ -85,8 +102,9 @@ class _ShardedLookup(torch.autograd.Function):
     def forward(ctx, mod: "RowWiseShardedEmbedding", ids: Tensor, *weights):
         F, B = ids.shape
         G, dev = mod.world, ids.device
-        C = list_capacity(B, G, mod.capacity_factor)
+        C = mod.capacity(B)
         send_ids, ret_pos = ops.a2a_pack_by_owner(ids, F, B, G, C, mod.overflow_flag(dev))
+        mod.publish_overflow(dev)
         recv_ids = torch.empty_like(send_ids)
         dist.all_to_all_single(recv_ids, send_ids, group=mod.group)            # [G_src, F, C]
         own_ids = recv_ids.permute(1, 0, 2).contiguous().view(-1)              # [F, G_src, C]
@@ -170,11 +188,12 @@ class _PeerLookup(torch.autograd.Function):
         G, S = mod.world, mod.slot_width
         (ids,) = ctx.saved_tensors
         dev = ids.device
-        C = list_capacity(B, G, mod.capacity_factor)
+        C = mod.capacity(B)
         pb = mod.peer_buffers(C, dev)
         if mod._dirty:  # the owners may still be consuming / resetting their buffers from an earlier backward
             mod.fence(dev)
         ret_pos = ops.a2a_pack_by_owner_peer(ids, F, B, G, C, mod.rank, pb["peer_ids"], mod.overflow_flag(dev))
+        mod.publish_overflow(dev)
         gs = []
         for k, D in enumerate(mod.dims):
             g = grads[k]
@@ -225,6 +244,17 @@ class RowWiseShardedEmbedding(nn.Module):
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.capacity_factor = capacity_factor
+        # Exchange lists are sized for the fullest owner of the lowest-cardinality field (ids uniform over the
+        # field's categories); a field with very few categories makes EVERY list that long, so it is better kept out
+        # of the sharded module (replicated) — say so once.
+        self.owner_share = owner_share([c.category_num for c in self.columns], self.world)
+        if self.owner_share > 2.0 / self.world:
+            import warnings
+            small = [getattr(c, "feature_name", "?") for c in self.columns if c.category_num < 2 * self.world]
+            warnings.warn(f"row-wise sharding over {self.world} ranks: columns {small} have fewer categories than "
+                          f"2 x ranks, so every exchange list is sized for {self.owner_share:.0%} of the batch instead "
+                          f"of {1.0 / self.world:.0%}; replicate such tiny tables instead of sharding them")
+        self._overflow_host: Dict[torch.device, Tensor] = {}
         self.grad_scale = 1.0 / self.world  # mean loss over the GLOBAL batch
         if self.world * len(self.columns) > 256:
             raise ValueError("world_size * n_fields must be <= 256")
@@ -379,12 +409,37 @@ class RowWiseShardedEmbedding(nn.Module):
             self._bufs[key] = b
         return b
 
+    def capacity(self, batch: int) -> int:
+        """Slots per (owner, field) exchange list for a per-rank batch of ``batch`` samples."""
+        return list_capacity(batch, self.world, self.capacity_factor, self.owner_share)
+
     def overflow_flag(self, device) -> Tensor:
         t = self._overflow.get(device)
         if t is None:
             t = torch.zeros(1, dtype=torch.int32, device=device)
             self._overflow[device] = t
         return t
+
+    def publish_overflow(self, device) -> None:
+        """Enqueue (or capture into the step graph) a copy of the sticky overflow word into pinned host memory, so
+        that ``poll_errors`` can see it without synchronising."""
+        pin = self._overflow_host.get(device)
+        if pin is None:
+            pin = self._overflow_host[device] = torch.zeros(1, dtype=torch.int32).pin_memory()
+        pin.copy_(self.overflow_flag(device), non_blocking=True)
+
+    def poll_errors(self) -> None:
+        """Non-synchronising check, called at the top of every forward / train_step: raises once a pack launch of an
+        EARLIER step is known to have overflowed a list (the word is sticky, so nothing is missed — the error
+        surfaces one or two steps late instead of corrupting the run silently: a dropped lookup reads as a zero
+        row in the forward and loses its gradient in the backward)."""
+        for pin in self._overflow_host.values():
+            v = int(pin[0])
+            if v:
+                raise RuntimeError(
+                    f"a row-wise sharded lookup list overflowed its capacity (needed {v} slots): lookups were dropped "
+                    "in an earlier step — results since then are invalid.  Raise capacity_factor (hot ids send all "
+                    "their duplicates to one owner) or replicate low-cardinality columns")
 
     def owner_layout(self, C: int, k: int = 0) -> ops.FeatureLayout:
         """Owner-side view of the received lists for width k: feature (f, src) reads table f, batch = C, and writes
@@ -406,6 +461,7 @@ class RowWiseShardedEmbedding(nn.Module):
         return lay
 
     def forward(self, batch: Dict[str, Tensor]):
+        self.poll_errors()
         if not self.egroups:
             self.egroups = [EmbeddingGroup([t for t in g], d) for g, d in zip(self.groups, self.dims)]
         ids = torch.stack([c.get_feature_data(batch).reshape(-1) for c in self.columns])  # [F, B]
@@ -432,7 +488,10 @@ class RowWiseShardedEmbedding(nn.Module):
             v = int(t.item())
             if v:
                 t.zero_()
-                raise RuntimeError(f"an all-to-all lookup list overflowed its capacity (needed {v}); raise capacity_factor")
+                for pin in self._overflow_host.values():
+                    pin.zero_()
+                raise RuntimeError(f"a row-wise sharded lookup list overflowed its capacity (needed {v} slots; lookups "
+                                   "were dropped); raise capacity_factor or replicate low-cardinality columns")
         for eg in self.egroups:
             eg.check_index_errors()
 
@@ -475,15 +534,60 @@ class ShardedDeepFM(DeepFM):
         out = {k: v.detach().cpu() for k, v in self.state_dict().items() if not k.startswith("sharded.")}
         for k, name in enumerate(self._GROUP_NAMES):
             for f, (col, table) in enumerate(zip(self.sparse_columns, self.sharded.groups[k])):
-                local = table.weight.detach().contiguous()
-                cap = (col.category_num + G - 1) // G
-                padded = torch.zeros(cap, local.shape[1], dtype=local.dtype, device=local.device)
-                padded[:local.shape[0]] = local
-                parts = [torch.empty_like(padded) for _ in range(G)]
-                dist.all_gather(parts, padded, group=self.sharded.group)
-                full = torch.stack(parts, dim=1).reshape(cap * G, local.shape[1])[:col.category_num]
-                out[f"{name}.{f}.weight"] = full.cpu()
+                n_own = shard_rows(col.category_num, G, self.sharded.rank)
+                full = self._gather_rows(table.weight[:n_own], col.category_num)
+                out[f"{name}.{f}.weight"] = full
         return out
+
+    def _gather_rows(self, local: Tensor, category_num: int) -> Tensor:
+        """[local_rows, ...] shards of every rank -> the full [category_num, ...] tensor (row = local_row * G + rank)."""
+        G = self.sharded.world
+        local = local.detach().contiguous()
+        cap = (category_num + G - 1) // G
+        padded = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        padded[:min(local.shape[0], cap)] = local[:cap]
+        parts = [torch.empty_like(padded) for _ in range(G)]
+        dist.all_gather(parts, padded, group=self.sharded.group)
+        return torch.stack(parts, dim=1).reshape((cap * G,) + tuple(local.shape[1:]))[:category_num].cpu()
+
+    @torch.no_grad()
+    def full_optimizer_state_dict(self) -> Dict:
+        """N4 ("incl. optimizer state"; the reference saves weights only, IModel.py:79-81): the fused
+        optimizer's state in UNSHARDED form (collective: call on every rank) —
+        ``{"tables": {"embeddings.{f}.weight": {"sum": [category_num, D]}, ...}, "dense": <state_dict of the dense
+        companion>, "step": n}`` — so that a run can restart on a different number of GPUs."""
+        opt = self.compiled_optimizers
+        if opt is None or not hasattr(opt, "table_state"):
+            raise RuntimeError("full_optimizer_state_dict needs a compiled pytorchrec_b200.optim sparse optimizer")
+        out = {"tables": {}, "step": int(opt._step_count_fused)}
+        for k, name in enumerate(self._GROUP_NAMES):
+            for f, (col, table) in enumerate(zip(self.sparse_columns, self.sharded.groups[k])):
+                shard_n = shard_rows(col.category_num, self.sharded.world, self.sharded.rank)
+                out["tables"][f"{name}.{f}.weight"] = {
+                    sn: self._gather_rows(st[:shard_n], col.category_num) for sn, st in opt.table_state(table.weight).items()}
+        opt._ensure_dense()
+        out["dense"] = copy.deepcopy(opt._dense.state_dict()) if opt._dense is not None else None
+        return out
+
+    @torch.no_grad()
+    def load_full_optimizer_state_dict(self, state: Dict) -> None:
+        """Inverse of ``full_optimizer_state_dict`` (each rank keeps rows ``rank::G`` of every table's state)."""
+        opt = self.compiled_optimizers
+        G, rank = self.sharded.world, self.sharded.rank
+        for k, name in enumerate(self._GROUP_NAMES):
+            for f, table in enumerate(self.sharded.groups[k]):
+                full = state["tables"][f"{name}.{f}.weight"]
+                cur = opt.table_state(table.weight)
+                for sn, v in full.items():
+                    shard = v[rank::G].to(cur[sn].device)
+                    cur[sn][:shard.shape[0]].copy_(shard)
+        if state.get("dense") is not None:
+            opt._ensure_dense()
+            opt._dense.load_state_dict(state["dense"])
+        opt._step_count_fused = int(state.get("step", 0))
+        opt._ptr_cache.clear()
+        if self.sharded.peer:
+            self.sharded.sync_peers()
 
     @torch.no_grad()
     def load_full_state_dict(self, state_dict: Dict[str, Tensor]) -> None:

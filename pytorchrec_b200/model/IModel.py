@@ -38,6 +38,38 @@ class History:
             self.history.setdefault(k, []).append(v)
 
 
+class _Callbacks:
+    """The slice of torchrec/callback/CallbackList.py that ``fit`` drives (IModel.py:160-208): ``set_model`` /
+    ``set_params`` at construction, then ``on_train_begin``, ``on_epoch_begin``, ``on_epoch_end``, ``on_train_end``.
+    Callbacks are duck-typed (a reference-style ``ICallback`` works unchanged); missing hooks are skipped."""
+
+    def __init__(self, callbacks, model, **params):
+        self.callbacks = list(callbacks or [])
+        for cb in self.callbacks:
+            if hasattr(cb, "set_model"):
+                cb.set_model(model)
+            if hasattr(cb, "set_params"):
+                cb.set_params(params)
+
+    def _call(self, hook: str, *args):
+        for cb in self.callbacks:
+            fn = getattr(cb, hook, None)
+            if fn is not None:
+                fn(*args)
+
+    def on_train_begin(self, logs=None):
+        self._call("on_train_begin", logs)
+
+    def on_train_end(self, logs=None):
+        self._call("on_train_end", logs)
+
+    def on_epoch_begin(self, epoch, logs=None):
+        self._call("on_epoch_begin", epoch, logs)
+
+    def on_epoch_end(self, epoch, logs=None):
+        self._call("on_epoch_end", epoch, logs)
+
+
 _LOOKUP_CACHE_KEY = "__ptrec_lookup_cache__"
 
 
@@ -169,7 +201,12 @@ class IModel(Module, ABC):
         self.to(device)
 
     def save_weights(self, filepath: str):
-        torch.save(self.state_dict(), filepath, pickle_protocol=pickle.HIGHEST_PROTOCOL)
+        # A table owned by a fused optimizer is a strided view of its interleaved weight | state buffer, and
+        # torch.save serialises a view's WHOLE storage: clone to contiguous tensors so that the file holds the
+        # weights only (the reference's checkpoint content, IModel.py:79-81) at their own size.
+        sd = {k: (v.detach().clone(memory_format=torch.contiguous_format) if isinstance(v, torch.Tensor) else v)
+              for k, v in self.state_dict().items()}
+        torch.save(sd, filepath, pickle_protocol=pickle.HIGHEST_PROTOCOL)
 
     def get_parameters(self):
         """Two param groups: weights, and biases with ``weight_decay=0`` (IModel.py:83-92)."""
@@ -204,6 +241,8 @@ class IModel(Module, ABC):
         self._graphed = _GraphedTrainStep(self, warmup) if enabled else None
 
     def train_step(self, data: Dict):
+        for m in self._flag_pollers():  # non-synchronising: error words published by earlier steps (pinned host memory)
+            m.poll_errors()
         if self._graphed is not None and self.compiled_device is not None and self.compiled_device.type == "cuda":
             return self._graphed.step(data)
         return self._eager_train_step(data)
@@ -305,6 +344,12 @@ class IModel(Module, ABC):
         self.compiled_optimizers.step(closure=None)
         return loss
 
+    def _flag_pollers(self) -> list:
+        p = self.__dict__.get("_pollers")
+        if p is None:
+            p = self.__dict__["_pollers"] = [m for m in self.modules() if m is not self and hasattr(m, "poll_errors")]
+        return p
+
     def _before_optimizer_step(self) -> None:
         """Hook between backward and step (data-parallel models all-reduce dense gradients here)."""
 
@@ -346,11 +391,16 @@ class IModel(Module, ABC):
             workers: int = 0, drop_last: bool = False, dev_batch_size: Optional[int] = None,
             dev_freq: int = 1) -> History:
         self._assert_compile_was_called()
-        callbacks = list(callbacks or [])
+        if not (hasattr(callbacks, "on_train_begin") and hasattr(callbacks, "on_epoch_end")):  # a plain list
+            n = len(dataset) if hasattr(dataset, "__len__") else 0
+            batches = n // batch_size if drop_last else (n + batch_size - 1) // batch_size
+            callbacks = _Callbacks(callbacks, self, verbose=verbose, epochs=epochs, batches=batches)
         self.history = History()
         self.stop_training = False
         logs: Dict[str, Any] = {}
+        callbacks.on_train_begin()
         for epoch in range(epochs):
+            callbacks.on_epoch_begin(epoch)
             if train_mode is not None and getattr(train_mode, "value", train_mode) == "pair_wise" \
                     and hasattr(dataset, "train_neg_sample"):
                 dataset.train_neg_sample()
@@ -366,13 +416,22 @@ class IModel(Module, ABC):
             epoch_logs = copy.copy(logs)
             if dev_dataset is not None and (epoch + 1) % dev_freq == 0:
                 epoch_logs.update(self.evaluate(dev_dataset, dev_batch_size or batch_size, workers=workers))
+            self._check_device_flags()
             self.history.on_epoch_end(epoch, epoch_logs)
-            for cb in callbacks:
-                if hasattr(cb, "on_epoch_end"):
-                    cb.on_epoch_end(epoch, epoch_logs)
+            callbacks.on_epoch_end(epoch, epoch_logs)
             if self.stop_training:
                 break
+        callbacks.on_train_end()
         return self.history
+
+    def _check_device_flags(self) -> None:
+        """Once per epoch (one host sync): raise on any error word the kernels set during it — an out-of-range id
+        (the reference raises IndexError from index_select on the CPU) or an overflowed exchange list of a row-wise
+        sharded table — instead of training on silently."""
+        for m in self.modules():
+            chk = getattr(m, "check_errors", None) or getattr(m, "check_index_errors", None)
+            if chk is not None and m is not self:
+                chk()
 
     @torch.no_grad()
     def evaluate(self, dataset: Dataset, batch_size: int, verbose: int = 0, callbacks=None, workers: int = 0):

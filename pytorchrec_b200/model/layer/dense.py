@@ -4,11 +4,11 @@
 ``MLP`` = ``Sequential`` of ``dense_{i}`` blocks under the attribute ``mlp``.
 
 On a CUDA device the Linear -> ReLU pair and its backward run on the tcgen05 tensor cores through K6
-(csrc/tc_linear.cu): every fp32 operand is split exactly into three bf16 planes and the product is accumulated in
-fp32 from the six significant plane pairs, which keeps fp32-level error (the reference computes these GEMMs in
-fp32 and the north star asks for 1e-5) at 3-5x the speed of the fp32 SIMT sgemm behind ``nn.Linear``.
-``PTREC_TC_MODE=fp16x2`` (``ops.set_tc_mode``) selects the two-plane fp16 operand format instead: a per-tensor
-power-of-two scale, 22 mantissa bits, half the MMAs and two thirds of the operand bytes (include/ptrec_b200.h).  The ReLU
+(csrc/tc_linear.cu) at fp32-level error (the reference computes these GEMMs in fp32 and the north star asks for
+1e-5), 3-5x faster than the fp32 SIMT sgemm behind ``nn.Linear``.  Default operand format ``fp16x2``: each fp32
+operand is scaled by a per-tensor power of two and split into two fp16 planes (22 mantissa bits), three MMAs per
+product.  ``PTREC_TC_MODE=bf16x3`` (``ops.set_tc_mode``) selects the exact three-plane bf16 split instead (six plane
+pairs accumulated in fp32; include/ptrec_b200.h).  The ReLU
 mask and the bias gradient are fused into the pass that splits the incoming gradient.  ``PTREC_TC_LINEAR=0`` selects
 the stock ``nn.Linear`` path (cuBLAS fp32) for A/B measurements."""
 import os

@@ -10,8 +10,10 @@ runs all lookups + pooling of a batch in one gather launch and one fused backwar
 
 Backward semantics: gradients never materialise as ``[rows, D]`` tensors.  When the tables are
 owned by a ``pytorchrec_b200.optim`` sparse optimizer the row update happens inside ``backward()``
-(sort -> dedup -> segment-sum -> update); otherwise ``weight.grad`` receives a coalesced
-``torch.sparse_coo_tensor`` built from the same segment sums.
+(sort -> dedup -> segment-sum -> update).  Otherwise (stock ``torch.optim`` / the reference's ``AdamW``)
+``weight.grad`` is built from the same segment sums with ``nn.Embedding``'s own convention: a dense
+``[rows, D]`` tensor by default (``sparse=False`` — what the reference's models produce, so ``adam`` / ``adamw`` /
+``sgd`` with weight decay keep working unchanged), a coalesced ``torch.sparse_coo_tensor`` with ``sparse=True``.
 """
 from typing import Dict, List, Optional, Sequence, Union
 
@@ -96,9 +98,14 @@ class EmbeddingGroup:
         for t, table in enumerate(self.tables):
             sel = valid & (seg_table == t)
             idx = keys[sel].long() & 0xFFFFFFFF
-            g = torch.sparse_coo_tensor(idx.unsqueeze(0), row_grad[:n][sel], size=table.weight.shape,
-                                        check_invariants=False)
-            grads.append(g._coalesced_(True))  # segments are unique sorted rows by construction
+            if getattr(table, "sparse", False):
+                g = torch.sparse_coo_tensor(idx.unsqueeze(0), row_grad[:n][sel], size=table.weight.shape,
+                                            check_invariants=False)
+                grads.append(g._coalesced_(True))  # segments are unique sorted rows by construction
+            else:  # nn.Embedding(sparse=False): the dense gradient every stock optimizer accepts
+                g = torch.zeros(table.weight.shape, dtype=row_grad.dtype, device=row_grad.device)
+                g[idx] = row_grad[:n][sel]       # unique rows: a plain scatter, no accumulation order involved
+                grads.append(g)
         return grads
 
 
@@ -154,12 +161,14 @@ class _FusedLookup(torch.autograd.Function):
 class EmbeddingTable(nn.Module):
     """``nn.Embedding``-compatible table: ``EmbeddingTable(num_embeddings, embedding_dim)``,
     parameter ``weight`` ``[num_embeddings, embedding_dim]`` fp32, N(0,1) at construction like
-    ``nn.Embedding.reset_parameters``.  ``forward(ids)`` returns ``weight[ids]`` for ids of any shape."""
+    ``nn.Embedding.reset_parameters``.  ``forward(ids)`` returns ``weight[ids]`` for ids of any shape.
+    ``sparse`` has ``nn.Embedding``'s meaning and matters only without a fused optimizer (module docstring)."""
 
-    def __init__(self, num_embeddings: int, embedding_dim: int, device=None):
+    def __init__(self, num_embeddings: int, embedding_dim: int, device=None, sparse: bool = False):
         super().__init__()
         self.num_embeddings = int(num_embeddings)
         self.embedding_dim = int(embedding_dim)
+        self.sparse = bool(sparse)
         self.weight = nn.Parameter(torch.empty(self.num_embeddings, self.embedding_dim, device=device))
         nn.init.normal_(self.weight)
         self._group = None
@@ -212,6 +221,10 @@ class EmbeddingTable(nn.Module):
             lens32 = lens.reshape(1, B).to(torch.int32).contiguous()
         return _FusedLookup.apply(self._group, lay, flat, lens32, B, None, self.weight)
 
+    def check_index_errors(self) -> None:
+        if self._group is not None:
+            self._group.check_index_errors()
+
     def extra_repr(self):
         return f"{self.num_embeddings}, {self.embedding_dim}"
 
@@ -230,6 +243,7 @@ class MultiTableEmbedding(nn.ModuleList):
     :param mask: 'none' | 'pad' (id != 0, SVDPP.py:49) | 'pad_keep_first' (model/utils.py:5-10) | 'lens'.
     :param lens_columns: for mask='lens', ``{feature_name: CategoricalColumn}`` giving the valid length.
     :param share: ``{feature_name: feature_name_of_table_owner}`` — several features reading one table.
+    :param sparse: ``nn.Embedding``'s flag for the gradient layout without a fused optimizer (dense by default).
     ``pooling`` / ``mask`` may also be dicts keyed by feature name.
     ``forward(batch)`` returns ``[B, F, D]`` in ``columns`` order.
     """
@@ -237,7 +251,7 @@ class MultiTableEmbedding(nn.ModuleList):
     def __init__(self, columns: Sequence[CategoricalColumn], emb_size: int,
                  pooling: Union[str, Dict[str, str]] = "sum", mask: Union[str, Dict[str, str]] = "none",
                  lens_columns: Optional[Dict[str, CategoricalColumn]] = None,
-                 share: Optional[Dict[str, str]] = None, device=None):
+                 share: Optional[Dict[str, str]] = None, device=None, sparse: bool = False):
         super().__init__()
         self.columns = list(columns)
         self.emb_size = int(emb_size)
@@ -252,7 +266,7 @@ class MultiTableEmbedding(nn.ModuleList):
                 if owner != name:
                     raise ValueError(f"feature {name} shares the table of {owner}, which must come first")
                 owner_index[owner] = len(self)
-                self.append(EmbeddingTable(c.category_num, self.emb_size, device=device))
+                self.append(EmbeddingTable(c.category_num, self.emb_size, device=device, sparse=sparse))
             self._table_of.append(owner_index[owner])
         self._pooling = {n: (pooling.get(n, "sum") if isinstance(pooling, dict) else pooling) for n in names}
         self._mask = {n: (mask.get(n, "none") if isinstance(mask, dict) else mask) for n in names}

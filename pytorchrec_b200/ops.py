@@ -80,14 +80,25 @@ class FeatureLayout:
         return self.total_bag_len * batch
 
 
-_workspaces: Dict[Tuple[str, torch.device], torch.Tensor] = {}
+_workspaces: Dict[tuple, torch.Tensor] = {}
+_retired_workspaces: List[torch.Tensor] = []  # superseded buffers: never handed back to the allocator (see below)
 
 
 def _workspace(name: str, nbytes: int, device: torch.device) -> torch.Tensor:
-    """Grow-only byte scratch per (name, device).  Caller-owned memory, per the ABI contract."""
-    key = (name, device)
+    """Byte scratch per (name, device, stream).  Caller-owned memory, per the ABI contract.
+
+    * Keyed by the CURRENT STREAM as well: the early sort on the side stream and a main-stream sort of another
+      embedding group never share scratch, so no cross-stream ordering is needed between them.
+    * Grow-only, and a superseded buffer is kept alive for the life of the process: its address may be baked into a
+      captured whole-step CUDA graph, whose replays would otherwise write into a block the caching allocator has
+      handed to someone else (a larger evaluate() batch, a second model in the process).  Growth is geometric so the
+      retired bytes stay below the live ones."""
+    key = (name, device, torch.cuda.current_stream(device).cuda_stream)
     t = _workspaces.get(key)
     if t is None or t.numel() < nbytes:
+        if t is not None:
+            _retired_workspaces.append(t)
+            nbytes = max(nbytes, 2 * t.numel())
         t = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
         _workspaces[key] = t
     return t

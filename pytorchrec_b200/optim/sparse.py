@@ -223,6 +223,25 @@ class _FusedSparseOptimizer(Optimizer):
                                                       ctypes.byref(args), stream), "ptrec_dense_optim_step")
         return True
 
+    # ---- per-table optimizer state (N4: sharded checkpoints gather / scatter it row-wise) -----------------------
+    def table_state(self, p: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """The state tensors of fused table ``p`` by name (``sum`` / ``exp_avg`` / ``exp_avg_sq``), created if the
+        first step has not happened yet; views into the interleaved buffer where there is one."""
+        if p not in self._fused:
+            raise KeyError("not a table owned by this fused optimizer")
+        if self.N_STATE:
+            self._state_tensors(p)
+        return {k: v for k, v in self.state[p].items() if torch.is_tensor(v)}
+
+    @torch.no_grad()
+    def load_table_state(self, p: torch.Tensor, state: Dict[str, torch.Tensor]) -> None:
+        cur = self.table_state(p)
+        for k, v in state.items():
+            if k not in cur or cur[k].shape != v.shape:
+                raise ValueError(f"optimizer state {k!r}: expected shape {tuple(cur[k].shape) if k in cur else None}, "
+                                 f"got {tuple(v.shape)}")
+            cur[k].copy_(v)
+
     def _ensure_dense(self):
         if self._dense is None and self._dense_spec is not None:
             cls, groups, kwargs = self._dense_spec

@@ -19,6 +19,75 @@ from pytorchrec_b200.model import DeepFM  # noqa: E402
 from pytorchrec_b200.optim import SparseAdagrad  # noqa: E402
 
 
+def full_capacity_check(B, world):
+    from pytorchrec_b200.distributed.sharded import owner_share
+    return list_capacity(B, world, 1.25, owner_share([103, 57, 1000, 64, 31, 5000], world))
+
+
+def low_cardinality_and_overflow(rank, world, dev):
+    """(1) a column with fewer categories than ranks and Zipf ids trains exactly like the unsharded
+    model (lists sized from the cardinalities); (2) a list that does overflow is FATAL: the sticky word reaches the
+    host through pinned memory and the next train_step raises, also when the step is a replayed CUDA graph."""
+    import warnings
+    F, nd, D, B = 4, 2, 16, 256
+    rows = [1, world - 1 if world > 2 else 1, 40, 3000]
+    scols = [Col(rows[f], f"C{f}") for f in range(F)]
+    dcols = [NumericColumn(f"I{j}", 0.0, 1.0, 0.5, 0.25) for j in range(nd)]
+    lab = Col(2, "label")
+    full = DeepFM(scols, dcols, lab, D, [32, 16], random_seed=4)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        shard = ShardedDeepFM(scols, dcols, lab, D, [32, 16], random_seed=4)
+    assert any("fewer categories" in str(x.message) for x in w)
+    assert shard.sharded.capacity(B) == (B + 15) // 16 * 16  # category_num 1: one owner takes the whole batch
+    shard.load_full_state_dict(full.state_dict())
+    full.compile(SparseAdagrad(full.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)
+    shard.compile(SparseAdagrad(shard.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)
+    shard.enable_cuda_graph(True, warmup=1)
+
+    def batch(step, hot=False):
+        rng = np.random.default_rng(2000 + step)
+        gb = {f"C{f}": torch.from_numpy(((rng.zipf(1.05, size=world * B) % rows[f]) if not hot else
+                                        np.full(world * B, min(1, rows[f] - 1))).astype(np.int64)) for f in range(F)}
+        gb.update({f"I{j}": torch.from_numpy(rng.random(world * B).astype(np.float32)) for j in range(nd)})
+        gb["label"] = torch.from_numpy(rng.integers(0, 2, size=world * B))
+        return gb, {k: v[rank * B:(rank + 1) * B] for k, v in gb.items()}
+
+    for step in range(4):
+        gb, lb = batch(step)
+        lf = full.train_step(gb)["loss"].item()
+        ls = shard.train_step(lb)["loss"]
+        t = ls.detach().clone()
+        dist.all_reduce(t)
+        np.testing.assert_allclose(t.item() / world, lf, rtol=2e-5)
+    shard.sharded.check_errors()
+    gathered = shard.full_state_dict()
+    for k, v in full.state_dict().items():
+        np.testing.assert_allclose(gathered[k].numpy(), v.cpu().numpy(), rtol=0, atol=3e-4, err_msg=k)
+
+    # (2) force an overflow: lists far below one owner's share, every id of the batch identical
+    shard.sharded.owner_share, shard.sharded.capacity_factor = 1.0 / world, 0.25
+    assert shard.sharded.capacity(B) < B
+    shard._graphed.entries.clear()  # new capacity = new buffers: re-warm and re-capture
+    for step in range(3):
+        shard.train_step(batch(10 + step)[1])
+    torch.cuda.synchronize()
+    shard.sharded.poll_errors()      # nothing overflowed so far
+    shard.train_step(batch(20, hot=True)[1])  # a replayed graph: rows[3] -> every lookup hits id 1 -> owner 1 % world
+    torch.cuda.synchronize()
+    try:
+        shard.train_step(batch(21)[1])
+        raise AssertionError("an overflowed exchange list must be fatal")
+    except RuntimeError as e:
+        assert "overflowed" in str(e), e
+    try:
+        shard.sharded.check_errors()
+        raise AssertionError("check_errors must raise too")
+    except RuntimeError as e:
+        assert "overflowed" in str(e), e
+    dist.barrier()
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device(f"cuda:{local}")
@@ -33,6 +102,7 @@ def main():
     # the pack kernel against its CPU restatement (bit-exact)
     ids = torch.stack([torch.randint(0, rows[f], (B,), generator=torch.Generator().manual_seed(f + 10 * rank)) for f in range(F)])
     C = list_capacity(B, world)
+    assert C == full_capacity_check(B, world)
     ovf = torch.zeros(1, dtype=torch.int32, device=dev)
     send_ids, ret_pos = ops.a2a_pack_by_owner(ids.to(dev), F, B, world, C, ovf)
     rs, rp, _ = ref_sharding.pack_by_owner_ref(ids, world, C)
@@ -82,7 +152,24 @@ def main():
         np.testing.assert_allclose(v.numpy(), fsd[k].cpu().numpy(), rtol=0, atol=3e-4, err_msg=k)
     probe = DeepFM(scols, dcols, lab, D, [32, 16], random_seed=99)
     probe.load_state_dict(gathered)
+    # N4, optimizer state: the gathered Adagrad sums are the unsharded optimizer's, and they load back row-wise
+    ost = shard.full_optimizer_state_dict()
+    fopt = full.compiled_optimizers
+    assert ost["step"] == fopt._step_count_fused and ost["dense"] is not None
+    for gname, mod in (("embeddings", full.embeddings), ("first_order", full.first_order)):
+        for f, t in enumerate(mod):
+            ref = fopt.table_state(t.weight)["sum"].cpu().numpy()
+            got = ost["tables"][f"{gname}.{f}.weight"]["sum"].numpy()
+            assert got.shape == ref.shape, (gname, f, got.shape, ref.shape)
+            np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-7, err_msg=f"{gname}.{f}.sum")
+    for t in shard.sharded.tables:  # wipe, reload, gather again: identical
+        shard.compiled_optimizers.table_state(t.weight)["sum"].zero_()
+    shard.load_full_optimizer_state_dict(ost)
+    ost2 = shard.full_optimizer_state_dict()
+    for k, d in ost["tables"].items():
+        assert torch.equal(d["sum"], ost2["tables"][k]["sum"]), k
     dist.barrier()
+    low_cardinality_and_overflow(rank, world, dev)
     if rank == 0:
         print("DIST_SHARDED_OK world=%d peer=%s" % (world, shard.sharded.peer), flush=True)
     torch.cuda.synchronize()

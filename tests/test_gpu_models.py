@@ -185,11 +185,14 @@ def test_lazy_adam_and_rowwise_run_and_state_dict_roundtrip(tmp_path):
         assert sd["step"] == 20
 
 
-def test_stock_sparse_optimizer_mode_gives_sparse_grads():
-    """Without a fused optimizer the tables still train: weight.grad is a coalesced sparse tensor equal
-    to the dense reference gradient."""
+@pytest.mark.parametrize("sparse", [False, True])
+def test_stock_optimizer_mode_gives_nn_embedding_style_grads(sparse):
+    """Without a fused optimizer the tables still train: weight.grad equals the dense reference gradient — a dense
+    tensor by default (nn.Embedding's sparse=False, the reference's models), a coalesced COO tensor with sparse=True."""
     scols, dcols, lab, rows = _ctr_setup(F=3, nd=0)
     m = FM(scols, [], lab, 8, random_seed=5).to(DEV)
+    for t in list(m.embeddings) + list(m.first_order):
+        t.sparse = sparse
     ref = ref_models.FMRef(5, scols, [], lab, 8)
     batch = _ctr_batch(rows, 0, 128, seed=1, zipf=True)
     dbatch = {k: v.to(DEV) for k, v in batch.items()}
@@ -199,8 +202,40 @@ def test_stock_sparse_optimizer_mode_gives_sparse_grads():
     torch.nn.functional.binary_cross_entropy_with_logits(rl, rt).backward()
     for f in range(3):
         g = m.embeddings[f].weight.grad
-        assert g.is_sparse
-        np.testing.assert_allclose(g.coalesce().to_dense().cpu().numpy(), ref.embeddings[f].weight.grad.numpy(), rtol=1e-4, atol=1e-7)
+        assert g.is_sparse == sparse
+        g = g.coalesce().to_dense() if sparse else g
+        np.testing.assert_allclose(g.cpu().numpy(), ref.embeddings[f].weight.grad.numpy(), rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("name,kw", [("sgd", dict(lr=0.1)), ("sgd", dict(lr=0.1, weight_decay=1e-3)),
+                                     ("adam", dict(lr=0.01)), ("adamw", dict(lr=0.01, weight_decay=1e-2)),
+                                     ("adagrad", dict(lr=0.05)), ("sparse_sgd", dict(lr=0.1)),
+                                     ("sparse_adagrad", dict(lr=0.05)), ("sparse_rowwise_adagrad", dict(lr=0.05)),
+                                     ("sparse_adam", dict(lr=0.01))])
+def test_every_registry_optimizer_trains_a_model(name, kw):
+    """get_optimizer(name)(params=model.get_parameters(), **kw) (RepeatTask.py:96) drives train_step for every entry
+    of the registry; the reference's own entries (sgd / adam / adamw: dense nn.Embedding gradients) reproduce the
+    oracle twin trained with the same stock optimizer on the CPU."""
+    from pytorchrec_b200.optim import get_optimizer
+    scols, dcols, lab, rows = _ctr_setup(F=3, nd=2)
+    m = FM(scols, dcols, lab, 8, random_seed=5)
+    m.compile(get_optimizer(name)(params=m.get_parameters(), **kw), torch.nn.BCEWithLogitsLoss(), [LogLoss()], DEV)
+    ref = None
+    if not name.startswith("sparse_") :
+        ref = ref_models.FMRef(5, scols, dcols, lab, 8)
+        ref.compile(get_optimizer(name)(params=ref.get_parameters(), **kw), torch.nn.BCEWithLogitsLoss())
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    for s in range(3):
+        batch = _ctr_batch(rows, 2, 64, seed=20 + s, zipf=True)
+        loss = m.train_step(batch)["loss"].item()
+        assert np.isfinite(loss)
+        if ref is not None:
+            np.testing.assert_allclose(loss, ref.train_step(batch)["loss"].item(), rtol=1e-5)
+    after = m.state_dict()
+    assert any(not torch.equal(before[k], after[k]) for k in before if k.startswith("embeddings"))
+    if ref is not None:
+        for (k, a), (_, b) in zip(after.items(), ref.state_dict().items()):
+            np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), rtol=2e-4, atol=2e-6, err_msg=k)
 
 
 def test_out_of_range_id_is_reported():

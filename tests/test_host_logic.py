@@ -227,3 +227,73 @@ def test_device_rank_equals_host_rank():
     ml = MetricList([Hit(100, 10), NDCG(100, 10)])
     a, b = ml(pred, None), ml(pred.numpy(), None)
     assert a.keys() == b.keys() and all(abs(a[k] - b[k]) < 1e-12 for k in a)
+
+
+def test_fit_drives_the_reference_callback_lifecycle_and_save_weights_stores_weights_only(tmp_path):
+    """IModel.fit calls set_model / on_train_begin / on_epoch_begin / on_epoch_end / on_train_end like the reference's
+    CallbackList (IModel.py:160-208) — an EarlyStopping-style callback can stop training and restore the best weights in
+    on_train_end; save_weights writes contiguous weight tensors, not the storage a strided table view lives in."""
+    from pytorchrec_b200.metric import LogLoss
+    from pytorchrec_b200.model.IModel import IModel
+
+    class Tiny(IModel):
+        def _init_weights(self):
+            self.lin = torch.nn.Linear(3, 1)
+
+        def forward(self, data):
+            return self.lin(data["x"]).squeeze(-1), data["y"]
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return 8
+
+        def __getitem__(self, i):
+            g = torch.Generator().manual_seed(i)
+            return {"x": torch.randn(3, generator=g), "y": torch.tensor(float(i % 2))}
+
+    calls = []
+
+    class Stopper:  # reference-style callback: keeps the model it was given, stops after epoch 1, restores at the end
+        def set_model(self, model):
+            self.model = model
+
+        def set_params(self, params):
+            calls.append(("params", params["epochs"], params["batches"]))
+
+        def on_train_begin(self, logs=None):
+            calls.append("train_begin")
+
+        def on_epoch_begin(self, epoch, logs=None):
+            calls.append(("epoch_begin", epoch))
+
+        def on_epoch_end(self, epoch, logs=None):
+            calls.append(("epoch_end", epoch, "loss" in logs))
+            if epoch == 0:
+                self.model.save_best_weights()
+            if epoch == 1:
+                self.model.stop_training = True
+
+        def on_train_end(self, logs=None):
+            calls.append("train_end")
+            self.model.load_best_weights()
+
+    m = Tiny(random_seed=3)
+    m.compile(torch.optim.SGD(m.parameters(), lr=0.1), torch.nn.MSELoss(), [LogLoss()], torch.device("cpu"))
+    m.fit(DS(), batch_size=4, epochs=5, callbacks=[Stopper()])
+    assert calls == [("params", 5, 2), "train_begin", ("epoch_begin", 0), ("epoch_end", 0, True), ("epoch_begin", 1),
+                     ("epoch_end", 1, True), "train_end"]
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, m.best_state_dict[k])
+
+    # a table re-housed as a strided view of a [rows, 2*D] weight | state buffer (what SparseAdagrad does on the GPU)
+    emb = FunkSVD(Col(50, "uid"), Col(40, "iid"), Col(2, "label"), 8, random_seed=1)
+    w = emb.uid_embeddings.weight if hasattr(emb, "uid_embeddings") else next(emb.parameters())
+    buf = torch.zeros(w.shape[0], 4 * w.shape[1])
+    buf[:, :w.shape[1]] = w.data
+    w.data = buf[:, :w.shape[1]]
+    path = str(tmp_path / "w.pt")
+    emb.save_weights(path)
+    loaded = torch.load(path, weights_only=False)
+    for k, v in emb.state_dict().items():
+        assert torch.equal(loaded[k], v) and loaded[k].is_contiguous()
+        assert loaded[k].untyped_storage().nbytes() == v.numel() * v.element_size(), k
