@@ -50,10 +50,16 @@ class IModelRef(nn.Module):
     def compile(self, optimizer, loss):
         self.opt, self.loss_fn = optimizer, loss
 
+    def fp64(self) -> "IModelRef":
+        """The same model in double precision — the "exact" result both fp32 implementations (this oracle's and the
+        CUDA path's) are measured against where fp32 summation order decides the outcome (Adagrad's
+        g / (sqrt(sum g^2) + eps) is discontinuous where duplicate gradients cancel).  Call before ``compile``."""
+        return self.double()
+
     def train_step(self, data: Dict[str, Tensor]):
         self.train()
         prediction, target = self(data)
-        loss = self.loss_fn(prediction, target)
+        loss = self.loss_fn(prediction, target.to(prediction.dtype))
         self.opt.zero_grad()
         loss.backward()
         self.opt.step()
@@ -175,6 +181,7 @@ class FMRef(IModelRef):
         v = torch.stack([e(i) for e, i in zip(self.embeddings, ids)], dim=1)        # [B, F, D]
         w = torch.stack([e(i) for e, i in zip(self.first_order, ids)], dim=1)       # [B, F, 1]
         x = torch.stack([c.get_feature_data(data) for c in self.dense_columns], dim=1) if self.dense_columns else None
+        x = x.to(v.dtype) if x is not None else None  # a no-op in fp32; widens the inputs of an fp64() twin
         s = v.sum(dim=1)
         fm2 = 0.5 * (s * s - (v * v).sum(dim=1)).sum(dim=-1)
         logit = w.sum(dim=(1, 2)) + fm2 + self.global_bias
@@ -267,7 +274,8 @@ class DCNRef(IModelRef):
         flat = torch.cat([e(i) for e, i in zip(self.embeddings, ids)], dim=1)
         x0 = flat
         if self.dense_columns:
-            x0 = torch.cat([flat, torch.stack([c.get_feature_data(data) for c in self.dense_columns], dim=1)], dim=1)
+            x0 = torch.cat([flat, torch.stack([c.get_feature_data(data) for c in self.dense_columns], dim=1).to(flat.dtype)],
+                           dim=1)
         x = x0
         for lin in self.cross.layers:
             x = x0 * lin(x) + x

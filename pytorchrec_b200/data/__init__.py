@@ -1,2 +1,2 @@
-from .synthetic import criteo_columns, criteo_batch  # noqa: F401
+from .synthetic import amazon_batch, amazon_columns, criteo_batch, criteo_columns  # noqa: F401
 from .tensor_reader import SplitDataset, TensorDataReader  # noqa: F401

@@ -33,3 +33,37 @@ def criteo_batch(batch: int, n_sparse: int, n_dense: int, rows: int, seed: int, 
     if pin:
         out = {k: v.pin_memory() for k, v in out.items()}
     return out
+
+
+# Amazon-Books-shaped statistics used for the DIN config (BASELINE.json configs[3]; SURVEY.md 8d: the published
+# DIN / DIEN dataset sizes — the reference ships no Books loader)
+AMAZON_BOOKS = dict(users=603_668, items=367_982, cates=1_600)
+
+
+def amazon_columns(L: int = 100, users: int = AMAZON_BOOKS["users"], items: int = AMAZON_BOOKS["items"],
+                   cates: int = AMAZON_BOOKS["cates"]):
+    """(uid, iid, cid, his_iid, his_cid, his_len, label) columns of the DIN config: right-padded ``[B, L]`` histories
+    with 0 = PAD and a length column clipped to >= 1 (HistoryDataReader.py:55-69)."""
+    C = CategoricalColumnWithIdentity
+    return (C(users, "uid"), C(items, "iid"), C(cates, "cid"), C(items, "his_iid"), C(cates, "his_cid"),
+            C(L + 1, "his_len"), C(2, "label"))
+
+
+def amazon_batch(batch: int, L: int = 100, seed: int = 0, users: int = AMAZON_BOOKS["users"],
+                 items: int = AMAZON_BOOKS["items"], cates: int = AMAZON_BOOKS["cates"],
+                 pin: bool = False) -> Dict[str, torch.Tensor]:
+    """Host batch of the DIN config: history lengths ~ U{1..L}, ids uniform in [1, n), padded tail = 0."""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(1, L + 1, size=batch)
+    pad = np.arange(L)[None, :] >= lens[:, None]
+    hi = rng.integers(1, items, size=(batch, L))
+    hi[pad] = 0
+    hc = rng.integers(1, cates, size=(batch, L))
+    hc[pad] = 0
+    out = {"uid": rng.integers(1, users, size=batch), "iid": rng.integers(1, items, size=batch),
+           "cid": rng.integers(1, cates, size=batch), "his_iid": hi, "his_cid": hc, "his_len": lens,
+           "label": (rng.random(batch) < 0.25).astype(np.int64)}
+    out = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in out.items()}
+    if pin:
+        out = {k: v.pin_memory() for k, v in out.items()}
+    return out
