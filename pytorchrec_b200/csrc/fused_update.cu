@@ -278,6 +278,104 @@ fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restric
   }
 }
 
+// ---- Adagrad, v2 thread mapping ---------------------------------------------------------------------------------
+// 2*LPR lanes own one unique row: lanes [0, LPR) its weight slice, lanes [LPR, 2*LPR) the matching slice of the
+// Adagrad sum.  With the interleaved layout (state = weight + D, row_stride = 2*D) one 128-bit load per lane reads
+// the row's whole 2*D*4-byte bundle as ONE contiguous request (a full 128-byte line at D = 16) and one 128-bit
+// store per lane writes it back as a full line; v1 issues two half-line loads and two half-line stores per row.
+// Both halves load the (same) gradient slice — a broadcast inside the load instruction — exchange w / sum with one
+// shuffle per float and compute the update redundantly; each stores its own half.  No metadata is carried across
+// rounds (v1 prefetches the next round's 6 words per segment into registers): the kernel stays under
+// 65536 / (128 * MINB) registers so that MINB CTAs are resident per SM and the latency of a round is hidden by other
+// warps instead of by registers.  Same arithmetic and the same (sorted = batch) summation order as v1.
+template <int VEC, int LPR, int SEGS, int MINB>
+__global__ void __launch_bounds__(kUpdThreads, MINB)
+fused_adagrad_pair_kernel(void* const* __restrict__ table_ptrs, void* const* __restrict__ state1_ptrs, int T, int D,
+                          const ptrec_feature_desc* __restrict__ feats, int F, int64_t B,
+                          const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_start,
+                          const ptrec_segment_meta* __restrict__ seg_meta, const int32_t* __restrict__ n_seg_ptr,
+                          const float* __restrict__ grad_out, int64_t stride, const float* __restrict__ bag_scale,
+                          OptParams op, int* __restrict__ long_count, int32_t* __restrict__ long_list) {
+  __shared__ SlotMap s_map;
+  build_slot_map(&s_map, feats, F, T, B);
+  constexpr int SW = 2 * LPR;  // lanes per row
+  constexpr int NSG = kUpdThreads / SW;
+  const int sg = threadIdx.x / SW, sl = threadIdx.x % SW;
+  const int half = sl / LPR, lane = sl % LPR;
+  const bool lane_on = lane * VEC < D;
+  const int n_seg = *n_seg_ptr;
+  const int n_round = (n_seg + NSG * SEGS - 1) / (NSG * SEGS);
+  for (int r = blockIdx.x; r < n_round; r += gridDim.x) {
+    int start[SEGS], end[SEGS];
+    int4 meta[SEGS];
+#pragma unroll
+    for (int q = 0; q < SEGS; ++q) {
+      const int u = (r * SEGS + q) * NSG + sg;
+      start[q] = end[q] = 0;
+      meta[q] = make_int4((int)kMaskedKey, 0, 0, 0);
+      if (u < n_seg) {
+        start[q] = seg_start[u];
+        end[q] = seg_start[u + 1];
+        meta[q] = *reinterpret_cast<const int4*>(seg_meta + u);
+      }
+    }
+    float* rowp[SEGS];
+    RowVec<VEC> x[SEGS], acc[SEGS];
+    bool work[SEGS];
+#pragma unroll
+    for (int q = 0; q < SEGS; ++q) {
+      const int u = (r * SEGS + q) * NSG + sg;
+      const bool live = u < n_seg && (uint32_t)meta[q].x != kMaskedKey;
+      const bool is_long = live && (end[q] - start[q]) > kLongSeg;
+      if (is_long && sl == 0) long_list[atomicAdd(long_count, 1)] = u;
+      work[q] = live && !is_long;
+      rowp[q] = nullptr;
+      x[q].zero();
+      acc[q].zero();
+      if (work[q]) {
+        float* base = reinterpret_cast<float*>(half == 0 ? table_ptrs[meta[q].z] : state1_ptrs[meta[q].z]);
+        rowp[q] = base + (int64_t)(uint32_t)meta[q].x * op.row_stride + lane * VEC;
+        if (lane_on) x[q] = load_row<VEC>(rowp[q]);
+        acc[q] = slot_grad<VEC>(&s_map, meta[q].z, B, meta[q].y, grad_out, stride, bag_scale, lane, lane_on);
+      }
+    }
+    // remaining gradient slots of longer segments (duplicates in the batch), in sorted order
+#pragma unroll
+    for (int q = 0; q < SEGS; ++q) {
+      if (work[q]) {
+        for (int j0 = start[q] + 1; j0 < end[q]; j0 += 4) {
+          RowVec<VEC> g[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            g[k].zero();
+            if (j0 + k < end[q])
+              g[k] = slot_grad<VEC>(&s_map, meta[q].z, B, perm[j0 + k], grad_out, stride, bag_scale, lane, lane_on);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[q].add(g[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < SEGS; ++q) {
+      RowVec<VEC> out;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        // the partner lane (same slice, other half) holds sum if this lane holds w, and vice versa; the shuffle is
+        // executed by every lane of the warp (work[] only gates the store)
+        const float other = __shfl_xor_sync(0xffffffffu, x[q].v[k], LPR);
+        const float w = half == 0 ? x[q].v[k] : other;
+        float sum = half == 0 ? other : x[q].v[k];
+        float g = acc[q].v[k];
+        if (op.weight_decay != 0.f) g += op.weight_decay * w;
+        sum += g * g;
+        out.v[k] = half == 0 ? w - op.lr * (g / (sqrtf(sum) + op.eps)) : sum;
+      }
+      if (work[q] && lane_on) store_row<VEC>(rowp[q], out);
+    }
+  }
+}
+
 // CTA per long segment
 template <int VEC, int LPR, int OPT>
 __global__ void __launch_bounds__(kLongThreads)
@@ -340,6 +438,27 @@ fused_update_long_kernel(void* const* __restrict__ table_ptrs, void* const* __re
   }
 }
 
+static int g_update_variant = 0;  // 0 = v1 for every optimizer; Adagrad: 1 = pair<SEGS 2, 8 CTAs/SM>, 2 = pair<4, 6>, 3 = pair<4, 4>
+}  // namespace ptrec
+extern "C" void ptrec_set_update_variant(int32_t v) { ptrec::g_update_variant = v < 0 ? 0 : (v > 3 ? 3 : v); }
+extern "C" int32_t ptrec_update_variant(void) { return ptrec::g_update_variant; }
+namespace ptrec {
+
+template <int VEC, int LPR, int SEGS, int MINB>
+static void launch_pair(void* const* table_ptrs, void* const* s1, int T, int D, const ptrec_feature_desc* feats, int F,
+                        int64_t B, int64_t N, const int32_t* perm, const int32_t* seg_start,
+                        const ptrec_segment_meta* seg_meta, const int32_t* n_seg, const float* grad_out, int64_t stride,
+                        const float* bag_scale, const OptParams& op, int* long_count, int32_t* long_list, int sms,
+                        cudaStream_t st) {
+  constexpr int NSG = kUpdThreads / (2 * LPR);
+  const int64_t rounds = ceil_div(N, NSG * SEGS);
+  const int64_t cap = (int64_t)sms * MINB;
+  const unsigned grid = (unsigned)(rounds < cap ? (rounds > 0 ? rounds : 1) : cap);
+  fused_adagrad_pair_kernel<VEC, LPR, SEGS, MINB><<<grid, kUpdThreads, 0, st>>>(
+      table_ptrs, s1, T, D, feats, F, B, perm, seg_start, seg_meta, n_seg, grad_out, stride, bag_scale, op, long_count,
+      long_list);
+}
+
 template <int VEC, int LPR, int OPT>
 static int launch_update(void* const* table_ptrs, void* const* s1, void* const* s2, int T, int D,
                          const ptrec_feature_desc* feats, int F, int64_t B, int64_t N,
@@ -355,10 +474,26 @@ static int launch_update(void* const* table_ptrs, void* const* s1, void* const* 
   // 4 CTAs per SM (register-limited): one wave, several rounds per CTA so that the metadata prefetch has a next round
   const unsigned grid = (unsigned)(rounds < (int64_t)sms * 4 ? (rounds > 0 ? rounds : 1) : (int64_t)sms * 4);
   if (OPT != kOptNone) PTREC_CUDA(cudaMemsetAsync(long_count, 0, sizeof(int), st));
-  fused_update_kernel<VEC, LPR, OPT><<<grid, kUpdThreads, 0, st>>>(
-      table_ptrs, s1, s2, T, D, feats, F, B, sorted_keys, perm, seg_start, seg_meta, n_seg, grad_out,
-      stride, bag_scale, op, long_count, long_list, row_grad);
-  PTREC_LAUNCH_CHECK("fused_update_kernel");
+  bool done = false;
+  if constexpr (OPT == PTREC_OPT_ADAGRAD && 2 * LPR <= 32) {
+    if (g_update_variant != 0) {
+#define PTREC_PAIR(S, M) \
+  launch_pair<VEC, LPR, S, M>(table_ptrs, s1, T, D, feats, F, B, N, perm, seg_start, seg_meta, n_seg, grad_out, stride, \
+                              bag_scale, op, long_count, long_list, sms, st)
+      if (g_update_variant == 1) PTREC_PAIR(2, 8);
+      else if (g_update_variant == 2) PTREC_PAIR(4, 6);
+      else PTREC_PAIR(4, 4);
+#undef PTREC_PAIR
+      PTREC_LAUNCH_CHECK("fused_adagrad_pair_kernel");
+      done = true;
+    }
+  }
+  if (!done) {
+    fused_update_kernel<VEC, LPR, OPT><<<grid, kUpdThreads, 0, st>>>(
+        table_ptrs, s1, s2, T, D, feats, F, B, sorted_keys, perm, seg_start, seg_meta, n_seg, grad_out,
+        stride, bag_scale, op, long_count, long_list, row_grad);
+    PTREC_LAUNCH_CHECK("fused_update_kernel");
+  }
   if (OPT != kOptNone) {
     fused_update_long_kernel<VEC, LPR, OPT><<<sms * 2, kLongThreads, 0, st>>>(
         table_ptrs, s1, s2, T, D, feats, F, B, sorted_keys, perm, seg_start, seg_meta, grad_out, stride,

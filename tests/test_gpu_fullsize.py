@@ -92,12 +92,15 @@ def test_dcn_cfg3_shape_step_matches_cpu_oracle_within_bf16_tolerance():
         np.testing.assert_allclose(pl, rl, rtol=1e-2, atol=1e-2 * max(1.0, float(np.abs(rl).max())))
         lp, lr32 = prod.train_step(batch)["loss"].item(), ref.train_step(batch)["loss"].item()
         np.testing.assert_allclose(lp, lr32, rtol=1e-2)
-    # after two Adagrad steps every weight has moved by at most ~2*lr; bf16 gradients may flip the step of elements
-    # whose gradient is ~0, so weights are compared at 1e-2 of that scale
+    # Adagrad moves a weight by at most lr per step (|g| / sqrt(sum g^2) <= 1), and a bf16-rounded gradient that is ~0
+    # may take the opposite sign: two models can differ by up to 2*lr per step on isolated elements — the hard bound;
+    # the bulk (median) must agree to 1e-2 of the two-step scale
     for (k, v), (_, v2) in zip(prod.state_dict().items(), ref.state_dict().items()):
-        np.testing.assert_allclose(v.cpu().numpy(), v2.numpy(), rtol=1e-2, atol=2 * lr, err_msg=k)
-        d = np.abs(v.cpu().numpy() - v2.numpy())
-        assert np.median(d) <= 1e-2 * 2 * lr + 1e-2 * np.median(np.abs(v2.numpy())), (k, float(np.median(d)))
+        a, b = v.cpu().numpy(), v2.numpy()
+        np.testing.assert_allclose(a, b, rtol=1e-2, atol=2 * 2 * lr, err_msg=k)
+        d = np.abs(a - b)
+        assert np.median(d) <= 1e-2 * 2 * lr + 1e-2 * np.median(np.abs(b)), (k, float(np.median(d)))
+        assert (d > 1e-2 * np.abs(b) + 2 * lr).mean() <= 1e-3, (k, float((d > 1e-2 * np.abs(b) + 2 * lr).mean()))
     prod.embeddings.check_index_errors()
 
 
