@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 18
+#define PTREC_ABI_VERSION 19
 
 /* error codes */
 #define PTREC_OK 0
@@ -163,6 +163,11 @@ int ptrec_embedding_gather_pool_fwd_sharded(const void* const* shard_ptrs, const
  * launch latency dominates; default), 2 = shared memory whenever a table's batch fits (<= 22528 slots). */
 void ptrec_set_smem_sort(int32_t mode);
 int32_t ptrec_smem_sort_enabled(void);
+/* Large batches (beyond the shared-memory path): on = the one-sweep radix sort — keys and the digit histograms of
+ * every pass in one launch, one decoupled-look-back launch per digit, one look-back dedup launch (P + 2 launches
+ * + a memset, instead of 3 P + 3); off = the histogram / scan / scatter launches per pass.  Identical outputs. */
+void ptrec_set_one_sweep_sort(int32_t on);
+int32_t ptrec_one_sweep_sort_enabled(void);
 
 /* ---------------------------------------------------------------------------------------------
  * K2a segmented sort + dedup of the lookups of one batch (the integer half of the backward).
@@ -211,6 +216,11 @@ int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* state1_ptrs,
                               int64_t grad_row_stride, const float* bag_scale,
                               const ptrec_optim_args* opt_host, void* workspace,
                               size_t workspace_bytes, void* stream);
+/* Thread mapping of the fused Adagrad update: 0 = one sub-warp of D/4 lanes per row, 4 rows in flight, metadata
+ * prefetched in registers (v1); 1..3 = 2*D/4 lanes per row (weight half | state half: whole-line loads and stores of
+ * the interleaved row), no register prefetch, {2 rows x 8 CTAs/SM, 4 x 6, 4 x 4}.  Identical arithmetic and order. */
+void ptrec_set_update_variant(int32_t variant);
+int32_t ptrec_update_variant(void);
 /* the four named entry points of SURVEY.md §8b: same arguments as ptrec_embedding_bwd_fused; each checks
  * opt_host->kind and forwards */
 #define PTREC_BWD_FUSED_ARGS                                                                                   \
@@ -345,6 +355,30 @@ typedef struct ptrec_dense_tensor {
 int32_t ptrec_dense_optim_chunk(void);
 int ptrec_dense_optim_step(const ptrec_dense_tensor* tensors, const int32_t* chunk_start, int32_t n_tensors,
                            int32_t n_chunks, const ptrec_optim_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * C2 cross-GPU ordering and the dense-gradient all-reduce over NVLink peer memory (csrc/peer_sync.cu).  No reference
+ * counterpart (single-device reference, torchrec/task/Task.py:187-190); replaces the NCCL launches of the row-wise
+ * sharded step (a 1-element all_reduce used as a fence; cat + all_reduce + div + copy-back of the dense gradients).
+ *   ptrec_peer_barrier  every rank's work enqueued before it on its stream is complete and visible (system scope)
+ *     before any rank's work enqueued after it starts.  peer_flags [G] device array: rank p's flag array
+ *     (uint32 [ptrec_peer_sync_slots()][ptrec_peer_sync_max_ranks()], symmetric memory, zero-initialised) as seen
+ *     from this GPU; local_epoch uint32 [slots] device (zero-initialised, private).  Every rank must issue the same
+ *     sequence of calls per slot.  Graph-capturable (the epoch lives in device memory).
+ *   ptrec_dense_pack    gradients named by a K7 descriptor table -> contiguous `stage` (tensor t at element
+ *     chunk_start[t] * ptrec_dense_optim_chunk(), zero padded): n_chunks * chunk floats.
+ *   ptrec_dense_optim_step_reduce  K7 with gradient = grad_scale * sum_r peer_stage[r][.] (rank order): the
+ *     all-reduce fused into the optimizer step.  peer_stage [G] device array of the ranks' stages.
+ */
+int32_t ptrec_peer_sync_max_ranks(void);
+int32_t ptrec_peer_sync_slots(void);
+int ptrec_peer_barrier(uint32_t* const* peer_flags, uint32_t* local_epoch, int32_t slot, int32_t G, int32_t my_rank,
+                       void* stream);
+int ptrec_dense_pack(const ptrec_dense_tensor* tensors, const int32_t* chunk_start, int32_t n_tensors,
+                     int32_t n_chunks, float* stage, void* stream);
+int ptrec_dense_optim_step_reduce(const ptrec_dense_tensor* tensors, const int32_t* chunk_start, int32_t n_tensors,
+                                  int32_t n_chunks, const ptrec_optim_args* args, const float* const* peer_stage,
+                                  int32_t G, float grad_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K6 fp32-faithful Linear layers of the DNN tower on tcgen05 (replaces the fp32 cuBLAS sgemm behind nn.Linear in

@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libptrec_b200.so")
 
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 # enums (mirror include/ptrec_b200.h)
 F32, BF16 = 0, 1
@@ -78,6 +78,10 @@ PROTOTYPES = {
                                                         c_int64, c_void_p, c_void_p]),
     "ptrec_set_smem_sort": (None, [c_int32]),
     "ptrec_smem_sort_enabled": (c_int32, []),
+    "ptrec_set_one_sweep_sort": (None, [c_int32]),
+    "ptrec_one_sweep_sort_enabled": (c_int32, []),
+    "ptrec_set_update_variant": (None, [c_int32]),
+    "ptrec_update_variant": (c_int32, []),
     "ptrec_sort_dedup_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "ptrec_sort_dedup": (c_int, [_FD, _FD, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p,
                                  c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -106,6 +110,12 @@ PROTOTYPES = {
                                  c_void_p, c_size_t, c_void_p]),
     "ptrec_dense_optim_chunk": (c_int32, []),
     "ptrec_dense_optim_step": (c_int, [c_void_p, c_void_p, c_int32, c_int32, POINTER(OptimArgs), c_void_p]),
+    "ptrec_peer_sync_max_ranks": (c_int32, []),
+    "ptrec_peer_sync_slots": (c_int32, []),
+    "ptrec_peer_barrier": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "ptrec_dense_pack": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "ptrec_dense_optim_step_reduce": (c_int, [c_void_p, c_void_p, c_int32, c_int32, POINTER(OptimArgs), c_void_p,
+                                              c_int32, c_float, c_void_p]),
     "ptrec_tc_set_2sm": (None, [c_int32]),
     "ptrec_tc_set_bk": (None, [c_int32]),
     "ptrec_tc_2sm_enabled": (c_int32, []),
@@ -187,6 +197,10 @@ def load():
     ver = lib.ptrec_abi_version()
     if ver != ABI_VERSION:
         raise RuntimeError(f"libptrec_b200.so ABI {ver} != binding ABI {ABI_VERSION}: rebuild")
+    if os.environ.get("PTREC_ONE_SWEEP"):     # K2a: one-sweep radix sort on / off (A/B measurements)
+        lib.ptrec_set_one_sweep_sort(int(os.environ["PTREC_ONE_SWEEP"]))
+    if os.environ.get("PTREC_UPDATE_VARIANT"):  # K2b: thread mapping of the fused Adagrad update
+        lib.ptrec_set_update_variant(int(os.environ["PTREC_UPDATE_VARIANT"]))
     if os.environ.get("PTREC_TC_BN"):  # K6 fp16 x 2 pair-tile width, 128 or 256 (A/B measurements)
         lib.ptrec_tc_set_bn(int(os.environ["PTREC_TC_BN"]))
     _lib = lib

@@ -11,8 +11,9 @@
 // Peer mode (ptrec_a2a_*_peer): the lists and the gradient rows are stored DIRECTLY into the owner's receive buffers
 // through peer pointers (NVLink / NVSwitch stores), in the layout the owner-side sort and fused update read:
 //     owner_ids [f, src, slot]          owner_grads [(src*F + f)*C + slot, :]
-// so the dispatch needs no all-to-all; the caller orders "all pushes done" before the owner consumes them with one
-// small collective (a fence), and the owner resets its own id lists to -1 after consuming them.
+// so the dispatch needs no all-to-all; the caller orders "all pushes done" before the owner consumes them with a
+// barrier (peer_sync.cu); every list is written in full (lookups, then -1 up to its capacity), so the owner never
+// resets anything.
 #include "common.cuh"
 
 namespace ptrec {
@@ -59,6 +60,7 @@ pack_scatter_kernel(const int64_t* __restrict__ ids, int64_t B, int F, int G, in
   constexpr int NW = kPackThreads / 32;
   __shared__ int s_cnt[NW][kMaxRanks];
   __shared__ int s_base[kMaxRanks];
+  __shared__ int s_total[kMaxRanks];
   __shared__ int64_t* s_peer[kMaxRanks];
   if (peer_ids != nullptr && threadIdx.x < G) s_peer[threadIdx.x] = peer_ids[threadIdx.x];
   const int f = blockIdx.y, tile = blockIdx.x;
@@ -95,8 +97,17 @@ pack_scatter_kernel(const int64_t* __restrict__ ids, int64_t B, int F, int G, in
       s_cnt[w][threadIdx.x] = run;
       run += c;
     }
+    s_total[threadIdx.x] = run;  // in the field's LAST tile: the final length of the list for this destination
   }
   __syncthreads();
+  if (peer_ids != nullptr && tile == tiles - 1) {
+    // peer mode: the owner's list is rewritten in full every step — the slots behind the last lookup read "no
+    // lookup" (-1) — so the owner never has to reset it and a forward without a backward leaves nothing stale
+    for (int d = 0; d < G; ++d) {
+      int64_t* list = s_peer[d] + ((int64_t)f * G + my_rank) * C;
+      for (int slot = min(s_total[d], C) + (int)threadIdx.x; slot < C; slot += kPackThreads) list[slot] = -1;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < kPackItems; ++i) {
     const int64_t b = beg + warp * (32 * kPackItems) + i * 32 + lane;

@@ -17,7 +17,7 @@ struct DenseHyper {
 
 __global__ void __launch_bounds__(kDoThreads)
 dense_optim_kernel(const ptrec_dense_tensor* __restrict__ tensors, const int32_t* __restrict__ chunk_start,
-                   int n_tensors, DenseHyper h) {
+                   int n_tensors, DenseHyper h, const float* const* __restrict__ peer_stage, int G, float gscale) {
   __shared__ int s_t;
   if (threadIdx.x == 0) {
     int t = 0;
@@ -36,7 +36,17 @@ dense_optim_kernel(const ptrec_dense_tensor* __restrict__ tensors, const int32_t
     const int64_t e = base + i * kDoThreads + threadIdx.x;
     if (e >= d.numel) break;
     float w = p[e];
-    float gr = g[e];
+    float gr;
+    if (peer_stage != nullptr) {
+      // reduce mode (peer_sync.cu): the gradient is the mean over the ranks' packed stages, summed in rank order so
+      // that every replica computes the same bits; element e of tensor t sits at stage[blockIdx.x * chunk + ...]
+      const int64_t off = (int64_t)blockIdx.x * kDoChunk + i * kDoThreads + threadIdx.x;
+      gr = 0.f;
+      for (int r = 0; r < G; ++r) gr += ldg_stream_f1(peer_stage[r] + off);
+      gr *= gscale;
+    } else {
+      gr = g[e];
+    }
     if (h.wd != 0.f) gr = gr + h.wd * w;           // grad.add(param, alpha=weight_decay)
     if (h.kind == PTREC_OPT_SGD) {
       w = w + (-h.lr) * gr;                        // param.add_(grad, alpha=-lr)
@@ -63,8 +73,9 @@ dense_optim_kernel(const ptrec_dense_tensor* __restrict__ tensors, const int32_t
 
 using namespace ptrec;
 
-extern "C" int ptrec_dense_optim_step(const ptrec_dense_tensor* tensors, const int32_t* chunk_start, int32_t n_tensors,
-                                      int32_t n_chunks, const ptrec_optim_args* args, void* stream) {
+static int dense_step_impl(const ptrec_dense_tensor* tensors, const int32_t* chunk_start, int32_t n_tensors,
+                           int32_t n_chunks, const ptrec_optim_args* args, const float* const* peer_stage, int32_t G,
+                           float gscale, void* stream) {
   PTREC_CHECK_ARG(tensors && chunk_start && args, PTREC_EINVAL, "dense_optim: null pointer");
   PTREC_CHECK_ARG(n_tensors >= 1 && n_tensors <= kDoMaxTensors && n_chunks >= 0, PTREC_EINVAL,
                   "dense_optim: n_tensors=%d out of range (max %d)", n_tensors, kDoMaxTensors);
@@ -84,9 +95,22 @@ extern "C" int ptrec_dense_optim_step(const ptrec_dense_tensor* tensors, const i
   const double bc2 = 1.0 - pow((double)args->beta2, (double)args->step);
   h.step_size = (float)((double)args->lr / (bc1 != 0.0 ? bc1 : 1.0));
   h.bc2_sqrt = (float)sqrt(bc2 > 0.0 ? bc2 : 1.0);
-  dense_optim_kernel<<<(unsigned)n_chunks, kDoThreads, 0, (cudaStream_t)stream>>>(tensors, chunk_start, n_tensors, h);
+  dense_optim_kernel<<<(unsigned)n_chunks, kDoThreads, 0, (cudaStream_t)stream>>>(tensors, chunk_start, n_tensors, h,
+                                                                                    peer_stage, G, gscale);
   PTREC_LAUNCH_CHECK("dense_optim_kernel");
   return PTREC_OK;
+}
+
+extern "C" int ptrec_dense_optim_step(const ptrec_dense_tensor* tensors, const int32_t* chunk_start, int32_t n_tensors,
+                                      int32_t n_chunks, const ptrec_optim_args* args, void* stream) {
+  return dense_step_impl(tensors, chunk_start, n_tensors, n_chunks, args, nullptr, 1, 1.f, stream);
+}
+
+extern "C" int ptrec_dense_optim_step_reduce(const ptrec_dense_tensor* tensors, const int32_t* chunk_start,
+                                             int32_t n_tensors, int32_t n_chunks, const ptrec_optim_args* args,
+                                             const float* const* peer_stage, int32_t G, float grad_scale, void* stream) {
+  PTREC_CHECK_ARG(peer_stage && G >= 1 && G <= 64, PTREC_EINVAL, "dense_optim_reduce: bad peer stage / G=%d", G);
+  return dense_step_impl(tensors, chunk_start, n_tensors, n_chunks, args, peer_stage, G, grad_scale, stream);
 }
 
 extern "C" int32_t ptrec_dense_optim_chunk(void) { return kDoChunk; }

@@ -254,6 +254,214 @@ struct SegOut {
 };
 
 
+// ---- one-sweep path: P + 2 launches instead of 3 P + 3 ------------------------------------------------------------
+// os_hist_kernel   keys generated ONCE from the id matrices (validity, masks) into a uint32 array; the digit
+//                  histograms of EVERY pass are counted in the same sweep (shared-memory atomics, then one global
+//                  integer atomicAdd per non-empty (table, pass, digit) — integer adds: order-independent); the
+//                  look-back words of the later launches are reset by the same CTAs.
+// os_pass_kernel   one launch per digit: a tile ranks its keys (warp match-any, stable), publishes its digit counts
+//                  and obtains the counts of the tiles before it IN ITS TABLE by decoupled look-back (aggregate /
+//                  inclusive words, 30-bit count + 2 flag bits, relaxed gpu-scope loads); digit bases come from the
+//                  table's global histogram, scanned by every CTA for itself.  A tile only ever waits on tiles with a
+//                  smaller block index, and every wait is bounded (trap instead of a hang).
+// os_dedup_kernel  head flags + look-back scan of the head counts + the 16-byte segment records, in one launch.
+// Same stable LSD order, so the outputs are bit-identical to the other two paths.
+constexpr uint32_t kOsAggr = 1u << 30, kOsIncl = 2u << 30, kOsMask = (1u << 30) - 1u;
+constexpr int kOsMaxPasses = 4;
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// exclusive prefix over the tiles [first, tile) of the published words at w[j * pitch]; bounded spin
+__device__ __forceinline__ uint32_t os_look_back(const uint32_t* w, int64_t pitch, int first, int tile) {
+  uint32_t ex = 0;
+  for (int j = tile - 1; j >= first; --j) {
+    uint32_t v = ld_relaxed_u32(w + (int64_t)j * pitch);
+    for (uint32_t spins = 0; (v >> 30) == 0; ++spins) {
+      if (spins > (1u << 22)) __trap();
+      __nanosleep(20);
+      v = ld_relaxed_u32(w + (int64_t)j * pitch);
+    }
+    ex += v & kOsMask;
+    if (v & kOsIncl) break;
+  }
+  return ex;
+}
+
+template <int RB>
+__global__ void __launch_bounds__(kSortThreads)
+os_hist_kernel(TableLayout lay, int64_t B, int P, const ptrec_feature_desc* __restrict__ feats, int F,
+               const int64_t* __restrict__ ids, const int32_t* __restrict__ lens,
+               const int64_t* __restrict__ table_rows, uint32_t* __restrict__ keys0, int* __restrict__ ghist,
+               uint32_t* __restrict__ status, uint32_t* __restrict__ status_seg) {
+  constexpr int kRadix = 1 << RB;
+  __shared__ int s_hist[kOsMaxPasses * kRadix];
+  __shared__ ptrec_feature_desc s_feats[kMaxFeatures];
+  __shared__ int s_rng[2];
+  const int tile = blockIdx.x;
+  const int t = table_of_tile(lay, tile);
+  const int k = tile - lay.tile_prefix[t];
+  const int64_t beg = lay.Lstart[t] * B + (int64_t)k * kSortTile;
+  const int64_t end = min(lay.Lstart[t + 1] * B, beg + kSortTile);
+  for (int d = threadIdx.x; d < P * kRadix; d += kSortThreads) s_hist[d] = 0;
+  // reset the look-back words this tile owns in every later launch of this call
+  for (int d = threadIdx.x; d < P * kRadix; d += kSortThreads)
+    status[((int64_t)(d / kRadix) * lay.total_tiles + tile) * kRadix + (d % kRadix)] = 0u;
+  if (threadIdx.x == 0) status_seg[tile] = 0u;
+  load_feats(s_feats, feats, F);
+  __syncthreads();
+  table_feature_range(s_feats, F, t, s_rng);
+  __syncthreads();
+  KeyGen gen{s_feats, s_rng[0], s_rng[1], ids, lens, table_rows[t], B};
+  for (int64_t j = beg + threadIdx.x; j < end; j += kSortThreads) {
+    const uint32_t key = gen(j);
+    keys0[j] = key;
+    for (int p = 0; p < P; ++p) atomicAdd(&s_hist[p * kRadix + ((key >> (RB * p)) & (kRadix - 1))], 1);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < P * kRadix; d += kSortThreads) {
+    const int c = s_hist[d];
+    if (c) atomicAdd(&ghist[(int64_t)t * (kOsMaxPasses * kRadix) + d], c);
+  }
+}
+
+template <int RB>
+__global__ void __launch_bounds__(kSortThreads)
+os_pass_kernel(TableLayout lay, int64_t B, int p, const uint32_t* __restrict__ keys_in,
+               const int32_t* __restrict__ perm_in, const int* __restrict__ ghist, uint32_t* __restrict__ status,
+               uint32_t* __restrict__ keys_out, int32_t* __restrict__ perm_out) {
+  constexpr int NW = kSortThreads / 32;
+  constexpr int kRadix = 1 << RB;
+  constexpr int DPT = kRadix / kSortThreads;  // consecutive digits per thread (1 or 4)
+  __shared__ int s_cnt[NW][kRadix];
+  __shared__ int s_goff[kRadix];
+  __shared__ int s_warp[33];
+  const int tile = blockIdx.x;
+  const int t = table_of_tile(lay, tile);
+  const int first = lay.tile_prefix[t];
+  const int64_t beg = lay.Lstart[t] * B + (int64_t)(tile - first) * kSortTile;
+  const int64_t end = min(lay.Lstart[t + 1] * B, beg + kSortTile);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int shift = RB * p;
+  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s_cnt[w][d] = 0;
+  }
+  __syncthreads();
+  uint32_t key[kSortItems];
+  int32_t pay[kSortItems];
+  int rank[kSortItems];
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int64_t j = beg + warp * (32 * kSortItems) + i * 32 + lane;
+    const bool in = j < end;
+    key[i] = 0;
+    pay[i] = 0;
+    if (in) {
+      key[i] = keys_in[j];
+      pay[i] = perm_in != nullptr ? perm_in[j] : (int32_t)j;
+    }
+    const int d = in ? (int)((key[i] >> shift) & (kRadix - 1)) : kRadix;  // kRadix = "no key" group
+    const unsigned m = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (in) base = s_cnt[warp][d];
+    __syncwarp();
+    if (in && lane == leader) s_cnt[warp][d] = base + __popc(m);
+    __syncwarp();
+    rank[i] = base + __popc(m & lt);
+  }
+  __syncthreads();
+  // this thread's digits: exclusive prefix over the warps, tile count, publish, look back, digit base
+  uint32_t* st = status + ((int64_t)p * lay.total_tiles) * kRadix;
+  int cnt[DPT], tot[DPT];
+  int mine = 0;
+#pragma unroll
+  for (int i = 0; i < DPT; ++i) {
+    const int d = threadIdx.x * DPT + i;
+    int run = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const int c = s_cnt[w][d];
+      s_cnt[w][d] = run;
+      run += c;
+    }
+    cnt[i] = run;
+    st_relaxed_u32(st + (int64_t)tile * kRadix + d, (tile == first ? kOsIncl : kOsAggr) | (uint32_t)run);
+    tot[i] = ghist[(int64_t)t * (kOsMaxPasses * kRadix) + p * kRadix + d];
+    mine += tot[i];
+  }
+  int total;
+  int dbase = block_exclusive_scan(mine, s_warp, &total) + (int)(lay.Lstart[t] * B);
+#pragma unroll
+  for (int i = 0; i < DPT; ++i) {
+    const int d = threadIdx.x * DPT + i;
+    uint32_t ex = 0;
+    if (tile != first) {
+      ex = os_look_back(st + d, kRadix, first, tile);
+      st_relaxed_u32(st + (int64_t)tile * kRadix + d, kOsIncl | (ex + (uint32_t)cnt[i]));
+    }
+    s_goff[d] = dbase + (int)ex;
+    dbase += tot[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int64_t j = beg + warp * (32 * kSortItems) + i * 32 + lane;
+    if (j < end) {
+      const int d = (int)((key[i] >> shift) & (kRadix - 1));
+      const int pos = s_goff[d] + s_cnt[warp][d] + rank[i];
+      keys_out[pos] = key[i];
+      perm_out[pos] = pay[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+os_dedup_kernel(HeadIn in, SegOut out, int64_t n, uint32_t* __restrict__ status_seg, int32_t* __restrict__ n_seg) {
+  __shared__ int s_warp[33];
+  __shared__ int s_prefix;
+  const int tile = blockIdx.x;
+  const int64_t base = (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int v[kScanItems];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const int64_t i = base + k;
+    v[k] = (i < n) ? in(i) : 0;
+    s += v[k];
+  }
+  int total;
+  int prefix = block_exclusive_scan(s, s_warp, &total);
+  if (threadIdx.x == 0) {
+    uint32_t ex = 0;
+    if (tile == 0) {
+      st_relaxed_u32(status_seg, kOsIncl | (uint32_t)total);
+    } else {
+      st_relaxed_u32(status_seg + tile, kOsAggr | (uint32_t)total);
+      ex = os_look_back(status_seg, 1, 0, tile);
+      st_relaxed_u32(status_seg + tile, kOsIncl | (ex + (uint32_t)total));
+    }
+    s_prefix = (int)ex;
+    if (tile == (int)gridDim.x - 1) *n_seg = (int)ex + total;
+  }
+  __syncthreads();
+  prefix += s_prefix;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const int64_t i = base + k;
+    if (i < n) out(i, prefix, v[k]);
+    prefix += v[k];
+  }
+}
+
+
 // ---- fast path: one CTA sorts one table's batch entirely in shared memory ---------------------------------------
 // When every table's slots fit (<= kSmemSortMax, e.g. the Criteo-shaped configs: 16384 lookups per table, ~21 k on
 // the owner side of the sharded path) the whole sort + dedup is 2 launches instead of 3 per radix pass + 3:
@@ -440,6 +648,9 @@ smem_segments_kernel(TableLayout lay, int64_t B, int64_t N, const uint32_t* __re
 
 using namespace ptrec;
 
+static int g_one_sweep = 1;  // large batches: 1 = one-sweep (P + 2 launches; default), 0 = 3 launches per radix pass + 3
+extern "C" void ptrec_set_one_sweep_sort(int32_t on) { g_one_sweep = on ? 1 : 0; }
+extern "C" int32_t ptrec_one_sweep_sort_enabled(void) { return g_one_sweep; }
 static int g_smem_sort = 1;  // 0 = never, 1 = automatic (small batches), 2 = whenever it fits
 extern "C" void ptrec_set_smem_sort(int32_t mode) { g_smem_sort = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 extern "C" int32_t ptrec_smem_sort_enabled(void) { return g_smem_sort; }
@@ -482,6 +693,9 @@ extern "C" size_t ptrec_sort_dedup_workspace_bytes(int64_t N, int32_t T) {
   bytes += align_up(tiles * kMaxRadix * 4, 256);               // hist
   bytes += align_up(((size_t)scan_num_tiles(N) + 1) * 4, 256); // head scan tile sums
   bytes += align_up((size_t)(kMaxTables + 1) * 4, 256);        // per-table segment counts (shared-memory path)
+  bytes += align_up((size_t)T * kOsMaxPasses * kMaxRadix * 4, 256);      // one-sweep: per-table digit histograms
+  bytes += align_up(tiles * kOsMaxPasses * kMaxRadix * 4, 256);          // one-sweep: look-back words per pass
+  bytes += align_up(tiles * 4, 256);                                     // one-sweep: look-back words of the dedup scan
   return bytes + 256;
 }
 
@@ -524,6 +738,13 @@ extern "C" int ptrec_sort_dedup(const ptrec_feature_desc* feats, const ptrec_fea
   int* tile_sums = reinterpret_cast<int*>(w);
   w += align_up(((size_t)scan_num_tiles(N) + 1) * 4, 256);
   int* seg_count = reinterpret_cast<int*>(w);
+  w += align_up((size_t)(kMaxTables + 1) * 4, 256);
+  int* ghist = reinterpret_cast<int*>(w);
+  const size_t ghist_bytes = (size_t)T * kOsMaxPasses * kMaxRadix * 4;
+  w += align_up(ghist_bytes, 256);
+  uint32_t* os_status = reinterpret_cast<uint32_t*>(w);
+  w += align_up(((size_t)ceil_div(N, kSortTile) + (size_t)T + 1) * kOsMaxPasses * kMaxRadix * 4, 256);
+  uint32_t* os_status_seg = reinterpret_cast<uint32_t*>(w);
 
   // shared-memory fast path: every table's slots fit one CTA
   int64_t n_max = 0;
@@ -552,6 +773,39 @@ extern "C" int ptrec_sort_dedup(const ptrec_feature_desc* feats, const ptrec_fea
     smem_segments_kernel<<<T, kSmemSortThreads, 0, st>>>(lay, B, N, sorted_keys, perm, seg_count, seg_start, seg_meta,
                                                          n_seg);
     PTREC_LAUNCH_CHECK("smem_segments_kernel");
+    return PTREC_OK;
+  }
+
+  if (g_one_sweep && P <= kOsMaxPasses && scan_num_tiles(N) <= lay.total_tiles) {
+    // keys0 lives in whichever key buffer pass 0 does NOT write
+    const bool first_to_out = ((P - 1) % 2) == 0;
+    uint32_t* keys0 = first_to_out ? keys_tmp : sorted_keys;
+    PTREC_CUDA(cudaMemsetAsync(ghist, 0, ghist_bytes, st));
+    if (RB == 10)
+      os_hist_kernel<10><<<lay.total_tiles, kSortThreads, 0, st>>>(lay, B, P, feats, F, ids, lens, table_rows, keys0, ghist,
+                                                                  os_status, os_status_seg);
+    else
+      os_hist_kernel<8><<<lay.total_tiles, kSortThreads, 0, st>>>(lay, B, P, feats, F, ids, lens, table_rows, keys0, ghist,
+                                                                 os_status, os_status_seg);
+    PTREC_LAUNCH_CHECK("os_hist_kernel");
+    const uint32_t* kin = keys0;
+    const int32_t* pin = nullptr;
+    for (int p = 0; p < P; ++p) {
+      const bool to_out = ((P - 1 - p) % 2) == 0;
+      uint32_t* kout = to_out ? sorted_keys : keys_tmp;
+      int32_t* pout = to_out ? perm : perm_tmp;
+      if (RB == 10)
+        os_pass_kernel<10><<<lay.total_tiles, kSortThreads, 0, st>>>(lay, B, p, kin, pin, ghist, os_status, kout, pout);
+      else
+        os_pass_kernel<8><<<lay.total_tiles, kSortThreads, 0, st>>>(lay, B, p, kin, pin, ghist, os_status, kout, pout);
+      PTREC_LAUNCH_CHECK("os_pass_kernel");
+      kin = kout;
+      pin = pout;
+    }
+    HeadIn hin{lay, B, sorted_keys};
+    SegOut sout{lay, B, N, seg_start, seg_meta, sorted_keys, perm};
+    os_dedup_kernel<<<scan_num_tiles(N), kScanThreads, 0, st>>>(hin, sout, N, os_status_seg, n_seg);
+    PTREC_LAUNCH_CHECK("os_dedup_kernel");
     return PTREC_OK;
   }
 

@@ -9,13 +9,17 @@ Peer-memory path (default on NCCL process groups while the shards stay below PTR
 ``peer=True/False`` or PTREC_PEER_GATHER=1/0 force one or the other):
 the shards and the owners' receive buffers live in symmetric memory, every rank holds the peers' pointers, and
 the exchange happens INSIDE the kernels over NVLink / NVSwitch:
-  forward   ONE gather launch per width; its 128-bit row loads go to whichever GPU owns the row  (no collective)
-  backward  pack ids by owner + scatter gradient rows, both stored straight into the owners' buffers
-            -> fence (1-element all_reduce: "every push has landed")
-            -> owner-side sort / dedup / segment-sum / fused optimizer update; owner resets its id lists
-  dense     one flat all_reduce(SUM) / G of the dense-tower gradients — also the fence that orders this step's table
-            updates and buffer reuse before the next step's peer reads and pushes.
-No kernel waits on another rank: cross-rank ordering comes only from stream order + those two collectives.
+  forward   ONE gather launch per width; its 128-bit row loads go to whichever GPU owns the row  (no collective).
+            Meanwhile, on a side stream: pack ids by owner, stored straight into the owners' lists -> barrier ->
+            owner-side sort / dedup of the received lists — all of it overlaps the forward and the dense tower.
+  backward  scatter gradient rows straight into the owners' buffers -> barrier ("every push has landed")
+            -> owner-side segment-sum + fused optimizer update (joins the early sort).
+  dense     the replicated tower's gradients are packed into a symmetric stage, one barrier, and the optimizer
+            kernel (K7) sums every rank's stage itself: the all-reduce is fused into the update.  That barrier is also
+            the fence that orders this step's table updates and buffer reuse before the next step's peer accesses.
+The barriers are kernels of this library on symmetric-memory flags (csrc/peer_sync.cu, ``ops.PeerSync``), not NCCL
+launches: a step of the peer path issues no NCCL collective at all (PTREC_PEER_SYNC=0 restores the NCCL fence and
+all_reduce; PTREC_EARLY_EXCHANGE=0 keeps the id exchange and the sort in the backward).
 
 All-to-all path (NCCL only; any backend that offers all_to_all_single):
   forward   pack ids by owner (fixed-capacity lists, no host sync)  -> all_to_all(ids)
@@ -162,8 +166,32 @@ class _ShardedLookup(torch.autograd.Function):
         return (None, None) + (None,) * (len(mod.dims) * len(mod.columns))
 
 
+_SIDE: Dict[torch.device, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    st = _SIDE.get(dev)
+    if st is None:
+        st = _SIDE[dev] = torch.cuda.Stream(dev)
+    return st
+
+
 class _PeerLookup(torch.autograd.Function):
     """The same lookup with the exchange inside the kernels (peer loads / stores over NVLink), see module docstring."""
+
+    @staticmethod
+    def _exchange_ids(mod, ids, F, B, dev):
+        """pack ids by owner into the owners' lists -> barrier -> owner-side sort / dedup of the lists received here.
+        Runs on whatever stream is current.  Returns (ret_pos, sort result, capacity)."""
+        C = mod.capacity(B)
+        pb = mod.peer_buffers(C, dev)
+        ret_pos = ops.a2a_pack_by_owner_peer(ids, F, B, mod.world, C, mod.rank, pb["peer_ids"], mod.overflow_flag(dev))
+        mod.publish_overflow(dev)
+        mod.barrier(ops.PeerSync.IDS, dev)  # every rank's lists have landed in every owner's buffer
+        eg = mod.egroups[0]                 # same ids and the same shard heights for every width: one sort
+        tables = eg.table_set.refresh([t.weight.data for t in eg.tables])
+        srt = ops.sort_dedup(tables, mod.owner_layout(C, 0), pb["recv_ids"], None, C)
+        return ret_pos, srt, C
 
     @staticmethod
     def forward(ctx, mod: "RowWiseShardedEmbedding", ids: Tensor, *weights):
@@ -171,6 +199,20 @@ class _PeerLookup(torch.autograd.Function):
         dev = ids.device
         if mod._dirty:
             mod.fence(dev)
+        ctx.early = None
+        if mod.early_exchange and any(ctx.needs_input_grad[2:]):
+            # the id exchange and the owner-side sort depend on the ids only: start them now on a side stream, where
+            # they overlap the gather, the interaction and the dense tower; the backward joins them with an event
+            main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ret_pos, srt, C = _PeerLookup._exchange_ids(mod, ids, F, B, dev)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            ids.record_stream(side)
+            for t in (ret_pos, srt.sorted_keys, srt.perm, srt.seg_start, srt.seg_meta, srt.n_seg):
+                t.record_stream(main)  # consumed on the main stream in backward
+            ctx.early = (ret_pos, srt, C, ev)
         flat = ids.reshape(-1)
         outs = []
         for k, D in enumerate(mod.dims):
@@ -188,12 +230,14 @@ class _PeerLookup(torch.autograd.Function):
         G, S = mod.world, mod.slot_width
         (ids,) = ctx.saved_tensors
         dev = ids.device
-        C = mod.capacity(B)
+        if ctx.early is not None:
+            ret_pos, srt, C, ev = ctx.early
+            torch.cuda.current_stream(dev).wait_event(ev)  # join the early exchange + sort
+        else:
+            if mod._dirty:  # the owners may still be consuming their buffers from an earlier backward
+                mod.fence(dev)
+            ret_pos, srt, C = _PeerLookup._exchange_ids(mod, ids, F, B, dev)
         pb = mod.peer_buffers(C, dev)
-        if mod._dirty:  # the owners may still be consuming / resetting their buffers from an earlier backward
-            mod.fence(dev)
-        ret_pos = ops.a2a_pack_by_owner_peer(ids, F, B, G, C, mod.rank, pb["peer_ids"], mod.overflow_flag(dev))
-        mod.publish_overflow(dev)
         gs = []
         for k, D in enumerate(mod.dims):
             g = grads[k]
@@ -201,9 +245,8 @@ class _PeerLookup(torch.autograd.Function):
             gs.append(g if g.is_contiguous() else g.contiguous())
         ops.a2a_scatter_rows_peer_multi(gs, mod.dims, mod.col_of, ret_pos, B, F, mod.grad_scale, pb["peer_g"], S, C, G,
                                         mod.rank)
-        mod.fence(dev)  # every rank's pushes have landed in every owner's buffers
-        recv_ids, recv_g = pb["recv_ids"], pb["recv_g"]
-        srt = None
+        mod.barrier(ops.PeerSync.GRADS, dev)  # every rank's gradient rows have landed in every owner's buffer
+        recv_g = pb["recv_g"]
         for k, D in enumerate(mod.dims):
             eg = mod.egroups[k]
             bind = eg.binding()
@@ -211,13 +254,39 @@ class _PeerLookup(torch.autograd.Function):
                 raise RuntimeError("row-wise sharded tables need a pytorchrec_b200.optim sparse optimizer")
             s1, s2, args = bind[0]._fused_prepare(eg, bind[1])  # may interleave weight | state: before taking pointers
             tables = eg.table_set.refresh([t.weight.data for t in eg.tables])
-            layout = mod.owner_layout(C, k)
-            if srt is None:
-                srt = ops.sort_dedup(tables, layout, recv_ids, None, C)
-            ops.bwd_fused(tables, s1, s2, layout, C, srt, recv_g, None, args, grad_row_stride=S)
-        recv_ids.fill_(-1)  # slots nobody writes next step must read "no lookup"
+            ops.bwd_fused(tables, s1, s2, mod.owner_layout(C, k), C, srt, recv_g, None, args, grad_row_stride=S)
         mod._dirty = True   # tables changed, buffers recycled: a fence must precede the next peer access
         return (None, None) + (None,) * (len(mod.dims) * len(mod.columns))
+
+
+class _DenseReducer:
+    """What a fused optimizer needs to average the replicated dense gradients over NVLink peer memory
+    (``optim/sparse.py::_fused_dense_step``): per-launch stages in symmetric memory, one barrier, a fallback."""
+
+    def __init__(self, mod: "RowWiseShardedEmbedding"):
+        self.mod = mod
+        self.world = mod.world
+        self._stages: Dict[tuple, tuple] = {}
+
+    def stage(self, key, n_floats: int, device):
+        rec = self._stages.get(key)
+        if rec is None or rec[0].numel() < n_floats:
+            import torch.distributed._symmetric_memory as symm
+            group = self.mod.group or dist.group.WORLD
+            buf = symm.empty(max(n_floats, 1024), dtype=torch.float32, device=device)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, group)
+            ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64).to(device)
+            self.mod.sync_peers()
+            rec = self._stages[key] = (buf, ptrs, hdl)
+        return rec[0], rec[1]
+
+    def barrier(self) -> None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.mod.barrier(ops.PeerSync.DENSE, dev)
+
+    def fallback(self, params) -> None:
+        allreduce_dense_grads(params, self.mod.group)
 
 
 class RowWiseShardedEmbedding(nn.Module):
@@ -278,6 +347,14 @@ class RowWiseShardedEmbedding(nn.Module):
             per_gpu = sum((c.category_num + self.world - 1) // self.world for c in self.columns) * sum(self.dims) * 8
             peer = dist.get_backend(group) == "nccl" and (env == "1" or (env != "0" and per_gpu <= cap_gb * 2 ** 30))
         self.peer = bool(peer)
+        # cross-rank ordering by this library's barrier kernels on symmetric-memory flags (default) or by NCCL
+        # (also serves the all-to-all path's dense-gradient reduction: any NCCL group can hold symmetric memory)
+        self.use_peer_sync = dist.get_backend(group) == "nccl" and os.environ.get("PTREC_PEER_SYNC", "1") != "0"
+        # NCCL collectives from a side stream would have to keep one issue order on every rank: early exchange only
+        # with the barrier kernels
+        self.early_exchange = self.peer and self.use_peer_sync and os.environ.get("PTREC_EARLY_EXCHANGE", "1") != "0"
+        self._sync: Optional[ops.PeerSync] = None
+        self._reducer: Optional[_DenseReducer] = None
         self._dirty = False                        # a table update / buffer reset not yet ordered by a collective
         self._peer_key = None                      # (data_ptr, row stride) of every table when pointers were exchanged
         self._symm: Dict[int, Tensor] = {}         # data_ptr -> symmetric-memory allocation that backs a table
@@ -292,13 +369,34 @@ class RowWiseShardedEmbedding(nn.Module):
             _PEER_MODULES.add(self)
 
     # ---- peer-memory path --------------------------------------------------------------------------------------
+    def peer_sync(self, device) -> ops.PeerSync:
+        if self._sync is None:  # collective on first use (symmetric allocation + rendezvous)
+            self._sync = ops.PeerSync(self.group, device)
+        return self._sync
+
+    def barrier(self, slot: int, device) -> None:
+        """Orders everything every rank enqueued before it (on the stream that is current there) ahead of everything
+        any rank enqueues after it: one tiny kernel of this library (``ops.PeerSync``), or — PTREC_PEER_SYNC=0 — a
+        1-element NCCL all_reduce."""
+        if self.use_peer_sync:
+            self.peer_sync(device).barrier(slot)
+        else:
+            if self._fence_buf is None:
+                self._fence_buf = torch.zeros(1, dtype=torch.float32, device=device)
+            dist.all_reduce(self._fence_buf, group=self.group)
+        if slot in (ops.PeerSync.FENCE, ops.PeerSync.DENSE):  # issued on the main stream after the step's updates
+            _mark_fenced(self.group)
+
     def fence(self, device) -> None:
-        """1-element all_reduce on the current stream: orders everything every rank enqueued before it ahead of
-        everything any rank enqueues after it (no kernel of ours ever waits on another rank)."""
-        if self._fence_buf is None:
-            self._fence_buf = torch.zeros(1, dtype=torch.float32, device=device)
-        dist.all_reduce(self._fence_buf, group=self.group)
-        _mark_fenced(self.group)
+        self.barrier(ops.PeerSync.FENCE, device)
+
+    def dense_reducer(self) -> Optional["_DenseReducer"]:
+        """The peer all-reduce hooks for the fused optimizers, or None when ordering goes through NCCL."""
+        if not self.use_peer_sync:
+            return None
+        if self._reducer is None:
+            self._reducer = _DenseReducer(self)
+        return self._reducer
 
     def sync_peers(self) -> None:
         """Host-synchronising fence: call (on every rank) after writing table rows outside the training step."""
@@ -376,7 +474,7 @@ class RowWiseShardedEmbedding(nn.Module):
             F, G = len(self.columns), self.world
             recv_ids = symm.empty(F * G * C, dtype=torch.int64, device=device)
             recv_g = symm.empty(G * F * C, self.slot_width, dtype=torch.float32, device=device)
-            recv_ids.fill_(-1)
+            recv_ids.fill_(-1)  # ranks that have not pushed yet read "no lookup"; every later step rewrites the lists in full
             recv_g.zero_()
             h_ids, h_g = symm.rendezvous(recv_ids, group), symm.rendezvous(recv_g, group)
             b = {"recv_ids": recv_ids, "recv_g": recv_g, "handles": (h_ids, h_g),
@@ -609,4 +707,9 @@ class ShardedDeepFM(DeepFM):
         return [p for p in self.parameters() if id(p) not in table_ids]
 
     def _before_optimizer_step(self) -> None:
-        allreduce_dense_grads(self._dense_params())
+        opt = self.compiled_optimizers
+        red = self.sharded.dense_reducer() if hasattr(opt, "_peer_reduce") else None
+        if red is not None:
+            opt._peer_reduce = red  # the optimizer's K7 launch sums the ranks' gradients itself (one barrier inside)
+        else:
+            allreduce_dense_grads(self._dense_params(), self.sharded.group)

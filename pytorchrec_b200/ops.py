@@ -490,6 +490,47 @@ def a2a_scatter_rows_peer_multi(srcs, dims, cols, ret_pos: torch.Tensor, B: int,
 
 
 # ----------------------------------------------------------------------------------------------
+# C2 cross-GPU ordering over symmetric memory (csrc/peer_sync.cu)
+# ----------------------------------------------------------------------------------------------
+class PeerSync:
+    """Barrier between the ranks of a process group, made of one tiny kernel of this library per call (release /
+    acquire flags in symmetric memory) instead of a NCCL collective.  ``barrier(slot)``: everything every rank
+    enqueued before it on its current stream is complete and visible before anything any rank enqueues after it
+    starts.  Every rank must issue the same sequence of calls per slot; slots are independent, so two streams may
+    each run their own.  Graph-capturable."""
+    FENCE, IDS, GRADS, DENSE = 0, 1, 2, 3
+
+    def __init__(self, group, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        lib = _lib.load()
+        self.group = group or dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        n = lib.ptrec_peer_sync_slots() * lib.ptrec_peer_sync_max_ranks()
+        self.flags = symm.empty(n, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self._hdl = symm.rendezvous(self.flags, self.group)
+        self.peer_flags = torch.tensor([int(p) for p in self._hdl.buffer_ptrs], dtype=torch.int64).to(device)
+        self.epoch = torch.zeros(lib.ptrec_peer_sync_slots(), dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)  # every rank's flags are zero before anyone signals
+
+    def barrier(self, slot: int) -> None:
+        dev = self.flags.device
+        _lib.check(_lib.load().ptrec_peer_barrier(_ptr(self.peer_flags), _ptr(self.epoch), int(slot), self.world,
+                                                  self.rank, _stream(dev)), "ptrec_peer_barrier")
+
+
+def dense_pack(descs: torch.Tensor, chunk_start: torch.Tensor, n_tensors: int, n_chunks: int, stage: torch.Tensor) -> None:
+    """Gradients named by a K7 descriptor table -> the contiguous ``stage`` (n_chunks * chunk floats)."""
+    _require_cuda(descs, chunk_start, stage)
+    assert stage.dtype == torch.float32 and stage.is_contiguous()
+    assert stage.numel() >= n_chunks * _lib.load().ptrec_dense_optim_chunk()
+    _lib.check(_lib.load().ptrec_dense_pack(_ptr(descs), _ptr(chunk_start), n_tensors, n_chunks, _ptr(stage),
+                                            _stream(stage.device)), "ptrec_dense_pack")
+
+
+# ----------------------------------------------------------------------------------------------
 # K6 fp32-faithful Linear on tcgen05 (bf16 x 3 split operands)
 # ----------------------------------------------------------------------------------------------
 def _pad8(n: int) -> int:

@@ -52,6 +52,9 @@ class _FusedSparseOptimizer(Optimizer):
         self._ptr_cache: Dict[int, tuple] = {}
         self._interleaved: Dict[int, torch.Tensor] = {}  # id(param) -> [rows, stride] buffer holding weight | state
         self._dense_plan: Dict[tuple, tuple] = {}        # (dense group, step bucket) -> (pointer key, descriptors, chunk starts, n)
+        # set by data-parallel models whose replicas exchange over NVLink peer memory (distributed/sharded.py):
+        # object with .world, .stage(key, n_floats, device) -> (stage, peer pointer array), .barrier(), .fallback(params)
+        self._peer_reduce = None
 
     def graph_safe(self) -> bool:
         """True when a captured step stays valid on replay (no host-side step count in the arithmetic)."""
@@ -129,6 +132,8 @@ class _FusedSparseOptimizer(Optimizer):
                     if k != "params" and k in group:
                         dg[k] = group[k]
             if not self._fused_dense_step():
+                if self._peer_reduce is not None:  # K7 not applicable: average the gradients with the library collective
+                    self._peer_reduce.fallback([p for g in self._dense.param_groups for p in g["params"]])
                 self._dense.step()
         return loss
 
@@ -157,6 +162,8 @@ class _FusedSparseOptimizer(Optimizer):
             plans.append((gi, dg, ps))
         lib = _lib.load()
         chunk = lib.ptrec_dense_optim_chunk()
+        # phase 1 (host only, may still return False): states, step counters, descriptor tables
+        staged = []
         for gi, dg, ps in plans:
             if not ps:
                 continue
@@ -178,6 +185,9 @@ class _FusedSparseOptimizer(Optimizer):
                         if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
                             return False
                 states.append(st)
+            staged.append((gi, dg, ps, states))
+        launches = []
+        for gi, dg, ps, states in staged:
             # torch.optim keeps one step counter per parameter (a parameter that skipped a step lags behind):
             # one launch per distinct counter value — a single launch in the usual case
             buckets: Dict[int, list] = {}
@@ -217,9 +227,29 @@ class _FusedSparseOptimizer(Optimizer):
                 args = OptimArgs(kind=kind, step=step, lr=dg["lr"], eps=dg.get("eps", 0.0), beta1=betas[0],
                                  beta2=betas[1], weight_decay=dg.get("weight_decay", 0.0),
                                  lr_decay=dg.get("lr_decay", 0.0))
-                stream = ctypes.c_void_p(torch.cuda.current_stream(bps[0].device).cuda_stream)
+                launches.append(((gi, bi), cached, len(bps), args, bps[0].device))
+        # phase 2: launches.  With a peer reducer attached (row-wise sharded models on NVLink peer memory) the
+        # data-parallel mean of the gradients is fused in: pack every group's gradients into this rank's symmetric
+        # stage, ONE barrier, then each K7 launch sums the ranks' stages itself (csrc/peer_sync.cu).
+        red = self._peer_reduce
+        if red is not None:
+            from .. import ops
+            stages = []
+            for pkey, cached, n, args, dev in launches:
+                stage, peer_ptrs = red.stage(pkey, cached[3] * chunk, dev)
+                ops.dense_pack(cached[1], cached[2], n, cached[3], stage)
+                stages.append(peer_ptrs)
+            red.barrier()
+        for li, (pkey, cached, n, args, dev) in enumerate(launches):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            if red is not None:
+                _lib.check(lib.ptrec_dense_optim_step_reduce(
+                    ctypes.c_void_p(cached[1].data_ptr()), ctypes.c_void_p(cached[2].data_ptr()), n, cached[3],
+                    ctypes.byref(args), ctypes.c_void_p(stages[li].data_ptr()), red.world, 1.0 / red.world, stream),
+                    "ptrec_dense_optim_step_reduce")
+            else:
                 _lib.check(lib.ptrec_dense_optim_step(ctypes.c_void_p(cached[1].data_ptr()),
-                                                      ctypes.c_void_p(cached[2].data_ptr()), len(bps), cached[3],
+                                                      ctypes.c_void_p(cached[2].data_ptr()), n, cached[3],
                                                       ctypes.byref(args), stream), "ptrec_dense_optim_step")
         return True
 

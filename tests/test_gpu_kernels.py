@@ -189,17 +189,22 @@ def _check_sort(layout, tables, ids_dev, lens_dev, B, specs, id_list, lens_list,
     return srt
 
 
-@pytest.fixture(params=["smem_sort", "global_sort"])
+@pytest.fixture(params=["smem_sort", "global_sort", "one_sweep_sort"])
 def sort_path(request):
-    """K2a has a one-CTA-per-table shared-memory path and a multi-launch global path: same outputs from both."""
+    """K2a has a one-CTA-per-table shared-memory path, a multi-launch global path (histogram / scan / scatter per
+    digit) and a one-sweep global path (decoupled look-back): same outputs from all three."""
     lib = _lib.load()
+    before = lib.ptrec_one_sweep_sort_enabled()
     lib.ptrec_set_smem_sort(2 if request.param == "smem_sort" else 0)
+    lib.ptrec_set_one_sweep_sort(1 if request.param == "one_sweep_sort" else 0)
     yield request.param
     lib.ptrec_set_smem_sort(1)
+    lib.ptrec_set_one_sweep_sort(before)
 
 
 @pytest.mark.parametrize("B", [1, 100, 2048, 5000, 22528, 30000])
-@pytest.mark.parametrize("rows", [[3, 70000, 257], [1 << 20, 9, 300]])
+@pytest.mark.parametrize("rows", [[3, 70000, 257], [1 << 20, 9, 300], [60000, 200, 7], [5, 1 << 26, 999]],
+                         ids=["17bit", "20bit", "16bit_8bit_digits", "26bit_3_passes"])
 def test_sort_dedup_bit_exact_onehot(B, rows, sort_path):
     D = 4
     weights = _tables([min(r, 64) for r in rows], D, seed=1)  # contents irrelevant: only row counts matter
@@ -265,12 +270,67 @@ OPT_CASES = [
 ]
 
 
-@pytest.mark.parametrize("opt_name,hp", OPT_CASES)
+@pytest.fixture(params=[0, 1, 2, 3], ids=["v1", "pair_2x8", "pair_4x6", "pair_4x4"])
+def update_variant(request):
+    """K2b's Adagrad update has two thread mappings (include/ptrec_b200.h: ptrec_set_update_variant)."""
+    lib = _lib.load()
+    before = lib.ptrec_update_variant()
+    lib.ptrec_set_update_variant(request.param)
+    yield request.param
+    lib.ptrec_set_update_variant(before)
+
+
+@pytest.mark.parametrize("D", [1, 2, 4, 16, 32, 64, 128])
+@pytest.mark.parametrize("hot", [False, True])
+def test_adagrad_update_variants_agree_on_interleaved_rows(D, hot, update_variant):
+    """The paired (weight half | state half) mapping on the interleaved [rows, 2*D] layout the optimizer uses equals
+    the v1 mapping: same sums in the same order, same update."""
+    lib = _lib.load()
+    B, rows = 3000, [777, 50000]
+    lay = ops.FeatureLayout([dict(table=0, bag_len=1), dict(table=1, bag_len=1)], D, 2)
+    g = torch.Generator().manual_seed(D)
+    init = [torch.randn(r, 2 * D, generator=g) for r in rows]
+    for b in init:
+        b[:, D:].abs_()
+    id_list = [_ids((B,), rows[0], seed=3, zipf=hot), _ids((B,), rows[1], seed=4, zipf=hot)]
+    ids = torch.cat(id_list).to(DEV)
+    go = torch.randn(B, 2 * D, generator=g).to(DEV)
+    args = _lib.OptimArgs(kind=_lib.OPT_ADAGRAD, step=2, lr=0.1, eps=1e-10, beta1=0, beta2=0, weight_decay=0.01, lr_decay=0.0)
+    results = []
+    for variant in (0, update_variant):
+        lib.ptrec_set_update_variant(variant)
+        bufs = [b.clone().to(DEV) for b in init]
+        tables = ops.TableSet().refresh([b[:, :D] for b in bufs])
+        p1 = ops.make_ptr_array([b[:, D:] for b in bufs])
+        srt = ops.sort_dedup(tables, lay, ids, None, B)
+        ops.bwd_fused(tables, p1, None, lay, B, srt, go, None, args)
+        results.append([b.cpu() for b in bufs])
+    for a, b, i0 in zip(results[0], results[1], init):
+        assert not torch.equal(a, i0)
+        np.testing.assert_allclose(b.numpy(), a.numpy(), rtol=1e-6, atol=1e-7)
+
+
+# every optimizer on the v1 mapping; Adagrad also on the three paired mappings
+OPT_VARIANT_CASES = [(n, hp, 0) for n, hp in OPT_CASES] + [(n, hp, v) for n, hp in OPT_CASES if n == "adagrad" for v in (1, 2, 3)]
+
+
+@pytest.mark.parametrize("opt_name,hp,variant", OPT_VARIANT_CASES,
+                         ids=[f"{n}-v{v}" for n, _, v in OPT_VARIANT_CASES])
 @pytest.mark.parametrize("D", [1, 8, 16, 64])
 @pytest.mark.parametrize("hot", [False, True])
-def test_fused_update_matches_dense_optimizers(opt_name, hp, D, hot):
+def test_fused_update_matches_dense_optimizers(opt_name, hp, variant, D, hot):
     """Three steps of sort+dedup+fused update vs torch's dense optimizer fed the dense reference gradient.
     `hot` makes ids Zipf-heavy so that runs longer than 32 exercise the CTA-per-segment kernel."""
+    lib = _lib.load()
+    before = lib.ptrec_update_variant()
+    lib.ptrec_set_update_variant(variant)
+    try:
+        _fused_update_case(opt_name, hp, D, hot)
+    finally:
+        lib.ptrec_set_update_variant(before)
+
+
+def _fused_update_case(opt_name, hp, D, hot):
     B, L = 600, 9
     rows = [50, 3000]
     weights = _tables(rows, D, seed=D + 1)
