@@ -73,8 +73,10 @@ def config_dict(a, world):
             "global_batch": a.batch * world, "id_dist": a.id_dist, "cuda_graph": not a.no_graph,
             "parallelism": "single GPU" if world == 1 else (
                 f"row-wise sharded tables x{world} ("
-                + ("NVLink peer-memory gather / push inside the kernels" if getattr(a, "peer_path", True)
-                   else "NCCL all-to-all") + ") + dense allreduce"),
+                + {"push": "owners push rows / requesters push gradients over NVLink inside the kernels, barrier kernels, "
+                           "dense all-reduce fused into the optimizer launch: no NCCL collective in the step",
+                   "pull": "NVLink peer-memory gather / gradient push inside the kernels",
+                   "a2a": "NCCL all-to-all"}[getattr(a, "exchange", "push")] + ")"),
             "l2": "tables %.2f GB >> 126 MB L2; a different random id batch every step" %
                   (26 * a.rows * (a.dim + 1) * 4 / 1e9)}
 
@@ -225,7 +227,7 @@ def measure_deepfm(a, dev, rank, world, lib, steps, warmup, with_e2e, sampler=No
     else:
         from pytorchrec_b200.distributed import ShardedDeepFM
         model = ShardedDeepFM(sparse, dense, label, a.dim, CFG["layers"], random_seed=2020, table_device=dev)
-    a.peer_path = bool(getattr(getattr(model, "sharded", None), "peer", False))
+    a.exchange = getattr(getattr(model, "sharded", None), "exchange", "none")
     opt = SparseAdagrad(params=model.get_parameters(), lr=0.01)
     model.compile(opt, torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)
     if not a.no_graph:

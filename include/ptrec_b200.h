@@ -484,8 +484,9 @@ int ptrec_a2a_scatter_rows(const float* src, int64_t src_row_stride, const int32
 
 /* Peer-memory dispatch (no all-to-all): the same lists and gradient rows are STORED straight into the owners'
  * receive buffers over NVLink, in the layout the owner-side ptrec_sort_dedup / ptrec_embedding_bwd_fused read:
- *   peer_ids [G] device array; peer_ids[o] = rank o's id buffer [F, G_src, C] int64 (the owner keeps unused slots
- *            at -1: it resets its buffer after consuming it); this rank writes peer_ids[o][(f*G + my_rank)*C + slot]
+ *   peer_ids [G] device array; peer_ids[o] = rank o's id buffer [F, G_src, C] int64; this rank writes its lists
+ *            peer_ids[o][(f*G + my_rank)*C + slot] IN FULL every call (lookups, then -1 up to C), so the owner
+ *            never resets anything
  *   peer_dst [G] device array; peer_dst[o] = rank o's gradient buffer [G_src*F*C, dst_row_stride] float32; this rank
  *            writes row my_rank*F*C + (ret_pos mod F*C), columns [dst_col, dst_col + D)
  * ret_pos keeps the meaning above.  The caller fences (one small collective) between these stores and the owners'
@@ -496,6 +497,29 @@ int ptrec_a2a_pack_by_owner_peer(const int64_t* ids, int64_t B, int32_t F, int32
 int ptrec_a2a_scatter_rows_peer(const float* src, int64_t src_row_stride, const int32_t* ret_pos, int64_t B,
                                 int32_t F, int32_t D, float scale, float* const* peer_dst, int64_t dst_row_stride,
                                 int64_t dst_col, int32_t C, int32_t G, int32_t my_rank, void* stream);
+
+/* Push mode of the forward exchange (the fused form of owner-side gather -> all-to-all(rows) -> gather by slot; no
+ * reference counterpart, torchrec/task/Task.py:187-190):
+ *   ptrec_a2a_pack_by_owner_push  as ..._peer, and also stores each lookup's sample index b into the owner's
+ *     peer_b[o][(f*G + my_rank)*C + slot] (int32) — where the owner must deliver the row; output rows that no owner
+ *     will write (negative id, overflowed list) are zeroed in local_out[k][b*out_row_strides[k] + f*dims[k] ...]
+ *     (local_out / out_row_strides / dims: HOST arrays of n_widths <= 4 entries).
+ *   ptrec_gather_push  run by the OWNER after a barrier: for every received slot (f, src, c) with id >= 0, read row
+ *     `id` of its shard of table f (every width k: table_ptrs[k] is a DEVICE array [F] of shard bases) and store it
+ *     into the requester's output  peer_out[k][src] + recv_b*out_row_strides[k] + f*dims[k]  over NVLink
+ *     (peer_out[k]: DEVICE array [G] of the ranks' output buffers of width k).  table_ptrs / peer_out / row_strides /
+ *     out_row_strides / dims: HOST arrays of n_widths entries.  shard_rows [F] device int64 (ids beyond -> err_flag).
+ * The caller puts a barrier (ptrec_peer_barrier) between pack and gather_push, and between gather_push and the
+ * requester's reads of its output. */
+int ptrec_a2a_pack_by_owner_push(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C, int32_t my_rank,
+                                 int64_t* const* peer_ids, int32_t* const* peer_b, float* const* local_out,
+                                 const int64_t* out_row_strides, const int32_t* dims, int32_t n_widths,
+                                 int32_t* ret_pos, int32_t* overflow, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+int ptrec_gather_push(const void* const* const* table_ptrs, float* const* const* peer_out, const int64_t* row_strides,
+                      const int64_t* out_row_strides, const int32_t* dims, int32_t n_widths, const int64_t* recv_ids,
+                      const int32_t* recv_b, const int64_t* shard_rows, int32_t F, int32_t G, int32_t C,
+                      int32_t* err_flag, void* stream);
 
 /* Same, every embedding width of the fields in one launch (srcs / strides / dims / dst_cols: HOST arrays of n_widths
  * entries, n_widths <= 4): the stores of one slot to its owner are adjacent. */

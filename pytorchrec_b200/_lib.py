@@ -148,6 +148,11 @@ PROTOTYPES = {
                                              c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ptrec_a2a_scatter_rows_peer": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p,
                                             c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p]),
+    "ptrec_a2a_pack_by_owner_push": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                             c_size_t, c_void_p]),
+    "ptrec_gather_push": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                  c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "ptrec_a2a_scatter_rows_peer_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64,
                                                   c_int32, c_float, c_void_p, c_int64, c_int32, c_int32, c_int32,
                                                   c_void_p]),

@@ -14,6 +14,8 @@
 // so the dispatch needs no all-to-all; the caller orders "all pushes done" before the owner consumes them with a
 // barrier (peer_sync.cu); every list is written in full (lookups, then -1 up to its capacity), so the owner never
 // resets anything.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ptrec {
@@ -53,10 +55,19 @@ __global__ void pack_scan_kernel(int* __restrict__ counts, int G, int tiles, int
   if (run > C && overflow != nullptr) atomicMax(overflow, run);
 }
 
+// push mode: rows that no owner will write (negative id, overflowed list) are zeroed here, in the local output
+struct ZeroFill {
+  float* out[4];
+  int64_t stride[4];
+  int32_t dim[4];
+  int32_t n;
+};
+
 __global__ void __launch_bounds__(kPackThreads)
 pack_scatter_kernel(const int64_t* __restrict__ ids, int64_t B, int F, int G, int tiles, int C,
                     const int* __restrict__ bases, int64_t* __restrict__ send_ids, int32_t* __restrict__ ret_pos,
-                    int64_t* const* __restrict__ peer_ids, int my_rank) {
+                    int64_t* const* __restrict__ peer_ids, int32_t* const* __restrict__ peer_b, ZeroFill zf,
+                    int my_rank) {
   constexpr int NW = kPackThreads / 32;
   __shared__ int s_cnt[NW][kMaxRanks];
   __shared__ int s_base[kMaxRanks];
@@ -117,10 +128,19 @@ pack_scatter_kernel(const int64_t* __restrict__ ids, int64_t B, int F, int G, in
         const int slot = s_cnt[warp][dest[i]] + rank[i];
         if (slot < C) {
           pos = (int32_t)(((int64_t)dest[i] * F + f) * C + slot);
-          if (peer_ids != nullptr)
-            s_peer[dest[i]][((int64_t)f * G + my_rank) * C + slot] = id[i] / G;
-          else
+          if (peer_ids != nullptr) {
+            const int64_t at = ((int64_t)f * G + my_rank) * C + slot;
+            s_peer[dest[i]][at] = id[i] / G;
+            if (peer_b != nullptr) peer_b[dest[i]][at] = (int32_t)b;  // push mode: where the owner must deliver the row
+          } else {
             send_ids[pos] = id[i] / G;
+          }
+        }
+      }
+      if (pos < 0) {
+        for (int k = 0; k < zf.n; ++k) {
+          float* o = zf.out[k] + b * zf.stride[k] + (int64_t)f * zf.dim[k];
+          for (int e = 0; e < zf.dim[k]; ++e) o[e] = 0.f;
         }
       }
       ret_pos[(int64_t)f * B + b] = pos;
@@ -205,9 +225,134 @@ scatter_rows_peer_multi_kernel(PeerWidths w, const int32_t* __restrict__ pos, in
   }
 }
 
+// ---- push mode forward: the OWNER gathers the rows of the lists it received and stores each one straight into the
+// requester's output row over NVLink / NVSwitch — the fused form of  owner-side gather -> all-to-all(rows) -> gather by
+// slot.  Random accesses stay local (the owner's own shard); remote traffic is contiguous row stores into a buffer of
+// batch x F x D floats.  Every width of a slot in one launch (lanes cover the float4 chunks of [width 0 | width 1 | ...]),
+// kPushUnroll slots in flight per sub-warp.
+constexpr int kPushUnroll = 4;
+struct PushArgs {
+  const void* const* table_ptrs[kMaxWidths];  // [T] shard bases of width k (device array)
+  float* const* peer_out[kMaxWidths];         // [G] the requesters' output buffers of width k (device array)
+  int64_t row_stride[kMaxWidths];
+  int64_t out_stride[kMaxWidths];
+  int32_t dim[kMaxWidths];
+  int32_t chunk0[kMaxWidths + 1];
+  int32_t n;
+};
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+gather_push_kernel(PushArgs a, const int64_t* __restrict__ recv_ids, const int32_t* __restrict__ recv_b,
+                   const int64_t* __restrict__ shard_rows, int F, int G, int C, int32_t* err_flag) {
+  const int lane = threadIdx.x % LPR;
+  const int64_t groups = (int64_t)gridDim.x * (256 / LPR);
+  const int64_t g0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) / LPR;
+  const int64_t n_slots = (int64_t)F * G * C;
+  if (lane >= a.chunk0[a.n]) return;
+  int k = 0;
+  while (k + 1 < a.n && lane >= a.chunk0[k + 1]) ++k;
+  const int c = (lane - a.chunk0[k]) * 4;  // first element of this lane's chunk inside width k
+  const int D = a.dim[k];
+  const bool vec = (c + 3 < D) && ((D & 3) == 0);
+  for (int64_t s0 = g0; s0 < n_slots; s0 += groups * kPushUnroll) {
+    float4 v[kPushUnroll];
+    float* dst[kPushUnroll];
+#pragma unroll
+    for (int u = 0; u < kPushUnroll; ++u) {
+      const int64_t s = s0 + u * groups;
+      dst[u] = nullptr;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s < n_slots) {
+        const int64_t id = recv_ids[s];
+        if (id >= 0) {
+          const int f = (int)(s / ((int64_t)G * C));
+          const int src = (int)((s - (int64_t)f * G * C) / C);
+          if (id < shard_rows[f]) {
+            const float* row = reinterpret_cast<const float*>(a.table_ptrs[k][f]) + id * a.row_stride[k] + c;
+            if (vec) {
+              v[u] = ldg_stream_f4(row);
+            } else {
+              v[u].x = row[0];
+              if (c + 1 < D) v[u].y = row[1];
+              if (c + 2 < D) v[u].z = row[2];
+            }
+            dst[u] = a.peer_out[k][src] + (int64_t)recv_b[s] * a.out_stride[k] + (int64_t)f * D + c;
+          } else if (err_flag != nullptr && lane == 0) {
+            *err_flag = 1;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPushUnroll; ++u) {
+      if (dst[u] == nullptr) continue;
+      if (vec) {
+        *reinterpret_cast<float4*>(dst[u]) = v[u];
+      } else {
+        dst[u][0] = v[u].x;
+        if (c + 1 < D) dst[u][1] = v[u].y;
+        if (c + 2 < D) dst[u][2] = v[u].z;
+      }
+    }
+  }
+}
+
 }  // namespace ptrec
 
 using namespace ptrec;
+
+extern "C" int ptrec_gather_push(const void* const* const* table_ptrs, float* const* const* peer_out,
+                                 const int64_t* row_strides, const int64_t* out_row_strides, const int32_t* dims,
+                                 int32_t n_widths, const int64_t* recv_ids, const int32_t* recv_b,
+                                 const int64_t* shard_rows, int32_t F, int32_t G, int32_t C, int32_t* err_flag,
+                                 void* stream) {
+  PTREC_CHECK_ARG(table_ptrs && peer_out && row_strides && out_row_strides && dims && recv_ids && recv_b && shard_rows,
+                  PTREC_EINVAL, "gather_push: null pointer");
+  PTREC_CHECK_ARG(n_widths >= 1 && n_widths <= kMaxWidths && F >= 1 && G >= 1 && G <= kMaxRanks && C >= 1, PTREC_EINVAL,
+                  "gather_push: bad sizes widths=%d F=%d G=%d C=%d", n_widths, F, G, C);
+  PushArgs a;
+  int chunks = 0;
+  for (int k = 0; k < kMaxWidths; ++k) {
+    const bool on = k < n_widths;
+    a.table_ptrs[k] = on ? table_ptrs[k] : nullptr;
+    a.peer_out[k] = on ? peer_out[k] : nullptr;
+    a.row_stride[k] = on ? row_strides[k] : 0;
+    a.out_stride[k] = on ? out_row_strides[k] : 0;
+    a.dim[k] = on ? dims[k] : 0;
+    a.chunk0[k] = chunks;
+    if (on) {
+      PTREC_CHECK_ARG(dims[k] >= 1 && dims[k] <= 128, PTREC_EINVAL, "gather_push: width %d", k);
+      PTREC_CHECK_ARG((dims[k] & 3) != 0 || (row_strides[k] % 4 == 0 && out_row_strides[k] % 4 == 0), PTREC_EALIGN,
+                      "gather_push: width %d strides must be multiples of 4 floats", k);
+      chunks += (dims[k] + 3) / 4;
+    }
+  }
+  a.chunk0[kMaxWidths] = chunks;
+  for (int k = n_widths; k <= kMaxWidths; ++k) a.chunk0[k] = chunks;
+  a.n = n_widths;
+  PTREC_CHECK_ARG(chunks <= 32, PTREC_EUNSUPPORTED, "gather_push: slot wider than 128 floats");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_slots = (int64_t)F * G * C;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#define PTREC_PUSH(P)                                                                                          \
+  {                                                                                                            \
+    const int64_t want = ceil_div(n_slots * P, 256 * kPushUnroll);                                             \
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * 8));            \
+    gather_push_kernel<P><<<grid, 256, 0, st>>>(a, recv_ids, recv_b, shard_rows, F, G, C, err_flag);            \
+    PTREC_LAUNCH_CHECK("gather_push_kernel");                                                                  \
+    return PTREC_OK;                                                                                           \
+  }
+  if (chunks <= 1) PTREC_PUSH(1)
+  if (chunks <= 2) PTREC_PUSH(2)
+  if (chunks <= 4) PTREC_PUSH(4)
+  if (chunks <= 8) PTREC_PUSH(8)
+  if (chunks <= 16) PTREC_PUSH(16)
+  PTREC_PUSH(32)
+#undef PTREC_PUSH
+}
 
 extern "C" size_t ptrec_a2a_pack_workspace_bytes(int64_t B, int32_t F, int32_t G) {
   const int64_t tiles = ceil_div(B, kPackTile);
@@ -215,8 +360,8 @@ extern "C" size_t ptrec_a2a_pack_workspace_bytes(int64_t B, int32_t F, int32_t G
 }
 
 static int pack_impl(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C, int64_t* send_ids,
-                     int64_t* const* peer_ids, int32_t my_rank, int32_t* ret_pos, int32_t* overflow, void* workspace,
-                     size_t workspace_bytes, void* stream) {
+                     int64_t* const* peer_ids, int32_t* const* peer_b, const ZeroFill& zf, int32_t my_rank,
+                     int32_t* ret_pos, int32_t* overflow, void* workspace, size_t workspace_bytes, void* stream) {
   PTREC_CHECK_ARG(ids && (send_ids || peer_ids) && ret_pos && workspace, PTREC_EINVAL, "a2a_pack: null pointer");
   PTREC_CHECK_ARG(my_rank >= 0 && my_rank < G, PTREC_EINVAL, "a2a_pack: rank %d outside [0, %d)", my_rank, G);
   PTREC_CHECK_ARG(B >= 0 && F >= 1 && F <= 65535 && G >= 1 && G <= kMaxRanks && C >= 1, PTREC_EINVAL,
@@ -235,7 +380,7 @@ static int pack_impl(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_
   pack_scan_kernel<<<F, kMaxRanks, 0, st>>>(counts, G, tiles, C, overflow);
   PTREC_LAUNCH_CHECK("pack_scan_kernel");
   pack_scatter_kernel<<<grid, kPackThreads, 0, st>>>(ids, B, F, G, tiles, C, counts, send_ids, ret_pos, peer_ids,
-                                                     my_rank);
+                                                     peer_b, zf, my_rank);
   PTREC_LAUNCH_CHECK("pack_scatter_kernel");
   return PTREC_OK;
 }
@@ -244,7 +389,9 @@ extern "C" int ptrec_a2a_pack_by_owner(const int64_t* ids, int64_t B, int32_t F,
                                        int64_t* send_ids, int32_t* ret_pos, int32_t* overflow, void* workspace,
                                        size_t workspace_bytes, void* stream) {
   PTREC_CHECK_ARG(send_ids, PTREC_EINVAL, "a2a_pack: null send_ids");
-  return pack_impl(ids, B, F, G, C, send_ids, nullptr, 0, ret_pos, overflow, workspace, workspace_bytes, stream);
+  ZeroFill zf{};
+  return pack_impl(ids, B, F, G, C, send_ids, nullptr, nullptr, zf, 0, ret_pos, overflow, workspace, workspace_bytes,
+                   stream);
 }
 
 extern "C" int ptrec_a2a_pack_by_owner_peer(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C,
@@ -252,7 +399,28 @@ extern "C" int ptrec_a2a_pack_by_owner_peer(const int64_t* ids, int64_t B, int32
                                             int32_t* overflow, void* workspace, size_t workspace_bytes,
                                             void* stream) {
   PTREC_CHECK_ARG(peer_ids, PTREC_EINVAL, "a2a_pack_peer: null peer pointer array");
-  return pack_impl(ids, B, F, G, C, nullptr, peer_ids, my_rank, ret_pos, overflow, workspace, workspace_bytes, stream);
+  ZeroFill zf{};
+  return pack_impl(ids, B, F, G, C, nullptr, peer_ids, nullptr, zf, my_rank, ret_pos, overflow, workspace,
+                   workspace_bytes, stream);
+}
+
+extern "C" int ptrec_a2a_pack_by_owner_push(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C,
+                                            int32_t my_rank, int64_t* const* peer_ids, int32_t* const* peer_b,
+                                            float* const* local_out, const int64_t* out_row_strides,
+                                            const int32_t* dims, int32_t n_widths, int32_t* ret_pos,
+                                            int32_t* overflow, void* workspace, size_t workspace_bytes, void* stream) {
+  PTREC_CHECK_ARG(peer_ids && peer_b && local_out && out_row_strides && dims, PTREC_EINVAL,
+                  "a2a_pack_push: null pointer");
+  PTREC_CHECK_ARG(n_widths >= 1 && n_widths <= 4, PTREC_EINVAL, "a2a_pack_push: 1..4 widths");
+  ZeroFill zf{};
+  zf.n = n_widths;
+  for (int k = 0; k < n_widths; ++k) {
+    zf.out[k] = local_out[k];
+    zf.stride[k] = out_row_strides[k];
+    zf.dim[k] = dims[k];
+  }
+  return pack_impl(ids, B, F, G, C, nullptr, peer_ids, peer_b, zf, my_rank, ret_pos, overflow, workspace,
+                   workspace_bytes, stream);
 }
 
 extern "C" int ptrec_a2a_scatter_rows(const float* src, int64_t src_row_stride, const int32_t* ret_pos, int64_t B,

@@ -5,7 +5,16 @@ has a reference counterpart, it widens the same hot path to the 8 x B200 box.
 
 Plan:  owner(id) = id mod G,  local_row = id div G.
 
-Peer-memory path (default on NCCL process groups while the shards stay below PTREC_PEER_MAX_GB = 16 GB per GPU;
+Push path (default on NCCL process groups; PTREC_EXCHANGE=push): nothing but small id lists and whole rows crosses
+NVLink, every random access stays on the GPU that owns the row, and no NCCL collective is issued:
+  forward   pack ids (+ the sample index of each lookup) by owner, stored straight into the owners' lists -> barrier
+            -> every OWNER gathers the rows of the lists it received and stores each one straight into the
+            requester's output row (``ptrec_gather_push``: the fused form of gather -> all-to-all -> gather by slot)
+            -> barrier.  The owner-side sort / dedup of the received lists runs on a side stream meanwhile.
+  backward  as the pull path below: gradient rows stored into the owners' buffers -> barrier -> fused update.
+  dense     as below (all-reduce fused into the K7 optimizer launch).
+
+Pull path (PTREC_EXCHANGE=pull or ``peer=True``; NCCL process groups while the shards stay below PTREC_PEER_MAX_GB = 16 GB per GPU;
 ``peer=True/False`` or PTREC_PEER_GATHER=1/0 force one or the other):
 the shards and the owners' receive buffers live in symmetric memory, every rank holds the peers' pointers, and
 the exchange happens INSIDE the kernels over NVLink / NVSwitch:
@@ -259,6 +268,77 @@ class _PeerLookup(torch.autograd.Function):
         return (None, None) + (None,) * (len(mod.dims) * len(mod.columns))
 
 
+class _PushLookup(torch.autograd.Function):
+    """Push-mode lookup (module docstring): owners deliver rows into the requesters' outputs over NVLink."""
+
+    @staticmethod
+    def forward(ctx, mod: "RowWiseShardedEmbedding", ids: Tensor, *weights):
+        F, B = ids.shape
+        dev = ids.device
+        G = mod.world
+        if mod._dirty:
+            mod.fence(dev)
+        C = mod.capacity(B)
+        pb = mod.peer_buffers(C, dev)
+        po = mod.push_outputs(B, dev)
+        ret_pos = ops.a2a_pack_by_owner_push(ids, F, B, G, C, mod.rank, pb["peer_ids"], pb["peer_b"], po["outs"], mod.dims,
+                                             mod.overflow_flag(dev))
+        mod.publish_overflow(dev)
+        mod.barrier(ops.PeerSync.IDS, dev)   # every rank's lists have landed in every owner's buffers
+        n_t = len(mod.columns)
+        tabs = [mod.egroups[k].table_set.refresh([w.detach() for w in weights[k * n_t:(k + 1) * n_t]])
+                for k in range(len(mod.dims))]
+        ctx.early = None
+        if any(ctx.needs_input_grad[2:]):
+            # the owner-side sort depends on the received ids only: side stream, joined by the backward
+            main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                srt = ops.sort_dedup(tabs[0], mod.owner_layout(C, 0), pb["recv_ids"], None, C)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            for t in (srt.sorted_keys, srt.perm, srt.seg_start, srt.seg_meta, srt.n_seg):
+                t.record_stream(main)
+            ctx.early = (srt, ev)
+        ops.gather_push([t.ptrs for t in tabs], po["peer_outs"], [t.row_stride or d for t, d in zip(tabs, mod.dims)],
+                        [o.stride(0) for o in po["outs"]], mod.dims, pb["recv_ids"], pb["recv_b"], tabs[0].rows, F, G, C,
+                        err_flag=mod.egroups[0].err_flag(dev))
+        mod.barrier(ops.PeerSync.ROWS, dev)  # every owner's rows have landed in this rank's outputs
+        ctx.mod, ctx.shape, ctx.C = mod, (F, B), C
+        ctx.save_for_backward(ret_pos)
+        return tuple(o.view(B, F, d) for o, d in zip(po["outs"], mod.dims))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        mod, C = ctx.mod, ctx.C
+        F, B = ctx.shape
+        G, S = mod.world, mod.slot_width
+        (ret_pos,) = ctx.saved_tensors
+        dev = ret_pos.device
+        pb = mod.peer_buffers(C, dev)
+        gs = []
+        for k, D in enumerate(mod.dims):
+            g = grads[k]
+            g = torch.zeros(B, F * D, device=dev) if g is None else g.reshape(B, F * D)
+            gs.append(g if g.is_contiguous() else g.contiguous())
+        ops.a2a_scatter_rows_peer_multi(gs, mod.dims, mod.col_of, ret_pos, B, F, mod.grad_scale, pb["peer_g"], S, C, G,
+                                        mod.rank)
+        mod.barrier(ops.PeerSync.GRADS, dev)  # every rank's gradient rows have landed in every owner's buffer
+        srt, ev = ctx.early
+        torch.cuda.current_stream(dev).wait_event(ev)  # join the early sort
+        recv_g = pb["recv_g"]
+        for k, D in enumerate(mod.dims):
+            eg = mod.egroups[k]
+            bind = eg.binding()
+            if bind is None:
+                raise RuntimeError("row-wise sharded tables need a pytorchrec_b200.optim sparse optimizer")
+            s1, s2, args = bind[0]._fused_prepare(eg, bind[1])  # may interleave weight | state: before taking pointers
+            tables = eg.table_set.refresh([t.weight.data for t in eg.tables])
+            ops.bwd_fused(tables, s1, s2, mod.owner_layout(C, k), C, srt, recv_g, None, args, grad_row_stride=S)
+        mod._dirty = True   # tables changed, buffers recycled: a fence must precede the next exchange
+        return (None, None) + (None,) * (len(mod.dims) * len(mod.columns))
+
+
 class _DenseReducer:
     """What a fused optimizer needs to average the replicated dense gradients over NVLink peer memory
     (``optim/sparse.py::_fused_dense_step``): per-launch stages in symmetric memory, one barrier, a fallback."""
@@ -336,16 +416,24 @@ class RowWiseShardedEmbedding(nn.Module):
         self._overflow: Dict[torch.device, Tensor] = {}
         self._bufs: Dict[tuple, dict] = {}
         # ---- peer-memory path state ----
-        if peer is None:
-            # Peer-memory exchange where the shards are small, NCCL all-to-all where they are huge: with 83 GB of
-            # weight|state per GPU (cfg5) random rows across 7 x 83 GB of peer mappings ran 10.1 ms/step against
-            # 6.8 ms for the all-to-all path (which touches remote memory only through contiguous buffers), while at
-            # cfg2 (< 2 GB per GPU) the peer path wins (profiles/r1_bench_cfg5_n8_{peer,a2a}.json).  The estimate uses
-            # the rank-independent shard height so that every rank takes the same decision.
-            env = os.environ.get("PTREC_PEER_GATHER", "auto")
-            cap_gb = float(os.environ.get("PTREC_PEER_MAX_GB", "16"))
-            per_gpu = sum((c.category_num + self.world - 1) // self.world for c in self.columns) * sum(self.dims) * 8
-            peer = dist.get_backend(group) == "nccl" and (env == "1" or (env != "0" and per_gpu <= cap_gb * 2 ** 30))
+        # exchange mode: "push" (owners deliver rows; default on NCCL groups), "pull" (requesters read the owners'
+        # shards in symmetric memory: the round-1 peer path; ``peer=True`` / PTREC_PEER_GATHER=1), "a2a" (NCCL
+        # all-to-all; any backend; ``peer=False`` / PTREC_PEER_GATHER=0)
+        nccl = dist.get_backend(group) == "nccl"
+        mode = os.environ.get("PTREC_EXCHANGE", "auto")
+        legacy = os.environ.get("PTREC_PEER_GATHER", "auto")
+        if peer is not None:
+            mode = "pull" if peer else "a2a"
+        elif mode == "auto" and legacy in ("0", "1"):
+            mode = "pull" if legacy == "1" else "a2a"
+        elif mode == "auto":
+            mode = "push" if nccl and os.environ.get("PTREC_PEER_SYNC", "1") != "0" else "a2a"
+        if mode not in ("push", "pull", "a2a"):
+            raise ValueError(f"PTREC_EXCHANGE must be push, pull, a2a or auto, got {mode!r}")
+        if mode != "a2a" and not nccl:
+            raise RuntimeError(f"exchange mode {mode!r} needs an NCCL process group (symmetric memory over NVLink)")
+        self.exchange = mode
+        peer = mode == "pull"
         self.peer = bool(peer)
         # cross-rank ordering by this library's barrier kernels on symmetric-memory flags (default) or by NCCL
         # (also serves the all-to-all path's dense-gradient reduction: any NCCL group can hold symmetric memory)
@@ -353,6 +441,9 @@ class RowWiseShardedEmbedding(nn.Module):
         # NCCL collectives from a side stream would have to keep one issue order on every rank: early exchange only
         # with the barrier kernels
         self.early_exchange = self.peer and self.use_peer_sync and os.environ.get("PTREC_EARLY_EXCHANGE", "1") != "0"
+        if self.exchange == "push" and not self.use_peer_sync:
+            raise RuntimeError("the push exchange orders its stores with the barrier kernels: PTREC_PEER_SYNC=0 is not compatible")
+        self._push_out: Dict[tuple, dict] = {}
         self._sync: Optional[ops.PeerSync] = None
         self._reducer: Optional[_DenseReducer] = None
         self._dirty = False                        # a table update / buffer reset not yet ordered by a collective
@@ -365,7 +456,7 @@ class RowWiseShardedEmbedding(nn.Module):
         self._plain_layouts: Dict[int, ops.FeatureLayout] = {}
         self._peer_bufs: Dict[tuple, dict] = {}
         self._fence_buf: Optional[Tensor] = None
-        if self.peer:
+        if self.exchange != "a2a":
             _PEER_MODULES.add(self)
 
     # ---- peer-memory path --------------------------------------------------------------------------------------
@@ -474,15 +565,40 @@ class RowWiseShardedEmbedding(nn.Module):
             F, G = len(self.columns), self.world
             recv_ids = symm.empty(F * G * C, dtype=torch.int64, device=device)
             recv_g = symm.empty(G * F * C, self.slot_width, dtype=torch.float32, device=device)
+            recv_b = symm.empty(F * G * C, dtype=torch.int32, device=device)  # push mode: sample index of each lookup
+            recv_b.zero_()
+            h_b = symm.rendezvous(recv_b, group)
             recv_ids.fill_(-1)  # ranks that have not pushed yet read "no lookup"; every later step rewrites the lists in full
             recv_g.zero_()
             h_ids, h_g = symm.rendezvous(recv_ids, group), symm.rendezvous(recv_g, group)
-            b = {"recv_ids": recv_ids, "recv_g": recv_g, "handles": (h_ids, h_g),
+            b = {"recv_ids": recv_ids, "recv_g": recv_g, "recv_b": recv_b, "handles": (h_ids, h_g, h_b),
+                 "peer_b": torch.tensor([int(p) for p in h_b.buffer_ptrs], dtype=torch.int64).to(device),
                  "peer_ids": torch.tensor([int(p) for p in h_ids.buffer_ptrs], dtype=torch.int64).to(device),
                  "peer_g": torch.tensor([int(p) for p in h_g.buffer_ptrs], dtype=torch.int64).to(device)}
             self._peer_bufs[key] = b
             self.sync_peers()
         return b
+
+    def push_outputs(self, B: int, device) -> dict:
+        """This rank's lookup outputs, one [B, F * D_k] buffer per width in symmetric memory (the owners store rows
+        into them), + the device arrays of every rank's buffers (collective on first use of a batch size)."""
+        key = (B, device)
+        po = self._push_out.get(key)
+        if po is None:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group or dist.group.WORLD
+            F = len(self.columns)
+            outs, peer_outs, handles = [], [], []
+            for d in self.dims:
+                o = symm.empty(B, F * d, dtype=torch.float32, device=device)
+                o.zero_()
+                h = symm.rendezvous(o, group)
+                outs.append(o)
+                handles.append(h)
+                peer_outs.append(torch.tensor([int(p) for p in h.buffer_ptrs], dtype=torch.int64).to(device))
+            po = self._push_out[key] = {"outs": outs, "peer_outs": peer_outs, "handles": handles}
+            self.sync_peers()
+        return po
 
     @property
     def emb_size(self) -> int:
@@ -570,7 +686,9 @@ class RowWiseShardedEmbedding(nn.Module):
                 if self.peer and getattr(t.weight, "_ptrec_alloc", None) is None:
                     t.weight._ptrec_alloc = self._symm_alloc((col.category_num + self.world - 1) // self.world)
                 weights.append(t.weight)
-        if self.peer:
+        if self.exchange == "push":
+            outs = _PushLookup.apply(self, ids, *weights)
+        elif self.peer:
             self._ensure_peer(ids.device)
             outs = _PeerLookup.apply(self, ids, *weights)
         else:
@@ -684,7 +802,7 @@ class ShardedDeepFM(DeepFM):
             opt._dense.load_state_dict(state["dense"])
         opt._step_count_fused = int(state.get("step", 0))
         opt._ptr_cache.clear()
-        if self.sharded.peer:
+        if self.sharded.exchange != "a2a":
             self.sharded.sync_peers()
 
     @torch.no_grad()
@@ -699,8 +817,8 @@ class ShardedDeepFM(DeepFM):
         for key, v in own.items():
             if not key.startswith("sharded."):
                 v.copy_(state_dict[key])
-        if self.sharded.peer:
-            self.sharded.sync_peers()  # peers read these rows directly
+        if self.sharded.exchange != "a2a":
+            self.sharded.sync_peers()  # peers read these rows directly / the next exchange must see them
 
     def _dense_params(self) -> List[Tensor]:
         table_ids = {id(t.weight) for t in self.sharded.tables}

@@ -462,6 +462,45 @@ def a2a_pack_by_owner_peer(ids: torch.Tensor, F: int, B: int, G: int, C: int, ra
     return ret_pos
 
 
+def a2a_pack_by_owner_push(ids: torch.Tensor, F: int, B: int, G: int, C: int, rank: int, peer_ids: torch.Tensor,
+                           peer_b: torch.Tensor, outs, dims, overflow: torch.Tensor) -> torch.Tensor:
+    """Push-mode pack: ids [F, B] -> ret_pos [F, B]; local rows go to the owners' id lists (``peer_ids`` [G] addresses
+    of int64 [F, G, C]) and the sample index of each lookup to their ``peer_b`` lists (int32, same indexing); rows
+    of the local outputs ``outs[k]`` [B, F*dims[k]] that no owner will write are zeroed."""
+    lib = _lib.load()
+    _require_cuda(ids, overflow, peer_ids, peer_b, *outs)
+    dev = ids.device
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.numel() == F * B and peer_ids.numel() == G == peer_b.numel()
+    n = len(outs)
+    assert n == len(dims) and all(o.dtype == torch.float32 and o.stride(-1) == 1 for o in outs)
+    ret_pos = torch.empty(F, B, dtype=torch.int32, device=dev)
+    ws = _workspace("a2a_pack", lib.ptrec_a2a_pack_workspace_bytes(B, F, G), dev)
+    a_out = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+    a_str = (ctypes.c_int64 * n)(*[o.stride(0) for o in outs])
+    a_dim = (ctypes.c_int32 * n)(*dims)
+    _lib.check(lib.ptrec_a2a_pack_by_owner_push(_ptr(ids), B, F, G, C, rank, _ptr(peer_ids), _ptr(peer_b), a_out, a_str,
+                                                a_dim, n, _ptr(ret_pos), _ptr(overflow), _ptr(ws), ws.numel(),
+                                                _stream(dev)), "ptrec_a2a_pack_by_owner_push")
+    return ret_pos
+
+
+def gather_push(table_ptrs, peer_outs, row_strides, out_strides, dims, recv_ids: torch.Tensor, recv_b: torch.Tensor,
+                shard_rows: torch.Tensor, F: int, G: int, C: int, err_flag: Optional[torch.Tensor] = None) -> None:
+    """Owner side of the push-mode forward: ``table_ptrs[k]`` int64 [F] device tensor of this rank's shard bases for
+    width k, ``peer_outs[k]`` int64 [G] device tensor of the ranks' output buffers of width k."""
+    lib = _lib.load()
+    _require_cuda(recv_ids, recv_b, shard_rows, err_flag, *table_ptrs, *peer_outs)
+    n = len(dims)
+    assert recv_ids.dtype == torch.int64 and recv_b.dtype == torch.int32 and recv_ids.numel() == F * G * C == recv_b.numel()
+    a_tab = (ctypes.c_void_p * n)(*[t.data_ptr() for t in table_ptrs])
+    a_out = (ctypes.c_void_p * n)(*[t.data_ptr() for t in peer_outs])
+    a_rs = (ctypes.c_int64 * n)(*row_strides)
+    a_os = (ctypes.c_int64 * n)(*out_strides)
+    a_dim = (ctypes.c_int32 * n)(*dims)
+    _lib.check(lib.ptrec_gather_push(a_tab, a_out, a_rs, a_os, a_dim, n, _ptr(recv_ids), _ptr(recv_b), _ptr(shard_rows),
+                                     F, G, C, _ptr(err_flag), _stream(recv_ids.device)), "ptrec_gather_push")
+
+
 def a2a_scatter_rows_peer(src: torch.Tensor, ret_pos: torch.Tensor, B: int, F: int, D: int, scale: float,
                           peer_dst: torch.Tensor, dst_row_stride: int, dst_col: int, C: int, G: int,
                           rank: int) -> None:
@@ -498,7 +537,7 @@ class PeerSync:
     enqueued before it on its current stream is complete and visible before anything any rank enqueues after it
     starts.  Every rank must issue the same sequence of calls per slot; slots are independent, so two streams may
     each run their own.  Graph-capturable."""
-    FENCE, IDS, GRADS, DENSE = 0, 1, 2, 3
+    FENCE, IDS, GRADS, DENSE, ROWS = 0, 1, 2, 3, 4
 
     def __init__(self, group, device):
         import torch.distributed as dist

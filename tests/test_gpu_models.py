@@ -274,10 +274,11 @@ def test_cuda_graph_train_step_equals_eager():
         m.train_step(_ctr_batch(rows, len(dcols), 256, seed=1))
 
 
-@pytest.mark.parametrize("peer", ["1", "0"], ids=["peer_memory", "all_to_all"])
+@pytest.mark.parametrize("peer", ["push", "1", "0"], ids=["push", "pull_peer_memory", "all_to_all"])
 def test_sharded_deepfm_matches_unsharded_on_two_gpus(peer):
-    """Row-wise sharded tables (exchange inside the kernels over NVLink peer memory, or NCCL all-to-all) + dense
-    allreduce == single-GPU model on the concatenated batch."""
+    """Row-wise sharded tables (owners push rows over NVLink; requesters pull from peer memory; NCCL all-to-all) + the
+    dense-gradient mean == single-GPU model on the concatenated batch; low-cardinality columns, a forced list overflow
+    (must be fatal) and the sharded checkpoint incl. optimizer state ride along (tests/dist_sharded_worker.py)."""
     import subprocess
     import sys
     if torch.cuda.device_count() < 2:
@@ -285,9 +286,10 @@ def test_sharded_deepfm_matches_unsharded_on_two_gpus(peer):
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29533" if peer == "1" else "29534",
+           "127.0.0.1", "--master-port", {"push": "29532", "1": "29533", "0": "29534"}[peer],
            os.path.join(root, "tests", "dist_sharded_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PTREC_PEER_GATHER=peer))
+    env = dict(os.environ, PTREC_EXCHANGE="push") if peer == "push" else dict(os.environ, PTREC_PEER_GATHER=peer)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert "DIST_SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
