@@ -489,11 +489,13 @@ int ptrec_a2a_scatter_rows(const float* src, int64_t src_row_stride, const int32
  *            never resets anything
  *   peer_dst [G] device array; peer_dst[o] = rank o's gradient buffer [G_src*F*C, dst_row_stride] float32; this rank
  *            writes row my_rank*F*C + (ret_pos mod F*C), columns [dst_col, dst_col + D)
- * ret_pos keeps the meaning above.  The caller fences (one small collective) between these stores and the owners'
- * reads, and between the owners' reads and the next step's stores. */
+ * ret_pos keeps the meaning above; slot_b (optional, [G*F*C] int32, local) receives its inverse: the sample b behind
+ * slot (o*F + f)*C + slot, -1 behind the last lookup of a list — what ptrec_a2a_scatter_rows_peer_ordered walks.  The
+ * caller puts a barrier (ptrec_peer_barrier) between these stores and the owners' reads, and between the owners' reads
+ * and the next step's stores. */
 int ptrec_a2a_pack_by_owner_peer(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C, int32_t my_rank,
-                                 int64_t* const* peer_ids, int32_t* ret_pos, int32_t* overflow, void* workspace,
-                                 size_t workspace_bytes, void* stream);
+                                 int64_t* const* peer_ids, int32_t* ret_pos, int32_t* slot_b, int32_t* overflow,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 int ptrec_a2a_scatter_rows_peer(const float* src, int64_t src_row_stride, const int32_t* ret_pos, int64_t B,
                                 int32_t F, int32_t D, float scale, float* const* peer_dst, int64_t dst_row_stride,
                                 int64_t dst_col, int32_t C, int32_t G, int32_t my_rank, void* stream);
@@ -514,8 +516,8 @@ int ptrec_a2a_scatter_rows_peer(const float* src, int64_t src_row_stride, const 
 int ptrec_a2a_pack_by_owner_push(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C, int32_t my_rank,
                                  int64_t* const* peer_ids, int32_t* const* peer_b, float* const* local_out,
                                  const int64_t* out_row_strides, const int32_t* dims, int32_t n_widths,
-                                 int32_t* ret_pos, int32_t* overflow, void* workspace, size_t workspace_bytes,
-                                 void* stream);
+                                 int32_t* ret_pos, int32_t* slot_b, int32_t* overflow, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 int ptrec_gather_push(const void* const* const* table_ptrs, float* const* const* peer_out, const int64_t* row_strides,
                       const int64_t* out_row_strides, const int32_t* dims, int32_t n_widths, const int64_t* recv_ids,
                       const int32_t* recv_b, const int64_t* shard_rows, int32_t F, int32_t G, int32_t C,
@@ -527,6 +529,13 @@ int ptrec_a2a_scatter_rows_peer_multi(const float* const* srcs, const int64_t* s
                                       const int64_t* dst_cols, int32_t n_widths, const int32_t* ret_pos, int64_t B,
                                       int32_t F, float scale, float* const* peer_dst, int64_t dst_row_stride,
                                       int32_t C, int32_t G, int32_t my_rank, void* stream);
+/* The same dispatch in DESTINATION order: one sub-warp per slot of this rank's lists (slot_b from the pack call names
+ * the sample), whole slots stored (dst_row_stride floats, pad lanes zero), so that the NVLink stores to one owner are
+ * long contiguous runs.  dst_cols[k] must be 4 * (float4 chunks of the widths before k). */
+int ptrec_a2a_scatter_rows_peer_ordered(const float* const* srcs, const int64_t* src_row_strides, const int32_t* dims,
+                                        const int64_t* dst_cols, int32_t n_widths, const int32_t* slot_b, int32_t F,
+                                        float scale, float* const* peer_dst, int64_t dst_row_stride, int32_t C,
+                                        int32_t G, int32_t my_rank, void* stream);
 
 #ifdef __cplusplus
 }

@@ -145,12 +145,14 @@ PROTOTYPES = {
     "ptrec_a2a_scatter_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p,
                                        c_int64, c_void_p]),
     "ptrec_a2a_pack_by_owner_peer": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p,
-                                             c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ptrec_a2a_scatter_rows_peer": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p,
                                             c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p]),
     "ptrec_a2a_pack_by_owner_push": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
-                                             c_size_t, c_void_p]),
+                                             c_void_p, c_size_t, c_void_p]),
+    "ptrec_a2a_scatter_rows_peer_ordered": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32,
+                                                    c_float, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p]),
     "ptrec_gather_push": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                   c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "ptrec_a2a_scatter_rows_peer_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64,

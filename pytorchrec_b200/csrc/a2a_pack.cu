@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kPackThreads)
 pack_scatter_kernel(const int64_t* __restrict__ ids, int64_t B, int F, int G, int tiles, int C,
                     const int* __restrict__ bases, int64_t* __restrict__ send_ids, int32_t* __restrict__ ret_pos,
                     int64_t* const* __restrict__ peer_ids, int32_t* const* __restrict__ peer_b, ZeroFill zf,
-                    int my_rank) {
+                    int32_t* __restrict__ slot_b, int my_rank) {
   constexpr int NW = kPackThreads / 32;
   __shared__ int s_cnt[NW][kMaxRanks];
   __shared__ int s_base[kMaxRanks];
@@ -119,6 +119,12 @@ pack_scatter_kernel(const int64_t* __restrict__ ids, int64_t B, int F, int G, in
       for (int slot = min(s_total[d], C) + (int)threadIdx.x; slot < C; slot += kPackThreads) list[slot] = -1;
     }
   }
+  if (slot_b != nullptr && tile == tiles - 1) {  // the local slot -> sample map is written in full as well
+    for (int d = 0; d < G; ++d) {
+      int32_t* list = slot_b + ((int64_t)d * F + f) * C;
+      for (int slot = min(s_total[d], C) + (int)threadIdx.x; slot < C; slot += kPackThreads) list[slot] = -1;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < kPackItems; ++i) {
     const int64_t b = beg + warp * (32 * kPackItems) + i * 32 + lane;
@@ -128,6 +134,7 @@ pack_scatter_kernel(const int64_t* __restrict__ ids, int64_t B, int F, int G, in
         const int slot = s_cnt[warp][dest[i]] + rank[i];
         if (slot < C) {
           pos = (int32_t)(((int64_t)dest[i] * F + f) * C + slot);
+          if (slot_b != nullptr) slot_b[pos] = (int32_t)b;  // inverse of ret_pos: the sample behind slot `pos`
           if (peer_ids != nullptr) {
             const int64_t at = ((int64_t)f * G + my_rank) * C + slot;
             s_peer[dest[i]][at] = id[i] / G;
@@ -222,6 +229,61 @@ scatter_rows_peer_multi_kernel(PeerWidths w, const int32_t* __restrict__ pos, in
     *reinterpret_cast<float4*>(d) = v;
   } else {
     for (int i = 0; i < 4 && c + i < D; ++i) d[i] = s[i] * scale;
+  }
+}
+
+// Same dispatch in DESTINATION order: one sub-warp per (owner, field, slot) of this rank's lists, `slot_b` (written by
+// the pack kernels) naming the sample behind the slot.  Neighbouring sub-warps store neighbouring slots of the same
+// owner, so the NVLink stores are long contiguous runs (whole slots, padding included) instead of isolated 64-byte
+// rows — scattered 16-byte pieces ran at ~250 GB/s (profiles/r2_kernels_step_n2_push_first.txt).
+template <int LPR>
+__global__ void __launch_bounds__(256)
+scatter_rows_peer_ordered_kernel(PeerWidths w, const int32_t* __restrict__ slot_b, int F, int C, int G, float scale,
+                                 float* const* __restrict__ peer_dst, int64_t dst_row_stride, int my_rank) {
+  const int lane = threadIdx.x % LPR;
+  const int64_t groups = (int64_t)gridDim.x * (256 / LPR);
+  const int64_t n_slots = (int64_t)G * F * C;
+  const int n_chunks = (int)(dst_row_stride / 4);  // the whole slot is written: the pad lanes store zeros
+  if (lane >= n_chunks) return;
+  int k = 0;
+  while (k + 1 < w.n && lane >= w.chunk0[k + 1]) ++k;
+  const bool pad = lane >= w.chunk0[w.n];
+  const int c = (lane - w.chunk0[k]) * 4;
+  const int D = w.dim[k];
+  for (int64_t s0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) / LPR; s0 < n_slots; s0 += groups * 4) {
+    float4 v[4];
+    float* dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t s = s0 + u * groups;
+      dst[u] = nullptr;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s < n_slots) {
+        const int b = slot_b[s];
+        if (b >= 0) {
+          const int owner = (int)(s / ((int64_t)F * C));
+          const int64_t rel = s - (int64_t)owner * F * C;  // f * C + slot
+          const int f = (int)(rel / C);
+          dst[u] = peer_dst[owner] + ((int64_t)my_rank * F * C + rel) * dst_row_stride + lane * 4;
+          if (!pad) {
+            const float* src = w.src[k] + (int64_t)b * w.stride[k] + (int64_t)f * D + c;
+            if (c + 3 < D && (D & 3) == 0) {
+              v[u] = *reinterpret_cast<const float4*>(src);
+            } else {
+              v[u].x = src[0];
+              if (c + 1 < D) v[u].y = src[1];
+              if (c + 2 < D) v[u].z = src[2];
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (dst[u] == nullptr) continue;
+      v[u].x *= scale; v[u].y *= scale; v[u].z *= scale; v[u].w *= scale;
+      *reinterpret_cast<float4*>(dst[u]) = v[u];
+    }
   }
 }
 
@@ -354,14 +416,74 @@ extern "C" int ptrec_gather_push(const void* const* const* table_ptrs, float* co
 #undef PTREC_PUSH
 }
 
+extern "C" int ptrec_a2a_scatter_rows_peer_ordered(const float* const* srcs, const int64_t* src_row_strides,
+                                                   const int32_t* dims, const int64_t* dst_cols, int32_t n_widths,
+                                                   const int32_t* slot_b, int32_t F, float scale,
+                                                   float* const* peer_dst, int64_t dst_row_stride, int32_t C, int32_t G,
+                                                   int32_t my_rank, void* stream) {
+  PTREC_CHECK_ARG(srcs && src_row_strides && dims && dst_cols && slot_b && peer_dst, PTREC_EINVAL,
+                  "a2a_scatter_rows_peer_ordered: null pointer");
+  PTREC_CHECK_ARG(n_widths >= 1 && n_widths <= kMaxWidths, PTREC_EINVAL, "a2a_scatter_rows_peer_ordered: 1..%d widths",
+                  kMaxWidths);
+  PTREC_CHECK_ARG(G >= 1 && G <= kMaxRanks && my_rank >= 0 && my_rank < G && C >= 1 && F >= 1, PTREC_EINVAL,
+                  "a2a_scatter_rows_peer_ordered: bad G=%d rank=%d C=%d", G, my_rank, C);
+  PTREC_CHECK_ARG(dst_row_stride % 4 == 0 && dst_row_stride <= 128, PTREC_EALIGN,
+                  "a2a_scatter_rows_peer_ordered: slot width must be a multiple of 4 floats, at most 128");
+  PeerWidths w;
+  w.n = n_widths;
+  int chunks = 0;
+  for (int k = 0; k < n_widths; ++k) {
+    PTREC_CHECK_ARG(srcs[k] && dims[k] >= 1 && dims[k] <= 128, PTREC_EINVAL, "a2a_scatter_rows_peer_ordered: width %d", k);
+    // the lanes of a slot cover its columns 4 by 4 in order: width k must start where width k-1's chunks end
+    PTREC_CHECK_ARG(dst_cols[k] == (int64_t)chunks * 4, PTREC_EINVAL,
+                    "a2a_scatter_rows_peer_ordered: widths must be packed at 16-byte boundaries in slot order");
+    const bool vec = (dims[k] & 3) == 0;
+    PTREC_CHECK_ARG(!vec || (((uintptr_t)srcs[k] & 15) == 0 && src_row_strides[k] % 4 == 0), PTREC_EALIGN,
+                    "a2a_scatter_rows_peer_ordered: width %d misaligned", k);
+    w.src[k] = srcs[k];
+    w.stride[k] = src_row_strides[k];
+    w.dim[k] = dims[k];
+    w.col[k] = (int32_t)dst_cols[k];
+    w.chunk0[k] = chunks;
+    chunks += (dims[k] + 3) / 4;
+  }
+  w.chunk0[n_widths] = chunks;
+  for (int k = n_widths; k < kMaxWidths; ++k) { w.src[k] = nullptr; w.stride[k] = 0; w.dim[k] = 0; w.col[k] = 0; }
+  for (int k = n_widths + 1; k <= kMaxWidths; ++k) w.chunk0[k] = chunks;
+  PTREC_CHECK_ARG((int64_t)chunks * 4 <= dst_row_stride, PTREC_EINVAL, "a2a_scatter_rows_peer_ordered: slot too narrow");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_slots = (int64_t)G * F * C;
+  const int lanes = (int)(dst_row_stride / 4);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#define PTREC_SCO(P)                                                                                          \
+  {                                                                                                           \
+    const int64_t want = ceil_div(n_slots * P, 256 * 4);                                                      \
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * 8));           \
+    scatter_rows_peer_ordered_kernel<P><<<grid, 256, 0, st>>>(w, slot_b, F, C, G, scale, peer_dst,            \
+                                                              dst_row_stride, my_rank);                       \
+    PTREC_LAUNCH_CHECK("scatter_rows_peer_ordered_kernel");                                                   \
+    return PTREC_OK;                                                                                          \
+  }
+  if (lanes <= 1) PTREC_SCO(1)
+  if (lanes <= 2) PTREC_SCO(2)
+  if (lanes <= 4) PTREC_SCO(4)
+  if (lanes <= 8) PTREC_SCO(8)
+  if (lanes <= 16) PTREC_SCO(16)
+  PTREC_SCO(32)
+#undef PTREC_SCO
+}
+
 extern "C" size_t ptrec_a2a_pack_workspace_bytes(int64_t B, int32_t F, int32_t G) {
   const int64_t tiles = ceil_div(B, kPackTile);
   return align_up((size_t)(F * tiles * G) * sizeof(int) + 16, 256);
 }
 
 static int pack_impl(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C, int64_t* send_ids,
-                     int64_t* const* peer_ids, int32_t* const* peer_b, const ZeroFill& zf, int32_t my_rank,
-                     int32_t* ret_pos, int32_t* overflow, void* workspace, size_t workspace_bytes, void* stream) {
+                     int64_t* const* peer_ids, int32_t* const* peer_b, const ZeroFill& zf, int32_t* slot_b,
+                     int32_t my_rank, int32_t* ret_pos, int32_t* overflow, void* workspace, size_t workspace_bytes,
+                     void* stream) {
   PTREC_CHECK_ARG(ids && (send_ids || peer_ids) && ret_pos && workspace, PTREC_EINVAL, "a2a_pack: null pointer");
   PTREC_CHECK_ARG(my_rank >= 0 && my_rank < G, PTREC_EINVAL, "a2a_pack: rank %d outside [0, %d)", my_rank, G);
   PTREC_CHECK_ARG(B >= 0 && F >= 1 && F <= 65535 && G >= 1 && G <= kMaxRanks && C >= 1, PTREC_EINVAL,
@@ -380,7 +502,7 @@ static int pack_impl(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_
   pack_scan_kernel<<<F, kMaxRanks, 0, st>>>(counts, G, tiles, C, overflow);
   PTREC_LAUNCH_CHECK("pack_scan_kernel");
   pack_scatter_kernel<<<grid, kPackThreads, 0, st>>>(ids, B, F, G, tiles, C, counts, send_ids, ret_pos, peer_ids,
-                                                     peer_b, zf, my_rank);
+                                                     peer_b, zf, slot_b, my_rank);
   PTREC_LAUNCH_CHECK("pack_scatter_kernel");
   return PTREC_OK;
 }
@@ -390,17 +512,17 @@ extern "C" int ptrec_a2a_pack_by_owner(const int64_t* ids, int64_t B, int32_t F,
                                        size_t workspace_bytes, void* stream) {
   PTREC_CHECK_ARG(send_ids, PTREC_EINVAL, "a2a_pack: null send_ids");
   ZeroFill zf{};
-  return pack_impl(ids, B, F, G, C, send_ids, nullptr, nullptr, zf, 0, ret_pos, overflow, workspace, workspace_bytes,
-                   stream);
+  return pack_impl(ids, B, F, G, C, send_ids, nullptr, nullptr, zf, nullptr, 0, ret_pos, overflow, workspace,
+                   workspace_bytes, stream);
 }
 
 extern "C" int ptrec_a2a_pack_by_owner_peer(const int64_t* ids, int64_t B, int32_t F, int32_t G, int32_t C,
                                             int32_t my_rank, int64_t* const* peer_ids, int32_t* ret_pos,
-                                            int32_t* overflow, void* workspace, size_t workspace_bytes,
-                                            void* stream) {
+                                            int32_t* slot_b, int32_t* overflow, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
   PTREC_CHECK_ARG(peer_ids, PTREC_EINVAL, "a2a_pack_peer: null peer pointer array");
   ZeroFill zf{};
-  return pack_impl(ids, B, F, G, C, nullptr, peer_ids, nullptr, zf, my_rank, ret_pos, overflow, workspace,
+  return pack_impl(ids, B, F, G, C, nullptr, peer_ids, nullptr, zf, slot_b, my_rank, ret_pos, overflow, workspace,
                    workspace_bytes, stream);
 }
 
@@ -408,7 +530,8 @@ extern "C" int ptrec_a2a_pack_by_owner_push(const int64_t* ids, int64_t B, int32
                                             int32_t my_rank, int64_t* const* peer_ids, int32_t* const* peer_b,
                                             float* const* local_out, const int64_t* out_row_strides,
                                             const int32_t* dims, int32_t n_widths, int32_t* ret_pos,
-                                            int32_t* overflow, void* workspace, size_t workspace_bytes, void* stream) {
+                                            int32_t* slot_b, int32_t* overflow, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
   PTREC_CHECK_ARG(peer_ids && peer_b && local_out && out_row_strides && dims, PTREC_EINVAL,
                   "a2a_pack_push: null pointer");
   PTREC_CHECK_ARG(n_widths >= 1 && n_widths <= 4, PTREC_EINVAL, "a2a_pack_push: 1..4 widths");
@@ -419,7 +542,7 @@ extern "C" int ptrec_a2a_pack_by_owner_push(const int64_t* ids, int64_t B, int32
     zf.stride[k] = out_row_strides[k];
     zf.dim[k] = dims[k];
   }
-  return pack_impl(ids, B, F, G, C, nullptr, peer_ids, peer_b, zf, my_rank, ret_pos, overflow, workspace,
+  return pack_impl(ids, B, F, G, C, nullptr, peer_ids, peer_b, zf, slot_b, my_rank, ret_pos, overflow, workspace,
                    workspace_bytes, stream);
 }
 

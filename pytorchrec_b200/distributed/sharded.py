@@ -194,7 +194,8 @@ class _PeerLookup(torch.autograd.Function):
         Runs on whatever stream is current.  Returns (ret_pos, sort result, capacity)."""
         C = mod.capacity(B)
         pb = mod.peer_buffers(C, dev)
-        ret_pos = ops.a2a_pack_by_owner_peer(ids, F, B, mod.world, C, mod.rank, pb["peer_ids"], mod.overflow_flag(dev))
+        ret_pos = ops.a2a_pack_by_owner_peer(ids, F, B, mod.world, C, mod.rank, pb["peer_ids"], mod.overflow_flag(dev),
+                                             slot_b=pb["slot_b"] if mod.ordered_scatter else None)
         mod.publish_overflow(dev)
         mod.barrier(ops.PeerSync.IDS, dev)  # every rank's lists have landed in every owner's buffer
         eg = mod.egroups[0]                 # same ids and the same shard heights for every width: one sort
@@ -252,8 +253,7 @@ class _PeerLookup(torch.autograd.Function):
             g = grads[k]
             g = torch.zeros(B, F * D, device=dev) if g is None else g.reshape(B, F * D)
             gs.append(g if g.is_contiguous() else g.contiguous())
-        ops.a2a_scatter_rows_peer_multi(gs, mod.dims, mod.col_of, ret_pos, B, F, mod.grad_scale, pb["peer_g"], S, C, G,
-                                        mod.rank)
+        mod.scatter_grads(gs, ret_pos, pb, B, F, C)
         mod.barrier(ops.PeerSync.GRADS, dev)  # every rank's gradient rows have landed in every owner's buffer
         recv_g = pb["recv_g"]
         for k, D in enumerate(mod.dims):
@@ -282,7 +282,7 @@ class _PushLookup(torch.autograd.Function):
         pb = mod.peer_buffers(C, dev)
         po = mod.push_outputs(B, dev)
         ret_pos = ops.a2a_pack_by_owner_push(ids, F, B, G, C, mod.rank, pb["peer_ids"], pb["peer_b"], po["outs"], mod.dims,
-                                             mod.overflow_flag(dev))
+                                             mod.overflow_flag(dev), slot_b=pb["slot_b"] if mod.ordered_scatter else None)
         mod.publish_overflow(dev)
         mod.barrier(ops.PeerSync.IDS, dev)   # every rank's lists have landed in every owner's buffers
         n_t = len(mod.columns)
@@ -321,8 +321,7 @@ class _PushLookup(torch.autograd.Function):
             g = grads[k]
             g = torch.zeros(B, F * D, device=dev) if g is None else g.reshape(B, F * D)
             gs.append(g if g.is_contiguous() else g.contiguous())
-        ops.a2a_scatter_rows_peer_multi(gs, mod.dims, mod.col_of, ret_pos, B, F, mod.grad_scale, pb["peer_g"], S, C, G,
-                                        mod.rank)
+        mod.scatter_grads(gs, ret_pos, pb, B, F, C)
         mod.barrier(ops.PeerSync.GRADS, dev)  # every rank's gradient rows have landed in every owner's buffer
         srt, ev = ctx.early
         torch.cuda.current_stream(dev).wait_event(ev)  # join the early sort
@@ -427,7 +426,17 @@ class RowWiseShardedEmbedding(nn.Module):
         elif mode == "auto" and legacy in ("0", "1"):
             mode = "pull" if legacy == "1" else "a2a"
         elif mode == "auto":
-            mode = "push" if nccl and os.environ.get("PTREC_PEER_SYNC", "1") != "0" else "a2a"
+            # Small shards: PULL (no barrier on the forward's critical path; measured at cfg2, 2 x B200: 0.845 ms / step
+            # against 0.876 for push).  Large shards: PUSH — random row reads over 7 x 83 GB of peer mappings ran
+            # 10.1 ms / step at cfg5 on 8 GPUs (round 1), while push keeps every random access local (cfg5, 2 GPUs:
+            # 4.71 ms against 5.74 for NCCL all-to-all).  The estimate uses the rank-independent shard height so that
+            # every rank takes the same decision.
+            cap_gb = float(os.environ.get("PTREC_PEER_MAX_GB", "16"))
+            per_gpu = sum((c.category_num + self.world - 1) // self.world for c in self.columns) * sum(self.dims) * 8
+            if nccl and os.environ.get("PTREC_PEER_SYNC", "1") != "0":
+                mode = "pull" if per_gpu <= cap_gb * 2 ** 30 else "push"
+            else:
+                mode = "a2a"
         if mode not in ("push", "pull", "a2a"):
             raise ValueError(f"PTREC_EXCHANGE must be push, pull, a2a or auto, got {mode!r}")
         if mode != "a2a" and not nccl:
@@ -444,6 +453,7 @@ class RowWiseShardedEmbedding(nn.Module):
         if self.exchange == "push" and not self.use_peer_sync:
             raise RuntimeError("the push exchange orders its stores with the barrier kernels: PTREC_PEER_SYNC=0 is not compatible")
         self._push_out: Dict[tuple, dict] = {}
+        self.ordered_scatter = os.environ.get("PTREC_ORDERED_SCATTER", "1") != "0" and self.slot_width <= 128
         self._sync: Optional[ops.PeerSync] = None
         self._reducer: Optional[_DenseReducer] = None
         self._dirty = False                        # a table update / buffer reset not yet ordered by a collective
@@ -572,12 +582,23 @@ class RowWiseShardedEmbedding(nn.Module):
             recv_g.zero_()
             h_ids, h_g = symm.rendezvous(recv_ids, group), symm.rendezvous(recv_g, group)
             b = {"recv_ids": recv_ids, "recv_g": recv_g, "recv_b": recv_b, "handles": (h_ids, h_g, h_b),
+                 "slot_b": torch.full((G * F * C,), -1, dtype=torch.int32, device=device),  # local: sample behind each slot
                  "peer_b": torch.tensor([int(p) for p in h_b.buffer_ptrs], dtype=torch.int64).to(device),
                  "peer_ids": torch.tensor([int(p) for p in h_ids.buffer_ptrs], dtype=torch.int64).to(device),
                  "peer_g": torch.tensor([int(p) for p in h_g.buffer_ptrs], dtype=torch.int64).to(device)}
             self._peer_bufs[key] = b
             self.sync_peers()
         return b
+
+    def scatter_grads(self, gs, ret_pos: Tensor, pb: dict, B: int, F: int, C: int) -> None:
+        """Gradient rows of every width -> the owners' receive buffers (NVLink stores): in destination order (long
+        contiguous runs; default) or in batch order (PTREC_ORDERED_SCATTER=0)."""
+        if self.ordered_scatter:
+            ops.a2a_scatter_rows_peer_ordered(gs, self.dims, self.col_of, pb["slot_b"], F, self.grad_scale, pb["peer_g"],
+                                              self.slot_width, C, self.world, self.rank)
+        else:
+            ops.a2a_scatter_rows_peer_multi(gs, self.dims, self.col_of, ret_pos, B, F, self.grad_scale, pb["peer_g"],
+                                            self.slot_width, C, self.world, self.rank)
 
     def push_outputs(self, B: int, device) -> dict:
         """This rank's lookup outputs, one [B, F * D_k] buffer per width in symmetric memory (the owners store rows

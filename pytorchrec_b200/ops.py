@@ -447,23 +447,25 @@ def a2a_scatter_rows(src: torch.Tensor, ret_pos: torch.Tensor, B: int, F: int, D
 
 
 def a2a_pack_by_owner_peer(ids: torch.Tensor, F: int, B: int, G: int, C: int, rank: int, peer_ids: torch.Tensor,
-                           overflow: torch.Tensor) -> torch.Tensor:
+                           overflow: torch.Tensor, slot_b: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ids [F, B] -> ret_pos [F, B]; the lists are stored into the owners' id buffers (``peer_ids`` int64 [G] device
-    tensor of their addresses, each [F, G, C] int64)."""
+    tensor of their addresses, each [F, G, C] int64).  ``slot_b`` (int32 [G*F*C], optional) receives the inverse of
+    ret_pos (the sample behind each slot, -1 for empty slots)."""
     lib = _lib.load()
     _require_cuda(ids, overflow, peer_ids)
     dev = ids.device
     assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.numel() == F * B and peer_ids.numel() == G
     ret_pos = torch.empty(F, B, dtype=torch.int32, device=dev)
     ws = _workspace("a2a_pack", lib.ptrec_a2a_pack_workspace_bytes(B, F, G), dev)
-    _lib.check(lib.ptrec_a2a_pack_by_owner_peer(_ptr(ids), B, F, G, C, rank, _ptr(peer_ids), _ptr(ret_pos),
+    _lib.check(lib.ptrec_a2a_pack_by_owner_peer(_ptr(ids), B, F, G, C, rank, _ptr(peer_ids), _ptr(ret_pos), _ptr(slot_b),
                                                 _ptr(overflow), _ptr(ws), ws.numel(), _stream(dev)),
                "ptrec_a2a_pack_by_owner_peer")
     return ret_pos
 
 
 def a2a_pack_by_owner_push(ids: torch.Tensor, F: int, B: int, G: int, C: int, rank: int, peer_ids: torch.Tensor,
-                           peer_b: torch.Tensor, outs, dims, overflow: torch.Tensor) -> torch.Tensor:
+                           peer_b: torch.Tensor, outs, dims, overflow: torch.Tensor,
+                           slot_b: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Push-mode pack: ids [F, B] -> ret_pos [F, B]; local rows go to the owners' id lists (``peer_ids`` [G] addresses
     of int64 [F, G, C]) and the sample index of each lookup to their ``peer_b`` lists (int32, same indexing); rows
     of the local outputs ``outs[k]`` [B, F*dims[k]] that no owner will write are zeroed."""
@@ -479,7 +481,7 @@ def a2a_pack_by_owner_push(ids: torch.Tensor, F: int, B: int, G: int, C: int, ra
     a_str = (ctypes.c_int64 * n)(*[o.stride(0) for o in outs])
     a_dim = (ctypes.c_int32 * n)(*dims)
     _lib.check(lib.ptrec_a2a_pack_by_owner_push(_ptr(ids), B, F, G, C, rank, _ptr(peer_ids), _ptr(peer_b), a_out, a_str,
-                                                a_dim, n, _ptr(ret_pos), _ptr(overflow), _ptr(ws), ws.numel(),
+                                                a_dim, n, _ptr(ret_pos), _ptr(slot_b), _ptr(overflow), _ptr(ws), ws.numel(),
                                                 _stream(dev)), "ptrec_a2a_pack_by_owner_push")
     return ret_pos
 
@@ -526,6 +528,24 @@ def a2a_scatter_rows_peer_multi(srcs, dims, cols, ret_pos: torch.Tensor, B: int,
     _lib.check(lib.ptrec_a2a_scatter_rows_peer_multi(a_src, a_str, a_dim, a_col, n, _ptr(ret_pos), B, F, float(scale),
                                                      _ptr(peer_dst), dst_row_stride, C, G, rank,
                                                      _stream(ret_pos.device)), "ptrec_a2a_scatter_rows_peer_multi")
+
+
+def a2a_scatter_rows_peer_ordered(srcs, dims, cols, slot_b: torch.Tensor, F: int, scale: float, peer_dst: torch.Tensor,
+                                  dst_row_stride: int, C: int, G: int, rank: int) -> None:
+    """``a2a_scatter_rows_peer_multi`` in destination order (``slot_b`` from the pack call): whole slots, contiguous
+    NVLink stores."""
+    lib = _lib.load()
+    _require_cuda(slot_b, peer_dst, *srcs)
+    n = len(srcs)
+    assert n == len(dims) == len(cols) and all(s.dtype == torch.float32 and s.stride(-1) == 1 for s in srcs)
+    assert slot_b.dtype == torch.int32 and slot_b.numel() == G * F * C
+    a_src = (ctypes.c_void_p * n)(*[s.data_ptr() for s in srcs])
+    a_str = (ctypes.c_int64 * n)(*[s.stride(0) for s in srcs])
+    a_dim = (ctypes.c_int32 * n)(*dims)
+    a_col = (ctypes.c_int64 * n)(*cols)
+    _lib.check(lib.ptrec_a2a_scatter_rows_peer_ordered(a_src, a_str, a_dim, a_col, n, _ptr(slot_b), F, float(scale),
+                                                       _ptr(peer_dst), dst_row_stride, C, G, rank,
+                                                       _stream(slot_b.device)), "ptrec_a2a_scatter_rows_peer_ordered")
 
 
 # ----------------------------------------------------------------------------------------------

@@ -38,7 +38,8 @@ def low_cardinality_and_overflow(rank, world, dev):
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
         shard = ShardedDeepFM(scols, dcols, lab, D, [32, 16], random_seed=4)
-    assert any("fewer categories" in str(x.message) for x in w)
+    if world > 2:  # at 2 ranks a one-category column costs no more than any other (owner share 1 vs 1/2 * 2)
+        assert any("fewer categories" in str(x.message) for x in w)
     assert shard.sharded.capacity(B) == (B + 15) // 16 * 16  # category_num 1: one owner takes the whole batch
     shard.load_full_state_dict(full.state_dict())
     full.compile(SparseAdagrad(full.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)

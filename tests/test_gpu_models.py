@@ -351,19 +351,82 @@ def test_peer_dispatch_kernels_equal_all_to_all_plan():
         # every width in one launch (DeepFM: D and 1) leaves the same bytes as one launch per width
         multi = [torch.zeros(G * F * C, S, device=DEV) for _ in range(G)]
         single = [torch.zeros(G * F * C, S, device=DEV) for _ in range(G)]
+        ordered = [torch.zeros(G * F * C, S, device=DEV) for _ in range(G)]
         pm = torch.tensor([t.data_ptr() for t in multi], dtype=torch.int64).to(DEV)
         ps = torch.tensor([t.data_ptr() for t in single], dtype=torch.int64).to(DEV)
+        po = torch.tensor([t.data_ptr() for t in ordered], dtype=torch.int64).to(DEV)
         for r in range(G):
             gen = torch.Generator().manual_seed(200 + r)
             ids = torch.stack([torch.randint(-1, rows, (B,), generator=gen) for _ in range(F)]).to(DEV)
             g0, g1 = torch.randn(B, F * D, generator=gen).to(DEV), torch.randn(B, F, generator=gen).to(DEV)
             scratch = torch.tensor([t.data_ptr() for t in own_ids], dtype=torch.int64).to(DEV)
-            ret_pos = ops.a2a_pack_by_owner_peer(ids, F, B, G, C, r, scratch, torch.zeros(1, dtype=torch.int32, device=DEV))
+            slot_b = torch.full((G * F * C,), 12345, dtype=torch.int32, device=DEV)
+            ret_pos = ops.a2a_pack_by_owner_peer(ids, F, B, G, C, r, scratch, torch.zeros(1, dtype=torch.int32, device=DEV),
+                                                 slot_b=slot_b)
+            # slot_b is the inverse of ret_pos, -1 behind the last lookup of every list
+            rp, sb = ret_pos.cpu(), slot_b.cpu()
+            want_sb = torch.full_like(sb, -1)
+            for f in range(F):
+                ok = rp[f] >= 0
+                want_sb[rp[f][ok].long()] = torch.arange(B, dtype=torch.int32)[ok]
+            assert torch.equal(sb, want_sb)
             ops.a2a_scatter_rows_peer_multi([g0, g1], [D, 1], [0, 16], ret_pos, B, F, 0.5, pm, S, C, G, r)
             ops.a2a_scatter_rows_peer(g0, ret_pos, B, F, D, 0.5, ps, S, 0, C, G, r)
             ops.a2a_scatter_rows_peer(g1, ret_pos, B, F, 1, 0.5, ps, S, 16, C, G, r)
+            if D == 16:  # the ordered kernel wants the widths packed at 16-byte boundaries in slot order
+                ops.a2a_scatter_rows_peer_ordered([g0, g1], [D, 1], [0, 16], slot_b, F, 0.5, po, S, C, G, r)
         for o in range(G):
             assert torch.equal(multi[o], single[o])
+            if D == 16:
+                assert torch.equal(ordered[o], single[o])  # destination order, whole slots (pad columns stay zero)
+
+
+@pytest.mark.parametrize("F,B,G,dims", [(3, 100, 2, [16, 1]), (26, 1031, 8, [16, 1]), (5, 2048, 4, [64, 1]), (4, 300, 3, [8])])
+def test_push_exchange_kernels_deliver_the_gathered_rows(F, B, G, dims):
+    """Push-mode forward on G virtual ranks of one device: pack (ids + sample index into the owners' lists) then every
+    owner's gather_push leave in each requester's outputs exactly table[id] (zeros for negative ids) — bit-exact, the
+    values are copied."""
+    from pytorchrec_b200 import ops
+    rows = [997, 5, 4099, 64, 31][:F] + [257] * max(0, F - 5)
+    C = (B + 15) // 16 * 16  # cannot overflow: a 5-row table sends everything to few owners
+    gen = torch.Generator().manual_seed(7)
+    full = [[torch.randn(rows[f], d, generator=gen) for f in range(F)] for d in dims]
+    # owner o holds rows o::G of every table, in a row-strided buffer (as the interleaved optimizer layout)
+    shards = [[[torch.zeros(max((rows[f] - o + G - 1) // G, 1), 2 * d + 4, device=DEV) for f in range(F)] for d in dims]
+              for o in range(G)]
+    for o in range(G):
+        for k, d in enumerate(dims):
+            for f in range(F):
+                part = full[k][f][o::G]
+                shards[o][k][f][:part.shape[0], :d] = part.to(DEV)
+    own_ids = [torch.full((F * G * C,), -1, dtype=torch.int64, device=DEV) for _ in range(G)]
+    own_b = [torch.zeros(F * G * C, dtype=torch.int32, device=DEV) for _ in range(G)]
+    peer_ids = torch.tensor([t.data_ptr() for t in own_ids], dtype=torch.int64).to(DEV)
+    peer_b = torch.tensor([t.data_ptr() for t in own_b], dtype=torch.int64).to(DEV)
+    outs = [[torch.full((B, F * d), 7.0, device=DEV) for d in dims] for _ in range(G)]
+    peer_outs = [torch.tensor([outs[r][k].data_ptr() for r in range(G)], dtype=torch.int64).to(DEV) for k in range(len(dims))]
+    all_ids = []
+    for r in range(G):
+        ids = torch.stack([torch.randint(-1, rows[f], (B,), generator=gen) for f in range(F)])
+        all_ids.append(ids)
+        ovf = torch.zeros(1, dtype=torch.int32, device=DEV)
+        ops.a2a_pack_by_owner_push(ids.to(DEV), F, B, G, C, r, peer_ids, peer_b, outs[r], dims, ovf)
+        assert ovf.item() == 0
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for o in range(G):
+        tabs = [torch.tensor([shards[o][k][f].data_ptr() for f in range(F)], dtype=torch.int64).to(DEV) for k in range(len(dims))]
+        shard_rows = torch.tensor([(rows[f] - o + G - 1) // G if rows[f] > o else 0 for f in range(F)], dtype=torch.int64).to(DEV)
+        ops.gather_push(tabs, peer_outs, [2 * d + 4 for d in dims], [F * d for d in dims], dims, own_ids[o], own_b[o],
+                        shard_rows, F, G, C, err_flag=err)
+    assert err.item() == 0
+    for r in range(G):
+        for k, d in enumerate(dims):
+            got = outs[r][k].cpu().view(B, F, d)
+            for f in range(F):
+                idf = all_ids[r][f]
+                want = torch.zeros(B, d)
+                want[idf >= 0] = full[k][f][idf[idf >= 0]]
+                assert torch.equal(got[:, f], want), (r, k, f)
 
 
 @pytest.mark.parametrize("G,D,stride_mult", [(2, 16, 1), (8, 16, 2), (4, 1, 1), (3, 64, 2)])
