@@ -216,11 +216,6 @@ int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* state1_ptrs,
                               int64_t grad_row_stride, const float* bag_scale,
                               const ptrec_optim_args* opt_host, void* workspace,
                               size_t workspace_bytes, void* stream);
-/* Thread mapping of the fused Adagrad update: 0 = one sub-warp of D/4 lanes per row, 4 rows in flight, metadata
- * prefetched in registers (v1); 1..3 = 2*D/4 lanes per row (weight half | state half: whole-line loads and stores of
- * the interleaved row), no register prefetch, {2 rows x 8 CTAs/SM, 4 x 6, 4 x 4}.  Identical arithmetic and order. */
-void ptrec_set_update_variant(int32_t variant);
-int32_t ptrec_update_variant(void);
 /* the four named entry points of SURVEY.md §8b: same arguments as ptrec_embedding_bwd_fused; each checks
  * opt_host->kind and forwards */
 #define PTREC_BWD_FUSED_ARGS                                                                                   \
@@ -301,6 +296,24 @@ int ptrec_dcn_cross_dgrad(const void* g_u, const void* weight_t, const void* g_o
 size_t ptrec_dcn_cross_wgrad_workspace_bytes(int64_t B, int32_t d);
 int ptrec_dcn_cross_wgrad(const void* g_u, const void* x_l, int64_t B, int32_t d, int64_t ld, float* grad_w,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Element-wise companions of the cross GEMMs (csrc/dcn_glue.cu), one launch each; dp = d rounded up to 8; every bf16
+ * [B, dp] operand is dense (row pitch dp) and 16-byte aligned.
+ *   prep_weight   W fp32 [d, d], b fp32 [d] -> w16 bf16 [dp, dp], w16t = its transpose, bias_pad fp32 [dp] (zero padded)
+ *   pack_input    x fp32 [B, d] (pitch ldx) -> out bf16 [B, dp] (zero padded);   unpack: the inverse into fp32 [B, d]
+ *   bwd_init      g fp32 [B, d] (pitch ldg) -> g_out = bf16(g) padded, g_u = g_out * x0
+ *   bwd_layer     g_x0 fp32 [B, dp] (+)= g_out * u;  grad_bias fp32 [d] = column sums of g_u (fixed order)
+ *   bwd_final     out fp32 [B, d] = g_x0 + g_out */
+int ptrec_dcn_prep_weight(const float* W, const float* b, int32_t d, int32_t dp, void* w16, void* w16t, float* bias_pad,
+                          void* stream);
+int ptrec_dcn_pack_input(const float* x, int64_t ldx, int64_t B, int32_t d, int32_t dp, void* out, void* stream);
+int ptrec_dcn_unpack(const void* x, int64_t B, int32_t d, int32_t dp, float* out, void* stream);
+int ptrec_dcn_bwd_init(const float* g, int64_t ldg, const void* x0, int64_t B, int32_t d, int32_t dp, void* g_out,
+                       void* g_u, void* stream);
+size_t ptrec_dcn_bwd_layer_workspace_bytes(int64_t B, int32_t dp);
+int ptrec_dcn_bwd_layer(const void* g_out, const void* u, const void* g_u, int64_t B, int32_t d, int32_t dp, float* g_x0,
+                        int32_t accumulate, float* grad_bias, void* workspace, size_t workspace_bytes, void* stream);
+int ptrec_dcn_bwd_final(const float* g_x0, const void* g_out, int64_t B, int32_t d, int32_t dp, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K8 the FM head: first-order sum + second-order interaction + dense-feature linear term + bias in one pass, and

@@ -80,8 +80,6 @@ PROTOTYPES = {
     "ptrec_smem_sort_enabled": (c_int32, []),
     "ptrec_set_one_sweep_sort": (None, [c_int32]),
     "ptrec_one_sweep_sort_enabled": (c_int32, []),
-    "ptrec_set_update_variant": (None, [c_int32]),
-    "ptrec_update_variant": (c_int32, []),
     "ptrec_sort_dedup_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "ptrec_sort_dedup": (c_int, [_FD, _FD, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p,
                                  c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -174,6 +172,14 @@ PROTOTYPES = {
     "ptrec_dcn_cross_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "ptrec_dcn_cross_wgrad": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_size_t,
                                       c_void_p]),
+    "ptrec_dcn_prep_weight": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ptrec_dcn_pack_input": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "ptrec_dcn_unpack": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "ptrec_dcn_bwd_init": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "ptrec_dcn_bwd_layer_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "ptrec_dcn_bwd_layer": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_void_p,
+                                    c_void_p, c_size_t, c_void_p]),
+    "ptrec_dcn_bwd_final": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "ptrec_fm2_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "ptrec_fm2_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
                               c_void_p, c_int64, c_void_p]),
@@ -206,8 +212,6 @@ def load():
         raise RuntimeError(f"libptrec_b200.so ABI {ver} != binding ABI {ABI_VERSION}: rebuild")
     if os.environ.get("PTREC_ONE_SWEEP"):     # K2a: one-sweep radix sort on / off (A/B measurements)
         lib.ptrec_set_one_sweep_sort(int(os.environ["PTREC_ONE_SWEEP"]))
-    if os.environ.get("PTREC_UPDATE_VARIANT"):  # K2b: thread mapping of the fused Adagrad update
-        lib.ptrec_set_update_variant(int(os.environ["PTREC_UPDATE_VARIANT"]))
     if os.environ.get("PTREC_TC_BN"):  # K6 fp16 x 2 pair-tile width, 128 or 256 (A/B measurements)
         lib.ptrec_tc_set_bn(int(os.environ["PTREC_TC_BN"]))
     _lib = lib

@@ -272,19 +272,39 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int K, 
   }
 }
 
-// [R, C] bf16 (pitch ld_in) -> [C, R] bf16 (pitch ld_out), 32x32 tiles through shared memory
-__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld_in, int R, int C,
-                                      __nv_bfloat16* __restrict__ out, int64_t ld_out) {
-  __shared__ __nv_bfloat16 tile[32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < C) ? in[(int64_t)r * ld_in + c] : __float2bfloat16(0.f);
+// [R, C] bf16 (pitch ld_in) -> [C, R] bf16 (pitch ld_out), 64x64 tiles through shared memory, 4-byte (bf16 x 2)
+// global accesses on both sides: a warp reads 128 contiguous bytes of an input row and writes 128 contiguous bytes of an
+// output row (the 32x32 / 2-byte version moved 64 B per warp access and ran at 28 % of the HBM rate: 60 us per
+// [32768, 848] operand, profiles/r2_step_kernels_dcn_before.txt).  ld_in, ld_out even; R, C arbitrary.
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld_in, int R, int C,
+                      __nv_bfloat16* __restrict__ out, int64_t ld_out) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;  // 8 warps
+  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  for (int i = wy; i < 64; i += 8) {
+    const int r = r0 + i, c = c0 + 2 * lane;
+    __nv_bfloat162 v = __halves2bfloat162(zero, zero);
+    if (r < R) {
+      if (c + 1 < C) {
+        v = *reinterpret_cast<const __nv_bfloat162*>(in + (int64_t)r * ld_in + c);
+      } else if (c < C) {
+        v = __halves2bfloat162(in[(int64_t)r * ld_in + c], zero);
+      }
+    }
+    *reinterpret_cast<__nv_bfloat162*>(&tile[i][2 * lane]) = v;
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (c < C && r < R) out[(int64_t)c * ld_out + r] = tile[threadIdx.x][i];
+  for (int i = wy; i < 64; i += 8) {
+    const int c = c0 + i, r = r0 + 2 * lane;  // output row c, output columns r, r + 1
+    if (c >= C) continue;
+    const __nv_bfloat162 v = __halves2bfloat162(tile[2 * lane][i], tile[2 * lane + 1][i]);
+    if (r + 1 < R) {
+      *reinterpret_cast<__nv_bfloat162*>(out + (int64_t)c * ld_out + r) = v;
+    } else if (r < R) {
+      out[(int64_t)c * ld_out + r] = v.x;
+    }
   }
 }
 
@@ -419,7 +439,7 @@ extern "C" int ptrec_dcn_cross_wgrad(const void* g_u, const void* x_l, int64_t B
   __nv_bfloat16* gt = reinterpret_cast<__nv_bfloat16*>(workspace);
   __nv_bfloat16* xt = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(workspace) +
                                                        align_up((size_t)d * ldt * 2, 256));
-  dim3 tb(32, 8), tg((unsigned)ceil_div(d, 32), (unsigned)ceil_div(B, 32));
+  dim3 tb(256), tg((unsigned)ceil_div(d, 64), (unsigned)ceil_div(B, 64));
   transpose_bf16_kernel<<<tg, tb, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g_u), ld, (int)B, d, gt, ldt);
   PTREC_LAUNCH_CHECK("transpose_bf16_kernel");
   transpose_bf16_kernel<<<tg, tb, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x_l), ld, (int)B, d, xt, ldt);

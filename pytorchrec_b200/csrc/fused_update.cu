@@ -15,7 +15,20 @@ namespace ptrec {
 constexpr int kUpdThreads = 128;
 constexpr int kLongThreads = 256;
 constexpr int kLongSeg = 32;
+constexpr int kLongChunk = 2048;  // slots one CTA reduces; longer runs are split over several CTAs (below)
 constexpr int kOptNone = -1;  // segment-sum only
+
+// Scratch of the long-segment path (in the caller's workspace).  Runs of more than kLongSeg slots are queued here by
+// the main kernel; one 64-bit atomic hands out BOTH the queue position (high word) and the first partial-sum row of
+// the run (low word), so the two stay monotone together.  Runs longer than kLongChunk (a padding id in every history
+// of a DIN batch is one run of ~4e5 slots; one CTA walking it alone took 2.2 ms) are reduced chunk by chunk by many
+// CTAs into `partial`, and the run's owner adds the chunks in order: the summation order is fixed, no fp atomics.
+struct LongWs {
+  unsigned long long* counter;  // (runs queued << 32) | partial rows handed out
+  int32_t* list;                // [cap] segment index of each queued run
+  int32_t* chunk_base;          // [cap] first partial row of the run (only runs longer than kLongChunk own rows)
+  float* partial;               // [partial rows][D]
+};
 
 struct OptParams {
   int64_t row_stride;  // floats between consecutive rows of a table AND of its element-wise state
@@ -176,8 +189,7 @@ fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restric
                     const uint32_t* __restrict__ sorted_keys, const int32_t* __restrict__ perm,
                     const int32_t* __restrict__ seg_start, const ptrec_segment_meta* __restrict__ seg_meta,
                     const int32_t* __restrict__ n_seg_ptr, const float* __restrict__ grad_out,
-                    int64_t stride, const float* __restrict__ bag_scale, OptParams op,
-                    int* __restrict__ long_count, int32_t* __restrict__ long_list,
+                    int64_t stride, const float* __restrict__ bag_scale, OptParams op, LongWs lw,
                     float* __restrict__ row_grad) {
   __shared__ SlotMap s_map;
   build_slot_map(&s_map, feats, F, T, B);
@@ -232,7 +244,13 @@ fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restric
       const int u = (r * SEGS + q) * NSG + sg;
       const bool masked = key[q] == kMaskedKey;
       const bool is_long = live[q] && !masked && (end[q] - start[q]) > kLongSeg && OPT != kOptNone;
-      if (is_long && lane == 0) long_list[atomicAdd(long_count, 1)] = u;
+      if (is_long && lane == 0) {
+        const int len = end[q] - start[q];
+        const unsigned nch = len > kLongChunk ? (unsigned)((len + kLongChunk - 1) / kLongChunk) : 0u;
+        const unsigned long long old = atomicAdd(lw.counter, (1ull << 32) | nch);
+        lw.list[old >> 32] = u;
+        lw.chunk_base[old >> 32] = (int32_t)(old & 0xffffffffu);
+      }
       work[q] = live[q] && !masked && !is_long;
       wrow[q] = s1[q] = s2[q] = nullptr;
       st[q].clear();
@@ -278,105 +296,80 @@ fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restric
   }
 }
 
-// ---- Adagrad, v2 thread mapping ---------------------------------------------------------------------------------
-// 2*LPR lanes own one unique row: lanes [0, LPR) its weight slice, lanes [LPR, 2*LPR) the matching slice of the
-// Adagrad sum.  With the interleaved layout (state = weight + D, row_stride = 2*D) one 128-bit load per lane reads
-// the row's whole 2*D*4-byte bundle as ONE contiguous request (a full 128-byte line at D = 16) and one 128-bit
-// store per lane writes it back as a full line; v1 issues two half-line loads and two half-line stores per row.
-// Both halves load the (same) gradient slice — a broadcast inside the load instruction — exchange w / sum with one
-// shuffle per float and compute the update redundantly; each stores its own half.  No metadata is carried across
-// rounds (v1 prefetches the next round's 6 words per segment into registers): the kernel stays under
-// 65536 / (128 * MINB) registers so that MINB CTAs are resident per SM and the latency of a round is hidden by other
-// warps instead of by registers.  Same arithmetic and the same (sorted = batch) summation order as v1.
-template <int VEC, int LPR, int SEGS, int MINB>
-__global__ void __launch_bounds__(kUpdThreads, MINB)
-fused_adagrad_pair_kernel(void* const* __restrict__ table_ptrs, void* const* __restrict__ state1_ptrs, int T, int D,
-                          const ptrec_feature_desc* __restrict__ feats, int F, int64_t B,
+// sum of the gradient rows of sorted slots [beg, end) of table t by one CTA: sub-warp sg walks slots beg + sg,
+// beg + sg + 2 NSG, ... two at a time, then a fixed-shape tree over the sub-warps.  The total ends up in the lanes of
+// sub-warp 0 (as `mine`, in shared memory).  Must be called by every thread of the CTA.
+template <int VEC, int LPR>
+__device__ __forceinline__ float* cta_slot_sum(const SlotMap* s_map, float* s_part, int t, int64_t B, int beg, int end,
+                                               const int32_t* __restrict__ perm, const float* __restrict__ grad_out,
+                                               int64_t stride, const float* __restrict__ bag_scale, int sg, int lane,
+                                               bool lane_on) {
+  constexpr int NSG = kLongThreads / LPR;
+  RowVec<VEC> acc;
+  acc.zero();
+  for (int j0 = beg + sg; j0 < end; j0 += NSG * 2) {
+    RowVec<VEC> g0, g1;
+    g0 = slot_grad<VEC>(s_map, t, B, perm[j0], grad_out, stride, bag_scale, lane, lane_on);
+    g1.zero();
+    if (j0 + NSG < end)
+      g1 = slot_grad<VEC>(s_map, t, B, perm[j0 + NSG], grad_out, stride, bag_scale, lane, lane_on);
+    acc.add(g0);
+    acc.add(g1);
+  }
+  float* mine = s_part + (sg * LPR + lane) * VEC;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) mine[k] = acc.v[k];
+  __syncthreads();
+  for (int h = NSG / 2; h > 0; h >>= 1) {
+    if (sg < h) {
+      const float* other = s_part + ((sg + h) * LPR + lane) * VEC;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) mine[k] += other[k];
+    }
+    __syncthreads();
+  }
+  return mine;
+}
+
+// pass A: CTA per kLongChunk-slot chunk of the runs longer than kLongChunk -> one partial row each
+template <int VEC, int LPR>
+__global__ void __launch_bounds__(kLongThreads)
+fused_update_chunk_kernel(int T, int D, const ptrec_feature_desc* __restrict__ feats, int F, int64_t B,
                           const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_start,
-                          const ptrec_segment_meta* __restrict__ seg_meta, const int32_t* __restrict__ n_seg_ptr,
-                          const float* __restrict__ grad_out, int64_t stride, const float* __restrict__ bag_scale,
-                          OptParams op, int* __restrict__ long_count, int32_t* __restrict__ long_list) {
+                          const ptrec_segment_meta* __restrict__ seg_meta, const float* __restrict__ grad_out,
+                          int64_t stride, const float* __restrict__ bag_scale, LongWs lw) {
+  const unsigned long long packed = *lw.counter;
+  const int n_long = (int)(packed >> 32), n_chunks = (int)(packed & 0xffffffffu);
+  if ((int)blockIdx.x >= n_chunks) return;  // the common case (no giant runs): exit before any setup
   __shared__ SlotMap s_map;
+  constexpr int NSG = kLongThreads / LPR;
+  __shared__ float s_part[NSG * LPR * VEC];
   build_slot_map(&s_map, feats, F, T, B);
-  constexpr int SW = 2 * LPR;  // lanes per row
-  constexpr int NSG = kUpdThreads / SW;
-  const int sg = threadIdx.x / SW, sl = threadIdx.x % SW;
-  const int half = sl / LPR, lane = sl % LPR;
+  const int sg = threadIdx.x / LPR, lane = threadIdx.x % LPR;
   const bool lane_on = lane * VEC < D;
-  const int n_seg = *n_seg_ptr;
-  const int n_round = (n_seg + NSG * SEGS - 1) / (NSG * SEGS);
-  for (int r = blockIdx.x; r < n_round; r += gridDim.x) {
-    int start[SEGS], end[SEGS];
-    int4 meta[SEGS];
-#pragma unroll
-    for (int q = 0; q < SEGS; ++q) {
-      const int u = (r * SEGS + q) * NSG + sg;
-      start[q] = end[q] = 0;
-      meta[q] = make_int4((int)kMaskedKey, 0, 0, 0);
-      if (u < n_seg) {
-        start[q] = seg_start[u];
-        end[q] = seg_start[u + 1];
-        meta[q] = *reinterpret_cast<const int4*>(seg_meta + u);
-      }
+  for (int ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
+    // the queued run owning partial row ci: the last entry whose first row is <= ci (entries without rows share the
+    // first row of the next entry that has some, and come before it)
+    int lo = 0, hi = n_long - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (lw.chunk_base[mid] <= ci) lo = mid; else hi = mid - 1;
     }
-    float* rowp[SEGS];
-    RowVec<VEC> x[SEGS], acc[SEGS];
-    bool work[SEGS];
+    const int u = lw.list[lo];
+    const int c = ci - lw.chunk_base[lo];
+    const int start = seg_start[u], end = seg_start[u + 1];
+    const int beg = start + c * kLongChunk;
+    const float* mine = cta_slot_sum<VEC, LPR>(&s_map, s_part, seg_meta[u].table, B, beg, min(end, beg + kLongChunk), perm,
+                                               grad_out, stride, bag_scale, sg, lane, lane_on);
+    if (sg == 0 && lane_on) {
 #pragma unroll
-    for (int q = 0; q < SEGS; ++q) {
-      const int u = (r * SEGS + q) * NSG + sg;
-      const bool live = u < n_seg && (uint32_t)meta[q].x != kMaskedKey;
-      const bool is_long = live && (end[q] - start[q]) > kLongSeg;
-      if (is_long && sl == 0) long_list[atomicAdd(long_count, 1)] = u;
-      work[q] = live && !is_long;
-      rowp[q] = nullptr;
-      x[q].zero();
-      acc[q].zero();
-      if (work[q]) {
-        float* base = reinterpret_cast<float*>(half == 0 ? table_ptrs[meta[q].z] : state1_ptrs[meta[q].z]);
-        rowp[q] = base + (int64_t)(uint32_t)meta[q].x * op.row_stride + lane * VEC;
-        if (lane_on) x[q] = load_row<VEC>(rowp[q]);
-        acc[q] = slot_grad<VEC>(&s_map, meta[q].z, B, meta[q].y, grad_out, stride, bag_scale, lane, lane_on);
-      }
+      for (int k = 0; k < VEC; ++k) lw.partial[(int64_t)ci * D + lane * VEC + k] = mine[k];
     }
-    // remaining gradient slots of longer segments (duplicates in the batch), in sorted order
-#pragma unroll
-    for (int q = 0; q < SEGS; ++q) {
-      if (work[q]) {
-        for (int j0 = start[q] + 1; j0 < end[q]; j0 += 4) {
-          RowVec<VEC> g[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            g[k].zero();
-            if (j0 + k < end[q])
-              g[k] = slot_grad<VEC>(&s_map, meta[q].z, B, perm[j0 + k], grad_out, stride, bag_scale, lane, lane_on);
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) acc[q].add(g[k]);
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < SEGS; ++q) {
-      RowVec<VEC> out;
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        // the partner lane (same slice, other half) holds sum if this lane holds w, and vice versa; the shuffle is
-        // executed by every lane of the warp (work[] only gates the store)
-        const float other = __shfl_xor_sync(0xffffffffu, x[q].v[k], LPR);
-        const float w = half == 0 ? x[q].v[k] : other;
-        float sum = half == 0 ? other : x[q].v[k];
-        float g = acc[q].v[k];
-        if (op.weight_decay != 0.f) g += op.weight_decay * w;
-        sum += g * g;
-        out.v[k] = half == 0 ? w - op.lr * (g / (sqrtf(sum) + op.eps)) : sum;
-      }
-      if (work[q] && lane_on) store_row<VEC>(rowp[q], out);
-    }
+    __syncthreads();
   }
 }
 
-// CTA per long segment
+// pass B: CTA per queued run: reduce it (directly, or from its chunks' partial rows in chunk order) and update the row
 template <int VEC, int LPR, int OPT>
 __global__ void __launch_bounds__(kLongThreads)
 fused_update_long_kernel(void* const* __restrict__ table_ptrs, void* const* __restrict__ state1_ptrs,
@@ -385,9 +378,8 @@ fused_update_long_kernel(void* const* __restrict__ table_ptrs, void* const* __re
                          const uint32_t* __restrict__ sorted_keys, const int32_t* __restrict__ perm,
                          const int32_t* __restrict__ seg_start, const ptrec_segment_meta* __restrict__ seg_meta,
                          const float* __restrict__ grad_out, int64_t stride,
-                         const float* __restrict__ bag_scale, OptParams op,
-                         const int* __restrict__ long_count, const int32_t* __restrict__ long_list) {
-  const int n_long = *long_count;
+                         const float* __restrict__ bag_scale, OptParams op, LongWs lw) {
+  const int n_long = (int)(*lw.counter >> 32);
   if ((int)blockIdx.x >= n_long) return;  // the common case (no hot rows): exit before any setup
   __shared__ SlotMap s_map;
   constexpr int NSG = kLongThreads / LPR;
@@ -396,36 +388,29 @@ fused_update_long_kernel(void* const* __restrict__ table_ptrs, void* const* __re
   const int sg = threadIdx.x / LPR, lane = threadIdx.x % LPR;
   const bool lane_on = lane * VEC < D;
   for (int i = blockIdx.x; i < n_long; i += gridDim.x) {
-    const int u = long_list[i];
+    const int u = lw.list[i];
     const int start = seg_start[u], end = seg_start[u + 1];
     const int t = seg_meta[u].table;
-    RowVec<VEC> acc;
-    acc.zero();
-    for (int j0 = start + sg; j0 < end; j0 += NSG * 2) {
-      RowVec<VEC> g0, g1;
-      g0 = slot_grad<VEC>(&s_map, t, B, perm[j0], grad_out, stride, bag_scale, lane, lane_on);
-      g1.zero();
-      if (j0 + NSG < end)
-        g1 = slot_grad<VEC>(&s_map, t, B, perm[j0 + NSG], grad_out, stride, bag_scale, lane, lane_on);
-      acc.add(g0);
-      acc.add(g1);
-    }
-    float* mine = s_part + (sg * LPR + lane) * VEC;
+    RowVec<VEC> tot;
+    tot.zero();
+    if (end - start > kLongChunk) {
+      if (sg == 0 && lane_on) {
+        const int nch = (end - start + kLongChunk - 1) / kLongChunk;
+        const float* p = lw.partial + (int64_t)lw.chunk_base[i] * D + lane * VEC;
+        for (int c = 0; c < nch; ++c) {
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) mine[k] = acc.v[k];
-    __syncthreads();
-    for (int h = NSG / 2; h > 0; h >>= 1) {
-      if (sg < h) {
-        const float* other = s_part + ((sg + h) * LPR + lane) * VEC;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) mine[k] += other[k];
+          for (int k = 0; k < VEC; ++k) tot.v[k] += p[(int64_t)c * D + k];
+        }
       }
-      __syncthreads();
+    } else {
+      const float* mine = cta_slot_sum<VEC, LPR>(&s_map, s_part, t, B, start, end, perm, grad_out, stride, bag_scale, sg,
+                                                 lane, lane_on);
+      if (sg == 0) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) tot.v[k] = mine[k];
+      }
     }
     if (sg == 0) {  // sub-warp 0 owns the row
-      RowVec<VEC> tot;
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) tot.v[k] = mine[k];
       const uint32_t key = sorted_keys[start];
       float* wrow = reinterpret_cast<float*>(table_ptrs[t]);
       float* s1 = state1_ptrs ? reinterpret_cast<float*>(state1_ptrs[t]) : nullptr;
@@ -438,34 +423,13 @@ fused_update_long_kernel(void* const* __restrict__ table_ptrs, void* const* __re
   }
 }
 
-static int g_update_variant = 0;  // 0 = v1 for every optimizer; Adagrad: 1 = pair<SEGS 2, 8 CTAs/SM>, 2 = pair<4, 6>, 3 = pair<4, 4>
-}  // namespace ptrec
-extern "C" void ptrec_set_update_variant(int32_t v) { ptrec::g_update_variant = v < 0 ? 0 : (v > 3 ? 3 : v); }
-extern "C" int32_t ptrec_update_variant(void) { return ptrec::g_update_variant; }
-namespace ptrec {
-
-template <int VEC, int LPR, int SEGS, int MINB>
-static void launch_pair(void* const* table_ptrs, void* const* s1, int T, int D, const ptrec_feature_desc* feats, int F,
-                        int64_t B, int64_t N, const int32_t* perm, const int32_t* seg_start,
-                        const ptrec_segment_meta* seg_meta, const int32_t* n_seg, const float* grad_out, int64_t stride,
-                        const float* bag_scale, const OptParams& op, int* long_count, int32_t* long_list, int sms,
-                        cudaStream_t st) {
-  constexpr int NSG = kUpdThreads / (2 * LPR);
-  const int64_t rounds = ceil_div(N, NSG * SEGS);
-  const int64_t cap = (int64_t)sms * MINB;
-  const unsigned grid = (unsigned)(rounds < cap ? (rounds > 0 ? rounds : 1) : cap);
-  fused_adagrad_pair_kernel<VEC, LPR, SEGS, MINB><<<grid, kUpdThreads, 0, st>>>(
-      table_ptrs, s1, T, D, feats, F, B, perm, seg_start, seg_meta, n_seg, grad_out, stride, bag_scale, op, long_count,
-      long_list);
-}
-
 template <int VEC, int LPR, int OPT>
 static int launch_update(void* const* table_ptrs, void* const* s1, void* const* s2, int T, int D,
                          const ptrec_feature_desc* feats, int F, int64_t B, int64_t N,
                          const uint32_t* sorted_keys, const int32_t* perm, const int32_t* seg_start,
                          const ptrec_segment_meta* seg_meta, const int32_t* n_seg, const float* grad_out,
-                         int64_t stride, const float* bag_scale, const OptParams& op, int* long_count,
-                         int32_t* long_list, float* row_grad, cudaStream_t st) {
+                         int64_t stride, const float* bag_scale, const OptParams& op, const LongWs& long_ws,
+                         float* row_grad, cudaStream_t st) {
   constexpr int NSG = kUpdThreads / LPR;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -473,31 +437,18 @@ static int launch_update(void* const* table_ptrs, void* const* s1, void* const* 
   const int64_t rounds = ceil_div(N, NSG * 4);
   // 4 CTAs per SM (register-limited): one wave, several rounds per CTA so that the metadata prefetch has a next round
   const unsigned grid = (unsigned)(rounds < (int64_t)sms * 4 ? (rounds > 0 ? rounds : 1) : (int64_t)sms * 4);
-  if (OPT != kOptNone) PTREC_CUDA(cudaMemsetAsync(long_count, 0, sizeof(int), st));
-  bool done = false;
-  if constexpr (OPT == PTREC_OPT_ADAGRAD && 2 * LPR <= 32) {
-    if (g_update_variant != 0) {
-#define PTREC_PAIR(S, M) \
-  launch_pair<VEC, LPR, S, M>(table_ptrs, s1, T, D, feats, F, B, N, perm, seg_start, seg_meta, n_seg, grad_out, stride, \
-                              bag_scale, op, long_count, long_list, sms, st)
-      if (g_update_variant == 1) PTREC_PAIR(2, 8);
-      else if (g_update_variant == 2) PTREC_PAIR(4, 6);
-      else PTREC_PAIR(4, 4);
-#undef PTREC_PAIR
-      PTREC_LAUNCH_CHECK("fused_adagrad_pair_kernel");
-      done = true;
-    }
-  }
-  if (!done) {
-    fused_update_kernel<VEC, LPR, OPT><<<grid, kUpdThreads, 0, st>>>(
-        table_ptrs, s1, s2, T, D, feats, F, B, sorted_keys, perm, seg_start, seg_meta, n_seg, grad_out,
-        stride, bag_scale, op, long_count, long_list, row_grad);
-    PTREC_LAUNCH_CHECK("fused_update_kernel");
-  }
+  if (OPT != kOptNone) PTREC_CUDA(cudaMemsetAsync(long_ws.counter, 0, sizeof(unsigned long long), st));
+  fused_update_kernel<VEC, LPR, OPT><<<grid, kUpdThreads, 0, st>>>(
+      table_ptrs, s1, s2, T, D, feats, F, B, sorted_keys, perm, seg_start, seg_meta, n_seg, grad_out,
+      stride, bag_scale, op, long_ws, row_grad);
+  PTREC_LAUNCH_CHECK("fused_update_kernel");
   if (OPT != kOptNone) {
+    fused_update_chunk_kernel<VEC, LPR><<<sms * 2, kLongThreads, 0, st>>>(T, D, feats, F, B, perm, seg_start, seg_meta,
+                                                                        grad_out, stride, bag_scale, long_ws);
+    PTREC_LAUNCH_CHECK("fused_update_chunk_kernel");
     fused_update_long_kernel<VEC, LPR, OPT><<<sms * 2, kLongThreads, 0, st>>>(
         table_ptrs, s1, s2, T, D, feats, F, B, sorted_keys, perm, seg_start, seg_meta, grad_out, stride,
-        bag_scale, op, long_count, long_list);
+        bag_scale, op, long_ws);
     PTREC_LAUNCH_CHECK("fused_update_long_kernel");
   }
   return PTREC_OK;
@@ -508,12 +459,11 @@ static int dispatch_D(void* const* table_ptrs, void* const* s1, void* const* s2,
                       const ptrec_feature_desc* feats, int F, int64_t B, int64_t N,
                       const uint32_t* sorted_keys, const int32_t* perm, const int32_t* seg_start,
                       const ptrec_segment_meta* seg_meta, const int32_t* n_seg, const float* grad_out,
-                      int64_t stride, const float* bag_scale, const OptParams& op, int* long_count,
-                      int32_t* long_list, float* row_grad, cudaStream_t st) {
+                      int64_t stride, const float* bag_scale, const OptParams& op, const LongWs& long_ws,
+                      float* row_grad, cudaStream_t st) {
 #define PTREC_UPD(V, P) \
   return launch_update<V, P, OPT>(table_ptrs, s1, s2, T, D, feats, F, B, N, sorted_keys, perm, seg_start, \
-                                  seg_meta, n_seg, grad_out, stride, bag_scale, op, long_count,        \
-                                  long_list, row_grad, st)
+                                  seg_meta, n_seg, grad_out, stride, bag_scale, op, long_ws, row_grad, st)
   if (D == 1) PTREC_UPD(1, 1);
   if (D == 2) PTREC_UPD(2, 1);
   const int lanes = D / 4;
@@ -530,9 +480,11 @@ static int dispatch_D(void* const* table_ptrs, void* const* s1, void* const* s2,
 
 using namespace ptrec;
 
+static size_t long_cap(int64_t N) { return (size_t)N / kLongSeg + 2; }               // runs that can be queued
+static size_t long_partial_rows(int64_t N) { return 2 * ((size_t)N / kLongChunk) + 2; }  // sum ceil(len / chunk), len > chunk
 extern "C" size_t ptrec_embedding_bwd_workspace_bytes(int64_t N, int32_t D) {
-  (void)D;
-  return align_up(256 + ((size_t)N / kLongSeg + 2) * sizeof(int32_t), 256);
+  return 256 + 2 * align_up(long_cap(N) * sizeof(int32_t), 256) +
+         align_up(long_partial_rows(N) * (size_t)(D > 0 ? D : 1) * sizeof(float), 256);
 }
 
 static int64_t total_slots(const ptrec_feature_desc* feats_host, int F, int64_t B) {
@@ -585,12 +537,21 @@ extern "C" int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* s
   op.inv_D = 1.0f / (float)D;
   op.lr = opt_host->lr;
   const int step = opt_host->step < 1 ? 1 : opt_host->step;
-  int* long_count = reinterpret_cast<int*>(workspace);
-  int32_t* long_list = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+  LongWs long_ws;
+  {
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    long_ws.counter = reinterpret_cast<unsigned long long*>(w);
+    w += 256;
+    long_ws.list = reinterpret_cast<int32_t*>(w);
+    w += align_up(long_cap(N) * sizeof(int32_t), 256);
+    long_ws.chunk_base = reinterpret_cast<int32_t*>(w);
+    w += align_up(long_cap(N) * sizeof(int32_t), 256);
+    long_ws.partial = reinterpret_cast<float*>(w);
+  }
   cudaStream_t st = (cudaStream_t)stream;
 #define PTREC_ARGS                                                                                      \
   table_ptrs, state1_ptrs, state2_ptrs, T, D, feats, F, B, N, sorted_keys, perm, seg_start, seg_meta, n_seg, \
-      grad_out, grad_row_stride, bag_scale, op, long_count, long_list, nullptr, st
+      grad_out, grad_row_stride, bag_scale, op, long_ws, nullptr, st
   switch (opt_host->kind) {
     case PTREC_OPT_SGD:
       return dispatch_D<PTREC_OPT_SGD>(PTREC_ARGS);
@@ -647,7 +608,8 @@ extern "C" int ptrec_embedding_bwd_segment_sum(int32_t T, int32_t D, const ptrec
   const int64_t N = total_slots(feats_host, F, B);
   if (N == 0) return PTREC_OK;
   OptParams op{};
+  LongWs none{};
   return dispatch_D<kOptNone>(nullptr, nullptr, nullptr, T, D, feats, F, B, N, sorted_keys, perm, seg_start,
-                              seg_meta, n_seg, grad_out, grad_row_stride, bag_scale, op, nullptr,
-                              nullptr, row_grad, (cudaStream_t)stream);
+                              seg_meta, n_seg, grad_out, grad_row_stride, bag_scale, op, none, row_grad,
+                              (cudaStream_t)stream);
 }

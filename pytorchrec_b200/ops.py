@@ -144,7 +144,10 @@ class TableSet:
         key = tuple((w.data_ptr(), w.stride(0)) for w in weights)
         if key != self._key:
             dev = weights[0].device
-            stride = weights[0].stride(0) if weights[0].shape[0] > 1 else weights[0].shape[1]
+            # the group's row stride comes from any table with more than one row (a one-row table has no meaningful
+            # stride: it may still be a plain [1, D] tensor while the others are interleaved with their state)
+            multi = [w for w in weights if w.shape[0] > 1]
+            stride = multi[0].stride(0) if multi else weights[0].shape[1]
             for w in weights:
                 _require_cuda(w)
                 if w.dtype != torch.float32 or w.dim() != 2 or w.stride(1) != 1 or w.device != dev:
@@ -831,49 +834,71 @@ def dcn_cross_wgrad(g_u: torch.Tensor, x_l: torch.Tensor) -> torch.Tensor:
 
 
 class _CrossNet(torch.autograd.Function):
-    """All cross layers in one autograd node so that each dgrad epilogue can emit the g_u of the layer below."""
+    """All cross layers in one autograd node so that each dgrad epilogue can emit the g_u of the layer below.  Every
+    element-wise step around the GEMMs (padding / casting, g_out * x0, the x0-gradient accumulation, the bias
+    gradients, the transposed weights) is one launch of csrc/dcn_glue.cu."""
 
     @staticmethod
     def forward(ctx, x0f, n_layers, *params):
+        lib = _lib.load()
         weights, biases = params[:n_layers], params[n_layers:]
         B, d = x0f.shape
         dp = (d + 7) // 8 * 8
-        x0 = torch.zeros(B, dp, dtype=torch.bfloat16, device=x0f.device)
-        x0[:, :d] = x0f
-        wb, xs, us = [], [x0], []
+        dev = x0f.device
+        st = _stream(dev)
+        if x0f.stride(1) != 1:
+            x0f = x0f.contiguous()
+        x0 = torch.empty(B, dp, dtype=torch.bfloat16, device=dev)
+        _lib.check(lib.ptrec_dcn_pack_input(_ptr(x0f), x0f.stride(0), B, d, dp, _ptr(x0), st), "ptrec_dcn_pack_input")
+        wts, xs, us = [], [x0], []
         x = x0
         for W, b in zip(weights, biases):
-            w16 = torch.zeros(dp, dp, dtype=torch.bfloat16, device=x0f.device)
-            w16[:d, :d] = W
-            bp = torch.zeros(dp, dtype=torch.float32, device=x0f.device)
-            bp[:d] = b
+            w16 = torch.empty(dp, dp, dtype=torch.bfloat16, device=dev)
+            w16t = torch.empty(dp, dp, dtype=torch.bfloat16, device=dev)
+            bp = torch.empty(dp, dtype=torch.float32, device=dev)
+            Wc, bc = W.detach().contiguous(), b.detach().contiguous()
+            _lib.check(lib.ptrec_dcn_prep_weight(_ptr(Wc), _ptr(bc), d, dp, _ptr(w16), _ptr(w16t), _ptr(bp), st),
+                       "ptrec_dcn_prep_weight")
             x, u = dcn_cross_fwd(x, x0, w16, bp, want_u=True)
-            wb.append(w16)
+            wts.append(w16t)
             xs.append(x)
             us.append(u)
+        out = torch.empty(B, d, dtype=torch.float32, device=dev)
+        _lib.check(lib.ptrec_dcn_unpack(_ptr(x), B, d, dp, _ptr(out), st), "ptrec_dcn_unpack")
         ctx.d, ctx.n = d, n_layers
-        ctx.save_for_backward(*xs[:-1], *us, *wb)
-        return x[:, :d].to(x0f.dtype)
+        ctx.save_for_backward(*xs[:-1], *us, *wts)
+        return out.to(x0f.dtype)
 
     @staticmethod
     def backward(ctx, g):
+        lib = _lib.load()
         n, d = ctx.n, ctx.d
         saved = ctx.saved_tensors
-        xs, us, wb = saved[:n], saved[n:2 * n], saved[2 * n:]
+        xs, us, wts = saved[:n], saved[n:2 * n], saved[2 * n:]
         x0 = xs[0]
         B, dp = x0.shape
-        g_out = torch.zeros(B, dp, dtype=torch.bfloat16, device=g.device)
-        g_out[:, :d] = g
-        g_u = g_out * x0
-        g_x0 = torch.zeros(B, dp, dtype=torch.float32, device=g.device)
+        dev = g.device
+        st = _stream(dev)
+        g = g.float()
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        g_out = torch.empty(B, dp, dtype=torch.bfloat16, device=dev)
+        g_u = torch.empty(B, dp, dtype=torch.bfloat16, device=dev)
+        _lib.check(lib.ptrec_dcn_bwd_init(_ptr(g), g.stride(0), _ptr(x0), B, d, dp, _ptr(g_out), _ptr(g_u), st),
+                   "ptrec_dcn_bwd_init")
+        g_x0 = torch.empty(B, dp, dtype=torch.float32, device=dev)
+        ws = _workspace("dcn_bwd_layer", lib.ptrec_dcn_bwd_layer_workspace_bytes(B, dp), dev)
         gws, gbs = [None] * n, [None] * n
         for l in range(n - 1, -1, -1):
-            g_x0.addcmul_(g_out.float(), us[l].float())          # d out / d x0 = u
+            gbs[l] = torch.empty(d, dtype=torch.float32, device=dev)
+            # d out / d x0 = u: g_x0 (+)= g_out * u_l; bias gradient = column sums of g_u
+            _lib.check(lib.ptrec_dcn_bwd_layer(_ptr(g_out), _ptr(us[l]), _ptr(g_u), B, d, dp, _ptr(g_x0), int(l != n - 1),
+                                               _ptr(gbs[l]), _ptr(ws), ws.numel(), st), "ptrec_dcn_bwd_layer")
             gws[l] = dcn_cross_wgrad(g_u, xs[l])[:d, :d]
-            gbs[l] = g_u.float().sum(0)[:d]
-            g_out, g_u = dcn_cross_dgrad(g_u, wb[l].t().contiguous(), g_out, x0, want_prev=l > 0)
-        g_x0 += g_out.float()                                      # x0 is also layer 0's x_l
-        return (g_x0[:, :d].to(g.dtype), None, *gws, *gbs)
+            g_out, g_u = dcn_cross_dgrad(g_u, wts[l], g_out, x0, want_prev=l > 0)
+        out = torch.empty(B, d, dtype=torch.float32, device=dev)  # x0 is also layer 0's x_l: + the chain's g_out
+        _lib.check(lib.ptrec_dcn_bwd_final(_ptr(g_x0), _ptr(g_out), B, d, dp, _ptr(out), st), "ptrec_dcn_bwd_final")
+        return (out, None, *gws, *gbs)
 
 
 def cross_net(x0: torch.Tensor, weights, biases) -> torch.Tensor:

@@ -60,11 +60,8 @@ def run(name, F, R, D, B, zipf=False):
     srts = [ops.sort_dedup(ts, lay, ids, None, B) for ids in id_batches]
     U = sum(int(s.n_seg.item()) for s in srts) / nb
     by = lookups * (4 + D * 4) + U * (8 + 4 * D * 4)
-    for v in range(4):
-        lib.ptrec_set_update_variant(v)
-        t = timeit(lambda i: ops.bwd_fused(ts, p1, None, lay, B, srts[i % nb], go, None, args))
-        res[f"update_v{v}"] = dict(us=t * 1e6, GBps=by / t / 1e9, frac=by / t / 1e9 / peak, unique=U)
-    lib.ptrec_set_update_variant(0)
+    t = timeit(lambda i: ops.bwd_fused(ts, p1, None, lay, B, srts[i % nb], go, None, args))
+    res["update"] = dict(us=t * 1e6, GBps=by / t / 1e9, frac=by / t / 1e9 / peak, unique=U)
     print(name, json.dumps({k: {a: round(b, 3) for a, b in v.items()} for k, v in res.items()}), flush=True)
     return res
 
