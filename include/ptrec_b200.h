@@ -271,7 +271,7 @@ int ptrec_din_attn_pool_fwd(const float* q, int64_t q_stride, const float* keys,
                             int32_t H2, const float* W1, const float* b1, const float* W2, const float* b2,
                             const float* W3, const float* b3, float* out, float* scores, void* stream);
 int32_t ptrec_din_attn_pool_grad_floats(int32_t DQ, int32_t H1, int32_t H2);
-size_t ptrec_din_attn_pool_bwd_workspace_bytes(int32_t DQ, int32_t H1, int32_t H2);
+size_t ptrec_din_attn_pool_bwd_workspace_bytes(int64_t B, int32_t DQ, int32_t H1, int32_t H2);
 int ptrec_din_attn_pool_bwd(const float* q, int64_t q_stride, const float* keys, int64_t k_stride_b,
                             int64_t k_stride_l, const int32_t* lens, int64_t B, int32_t L, int32_t DQ, int32_t H1,
                             int32_t H2, const float* W1, const float* b1, const float* W2, const float* b2,

@@ -160,7 +160,7 @@ PROTOTYPES = {
                                         c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "ptrec_din_attn_pool_grad_floats": (c_int32, [c_int32, c_int32, c_int32]),
-    "ptrec_din_attn_pool_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "ptrec_din_attn_pool_bwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
     "ptrec_din_attn_pool_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int32,
                                         c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,

@@ -166,6 +166,7 @@ din_fwd_kernel(const float* __restrict__ q, int64_t q_stride, const float* __res
 
 // ------------------------------------------------------------------------------------------------ backward
 constexpr int kDinBwdThreads = 256;
+constexpr int kDinBwdGroup = 8;  // samples per CTA of the backward
 
 template <int DQ, int H1, int H2>
 struct DinBwdSmem {
@@ -208,7 +209,13 @@ din_bwd_kernel(const float* __restrict__ q, int64_t q_stride, const float* __res
   const int mjb = t / MB_I, mib = t % MB_I;             // M tile: rows 4*mjb.., cols 4*mib..
   const int wmb = t / WB_J, wjb = t % WB_J;             // W2 tile: rows (m) 4*wmb.., cols (j) 4*wjb..
 
-  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+  // A CTA owns kDinBwdGroup CONSECUTIVE samples: its weight-gradient accumulators see chains of at most L positions
+  // (per-sample tiles) + kDinBwdGroup samples, and the per-CTA partials are summed two-level by the reduce kernel.
+  // (One CTA per SM walking B / 148 samples kept chains of ~5500 fp32 additions: the resulting gradient noise, turned
+  // into weight noise by Adagrad's g / sqrt(sum g^2), was 100x the CPU oracle's at the 99th percentile —
+  // tests/test_gpu_fullsize.py with the fp64 oracle as referee.)
+  const int64_t b_end = min(B, ((int64_t)blockIdx.x + 1) * kDinBwdGroup);
+  for (int64_t b = (int64_t)blockIdx.x * kDinBwdGroup; b < b_end; ++b) {
     const int len = lens ? min(max(lens[b], 0), L) : L;
     __syncthreads();
     if (t < DQ) {
@@ -378,13 +385,19 @@ din_bwd_kernel(const float* __restrict__ q, int64_t q_stride, const float* __res
   if (t == kDinBwdThreads - 1) PW2[H2 * H1 + 2 * H2] = Ab3;
 }
 
-// out[e] = sum over CTAs (fixed order) of partials[cta][e]
+// out[e] = sum over CTAs of partials[cta][e], two fixed-order levels (runs of 32 rows, then the run sums): coalesced
+// over e, chains of 32 + n_cta / 32 additions
 __global__ void din_reduce_partials_kernel(const float* __restrict__ partials, int n_cta, int n, float* __restrict__ out) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
-  float acc = 0.f;
-  for (int c = 0; c < n_cta; ++c) acc += partials[(int64_t)c * n + e];
-  out[e] = acc;
+  float total = 0.f;
+  for (int c0 = 0; c0 < n_cta; c0 += 32) {
+    float acc = 0.f;
+    const int c1 = min(n_cta, c0 + 32);
+    for (int c = c0; c < c1; ++c) acc += partials[(int64_t)c * n + e];
+    total += acc;
+  }
+  out[e] = total;
 }
 
 static int din_grid() {
@@ -414,7 +427,7 @@ static int din_bwd_launch(const float* q, int64_t qs, const float* keys, int64_t
                           int64_t gksb, int64_t gksl, float* grads, float* partials, cudaStream_t st) {
   const size_t smem = sizeof(DinBwdSmem<DQ, H1, H2>);
   PTREC_CUDA(cudaFuncSetAttribute(din_bwd_kernel<DQ, H1, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (int)(B < (int64_t)din_grid() ? B : (int64_t)din_grid());
+  const int grid = (int)((B + kDinBwdGroup - 1) / kDinBwdGroup);
   din_bwd_kernel<DQ, H1, H2><<<grid, kDinBwdThreads, smem, st>>>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3,
                                                                   g_pooled, g_q, g_keys, gksb, gksl, partials);
   PTREC_LAUNCH_CHECK("din_bwd_kernel");
@@ -467,8 +480,9 @@ extern "C" int32_t ptrec_din_attn_pool_grad_floats(int32_t DQ, int32_t H1, int32
   return H1 * 4 * DQ + H1 + H2 * H1 + H2 + H2 + 1;
 }
 
-extern "C" size_t ptrec_din_attn_pool_bwd_workspace_bytes(int32_t DQ, int32_t H1, int32_t H2) {
-  return align_up((size_t)din_grid() * (size_t)ptrec_din_attn_pool_grad_floats(DQ, H1, H2) * sizeof(float), 256);
+extern "C" size_t ptrec_din_attn_pool_bwd_workspace_bytes(int64_t B, int32_t DQ, int32_t H1, int32_t H2) {
+  const size_t rows = (size_t)((B > 0 ? B : 1) + kDinBwdGroup - 1) / kDinBwdGroup;  // one partial row per CTA
+  return align_up(rows * (size_t)ptrec_din_attn_pool_grad_floats(DQ, H1, H2) * sizeof(float), 256);
 }
 
 extern "C" int ptrec_din_attn_pool_bwd(const float* q, int64_t q_stride, const float* keys, int64_t k_stride_b,
@@ -482,7 +496,7 @@ extern "C" int ptrec_din_attn_pool_bwd(const float* q, int64_t q_stride, const f
   PTREC_CHECK_ARG(W1 && b1 && W2 && b2 && W3 && b3 && g_pooled && g_q && g_keys && grad_params && workspace, PTREC_EINVAL,
                   "din_attn_pool_bwd: null pointer");
   PTREC_CHECK_ARG(aligned16(g_keys) && gk_stride_b % 4 == 0 && gk_stride_l % 4 == 0, PTREC_EALIGN, "din_attn_pool_bwd: g_keys alignment");
-  PTREC_CHECK_ARG(workspace_bytes >= ptrec_din_attn_pool_bwd_workspace_bytes(DQ, H1, H2), PTREC_EWORKSPACE,
+  PTREC_CHECK_ARG(workspace_bytes >= ptrec_din_attn_pool_bwd_workspace_bytes(B, DQ, H1, H2), PTREC_EWORKSPACE,
                   "din_attn_pool_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   if (B == 0) {

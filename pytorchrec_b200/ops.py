@@ -944,7 +944,7 @@ def din_attn_pool_bwd(q, keys, lens, params, g_pooled):
     g_keys = torch.empty(B, L, DQ, dtype=torch.float32, device=q.device)
     n = lib.ptrec_din_attn_pool_grad_floats(DQ, H1, H2)
     flat = torch.empty(n, dtype=torch.float32, device=q.device)
-    ws = _workspace("din_bwd", lib.ptrec_din_attn_pool_bwd_workspace_bytes(DQ, H1, H2), q.device)
+    ws = _workspace("din_bwd", lib.ptrec_din_attn_pool_bwd_workspace_bytes(B, DQ, H1, H2), q.device)
     _lib.check(lib.ptrec_din_attn_pool_bwd(_ptr(q), q.stride(0), _ptr(keys), keys.stride(0), keys.stride(1), _ptr(lens),
                                            B, L, DQ, H1, H2, *[_ptr(p) for p in params], _ptr(g_pooled), _ptr(g_q),
                                            _ptr(g_keys), g_keys.stride(0), g_keys.stride(1), _ptr(flat), _ptr(ws),
