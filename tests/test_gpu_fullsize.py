@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_as_exact_as_the_oracle
+from conftest import adagrad_sums, assert_as_exact_as_the_oracle
 from oracle import ref_models
 from pytorchrec_b200.data import amazon_batch, amazon_columns, criteo_batch, criteo_columns
 from pytorchrec_b200.metric import LogLoss
@@ -60,17 +60,18 @@ def test_deepfm_cfg2_full_size_steps_match_cpu_oracle():
         lr32 = ref.train_step(batch)["loss"].item()
         ref64.train_step(batch)
         np.testing.assert_allclose(lp, lr32, rtol=1e-5)
-    sd64 = ref64.state_dict()
+    sd64, sums = ref64.state_dict(), adagrad_sums(ref64)
     for (k, v), (_, v2) in zip(prod.state_dict().items(), ref.state_dict().items()):
         a, b = v.cpu(), v2
         if k.startswith(("embeddings.", "first_order.")):
             f = int(k.split(".")[1])
             # rows no lookup touched are bit-identical to the init (the dense CPU update adds exactly 0 to them)
             assert torch.equal(a[~touched[f]], b[~touched[f]]), k
-            a, b, b64 = a[touched[f]], b[touched[f]], sd64[k][touched[f]]
+            a, b, b64, s64 = a[touched[f]], b[touched[f]], sd64[k][touched[f]], sums[k][touched[f]]
         else:
-            b64 = sd64[k]
-        assert_as_exact_as_the_oracle(k, a.numpy(), b.numpy(), b64.numpy(), rtol=1e-5, atol=1e-5 * 2 * lr)
+            b64, s64 = sd64[k], sums[k]
+        assert_as_exact_as_the_oracle(k, a.numpy(), b.numpy(), b64.numpy(), rtol=1e-5, atol=1e-5 * 2 * lr,
+                                      adagrad=(s64.numpy(), lr, 2))
     prod.embeddings.check_index_errors()
 
 
@@ -125,6 +126,7 @@ def test_din_cfg4_full_size_step_matches_cpu_oracle():
         lp, lr32 = prod.train_step(batch)["loss"].item(), ref.train_step(batch)["loss"].item()
         ref64.train_step(batch)
         np.testing.assert_allclose(lp, lr32, rtol=1e-5)
-    sd64 = ref64.state_dict()
+    sd64, sums = ref64.state_dict(), adagrad_sums(ref64)
     for (k, v), (_, v2) in zip(prod.state_dict().items(), ref.state_dict().items()):
-        assert_as_exact_as_the_oracle(k, v.cpu().numpy(), v2.numpy(), sd64[k].numpy(), rtol=1e-5, atol=1e-5 * 2 * lr)
+        assert_as_exact_as_the_oracle(k, v.cpu().numpy(), v2.numpy(), sd64[k].numpy(), rtol=1e-5, atol=1e-5 * 2 * lr,
+                                      adagrad=(sums[k].numpy(), lr, 2))
