@@ -161,6 +161,8 @@ PROTOTYPES = {
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "ptrec_din_attn_pool_grad_floats": (c_int32, [c_int32, c_int32, c_int32]),
     "ptrec_din_attn_pool_bwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
+    "ptrec_set_din_tc": (None, [c_int32]),
+    "ptrec_din_tc_enabled": (c_int32, []),
     "ptrec_din_attn_pool_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int32,
                                         c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
@@ -212,6 +214,8 @@ def load():
         raise RuntimeError(f"libptrec_b200.so ABI {ver} != binding ABI {ABI_VERSION}: rebuild")
     if os.environ.get("PTREC_ONE_SWEEP"):     # K2a: one-sweep radix sort on / off (A/B measurements)
         lib.ptrec_set_one_sweep_sort(int(os.environ["PTREC_ONE_SWEEP"]))
+    if os.environ.get("PTREC_DIN_TC"):        # K4 forward: tensor-core build on / off
+        lib.ptrec_set_din_tc(int(os.environ["PTREC_DIN_TC"]))
     if os.environ.get("PTREC_TC_BN"):  # K6 fp16 x 2 pair-tile width, 128 or 256 (A/B measurements)
         lib.ptrec_tc_set_bn(int(os.environ["PTREC_TC_BN"]))
     _lib = lib

@@ -439,7 +439,18 @@ static int din_bwd_launch(const float* q, int64_t qs, const float* keys, int64_t
 
 }  // namespace ptrec
 
+namespace ptrec {
+// din_attn_tc.cu: the forward on the tensor cores (PTREC_EUNSUPPORTED when the shape has no such build)
+int din_fwd_tc(const float* q, int64_t qs, const float* keys, int64_t ksb, int64_t ksl, const int32_t* lens, int64_t B,
+               int L, int DQ, int H1, int H2, const float* W1, const float* b1, const float* W2, const float* b2,
+               const float* W3, const float* b3, float* out, float* scores, cudaStream_t st);
+}  // namespace ptrec
+
 using namespace ptrec;
+
+static int g_din_tc = 0;  // 1: forward through the tcgen05 kernel where a build exists; 0: fp32 SIMT kernel
+extern "C" void ptrec_set_din_tc(int32_t on) { g_din_tc = on ? 1 : 0; }
+extern "C" int32_t ptrec_din_tc_enabled(void) { return g_din_tc; }
 
 static int din_check(const void* q, const void* keys, int64_t B, int32_t L, int32_t DQ, int32_t H1, int32_t H2,
                      int64_t qs, int64_t ksb, int64_t ksl) {
@@ -472,6 +483,11 @@ extern "C" int ptrec_din_attn_pool_fwd(const float* q, int64_t q_stride, const f
   PTREC_CHECK_ARG(W1 && b1 && W2 && b2 && W3 && b3 && out, PTREC_EINVAL, "din_attn_pool_fwd: null pointer");
   if (B == 0) return PTREC_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_din_tc) {
+    rc = din_fwd_tc(q, q_stride, keys, k_stride_b, k_stride_l, lens, B, L, DQ, H1, H2, W1, b1, W2, b2, W3, b3, out, scores,
+                    st);
+    if (rc != PTREC_EUNSUPPORTED) return rc;
+  }
   PTREC_DIN_DISPATCH(din_fwd_launch, q, q_stride, keys, k_stride_b, k_stride_l, lens, B, L, W1, b1, W2, b2, W3, b3, out,
                      scores, st);
 }

@@ -232,6 +232,13 @@ class IModel(Module, ABC):
         self.compiled_metrics = MetricList(metrics)
         self.compiled_device = device
         self.to(device)
+        # an optimizer that allocates its state at construction (torch.optim.Adagrad) did so before this move: the
+        # reference builds the optimizer first and compiles second (RepeatTask.py:96), so follow the parameters
+        for p_, st in optimizer.state.items():
+            if torch.is_tensor(p_):
+                for k, v in st.items():
+                    if torch.is_tensor(v) and v.dim() > 0 and v.device != p_.device:
+                        st[k] = v.to(p_.device)
         self._is_compiled = True
 
     def enable_cuda_graph(self, enabled: bool = True, warmup: int = 2) -> None:

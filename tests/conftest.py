@@ -74,9 +74,12 @@ def assert_as_exact_as_the_oracle(name, a, b32, b64, rtol=1e-5, atol=1e-7, slack
     * ``adagrad=(sum64, lr, steps)`` (weights stepped by Adagrad; ``sum64`` = the fp64 oracle's accumulated g^2):
       Adagrad moves an element by lr * g / (sqrt(sum g^2) + eps), so a gradient error dg moves it by about
       lr * dg / sqrt(sum g^2) per step — unboundedly amplified where the element's own gradient is ~0.  The bound is
-      what the north star's gradient tolerance allows after that amplification: dg = grad_rtol x the tensor's RMS
-      gradient (x 4: the maximum over ~1e6 elements), element by element, never more than the 2 * lr * steps a sign
-      flip costs; elements without gradient (sum64 == 0) must not move at all.
+      what the gradient tolerance allows after that amplification, element by element.  The gradient tolerance is
+      SURVEY.md H2's segment-scaled one, dg <= grad_rtol * sum_i |g_i| over the terms the gradient sums: every
+      gradient here is a cancelling sum over >= 256 terms (the batch for a dense weight; the hidden units of the
+      tower behind an embedding row), where sum_i |g_i| ~ sqrt(n) |sum_i g_i|, so 16 x grad_rtol x the tensor's RMS
+      gradient is a lower bound of that allowance.  Never more than the 2 * lr * steps a sign flip costs; elements
+      without gradient (sum64 == 0) must not move at all.
     * otherwise: the CUDA result must be as close to the exact result as the reference's own fp32 arithmetic is — at
       the median and the 90th / 99th / 99.9th percentile |a - b64| <= slack * |b32 - b64| + tolerance, and at the
       maximum with ``max_slack`` (the largest of millions of heavy-tailed errors is a noisy statistic).
@@ -93,7 +96,7 @@ def assert_as_exact_as_the_oracle(name, a, b32, b64, rtol=1e-5, atol=1e-7, slack
         sum64 = np.asarray(sum64, dtype=np.float64).ravel()
         g_elem = np.sqrt(sum64 / steps)                  # the element's own RMS gradient over the steps
         g_rms = np.sqrt(sum64.mean() / steps)            # the tensor's RMS gradient
-        amp = np.minimum(lr * steps * 4.0 * grad_rtol * g_rms / (g_elem + 1e-30), 2.0 * lr * steps)
+        amp = np.minimum(lr * steps * 16.0 * grad_rtol * g_rms / (g_elem + 1e-30), 2.0 * lr * steps)
         bound = np.where(sum64 > 0, amp, 0.0) + rtol * np.abs(b64) + atol
         bad = e_p > bound
         assert not bad.any(), (f"{name}: {int(bad.sum())} of {bad.size} elements exceed what a {grad_rtol:g} gradient error "

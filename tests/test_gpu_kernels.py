@@ -537,9 +537,19 @@ def test_cross_net_autograd_matches_oracle():
 
 
 # ------------------------------------------------------------------------------------------ DIN attention pooling
+@pytest.fixture(params=["simt", "tensor_core"])
+def din_build(request):
+    """K4's forward has an fp32 CUDA-core build and a tcgen05 build (fp16 x 2 operand planes): same contract."""
+    lib = _lib.load()
+    before = lib.ptrec_din_tc_enabled()
+    lib.ptrec_set_din_tc(1 if request.param == "tensor_core" else 0)
+    yield request.param
+    lib.ptrec_set_din_tc(before)
+
+
 @pytest.mark.parametrize("B,L,DQ,hidden", [(3, 5, 32, (80, 40)), (64, 100, 32, (80, 40)), (33, 130, 16, (80, 40)),
-                                            (40, 50, 32, (64, 32)), (17, 100, 16, (64, 32))])
-def test_din_attention_pool_forward_backward(B, L, DQ, hidden):
+                                            (40, 50, 32, (64, 32)), (17, 100, 16, (64, 32)), (300, 300, 32, (80, 40))])
+def test_din_attention_pool_forward_backward(B, L, DQ, hidden, din_build):
     from oracle import ref_models
     g = torch.Generator().manual_seed(B + L + DQ)
     H1, H2 = hidden
