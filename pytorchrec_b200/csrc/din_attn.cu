@@ -448,7 +448,7 @@ int din_fwd_tc(const float* q, int64_t qs, const float* keys, int64_t ksb, int64
 
 using namespace ptrec;
 
-static int g_din_tc = 0;  // 1: forward through the tcgen05 kernel where a build exists; 0: fp32 SIMT kernel
+static int g_din_tc = 1;  // 1 (default): forward through the tcgen05 kernel where a build exists; 0: fp32 SIMT kernel
 extern "C" void ptrec_set_din_tc(int32_t on) { g_din_tc = on ? 1 : 0; }
 extern "C" int32_t ptrec_din_tc_enabled(void) { return g_din_tc; }
 

@@ -46,6 +46,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16 columns of two accumulators (main, correction) with ONE wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float* va, float* vb) {
+  uint32_t a[16], b[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
+        "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+      : "r"(ta));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]),
+        "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15])
+      : "r"(tb));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    va[i] = __uint_as_float(a[i]);
+    vb[i] = __uint_as_float(b[i]);
+  }
+}
 // power of two s with s * amax in [2^13, 2^14)  (1 for an all-zero tile)
 __device__ __forceinline__ float h2_scale(float amax) {
   if (!(amax > 0.f)) return 1.f;
@@ -83,10 +103,8 @@ struct DinTcSmem {
   alignas(128) unsigned char m[2][H1 * DQ * 2];
   alignas(128) unsigned char h1[2][kTcPos * H1 * 2];
   alignas(128) unsigned char w2[2][H2P * H1 * 2];
-  // fp32 side
-  alignas(16) float Wkd[H1][DQ];   // W1k - W1d
-  alignas(16) float W1p[H1][DQ];
-  alignas(16) float Wq[H1][DQ];    // W1q + W1d
+  // fp32 side (W1 itself stays in global memory: 40 KB shared by every CTA, L2-resident — keeping the three derived
+  // [H1, DQ] matrices here cost 30 KB and the second resident CTA per SM)
   alignas(16) float b1[H1];
   alignas(16) float b2[H2P];
   alignas(16) float W3[H2P];
@@ -103,7 +121,7 @@ struct DinTcSmem {
 };
 
 template <int DQ, int H1, int H2>
-__global__ void __launch_bounds__(kTcPos, 1)
+__global__ void __launch_bounds__(kTcPos, 2)
 din_fwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __restrict__ keys, int64_t ksb, int64_t ksl,
                   const int32_t* __restrict__ lens, int64_t B, int L, const float* __restrict__ W1,
                   const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
@@ -120,14 +138,6 @@ din_fwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
   const int t = threadIdx.x, warp = t >> 5;
 
   // ---- once per CTA: weights (fp32 side), W2 planes, barriers, TMEM -------------------------------------------------
-  for (int e = t; e < H1 * DQ; e += kTcPos) {
-    const int j = e / DQ, i = e - j * DQ;
-    const float* row = W1 + (int64_t)j * 4 * DQ;
-    const float wq = row[i], wk = row[DQ + i], wd = row[2 * DQ + i], wp = row[3 * DQ + i];
-    s->Wkd[j][i] = wk - wd;
-    s->W1p[j][i] = wp;
-    s->Wq[j][i] = wq + wd;
-  }
   for (int e = t; e < H1; e += kTcPos) s->b1[e] = b1[e];
   for (int e = t; e < H2P; e += kTcPos) {
     s->b2[e] = e < H2 ? b2[e] : 0.f;
@@ -182,17 +192,32 @@ din_fwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
       const int ch = t + r * kTcPos;  // chunk: row j, columns 8*ci..
       if (ch < H1 * DQ / 8) {
         const int j = ch / (DQ / 8), ci = ch - j * (DQ / 8);
+        const float* row = W1 + (int64_t)j * 4 * DQ + ci * 8;  // [W1q | W1k | W1d | W1p], DQ columns each
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          mv[r][i] = s->Wkd[j][ci * 8 + i] + s->W1p[j][ci * 8 + i] * s->q[ci * 8 + i];
-          mmax = fmaxf(mmax, fabsf(mv[r][i]));
+        for (int h = 0; h < 2; ++h) {
+          const float4 wk = __ldg(reinterpret_cast<const float4*>(row + DQ + 4 * h));
+          const float4 wd = __ldg(reinterpret_cast<const float4*>(row + 2 * DQ + 4 * h));
+          const float4 wp = __ldg(reinterpret_cast<const float4*>(row + 3 * DQ + 4 * h));
+          const float* qq = &s->q[ci * 8 + 4 * h];
+          mv[r][4 * h + 0] = (wk.x - wd.x) + wp.x * qq[0];
+          mv[r][4 * h + 1] = (wk.y - wd.y) + wp.y * qq[1];
+          mv[r][4 * h + 2] = (wk.z - wd.z) + wp.z * qq[2];
+          mv[r][4 * h + 3] = (wk.w - wd.w) + wp.w * qq[3];
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mmax = fmaxf(mmax, fabsf(mv[r][i]));
       }
     }
     if (t < H1) {
       float acc = s->b1[t];
+      const float* row = W1 + (int64_t)t * 4 * DQ;
 #pragma unroll
-      for (int i = 0; i < DQ; ++i) acc += s->Wq[t][i] * s->q[i];
+      for (int i = 0; i < DQ; i += 4) {
+        const float4 wq = __ldg(reinterpret_cast<const float4*>(row + i));
+        const float4 wd = __ldg(reinterpret_cast<const float4*>(row + 2 * DQ + i));
+        acc += (wq.x + wd.x) * s->q[i] + (wq.y + wd.y) * s->q[i + 1] + (wq.z + wd.z) * s->q[i + 2] +
+               (wq.w + wd.w) * s->q[i + 3];
+      }
       s->c[t] = acc;
     }
     mmax = block_max_128(mmax, s->mx);
@@ -263,30 +288,36 @@ din_fwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
       mbar_wait(&s->bar[0], phase);
       tcgen05_fence_after();
       // ---- epilogue 1: h1 = relu(H1pre + c) for this thread's position; planes of h1 ------------------------------
-      float hv[H1];
+      // (two passes over TMEM — the maximum of the tile first, the planes second — instead of H1 live registers)
       const float inv1 = 1.f / (sk * sm);
       float hmax = 0.f;
 #pragma unroll
-      for (int c0 = 0; c0 < H1; c0 += 16) {
+      for (int c0 = 0; c0 < H1; c0 += 16) {  // tcgen05.ld is warp-collective: every lane executes it, rows >= n are masked
         float dm[16], dc[16];
-        tmem_ld16(tD1 + lane_base + c0, dm);
-        tmem_ld16(tC1 + lane_base + c0, dc);
+        tmem_ld16x2(tD1 + lane_base + c0, tC1 + lane_base + c0, dm, dc);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float h = (dm[i] + dc[i] * (1.f / 2048.f)) * inv1 + s->c[c0 + i];
+          hmax = fmaxf(hmax, t < n ? h : 0.f);
+        }
+      }
+      hmax = block_max_128(hmax, s->mx);  // relu: only positive values matter (the initial 0 covers all-negative tiles)
+      const float sh = h2_scale(hmax);
+#pragma unroll
+      for (int c0 = 0; c0 < H1; c0 += 16) {
+        float dm[16], dc[16], x[16];
+        tmem_ld16x2(tD1 + lane_base + c0, tC1 + lane_base + c0, dm, dc);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float h = fmaxf((dm[i] + dc[i] * (1.f / 2048.f)) * inv1 + s->c[c0 + i], 0.f);
-          hv[c0 + i] = t < n ? h : 0.f;
-          hmax = fmaxf(hmax, hv[c0 + i]);
+          x[i] = t < n ? h * sh : 0.f;
         }
-      }
-      hmax = block_max_128(hmax, s->mx);
-      const float sh = h2_scale(hmax);
 #pragma unroll
-      for (int cj = 0; cj < H1 / 8; ++cj) {
-        float x[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = hv[cj * 8 + i] * sh;
-        const uint32_t off = (uint32_t)(t >> 3) * (H1 / 8) * 128 + cj * 128 + (t & 7) * 16;
-        h2_split8(x, reinterpret_cast<uint4*>(s->h1[0] + off), reinterpret_cast<uint4*>(s->h1[1] + off));
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cj = c0 / 8 + hh;
+          const uint32_t off = (uint32_t)(t >> 3) * (H1 / 8) * 128 + cj * 128 + (t & 7) * 16;
+          h2_split8(x + 8 * hh, reinterpret_cast<uint4*>(s->h1[0] + off), reinterpret_cast<uint4*>(s->h1[1] + off));
+        }
       }
       fence_proxy_async();
       tcgen05_fence_before();
@@ -314,8 +345,7 @@ din_fwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
 #pragma unroll
       for (int c0 = 0; c0 < H2P; c0 += 16) {
         float dm[16], dc[16];
-        tmem_ld16(tD2 + lane_base + c0, dm);
-        tmem_ld16(tC2 + lane_base + c0, dc);
+        tmem_ld16x2(tD2 + lane_base + c0, tC2 + lane_base + c0, dm, dc);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           a += s->W3[c0 + i] * fmaxf((dm[i] + dc[i] * (1.f / 2048.f)) * inv2 + s->b2[c0 + i], 0.f);
@@ -357,7 +387,7 @@ static int din_fwd_tc_launch(const float* q, int64_t qs, const float* keys, int6
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = (int)(B < (int64_t)sms ? B : (int64_t)sms);
+  const int grid = (int)(B < (int64_t)sms * 2 ? B : (int64_t)sms * 2);  // two CTAs per SM (~100 KB of shared memory each)
   din_fwd_tc_kernel<DQ, H1, H2><<<grid, kTcPos, smem, st>>>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3,
                                                              out, scores);
   PTREC_LAUNCH_CHECK("din_fwd_tc_kernel");
