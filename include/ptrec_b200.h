@@ -274,8 +274,10 @@ int32_t ptrec_din_attn_pool_grad_floats(int32_t DQ, int32_t H1, int32_t H2);
 size_t ptrec_din_attn_pool_bwd_workspace_bytes(int64_t B, int32_t DQ, int32_t H1, int32_t H2);
 /* The forward has two builds with the same contract: fp32 CUDA cores (din_attn.cu) and tcgen05 tensor cores with
  * fp32-faithful fp16 x 2 operand planes (din_attn_tc.cu: both hidden layers as M = 128 MMAs over tiles of 128
- * positions).  on = 1 selects the tensor-core build where the shape has one. */
-void ptrec_set_din_tc(int32_t on);
+ * positions); the backward likewise (recompute + four gradient contractions as MMAs, operand tiles read in both
+ * orientations).  mode bit 0: tensor-core forward, bit 1: tensor-core backward (default 3: both); where the shape has no
+ * tensor-core build the fp32 kernel runs. */
+void ptrec_set_din_tc(int32_t mode);
 int32_t ptrec_din_tc_enabled(void);
 int ptrec_din_attn_pool_bwd(const float* q, int64_t q_stride, const float* keys, int64_t k_stride_b,
                             int64_t k_stride_l, const int32_t* lens, int64_t B, int32_t L, int32_t DQ, int32_t H1,

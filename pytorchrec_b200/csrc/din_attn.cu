@@ -444,12 +444,17 @@ namespace ptrec {
 int din_fwd_tc(const float* q, int64_t qs, const float* keys, int64_t ksb, int64_t ksl, const int32_t* lens, int64_t B,
                int L, int DQ, int H1, int H2, const float* W1, const float* b1, const float* W2, const float* b2,
                const float* W3, const float* b3, float* out, float* scores, cudaStream_t st);
+int din_bwd_tc(const float* q, int64_t qs, const float* keys, int64_t ksb, int64_t ksl, const int32_t* lens, int64_t B,
+               int L, int DQ, int H1, int H2, const float* W1, const float* b1, const float* W2, const float* b2,
+               const float* W3, const float* b3, const float* g_pooled, float* g_q, float* g_keys, int64_t gksb,
+               int64_t gksl, float* partials, int* n_rows, cudaStream_t st);
 }  // namespace ptrec
 
 using namespace ptrec;
 
-static int g_din_tc = 1;  // 1 (default): forward through the tcgen05 kernel where a build exists; 0: fp32 SIMT kernel
-extern "C" void ptrec_set_din_tc(int32_t on) { g_din_tc = on ? 1 : 0; }
+// bit 0: forward through the tcgen05 kernel where a build exists; bit 1: backward as well (default: both); 0: fp32 SIMT
+static int g_din_tc = 3;
+extern "C" void ptrec_set_din_tc(int32_t mode) { g_din_tc = mode & 3; }
 extern "C" int32_t ptrec_din_tc_enabled(void) { return g_din_tc; }
 
 static int din_check(const void* q, const void* keys, int64_t B, int32_t L, int32_t DQ, int32_t H1, int32_t H2,
@@ -483,7 +488,7 @@ extern "C" int ptrec_din_attn_pool_fwd(const float* q, int64_t q_stride, const f
   PTREC_CHECK_ARG(W1 && b1 && W2 && b2 && W3 && b3 && out, PTREC_EINVAL, "din_attn_pool_fwd: null pointer");
   if (B == 0) return PTREC_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_din_tc) {
+  if (g_din_tc & 1) {
     rc = din_fwd_tc(q, q_stride, keys, k_stride_b, k_stride_l, lens, B, L, DQ, H1, H2, W1, b1, W2, b2, W3, b3, out, scores,
                     st);
     if (rc != PTREC_EUNSUPPORTED) return rc;
@@ -520,6 +525,18 @@ extern "C" int ptrec_din_attn_pool_bwd(const float* q, int64_t q_stride, const f
     return PTREC_OK;
   }
   float* partials = reinterpret_cast<float*>(workspace);
+  if (g_din_tc & 2) {
+    int n_rows = 0;
+    rc = din_bwd_tc(q, q_stride, keys, k_stride_b, k_stride_l, lens, B, L, DQ, H1, H2, W1, b1, W2, b2, W3, b3, g_pooled,
+                    g_q, g_keys, gk_stride_b, gk_stride_l, partials, &n_rows, st);
+    if (rc == PTREC_OK) {
+      const int n = ptrec_din_attn_pool_grad_floats(DQ, H1, H2);
+      din_reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(partials, n_rows, n, grad_params);
+      PTREC_LAUNCH_CHECK("din_reduce_partials_kernel");
+      return PTREC_OK;
+    }
+    if (rc != PTREC_EUNSUPPORTED) return rc;
+  }
   PTREC_DIN_DISPATCH(din_bwd_launch, q, q_stride, keys, k_stride_b, k_stride_l, lens, B, L, W1, b1, W2, b2, W3, b3,
                      g_pooled, g_q, g_keys, gk_stride_b, gk_stride_l, grad_params, partials, st);
 }

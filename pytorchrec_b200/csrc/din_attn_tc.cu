@@ -394,6 +394,592 @@ static int din_fwd_tc_launch(const float* q, int64_t qs, const float* keys, int6
   return PTREC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ backward
+// Recomputes the unit (G1, G2 as in the forward) and runs its four gradient contractions on the tensor core as well.
+// Every operand tile is stored ONCE, in the un-swizzled core-matrix layout, and read in both orientations: a tile
+// stored [l][x] (x contiguous) is a K-major operand when the MMA reduces over x, and the SAME bytes are an MN-major
+// operand (major bit of the instruction descriptor; LBO = 128 along x, SBO = the 8-row group stride along l) when the
+// MMA reduces over the positions l — no transposed copies.
+//   G3  dH1pre [128, H1] = dH2 [128, H2p] . W2              A = dH2 (K-major), B = W2 planes read MN-major
+//   G4  [H1e, H2p]       = H1e^T . dH2    (over l)          A = H1e planes read MN-major (M = 128 covers the H1e rows),
+//                                                           B = dH2 read MN-major;  H1e = [h1 | 1]: row H1 = grad b2
+//   G5  [H1, DQe]        = dH1^T . Ke     (over l)          A = dH1 read MN-major, B = Ke = [k | 1] read MN-major:
+//                                                           columns < DQ = grad M_b, column DQ = grad c_b
+//   G6  dk [128, DQ]     = dH1 . M_b                        A = dH1 (K-major), B = M_b planes read MN-major
+// The "ones" columns are stored unscaled (1.0 in the high plane), so their results carry only the other operand's
+// scale.  Results leave TMEM per tile (the tiles have different scales) into fp32 accumulators in shared memory, one
+// row per thread; a CTA owns kTcBwdGroup consecutive samples and writes one partial row (the layout of
+// din_attn.cu's backward, reduced by its two-level kernel): short fixed-order chains, bit-reproducible.
+constexpr int kTcBwdGroup = 8;
+
+template <int DQ, int H1, int H2>
+struct DinTcBwdSmem {
+  static constexpr int H2P = (H2 + 15) / 16 * 16;
+  static constexpr int DQE = DQ + 16;   // keys + the ones column (+ zero padding to the MMA granule)
+  static constexpr int H1E = H1 + 16;   // h1 + the ones column
+  alignas(1024) unsigned char k[2][kTcPos * DQE * 2];
+  alignas(128) unsigned char m[2][H1 * DQ * 2];
+  alignas(128) unsigned char h1[2][kTcPos * H1E * 2];   // h1 planes, later overwritten by the dH1 planes
+  alignas(128) unsigned char w2[2][H2P * H1E * 2];
+  alignas(128) unsigned char dh2[2][kTcPos * H2P * 2];
+  alignas(16) float kf[kTcPos][DQ + 1];
+  alignas(16) float accWkd[H1][DQ + 1];
+  alignas(16) float accW1p[H1][DQ + 1];
+  alignas(16) float accWq[H1][DQ + 1];
+  alignas(16) float accW2T[H1][H2P + 1];
+  alignas(16) float tmp[H1][DQ + 1];     // per-row contributions to grad q, summed over the rows in order
+  alignas(16) float b1[H1];
+  alignas(16) float b2[H2P];
+  alignas(16) float W3[H2P];
+  alignas(16) float c[H1];
+  alignas(16) float q[DQ];
+  alignas(16) float gp[DQ];
+  float accb1[H1];
+  float accb2[H2P];
+  float accW3[H2P];
+  float wpart[4][H2P + 1];               // per-warp partial column sums (grad W3)
+  float bpart[4];
+  float accb3;
+  float mx[4];
+  float b3;
+  float s_w2;
+  alignas(8) uint64_t bar[4];
+  uint32_t tmem_slot;
+};
+
+// The same tile read MN-major (reduction over its ROWS): core matrices are the same 8 x 16-byte blocks; for the
+// un-swizzled layout both majors name the strides alike — SBO between core matrices along M / N (here: the 128-byte
+// step between column groups), LBO between core matrices along K (here: the 8-row group stride).  (Verified on B200:
+// the swapped assignment produces garbage, this one matches the fp32 kernel to 3e-7; tools/diag_din_bwd_tc.py.)
+__device__ __forceinline__ uint64_t make_nosw_mn_desc(const void* smem_tile, uint32_t group_stride) {
+  return make_nosw_desc(smem_tile, group_stride, 128);
+}
+
+// three MMAs of one K = 16 step of a split product
+__device__ __forceinline__ void umma3(uint32_t tD, uint32_t tC, uint64_t a0, uint64_t a1, uint64_t b0, uint64_t b1,
+                                      uint32_t idesc, uint32_t acc) {
+  umma_bf16(tC, a0, b1, idesc, acc);
+  umma_bf16(tC, a1, b0, idesc, 1u);
+  umma_bf16(tD, a0, b0, idesc, acc);
+}
+
+template <int DQ, int H1, int H2>
+__global__ void __launch_bounds__(kTcPos, 1)
+din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __restrict__ keys, int64_t ksb, int64_t ksl,
+                  const int32_t* __restrict__ lens, int64_t B, int L, const float* __restrict__ W1,
+                  const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
+                  const float* __restrict__ W3, const float* __restrict__ b3, const float* __restrict__ g_pooled,
+                  float* __restrict__ g_q, float* __restrict__ g_keys, int64_t gksb, int64_t gksl,
+                  float* __restrict__ partials) {
+  using S = DinTcBwdSmem<DQ, H1, H2>;
+  constexpr int H2P = S::H2P, DQE = S::DQE, H1E = S::H1E;
+  static_assert(DQ % 16 == 0 && H1 % 16 == 0 && H1E <= 128 && H1 + 1 <= kTcPos, "MMA shape constraints");
+  // TMEM columns: region X = [0, 2 H1) holds (D1 | C1), then (D3 | C3), then (D5 | C5); region Y = [2 H1, 2 H1 + 2 H2P)
+  // holds (D2 | C2), then (D4 | C4), then (D6 | C6)
+  constexpr uint32_t kTmemCols = 256;
+  static_assert(2 * H1 + 2 * H2P <= kTmemCols && 2 * DQE <= 2 * H1 && 2 * DQ <= 2 * H2P, "accumulators exceed TMEM");
+  extern __shared__ unsigned char smem_raw[];
+  S* s = reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  constexpr uint32_t kSboK = (DQE / 8) * 128, kSboM = (DQ / 8) * 128, kSboH = (H1E / 8) * 128, kSboW = (H1E / 8) * 128,
+                     kSboG = (H2P / 8) * 128;
+
+  // ---- once per CTA --------------------------------------------------------------------------------------------------
+  for (int e = t; e < H1; e += kTcPos) {
+    s->b1[e] = b1[e];
+    s->accb1[e] = 0.f;
+  }
+  for (int e = t; e < H2P; e += kTcPos) {
+    s->b2[e] = e < H2 ? b2[e] : 0.f;
+    s->W3[e] = e < H2 ? W3[e] : 0.f;
+    s->accb2[e] = 0.f;
+    s->accW3[e] = 0.f;
+  }
+  for (int e = t; e < H1 * (DQ + 1); e += kTcPos) {
+    (&s->accWkd[0][0])[e] = 0.f;
+    (&s->accW1p[0][0])[e] = 0.f;
+    (&s->accWq[0][0])[e] = 0.f;
+  }
+  for (int e = t; e < H1 * (H2P + 1); e += kTcPos) (&s->accW2T[0][0])[e] = 0.f;
+  float wmax = 0.f;
+  for (int e = t; e < H2 * H1; e += kTcPos) wmax = fmaxf(wmax, fabsf(W2[e]));
+  wmax = block_max_128(wmax, s->mx);
+  const float sw2 = h2_scale(wmax);
+  if (t == 0) {
+    s->b3 = b3[0];
+    s->s_w2 = sw2;
+    s->accb3 = 0.f;
+    for (int i = 0; i < 4; ++i) mbar_init(&s->bar[i], 1);
+    fence_mbar_init();
+  }
+  for (int ch = t; ch < H2P * (H1E / 8); ch += kTcPos) {  // W2 planes [H2P rows m][H1E columns j], zero padded
+    const int mrow = ch / (H1E / 8), cj = ch - mrow * (H1E / 8);
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = (mrow < H2 && cj * 8 + i < H1) ? W2[mrow * H1 + cj * 8 + i] * sw2 : 0.f;
+    const uint32_t off = (uint32_t)(mrow >> 3) * kSboW + cj * 128 + (mrow & 7) * 16;
+    h2_split8(x, reinterpret_cast<uint4*>(s->w2[0] + off), reinterpret_cast<uint4*>(s->w2[1] + off));
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s->tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s->tmem_slot;
+  const uint32_t tX = tmem, tY = tmem + 2 * H1;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  constexpr uint32_t kM = (uint32_t)(kTcPos >> 4) << 24, kF = 1u << 4, kAmn = 1u << 15, kBmn = 1u << 16;
+  constexpr uint32_t kI1 = kF | kM | ((uint32_t)(H1 >> 3) << 17);                   // G1: N = H1, K-major / K-major
+  constexpr uint32_t kI2 = kF | kM | ((uint32_t)(H2P >> 3) << 17);                  // G2: N = H2P
+  constexpr uint32_t kI3 = kF | kM | ((uint32_t)(H1 >> 3) << 17) | kBmn;            // G3: N = H1, B MN-major
+  constexpr uint32_t kI4 = kF | kM | ((uint32_t)(H2P >> 3) << 17) | kAmn | kBmn;    // G4: N = H2P, both MN-major
+  constexpr uint32_t kI5 = kF | kM | ((uint32_t)(DQE >> 3) << 17) | kAmn | kBmn;    // G5: N = DQE, both MN-major
+  constexpr uint32_t kI6 = kF | kM | ((uint32_t)(DQ >> 3) << 17) | kBmn;            // G6: N = DQ, B MN-major
+  uint32_t phase = 0;
+  const __half one = __float2half_rn(1.f);
+
+  const int64_t b_end = min(B, ((int64_t)blockIdx.x + 1) * kTcBwdGroup);
+  for (int64_t b = (int64_t)blockIdx.x * kTcBwdGroup; b < b_end; ++b) {
+    const int len = lens ? min(max(lens[b], 0), L) : L;
+    __syncthreads();
+    if (t < DQ) {
+      s->q[t] = q[b * q_stride + t];
+      s->gp[t] = g_pooled[b * DQ + t];
+    }
+    __syncthreads();
+    // ---- M_b planes and c_b (as in the forward) ----------------------------------------------------------------------
+    float mv[(H1 * DQ / 8 + kTcPos - 1) / kTcPos][8];
+    float mmax = 0.f;
+#pragma unroll
+    for (int r = 0; r < (H1 * DQ / 8 + kTcPos - 1) / kTcPos; ++r) {
+      const int ch = t + r * kTcPos;
+      if (ch < H1 * DQ / 8) {
+        const int j = ch / (DQ / 8), ci = ch - j * (DQ / 8);
+        const float* row = W1 + (int64_t)j * 4 * DQ + ci * 8;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 wk = __ldg(reinterpret_cast<const float4*>(row + DQ + 4 * h));
+          const float4 wd = __ldg(reinterpret_cast<const float4*>(row + 2 * DQ + 4 * h));
+          const float4 wp = __ldg(reinterpret_cast<const float4*>(row + 3 * DQ + 4 * h));
+          const float* qq = &s->q[ci * 8 + 4 * h];
+          mv[r][4 * h + 0] = (wk.x - wd.x) + wp.x * qq[0];
+          mv[r][4 * h + 1] = (wk.y - wd.y) + wp.y * qq[1];
+          mv[r][4 * h + 2] = (wk.z - wd.z) + wp.z * qq[2];
+          mv[r][4 * h + 3] = (wk.w - wd.w) + wp.w * qq[3];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mmax = fmaxf(mmax, fabsf(mv[r][i]));
+      }
+    }
+    if (t < H1) {
+      float acc = s->b1[t];
+      const float* row = W1 + (int64_t)t * 4 * DQ;
+#pragma unroll
+      for (int i = 0; i < DQ; i += 4) {
+        const float4 wq = __ldg(reinterpret_cast<const float4*>(row + i));
+        const float4 wd = __ldg(reinterpret_cast<const float4*>(row + 2 * DQ + i));
+        acc += (wq.x + wd.x) * s->q[i] + (wq.y + wd.y) * s->q[i + 1] + (wq.z + wd.z) * s->q[i + 2] +
+               (wq.w + wd.w) * s->q[i + 3];
+      }
+      s->c[t] = acc;
+    }
+    mmax = block_max_128(mmax, s->mx);
+    const float sm = h2_scale(mmax);
+#pragma unroll
+    for (int r = 0; r < (H1 * DQ / 8 + kTcPos - 1) / kTcPos; ++r) {
+      const int ch = t + r * kTcPos;
+      if (ch < H1 * DQ / 8) {
+        const int j = ch / (DQ / 8), ci = ch - j * (DQ / 8);
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = mv[r][i] * sm;
+        const uint32_t off = (uint32_t)(j >> 3) * kSboM + ci * 128 + (j & 7) * 16;
+        h2_split8(x, reinterpret_cast<uint4*>(s->m[0] + off), reinterpret_cast<uint4*>(s->m[1] + off));
+      }
+    }
+    float gq_acc = 0.f;  // thread i < DQ: grad q[i], summed over the tiles
+    for (int l0 = 0; l0 < max(len, 1); l0 += kTcPos) {
+      const int n = max(0, min(kTcPos, len - l0));
+      const bool live = t < n;
+      // ---- Ke planes: this thread's key row | 1 | 0 ... ----------------------------------------------------------------
+      float kk[DQ];
+      float kmax = 0.f;
+      if (live) {
+        const float* kp = keys + b * ksb + (int64_t)(l0 + t) * ksl;
+#pragma unroll
+        for (int x = 0; x < DQ; x += 4) {
+          const float4 v = ldg_stream_f4(kp + x);
+          kk[x] = v.x; kk[x + 1] = v.y; kk[x + 2] = v.z; kk[x + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int x = 0; x < DQ; ++x) kk[x] = 0.f;
+      }
+      float ga = 0.f;  // d loss / d a_l = <g_pooled, k_l>
+#pragma unroll
+      for (int x = 0; x < DQ; ++x) {
+        kmax = fmaxf(kmax, fabsf(kk[x]));
+        s->kf[t][x] = kk[x];
+        ga += s->gp[x] * kk[x];
+      }
+      kmax = block_max_128(kmax, s->mx);
+      const float sk = h2_scale(kmax);
+      {
+        const uint32_t rowoff = (uint32_t)(t >> 3) * kSboK + (t & 7) * 16;
+#pragma unroll
+        for (int ci = 0; ci < DQ / 8; ++ci) {
+          float x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = kk[ci * 8 + i] * sk;
+          h2_split8(x, reinterpret_cast<uint4*>(s->k[0] + rowoff + ci * 128), reinterpret_cast<uint4*>(s->k[1] + rowoff + ci * 128));
+        }
+        // columns DQ .. DQE: the ones column (unscaled, rows of live positions only), then zeros
+        __half ext[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ext[i] = __float2half_rn(0.f);
+        const uint4 zero = *reinterpret_cast<const uint4*>(ext);
+        ext[0] = live ? one : ext[0];
+        *reinterpret_cast<uint4*>(s->k[0] + rowoff + (DQ / 8) * 128) = *reinterpret_cast<const uint4*>(ext);
+        *reinterpret_cast<uint4*>(s->k[1] + rowoff + (DQ / 8) * 128) = zero;
+        *reinterpret_cast<uint4*>(s->k[0] + rowoff + (DQ / 8 + 1) * 128) = zero;
+        *reinterpret_cast<uint4*>(s->k[1] + rowoff + (DQ / 8 + 1) * 128) = zero;
+      }
+      fence_proxy_async();
+      tcgen05_fence_before();
+      __syncthreads();
+      if (t == 0) {  // G1
+        tcgen05_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < DQ / 16; ++ks)
+          umma3(tX, tX + H1, make_nosw_desc(s->k[0] + ks * 256, 128, kSboK), make_nosw_desc(s->k[1] + ks * 256, 128, kSboK),
+                make_nosw_desc(s->m[0] + ks * 256, 128, kSboM), make_nosw_desc(s->m[1] + ks * 256, 128, kSboM), kI1,
+                ks > 0 ? 1u : 0u);
+        umma_commit(&s->bar[0]);
+      }
+      mbar_wait(&s->bar[0], phase);
+      tcgen05_fence_after();
+      // ---- epilogue 1: h1 -> H1e planes; keep the ReLU mask of this position -------------------------------------------
+      const float inv1 = 1.f / (sk * sm);
+      float hmax = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < H1; c0 += 16) {
+        float dm[16], dc[16];
+        tmem_ld16x2(tX + lane_base + c0, tX + H1 + lane_base + c0, dm, dc);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          hmax = fmaxf(hmax, live ? (dm[i] + dc[i] * (1.f / 2048.f)) * inv1 + s->c[c0 + i] : 0.f);
+      }
+      hmax = block_max_128(hmax, s->mx);
+      const float sh = h2_scale(hmax);
+      uint32_t mask1[(H1 + 31) / 32];
+#pragma unroll
+      for (int w = 0; w < (H1 + 31) / 32; ++w) mask1[w] = 0u;
+      {
+        const uint32_t rowoff = (uint32_t)(t >> 3) * kSboH + (t & 7) * 16;
+#pragma unroll
+        for (int c0 = 0; c0 < H1; c0 += 16) {
+          float dm[16], dc[16], x[16];
+          tmem_ld16x2(tX + lane_base + c0, tX + H1 + lane_base + c0, dm, dc);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float h = (dm[i] + dc[i] * (1.f / 2048.f)) * inv1 + s->c[c0 + i];
+            const bool on = live && h > 0.f;
+            if (on) mask1[(c0 + i) >> 5] |= 1u << ((c0 + i) & 31);
+            x[i] = on ? h * sh : 0.f;
+          }
+          h2_split8(x, reinterpret_cast<uint4*>(s->h1[0] + rowoff + (c0 / 8) * 128), reinterpret_cast<uint4*>(s->h1[1] + rowoff + (c0 / 8) * 128));
+          h2_split8(x + 8, reinterpret_cast<uint4*>(s->h1[0] + rowoff + (c0 / 8 + 1) * 128),
+                    reinterpret_cast<uint4*>(s->h1[1] + rowoff + (c0 / 8 + 1) * 128));
+        }
+        __half ext[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ext[i] = __float2half_rn(0.f);
+        const uint4 zero = *reinterpret_cast<const uint4*>(ext);
+        ext[0] = live ? one : ext[0];
+        *reinterpret_cast<uint4*>(s->h1[0] + rowoff + (H1 / 8) * 128) = *reinterpret_cast<const uint4*>(ext);
+        *reinterpret_cast<uint4*>(s->h1[1] + rowoff + (H1 / 8) * 128) = zero;
+        *reinterpret_cast<uint4*>(s->h1[0] + rowoff + (H1 / 8 + 1) * 128) = zero;
+        *reinterpret_cast<uint4*>(s->h1[1] + rowoff + (H1 / 8 + 1) * 128) = zero;
+      }
+      fence_proxy_async();
+      tcgen05_fence_before();
+      __syncthreads();
+      if (t == 0) {  // G2 (the ones column meets zero columns of the W2 planes)
+        tcgen05_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < H1 / 16; ++ks)
+          umma3(tY, tY + H2P, make_nosw_desc(s->h1[0] + ks * 256, 128, kSboH), make_nosw_desc(s->h1[1] + ks * 256, 128, kSboH),
+                make_nosw_desc(s->w2[0] + ks * 256, 128, kSboW), make_nosw_desc(s->w2[1] + ks * 256, 128, kSboW), kI2,
+                ks > 0 ? 1u : 0u);
+        umma_commit(&s->bar[1]);
+      }
+      mbar_wait(&s->bar[1], phase);
+      tcgen05_fence_after();
+      // ---- epilogue 2: a_l, dH2 planes, grad W3 / b3 (column sums over the positions: warp tree, then the warps in order)
+      const float inv2 = 1.f / (sh * s->s_w2);
+      float a = s->b3;
+      float gmax = 0.f;
+      float dh2[H2P];
+      float gw3[H2P];
+#pragma unroll
+      for (int c0 = 0; c0 < H2P; c0 += 16) {
+        float dm[16], dc[16];
+        tmem_ld16x2(tY + lane_base + c0, tY + H2P + lane_base + c0, dm, dc);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float pre = (dm[i] + dc[i] * (1.f / 2048.f)) * inv2 + s->b2[c0 + i];
+          const float r = fmaxf(pre, 0.f);
+          a += s->W3[c0 + i] * r;
+          dh2[c0 + i] = (live && pre > 0.f) ? ga * s->W3[c0 + i] : 0.f;
+          gw3[c0 + i] = live ? ga * r : 0.f;
+          gmax = fmaxf(gmax, fabsf(dh2[c0 + i]));
+        }
+      }
+      if (!live) { a = 0.f; ga = 0.f; }
+      gmax = block_max_128(gmax, s->mx);
+      const float sg2 = h2_scale(gmax);
+      {
+        const uint32_t rowoff = (uint32_t)(t >> 3) * kSboG + (t & 7) * 16;
+#pragma unroll
+        for (int cj = 0; cj < H2P / 8; ++cj) {
+          float x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = dh2[cj * 8 + i] * sg2;
+          h2_split8(x, reinterpret_cast<uint4*>(s->dh2[0] + rowoff + cj * 128), reinterpret_cast<uint4*>(s->dh2[1] + rowoff + cj * 128));
+        }
+      }
+      float gb3 = ga;
+#pragma unroll
+      for (int m = 0; m < H2P; ++m) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gw3[m] += __shfl_xor_sync(0xffffffffu, gw3[m], o);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) gb3 += __shfl_xor_sync(0xffffffffu, gb3, o);
+      if (lane == 0) {
+#pragma unroll
+        for (int m = 0; m < H2P; ++m) s->wpart[warp][m] = gw3[m];
+        s->bpart[warp] = gb3;
+      }
+      fence_proxy_async();
+      tcgen05_fence_before();
+      __syncthreads();
+      if (t == 0) {  // G3 into region X, G4 into region Y (both read the dH2 planes; G4 also the H1e planes)
+        tcgen05_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < H2P / 16; ++ks)  // reduce over m: dH2 K-major (+256 B), W2 MN-major (2 groups of 8 m-rows)
+          umma3(tX, tX + H1, make_nosw_desc(s->dh2[0] + ks * 256, 128, kSboG), make_nosw_desc(s->dh2[1] + ks * 256, 128, kSboG),
+                make_nosw_mn_desc(s->w2[0] + ks * 2 * kSboW, kSboW), make_nosw_mn_desc(s->w2[1] + ks * 2 * kSboW, kSboW),
+                kI3, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < kTcPos / 16; ++ks)  // reduce over l: both MN-major (2 groups of 8 position rows per step)
+          umma3(tY, tY + H2P, make_nosw_mn_desc(s->h1[0] + ks * 2 * kSboH, kSboH),
+                make_nosw_mn_desc(s->h1[1] + ks * 2 * kSboH, kSboH), make_nosw_mn_desc(s->dh2[0] + ks * 2 * kSboG, kSboG),
+                make_nosw_mn_desc(s->dh2[1] + ks * 2 * kSboG, kSboG), kI4, ks > 0 ? 1u : 0u);
+        umma_commit(&s->bar[2]);
+      }
+      if (t < H2) {  // grad W3 / b3 of this tile: the four warps in order (runs while the MMAs do)
+        s->accW3[t] += ((s->wpart[0][t] + s->wpart[1][t]) + s->wpart[2][t]) + s->wpart[3][t];
+      } else if (t == H2P) {
+        s->accb3 += ((s->bpart[0] + s->bpart[1]) + s->bpart[2]) + s->bpart[3];
+      }
+      mbar_wait(&s->bar[2], phase);
+      tcgen05_fence_after();
+      // ---- epilogue 3: dH1 planes (into the H1e buffer: G4 is done with it); grad W2 / b2 rows ---------------------------
+      const float inv3 = 1.f / (sg2 * s->s_w2);
+      float g1max = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < H1; c0 += 16) {
+        float dm[16], dc[16];
+        tmem_ld16x2(tX + lane_base + c0, tX + H1 + lane_base + c0, dm, dc);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const bool on = (mask1[(c0 + i) >> 5] >> ((c0 + i) & 31)) & 1u;
+          g1max = fmaxf(g1max, on ? fabsf((dm[i] + dc[i] * (1.f / 2048.f)) * inv3) : 0.f);
+        }
+      }
+      {  // row t of G4: t < H1 -> grad W2[:, t] of this tile, t == H1 -> grad b2
+        const float inv4 = t < H1 ? 1.f / (sh * sg2) : 1.f / sg2;
+#pragma unroll
+        for (int c0 = 0; c0 < H2P; c0 += 16) {
+          float dm[16], dc[16];
+          tmem_ld16x2(tY + lane_base + c0, tY + H2P + lane_base + c0, dm, dc);
+          if (t < H1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s->accW2T[t][c0 + i] += (dm[i] + dc[i] * (1.f / 2048.f)) * inv4;
+          } else if (t == H1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s->accb2[c0 + i] += (dm[i] + dc[i] * (1.f / 2048.f)) * inv4;
+          }
+        }
+      }
+      g1max = block_max_128(g1max, s->mx);
+      const float sg1 = h2_scale(g1max);
+      {
+        const uint32_t rowoff = (uint32_t)(t >> 3) * kSboH + (t & 7) * 16;
+#pragma unroll
+        for (int c0 = 0; c0 < H1; c0 += 16) {
+          float dm[16], dc[16], x[16];
+          tmem_ld16x2(tX + lane_base + c0, tX + H1 + lane_base + c0, dm, dc);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const bool on = (mask1[(c0 + i) >> 5] >> ((c0 + i) & 31)) & 1u;
+            x[i] = on ? (dm[i] + dc[i] * (1.f / 2048.f)) * inv3 * sg1 : 0.f;
+          }
+          h2_split8(x, reinterpret_cast<uint4*>(s->h1[0] + rowoff + (c0 / 8) * 128), reinterpret_cast<uint4*>(s->h1[1] + rowoff + (c0 / 8) * 128));
+          h2_split8(x + 8, reinterpret_cast<uint4*>(s->h1[0] + rowoff + (c0 / 8 + 1) * 128),
+                    reinterpret_cast<uint4*>(s->h1[1] + rowoff + (c0 / 8 + 1) * 128));
+        }
+        // the ones column of H1e becomes a zero column of the dH1 planes
+        __half ext[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ext[i] = __float2half_rn(0.f);
+        *reinterpret_cast<uint4*>(s->h1[0] + rowoff + (H1 / 8) * 128) = *reinterpret_cast<const uint4*>(ext);
+      }
+      fence_proxy_async();
+      tcgen05_fence_before();
+      __syncthreads();
+      if (t == 0) {  // G5 into region X, G6 into region Y
+        tcgen05_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < kTcPos / 16; ++ks)  // reduce over l: dH1 MN-major, Ke MN-major
+          umma3(tX, tX + DQE, make_nosw_mn_desc(s->h1[0] + ks * 2 * kSboH, kSboH),
+                make_nosw_mn_desc(s->h1[1] + ks * 2 * kSboH, kSboH), make_nosw_mn_desc(s->k[0] + ks * 2 * kSboK, kSboK),
+                make_nosw_mn_desc(s->k[1] + ks * 2 * kSboK, kSboK), kI5, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < H1 / 16; ++ks)  // reduce over j: dH1 K-major, M_b MN-major
+          umma3(tY, tY + DQ, make_nosw_desc(s->h1[0] + ks * 256, 128, kSboH), make_nosw_desc(s->h1[1] + ks * 256, 128, kSboH),
+                make_nosw_mn_desc(s->m[0] + ks * 2 * kSboM, kSboM), make_nosw_mn_desc(s->m[1] + ks * 2 * kSboM, kSboM),
+                kI6, ks > 0 ? 1u : 0u);
+        umma_commit(&s->bar[3]);
+      }
+      mbar_wait(&s->bar[3], phase);
+      tcgen05_fence_after();
+      phase ^= 1u;
+      // ---- epilogue 4: grad keys of this position; row t of G5 -> grads of M_b / c_b -> W1 accumulators, grad q ---------
+      {
+        const float inv6 = 1.f / (sg1 * sm);
+        float gk[DQ];
+#pragma unroll
+        for (int c0 = 0; c0 < DQ; c0 += 16) {
+          float dm[16], dc[16];
+          tmem_ld16x2(tY + lane_base + c0, tY + DQ + lane_base + c0, dm, dc);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) gk[c0 + i] = (dm[i] + dc[i] * (1.f / 2048.f)) * inv6 + a * s->gp[c0 + i];
+        }
+        if (live) {
+          float* gkp = g_keys + b * gksb + (int64_t)(l0 + t) * gksl;
+#pragma unroll
+          for (int x = 0; x < DQ; x += 4) st_f4(gkp + x, make_float4(gk[x], gk[x + 1], gk[x + 2], gk[x + 3]));
+        }
+      }
+      {
+        const float inv5 = 1.f / (sg1 * sk);
+        float dM[DQ];
+        float dcj = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < DQE; c0 += 16) {
+          float dm[16], dc[16];
+          tmem_ld16x2(tX + lane_base + c0, tX + DQE + lane_base + c0, dm, dc);
+          if (c0 < DQ) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dM[c0 + i] = (dm[i] + dc[i] * (1.f / 2048.f)) * inv5;
+          } else {
+            dcj = (dm[0] + dc[0] * (1.f / 2048.f)) / sg1;  // the ones column: only dH1's scale
+          }
+        }
+        if (t < H1) {
+          const float* row = W1 + (int64_t)t * 4 * DQ;
+          s->accb1[t] += dcj;
+#pragma unroll
+          for (int i = 0; i < DQ; ++i) {
+            const float qv = s->q[i];
+            s->accWkd[t][i] += dM[i];
+            s->accW1p[t][i] += dM[i] * qv;
+            s->accWq[t][i] += dcj * qv;
+            // d c / d q = Wq = W1q + W1d ; d M / d q = W1p (column-wise)
+            s->tmp[t][i] = (__ldg(row + i) + __ldg(row + 2 * DQ + i)) * dcj + __ldg(row + 3 * DQ + i) * dM[i];
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncthreads();
+      if (t < DQ) {
+        float r = 0.f;
+        for (int j = 0; j < H1; ++j) r += s->tmp[j][t];
+        gq_acc += r;
+      }
+    }
+    // zero gradient for the padded tail of the history; grad q
+    for (int64_t e = len * (int64_t)DQ + t; e < (int64_t)L * DQ; e += kTcPos) {
+      const int64_t l = e / DQ;
+      g_keys[b * gksb + l * gksl + (e - l * DQ)] = 0.f;
+    }
+    if (t < DQ) g_q[b * DQ + t] = gq_acc;
+  }
+  __syncthreads();
+  // ---- per-CTA partial weight gradients: [W1 (H1 x 4DQ) | b1 | W2 (H2 x H1) | b2 | W3 | b3] (din_attn.cu's layout) ----------
+  float* P = partials + (int64_t)blockIdx.x * (H1 * 4 * DQ + H1 + H2 * H1 + H2 + H2 + 1);
+  for (int e = t; e < H1 * DQ; e += kTcPos) {
+    const int j = e / DQ, i = e - j * DQ;
+    float* row = P + (int64_t)j * 4 * DQ;
+    const float a3 = s->accWq[j][i], a1 = s->accWkd[j][i];
+    row[i] = a3;                 // W1q
+    row[DQ + i] = a1;            // W1k
+    row[2 * DQ + i] = a3 - a1;   // W1d  (Wq = W1q + W1d, Wkd = W1k - W1d)
+    row[3 * DQ + i] = s->accW1p[j][i];
+  }
+  for (int e = t; e < H1; e += kTcPos) P[H1 * 4 * DQ + e] = s->accb1[e];
+  float* PW2 = P + H1 * 4 * DQ + H1;
+  for (int e = t; e < H2 * H1; e += kTcPos) {
+    const int m = e / H1, j = e - m * H1;
+    PW2[e] = s->accW2T[j][m];
+  }
+  for (int e = t; e < H2; e += kTcPos) {
+    PW2[H2 * H1 + e] = s->accb2[e];
+    PW2[H2 * H1 + H2 + e] = s->accW3[e];
+  }
+  if (t == 0) PW2[H2 * H1 + 2 * H2] = s->accb3;
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
+template <int DQ, int H1, int H2>
+static int din_bwd_tc_launch(const float* q, int64_t qs, const float* keys, int64_t ksb, int64_t ksl, const int32_t* lens,
+                             int64_t B, int L, const float* W1, const float* b1, const float* W2, const float* b2,
+                             const float* W3, const float* b3, const float* g_pooled, float* g_q, float* g_keys,
+                             int64_t gksb, int64_t gksl, float* partials, int* n_rows, cudaStream_t st) {
+  const size_t smem = sizeof(DinTcBwdSmem<DQ, H1, H2>) + 1024;
+  PTREC_CUDA(cudaFuncSetAttribute(din_bwd_tc_kernel<DQ, H1, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)((B + kTcBwdGroup - 1) / kTcBwdGroup);
+  din_bwd_tc_kernel<DQ, H1, H2><<<grid, kTcPos, smem, st>>>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3,
+                                                             g_pooled, g_q, g_keys, gksb, gksl, partials);
+  PTREC_LAUNCH_CHECK("din_bwd_tc_kernel");
+  *n_rows = grid;
+  return PTREC_OK;
+}
+
+// backward entry: fills g_q, g_keys and `*n_rows` partial rows of weight gradients (the caller reduces them)
+int din_bwd_tc(const float* q, int64_t qs, const float* keys, int64_t ksb, int64_t ksl, const int32_t* lens, int64_t B,
+               int L, int DQ, int H1, int H2, const float* W1, const float* b1, const float* W2, const float* b2,
+               const float* W3, const float* b3, const float* g_pooled, float* g_q, float* g_keys, int64_t gksb,
+               int64_t gksl, float* partials, int* n_rows, cudaStream_t st) {
+  if (DQ == 32 && H1 == 80 && H2 == 40)
+    return din_bwd_tc_launch<32, 80, 40>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3, g_pooled, g_q, g_keys,
+                                         gksb, gksl, partials, n_rows, st);
+  if (DQ == 32 && H1 == 64 && H2 == 32)
+    return din_bwd_tc_launch<32, 64, 32>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3, g_pooled, g_q, g_keys,
+                                         gksb, gksl, partials, n_rows, st);
+  return PTREC_EUNSUPPORTED;
+}
+
 // entry used by din_attn.cu's dispatcher: PTREC_OK, or PTREC_EUNSUPPORTED when this shape has no tensor-core build
 int din_fwd_tc(const float* q, int64_t qs, const float* keys, int64_t ksb, int64_t ksl, const int32_t* lens, int64_t B,
                int L, int DQ, int H1, int H2, const float* W1, const float* b1, const float* W2, const float* b2,

@@ -88,7 +88,9 @@ class _FusedSparseOptimizer(Optimizer):
             new[:, (len(names) + 1) * D:].zero_()
         p.data = new[:, :D]
         self._interleaved[id(p)] = new
-        self._ptr_cache.clear()
+        # (no cache flush here: the pointer arrays cached per embedding group are keyed by the tables' addresses, so
+        # the group this table belongs to rebuilds its own entry; flushing everything made the FIRST group of a model
+        # with two widths rebuild its arrays one step later — inside the CUDA-graph capture when warmup == 1)
 
     # ---- called by EmbeddingGroup.apply_backward -------------------------------------------------
     def _state_tensors(self, p: torch.Tensor):

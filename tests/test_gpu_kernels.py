@@ -537,12 +537,13 @@ def test_cross_net_autograd_matches_oracle():
 
 
 # ------------------------------------------------------------------------------------------ DIN attention pooling
-@pytest.fixture(params=["simt", "tensor_core"])
+@pytest.fixture(params=["simt", "tensor_core_fwd", "tensor_core_fwd_bwd"])
 def din_build(request):
-    """K4's forward has an fp32 CUDA-core build and a tcgen05 build (fp16 x 2 operand planes): same contract."""
+    """K4 has fp32 CUDA-core kernels and tcgen05 kernels (fp16 x 2 operand planes) for forward and backward: same
+    contract."""
     lib = _lib.load()
     before = lib.ptrec_din_tc_enabled()
-    lib.ptrec_set_din_tc(1 if request.param == "tensor_core" else 0)
+    lib.ptrec_set_din_tc({"simt": 0, "tensor_core_fwd": 1, "tensor_core_fwd_bwd": 3}[request.param])
     yield request.param
     lib.ptrec_set_din_tc(before)
 
