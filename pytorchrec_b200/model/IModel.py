@@ -149,11 +149,18 @@ class IModel(Module, ABC):
 
     @classmethod
     def get_argument_descriptions(cls) -> list:
-        return []
+        """Hyper-parameter metadata in the reference's form (torchrec/model/IModel.py + utils/argument): subclasses
+        extend the list (FunkSVD.py:13-25); ``random_seed`` is the one argument every model takes (IModel.py:37)."""
+        from ..utils.argument import ArgumentDescription
+        return [ArgumentDescription(name="random_seed", type_=int, help_info="seed of torch's generators (set_torch_seed)",
+                                    default_value=2020)]
 
     @classmethod
     def check_argument_values(cls, arguments: Dict[str, Any]) -> None:
-        return None
+        """Validate ``arguments`` (name -> value) against the descriptions; unknown names are left to the caller."""
+        for d in cls.get_argument_descriptions():
+            if d.name in arguments:
+                d.check(arguments[d.name])
 
     def __init__(self, random_seed: int, **kwargs):  # noqa
         set_torch_seed(random_seed)

@@ -28,6 +28,15 @@ def _dense_matrix(dense_columns: List[NumericColumn], data: Dict[str, Tensor]) -
 
 
 class FM(IModel):
+    @classmethod
+    def get_argument_descriptions(cls) -> list:
+        from ..utils.argument import ArgumentDescription
+        descriptions = super().get_argument_descriptions()
+        descriptions.extend([
+            ArgumentDescription(name="emb_size", type_=int, help_info="embedding dimension (1, 2 or a multiple of 4 up to 128)", default_value=16, lower_closed_bound=1, upper_closed_bound=128)
+        ])
+        return descriptions
+
     def __init__(self, sparse_columns: List[CategoricalColumnWithIdentity], dense_columns: List[NumericColumn],
                  label_column: CategoricalColumnWithIdentity, emb_size: int, table_device=None, **kwargs):
         # table_device: build the tables directly on that device (skips the CPU init of multi-GB
@@ -81,6 +90,15 @@ class FM(IModel):
 
 
 class DeepFM(FM):
+    @classmethod
+    def get_argument_descriptions(cls) -> list:
+        from ..utils.argument import ArgumentDescription
+        descriptions = super().get_argument_descriptions()
+        descriptions.extend([
+            ArgumentDescription(name="dropout", type_=float, help_info="dropout of the dense tower", default_value=0.0, lower_closed_bound=0.0, upper_open_bound=1.0)
+        ])
+        return descriptions
+
     def __init__(self, sparse_columns, dense_columns, label_column, emb_size: int, layers: List[int],
                  dropout: float = 0.0, table_device=None, **kwargs):
         self.layers = list(layers)
@@ -110,6 +128,17 @@ class DCN(IModel):
     """DCN-v2 (parallel structure): ``y = Linear(concat(CrossNet(x0), MLP(x0)))``, ``x0 = concat_f v_f || x_dense``.
     Cross layers run in bf16 on tensor cores (tolerance 1e-2 vs the fp32 oracle twin); the deep tower and the
     embedding path stay fp32."""
+
+    @classmethod
+    def get_argument_descriptions(cls) -> list:
+        from ..utils.argument import ArgumentDescription
+        descriptions = super().get_argument_descriptions()
+        descriptions.extend([
+            ArgumentDescription(name="emb_size", type_=int, help_info="embedding dimension (1, 2 or a multiple of 4 up to 128)", default_value=16, lower_closed_bound=1, upper_closed_bound=128),
+            ArgumentDescription(name="cross_layers", type_=int, help_info="number of DCN-v2 cross layers", default_value=3, lower_closed_bound=1),
+            ArgumentDescription(name="dropout", type_=float, help_info="dropout of the dense tower", default_value=0.0, lower_closed_bound=0.0, upper_open_bound=1.0)
+        ])
+        return descriptions
 
     def __init__(self, sparse_columns: List[CategoricalColumnWithIdentity], dense_columns: List[NumericColumn],
                  label_column: CategoricalColumnWithIdentity, emb_size: int, cross_layers: int, layers: List[int],
@@ -148,6 +177,16 @@ class DIN(IModel):
     go through ONE fused lookup per step (so each table sees one sort / dedup / update), the query is
     ``[item(cand) || cate(cand)]`` and the keys ``[item(h_l) || cate(h_l)]``.
         y = Linear(MLP([user || q || sum_{l<len} a_l k_l]))"""
+
+    @classmethod
+    def get_argument_descriptions(cls) -> list:
+        from ..utils.argument import ArgumentDescription
+        descriptions = super().get_argument_descriptions()
+        descriptions.extend([
+            ArgumentDescription(name="emb_size", type_=int, help_info="embedding dimension (1, 2 or a multiple of 4 up to 128)", default_value=16, lower_closed_bound=1, upper_closed_bound=128),
+            ArgumentDescription(name="dropout", type_=float, help_info="dropout of the dense tower", default_value=0.0, lower_closed_bound=0.0, upper_open_bound=1.0)
+        ])
+        return descriptions
 
     def __init__(self, uid_column, iid_column, cid_column, his_iid_column, his_cid_column, his_len_column, label_column,
                  emb_size: int, layers: List[int], attention_hidden=(80, 40), dropout: float = 0.0, table_device=None,

@@ -24,6 +24,15 @@ def _candidate_target(prediction: Tensor) -> Tensor:
 
 
 class FunkSVD(IModel):
+    @classmethod
+    def get_argument_descriptions(cls) -> list:
+        from ..utils.argument import ArgumentDescription
+        descriptions = super().get_argument_descriptions()
+        descriptions.extend([
+            ArgumentDescription(name="emb_size", type_=int, help_info="embedding dimension", default_value=64, lower_closed_bound=1)
+        ])
+        return descriptions
+
     def __init__(self, uid_column: CategoricalColumnWithIdentity, iid_column: CategoricalColumnWithIdentity,
                  label_column: CategoricalColumnWithIdentity, emb_size: int, **kwargs):
         self.uid_column = uid_column
@@ -53,6 +62,15 @@ class FunkSVD(IModel):
 
 
 class SVDPP(IModel):
+    @classmethod
+    def get_argument_descriptions(cls) -> list:
+        from ..utils.argument import ArgumentDescription
+        descriptions = super().get_argument_descriptions()
+        descriptions.extend([
+            ArgumentDescription(name="emb_size", type_=int, help_info="embedding dimension", default_value=64, lower_closed_bound=1)
+        ])
+        return descriptions
+
     def __init__(self, random_seed: int, uid_column: CategoricalColumnWithIdentity,
                  iid_column: CategoricalColumnWithIdentity, iids_column: CategoricalColumnWithIdentity,
                  label_column: CategoricalColumnWithIdentity, emb_size: int):
@@ -95,6 +113,16 @@ class NCF(IModel):
     """Neural collaborative filtering (torchrec/model/NCF.py:38-79): GMF branch ``mf_u * mf_i`` beside
     ``MLP([mlp_u, mlp_i])``, ``Linear(emb + layers[-1], 1, bias=False)`` on their concatenation.  ``iid`` is
     ``[B, N]`` (candidates; N = 2 for pair-wise training) and the user is repeated over the candidates."""
+
+    @classmethod
+    def get_argument_descriptions(cls) -> list:
+        from ..utils.argument import ArgumentDescription
+        descriptions = super().get_argument_descriptions()
+        descriptions.extend([
+            ArgumentDescription(name="emb_size", type_=int, help_info="embedding dimension", default_value=64, lower_closed_bound=1),
+            ArgumentDescription(name="dropout", type_=float, help_info="dropout of the dense tower", default_value=0.0, lower_closed_bound=0.0, upper_open_bound=1.0)
+        ])
+        return descriptions
 
     def __init__(self, random_seed: int, uid_column: CategoricalColumnWithIdentity,
                  iid_column: CategoricalColumnWithIdentity, label_column: CategoricalColumnWithIdentity,
