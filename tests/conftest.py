@@ -79,7 +79,12 @@ def assert_as_exact_as_the_oracle(name, a, b32, b64, rtol=1e-5, atol=1e-7, slack
       gradient here is a cancelling sum over >= 256 terms (the batch for a dense weight; the hidden units of the
       tower behind an embedding row), where sum_i |g_i| ~ sqrt(n) |sum_i g_i|, so 16 x grad_rtol x the tensor's RMS
       gradient is a lower bound of that allowance.  Never more than the 2 * lr * steps a sign flip costs; elements
-      without gradient (sum64 == 0) must not move at all.
+      without gradient (sum64 == 0) must not move at all.  The network itself is discontinuous too: a ReLU whose
+      pre-activation is ~0 is on in one arithmetic and off in another, which changes one sample's whole gradient by a
+      finite amount — it strikes the fp32 CPU oracle exactly as it strikes the CUDA path (profiles/
+      r2_diag_cfg2_grad.txt: per-sample error of dL/dv against fp64, median 5.7e-5 and maximum 8.3e-3 for BOTH), on
+      different samples.  Elements beyond the bound are therefore tolerated only in the number the fp32 oracle itself
+      shows (x 3), or 1e-4 of the tensor, whichever is larger — and never beyond the sign-flip cap.
     * otherwise: the CUDA result must be as close to the exact result as the reference's own fp32 arithmetic is — at
       the median and the 90th / 99th / 99.9th percentile |a - b64| <= slack * |b32 - b64| + tolerance, and at the
       maximum with ``max_slack`` (the largest of millions of heavy-tailed errors is a noisy statistic).
@@ -98,10 +103,13 @@ def assert_as_exact_as_the_oracle(name, a, b32, b64, rtol=1e-5, atol=1e-7, slack
         g_rms = np.sqrt(sum64.mean() / steps)            # the tensor's RMS gradient
         amp = np.minimum(lr * steps * 16.0 * grad_rtol * g_rms / (g_elem + 1e-30), 2.0 * lr * steps)
         bound = np.where(sum64 > 0, amp, 0.0) + rtol * np.abs(b64) + atol
-        bad = e_p > bound
-        assert not bad.any(), (f"{name}: {int(bad.sum())} of {bad.size} elements exceed what a {grad_rtol:g} gradient error "
-                               f"can cause through Adagrad; worst {e_p[bad].max():.3e} against a bound of "
-                               f"{bound[bad][np.argmax(e_p[bad])]:.3e}")
+        bad, bad_ref = e_p > bound, e_r > bound
+        allowed = max(3 * int(bad_ref.sum()), int(1e-4 * bad.size))
+        cap = np.where(sum64 > 0, 2.0 * lr * steps, 0.0) + rtol * np.abs(b64) + atol
+        assert int(bad.sum()) <= allowed and not (e_p > cap).any(), (
+            f"{name}: {int(bad.sum())} of {bad.size} elements exceed what a {grad_rtol:g} gradient error can cause through "
+            f"Adagrad (the fp32 oracle itself: {int(bad_ref.sum())}; allowed {allowed}); worst {e_p[bad].max():.3e} against a "
+            f"bound of {bound[bad][np.argmax(e_p[bad])]:.3e}")
         return
     floor = float(tol.max())
     for q in (0.5, 0.9, 0.99, 0.999, 1.0):
