@@ -243,8 +243,8 @@ class IModel(Module, ABC):
         # reference builds the optimizer first and compiles second (RepeatTask.py:96), so follow the parameters
         for p_, st in optimizer.state.items():
             if torch.is_tensor(p_):
-                for k, v in st.items():
-                    if torch.is_tensor(v) and v.dim() > 0 and v.device != p_.device:
+                for k, v in st.items():  # ("step" counters stay where the optimizer put them: host tensors by default)
+                    if torch.is_tensor(v) and k != "step" and v.device != p_.device:
                         st[k] = v.to(p_.device)
         self._is_compiled = True
 

@@ -44,7 +44,7 @@ def low_cardinality_and_overflow(rank, world, dev):
     shard.load_full_state_dict(full.state_dict())
     full.compile(SparseAdagrad(full.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)
     shard.compile(SparseAdagrad(shard.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], dev)
-    shard.enable_cuda_graph(True, warmup=1)
+    shard.enable_cuda_graph(True, warmup=2)  # pull mode re-exchanges its pointers in step 2 (tables re-housed in step 1)
 
     def batch(step, hot=False):
         rng = np.random.default_rng(2000 + step)
@@ -66,21 +66,25 @@ def low_cardinality_and_overflow(rank, world, dev):
     for k, v in full.state_dict().items():
         np.testing.assert_allclose(gathered[k].numpy(), v.cpu().numpy(), rtol=0, atol=3e-4, err_msg=k)
 
-    # (2) force an overflow: lists far below one owner's share, every id of the batch identical
+    # (2) force an overflow: lists far below the fullest owner's share (the one-category column sends its whole batch
+    # to one owner).  The sticky word reaches the host through pinned memory: a train_step within the next few steps
+    # raises (eager or replayed graph alike), and check_errors raises too.
     shard.sharded.owner_share, shard.sharded.capacity_factor = 1.0 / world, 0.25
     assert shard.sharded.capacity(B) < B
     shard._graphed.entries.clear()  # new capacity = new buffers: re-warm and re-capture
-    for step in range(3):
-        shard.train_step(batch(10 + step)[1])
-    torch.cuda.synchronize()
-    shard.sharded.poll_errors()      # nothing overflowed so far
-    shard.train_step(batch(20, hot=True)[1])  # a replayed graph: rows[3] -> every lookup hits id 1 -> owner 1 % world
-    torch.cuda.synchronize()
-    try:
-        shard.train_step(batch(21)[1])
-        raise AssertionError("an overflowed exchange list must be fatal")
-    except RuntimeError as e:
-        assert "overflowed" in str(e), e
+    raised = False
+    for step in range(4):
+        try:
+            shard.train_step(batch(10 + step)[1])
+        except RuntimeError as e:
+            assert "overflowed" in str(e), e
+            raised = True
+            break
+        torch.cuda.synchronize()
+    assert raised, "an overflowed exchange list must be fatal"
+    flags = torch.tensor([1.0 if raised else 0.0], device=dev)
+    dist.all_reduce(flags)               # every rank saw it (each packs the same one-category column)
+    assert flags.item() == world
     try:
         shard.sharded.check_errors()
         raise AssertionError("check_errors must raise too")
