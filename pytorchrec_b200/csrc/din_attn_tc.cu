@@ -440,7 +440,7 @@ struct DinTcBwdSmem {
   float wpart[4][H2P + 1];               // per-warp partial column sums (grad W3)
   float bpart[4];
   float accb3;
-  float mx[4];
+  float mx[8];
   float b3;
   float s_w2;
   alignas(8) uint64_t bar[4];
@@ -463,8 +463,28 @@ __device__ __forceinline__ void umma3(uint32_t tD, uint32_t tC, uint64_t a0, uin
   umma_bf16(tD, a0, b0, idesc, acc);
 }
 
+// Thread layout of the backward: 256 threads = two TEAMS of 128.  Thread (team, r) works on position r (TMEM lane r:
+// warps w and w + 4 share a lane quadrant) and on the 16-column chunks of every epilogue whose index has the team's
+// parity, so each epilogue's work is halved per thread and every scheduler has two warps to interleave (one 4-warp
+// team left the tensor core and the LSU idle behind a single dependent instruction stream: 26 us per tile, IPC 0.13,
+// profiles/r2_ncu_full_din_tc_raw.csv).  Row-level scalars (the tile maxima, a_l, <g_pooled, k_l>) are combined
+// through shared memory in a fixed order.
+constexpr int kTcBwdThreads = 2 * kTcPos;
+
+__device__ __forceinline__ float block_max_256(float v, float* s_red) {  // 8 warps; s_red: 8 floats; all threads call
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float m = s_red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, s_red[i]);
+  return m;
+}
+
 template <int DQ, int H1, int H2>
-__global__ void __launch_bounds__(kTcPos, 1)
+__global__ void __launch_bounds__(kTcBwdThreads, 1)
 din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __restrict__ keys, int64_t ksb, int64_t ksl,
                   const int32_t* __restrict__ lens, int64_t B, int L, const float* __restrict__ W1,
                   const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
@@ -473,37 +493,36 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
                   float* __restrict__ partials) {
   using S = DinTcBwdSmem<DQ, H1, H2>;
   constexpr int H2P = S::H2P, DQE = S::DQE, H1E = S::H1E;
-  static_assert(DQ % 16 == 0 && H1 % 16 == 0 && H1E <= 128 && H1 + 1 <= kTcPos, "MMA shape constraints");
-  // TMEM columns: region X = [0, 2 H1) holds (D1 | C1), then (D3 | C3), then (D5 | C5); region Y = [2 H1, 2 H1 + 2 H2P)
-  // holds (D2 | C2), then (D4 | C4), then (D6 | C6)
+  static_assert(DQ == 32 && H1 % 16 == 0 && H1E <= 128 && H1 + 1 <= kTcPos, "MMA shape / team split constraints");
   constexpr uint32_t kTmemCols = 256;
   static_assert(2 * H1 + 2 * H2P <= kTmemCols && 2 * DQE <= 2 * H1 && 2 * DQ <= 2 * H2P, "accumulators exceed TMEM");
   extern __shared__ unsigned char smem_raw[];
   S* s = reinterpret_cast<S*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int team = t >> 7, r = t & (kTcPos - 1);
   constexpr uint32_t kSboK = (DQE / 8) * 128, kSboM = (DQ / 8) * 128, kSboH = (H1E / 8) * 128, kSboW = (H1E / 8) * 128,
                      kSboG = (H2P / 8) * 128;
 
   // ---- once per CTA --------------------------------------------------------------------------------------------------
-  for (int e = t; e < H1; e += kTcPos) {
+  for (int e = t; e < H1; e += kTcBwdThreads) {
     s->b1[e] = b1[e];
     s->accb1[e] = 0.f;
   }
-  for (int e = t; e < H2P; e += kTcPos) {
+  for (int e = t; e < H2P; e += kTcBwdThreads) {
     s->b2[e] = e < H2 ? b2[e] : 0.f;
     s->W3[e] = e < H2 ? W3[e] : 0.f;
     s->accb2[e] = 0.f;
     s->accW3[e] = 0.f;
   }
-  for (int e = t; e < H1 * (DQ + 1); e += kTcPos) {
+  for (int e = t; e < H1 * (DQ + 1); e += kTcBwdThreads) {
     (&s->accWkd[0][0])[e] = 0.f;
     (&s->accW1p[0][0])[e] = 0.f;
     (&s->accWq[0][0])[e] = 0.f;
   }
-  for (int e = t; e < H1 * (H2P + 1); e += kTcPos) (&s->accW2T[0][0])[e] = 0.f;
+  for (int e = t; e < H1 * (H2P + 1); e += kTcBwdThreads) (&s->accW2T[0][0])[e] = 0.f;
   float wmax = 0.f;
-  for (int e = t; e < H2 * H1; e += kTcPos) wmax = fmaxf(wmax, fabsf(W2[e]));
-  wmax = block_max_128(wmax, s->mx);
+  for (int e = t; e < H2 * H1; e += kTcBwdThreads) wmax = fmaxf(wmax, fabsf(W2[e]));
+  wmax = block_max_256(wmax, s->mx);
   const float sw2 = h2_scale(wmax);
   if (t == 0) {
     s->b3 = b3[0];
@@ -512,7 +531,7 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
     for (int i = 0; i < 4; ++i) mbar_init(&s->bar[i], 1);
     fence_mbar_init();
   }
-  for (int ch = t; ch < H2P * (H1E / 8); ch += kTcPos) {  // W2 planes [H2P rows m][H1E columns j], zero padded
+  for (int ch = t; ch < H2P * (H1E / 8); ch += kTcBwdThreads) {  // W2 planes [H2P rows m][H1E columns j], zero padded
     const int mrow = ch / (H1E / 8), cj = ch - mrow * (H1E / 8);
     float x[8];
 #pragma unroll
@@ -531,16 +550,17 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
   tcgen05_fence_after();
   const uint32_t tmem = s->tmem_slot;
   const uint32_t tX = tmem, tY = tmem + 2 * H1;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;  // both teams' warps of a quadrant read the same lanes
   constexpr uint32_t kM = (uint32_t)(kTcPos >> 4) << 24, kF = 1u << 4, kAmn = 1u << 15, kBmn = 1u << 16;
-  constexpr uint32_t kI1 = kF | kM | ((uint32_t)(H1 >> 3) << 17);                   // G1: N = H1, K-major / K-major
-  constexpr uint32_t kI2 = kF | kM | ((uint32_t)(H2P >> 3) << 17);                  // G2: N = H2P
-  constexpr uint32_t kI3 = kF | kM | ((uint32_t)(H1 >> 3) << 17) | kBmn;            // G3: N = H1, B MN-major
-  constexpr uint32_t kI4 = kF | kM | ((uint32_t)(H2P >> 3) << 17) | kAmn | kBmn;    // G4: N = H2P, both MN-major
-  constexpr uint32_t kI5 = kF | kM | ((uint32_t)(DQE >> 3) << 17) | kAmn | kBmn;    // G5: N = DQE, both MN-major
-  constexpr uint32_t kI6 = kF | kM | ((uint32_t)(DQ >> 3) << 17) | kBmn;            // G6: N = DQ, B MN-major
+  constexpr uint32_t kI1 = kF | kM | ((uint32_t)(H1 >> 3) << 17);
+  constexpr uint32_t kI2 = kF | kM | ((uint32_t)(H2P >> 3) << 17);
+  constexpr uint32_t kI3 = kF | kM | ((uint32_t)(H1 >> 3) << 17) | kBmn;
+  constexpr uint32_t kI4 = kF | kM | ((uint32_t)(H2P >> 3) << 17) | kAmn | kBmn;
+  constexpr uint32_t kI5 = kF | kM | ((uint32_t)(DQE >> 3) << 17) | kAmn | kBmn;
+  constexpr uint32_t kI6 = kF | kM | ((uint32_t)(DQ >> 3) << 17) | kBmn;
   uint32_t phase = 0;
   const __half one = __float2half_rn(1.f);
+  float* s_pair = &s->kf[0][0];  // [2][kTcPos] per-team row partials (kf is not otherwise used by the backward)
 
   const int64_t b_end = min(B, ((int64_t)blockIdx.x + 1) * kTcBwdGroup);
   for (int64_t b = (int64_t)blockIdx.x * kTcBwdGroup; b < b_end; ++b) {
@@ -551,12 +571,13 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
       s->gp[t] = g_pooled[b * DQ + t];
     }
     __syncthreads();
-    // ---- M_b planes and c_b (as in the forward) ----------------------------------------------------------------------
-    float mv[(H1 * DQ / 8 + kTcPos - 1) / kTcPos][8];
+    // ---- M_b planes and c_b ------------------------------------------------------------------------------------------
+    constexpr int kMCh = (H1 * DQ / 8 + kTcBwdThreads - 1) / kTcBwdThreads;
+    float mv[kMCh][8];
     float mmax = 0.f;
 #pragma unroll
-    for (int r = 0; r < (H1 * DQ / 8 + kTcPos - 1) / kTcPos; ++r) {
-      const int ch = t + r * kTcPos;
+    for (int rr = 0; rr < kMCh; ++rr) {
+      const int ch = t + rr * kTcBwdThreads;
       if (ch < H1 * DQ / 8) {
         const int j = ch / (DQ / 8), ci = ch - j * (DQ / 8);
         const float* row = W1 + (int64_t)j * 4 * DQ + ci * 8;
@@ -566,13 +587,13 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
           const float4 wd = __ldg(reinterpret_cast<const float4*>(row + 2 * DQ + 4 * h));
           const float4 wp = __ldg(reinterpret_cast<const float4*>(row + 3 * DQ + 4 * h));
           const float* qq = &s->q[ci * 8 + 4 * h];
-          mv[r][4 * h + 0] = (wk.x - wd.x) + wp.x * qq[0];
-          mv[r][4 * h + 1] = (wk.y - wd.y) + wp.y * qq[1];
-          mv[r][4 * h + 2] = (wk.z - wd.z) + wp.z * qq[2];
-          mv[r][4 * h + 3] = (wk.w - wd.w) + wp.w * qq[3];
+          mv[rr][4 * h + 0] = (wk.x - wd.x) + wp.x * qq[0];
+          mv[rr][4 * h + 1] = (wk.y - wd.y) + wp.y * qq[1];
+          mv[rr][4 * h + 2] = (wk.z - wd.z) + wp.z * qq[2];
+          mv[rr][4 * h + 3] = (wk.w - wd.w) + wp.w * qq[3];
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mmax = fmaxf(mmax, fabsf(mv[r][i]));
+        for (int i = 0; i < 8; ++i) mmax = fmaxf(mmax, fabsf(mv[rr][i]));
       }
     }
     if (t < H1) {
@@ -587,16 +608,16 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
       }
       s->c[t] = acc;
     }
-    mmax = block_max_128(mmax, s->mx);
+    mmax = block_max_256(mmax, s->mx);
     const float sm = h2_scale(mmax);
 #pragma unroll
-    for (int r = 0; r < (H1 * DQ / 8 + kTcPos - 1) / kTcPos; ++r) {
-      const int ch = t + r * kTcPos;
+    for (int rr = 0; rr < kMCh; ++rr) {
+      const int ch = t + rr * kTcBwdThreads;
       if (ch < H1 * DQ / 8) {
         const int j = ch / (DQ / 8), ci = ch - j * (DQ / 8);
         float x[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = mv[r][i] * sm;
+        for (int i = 0; i < 8; ++i) x[i] = mv[rr][i] * sm;
         const uint32_t off = (uint32_t)(j >> 3) * kSboM + ci * 128 + (j & 7) * 16;
         h2_split8(x, reinterpret_cast<uint4*>(s->m[0] + off), reinterpret_cast<uint4*>(s->m[1] + off));
       }
@@ -604,49 +625,52 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
     float gq_acc = 0.f;  // thread i < DQ: grad q[i], summed over the tiles
     for (int l0 = 0; l0 < max(len, 1); l0 += kTcPos) {
       const int n = max(0, min(kTcPos, len - l0));
-      const bool live = t < n;
-      // ---- Ke planes: this thread's key row | 1 | 0 ... ----------------------------------------------------------------
-      float kk[DQ];
-      float kmax = 0.f;
+      const bool live = r < n;
+      // ---- Ke planes: team 0 formats columns [0, 16), team 1 columns [16, 32) and the ones / zero chunks ---------------
+      constexpr int kHalf = DQ / 2;
+      float kk[kHalf];
+      float kmax = 0.f, gpart = 0.f;
       if (live) {
-        const float* kp = keys + b * ksb + (int64_t)(l0 + t) * ksl;
+        const float* kp = keys + b * ksb + (int64_t)(l0 + r) * ksl + team * kHalf;
 #pragma unroll
-        for (int x = 0; x < DQ; x += 4) {
+        for (int x = 0; x < kHalf; x += 4) {
           const float4 v = ldg_stream_f4(kp + x);
           kk[x] = v.x; kk[x + 1] = v.y; kk[x + 2] = v.z; kk[x + 3] = v.w;
         }
       } else {
 #pragma unroll
-        for (int x = 0; x < DQ; ++x) kk[x] = 0.f;
+        for (int x = 0; x < kHalf; ++x) kk[x] = 0.f;
       }
-      float ga = 0.f;  // d loss / d a_l = <g_pooled, k_l>
 #pragma unroll
-      for (int x = 0; x < DQ; ++x) {
+      for (int x = 0; x < kHalf; ++x) {
         kmax = fmaxf(kmax, fabsf(kk[x]));
-        s->kf[t][x] = kk[x];
-        ga += s->gp[x] * kk[x];
+        gpart += s->gp[team * kHalf + x] * kk[x];
       }
-      kmax = block_max_128(kmax, s->mx);
+      s_pair[team * kTcPos + r] = gpart;
+      kmax = block_max_256(kmax, s->mx);  // (its barriers also publish s_pair)
+      const float ga_raw = s_pair[r] + s_pair[kTcPos + r];  // d loss / d a_l = <g_pooled, k_l>, same order in both teams
       const float sk = h2_scale(kmax);
       {
-        const uint32_t rowoff = (uint32_t)(t >> 3) * kSboK + (t & 7) * 16;
+        const uint32_t rowoff = (uint32_t)(r >> 3) * kSboK + (r & 7) * 16;
 #pragma unroll
-        for (int ci = 0; ci < DQ / 8; ++ci) {
+        for (int ci = 0; ci < kHalf / 8; ++ci) {
           float x[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) x[i] = kk[ci * 8 + i] * sk;
-          h2_split8(x, reinterpret_cast<uint4*>(s->k[0] + rowoff + ci * 128), reinterpret_cast<uint4*>(s->k[1] + rowoff + ci * 128));
+          const uint32_t o = rowoff + (team * (kHalf / 8) + ci) * 128;
+          h2_split8(x, reinterpret_cast<uint4*>(s->k[0] + o), reinterpret_cast<uint4*>(s->k[1] + o));
         }
-        // columns DQ .. DQE: the ones column (unscaled, rows of live positions only), then zeros
-        __half ext[8];
+        if (team == 1) {  // columns DQ .. DQE: the ones column (unscaled, live positions only), then zeros
+          __half ext[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ext[i] = __float2half_rn(0.f);
-        const uint4 zero = *reinterpret_cast<const uint4*>(ext);
-        ext[0] = live ? one : ext[0];
-        *reinterpret_cast<uint4*>(s->k[0] + rowoff + (DQ / 8) * 128) = *reinterpret_cast<const uint4*>(ext);
-        *reinterpret_cast<uint4*>(s->k[1] + rowoff + (DQ / 8) * 128) = zero;
-        *reinterpret_cast<uint4*>(s->k[0] + rowoff + (DQ / 8 + 1) * 128) = zero;
-        *reinterpret_cast<uint4*>(s->k[1] + rowoff + (DQ / 8 + 1) * 128) = zero;
+          for (int i = 0; i < 8; ++i) ext[i] = __float2half_rn(0.f);
+          const uint4 zero = *reinterpret_cast<const uint4*>(ext);
+          ext[0] = live ? one : ext[0];
+          *reinterpret_cast<uint4*>(s->k[0] + rowoff + (DQ / 8) * 128) = *reinterpret_cast<const uint4*>(ext);
+          *reinterpret_cast<uint4*>(s->k[1] + rowoff + (DQ / 8) * 128) = zero;
+          *reinterpret_cast<uint4*>(s->k[0] + rowoff + (DQ / 8 + 1) * 128) = zero;
+          *reinterpret_cast<uint4*>(s->k[1] + rowoff + (DQ / 8 + 1) * 128) = zero;
+        }
       }
       fence_proxy_async();
       tcgen05_fence_before();
@@ -662,26 +686,28 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
       }
       mbar_wait(&s->bar[0], phase);
       tcgen05_fence_after();
-      // ---- epilogue 1: h1 -> H1e planes; keep the ReLU mask of this position -------------------------------------------
+      // ---- epilogue 1: h1 -> H1e planes (this team's chunks); ReLU mask bits of those chunks ---------------------------
       const float inv1 = 1.f / (sk * sm);
       float hmax = 0.f;
 #pragma unroll
       for (int c0 = 0; c0 < H1; c0 += 16) {
+        if (((c0 >> 4) & 1) != team) continue;
         float dm[16], dc[16];
         tmem_ld16x2(tX + lane_base + c0, tX + H1 + lane_base + c0, dm, dc);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           hmax = fmaxf(hmax, live ? (dm[i] + dc[i] * (1.f / 2048.f)) * inv1 + s->c[c0 + i] : 0.f);
       }
-      hmax = block_max_128(hmax, s->mx);
+      hmax = block_max_256(hmax, s->mx);
       const float sh = h2_scale(hmax);
       uint32_t mask1[(H1 + 31) / 32];
 #pragma unroll
       for (int w = 0; w < (H1 + 31) / 32; ++w) mask1[w] = 0u;
       {
-        const uint32_t rowoff = (uint32_t)(t >> 3) * kSboH + (t & 7) * 16;
+        const uint32_t rowoff = (uint32_t)(r >> 3) * kSboH + (r & 7) * 16;
 #pragma unroll
         for (int c0 = 0; c0 < H1; c0 += 16) {
+          if (((c0 >> 4) & 1) != team) continue;
           float dm[16], dc[16], x[16];
           tmem_ld16x2(tX + lane_base + c0, tX + H1 + lane_base + c0, dm, dc);
 #pragma unroll
@@ -695,20 +721,22 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
           h2_split8(x + 8, reinterpret_cast<uint4*>(s->h1[0] + rowoff + (c0 / 8 + 1) * 128),
                     reinterpret_cast<uint4*>(s->h1[1] + rowoff + (c0 / 8 + 1) * 128));
         }
-        __half ext[8];
+        if (team == 1) {
+          __half ext[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ext[i] = __float2half_rn(0.f);
-        const uint4 zero = *reinterpret_cast<const uint4*>(ext);
-        ext[0] = live ? one : ext[0];
-        *reinterpret_cast<uint4*>(s->h1[0] + rowoff + (H1 / 8) * 128) = *reinterpret_cast<const uint4*>(ext);
-        *reinterpret_cast<uint4*>(s->h1[1] + rowoff + (H1 / 8) * 128) = zero;
-        *reinterpret_cast<uint4*>(s->h1[0] + rowoff + (H1 / 8 + 1) * 128) = zero;
-        *reinterpret_cast<uint4*>(s->h1[1] + rowoff + (H1 / 8 + 1) * 128) = zero;
+          for (int i = 0; i < 8; ++i) ext[i] = __float2half_rn(0.f);
+          const uint4 zero = *reinterpret_cast<const uint4*>(ext);
+          ext[0] = live ? one : ext[0];
+          *reinterpret_cast<uint4*>(s->h1[0] + rowoff + (H1 / 8) * 128) = *reinterpret_cast<const uint4*>(ext);
+          *reinterpret_cast<uint4*>(s->h1[1] + rowoff + (H1 / 8) * 128) = zero;
+          *reinterpret_cast<uint4*>(s->h1[0] + rowoff + (H1 / 8 + 1) * 128) = zero;
+          *reinterpret_cast<uint4*>(s->h1[1] + rowoff + (H1 / 8 + 1) * 128) = zero;
+        }
       }
       fence_proxy_async();
       tcgen05_fence_before();
       __syncthreads();
-      if (t == 0) {  // G2 (the ones column meets zero columns of the W2 planes)
+      if (t == 0) {  // G2
         tcgen05_fence_after();
 #pragma unroll
         for (int ks = 0; ks < H1 / 16; ++ks)
@@ -719,70 +747,94 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
       }
       mbar_wait(&s->bar[1], phase);
       tcgen05_fence_after();
-      // ---- epilogue 2: a_l, dH2 planes, grad W3 / b3 (column sums over the positions: warp tree, then the warps in order)
+      // ---- epilogue 2: a_l (two partial sums, team 0 first), dH2 planes, grad W3 / b3 ----------------------------------
       const float inv2 = 1.f / (sh * s->s_w2);
-      float a = s->b3;
+      const float ga = live ? ga_raw : 0.f;
+      float apart = 0.f;
       float gmax = 0.f;
-      float dh2[H2P];
-      float gw3[H2P];
+      constexpr int kC2 = (H2P / 16 + 1) / 2;  // chunks of H2P a team can own
+      float dh2[kC2][16];
+      float gw3[kC2][16];
 #pragma unroll
-      for (int c0 = 0; c0 < H2P; c0 += 16) {
-        float dm[16], dc[16];
-        tmem_ld16x2(tY + lane_base + c0, tY + H2P + lane_base + c0, dm, dc);
+      for (int cc = 0; cc < kC2; ++cc) {
+        const int c0 = (2 * cc + team) * 16;
+        if (c0 < H2P) {
+          float dm[16], dc[16];
+          tmem_ld16x2(tY + lane_base + c0, tY + H2P + lane_base + c0, dm, dc);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float pre = (dm[i] + dc[i] * (1.f / 2048.f)) * inv2 + s->b2[c0 + i];
-          const float r = fmaxf(pre, 0.f);
-          a += s->W3[c0 + i] * r;
-          dh2[c0 + i] = (live && pre > 0.f) ? ga * s->W3[c0 + i] : 0.f;
-          gw3[c0 + i] = live ? ga * r : 0.f;
-          gmax = fmaxf(gmax, fabsf(dh2[c0 + i]));
+          for (int i = 0; i < 16; ++i) {
+            const float pre = (dm[i] + dc[i] * (1.f / 2048.f)) * inv2 + s->b2[c0 + i];
+            const float rl = fmaxf(pre, 0.f);
+            apart += s->W3[c0 + i] * rl;
+            dh2[cc][i] = (live && pre > 0.f) ? ga * s->W3[c0 + i] : 0.f;
+            gw3[cc][i] = ga * rl;
+            gmax = fmaxf(gmax, fabsf(dh2[cc][i]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dh2[cc][i] = gw3[cc][i] = 0.f;
         }
       }
-      if (!live) { a = 0.f; ga = 0.f; }
-      gmax = block_max_128(gmax, s->mx);
+      s_pair[team * kTcPos + r] = apart;
+      gmax = block_max_256(gmax, s->mx);  // (its barriers also publish s_pair)
+      const float a = live ? s->b3 + s_pair[r] + s_pair[kTcPos + r] : 0.f;
       const float sg2 = h2_scale(gmax);
       {
-        const uint32_t rowoff = (uint32_t)(t >> 3) * kSboG + (t & 7) * 16;
+        const uint32_t rowoff = (uint32_t)(r >> 3) * kSboG + (r & 7) * 16;
 #pragma unroll
-        for (int cj = 0; cj < H2P / 8; ++cj) {
-          float x[8];
+        for (int cc = 0; cc < kC2; ++cc) {
+          const int c0 = (2 * cc + team) * 16;
+          if (c0 < H2P) {
+            float x[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = dh2[cj * 8 + i] * sg2;
-          h2_split8(x, reinterpret_cast<uint4*>(s->dh2[0] + rowoff + cj * 128), reinterpret_cast<uint4*>(s->dh2[1] + rowoff + cj * 128));
+            for (int i = 0; i < 16; ++i) x[i] = dh2[cc][i] * sg2;
+            h2_split8(x, reinterpret_cast<uint4*>(s->dh2[0] + rowoff + (c0 / 8) * 128), reinterpret_cast<uint4*>(s->dh2[1] + rowoff + (c0 / 8) * 128));
+            h2_split8(x + 8, reinterpret_cast<uint4*>(s->dh2[0] + rowoff + (c0 / 8 + 1) * 128),
+                      reinterpret_cast<uint4*>(s->dh2[1] + rowoff + (c0 / 8 + 1) * 128));
+          }
         }
       }
-      float gb3 = ga;
+      // column sums over the positions: warp tree, then this team's four warps in order (by the column's owner below)
 #pragma unroll
-      for (int m = 0; m < H2P; ++m) {
+      for (int cc = 0; cc < kC2; ++cc) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) gw3[m] += __shfl_xor_sync(0xffffffffu, gw3[m], o);
+        for (int i = 0; i < 16; ++i) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) gw3[cc][i] += __shfl_xor_sync(0xffffffffu, gw3[cc][i], o);
+        }
       }
+      float gb3 = team == 0 ? ga : 0.f;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) gb3 += __shfl_xor_sync(0xffffffffu, gb3, o);
       if (lane == 0) {
 #pragma unroll
-        for (int m = 0; m < H2P; ++m) s->wpart[warp][m] = gw3[m];
-        s->bpart[warp] = gb3;
+        for (int cc = 0; cc < kC2; ++cc) {
+          const int c0 = (2 * cc + team) * 16;
+          if (c0 < H2P) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s->wpart[warp & 3][c0 + i] = gw3[cc][i];
+          }
+        }
+        if (team == 0) s->bpart[warp] = gb3;
       }
       fence_proxy_async();
       tcgen05_fence_before();
       __syncthreads();
-      if (t == 0) {  // G3 into region X, G4 into region Y (both read the dH2 planes; G4 also the H1e planes)
+      if (t == 0) {  // G3 into region X, G4 into region Y
         tcgen05_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < H2P / 16; ++ks)  // reduce over m: dH2 K-major (+256 B), W2 MN-major (2 groups of 8 m-rows)
+        for (int ks = 0; ks < H2P / 16; ++ks)
           umma3(tX, tX + H1, make_nosw_desc(s->dh2[0] + ks * 256, 128, kSboG), make_nosw_desc(s->dh2[1] + ks * 256, 128, kSboG),
                 make_nosw_mn_desc(s->w2[0] + ks * 2 * kSboW, kSboW), make_nosw_mn_desc(s->w2[1] + ks * 2 * kSboW, kSboW),
                 kI3, ks > 0 ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < kTcPos / 16; ++ks)  // reduce over l: both MN-major (2 groups of 8 position rows per step)
+        for (int ks = 0; ks < kTcPos / 16; ++ks)
           umma3(tY, tY + H2P, make_nosw_mn_desc(s->h1[0] + ks * 2 * kSboH, kSboH),
                 make_nosw_mn_desc(s->h1[1] + ks * 2 * kSboH, kSboH), make_nosw_mn_desc(s->dh2[0] + ks * 2 * kSboG, kSboG),
                 make_nosw_mn_desc(s->dh2[1] + ks * 2 * kSboG, kSboG), kI4, ks > 0 ? 1u : 0u);
         umma_commit(&s->bar[2]);
       }
-      if (t < H2) {  // grad W3 / b3 of this tile: the four warps in order (runs while the MMAs do)
+      if (t < H2) {  // grad W3 / b3 of this tile (each column's four warp partials in order); overlaps the MMAs
         s->accW3[t] += ((s->wpart[0][t] + s->wpart[1][t]) + s->wpart[2][t]) + s->wpart[3][t];
       } else if (t == H2P) {
         s->accb3 += ((s->bpart[0] + s->bpart[1]) + s->bpart[2]) + s->bpart[3];
@@ -794,6 +846,7 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
       float g1max = 0.f;
 #pragma unroll
       for (int c0 = 0; c0 < H1; c0 += 16) {
+        if (((c0 >> 4) & 1) != team) continue;
         float dm[16], dc[16];
         tmem_ld16x2(tX + lane_base + c0, tX + H1 + lane_base + c0, dm, dc);
 #pragma unroll
@@ -802,27 +855,29 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
           g1max = fmaxf(g1max, on ? fabsf((dm[i] + dc[i] * (1.f / 2048.f)) * inv3) : 0.f);
         }
       }
-      {  // row t of G4: t < H1 -> grad W2[:, t] of this tile, t == H1 -> grad b2
-        const float inv4 = t < H1 ? 1.f / (sh * sg2) : 1.f / sg2;
+      {  // row r of G4: r < H1 -> grad W2[:, r] of this tile, r == H1 -> grad b2; this team's chunks of the columns
+        const float inv4 = r < H1 ? 1.f / (sh * sg2) : 1.f / sg2;
 #pragma unroll
         for (int c0 = 0; c0 < H2P; c0 += 16) {
+          if (((c0 >> 4) & 1) != team) continue;
           float dm[16], dc[16];
           tmem_ld16x2(tY + lane_base + c0, tY + H2P + lane_base + c0, dm, dc);
-          if (t < H1) {
+          if (r < H1) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) s->accW2T[t][c0 + i] += (dm[i] + dc[i] * (1.f / 2048.f)) * inv4;
-          } else if (t == H1) {
+            for (int i = 0; i < 16; ++i) s->accW2T[r][c0 + i] += (dm[i] + dc[i] * (1.f / 2048.f)) * inv4;
+          } else if (r == H1) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) s->accb2[c0 + i] += (dm[i] + dc[i] * (1.f / 2048.f)) * inv4;
           }
         }
       }
-      g1max = block_max_128(g1max, s->mx);
+      g1max = block_max_256(g1max, s->mx);
       const float sg1 = h2_scale(g1max);
       {
-        const uint32_t rowoff = (uint32_t)(t >> 3) * kSboH + (t & 7) * 16;
+        const uint32_t rowoff = (uint32_t)(r >> 3) * kSboH + (r & 7) * 16;
 #pragma unroll
         for (int c0 = 0; c0 < H1; c0 += 16) {
+          if (((c0 >> 4) & 1) != team) continue;
           float dm[16], dc[16], x[16];
           tmem_ld16x2(tX + lane_base + c0, tX + H1 + lane_base + c0, dm, dc);
 #pragma unroll
@@ -834,11 +889,12 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
           h2_split8(x + 8, reinterpret_cast<uint4*>(s->h1[0] + rowoff + (c0 / 8 + 1) * 128),
                     reinterpret_cast<uint4*>(s->h1[1] + rowoff + (c0 / 8 + 1) * 128));
         }
-        // the ones column of H1e becomes a zero column of the dH1 planes
-        __half ext[8];
+        if (team == 1) {  // the ones column of H1e becomes a zero column of the dH1 planes
+          __half ext[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ext[i] = __float2half_rn(0.f);
-        *reinterpret_cast<uint4*>(s->h1[0] + rowoff + (H1 / 8) * 128) = *reinterpret_cast<const uint4*>(ext);
+          for (int i = 0; i < 8; ++i) ext[i] = __float2half_rn(0.f);
+          *reinterpret_cast<uint4*>(s->h1[0] + rowoff + (H1 / 8) * 128) = *reinterpret_cast<const uint4*>(ext);
+        }
       }
       fence_proxy_async();
       tcgen05_fence_before();
@@ -846,12 +902,12 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
       if (t == 0) {  // G5 into region X, G6 into region Y
         tcgen05_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < kTcPos / 16; ++ks)  // reduce over l: dH1 MN-major, Ke MN-major
+        for (int ks = 0; ks < kTcPos / 16; ++ks)
           umma3(tX, tX + DQE, make_nosw_mn_desc(s->h1[0] + ks * 2 * kSboH, kSboH),
                 make_nosw_mn_desc(s->h1[1] + ks * 2 * kSboH, kSboH), make_nosw_mn_desc(s->k[0] + ks * 2 * kSboK, kSboK),
                 make_nosw_mn_desc(s->k[1] + ks * 2 * kSboK, kSboK), kI5, ks > 0 ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < H1 / 16; ++ks)  // reduce over j: dH1 K-major, M_b MN-major
+        for (int ks = 0; ks < H1 / 16; ++ks)
           umma3(tY, tY + DQ, make_nosw_desc(s->h1[0] + ks * 256, 128, kSboH), make_nosw_desc(s->h1[1] + ks * 256, 128, kSboH),
                 make_nosw_mn_desc(s->m[0] + ks * 2 * kSboM, kSboM), make_nosw_mn_desc(s->m[1] + ks * 2 * kSboM, kSboM),
                 kI6, ks > 0 ? 1u : 0u);
@@ -860,62 +916,60 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
       mbar_wait(&s->bar[3], phase);
       tcgen05_fence_after();
       phase ^= 1u;
-      // ---- epilogue 4: grad keys of this position; row t of G5 -> grads of M_b / c_b -> W1 accumulators, grad q ---------
+      // ---- epilogue 4: grad keys (this team's 16 columns); row r of G5 -> grads of M_b / c_b -> W1 accumulators, grad q -
       {
         const float inv6 = 1.f / (sg1 * sm);
-        float gk[DQ];
+        const int c0 = team * 16;
+        float dm[16], dc[16], gk[16];
+        tmem_ld16x2(tY + lane_base + c0, tY + DQ + lane_base + c0, dm, dc);
 #pragma unroll
-        for (int c0 = 0; c0 < DQ; c0 += 16) {
-          float dm[16], dc[16];
-          tmem_ld16x2(tY + lane_base + c0, tY + DQ + lane_base + c0, dm, dc);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) gk[c0 + i] = (dm[i] + dc[i] * (1.f / 2048.f)) * inv6 + a * s->gp[c0 + i];
-        }
+        for (int i = 0; i < 16; ++i) gk[i] = (dm[i] + dc[i] * (1.f / 2048.f)) * inv6 + a * s->gp[c0 + i];
         if (live) {
-          float* gkp = g_keys + b * gksb + (int64_t)(l0 + t) * gksl;
+          float* gkp = g_keys + b * gksb + (int64_t)(l0 + r) * gksl + c0;
 #pragma unroll
-          for (int x = 0; x < DQ; x += 4) st_f4(gkp + x, make_float4(gk[x], gk[x + 1], gk[x + 2], gk[x + 3]));
+          for (int x = 0; x < 16; x += 4) st_f4(gkp + x, make_float4(gk[x], gk[x + 1], gk[x + 2], gk[x + 3]));
         }
       }
       {
         const float inv5 = 1.f / (sg1 * sk);
-        float dM[DQ];
-        float dcj = 0.f;
+        const int c0 = team * 16;
+        float dm[16], dc[16], em[16], ec[16];
+        tmem_ld16x2(tX + lane_base + c0, tX + DQE + lane_base + c0, dm, dc);
+        tmem_ld16x2(tX + lane_base + DQ, tX + DQE + lane_base + DQ, em, ec);  // the ones column: only dH1's scale
+        const float dcj = (em[0] + ec[0] * (1.f / 2048.f)) / sg1;
+        if (r < H1) {
+          const float* row = W1 + (int64_t)r * 4 * DQ + c0;
+          if (team == 0) s->accb1[r] += dcj;
 #pragma unroll
-        for (int c0 = 0; c0 < DQE; c0 += 16) {
-          float dm[16], dc[16];
-          tmem_ld16x2(tX + lane_base + c0, tX + DQE + lane_base + c0, dm, dc);
-          if (c0 < DQ) {
+          for (int i4 = 0; i4 < 16; i4 += 4) {
+            const float4 wq = __ldg(reinterpret_cast<const float4*>(row + i4));
+            const float4 wd = __ldg(reinterpret_cast<const float4*>(row + 2 * DQ + i4));
+            const float4 wp = __ldg(reinterpret_cast<const float4*>(row + 3 * DQ + i4));
+            const float wqs[4] = {wq.x + wd.x, wq.y + wd.y, wq.z + wd.z, wq.w + wd.w};
+            const float wps[4] = {wp.x, wp.y, wp.z, wp.w};
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dM[c0 + i] = (dm[i] + dc[i] * (1.f / 2048.f)) * inv5;
-          } else {
-            dcj = (dm[0] + dc[0] * (1.f / 2048.f)) / sg1;  // the ones column: only dH1's scale
-          }
-        }
-        if (t < H1) {
-          const float* row = W1 + (int64_t)t * 4 * DQ;
-          s->accb1[t] += dcj;
-#pragma unroll
-          for (int i = 0; i < DQ; ++i) {
-            const float qv = s->q[i];
-            s->accWkd[t][i] += dM[i];
-            s->accW1p[t][i] += dM[i] * qv;
-            s->accWq[t][i] += dcj * qv;
-            // d c / d q = Wq = W1q + W1d ; d M / d q = W1p (column-wise)
-            s->tmp[t][i] = (__ldg(row + i) + __ldg(row + 2 * DQ + i)) * dcj + __ldg(row + 3 * DQ + i) * dM[i];
+            for (int u = 0; u < 4; ++u) {
+              const int i = c0 + i4 + u;
+              const float dMv = (dm[i4 + u] + dc[i4 + u] * (1.f / 2048.f)) * inv5;
+              const float qv = s->q[i];
+              s->accWkd[r][i] += dMv;
+              s->accW1p[r][i] += dMv * qv;
+              s->accWq[r][i] += dcj * qv;
+              s->tmp[r][i] = wqs[u] * dcj + wps[u] * dMv;  // d c / d q = W1q + W1d ; d M / d q = W1p (column-wise)
+            }
           }
         }
       }
       tcgen05_fence_before();
       __syncthreads();
       if (t < DQ) {
-        float r = 0.f;
-        for (int j = 0; j < H1; ++j) r += s->tmp[j][t];
-        gq_acc += r;
+        float rs = 0.f;
+        for (int j = 0; j < H1; ++j) rs += s->tmp[j][t];
+        gq_acc += rs;
       }
     }
     // zero gradient for the padded tail of the history; grad q
-    for (int64_t e = len * (int64_t)DQ + t; e < (int64_t)L * DQ; e += kTcPos) {
+    for (int64_t e = len * (int64_t)DQ + t; e < (int64_t)L * DQ; e += kTcBwdThreads) {
       const int64_t l = e / DQ;
       g_keys[b * gksb + l * gksl + (e - l * DQ)] = 0.f;
     }
@@ -924,7 +978,7 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
   __syncthreads();
   // ---- per-CTA partial weight gradients: [W1 (H1 x 4DQ) | b1 | W2 (H2 x H1) | b2 | W3 | b3] (din_attn.cu's layout) ----------
   float* P = partials + (int64_t)blockIdx.x * (H1 * 4 * DQ + H1 + H2 * H1 + H2 + H2 + 1);
-  for (int e = t; e < H1 * DQ; e += kTcPos) {
+  for (int e = t; e < H1 * DQ; e += kTcBwdThreads) {
     const int j = e / DQ, i = e - j * DQ;
     float* row = P + (int64_t)j * 4 * DQ;
     const float a3 = s->accWq[j][i], a1 = s->accWkd[j][i];
@@ -933,13 +987,13 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
     row[2 * DQ + i] = a3 - a1;   // W1d  (Wq = W1q + W1d, Wkd = W1k - W1d)
     row[3 * DQ + i] = s->accW1p[j][i];
   }
-  for (int e = t; e < H1; e += kTcPos) P[H1 * 4 * DQ + e] = s->accb1[e];
+  for (int e = t; e < H1; e += kTcBwdThreads) P[H1 * 4 * DQ + e] = s->accb1[e];
   float* PW2 = P + H1 * 4 * DQ + H1;
-  for (int e = t; e < H2 * H1; e += kTcPos) {
+  for (int e = t; e < H2 * H1; e += kTcBwdThreads) {
     const int m = e / H1, j = e - m * H1;
     PW2[e] = s->accW2T[j][m];
   }
-  for (int e = t; e < H2; e += kTcPos) {
+  for (int e = t; e < H2; e += kTcBwdThreads) {
     PW2[H2 * H1 + e] = s->accb2[e];
     PW2[H2 * H1 + H2 + e] = s->accW3[e];
   }
@@ -959,7 +1013,7 @@ static int din_bwd_tc_launch(const float* q, int64_t qs, const float* keys, int6
   const size_t smem = sizeof(DinTcBwdSmem<DQ, H1, H2>) + 1024;
   PTREC_CUDA(cudaFuncSetAttribute(din_bwd_tc_kernel<DQ, H1, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)((B + kTcBwdGroup - 1) / kTcBwdGroup);
-  din_bwd_tc_kernel<DQ, H1, H2><<<grid, kTcPos, smem, st>>>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3,
+  din_bwd_tc_kernel<DQ, H1, H2><<<grid, kTcBwdThreads, smem, st>>>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3,
                                                              g_pooled, g_q, g_keys, gksb, gksl, partials);
   PTREC_LAUNCH_CHECK("din_bwd_tc_kernel");
   *n_rows = grid;
