@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 19
+#define PTREC_ABI_VERSION 20
 
 /* error codes */
 #define PTREC_OK 0
@@ -480,6 +480,39 @@ int ptrec_tc_gemm_split2h(const void* a_planes, const float* scale_a, int64_t M,
 int ptrec_tc_gemm_split2h_tn(const void* a_planes, const float* scale_a, int64_t M, int64_t lda, const void* b_planes,
                              const float* scale_b, int64_t N, int64_t ldb, int64_t K, float* out, int64_t ldo,
                              int32_t splits, void* workspace, size_t workspace_bytes, void* stream);
+
+/* K6, the fused tower (fp16 x 2, CTA-pair kernel).  Between two GEMMs of an MLP (Dense.py:9-17 stacked by MLP.py:13-21)
+ * the reference materialises an fp32 activation / gradient; the entry points above then read it back twice (maximum,
+ * split).  Here the producing GEMM's epilogue writes its result directly as the consumer's fp16 planes, so no pass runs
+ * between two GEMMs.  That needs the power-of-two scale BEFORE the tensor exists, so scales are CARRIED from step to step:
+ *
+ * slots  fp32 [n_slots][2] = {scale, max}: one slot per tensor of the tower (input, every weight, every hidden
+ *   activation, every gradient).  `max` is raised (atomicMax on the bit pattern) by every kernel that writes the
+ *   tensor's planes; the caller seeds it with a measured maximum before the first roll.
+ * ptrec_tc_scale_roll: once per forward.  scale <- the power of two that puts `max` in [2^5, 2^6) (a tensor may grow
+ *   256-fold between two steps before fp16 overflows; elements below 2^-19 of the maximum start losing mantissa bits,
+ *   at an absolute error of 2^-41 of the maximum), max <- 0, call_scales[i] <- scale (the array one forward / backward
+ *   reads); *err |= 1 if a maximum left the fp16 range under the scale it was split with (the caller polls it).
+ * ptrec_tc_split2h_prescaled: ptrec_tc_split2h with the scale read from *scale_in; one kernel, no maximum pass;
+ *   *max_out (or NULL) is raised to max |masked src|.
+ * ptrec_tc_gemm_split2h_fused: ptrec_tc_gemm_split2h (splits == 1) whose epilogue can also
+ *   - write the result as fp16 planes [2][M][out_planes_ld] split with *out_scale (out may then be NULL),
+ *   - multiply it by a bit mask first (mask_in: [M][mask_ld] words, bit c%32 of word c/32 = keep; ReLU backward),
+ *   - write the mask of its own positive entries (mask_out, same layout; mask_ld a multiple of 4 words >= ceil(N/32)),
+ *   - reduce its column sums (colsum [N], fixed order: the bias gradient; workspace ptrec_tc_gemm_fused_workspace_bytes),
+ *   - raise *absmax_out to max |masked result| (NOT zeroed by the caller here: it is a slot's `max`).
+ *   Stores are staged through shared memory: whole 128-byte row segments per instruction. */
+int ptrec_tc_scale_roll(float* slots, int32_t n_slots, float* call_scales, int32_t* err, void* stream);
+int ptrec_tc_split2h_prescaled(const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref, int64_t ld_ref,
+                               void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld, float* colsum,
+                               const float* scale_in, float* max_out, void* workspace, size_t workspace_bytes,
+                               void* stream);
+size_t ptrec_tc_gemm_fused_workspace_bytes(int64_t M, int64_t N);
+int ptrec_tc_gemm_split2h_fused(const void* a_planes, const float* scale_a, int64_t M, int64_t lda, const void* b_planes,
+                                const float* scale_b, int64_t N, int64_t ldb, int64_t K, const float* bias, int32_t relu,
+                                float* out, int64_t ldo, void* out_planes, int64_t out_planes_ld, const float* out_scale,
+                                const uint32_t* mask_in, uint32_t* mask_out, int64_t mask_ld, float* colsum,
+                                float* absmax_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * C1 row-wise sharding: pack / unpack either side of the all-to-all (NCCL, issued by the host through

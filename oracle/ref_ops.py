@@ -149,6 +149,35 @@ def split2h_ref(x: torch.Tensor, mask_ref: torch.Tensor = None):
     return h0, h1, scale
 
 
+H2_HEADROOM = 8  # tc_linear.cu::kH2Headroom
+
+
+def h2_carried_scale_ref(absmax: float) -> float:
+    """Scale a slot takes at a roll: the maximum lands in [2^5, 2^6), eight binades below ``h2_scale_ref``'s target
+    (tc_linear.cu::scale_roll_kernel)."""
+    import math
+    e = int(math.log2(h2_scale_ref(absmax))) - H2_HEADROOM
+    return 2.0 ** max(-126, e)
+
+
+def split2h_prescaled_ref(x: torch.Tensor, scale: float, mask_bits: torch.Tensor = None):
+    """(h0, h1) of x * scale with the scale GIVEN; ``mask_bits`` (bool, same shape) zeroes elements first."""
+    x = x.float()
+    if mask_bits is not None:
+        x = x * mask_bits
+    xs = x * scale
+    h0 = xs.half()
+    h1 = ((xs - h0.float()) * 2048.0).half()
+    return h0, h1
+
+
+def unpack_mask_ref(words: torch.Tensor, n: int) -> torch.Tensor:
+    """int32 [M, W] bit mask (bit c % 32 of word c // 32) -> bool [M, n]."""
+    w = words.to(torch.int64) & 0xFFFFFFFF
+    cols = torch.arange(n)
+    return ((w[:, cols // 32] >> (cols % 32)) & 1).bool()
+
+
 def gemm_split2h_ref(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """A B^T through the fp16 x 2 format with fp32 accumulation (CPU emulation of the K6 arithmetic: plane products
     are exact in fp32, the accumulation order differs from the tensor core's)."""

@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libptrec_b200.so")
 
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 # enums (mirror include/ptrec_b200.h)
 F32, BF16 = 0, 1
@@ -137,6 +137,14 @@ PROTOTYPES = {
                                       c_size_t, c_void_p]),
     "ptrec_tc_gemm_split2h_tn": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64,
                                          c_int64, c_void_p, c_int64, c_int32, c_void_p, c_size_t, c_void_p]),
+    "ptrec_tc_scale_roll": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "ptrec_tc_split2h_prescaled": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                           c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ptrec_tc_gemm_fused_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "ptrec_tc_gemm_split2h_fused": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+                                            c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                            c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
+                                            c_void_p]),
     "ptrec_a2a_pack_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "ptrec_a2a_pack_by_owner": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_size_t, c_void_p]),

@@ -50,6 +50,11 @@ struct Split3Args {
   const float* absmax_part;
   int n_part;
   float* scale_out;
+  // NP == 2, "prescaled" mode (scale_in != null): the scale is given (a word the caller carries from step to step,
+  // ptrec_tc_scale_roll) instead of being derived from this tensor's maximum, so there is no maximum pass; the
+  // kernel raises *max_out to max |masked src| (atomicMax on the bit pattern) for the next roll.
+  const float* scale_in;
+  uint32_t* max_out;
 };
 
 // |src| maxima, one per CTA (no atomics: the split kernel reduces the partials itself).  Warp per row, lanes stride
@@ -88,7 +93,10 @@ __global__ void __launch_bounds__(kSpThreads) split_kernel(const Split3Args a) {
   __shared__ float s_cs[16][kSpTile];
   __shared__ float s_red[kSpThreads / 32];
   float scale = 1.f;
-  if (NP == 2) {
+  float amax = 0.f;  // prescaled mode: max |masked src| seen by this thread
+  if (NP == 2 && a.scale_in != nullptr) {
+    scale = *a.scale_in;
+  } else if (NP == 2) {
     float m = 0.f;
     for (int i = threadIdx.x; i < a.n_part; i += kSpThreads) m = fmaxf(m, a.absmax_part[i]);
 #pragma unroll
@@ -152,6 +160,7 @@ __global__ void __launch_bounds__(kSpThreads) split_kernel(const Split3Args a) {
         split2h(v[i], scale, h0, h1);
         pl[0][i] = __half_as_ushort(h0);
         pl[1][i] = __half_as_ushort(h1);
+        amax = fmaxf(amax, fabsf(v[i]));
       }
       cs[i] += v[i];
     }
@@ -171,6 +180,11 @@ __global__ void __launch_bounds__(kSpThreads) split_kernel(const Split3Args a) {
   if (a.colsum_part != nullptr) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) s_cs[rr][cg * 4 + i] = cs[i];
+  }
+  if (NP == 2 && a.max_out != nullptr) {  // one combining atomic per warp (non-negative floats order as uints)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(a.max_out, __float_as_uint(amax));
   }
   __syncthreads();
   if (a.colsum_part != nullptr && threadIdx.x < kSpTile && c0 + (int)threadIdx.x < a.C) {
@@ -195,6 +209,32 @@ __global__ void __launch_bounds__(kSpThreads) split_kernel(const Split3Args a) {
       }
     }
   }
+}
+
+// Carried scales of the fused tower.  A slot = {last scale, max |tensor| seen since the last roll (fp32 bits, raised by
+// atomicMax from the kernels that wrote the tensor's planes)}.  The roll turns every slot's maximum into the scale of
+// the NEXT use — the maximum lands in [2^(13-kH2Headroom), 2^(14-kH2Headroom)), so a tensor may grow 2^kH2Headroom-fold
+// from one step to the next before its first plane leaves the fp16 range — copies the scales into a per-call array
+// (what the kernels of one forward / backward read: a later roll cannot change the scale of planes already written)
+// and raises *err if a maximum did leave the range under the scale it was split with.
+constexpr int kH2Headroom = 8;
+__global__ void scale_roll_kernel(float* __restrict__ slots, int n, float* __restrict__ call_scales,
+                                  int32_t* __restrict__ err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* s = slots + 2 * i;
+  const float last = s[0], m = s[1];
+  float next = last;
+  if (m > 0.f) {
+    if (last > 0.f && !(m * last < 65504.f)) atomicOr(err, 1);  // inf in a plane written since the last roll
+    const float full = h2_scale(m);                              // max -> [2^13, 2^14)
+    const int se = max(-126, (int)((__float_as_uint(full) >> 23) & 0xFFu) - 127 - kH2Headroom);
+    next = __uint_as_float((uint32_t)(se + 127) << 23);
+  }
+  if (!(next > 0.f)) next = 1.f;  // never used: a slot is seeded with a measured maximum before its first roll
+  s[0] = next;
+  s[1] = 0.f;
+  call_scales[i] = next;
 }
 
 // out[c] = sum over row tiles of part[t][c]: 8 lanes per column stride over the tiles, then a fixed xor tree
@@ -263,6 +303,15 @@ struct LinEpi {
   const float* scale_b;
   uint32_t* absmax_out;   // optional: max |out| as fp32 bits, combined with atomicMax (the caller zeroes the word); lets the
                           // next split of `out` skip its own pass over the tensor
+  // CTA-pair kernel, fp16 x 2 only — the fused tower (ptrec_tc_gemm_split2h_fused): the epilogue hands the result to its
+  // consumer in the consumer's operand format, so no split / maximum pass runs between two GEMMs
+  unsigned short* h2_planes;  // [2][M][h2_ld] fp16 planes of the (masked) result, split with *h2_scale; out may then be null
+  int64_t h2_ld, h2_plane;
+  const float* h2_scale;      // device word: power-of-two scale carried from the previous step (ptrec_tc_scale_roll)
+  const uint32_t* mask_in;    // [M][mask_ld] bit c%32 of word c/32 set = keep element (row, c): ReLU backward of the layer below
+  uint32_t* mask_out;         // same layout: bit set where the result (after bias / ReLU) is > 0
+  int64_t mask_ld;            // words per row, a multiple of 4 >= ceil(N / 32)
+  float* colsum_part;         // [ceil(M / 32)][N] column sums of the masked result per 32-row block (bias gradient)
 };
 
 // acc = main + correction.  bf16 x 3: plain sum.  fp16 x 2: the correction accumulator holds 2^11 (A0 B1 + A1 B0) of
@@ -559,6 +608,14 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // remote a
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
+// 32 bytes per thread in one store (sm_100: STG.256): fills a whole sector, p 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void* p, const void* regs) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(regs);
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 // BK = K elements per stage: 32 (64-byte swizzle, 4 stages of 48 KB) or 64 (128-byte swizzle, 2 stages of 96 KB)
 template <bool MN_MAJOR, int BK, int NP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
@@ -698,6 +755,13 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
       }
     }
   } else {
+    // Epilogue, thread = accumulator row (TMEM lane), a warp = 32 rows x 128 columns.  The warp pulls its part of the
+    // accumulator pair into registers and hands TMEM back (the next tile's MMAs start while it works), then walks the
+    // columns in chunks of 32: bias, ReLU, the ReLU-backward bit mask of the layer below (one word per row and chunk),
+    // the > 0 bits of the result, |max|; the result leaves as fp32 and / or as the consumer's two fp16 planes with
+    // 256-bit stores — every store fills whole 32-byte sectors (128-bit stores when a pitch is not 32-byte aligned);
+    // column sums (bias gradient) by a fixed butterfly over the warp's rows.  Nothing is staged through shared
+    // memory: the MMAs keep its port busy, and a staged transpose measured slower.
     const int e = warp - 2;
     const int q = warp & 3;
     const int half = e >> 2;
@@ -705,6 +769,14 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
     const int et = threadIdx.x - 64;
     const float inv_a = (NP == 2) ? 1.f / ep.scale_a[0] : 1.f;
     const float inv_b = (NP == 2) ? 1.f / ep.scale_b[0] : 1.f;
+    const bool want_h2 = NP == 2 && ep.h2_planes != nullptr;
+    const float oscale = want_h2 ? ep.h2_scale[0] : 1.f;
+    const bool out_v8 = ep.out != nullptr && (ep.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(ep.out) & 31) == 0);
+    const bool h2_v8 = want_h2 && (ep.h2_ld % 16 == 0) && ((reinterpret_cast<uintptr_t>(ep.h2_planes) & 31) == 0) &&
+                       ((ep.h2_plane * 2) % 32 == 0);
+    const bool masked = NP == 2 && (ep.mask_in != nullptr || ep.mask_out != nullptr || ep.colsum_part != nullptr ||
+                                    ep.absmax_out != nullptr || want_h2);
+    float amax = 0.f;
     int it = 0;
     for (int tile = cid; tile < n_tiles; tile += n_clusters, ++it) {
       const int mn = tile % mn_tiles, split = tile / mn_tiles;
@@ -714,11 +786,14 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
         if (et < 256) s_bias[et] = (n0 + et < N) ? ep.bias[n0 + et] : 0.f;
         asm volatile("bar.sync 2, %0;" ::"n"(32 * kLEpiWarps) : "memory");
       }
+      const int row = m0 + r, col0 = n0 + half * 128;
+      const bool live = col0 < N;
+      uint4 mw = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      if (NP == 2 && ep.mask_in != nullptr && live && row < M)  // requested before the accumulator is waited for
+        mw = *reinterpret_cast<const uint4*>(ep.mask_in + (int64_t)row * ep.mask_ld + (col0 >> 5));
       mbar_wait(acc_full, it & 1);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
-      const int row = m0 + r, col0 = n0 + half * 128;
-      const bool live = col0 < N;
       uint32_t v[128];
       if (live) {
 #pragma unroll
@@ -735,36 +810,111 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(acc_empty);
-      float amax = 0.f;
-      if (live && row < M) {
-        float* o = ep.out + ((int64_t)split * M + row) * ep.ldo + col0;
+      if (live) {
         const bool has_bias = ep.bias != nullptr;
+        const uint32_t mwa[4] = {mw.x, mw.y, mw.z, mw.w};
+        uint32_t mo[4] = {0u, 0u, 0u, 0u};
+        float* orow = ep.out != nullptr ? ep.out + ((int64_t)split * M + row) * ep.ldo + col0 : nullptr;
+        unsigned short* prow = want_h2 ? ep.h2_planes + (int64_t)row * ep.h2_ld + col0 : nullptr;
 #pragma unroll
-        for (int j = 0; j < 128; j += 4) {
-          if (col0 + j < N) {
-            float4 t = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                   __uint_as_float(v[j + 3]));
-            if (has_bias) {
-              const float4 b = *reinterpret_cast<const float4*>(&s_bias[half * 128 + j]);
-              t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+        for (int c = 0; c < 4; ++c) {
+          const int cc0 = col0 + c * 32;
+          if (cc0 < N) {  // warp-uniform
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float t = __uint_as_float(v[c * 32 + j]);
+              if (has_bias) t += s_bias[half * 128 + c * 32 + j];
+              if (ep.relu) t = fmaxf(t, 0.f);
+              x[j] = t;
             }
-            if (ep.relu) {
-              t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+            if (masked) {  // warp-uniform: the plain fp32 product (wgrad partials, per-layer path) skips all of this
+              const int nvalid = min(32, N - cc0);
+              uint32_t keep = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);  // TMEM columns >= N hold nothing
+              keep = row < M ? (keep & mwa[c]) : 0u;
+              uint32_t bits = 0u;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float t = ((keep >> j) & 1u) ? x[j] : 0.f;
+                bits |= (t > 0.f ? 1u : 0u) << j;
+                amax = fmaxf(amax, fabsf(t));
+                x[j] = t;
+              }
+              mo[c] = bits;
             }
-            *reinterpret_cast<float4*>(o + j) = t;
-            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
-            if (NP == 3 && ep.planes != nullptr) {  // pl_ld >= N rounded up to 8: the group of 4 is inside the pitch
-              const float tv[4] = {t.x, t.y, t.z, t.w};
-              split3_store4(tv, ep.planes + (int64_t)row * ep.pl_ld + col0 + j, ep.pl_plane);
+            if (row < M) {
+              if (orow != nullptr) {
+                if (out_v8) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 8)
+                    if (cc0 + j < N) st_global_v8(orow + c * 32 + j, x + j);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4)
+                    if (cc0 + j < N)  // ldo % 4 == 0 and ldo >= round_up(N, 4): the whole group is inside the pitch
+                      *reinterpret_cast<float4*>(orow + c * 32 + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+                }
+              }
+              if (want_h2) {
+                unsigned short* o0 = prow + c * 32;
+                unsigned short* o1 = o0 + ep.h2_plane;
+#pragma unroll
+                for (int g = 0; g < 32; g += 16) {  // 16 columns of each plane at a time, two fp16 per word
+                  if (cc0 + g < N) {                // pitch % 8 == 0 (% 16 for the 256-bit form): groups stay inside the row
+                    uint32_t p0[8], p1[8];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                      __half a0, a1, b0, b1;
+                      split2h(x[g + j], oscale, a0, a1);
+                      split2h(x[g + j + 1], oscale, b0, b1);
+                      p0[j >> 1] = (uint32_t)__half_as_ushort(a0) | ((uint32_t)__half_as_ushort(b0) << 16);
+                      p1[j >> 1] = (uint32_t)__half_as_ushort(a1) | ((uint32_t)__half_as_ushort(b1) << 16);
+                    }
+                    if (h2_v8) {
+                      st_global_v8(o0 + g, p0);
+                      st_global_v8(o1 + g, p1);
+                    } else {
+                      *reinterpret_cast<uint4*>(o0 + g) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+                      *reinterpret_cast<uint4*>(o1 + g) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+                      if (cc0 + g + 8 < N) {
+                        *reinterpret_cast<uint4*>(o0 + g + 8) = make_uint4(p0[4], p0[5], p0[6], p0[7]);
+                        *reinterpret_cast<uint4*>(o1 + g + 8) = make_uint4(p1[4], p1[5], p1[6], p1[7]);
+                      }
+                    }
+                  }
+                }
+              }
+              if (NP == 3 && ep.planes != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  if (cc0 + j < N) split3_store4(x + j, ep.planes + (int64_t)row * ep.pl_ld + cc0 + j, ep.pl_plane);
+              }
+            }
+            if (NP == 2 && ep.colsum_part != nullptr) {
+              // column sums over the warp's 32 rows: a butterfly that halves the columns a lane carries at every step
+              // (31 shuffles for 32 columns); lane l ends with column l.  Fixed order: deterministic.
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int k = 0; k < o; ++k) {
+                  const float send = up ? x[k] : x[k + o];
+                  const float recv = __shfl_xor_sync(0xffffffffu, send, o);
+                  x[k] = (up ? x[k + o] : x[k]) + recv;
+                }
+              }
+              if (cc0 + lane < N) ep.colsum_part[(int64_t)((m0 + q * 32) >> 5) * N + cc0 + lane] = x[0];
             }
           }
         }
+        if (NP == 2 && ep.mask_out != nullptr && row < M)
+          *reinterpret_cast<uint4*>(ep.mask_out + (int64_t)row * ep.mask_ld + (col0 >> 5)) = make_uint4(mo[0], mo[1], mo[2], mo[3]);
       }
-      if (ep.absmax_out != nullptr) {  // warp-uniform branch; one combining atomic per warp and tile
+    }
+    if (ep.absmax_out != nullptr) {  // one combining atomic per warp (non-negative floats order as uints)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-        if (lane == 0 && amax > 0.f) atomicMax(ep.absmax_out, __float_as_uint(amax));  // non-negative floats order as uints
-      }
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      if (lane == 0 && amax > 0.f) atomicMax(ep.absmax_out, __float_as_uint(amax));
     }
   }
   tcgen05_fence_before();
@@ -1031,7 +1181,8 @@ extern "C" size_t ptrec_tc_split2h_workspace_bytes(int64_t R, int64_t C) {
 // np = 3: bf16 x 3 planes; np = 2: fp16 x 2 planes of src * scale (scale_out receives the power-of-two scale)
 static int split_impl(int np, const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref, int64_t ld_ref,
                       void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld, float* colsum, float* scale_out,
-                      const float* absmax_in, void* workspace, size_t workspace_bytes, void* stream) {
+                      const float* absmax_in, void* workspace, size_t workspace_bytes, void* stream,
+                      const float* scale_in = nullptr, float* max_out = nullptr) {
   PTREC_CHECK_ARG(src != nullptr && (planes || planes_t || colsum), PTREC_EINVAL, "tc_split: null pointer");
   PTREC_CHECK_ARG(R >= 1 && C >= 1 && R < (1ll << 31) && C < (1ll << 31) && ld >= C, PTREC_EINVAL,
                   "tc_split: bad shape R=%lld C=%lld ld=%lld", (long long)R, (long long)C, (long long)ld);
@@ -1041,9 +1192,9 @@ static int split_impl(int np, const float* src, int64_t ld, int64_t R, int64_t C
                   "tc_split: transposed plane pitch must be a multiple of 8 elements >= R, base 16-byte aligned");
   PTREC_CHECK_ARG(!relu_ref || ld_ref >= C, PTREC_EINVAL, "tc_split: bad ld_ref");
   const size_t need = np == 2 ? ptrec_tc_split2h_workspace_bytes(R, C) : ptrec_tc_split3_workspace_bytes(R, C);
-  PTREC_CHECK_ARG(!(colsum || np == 2) || (workspace && workspace_bytes >= need), PTREC_EWORKSPACE,
+  PTREC_CHECK_ARG(!(colsum || (np == 2 && !scale_in)) || (workspace && workspace_bytes >= need), PTREC_EWORKSPACE,
                   "tc_split: workspace too small (%zu < %zu)", workspace_bytes, need);
-  PTREC_CHECK_ARG(np == 3 || scale_out != nullptr, PTREC_EINVAL, "tc_split2h: scale_out is null");
+  PTREC_CHECK_ARG(np == 3 || scale_out != nullptr || scale_in != nullptr, PTREC_EINVAL, "tc_split2h: scale_out is null");
   cudaStream_t st = (cudaStream_t)stream;
   Split3Args a;
   a.src = src; a.ld = ld; a.R = (int)R; a.C = (int)C; a.ref = relu_ref; a.ld_ref = ld_ref;
@@ -1053,8 +1204,11 @@ static int split_impl(int np, const float* src, int64_t ld, int64_t R, int64_t C
   a.Rp = (int)std::min<int64_t>(pt_ld, (R + 7) / 8 * 8);
   a.colsum_part = colsum ? reinterpret_cast<float*>(workspace) : nullptr;
   a.absmax_part = nullptr; a.n_part = 0; a.scale_out = scale_out;
+  a.scale_in = scale_in; a.max_out = reinterpret_cast<uint32_t*>(max_out);
   dim3 grid((unsigned)ceil_div(C, kSpTile), (unsigned)ceil_div(R, kSpTile));
-  if (np == 2) {
+  if (np == 2 && scale_in != nullptr) {
+    split_kernel<2><<<grid, kSpThreads, 0, st>>>(a);
+  } else if (np == 2) {
     if (absmax_in != nullptr) {  // the producer of src already reduced max |src| into one word (GEMM epilogue)
       a.absmax_part = absmax_in; a.n_part = 1;
     } else {
@@ -1175,12 +1329,23 @@ static int gemm_launch(bool mn_major, bool two_sm, bool db, int bk, int sms, con
   return PTREC_OK;
 }
 
+struct LinFused {  // ptrec_tc_gemm_split2h_fused: what the epilogue writes besides / instead of the fp32 result
+  void* h2_planes = nullptr;
+  int64_t h2_ld = 0;
+  const float* h2_scale = nullptr;
+  const uint32_t* mask_in = nullptr;
+  uint32_t* mask_out = nullptr;
+  int64_t mask_ld = 0;
+  float* colsum = nullptr;
+};
+
 static int gemm_split_impl(int np, bool mn_major, const void* a_planes, const float* scale_a, int64_t M, int64_t lda,
                            const void* b_planes, const float* scale_b, int64_t N, int64_t ldb, int64_t K,
                            const float* bias, int32_t relu, float* out, int64_t ldo, void* out_planes,
                            int64_t out_planes_ld, float* absmax_out, int32_t splits, void* workspace,
-                           size_t workspace_bytes, void* stream) {
-  PTREC_CHECK_ARG(a_planes && b_planes && out, PTREC_EINVAL, "tc_gemm_split: null pointer");
+                           size_t workspace_bytes, void* stream, const LinFused* fu = nullptr) {
+  PTREC_CHECK_ARG(a_planes && b_planes && (out || (fu && fu->h2_planes)), PTREC_EINVAL, "tc_gemm_split: null pointer");
+  if (out == nullptr) ldo = (N + 3) / 4 * 4;
   PTREC_CHECK_ARG(np == 3 || (scale_a && scale_b), PTREC_EINVAL, "tc_gemm_split2h: null operand scale");
   PTREC_CHECK_ARG(M >= 1 && N >= 1 && K >= 1 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), PTREC_EINVAL,
                   "tc_gemm_split: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
@@ -1219,6 +1384,32 @@ static int gemm_split_impl(int np, bool mn_major, const void* a_planes, const fl
   ep.out = splits > 1 ? reinterpret_cast<float*>(workspace) : out;
   ep.scale_a = scale_a; ep.scale_b = scale_b;
   ep.absmax_out = reinterpret_cast<uint32_t*>(absmax_out);
+  ep.h2_planes = nullptr; ep.h2_ld = 0; ep.h2_plane = 0; ep.h2_scale = nullptr;
+  ep.mask_in = nullptr; ep.mask_out = nullptr; ep.mask_ld = 0; ep.colsum_part = nullptr;
+  if (fu != nullptr) {
+    PTREC_CHECK_ARG(np == 2 && two_sm && !db && !mn_major && splits == 1, PTREC_EUNSUPPORTED,
+                    "tc_gemm_split2h_fused needs the CTA-pair fp16 x 2 kernel (256-wide tiles), K-major operands, no split-K");
+    PTREC_CHECK_ARG(!fu->h2_planes || (fu->h2_scale && aligned16(fu->h2_planes) && fu->h2_ld % 8 == 0 && fu->h2_ld >= N),
+                    PTREC_EALIGN, "tc_gemm_split2h_fused: output planes need a scale word and a pitch that is a multiple of 8 >= N");
+    PTREC_CHECK_ARG(!(fu->mask_in || fu->mask_out) || (fu->mask_ld % 4 == 0 && fu->mask_ld * 32 >= N &&
+                                                        (!fu->mask_in || aligned16(fu->mask_in)) &&
+                                                        (!fu->mask_out || aligned16(fu->mask_out))),
+                    PTREC_EALIGN, "tc_gemm_split2h_fused: mask pitch must be a multiple of 4 words covering N, base 16-byte aligned");
+    const size_t need = align_up((size_t)ceil_div(M, (int64_t)32) * N * sizeof(float), 256);
+    PTREC_CHECK_ARG(!fu->colsum || (workspace && workspace_bytes >= need), PTREC_EWORKSPACE,
+                    "tc_gemm_split2h_fused: workspace too small for the column-sum partials (%zu < %zu)", workspace_bytes, need);
+    ep.h2_planes = reinterpret_cast<unsigned short*>(fu->h2_planes); ep.h2_ld = fu->h2_ld; ep.h2_plane = M * fu->h2_ld;
+    ep.h2_scale = fu->h2_scale; ep.mask_in = fu->mask_in; ep.mask_out = fu->mask_out; ep.mask_ld = fu->mask_ld;
+    ep.colsum_part = fu->colsum ? reinterpret_cast<float*>(workspace) : nullptr;
+    const int rc2 = gemm_launch<2>(false, true, false, bk, sms, maps, M, N, K, ep, out, st);
+    if (rc2 != PTREC_OK) return rc2;
+    if (fu->colsum) {
+      colsum_reduce_kernel<<<(unsigned)ceil_div(N, (int64_t)32), 256, 0, st>>>(ep.colsum_part, (int)ceil_div(M, (int64_t)32),
+                                                                                (int)N, fu->colsum);
+      PTREC_LAUNCH_CHECK("colsum_reduce_kernel");
+    }
+    return PTREC_OK;
+  }
   return np == 3 ? gemm_launch<3>(mn_major, two_sm, false, bk, sms, maps, M, N, K, ep, out, st)
                  : gemm_launch<2>(mn_major, two_sm, db, bk, sms, maps, M, N, K, ep, out, st);
 }
@@ -1252,4 +1443,38 @@ extern "C" int ptrec_tc_gemm_split2h_tn(const void* a_planes, const float* scale
                                         size_t workspace_bytes, void* stream) {
   return gemm_split_impl(2, true, a_planes, scale_a, M, lda, b_planes, scale_b, N, ldb, K, nullptr, 0, out, ldo,
                          nullptr, 0, nullptr, splits, workspace, workspace_bytes, stream);
+}
+
+// ---- the fused tower: carried scales, prescaled split, GEMM epilogue that writes its consumer's operand planes ----
+extern "C" int ptrec_tc_scale_roll(float* slots, int32_t n_slots, float* call_scales, int32_t* err, void* stream) {
+  PTREC_CHECK_ARG(slots && call_scales && err && n_slots >= 1, PTREC_EINVAL, "tc_scale_roll: null pointer");
+  scale_roll_kernel<<<(unsigned)ceil_div(n_slots, 128), 128, 0, (cudaStream_t)stream>>>(slots, n_slots, call_scales, err);
+  PTREC_LAUNCH_CHECK("scale_roll_kernel");
+  return PTREC_OK;
+}
+
+extern "C" int ptrec_tc_split2h_prescaled(const float* src, int64_t ld, int64_t R, int64_t C, const float* relu_ref,
+                                          int64_t ld_ref, void* planes, int64_t pl_ld, void* planes_t, int64_t pt_ld,
+                                          float* colsum, const float* scale_in, float* max_out, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  PTREC_CHECK_ARG(scale_in != nullptr, PTREC_EINVAL, "tc_split2h_prescaled: scale_in is null");
+  return split_impl(2, src, ld, R, C, relu_ref, ld_ref, planes, pl_ld, planes_t, pt_ld, colsum, nullptr, nullptr,
+                    workspace, workspace_bytes, stream, scale_in, max_out);
+}
+
+extern "C" size_t ptrec_tc_gemm_fused_workspace_bytes(int64_t M, int64_t N) {
+  return align_up((size_t)ceil_div(M, (int64_t)32) * N * sizeof(float), 256);
+}
+
+extern "C" int ptrec_tc_gemm_split2h_fused(const void* a_planes, const float* scale_a, int64_t M, int64_t lda,
+                                           const void* b_planes, const float* scale_b, int64_t N, int64_t ldb, int64_t K,
+                                           const float* bias, int32_t relu, float* out, int64_t ldo, void* out_planes,
+                                           int64_t out_planes_ld, const float* out_scale, const uint32_t* mask_in,
+                                           uint32_t* mask_out, int64_t mask_ld, float* colsum, float* absmax_out,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+  LinFused fu;
+  fu.h2_planes = out_planes; fu.h2_ld = out_planes_ld; fu.h2_scale = out_scale;
+  fu.mask_in = mask_in; fu.mask_out = mask_out; fu.mask_ld = mask_ld; fu.colsum = colsum;
+  return gemm_split_impl(2, false, a_planes, scale_a, M, lda, b_planes, scale_b, N, ldb, K, bias, relu, out, ldo, nullptr,
+                         0, absmax_out, 1, workspace, workspace_bytes, stream, &fu);
 }

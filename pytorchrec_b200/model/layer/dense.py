@@ -142,6 +142,125 @@ class Dense(Module):
         return self.dropout(self.activation(self.linear(x)))
 
 
+class _TowerScales:
+    """Carried power-of-two scales of one MLP on the fused K6 path (include/ptrec_b200.h, "the fused tower"): one slot
+    {scale, max since the last roll} per tensor — input, every weight, every hidden activation, every pre-activation
+    gradient.  The slots are seeded with measured maxima by one forward / backward on the per-layer path
+    (``MLP._forward_recording``); from then on every kernel that writes a tensor's planes raises the slot's maximum and
+    ``roll`` (once per forward) turns it into the next step's scale."""
+
+    def __init__(self, n_layers: int, device: torch.device):
+        self.L = n_layers
+        self.device = device
+        self.slots = torch.zeros(3 * n_layers, 2, dtype=torch.float32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.fwd_ready = False
+        self.bwd_ready = False
+
+    # slot indices
+    def i_x(self): return 0
+    def i_w(self, l): return 1 + l
+    def i_y(self, l): return self.L + 1 + l        # output of hidden layer l (l < L - 1) = input of layer l + 1
+    def i_g(self, l): return 2 * self.L + l        # gradient w.r.t. the pre-activation of layer l
+
+    def i_in(self, l): return self.i_x() if l == 0 else self.i_y(l - 1)
+
+    def seed(self, i: int, t: torch.Tensor) -> None:
+        m = self.slots[i, 1]
+        torch.maximum(m, t.detach().abs().max().to(torch.float32), out=m)
+
+    def max_word(self, i: int) -> torch.Tensor:
+        return self.slots[i, 1:2]
+
+    def roll(self) -> torch.Tensor:
+        cs = ops.tc_scale_roll(self.slots, self.err)
+        self.err_host.copy_(self.err, non_blocking=True)  # polled without synchronising (MLP.poll_errors)
+        return cs
+
+
+class _TcMLP(torch.autograd.Function):
+    """The whole Linear -> ReLU stack on K6 with nothing between two GEMMs: the epilogue of layer l writes relu(x W^T + b)
+    as the fp16 planes layer l + 1 consumes (and its weight gradient re-reads MN-major) plus one bit per element (> 0);
+    the input-gradient GEMM of layer l + 1 applies that bit mask, writes the planes of layer l's pre-activation gradient
+    and its column sums (bias gradient).  fp32 is materialised only for the tower's output and its input gradient."""
+
+    @staticmethod
+    def forward(ctx, x, mlp, *params):
+        sl: _TowerScales = mlp._scales
+        L = sl.L
+        cs = sl.roll()
+        sc = lambda i: cs[i:i + 1]
+        need_dx = ctx.needs_input_grad[0]
+        any_grad = any(ctx.needs_input_grad)
+        px, _, _ = ops.tc_split2h_prescaled(x, sc(sl.i_x()), sl.max_word(sl.i_x()))
+        acts, masks, pwts = [px], [], []
+        y = None
+        for l in range(L):
+            W, b = params[2 * l], params[2 * l + 1]
+            pw, pwt, _ = ops.tc_split2h_prescaled(W, sc(sl.i_w(l)), sl.max_word(sl.i_w(l)),
+                                                  want_t=any_grad and (l > 0 or need_dx))
+            pwts.append(pwt)
+            last = l == L - 1
+            y, py, mask, _ = ops.tc_gemm_split2h_fused(
+                acts[l], sc(sl.i_in(l)), pw, sc(sl.i_w(l)), W.shape[1], bias=b, relu=True, want_out=last,
+                out_scale=None if last else sc(sl.i_y(l)), want_mask=any_grad and not last,
+                max_out=None if last else sl.max_word(sl.i_y(l)))
+            if not last:
+                acts.append(py)
+                masks.append(mask)
+        if getattr(mlp, "_keep_masks", False):  # test introspection: the ReLU decisions this forward took
+            mlp._last_masks = list(masks)
+        ctx.scales = sl
+        ctx.dims = [(params[2 * l].shape[0], params[2 * l].shape[1]) for l in range(L)]
+        ctx.has_bias = [params[2 * l + 1] is not None for l in range(L)]
+        if any_grad:
+            ctx.n_masks = len(masks)
+            ctx.save_for_backward(y, cs, *acts, *masks, *[t for t in pwts if t is not None])
+            ctx.pwt_present = [t is not None for t in pwts]
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        sl: _TowerScales = ctx.scales
+        L = sl.L
+        saved = ctx.saved_tensors
+        y, cs = saved[0], saved[1]
+        acts = list(saved[2:2 + L])
+        masks = list(saved[2 + L:2 + L + ctx.n_masks])
+        rest = list(saved[2 + L + ctx.n_masks:])
+        pwts = [rest.pop(0) if present else None for present in ctx.pwt_present]
+        sc = lambda i: cs[i:i + 1]
+        need = ctx.needs_input_grad
+        if gy.stride(-1) != 1:
+            gy = gy.contiguous()
+        grads = [None] * (2 * L)
+        pg, _, db = ops.tc_split2h_prescaled(gy, sc(sl.i_g(L - 1)), sl.max_word(sl.i_g(L - 1)), relu_ref=y,
+                                             want_colsum=ctx.has_bias[L - 1] and need[2 + 2 * (L - 1) + 1])
+        dx = None
+        for l in range(L - 1, -1, -1):
+            N, K = ctx.dims[l]
+            pg_prev = db_prev = None
+            if l > 0:    # g W, masked by the ReLU of layer l - 1, as planes + bias gradient of layer l - 1
+                _, pg_prev, _, db_prev = ops.tc_gemm_split2h_fused(
+                    pg, sc(sl.i_g(l)), pwts[l], sc(sl.i_w(l)), N, want_out=False, out_scale=sc(sl.i_g(l - 1)),
+                    mask_in=masks[l - 1], want_colsum=ctx.has_bias[l - 1] and need[2 + 2 * (l - 1) + 1],
+                    max_out=sl.max_word(sl.i_g(l - 1)))
+            elif need[0]:
+                dx, _, _, _ = ops.tc_gemm_split2h_fused(pg, sc(sl.i_g(0)), pwts[0], sc(sl.i_w(0)), N)
+            if need[2 + 2 * l]:
+                dw = ops.tc_gemm_split2h_tn(pg, sc(sl.i_g(l)), N, acts[l], sc(sl.i_in(l)), K)   # g^T x  [N, K]
+                grads[2 * l] = dw if dw.is_contiguous() else dw.contiguous()
+            grads[2 * l + 1] = db
+            pg, db = pg_prev, db_prev
+        sl.bwd_ready = True
+        return (dx, None, *grads)
+
+
+def tc_fused_enabled() -> bool:
+    return os.environ.get("PTREC_TC_FUSED", "1") != "0"
+
+
 class MLP(Module):
     def __init__(self, input_units: int, hidden_units_list: List[int], activation: str, dropout: float):
         super().__init__()
@@ -150,9 +269,71 @@ class MLP(Module):
         for index, hidden_units in enumerate(hidden_units_list):
             self.mlp.add_module(f"dense_{index}", Dense(units, hidden_units, activation, dropout))
             units = hidden_units
-        # Dense.emit_planes (the GEMM epilogue writes the next layer's planes) stays off: the epilogue stores are
-        # per-thread rows (8-byte pieces, uncoalesced) and measured slower than the separate split pass
-        # (cfg2 step 0.72 -> 0.85 ms); it needs a shared-memory-staged epilogue first.
+        self._scales = None  # _TowerScales, created on the first CUDA forward that qualifies for the fused path
+
+    def _fused_eligible(self, x) -> bool:
+        if not (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and tc_linear_enabled() and tc_fused_enabled()
+                and ops.tc_mode() == "fp16x2" and ops.tc_fused_supported() and not torch.is_autocast_enabled()
+                and len(self.mlp) >= 1):
+            return False
+        for d in self.mlp:
+            if not isinstance(d, Dense) or d.linear.weight.dtype != torch.float32 or d.linear.bias is None \
+                    or (self.training and d.dropout.p > 0) or x.shape[0] * d.linear.weight.numel() < TC_MIN_MACS:
+                return False
+        return True
+
+    def _forward_recording(self, x, want_grad: bool):
+        """One pass on the per-layer path that seeds the carried scales with measured maxima (a hidden activation's
+        gradient bounds its ReLU-masked version, which is what the slot describes)."""
+        sl = self._scales
+        L = sl.L
+        sl.seed(sl.i_x(), x)
+        h = x
+        for l, d in enumerate(self.mlp):
+            sl.seed(sl.i_w(l), d.linear.weight)
+            h = d(h)
+            if l < L - 1:
+                sl.seed(sl.i_y(l), h)
+            if want_grad and h.requires_grad:
+                def hook(g, i=sl.i_g(l), first=(l == 0)):
+                    sl.seed(i, g)
+                    if first:
+                        sl.bwd_ready = True
+                h.register_hook(hook)
+        sl.fwd_ready = True
+        return h
 
     def forward(self, x):
-        return self.mlp(x)
+        if not self._fused_eligible(x):
+            return self.mlp(x)
+        if self._scales is None or self._scales.device != x.device or self._scales.L != len(self.mlp):
+            self._scales = _TowerScales(len(self.mlp), x.device)
+        sl = self._scales
+        want_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if not sl.fwd_ready or (want_grad and not sl.bwd_ready):
+            return self._forward_recording(x, want_grad)
+        x2 = x if x.stride(-1) == 1 else x.contiguous()
+        params = []
+        for d in self.mlp:
+            params += [d.linear.weight, d.linear.bias]
+        return _TcMLP.apply(x2, self, *params)
+
+    # picked up by IModel.train_step (non-synchronising) and IModel._check_device_flags (once per epoch)
+    def poll_errors(self) -> None:
+        if self._scales is not None and int(self._scales.err_host[0]):
+            self._raise_scale_error()
+
+    def check_errors(self) -> None:
+        if self._scales is not None and int(self._scales.err.item()):
+            self._raise_scale_error()
+
+    def reset_scales(self) -> None:
+        """Forget the carried scales: the next forward / backward measures them again on the per-layer path."""
+        self._scales = None
+
+    def _raise_scale_error(self):
+        raise RuntimeError(
+            "K6 fused tower: a tensor grew more than 256-fold between two consecutive steps and left the fp16 range of "
+            "its carried scale — results since then are invalid (the run is diverging, or the inputs changed scale "
+            "abruptly).  MLP.reset_scales() re-measures; PTREC_TC_FUSED=0 selects the per-layer path, which derives "
+            "every scale from the tensor itself")

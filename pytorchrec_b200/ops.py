@@ -743,7 +743,7 @@ def tc_gemm_split2h(a_planes: torch.Tensor, scale_a: torch.Tensor, b_planes: tor
     dev = a_planes.device
     if splits == 0:
         splits = lib.ptrec_tc_gemm_split3_default_splits(M, N, K)
-    ldo = (N + 3) // 4 * 4
+    ldo = _pad8(N)  # 32-byte aligned rows: the epilogue stores 256 bits per thread
     out = torch.empty(M, ldo, dtype=torch.float32, device=dev)
     nbytes = lib.ptrec_tc_gemm_split3_workspace_bytes(M, ldo, splits)
     ws = _workspace("tc_gemm_split3", nbytes, dev) if nbytes else None
@@ -768,7 +768,7 @@ def tc_gemm_split2h_tn(a_planes: torch.Tensor, scale_a: torch.Tensor, M: int, b_
     dev = a_planes.device
     if splits == 0:
         splits = lib.ptrec_tc_gemm_split3_default_splits(M, N, K)
-    ldo = (N + 3) // 4 * 4
+    ldo = _pad8(N)
     out = torch.empty(M, ldo, dtype=torch.float32, device=dev)
     nbytes = lib.ptrec_tc_gemm_split3_workspace_bytes(M, ldo, splits)
     ws = _workspace("tc_gemm_split3", nbytes, dev) if nbytes else None
@@ -776,6 +776,90 @@ def tc_gemm_split2h_tn(a_planes: torch.Tensor, scale_a: torch.Tensor, M: int, b_
                                             K, _ptr(out), ldo, splits, _ptr(ws), ws.numel() if ws is not None else 0,
                                             _stream(dev)), "ptrec_tc_gemm_split2h_tn")
     return out[:, :N] if ldo != N else out
+
+
+# ---- the fused tower: carried scales, GEMM epilogues that write their consumer's operand planes -------------------
+def tc_scale_roll(slots: torch.Tensor, err: torch.Tensor) -> torch.Tensor:
+    """``slots`` fp32 [n, 2] = {scale, max since the last roll}: every slot's maximum becomes its next scale (8 binades
+    of headroom), the maxima restart at zero; returns the scales as a fresh [n] tensor — what ONE forward / backward
+    reads.  ``err`` (int32 word) is raised if a maximum left the fp16 range under the scale it was split with."""
+    lib = _lib.load()
+    _require_cuda(slots, err)
+    assert slots.dtype == torch.float32 and slots.dim() == 2 and slots.shape[1] == 2 and slots.is_contiguous()
+    assert err.dtype == torch.int32
+    out = torch.empty(slots.shape[0], dtype=torch.float32, device=slots.device)
+    _lib.check(lib.ptrec_tc_scale_roll(_ptr(slots), slots.shape[0], _ptr(out), _ptr(err), _stream(slots.device)),
+               "ptrec_tc_scale_roll")
+    return out
+
+
+def tc_split2h_prescaled(src: torch.Tensor, scale: torch.Tensor, max_out: Optional[torch.Tensor],
+                         relu_ref: Optional[torch.Tensor] = None, want_planes: bool = True, want_t: bool = False,
+                         want_colsum: bool = False):
+    """``tc_split2h`` with the scale given (a one-element view of ``tc_scale_roll``'s result): one kernel, no maximum
+    pass.  ``max_out`` (one-element fp32 view of the slot's maximum) is raised to max |masked src|.
+    Returns (planes, planes_t, colsum)."""
+    lib = _lib.load()
+    _require_cuda(src, relu_ref, scale, max_out)
+    assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1
+    assert scale.dtype == torch.float32 and scale.numel() == 1
+    R, C = src.shape
+    dev = src.device
+    if relu_ref is not None:
+        assert relu_ref.shape == src.shape and relu_ref.dtype == torch.float32 and relu_ref.stride(1) == 1
+    planes = torch.empty(2, R, _pad8(C), dtype=torch.float16, device=dev) if want_planes else None
+    planes_t = torch.empty(2, C, _pad8(R), dtype=torch.float16, device=dev) if want_t else None
+    colsum = torch.empty(C, dtype=torch.float32, device=dev) if want_colsum else None
+    ws = _workspace("tc_split2h", lib.ptrec_tc_split2h_workspace_bytes(R, C), dev) if want_colsum else None
+    _lib.check(lib.ptrec_tc_split2h_prescaled(_ptr(src), src.stride(0), R, C, _ptr(relu_ref),
+                                              relu_ref.stride(0) if relu_ref is not None else 0, _ptr(planes), _pad8(C),
+                                              _ptr(planes_t), _pad8(R), _ptr(colsum), _ptr(scale), _ptr(max_out),
+                                              _ptr(ws), ws.numel() if ws is not None else 0, _stream(dev)),
+               "ptrec_tc_split2h_prescaled")
+    return planes, planes_t, colsum
+
+
+def tc_fused_supported() -> bool:
+    """The fused tower runs on the CTA-pair kernel with 256-wide tiles (the default configuration)."""
+    lib = _lib.load()
+    return bool(lib.ptrec_tc_2sm_enabled()) and lib.ptrec_tc_get_bn() == 256
+
+
+def mask_words(n: int) -> int:
+    """Words per row of a ReLU bit mask over n columns (multiple of 4: rows are read 16 bytes at a time)."""
+    return ((n + 31) // 32 + 3) // 4 * 4
+
+
+def tc_gemm_split2h_fused(a_planes: torch.Tensor, scale_a: torch.Tensor, b_planes: torch.Tensor, scale_b: torch.Tensor,
+                          K: int, bias: Optional[torch.Tensor] = None, relu: bool = False, want_out: bool = True,
+                          out_scale: Optional[torch.Tensor] = None, mask_in: Optional[torch.Tensor] = None,
+                          want_mask: bool = False, want_colsum: bool = False, max_out: Optional[torch.Tensor] = None):
+    """A[M, K] B[N, K]^T (+ bias) (ReLU) (* mask_in) on the CTA-pair fp16 x 2 kernel, handed over in the consumer's
+    format.  Returns (out fp32 [M, N] or None, planes [2, M, pad16(N)] fp16 split with ``out_scale`` or None,
+    mask int32 [M, mask_words(N)] of the positive entries or None, colsum [N] or None)."""
+    lib = _lib.load()
+    _check_h2(a_planes, scale_a, b_planes, scale_b)
+    M, lda = a_planes.shape[1], a_planes.shape[2]
+    N, ldb = b_planes.shape[1], b_planes.shape[2]
+    dev = a_planes.device
+    ldo = _pad8(N)            # 32-byte aligned rows of both outputs: the epilogue stores 256 bits per thread
+    pld = (N + 15) // 16 * 16
+    out = torch.empty(M, ldo, dtype=torch.float32, device=dev) if want_out else None
+    planes = torch.empty(2, M, pld, dtype=torch.float16, device=dev) if out_scale is not None else None
+    mw = mask_words(N)
+    mask = torch.empty(M, mw, dtype=torch.int32, device=dev) if want_mask else None
+    if mask_in is not None:
+        assert mask_in.dtype == torch.int32 and tuple(mask_in.shape) == (M, mw) and mask_in.is_contiguous()
+    colsum = torch.empty(N, dtype=torch.float32, device=dev) if want_colsum else None
+    ws = _workspace("tc_gemm_fused", lib.ptrec_tc_gemm_fused_workspace_bytes(M, N), dev) if want_colsum else None
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
+    _lib.check(lib.ptrec_tc_gemm_split2h_fused(
+        _ptr(a_planes), _ptr(scale_a), M, lda, _ptr(b_planes), _ptr(scale_b), N, ldb, K, _ptr(bias), int(relu),
+        _ptr(out), ldo, _ptr(planes), pld, _ptr(out_scale), _ptr(mask_in), _ptr(mask), mw, _ptr(colsum),
+        _ptr(max_out), _ptr(ws), ws.numel() if ws is not None else 0, _stream(dev)), "ptrec_tc_gemm_split2h_fused")
+    y = None if out is None else (out[:, :N] if ldo != N else out)
+    return y, planes, mask, colsum
 
 
 # ----------------------------------------------------------------------------------------------

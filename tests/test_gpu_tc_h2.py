@@ -136,10 +136,12 @@ def test_gemm_split2h_tn_weight_gradient_from_row_major_planes(B, N, K, tc_kerne
         assert _err(dw, ref, scale) <= tol, (splits, _err(dw, ref, scale), fp32_err)
 
 
-def test_mlp_carries_absmax_words_between_layers_and_matches_fp64():
-    """Three Dense layers: outputs / input gradients travel with the word holding their maximum (no extra pass), and
-    the whole tower agrees with an fp64 evaluation."""
+def test_mlp_carries_absmax_words_between_layers_and_matches_fp64(monkeypatch):
+    """Three Dense layers on the per-layer path (PTREC_TC_FUSED=0; the fused tower has tests/test_gpu_tc_fused.py):
+    outputs / input gradients travel with the word holding their maximum (no extra pass), and the whole tower agrees
+    with an fp64 evaluation."""
     from pytorchrec_b200.model.layer import dense
+    monkeypatch.setenv("PTREC_TC_FUSED", "0")
     old, dense.TC_MIN_MACS = dense.TC_MIN_MACS, 0
     try:
         torch.manual_seed(5)
