@@ -324,6 +324,9 @@ __device__ __forceinline__ float lin_combine(float main_acc, float corr_acc, flo
 
 struct LinMaps {
   CUtensorMap a, b;  // 3-D: K-major (k, row, plane) or MN-major (mn, k row, plane)
+  // CTA-pair kernel: where the epilogue's TMA stores go.  c: fp32 result (col, row, split-K slab), boxes of 32 x 32,
+  // 128-byte swizzle; p: fp16 planes of the result (col, row, plane), boxes of 32 x 32 x 1, 64-byte swizzle
+  CUtensorMap c, p;
 };
 
 // K-major, 64B swizzle (rows of 32 bf16): 8-row atoms of 512 B; LBO unused (1), SBO = 512 B
@@ -571,7 +574,13 @@ gemm_split3_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, Li
 #ifndef K2_STAGES
 #define K2_STAGES 4
 #endif
-constexpr size_t k2Smem = (size_t)(K2_STAGES == 3 ? 144 : 192) * 1024 + 1024 /*align*/ + 2048 /*barriers + bias slice*/;
+// 16 epilogue warps (4 per scheduler): the epilogue is a chain of dependent fixed-latency instructions per element, and
+// with 2 warps per scheduler it ran at ~0.1 instructions per cycle and warp (8.2k cycles per tile, tools/diag_k6_timeline.py)
+constexpr int k2EpiWarps = 16;
+constexpr int k2Threads = 64 + 32 * k2EpiWarps;
+constexpr uint32_t k2Staging = k2EpiWarps * 4096;  // epilogue: one 32 x 32 fp32 (or 2 x 32 x 32 fp16) box per warp
+constexpr size_t k2Smem = 232448;                  // everything a CTA may use: stages + staging + barriers
+constexpr size_t k2StageBudget = k2Smem - k2Staging - 1024 /*align*/ - 2048 /*barriers + bias slice*/;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;         // clears the CTA-pair bit of a shared::cluster address -> leader
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -608,26 +617,39 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // remote a
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
-// 32 bytes per thread in one store (sm_100: STG.256): fills a whole sector, p 32-byte aligned
-__device__ __forceinline__ void st_global_v8(void* p, const void* regs) {
-  const uint32_t* r = reinterpret_cast<const uint32_t*>(regs);
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
-               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 
+#ifdef PTREC_K6_TIMELINE
+// Diagnostic build (make EXTRA=-DPTREC_K6_TIMELINE; tools/diag_k6_timeline.py): the first epilogue thread of every CTA
+// stamps %globaltimer at the kernel's milestones into g_k6_timeline[cta][32].
+__device__ unsigned long long* g_k6_timeline = nullptr;
+__device__ __forceinline__ void k6_stamp(int slot) {
+  if (g_k6_timeline != nullptr && threadIdx.x == 64 && slot < 32) {  // SM cycle counter: ~0.52 ns at 1.9 GHz
+    g_k6_timeline[(size_t)blockIdx.x * 32 + slot] = (unsigned long long)clock64();
+  }
+}
+#define K6_STAMP(slot) k6_stamp(slot)
+#else
+#define K6_STAMP(slot)
+#endif
+
 // BK = K elements per stage: 32 (64-byte swizzle, 4 stages of 48 KB) or 64 (128-byte swizzle, 2 stages of 96 KB)
 template <bool MN_MAJOR, int BK, int NP>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K, LinEpi ep) {
-  // bf16 x 3: 6 tiles per stage (48 / 96 KB) -> 4 / 2 stages; fp16 x 2: 4 tiles (32 / 64 KB) -> 6 / 3 stages
-  constexpr int k2Stages = NP == 3 ? (BK == 64 ? 2 : K2_STAGES) : (BK == 64 ? 3 : 6);
+  // a stage = NP planes of A (128 rows) and of this CTA's B half: fp16 x 2, BK 32: 32 KB -> 5 stages; bf16 x 3: 48 KB -> 3
   constexpr uint32_t k2Tile = 128 * BK * 2;     // any plane tile: 128 rows (or 2 boxes of 64 mn) x BK 16-bit elements
   constexpr uint32_t k2StageBytes = 2 * NP * k2Tile; // A planes, then B planes (B = this CTA's half)
-  static_assert((size_t)k2Stages * k2StageBytes + 3072 <= k2Smem, "stages exceed the shared-memory budget");
+  constexpr int k2Stages = (int)(k2StageBudget / k2StageBytes);
+  static_assert(k2Stages >= 1, "a stage exceeds the shared-memory budget");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)k2Stages * k2StageBytes);
+  unsigned char* staging = smem + (size_t)k2Stages * k2StageBytes;  // 1024-byte aligned: the stages are multiples of 1 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + k2Staging);
   uint64_t* full = bars;                    // [k2Stages]  (the leader's are the ones in use)
   uint64_t* empty = bars + k2Stages;        // [k2Stages]
   uint64_t* acc_full = bars + 2 * k2Stages; // [1]
@@ -644,6 +666,7 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
   const int total_kb = (K + BK - 1) / BK;
   const int kb_per_split = (total_kb + splits - 1) / splits;
   const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  K6_STAMP(0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < k2Stages; ++s) {
@@ -651,7 +674,7 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
       mbar_init(&empty[s], 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 2 * kLEpiWarps);  // the epilogue warps of both CTAs
+    mbar_init(acc_empty, 2 * k2EpiWarps);  // the epilogue warps of both CTAs
     fence_mbar_init();
   }
   cluster_sync_all();  // the peer's barriers exist before anything arrives on them
@@ -755,162 +778,166 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
       }
     }
   } else {
-    // Epilogue, thread = accumulator row (TMEM lane), a warp = 32 rows x 128 columns.  The warp pulls its part of the
-    // accumulator pair into registers and hands TMEM back (the next tile's MMAs start while it works), then walks the
-    // columns in chunks of 32: bias, ReLU, the ReLU-backward bit mask of the layer below (one word per row and chunk),
-    // the > 0 bits of the result, |max|; the result leaves as fp32 and / or as the consumer's two fp16 planes with
-    // 256-bit stores — every store fills whole 32-byte sectors (128-bit stores when a pitch is not 32-byte aligned);
-    // column sums (bias gradient) by a fixed butterfly over the warp's rows.  Nothing is staged through shared
-    // memory: the MMAs keep its port busy, and a staged transpose measured slower.
+    // Epilogue, thread = accumulator row (TMEM lane), a warp = 32 rows (its TMEM lane quadrant) x 64 columns, walked in
+    // two chunks of 32: bias, ReLU, the ReLU-backward bit mask of the layer below (one word per row and chunk), the > 0
+    // bits of the result, |max|, column sums (bias gradient) by a fixed butterfly over the warp's rows.  The result
+    // leaves as fp32 and / or as the consumer's two fp16 planes through a swizzled 4 KB staging box per warp and one
+    // TMA store per box (whole 128-byte lines, clipped at M / N by the tensor map).  TMEM goes back to the tensor core
+    // as soon as the warp's second chunk is in registers.
     const int e = warp - 2;
-    const int q = warp & 3;
-    const int half = e >> 2;
+    const int q = warp & 3;   // TMEM lane quadrant this warp may access
+    const int grp = e >> 2;   // 64-column group of the tile
     const int r = q * 32 + lane;
     const int et = threadIdx.x - 64;
     const float inv_a = (NP == 2) ? 1.f / ep.scale_a[0] : 1.f;
     const float inv_b = (NP == 2) ? 1.f / ep.scale_b[0] : 1.f;
     const bool want_h2 = NP == 2 && ep.h2_planes != nullptr;
     const float oscale = want_h2 ? ep.h2_scale[0] : 1.f;
-    const bool out_v8 = ep.out != nullptr && (ep.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(ep.out) & 31) == 0);
-    const bool h2_v8 = want_h2 && (ep.h2_ld % 16 == 0) && ((reinterpret_cast<uintptr_t>(ep.h2_planes) & 31) == 0) &&
-                       ((ep.h2_plane * 2) % 32 == 0);
+    unsigned char* stg = staging + e * 4096;  // this warp's staging box
     const bool masked = NP == 2 && (ep.mask_in != nullptr || ep.mask_out != nullptr || ep.colsum_part != nullptr ||
                                     ep.absmax_out != nullptr || want_h2);
+    const bool has_bias = ep.bias != nullptr;
     float amax = 0.f;
     int it = 0;
     for (int tile = cid; tile < n_tiles; tile += n_clusters, ++it) {
       const int mn = tile % mn_tiles, split = tile / mn_tiles;
       const int m0 = (mn % tiles_m) * 256 + rank * 128, n0 = (mn / tiles_m) * 256;
-      if (ep.bias != nullptr) {
-        asm volatile("bar.sync 2, %0;" ::"n"(32 * kLEpiWarps) : "memory");
+      if (has_bias) {
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * k2EpiWarps) : "memory");
         if (et < 256) s_bias[et] = (n0 + et < N) ? ep.bias[n0 + et] : 0.f;
-        asm volatile("bar.sync 2, %0;" ::"n"(32 * kLEpiWarps) : "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * k2EpiWarps) : "memory");
       }
-      const int row = m0 + r, col0 = n0 + half * 128;
+      const int row = m0 + r, col0 = n0 + grp * 64;
       const bool live = col0 < N;
-      uint4 mw = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      uint2 mw = make_uint2(0xffffffffu, 0xffffffffu);
       if (NP == 2 && ep.mask_in != nullptr && live && row < M)  // requested before the accumulator is waited for
-        mw = *reinterpret_cast<const uint4*>(ep.mask_in + (int64_t)row * ep.mask_ld + (col0 >> 5));
+        mw = *reinterpret_cast<const uint2*>(ep.mask_in + (int64_t)row * ep.mask_ld + (col0 >> 5));
+      K6_STAMP(1 + 4 * it);
       mbar_wait(acc_full, it & 1);
       tcgen05_fence_after();
-      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
-      uint32_t v[128];
-      if (live) {
+      K6_STAMP(2 + 4 * it);
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 64);
+      uint32_t mo[2] = {0u, 0u};
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
+      for (int cl = 0; cl < 2; ++cl) {
+        const int cc0 = col0 + cl * 32;
+        const bool on = cc0 < N;  // warp-uniform; a narrow remainder tile leaves chunks (or the whole warp) empty
+        float x[32];
+        if (on) {
           uint32_t w[32];
-          tmem_ld32(tacc + h * 32, v + h * 32);
-          tmem_ld32(tacc + 256 + h * 32, w);
+          tmem_ld32_async(tacc + cl * 32, reinterpret_cast<uint32_t*>(x));
+          tmem_ld32_async(tacc + 256 + cl * 32, w);
+          tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[h * 32 + j] = __float_as_uint(lin_combine<NP>(__uint_as_float(v[h * 32 + j]), __uint_as_float(w[j]),
-                                                            inv_a, inv_b));
+          for (int j = 0; j < 32; ++j) x[j] = lin_combine<NP>(x[j], __uint_as_float(w[j]), inv_a, inv_b);
         }
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(acc_empty);
-      if (live) {
-        const bool has_bias = ep.bias != nullptr;
-        const uint32_t mwa[4] = {mw.x, mw.y, mw.z, mw.w};
-        uint32_t mo[4] = {0u, 0u, 0u, 0u};
-        float* orow = ep.out != nullptr ? ep.out + ((int64_t)split * M + row) * ep.ldo + col0 : nullptr;
-        unsigned short* prow = want_h2 ? ep.h2_planes + (int64_t)row * ep.h2_ld + col0 : nullptr;
+        if (cl == 1) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(acc_empty);
+          K6_STAMP(3 + 4 * it);
+        }
+        if (on) {
+          if (has_bias) {  // 8 independent 16-byte broadcast loads
+            float4 bq[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int cc0 = col0 + c * 32;
-          if (cc0 < N) {  // warp-uniform
-            float x[32];
+            for (int j4 = 0; j4 < 8; ++j4) bq[j4] = *reinterpret_cast<const float4*>(&s_bias[grp * 64 + cl * 32 + 4 * j4]);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float t = __uint_as_float(v[c * 32 + j]);
-              if (has_bias) t += s_bias[half * 128 + c * 32 + j];
-              if (ep.relu) t = fmaxf(t, 0.f);
-              x[j] = t;
-            }
-            if (masked) {  // warp-uniform: the plain fp32 product (wgrad partials, per-layer path) skips all of this
-              const int nvalid = min(32, N - cc0);
-              uint32_t keep = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);  // TMEM columns >= N hold nothing
-              keep = row < M ? (keep & mwa[c]) : 0u;
-              uint32_t bits = 0u;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float t = ((keep >> j) & 1u) ? x[j] : 0.f;
-                bits |= (t > 0.f ? 1u : 0u) << j;
-                amax = fmaxf(amax, fabsf(t));
-                x[j] = t;
-              }
-              mo[c] = bits;
-            }
-            if (row < M) {
-              if (orow != nullptr) {
-                if (out_v8) {
-#pragma unroll
-                  for (int j = 0; j < 32; j += 8)
-                    if (cc0 + j < N) st_global_v8(orow + c * 32 + j, x + j);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 32; j += 4)
-                    if (cc0 + j < N)  // ldo % 4 == 0 and ldo >= round_up(N, 4): the whole group is inside the pitch
-                      *reinterpret_cast<float4*>(orow + c * 32 + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-                }
-              }
-              if (want_h2) {
-                unsigned short* o0 = prow + c * 32;
-                unsigned short* o1 = o0 + ep.h2_plane;
-#pragma unroll
-                for (int g = 0; g < 32; g += 16) {  // 16 columns of each plane at a time, two fp16 per word
-                  if (cc0 + g < N) {                // pitch % 8 == 0 (% 16 for the 256-bit form): groups stay inside the row
-                    uint32_t p0[8], p1[8];
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                      __half a0, a1, b0, b1;
-                      split2h(x[g + j], oscale, a0, a1);
-                      split2h(x[g + j + 1], oscale, b0, b1);
-                      p0[j >> 1] = (uint32_t)__half_as_ushort(a0) | ((uint32_t)__half_as_ushort(b0) << 16);
-                      p1[j >> 1] = (uint32_t)__half_as_ushort(a1) | ((uint32_t)__half_as_ushort(b1) << 16);
-                    }
-                    if (h2_v8) {
-                      st_global_v8(o0 + g, p0);
-                      st_global_v8(o1 + g, p1);
-                    } else {
-                      *reinterpret_cast<uint4*>(o0 + g) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
-                      *reinterpret_cast<uint4*>(o1 + g) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-                      if (cc0 + g + 8 < N) {
-                        *reinterpret_cast<uint4*>(o0 + g + 8) = make_uint4(p0[4], p0[5], p0[6], p0[7]);
-                        *reinterpret_cast<uint4*>(o1 + g + 8) = make_uint4(p1[4], p1[5], p1[6], p1[7]);
-                      }
-                    }
-                  }
-                }
-              }
-              if (NP == 3 && ep.planes != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  if (cc0 + j < N) split3_store4(x + j, ep.planes + (int64_t)row * ep.pl_ld + cc0 + j, ep.pl_plane);
-              }
-            }
-            if (NP == 2 && ep.colsum_part != nullptr) {
-              // column sums over the warp's 32 rows: a butterfly that halves the columns a lane carries at every step
-              // (31 shuffles for 32 columns); lane l ends with column l.  Fixed order: deterministic.
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                const bool up = (lane & o) != 0;
-#pragma unroll
-                for (int k = 0; k < o; ++k) {
-                  const float send = up ? x[k] : x[k + o];
-                  const float recv = __shfl_xor_sync(0xffffffffu, send, o);
-                  x[k] = (up ? x[k + o] : x[k]) + recv;
-                }
-              }
-              if (cc0 + lane < N) ep.colsum_part[(int64_t)((m0 + q * 32) >> 5) * N + cc0 + lane] = x[0];
+            for (int j4 = 0; j4 < 8; ++j4) {
+              x[4 * j4] += bq[j4].x; x[4 * j4 + 1] += bq[j4].y; x[4 * j4 + 2] += bq[j4].z; x[4 * j4 + 3] += bq[j4].w;
             }
           }
+          if (ep.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+          }
+          if (masked) {  // warp-uniform: the plain fp32 product (wgrad partials, per-layer path) skips all of this
+            const int nvalid = min(32, N - cc0);
+            uint32_t keep = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);  // TMEM columns >= N hold nothing
+            keep = row < M ? (keep & (cl == 0 ? mw.x : mw.y)) : 0u;
+            uint32_t bits = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float t = ((keep >> j) & 1u) ? x[j] : 0.f;
+              bits |= (t > 0.f ? 1u : 0u) << j;
+              amax = fmaxf(amax, fabsf(t));
+              x[j] = t;
+            }
+            mo[cl] = bits;
+          }
+          if (ep.out != nullptr) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the box's last store has read it
+            __syncwarp();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)  // row = lane, 128 B per row, 16-byte chunk j4 at j4 ^ (row & 7): SWIZZLE_128B
+              *reinterpret_cast<float4*>(stg + lane * 128 + ((j4 ^ (lane & 7)) << 4)) =
+                  make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&maps.c, stg, cc0, m0 + q * 32, split);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          if (want_h2) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 32; g += 16) {  // 16 columns at a time (register pressure), two fp16 per word
+              uint32_t p0[8], p1[8];
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                __half a0, a1, b0, b1;
+                split2h(x[g + j], oscale, a0, a1);
+                split2h(x[g + j + 1], oscale, b0, b1);
+                p0[j >> 1] = (uint32_t)__half_as_ushort(a0) | ((uint32_t)__half_as_ushort(b0) << 16);
+                p1[j >> 1] = (uint32_t)__half_as_ushort(a1) | ((uint32_t)__half_as_ushort(b1) << 16);
+              }
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {  // 64 B per row and plane, 16-byte chunk j4 at j4 ^ ((row >> 1) & 3): SWIZZLE_64B
+                const int j4 = (g >> 3) + h;
+                const int o = lane * 64 + ((j4 ^ ((lane >> 1) & 3)) << 4);
+                *reinterpret_cast<uint4*>(stg + o) = make_uint4(p0[4 * h], p0[4 * h + 1], p0[4 * h + 2], p0[4 * h + 3]);
+                *reinterpret_cast<uint4*>(stg + 2048 + o) = make_uint4(p1[4 * h], p1[4 * h + 1], p1[4 * h + 2], p1[4 * h + 3]);
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&maps.p, stg, cc0, m0 + q * 32, 0);
+              tma_store_3d(&maps.p, stg + 2048, cc0, m0 + q * 32, 1);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          if (NP == 3 && ep.planes != nullptr && row < M) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (cc0 + j < N) split3_store4(x + j, ep.planes + (int64_t)row * ep.pl_ld + cc0 + j, ep.pl_plane);
+          }
+          if (NP == 2 && ep.colsum_part != nullptr) {
+            // column sums over the warp's 32 rows: a butterfly that halves the columns a lane carries at every step
+            // (31 shuffles for 32 columns); lane l ends with column l.  Fixed order: deterministic.
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const bool up = (lane & o) != 0;
+#pragma unroll
+              for (int k = 0; k < o; ++k) {
+                const float send = up ? x[k] : x[k + o];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, o);
+                x[k] = (up ? x[k + o] : x[k]) + recv;
+              }
+            }
+            if (cc0 + lane < N) ep.colsum_part[(int64_t)((m0 + q * 32) >> 5) * N + cc0 + lane] = x[0];
+          }
         }
-        if (NP == 2 && ep.mask_out != nullptr && row < M)
-          *reinterpret_cast<uint4*>(ep.mask_out + (int64_t)row * ep.mask_ld + (col0 >> 5)) = make_uint4(mo[0], mo[1], mo[2], mo[3]);
       }
+      if (NP == 2 && ep.mask_out != nullptr && live && row < M)
+        *reinterpret_cast<uint2*>(ep.mask_out + (int64_t)row * ep.mask_ld + (col0 >> 5)) = make_uint2(mo[0], mo[1]);
+      K6_STAMP(4 + 4 * it);
     }
+    K6_STAMP(13);
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's TMA stores have landed
+    K6_STAMP(14);
     if (ep.absmax_out != nullptr) {  // one combining atomic per warp (non-negative floats order as uints)
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -1165,6 +1192,25 @@ static int make_map3_mn(CUtensorMap* map, const void* base, int64_t k_rows, int6
   return PTREC_OK;
 }
 
+// Output of the CTA-pair kernel's TMA stores: 3-D (cols, rows, slab) over [slabs][rows][ld], boxes of 32 x 32 x 1.
+// fp32 result: slab = split-K partial, 128-byte swizzle; fp16 planes: slab = plane, 64-byte swizzle.
+static int make_map_out(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int64_t slab,
+                        int64_t slabs, bool f16) {
+  EncodeTiledFn enc = get_encode();
+  PTREC_CHECK_ARG(enc != nullptr, PTREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t esz = f16 ? 2 : 4;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)slabs};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * esz, (cuuint64_t)slab * esz};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PTREC_CHECK_ARG(r == CUDA_SUCCESS, PTREC_ECUDA, "cuTensorMapEncodeTiled(output) failed (%d)", (int)r);
+  return PTREC_OK;
+}
+
 }  // namespace ptrec
 
 using namespace ptrec;
@@ -1304,13 +1350,13 @@ static int gemm_launch(bool mn_major, bool two_sm, bool db, int bk, int sms, con
     const int64_t clusters = std::min<int64_t>(pair_tiles, sms / 2);
     const unsigned grid2 = (unsigned)(2 * clusters);
     if (mn_major && bk == 64)
-      gemm_split3_2sm_kernel<true, 64, NP><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+      gemm_split3_2sm_kernel<true, 64, NP><<<grid2, k2Threads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
     else if (mn_major)
-      gemm_split3_2sm_kernel<true, 32, NP><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+      gemm_split3_2sm_kernel<true, 32, NP><<<grid2, k2Threads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
     else if (bk == 64)
-      gemm_split3_2sm_kernel<false, 64, NP><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+      gemm_split3_2sm_kernel<false, 64, NP><<<grid2, k2Threads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
     else
-      gemm_split3_2sm_kernel<false, 32, NP><<<grid2, kLThreads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
+      gemm_split3_2sm_kernel<false, 32, NP><<<grid2, k2Threads, k2Smem, st>>>(maps, (int)M, (int)N, (int)K, ep);
     PTREC_LAUNCH_CHECK("gemm_split3_2sm_kernel");
   } else {
     const int64_t tiles = ceil_div(N, kLBN) * ceil_div(M, kLBM) * splits;
@@ -1386,6 +1432,10 @@ static int gemm_split_impl(int np, bool mn_major, const void* a_planes, const fl
   ep.absmax_out = reinterpret_cast<uint32_t*>(absmax_out);
   ep.h2_planes = nullptr; ep.h2_ld = 0; ep.h2_plane = 0; ep.h2_scale = nullptr;
   ep.mask_in = nullptr; ep.mask_out = nullptr; ep.mask_ld = 0; ep.colsum_part = nullptr;
+  if (two_sm && !db && ep.out != nullptr) {  // the CTA-pair kernel stores through TMA
+    rc = make_map_out(&maps.c, ep.out, M, N, ldo, M * ldo, splits, false);
+    if (rc != PTREC_OK) return rc;
+  }
   if (fu != nullptr) {
     PTREC_CHECK_ARG(np == 2 && two_sm && !db && !mn_major && splits == 1, PTREC_EUNSUPPORTED,
                     "tc_gemm_split2h_fused needs the CTA-pair fp16 x 2 kernel (256-wide tiles), K-major operands, no split-K");
@@ -1401,6 +1451,10 @@ static int gemm_split_impl(int np, bool mn_major, const void* a_planes, const fl
     ep.h2_planes = reinterpret_cast<unsigned short*>(fu->h2_planes); ep.h2_ld = fu->h2_ld; ep.h2_plane = M * fu->h2_ld;
     ep.h2_scale = fu->h2_scale; ep.mask_in = fu->mask_in; ep.mask_out = fu->mask_out; ep.mask_ld = fu->mask_ld;
     ep.colsum_part = fu->colsum ? reinterpret_cast<float*>(workspace) : nullptr;
+    if (ep.h2_planes != nullptr) {
+      rc = make_map_out(&maps.p, ep.h2_planes, M, N, ep.h2_ld, ep.h2_plane, 2, true);
+      if (rc != PTREC_OK) return rc;
+    }
     const int rc2 = gemm_launch<2>(false, true, false, bk, sms, maps, M, N, K, ep, out, st);
     if (rc2 != PTREC_OK) return rc2;
     if (fu->colsum) {
@@ -1478,3 +1532,9 @@ extern "C" int ptrec_tc_gemm_split2h_fused(const void* a_planes, const float* sc
   return gemm_split_impl(2, false, a_planes, scale_a, M, lda, b_planes, scale_b, N, ldb, K, bias, relu, out, ldo, nullptr,
                          0, absmax_out, 1, workspace, workspace_bytes, stream, &fu);
 }
+
+#ifdef PTREC_K6_TIMELINE
+extern "C" int ptrec_debug_k6_timeline(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(ptrec::g_k6_timeline, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
+}
+#endif
