@@ -782,8 +782,9 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
     // two chunks of 32: bias, ReLU, the ReLU-backward bit mask of the layer below (one word per row and chunk), the > 0
     // bits of the result, |max|, column sums (bias gradient) by a fixed butterfly over the warp's rows.  The result
     // leaves as fp32 and / or as the consumer's two fp16 planes through a swizzled 4 KB staging box per warp and one
-    // TMA store per box (whole 128-byte lines, clipped at M / N by the tensor map).  TMEM goes back to the tensor core
-    // as soon as the warp's second chunk is in registers.
+    // TMA store per box (whole 128-byte lines, clipped at M / N by the tensor map): per-thread-row stores (32 lines per
+    // instruction, 16 or 32 bytes each) back up the LSU and measured 1.5x - 2.5x this epilogue's time
+    // (tools/diag_k6_timeline.py).  TMEM goes back to the tensor core as soon as the warp's second chunk is in registers.
     const int e = warp - 2;
     const int q = warp & 3;   // TMEM lane quadrant this warp may access
     const int grp = e >> 2;   // 64-column group of the tile
