@@ -36,7 +36,11 @@ extern "C" {
 #define PTREC_ECUDA (-4)        /* a CUDA runtime call failed                     */
 #define PTREC_EWORKSPACE (-5)   /* workspace too small                            */
 
-/* table element types */
+/* table element types (the `dtype` argument of K1 / K2).  PTREC_BF16: rows stored as bf16 — half the HBM bytes per
+ * lookup; row_stride counts ELEMENTS.  K1 widens the row exactly to fp32 (outputs, pooling and every gradient stay
+ * fp32); K2b widens the row, applies the optimizer in fp32 against fp32 state tensors (same row stride in elements, not
+ * interleaved with the weights) and rounds the row back to bf16 (nearest even).  The row-wise sharded entry points
+ * take fp32 tables only. */
 #define PTREC_F32 0
 #define PTREC_BF16 1
 

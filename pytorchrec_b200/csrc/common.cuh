@@ -134,6 +134,61 @@ __device__ __forceinline__ void store_row(float* p, const RowVec<VEC>& r) {
   }
 }
 
+// ---- bf16 tables (dtype PTREC_BF16): rows stored as bf16, every computation in fp32.  VEC elements = VEC * 2 bytes.
+// bf16 -> fp32 is exact (a 16-bit shift); fp32 -> bf16 rounds to nearest even.
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
+__device__ __forceinline__ uint32_t float_to_bf16_bits(float f) {
+  uint32_t u = __float_as_uint(f);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (u >> 16) | 0x40u;  // NaN stays NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return u >> 16;
+}
+template <int VEC, bool STREAM>
+__device__ __forceinline__ RowVec<VEC> load_row_bf16(const uint16_t* p) {
+  RowVec<VEC> r;
+  if constexpr (VEC == 4) {
+    uint2 t;
+    if constexpr (STREAM) asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(t.x), "=r"(t.y) : "l"(p));
+    else t = *reinterpret_cast<const uint2*>(p);
+    r.v[0] = bf16_bits_to_float(t.x & 0xffffu); r.v[1] = bf16_bits_to_float(t.x >> 16);
+    r.v[2] = bf16_bits_to_float(t.y & 0xffffu); r.v[3] = bf16_bits_to_float(t.y >> 16);
+  } else if constexpr (VEC == 2) {
+    uint32_t t;
+    if constexpr (STREAM) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(t) : "l"(p));
+    else t = *reinterpret_cast<const uint32_t*>(p);
+    r.v[0] = bf16_bits_to_float(t & 0xffffu); r.v[1] = bf16_bits_to_float(t >> 16);
+  } else {
+    uint16_t t;
+    if constexpr (STREAM) asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(t) : "l"(p));
+    else t = *p;
+    r.v[0] = bf16_bits_to_float(t);
+  }
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void store_row_bf16(uint16_t* p, const RowVec<VEC>& r) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(float_to_bf16_bits(r.v[0]) | (float_to_bf16_bits(r.v[1]) << 16),
+                                              float_to_bf16_bits(r.v[2]) | (float_to_bf16_bits(r.v[3]) << 16));
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<uint32_t*>(p) = float_to_bf16_bits(r.v[0]) | (float_to_bf16_bits(r.v[1]) << 16);
+  } else {
+    *p = (uint16_t)float_to_bf16_bits(r.v[0]);
+  }
+}
+// table rows of either element type behind one pointer: WB = weights are bf16
+template <int VEC, bool WB, bool STREAM>
+__device__ __forceinline__ RowVec<VEC> load_table_row(const void* base, int64_t elem_off) {
+  if constexpr (WB) return load_row_bf16<VEC, STREAM>(reinterpret_cast<const uint16_t*>(base) + elem_off);
+  else if constexpr (STREAM) return load_row_stream<VEC>(reinterpret_cast<const float*>(base) + elem_off);
+  else return load_row<VEC>(reinterpret_cast<const float*>(base) + elem_off);
+}
+template <int VEC, bool WB>
+__device__ __forceinline__ void store_table_row(void* base, int64_t elem_off, const RowVec<VEC>& r) {
+  if constexpr (WB) store_row_bf16<VEC>(reinterpret_cast<uint16_t*>(base) + elem_off, r);
+  else store_row<VEC>(reinterpret_cast<float*>(base) + elem_off, r);
+}
+
 // ---- mbarrier + 1-D TMA bulk copy (global -> shared), used to stage index lists -------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -62,17 +62,19 @@ __device__ __forceinline__ float group_sum_sq(const RowVec<VEC>& g) {
 
 // Row state issued BEFORE the gradient gather so that the weight / state reads overlap it
 // (they depend only on the segment key, not on the gradient).
-template <int VEC, int OPT>
+// WB: the weights are bf16 (dtype PTREC_BF16): widened exactly on load, rounded to nearest even on store; optimizer
+// state and all arithmetic stay fp32 (state tensors then have the weight's row stride IN ELEMENTS, no interleaving).
+template <int VEC, int OPT, bool WB = false>
 struct RowState {
   RowVec<VEC> w, a, b;  // weight, state1 slice, state2 slice
   float r;              // row-wise state
   __device__ __forceinline__ void clear() { w.zero(); a.zero(); b.zero(); r = 0.f; }
-  __device__ __forceinline__ void load(const float* wrow, const float* s1, const float* s2, int64_t row,
+  __device__ __forceinline__ void load(const void* wrow, const float* s1, const float* s2, int64_t row,
                                        int64_t row_stride, int lane, bool lane_on) {
     const int64_t off = row * row_stride + lane * VEC;
     clear();
     if constexpr (OPT == kOptNone) return;
-    if (lane_on) w = load_row<VEC>(wrow + off);
+    if (lane_on) w = load_table_row<VEC, WB, false>(wrow, off);
     if constexpr (OPT == PTREC_OPT_ADAGRAD) { if (lane_on) a = load_row<VEC>(s1 + off); }
     if constexpr (OPT == PTREC_OPT_ROWWISE_ADAGRAD) { r = s1[row]; }
     if constexpr (OPT == PTREC_OPT_LAZY_ADAM) {
@@ -82,8 +84,8 @@ struct RowState {
 };
 
 // apply the optimizer to this lane's VEC-float slice of row `row`
-template <int VEC, int LPR, int OPT>
-__device__ __forceinline__ void apply_update(RowVec<VEC> g, const RowState<VEC, OPT>& st, float* __restrict__ wrow,
+template <int VEC, int LPR, int OPT, bool WB = false>
+__device__ __forceinline__ void apply_update(RowVec<VEC> g, const RowState<VEC, OPT, WB>& st, void* __restrict__ wrow,
                                              float* __restrict__ s1, float* __restrict__ s2,
                                              int64_t row, int D, int lane, bool lane_on,
                                              const OptParams& op, float* row_grad_out) {
@@ -132,7 +134,7 @@ __device__ __forceinline__ void apply_update(RowVec<VEC> g, const RowState<VEC, 
       store_row<VEC>(s2 + off, v);
     }
   }
-  if (lane_on) store_row<VEC>(wrow + off, w);
+  if (lane_on) store_table_row<VEC, WB>(wrow, off, w);
 }
 
 // Per-CTA shared lookup: features of each table (contiguous range) and each feature's first slot.
@@ -181,7 +183,7 @@ __device__ __forceinline__ RowVec<VEC> slot_grad(const SlotMap* m, int t, int64_
   return g;
 }
 
-template <int VEC, int LPR, int OPT>
+template <int VEC, int LPR, int OPT, bool WB>
 __global__ void __launch_bounds__(kUpdThreads)
 fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restrict__ state1_ptrs,
                     void* const* __restrict__ state2_ptrs, int T, int D,
@@ -234,10 +236,10 @@ fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restric
     }
     fetch_meta(r + gridDim.x);
     // round 3: weight / state rows and the first gradient row of every segment
-    float* wrow[SEGS];
+    void* wrow[SEGS];
     float* s1[SEGS];
     float* s2[SEGS];
-    RowState<VEC, OPT> st[SEGS];
+    RowState<VEC, OPT, WB> st[SEGS];
     RowVec<VEC> acc[SEGS];
 #pragma unroll
     for (int q = 0; q < SEGS; ++q) {
@@ -252,12 +254,13 @@ fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restric
         lw.chunk_base[old >> 32] = (int32_t)(old & 0xffffffffu);
       }
       work[q] = live[q] && !masked && !is_long;
-      wrow[q] = s1[q] = s2[q] = nullptr;
+      wrow[q] = nullptr;
+      s1[q] = s2[q] = nullptr;
       st[q].clear();
       acc[q].zero();
       if (work[q]) {
         if constexpr (OPT != kOptNone) {
-          wrow[q] = reinterpret_cast<float*>(table_ptrs[tab[q]]);
+          wrow[q] = table_ptrs[tab[q]];
           if (state1_ptrs) s1[q] = reinterpret_cast<float*>(state1_ptrs[tab[q]]);
           if (state2_ptrs) s2[q] = reinterpret_cast<float*>(state2_ptrs[tab[q]]);
           st[q].load(wrow[q], s1[q], s2[q], (int64_t)key[q], op.row_stride, lane, lane_on);
@@ -286,11 +289,11 @@ fused_update_kernel(void* const* __restrict__ table_ptrs, void* const* __restric
     for (int q = 0; q < SEGS; ++q) {
       const int u = (r * SEGS + q) * NSG + sg;
       if constexpr (OPT == kOptNone) {
-        if (live[q]) apply_update<VEC, LPR, OPT>(acc[q], st[q], nullptr, nullptr, nullptr, 0, D, lane, lane_on, op,
-                                                 row_grad + (int64_t)u * D);
+        if (live[q]) apply_update<VEC, LPR, OPT, WB>(acc[q], st[q], nullptr, nullptr, nullptr, 0, D, lane, lane_on, op,
+                                                     row_grad + (int64_t)u * D);
       } else {
-        if (work[q]) apply_update<VEC, LPR, OPT>(acc[q], st[q], wrow[q], s1[q], s2[q], (int64_t)key[q], D, lane, lane_on,
-                                                 op, nullptr);
+        if (work[q]) apply_update<VEC, LPR, OPT, WB>(acc[q], st[q], wrow[q], s1[q], s2[q], (int64_t)key[q], D, lane,
+                                                     lane_on, op, nullptr);
       }
     }
   }
@@ -370,7 +373,7 @@ fused_update_chunk_kernel(int T, int D, const ptrec_feature_desc* __restrict__ f
 }
 
 // pass B: CTA per queued run: reduce it (directly, or from its chunks' partial rows in chunk order) and update the row
-template <int VEC, int LPR, int OPT>
+template <int VEC, int LPR, int OPT, bool WB>
 __global__ void __launch_bounds__(kLongThreads)
 fused_update_long_kernel(void* const* __restrict__ table_ptrs, void* const* __restrict__ state1_ptrs,
                          void* const* __restrict__ state2_ptrs, int T, int D,
@@ -412,18 +415,18 @@ fused_update_long_kernel(void* const* __restrict__ table_ptrs, void* const* __re
     }
     if (sg == 0) {  // sub-warp 0 owns the row
       const uint32_t key = sorted_keys[start];
-      float* wrow = reinterpret_cast<float*>(table_ptrs[t]);
+      void* wrow = table_ptrs[t];
       float* s1 = state1_ptrs ? reinterpret_cast<float*>(state1_ptrs[t]) : nullptr;
       float* s2 = state2_ptrs ? reinterpret_cast<float*>(state2_ptrs[t]) : nullptr;
-      RowState<VEC, OPT> st;
+      RowState<VEC, OPT, WB> st;
       st.load(wrow, s1, s2, (int64_t)key, op.row_stride, lane, lane_on);
-      apply_update<VEC, LPR, OPT>(tot, st, wrow, s1, s2, (int64_t)key, D, lane, lane_on, op, nullptr);
+      apply_update<VEC, LPR, OPT, WB>(tot, st, wrow, s1, s2, (int64_t)key, D, lane, lane_on, op, nullptr);
     }
     __syncthreads();
   }
 }
 
-template <int VEC, int LPR, int OPT>
+template <int VEC, int LPR, int OPT, bool WB>
 static int launch_update(void* const* table_ptrs, void* const* s1, void* const* s2, int T, int D,
                          const ptrec_feature_desc* feats, int F, int64_t B, int64_t N,
                          const uint32_t* sorted_keys, const int32_t* perm, const int32_t* seg_start,
@@ -438,7 +441,7 @@ static int launch_update(void* const* table_ptrs, void* const* s1, void* const* 
   // 4 CTAs per SM (register-limited): one wave, several rounds per CTA so that the metadata prefetch has a next round
   const unsigned grid = (unsigned)(rounds < (int64_t)sms * 4 ? (rounds > 0 ? rounds : 1) : (int64_t)sms * 4);
   if (OPT != kOptNone) PTREC_CUDA(cudaMemsetAsync(long_ws.counter, 0, sizeof(unsigned long long), st));
-  fused_update_kernel<VEC, LPR, OPT><<<grid, kUpdThreads, 0, st>>>(
+  fused_update_kernel<VEC, LPR, OPT, WB><<<grid, kUpdThreads, 0, st>>>(
       table_ptrs, s1, s2, T, D, feats, F, B, sorted_keys, perm, seg_start, seg_meta, n_seg, grad_out,
       stride, bag_scale, op, long_ws, row_grad);
   PTREC_LAUNCH_CHECK("fused_update_kernel");
@@ -446,7 +449,7 @@ static int launch_update(void* const* table_ptrs, void* const* s1, void* const* 
     fused_update_chunk_kernel<VEC, LPR><<<sms * 2, kLongThreads, 0, st>>>(T, D, feats, F, B, perm, seg_start, seg_meta,
                                                                         grad_out, stride, bag_scale, long_ws);
     PTREC_LAUNCH_CHECK("fused_update_chunk_kernel");
-    fused_update_long_kernel<VEC, LPR, OPT><<<sms * 2, kLongThreads, 0, st>>>(
+    fused_update_long_kernel<VEC, LPR, OPT, WB><<<sms * 2, kLongThreads, 0, st>>>(
         table_ptrs, s1, s2, T, D, feats, F, B, sorted_keys, perm, seg_start, seg_meta, grad_out, stride,
         bag_scale, op, long_ws);
     PTREC_LAUNCH_CHECK("fused_update_long_kernel");
@@ -454,7 +457,7 @@ static int launch_update(void* const* table_ptrs, void* const* s1, void* const* 
   return PTREC_OK;
 }
 
-template <int OPT>
+template <int OPT, bool WB = false>
 static int dispatch_D(void* const* table_ptrs, void* const* s1, void* const* s2, int T, int D,
                       const ptrec_feature_desc* feats, int F, int64_t B, int64_t N,
                       const uint32_t* sorted_keys, const int32_t* perm, const int32_t* seg_start,
@@ -462,7 +465,7 @@ static int dispatch_D(void* const* table_ptrs, void* const* s1, void* const* s2,
                       int64_t stride, const float* bag_scale, const OptParams& op, const LongWs& long_ws,
                       float* row_grad, cudaStream_t st) {
 #define PTREC_UPD(V, P) \
-  return launch_update<V, P, OPT>(table_ptrs, s1, s2, T, D, feats, F, B, N, sorted_keys, perm, seg_start, \
+  return launch_update<V, P, OPT, WB>(table_ptrs, s1, s2, T, D, feats, F, B, N, sorted_keys, perm, seg_start, \
                                   seg_meta, n_seg, grad_out, stride, bag_scale, op, long_ws, row_grad, st)
   if (D == 1) PTREC_UPD(1, 1);
   if (D == 2) PTREC_UPD(2, 1);
@@ -495,7 +498,7 @@ static int64_t total_slots(const ptrec_feature_desc* feats_host, int F, int64_t 
 
 static int check_common(int32_t T, int32_t D, int32_t dtype, int32_t F, const void* grad_out,
                         int64_t stride) {
-  PTREC_CHECK_ARG(dtype == PTREC_F32, PTREC_EUNSUPPORTED, "bwd: only fp32 tables are built (dtype=%d)", dtype);
+  PTREC_CHECK_ARG(dtype == PTREC_F32 || dtype == PTREC_BF16, PTREC_EUNSUPPORTED, "bwd: unknown table dtype %d", dtype);
   PTREC_CHECK_ARG(T >= 1 && T <= kMaxTables && F >= 1 && F <= kMaxFeatures, PTREC_EINVAL, "bwd: T=%d F=%d out of range", T, F);
   const bool d_ok = D == 1 || D == 2 || (D >= 4 && D <= 128 && D % 4 == 0);
   PTREC_CHECK_ARG(d_ok, PTREC_EUNSUPPORTED, "bwd: D=%d unsupported", D);
@@ -552,23 +555,24 @@ extern "C" int ptrec_embedding_bwd_fused(void* const* table_ptrs, void* const* s
 #define PTREC_ARGS                                                                                      \
   table_ptrs, state1_ptrs, state2_ptrs, T, D, feats, F, B, N, sorted_keys, perm, seg_start, seg_meta, n_seg, \
       grad_out, grad_row_stride, bag_scale, op, long_ws, nullptr, st
+  const bool wb = dtype == PTREC_BF16;
   switch (opt_host->kind) {
     case PTREC_OPT_SGD:
-      return dispatch_D<PTREC_OPT_SGD>(PTREC_ARGS);
+      return wb ? dispatch_D<PTREC_OPT_SGD, true>(PTREC_ARGS) : dispatch_D<PTREC_OPT_SGD>(PTREC_ARGS);
     case PTREC_OPT_ADAGRAD:
       PTREC_CHECK_ARG(state1_ptrs, PTREC_EINVAL, "bwd_fused: Adagrad needs state1");
       op.lr = (float)((double)opt_host->lr / (1.0 + (double)(step - 1) * (double)opt_host->lr_decay));
-      return dispatch_D<PTREC_OPT_ADAGRAD>(PTREC_ARGS);
+      return wb ? dispatch_D<PTREC_OPT_ADAGRAD, true>(PTREC_ARGS) : dispatch_D<PTREC_OPT_ADAGRAD>(PTREC_ARGS);
     case PTREC_OPT_ROWWISE_ADAGRAD:
       PTREC_CHECK_ARG(state1_ptrs, PTREC_EINVAL, "bwd_fused: row-wise Adagrad needs state1");
       op.lr = (float)((double)opt_host->lr / (1.0 + (double)(step - 1) * (double)opt_host->lr_decay));
-      return dispatch_D<PTREC_OPT_ROWWISE_ADAGRAD>(PTREC_ARGS);
+      return wb ? dispatch_D<PTREC_OPT_ROWWISE_ADAGRAD, true>(PTREC_ARGS) : dispatch_D<PTREC_OPT_ROWWISE_ADAGRAD>(PTREC_ARGS);
     case PTREC_OPT_LAZY_ADAM: {
       PTREC_CHECK_ARG(state1_ptrs && state2_ptrs, PTREC_EINVAL, "bwd_fused: lazy Adam needs state1 and state2");
       const double bc1 = 1.0 - pow((double)opt_host->beta1, (double)step);
       const double bc2 = 1.0 - pow((double)opt_host->beta2, (double)step);
       op.lr = (float)((double)opt_host->lr * sqrt(bc2) / bc1);
-      return dispatch_D<PTREC_OPT_LAZY_ADAM>(PTREC_ARGS);
+      return wb ? dispatch_D<PTREC_OPT_LAZY_ADAM, true>(PTREC_ARGS) : dispatch_D<PTREC_OPT_LAZY_ADAM>(PTREC_ARGS);
     }
     default:
       PTREC_CHECK_ARG(false, PTREC_EINVAL, "bwd_fused: unknown optimizer kind %d", opt_host->kind);

@@ -1,7 +1,8 @@
 // K1: multi-table embedding gather + sum/mean/sqrtn pooling (forward), and index_prep.
 //
 // Bound: HBM.  Algorithmic bytes per launch = lookups*8 (ids) + lookups*D*4 (rows) + bags*D*4 (out).
-// Layout: tables are independent [rows, D] fp32 row-major arrays reached through a device pointer
+// Layout: tables are independent [rows, D] fp32 (or bf16, dtype PTREC_BF16: same kernels, rows read as bf16 and
+// widened exactly; output and pooling arithmetic stay fp32) row-major arrays reached through a device pointer
 // array; ids are feature-major padded matrices; output rows are sample-major so that the DNN input
 // is a view of them.
 //
@@ -30,7 +31,7 @@ constexpr int kUnroll = 4;
 // SHARDED: the tables are row-wise shards owned by `shards` GPUs of one NVLink domain (owner = id mod shards,
 // local row = id div shards); table_ptrs is [T][shards] and may hold PEER pointers, so the same 128-bit row loads
 // travel over NVLink / NVSwitch and the lookup needs no collective.  table_rows stays the GLOBAL row count.
-template <int VEC, int LPR, bool SHARDED>
+template <int VEC, int LPR, bool SHARDED, bool WB>
 __global__ void __launch_bounds__(kOneHotThreads)
 gather_onehot_kernel(const void* const* __restrict__ table_ptrs, const int64_t* __restrict__ table_rows,
                      int D, int64_t row_stride, const ptrec_feature_desc* __restrict__ feats, FeatSel sel,
@@ -41,7 +42,7 @@ gather_onehot_kernel(const void* const* __restrict__ table_ptrs, const int64_t* 
   int64_t* s_ids = reinterpret_cast<int64_t*>(smem_raw);
   const int nsel = sel.n;
   const int nsh = SHARDED ? shards : 1;
-  const float** s_tab = reinterpret_cast<const float**>(s_ids + (size_t)nsel * kOneHotTileB);
+  const void** s_tab = reinterpret_cast<const void**>(s_ids + (size_t)nsel * kOneHotTileB);
   int64_t* s_rows = reinterpret_cast<int64_t*>(s_tab + (size_t)nsel * nsh);
   int64_t* s_col = s_rows + nsel;
   int64_t* s_flag = s_col + nsel;
@@ -61,7 +62,7 @@ gather_onehot_kernel(const void* const* __restrict__ table_ptrs, const int64_t* 
   for (int s = tid; s < nsel; s += blockDim.x) {
     const ptrec_feature_desc fd = feats[sel.idx[s]];
     for (int g = 0; g < nsh; ++g)
-      s_tab[(size_t)s * nsh + g] = reinterpret_cast<const float*>(table_ptrs[(size_t)fd.table * nsh + g]);
+      s_tab[(size_t)s * nsh + g] = table_ptrs[(size_t)fd.table * nsh + g];
     s_rows[s] = table_rows[fd.table];
     s_col[s] = fd.out_col;
     s_flag[s] = fd.flags;
@@ -99,7 +100,7 @@ gather_onehot_kernel(const void* const* __restrict__ table_ptrs, const int64_t* 
         const int64_t id = s_ids[(size_t)s * kOneHotTileB + bl];
         dst[u] = out + (b0 + bl) * out_row_stride + s_col[s] + lane * VEC;
         if ((uint64_t)id < (uint64_t)s_rows[s]) {
-          const float* tab;
+          const void* tab;
           int64_t row;
           if (SHARDED) {
             int own;
@@ -116,7 +117,7 @@ gather_onehot_kernel(const void* const* __restrict__ table_ptrs, const int64_t* 
             tab = s_tab[s];
             row = id;
           }
-          if (lane_on) r[u] = load_row_stream<VEC>(tab + row * row_stride + lane * VEC);
+          if (lane_on) r[u] = load_table_row<VEC, WB, true>(tab, row * row_stride + lane * VEC);
         } else if (err_flag != nullptr && lane == 0 && !(id < 0 && (s_flag[s] & PTREC_FEAT_NEG_IS_PAD))) {
           *err_flag = 1;
         }
@@ -134,7 +135,7 @@ constexpr int kBagThreads = 128;  // 4 warps = 4 bags per CTA
 constexpr int kBagsPerCta = kBagThreads / 32;
 constexpr int kBagStageMaxL = 2048;  // 4 * 2048 * 8 B = 64 KB of shared memory at most
 
-template <int VEC, int LPR>
+template <int VEC, int LPR, bool WB>
 __global__ void __launch_bounds__(kBagThreads)
 gather_bag_kernel(const void* const* __restrict__ table_ptrs, const int64_t* __restrict__ table_rows,
                   int D, int64_t row_stride, const ptrec_feature_desc* __restrict__ feats, FeatSel sel,
@@ -180,7 +181,7 @@ gather_bag_kernel(const void* const* __restrict__ table_ptrs, const int64_t* __r
   if (warp >= nb) return;
 
   const int64_t b = b0 + warp;
-  const float* tab = reinterpret_cast<const float*>(table_ptrs[fd.table]);
+  const void* tab = table_ptrs[fd.table];
   const int64_t rows = table_rows[fd.table];
   constexpr int RPW = 32 / LPR;  // rows in flight per warp-load
   const int sg = lane32 / LPR, lane = lane32 % LPR;
@@ -210,7 +211,7 @@ gather_bag_kernel(const void* const* __restrict__ table_ptrs, const int64_t* __r
         if (valid) {
           ++count;
           if ((uint64_t)id < (uint64_t)rows) {
-            if (lane_on) r[u] = load_row_stream<VEC>(tab + id * row_stride + lane * VEC);
+            if (lane_on) r[u] = load_table_row<VEC, WB, true>(tab, id * row_stride + lane * VEC);
           } else if (err_flag != nullptr && lane == 0) {
             *err_flag = 1;
           }
@@ -236,7 +237,7 @@ gather_bag_kernel(const void* const* __restrict__ table_ptrs, const int64_t* __r
 }
 
 // ------------------------------------------------------------------------------------ dispatch
-template <int VEC, int LPR>
+template <int VEC, int LPR, bool WB>
 static int launch_gather(const void* const* table_ptrs, const int64_t* table_rows, int D, int64_t row_stride,
                          const ptrec_feature_desc* feats, const FeatSel& onehot, const FeatSel& bags,
                          int max_bag_len, const int64_t* ids, const int32_t* lens, int64_t B,
@@ -249,13 +250,13 @@ static int launch_gather(const void* const* table_ptrs, const int64_t* table_row
     const unsigned grid = (unsigned)ceil_div(B, kOneHotTileB);
     if (shards > 1) {
       if (smem > 48 * 1024)
-        PTREC_CUDA(cudaFuncSetAttribute(gather_onehot_kernel<VEC, LPR, true>,
+        PTREC_CUDA(cudaFuncSetAttribute(gather_onehot_kernel<VEC, LPR, true, WB>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      gather_onehot_kernel<VEC, LPR, true><<<grid, kOneHotThreads, smem, st>>>(
+      gather_onehot_kernel<VEC, LPR, true, WB><<<grid, kOneHotThreads, smem, st>>>(
           table_ptrs, table_rows, D, row_stride, feats, onehot, ids, B, out, out_row_stride, err_flag, use_bulk,
           shards);
     } else {
-      gather_onehot_kernel<VEC, LPR, false><<<grid, kOneHotThreads, smem, st>>>(
+      gather_onehot_kernel<VEC, LPR, false, WB><<<grid, kOneHotThreads, smem, st>>>(
           table_ptrs, table_rows, D, row_stride, feats, onehot, ids, B, out, out_row_stride, err_flag, use_bulk, 1);
     }
     PTREC_LAUNCH_CHECK("gather_onehot_kernel");
@@ -264,11 +265,11 @@ static int launch_gather(const void* const* table_ptrs, const int64_t* table_row
     const int stage_L = max_bag_len <= kBagStageMaxL ? max_bag_len : 0;
     const size_t smem = (size_t)stage_L * kBagsPerCta * 8;
     if (smem > 48 * 1024) {
-      PTREC_CUDA(cudaFuncSetAttribute(gather_bag_kernel<VEC, LPR>,
+      PTREC_CUDA(cudaFuncSetAttribute(gather_bag_kernel<VEC, LPR, WB>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     dim3 grid((unsigned)ceil_div(B, kBagsPerCta), (unsigned)bags.n);
-    gather_bag_kernel<VEC, LPR><<<grid, kBagThreads, smem, st>>>(
+    gather_bag_kernel<VEC, LPR, WB><<<grid, kBagThreads, smem, st>>>(
         table_ptrs, table_rows, D, row_stride, feats, bags, ids, lens, B, out, out_row_stride, bag_scale,
         err_flag, ids_al, stage_L * kBagsPerCta);
     PTREC_LAUNCH_CHECK("gather_bag_kernel");
@@ -369,7 +370,7 @@ static int gather_pool_fwd_impl(const void* const* table_ptrs, const int64_t* ta
                                 const ptrec_feature_desc* feats_host, int32_t F, const int64_t* ids,
                                 const int32_t* lens, int64_t B, float* out, int64_t out_row_stride,
                                 float* bag_scale, int32_t* err_flag, void* stream) {
-  PTREC_CHECK_ARG(dtype == PTREC_F32, PTREC_EUNSUPPORTED, "gather: only fp32 tables are built (dtype=%d)", dtype);
+  PTREC_CHECK_ARG(dtype == PTREC_F32 || dtype == PTREC_BF16, PTREC_EUNSUPPORTED, "gather: unknown table dtype %d", dtype);
   PTREC_CHECK_ARG(T >= 1 && T <= kMaxTables && F >= 1 && F <= kMaxFeatures, PTREC_EINVAL,
                   "gather: T=%d F=%d out of range (max %d)", T, F, kMaxFeatures);
   PTREC_CHECK_ARG(table_ptrs && table_rows && feats && feats_host && ids && out, PTREC_EINVAL, "gather: null pointer");
@@ -408,9 +409,12 @@ static int gather_pool_fwd_impl(const void* const* table_ptrs, const int64_t* ta
                   "gather: row-wise sharded tables serve one-hot fields only (pooled bags stay unsharded)");
   cudaStream_t st = (cudaStream_t)stream;
 
-#define PTREC_GATHER(V, P) \
-  return launch_gather<V, P>(table_ptrs, table_rows, D, row_stride, feats, onehot, bags, max_bag_len, ids, lens, B, \
-                             out, out_row_stride, bag_scale, err_flag, shards, st)
+#define PTREC_GATHER(V, P)                                                                                           \
+  return dtype == PTREC_BF16                                                                                         \
+             ? launch_gather<V, P, true>(table_ptrs, table_rows, D, row_stride, feats, onehot, bags, max_bag_len, ids, \
+                                         lens, B, out, out_row_stride, bag_scale, err_flag, shards, st)              \
+             : launch_gather<V, P, false>(table_ptrs, table_rows, D, row_stride, feats, onehot, bags, max_bag_len, ids, \
+                                          lens, B, out, out_row_stride, bag_scale, err_flag, shards, st)
   if (D == 1) PTREC_GATHER(1, 1);
   if (D == 2) PTREC_GATHER(2, 1);
   const int lanes = D / 4;

@@ -38,10 +38,13 @@ class FM(IModel):
         return descriptions
 
     def __init__(self, sparse_columns: List[CategoricalColumnWithIdentity], dense_columns: List[NumericColumn],
-                 label_column: CategoricalColumnWithIdentity, emb_size: int, table_device=None, **kwargs):
+                 label_column: CategoricalColumnWithIdentity, emb_size: int, table_device=None,
+                 table_dtype: torch.dtype = torch.float32, **kwargs):
         # table_device: build the tables directly on that device (skips the CPU init of multi-GB
         # tables; seeded CPU-init parity with the reference then no longer applies)
+        # table_dtype: torch.bfloat16 stores the embedding rows in bf16 (EmbeddingTable; fp32 arithmetic and state)
         self.table_device = table_device
+        self.table_dtype = table_dtype
         self.sparse_columns = list(sparse_columns)
         self.dense_columns = list(dense_columns or [])
         self.label_column = label_column
@@ -50,7 +53,7 @@ class FM(IModel):
 
     def _make_embedding(self, emb_size: int):
         """Table-group factory (overridden by the row-wise sharded variant)."""
-        return MultiTableEmbedding(self.sparse_columns, emb_size, device=self.table_device)
+        return MultiTableEmbedding(self.sparse_columns, emb_size, device=self.table_device, dtype=self.table_dtype)
 
     def _init_weights(self):
         self.embeddings = self._make_embedding(self.emb_size)
@@ -100,10 +103,11 @@ class DeepFM(FM):
         return descriptions
 
     def __init__(self, sparse_columns, dense_columns, label_column, emb_size: int, layers: List[int],
-                 dropout: float = 0.0, table_device=None, **kwargs):
+                 dropout: float = 0.0, table_device=None, table_dtype: torch.dtype = torch.float32, **kwargs):
         self.layers = list(layers)
         self.dropout = dropout
-        super().__init__(sparse_columns, dense_columns, label_column, emb_size, table_device=table_device, **kwargs)
+        super().__init__(sparse_columns, dense_columns, label_column, emb_size, table_device=table_device,
+                         table_dtype=table_dtype, **kwargs)
 
     def _init_weights(self):
         super()._init_weights()

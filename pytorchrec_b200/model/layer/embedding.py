@@ -98,13 +98,13 @@ class EmbeddingGroup:
         for t, table in enumerate(self.tables):
             sel = valid & (seg_table == t)
             idx = keys[sel].long() & 0xFFFFFFFF
+            rows_g = row_grad[:n][sel].to(table.weight.dtype)  # a bf16 table takes a bf16 gradient (autograd's rule)
             if getattr(table, "sparse", False):
-                g = torch.sparse_coo_tensor(idx.unsqueeze(0), row_grad[:n][sel], size=table.weight.shape,
-                                            check_invariants=False)
+                g = torch.sparse_coo_tensor(idx.unsqueeze(0), rows_g, size=table.weight.shape, check_invariants=False)
                 grads.append(g._coalesced_(True))  # segments are unique sorted rows by construction
             else:  # nn.Embedding(sparse=False): the dense gradient every stock optimizer accepts
-                g = torch.zeros(table.weight.shape, dtype=row_grad.dtype, device=row_grad.device)
-                g[idx] = row_grad[:n][sel]       # unique rows: a plain scatter, no accumulation order involved
+                g = torch.zeros(table.weight.shape, dtype=table.weight.dtype, device=row_grad.device)
+                g[idx] = rows_g                  # unique rows: a plain scatter, no accumulation order involved
                 grads.append(g)
         return grads
 
@@ -162,15 +162,22 @@ class EmbeddingTable(nn.Module):
     """``nn.Embedding``-compatible table: ``EmbeddingTable(num_embeddings, embedding_dim)``,
     parameter ``weight`` ``[num_embeddings, embedding_dim]`` fp32, N(0,1) at construction like
     ``nn.Embedding.reset_parameters``.  ``forward(ids)`` returns ``weight[ids]`` for ids of any shape.
-    ``sparse`` has ``nn.Embedding``'s meaning and matters only without a fused optimizer (module docstring)."""
+    ``sparse`` has ``nn.Embedding``'s meaning and matters only without a fused optimizer (module docstring).
+    ``dtype=torch.bfloat16`` stores the rows in bf16 (half the HBM bytes per lookup; ``include/ptrec_b200.h``
+    PTREC_BF16): lookups widen exactly to fp32, the fused optimizers keep fp32 state, compute the step in fp32 and
+    round the row back to bf16 (nearest even).  The initial draw is the fp32 one, rounded."""
 
-    def __init__(self, num_embeddings: int, embedding_dim: int, device=None, sparse: bool = False):
+    def __init__(self, num_embeddings: int, embedding_dim: int, device=None, sparse: bool = False,
+                 dtype: torch.dtype = torch.float32):
         super().__init__()
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("EmbeddingTable dtype must be torch.float32 or torch.bfloat16")
         self.num_embeddings = int(num_embeddings)
         self.embedding_dim = int(embedding_dim)
         self.sparse = bool(sparse)
-        self.weight = nn.Parameter(torch.empty(self.num_embeddings, self.embedding_dim, device=device))
-        nn.init.normal_(self.weight)
+        w = torch.empty(self.num_embeddings, self.embedding_dim, device=device)
+        nn.init.normal_(w)
+        self.weight = nn.Parameter(w if dtype == torch.float32 else w.to(dtype))
         self._group = None
         self._layout = None
         self._tag()
@@ -244,6 +251,7 @@ class MultiTableEmbedding(nn.ModuleList):
     :param lens_columns: for mask='lens', ``{feature_name: CategoricalColumn}`` giving the valid length.
     :param share: ``{feature_name: feature_name_of_table_owner}`` — several features reading one table.
     :param sparse: ``nn.Embedding``'s flag for the gradient layout without a fused optimizer (dense by default).
+    :param dtype: ``torch.float32`` (default) or ``torch.bfloat16`` table storage (see ``EmbeddingTable``).
     ``pooling`` / ``mask`` may also be dicts keyed by feature name.
     ``forward(batch)`` returns ``[B, F, D]`` in ``columns`` order.
     """
@@ -251,7 +259,8 @@ class MultiTableEmbedding(nn.ModuleList):
     def __init__(self, columns: Sequence[CategoricalColumn], emb_size: int,
                  pooling: Union[str, Dict[str, str]] = "sum", mask: Union[str, Dict[str, str]] = "none",
                  lens_columns: Optional[Dict[str, CategoricalColumn]] = None,
-                 share: Optional[Dict[str, str]] = None, device=None, sparse: bool = False):
+                 share: Optional[Dict[str, str]] = None, device=None, sparse: bool = False,
+                 dtype: torch.dtype = torch.float32):
         super().__init__()
         self.columns = list(columns)
         self.emb_size = int(emb_size)
@@ -266,7 +275,7 @@ class MultiTableEmbedding(nn.ModuleList):
                 if owner != name:
                     raise ValueError(f"feature {name} shares the table of {owner}, which must come first")
                 owner_index[owner] = len(self)
-                self.append(EmbeddingTable(c.category_num, self.emb_size, device=device, sparse=sparse))
+                self.append(EmbeddingTable(c.category_num, self.emb_size, device=device, sparse=sparse, dtype=dtype))
             self._table_of.append(owner_index[owner])
         self._pooling = {n: (pooling.get(n, "sum") if isinstance(pooling, dict) else pooling) for n in names}
         self._mask = {n: (mask.get(n, "none") if isinstance(mask, dict) else mask) for n in names}

@@ -139,25 +139,30 @@ class TableSet:
         self.rows = None
         self.max_rows = 0
         self.row_stride = 0
+        self.dtype = _lib.F32   # PTREC_F32 / PTREC_BF16: element type of every table of the group
 
     def refresh(self, weights: Sequence[torch.Tensor]):
-        key = tuple((w.data_ptr(), w.stride(0)) for w in weights)
+        key = tuple((w.data_ptr(), w.stride(0), w.dtype) for w in weights)
         if key != self._key:
             dev = weights[0].device
             # the group's row stride comes from any table with more than one row (a one-row table has no meaningful
             # stride: it may still be a plain [1, D] tensor while the others are interleaved with their state)
             multi = [w for w in weights if w.shape[0] > 1]
             stride = multi[0].stride(0) if multi else weights[0].shape[1]
+            wdt = weights[0].dtype
             for w in weights:
                 _require_cuda(w)
-                if w.dtype != torch.float32 or w.dim() != 2 or w.stride(1) != 1 or w.device != dev:
-                    raise RuntimeError("embedding tables must be fp32 [rows, D] CUDA tensors with unit inner stride on one device")
+                if w.dtype not in (torch.float32, torch.bfloat16) or w.dtype != wdt or w.dim() != 2 or w.stride(1) != 1 \
+                        or w.device != dev:
+                    raise RuntimeError("embedding tables of one group must be fp32 (or all bf16) [rows, D] CUDA tensors "
+                                       "with unit inner stride on one device")
                 if w.shape[0] > 1 and w.stride(0) != stride:
                     raise RuntimeError("all tables of one embedding group must share the same row stride "
                                        "(all plain, or all interleaved with their optimizer state)")
-                align = 16 if w.shape[1] >= 4 else 4 * w.shape[1]
-                if w.data_ptr() % align != 0:
-                    raise RuntimeError("embedding table base pointer is misaligned")
+                align = (16 if w.shape[1] >= 4 else 4 * w.shape[1]) // (2 if wdt == torch.bfloat16 else 1)
+                if w.data_ptr() % align != 0 or (w.shape[0] > 1 and (w.stride(0) * w.element_size()) % align != 0):
+                    raise RuntimeError("embedding table base pointer / row pitch is misaligned")
+            self.dtype = _lib.BF16 if wdt == torch.bfloat16 else _lib.F32
             self.row_stride = int(stride)
             self.ptrs = torch.tensor([w.data_ptr() for w in weights], dtype=torch.int64).to(dev)
             self.rows = torch.tensor([w.shape[0] for w in weights], dtype=torch.int64).to(dev)
@@ -191,7 +196,7 @@ def gather_pool_fwd(tables: TableSet, layout: FeatureLayout, ids: torch.Tensor,
 def _gather_call(lib, tables, layout, ids, lens, batch, out, bag_scale, err_flag, dev, row_stride):
     feats_dev = layout.device_array(dev)
     return lib.ptrec_embedding_gather_pool_fwd(
-        _ptr(tables.ptrs), _ptr(tables.rows), layout.n_tables, layout.dim, tables.row_stride or layout.dim, _lib.F32,
+        _ptr(tables.ptrs), _ptr(tables.rows), layout.n_tables, layout.dim, tables.row_stride or layout.dim, tables.dtype,
         ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)), layout.host,
         layout.n_features, _ptr(ids), _ptr(lens), batch, _ptr(out), row_stride, _ptr(bag_scale),
         _ptr(err_flag), _stream(dev))
@@ -275,7 +280,7 @@ def bwd_fused(tables: TableSet, state1_ptrs: Optional[torch.Tensor], state2_ptrs
     feats_dev = layout.device_array(dev)
     fn = getattr(lib, _BWD_FN[opt.kind])
     _lib.check(fn(_ptr(tables.ptrs), _ptr(state1_ptrs), _ptr(state2_ptrs), layout.n_tables, layout.dim,
-                  tables.row_stride or layout.dim, _lib.F32, ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)),
+                  tables.row_stride or layout.dim, tables.dtype, ctypes.cast(ctypes.c_void_p(feats_dev.data_ptr()), ctypes.POINTER(FeatureDesc)),
                   layout.host, layout.n_features, batch, _ptr(srt.sorted_keys), _ptr(srt.perm),
                   _ptr(srt.seg_start), _ptr(srt.seg_meta), _ptr(srt.n_seg), _ptr(grad_out),
                   grad_row_stride, _ptr(bag_scale), ctypes.byref(opt), _ptr(ws), ws.numel(),

@@ -341,10 +341,12 @@ class SparseAdagrad(_FusedSparseOptimizer):
 
     def _state_tensors(self, p):
         st = self.state[p]
-        if self.interleave and type(self) is SparseAdagrad:
+        if self.interleave and type(self) is SparseAdagrad and p.dtype == torch.float32:
             self._interleave(p, ["sum"], [self._init_acc(p)], slots=2)
         elif "sum" not in st or st["sum"].device != p.device:
-            st["sum"] = torch.full_like(p.data, self._init_acc(p)) if "sum" not in st else st["sum"].to(p.device)
+            # bf16 tables: the accumulator stays fp32, in a tensor of its own with the weight's row stride in elements
+            st["sum"] = (torch.full(p.shape, self._init_acc(p), dtype=torch.float32, device=p.device)
+                         if "sum" not in st else st["sum"].to(p.device))
         return st["sum"], None
 
     def _optim_args(self, group):
@@ -386,12 +388,12 @@ class SparseAdam(_FusedSparseOptimizer):
 
     def _state_tensors(self, p):
         st = self.state[p]
-        if self.interleave:
+        if self.interleave and p.dtype == torch.float32:
             self._interleave(p, ["exp_avg", "exp_avg_sq"], [0.0, 0.0], slots=4)  # w | m | v | pad: 2 lines at D=16
             return st["exp_avg"], st["exp_avg_sq"]
         for k in ("exp_avg", "exp_avg_sq"):
             if k not in st:
-                st[k] = torch.zeros_like(p.data)
+                st[k] = torch.zeros(p.shape, dtype=torch.float32, device=p.device)  # fp32 moments for bf16 tables too
             elif st[k].device != p.device:
                 st[k] = st[k].to(p.device)
         return st["exp_avg"], st["exp_avg_sq"]
