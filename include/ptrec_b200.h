@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 20
+#define PTREC_ABI_VERSION 21
 
 /* error codes */
 #define PTREC_OK 0
@@ -352,6 +352,20 @@ int ptrec_fm_head_bwd(const float* v, int64_t v_row_stride, const float* x, int6
                       int64_t grad_x_row_stride, float* grad_wd, float* grad_bias, void* workspace,
                       size_t workspace_bytes, void* stream);
 /* y[b] = h[b, :] . w  (h [B, H], w [H]);  backward: grad_h = g (x) w (or NULL), grad_w = h^T g (or NULL) */
+/* K8 writing / reading the K6 fused tower's operand planes directly (fp16 x 2, carried scales: see "the fused tower"):
+ * ptrec_fm_head_fwd_h2: ptrec_fm_head_fwd whose tower input leaves as two fp16 planes [2][B][planes_ld] split with
+ *   *scale (deep_in may be NULL: the tower then reads the planes only); *max_out is raised to max |tower input|.
+ * ptrec_rowdot_bwd_h2: ptrec_rowdot_bwd where h is the ReLU output of the tower's last layer: instead of fp32 g_h it
+ *   writes the planes of (g (x) w) * (h > 0) split with *scale — the gradient of that layer's pre-activation — its
+ *   column sums (colsum [H] or NULL: the layer's bias gradient, fixed order) and raises *max_out to its |max|.
+ *   workspace: 2 x ptrec_rowdot_bwd_workspace_bytes(H). */
+int ptrec_fm_head_fwd_h2(const float* v, int64_t v_row_stride, const float* w1, int64_t w1_row_stride, const float* x,
+                         int64_t x_row_stride, const float* wd, const float* bias, int64_t B, int32_t F, int32_t D,
+                         int32_t nd, float* logit, float* deep_in, int64_t deep_in_row_stride, void* planes,
+                         int64_t planes_ld, const float* scale, float* max_out, void* stream);
+int ptrec_rowdot_bwd_h2(const float* h, int64_t h_row_stride, const float* w, const float* g, int64_t B, int32_t H,
+                        void* planes, int64_t planes_ld, const float* scale, float* max_out, float* colsum,
+                        float* grad_w, void* workspace, size_t workspace_bytes, void* stream);
 int ptrec_rowdot_supported(int32_t H);
 int ptrec_rowdot_fwd(const float* h, int64_t h_row_stride, const float* w, int64_t B, int32_t H, float* y,
                      void* stream);

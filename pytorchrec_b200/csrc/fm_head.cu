@@ -33,13 +33,20 @@ fm_head_fwd_kernel(const float* __restrict__ v, int64_t vs, const float* __restr
                    const float* __restrict__ x, int64_t xs, const float* __restrict__ wd,
                    const float* __restrict__ bias, int64_t B, int F, int n_chunks, int lanes_per_row, int nd,
                    float* __restrict__ logit, float* __restrict__ deep_in, int64_t ds,
-                   __nv_bfloat16* __restrict__ planes, int64_t pl_ld, int64_t pl_plane) {
+                   __nv_bfloat16* __restrict__ planes, int64_t pl_ld, int64_t pl_plane,
+                   const float* __restrict__ h2_scale, uint32_t* __restrict__ h2_max) {
+  // h2_scale != null: `planes` are the TWO fp16 planes of the K6 fused tower (tc_linear.cu), split with the carried
+  // scale *h2_scale; *h2_max is raised to max |tower input| for the next roll.  Otherwise three exact bf16 planes.
   const int64_t b = (int64_t)blockIdx.x * kHdWarps + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31;
   const float* row = v + b * vs;
   float* drow = deep_in ? deep_in + b * ds : nullptr;
-  __nv_bfloat16* prow = planes ? planes + b * pl_ld : nullptr;
+  const bool h2 = h2_scale != nullptr;
+  const float hs = h2 ? *h2_scale : 1.f;
+  float amax = 0.f;
+  __nv_bfloat16* prow = (planes && !h2) ? planes + b * pl_ld : nullptr;
+  unsigned short* hrow = (planes && h2) ? reinterpret_cast<unsigned short*>(planes) + b * pl_ld : nullptr;
   float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
   float Q = 0.f;
   for (int q0 = lane; q0 < n_chunks; q0 += 32 * 4) {
@@ -58,6 +65,20 @@ fm_head_fwd_kernel(const float* __restrict__ v, int64_t vs, const float* __restr
       if (prow && q < n_chunks) {
         const float tv[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
         split3_store4(tv, prow + q * 4, pl_plane);
+      }
+      if (hrow && q < n_chunks) {
+        const float tv[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+        unsigned short p0[4], p1[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half a0, a1;
+          split2h(tv[i], hs, a0, a1);
+          p0[i] = __half_as_ushort(a0);
+          p1[i] = __half_as_ushort(a1);
+          amax = fmaxf(amax, fabsf(tv[i]));
+        }
+        *reinterpret_cast<uint2*>(hrow + q * 4) = *reinterpret_cast<const uint2*>(p0);
+        *reinterpret_cast<uint2*>(hrow + pl_plane + q * 4) = *reinterpret_cast<const uint2*>(p1);
       }
     }
   }
@@ -83,6 +104,20 @@ fm_head_fwd_kernel(const float* __restrict__ v, int64_t vs, const float* __restr
       o[pl_plane] = p1;
       o[2 * pl_plane] = p2;
     }
+  }
+  if (hrow) {  // dense columns and the zero pad up to the plane pitch
+    for (int j = lane; n_chunks * 4 + j < pl_ld; j += 32) {
+      const float xv = (x != nullptr && j < nd) ? x[b * xs + j] : 0.f;
+      __half a0, a1;
+      split2h(xv, hs, a0, a1);
+      hrow[n_chunks * 4 + j] = __half_as_ushort(a0);
+      hrow[pl_plane + n_chunks * 4 + j] = __half_as_ushort(a1);
+      amax = fmaxf(amax, fabsf(xv));
+    }
+    float m = amax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m > 0.f && h2_max != nullptr) atomicMax(h2_max, __float_as_uint(m));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -213,17 +248,25 @@ rowdot_fwd_kernel(const float* __restrict__ h, int64_t hs, const float* __restri
 }
 
 // g_h[b,k] = g[b]*w[k];  per-CTA partials of g_w[k] = sum_b g[b]*h[b,k]  (H % 4 == 0, H <= 128*MAXC, aligned)
-template <int MAXC>
+// H2 (the K6 fused tower's hand-off, tc_linear.cu): h is the ReLU output of the tower's last layer, so the gradient of
+// its pre-activation is g (x) w where h > 0; that product leaves as two fp16 planes split with *h2_scale (no fp32
+// g_h, no split pass), its column sums (the last bias gradient) as per-CTA partials, its |max| into *h2_max.
+template <int MAXC, bool H2>
 __global__ void __launch_bounds__(kHdWarps * 32)
 rowdot_bwd_kernel(const float* __restrict__ h, int64_t hs, const float* __restrict__ w, const float* __restrict__ g,
-                  int64_t B, int H, float* __restrict__ gh, int64_t ghs, float* __restrict__ part) {
+                  int64_t B, int H, float* __restrict__ gh, int64_t ghs, float* __restrict__ part,
+                  unsigned short* __restrict__ planes, int64_t pl_ld, int64_t pl_plane,
+                  const float* __restrict__ h2_scale, uint32_t* __restrict__ h2_max, float* __restrict__ cs_part) {
   extern __shared__ float s_acc[];  // [kHdWarps][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = H / 4;
-  float4 a[MAXC], wv[MAXC];
+  float4 a[MAXC], wv[MAXC], cs[H2 ? MAXC : 1];
+  const float hsc = H2 ? *h2_scale : 1.f;
+  float amax = 0.f;
 #pragma unroll
   for (int u = 0; u < MAXC; ++u) {
     a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (H2) cs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int q = lane + u * 32;
     wv[u] = q < nq ? *reinterpret_cast<const float4*>(w + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -242,6 +285,44 @@ rowdot_bwd_kernel(const float* __restrict__ h, int64_t hs, const float* __restri
       const int q = lane + u * 32;
       a[u].x += gb * t[u].x; a[u].y += gb * t[u].y; a[u].z += gb * t[u].z; a[u].w += gb * t[u].w;
       if (orow && q < nq) st_f4(orow + q * 4, make_float4(gb * wv[u].x, gb * wv[u].y, gb * wv[u].z, gb * wv[u].w));
+      if (H2 && q < nq) {
+        const float tv[4] = {t[u].x > 0.f ? gb * wv[u].x : 0.f, t[u].y > 0.f ? gb * wv[u].y : 0.f,
+                             t[u].z > 0.f ? gb * wv[u].z : 0.f, t[u].w > 0.f ? gb * wv[u].w : 0.f};
+        unsigned short p0[4], p1[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half a0, a1;
+          split2h(tv[i], hsc, a0, a1);
+          p0[i] = __half_as_ushort(a0);
+          p1[i] = __half_as_ushort(a1);
+          amax = fmaxf(amax, fabsf(tv[i]));
+        }
+        unsigned short* o = planes + b * pl_ld + q * 4;
+        *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(p0);
+        *reinterpret_cast<uint2*>(o + pl_plane) = *reinterpret_cast<const uint2*>(p1);
+        cs[u].x += tv[0]; cs[u].y += tv[1]; cs[u].z += tv[2]; cs[u].w += tv[3];
+      }
+    }
+  }
+  if (H2) {
+    // (pad columns [H, pl_ld) are never read: the GEMMs' tensor maps end at H)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0 && amax > 0.f && h2_max != nullptr) atomicMax(h2_max, __float_as_uint(amax));
+    if (cs_part != nullptr) {  // fixed-order per-CTA column sums of the masked gradient (bias gradient)
+#pragma unroll
+      for (int u = 0; u < MAXC; ++u) {
+        const int q = lane + u * 32;
+        if (q < nq) *reinterpret_cast<float4*>(&s_acc[(size_t)warp * H + q * 4]) = cs[u];
+      }
+      __syncthreads();
+      for (int k = threadIdx.x; k < H; k += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < kHdWarps; ++wi) s += s_acc[(size_t)wi * H + k];
+        cs_part[(int64_t)blockIdx.x * H + k] = s;
+      }
+      __syncthreads();
     }
   }
   if (part == nullptr) return;
@@ -299,7 +380,33 @@ extern "C" int ptrec_fm_head_fwd(const float* v, int64_t v_row_stride, const flo
   fm_head_fwd_kernel<<<(unsigned)ceil_div(B, kHdWarps), kHdWarps * 32, 0, (cudaStream_t)stream>>>(
       v, v_row_stride, w1, w1_row_stride, nd ? x : nullptr, x_row_stride, wd, bias, B, F, F * D / 4, D / 4, nd, logit,
       deep_in, deep_in_row_stride, reinterpret_cast<__nv_bfloat16*>(deep_in_planes), deep_in_planes_ld,
-      B * deep_in_planes_ld);
+      B * deep_in_planes_ld, nullptr, nullptr);
+  PTREC_LAUNCH_CHECK("fm_head_fwd_kernel");
+  return PTREC_OK;
+}
+
+// the same pass writing the tower input as the fp16 x 2 planes of the K6 fused tower (carried scale, tc_linear.cu);
+// deep_in (fp32) may be NULL when the tower reads the planes only
+extern "C" int ptrec_fm_head_fwd_h2(const float* v, int64_t v_row_stride, const float* w1, int64_t w1_row_stride,
+                                    const float* x, int64_t x_row_stride, const float* wd, const float* bias, int64_t B,
+                                    int32_t F, int32_t D, int32_t nd, float* logit, float* deep_in,
+                                    int64_t deep_in_row_stride, void* planes, int64_t planes_ld, const float* scale,
+                                    float* max_out, void* stream) {
+  PTREC_CHECK_ARG(v && logit && planes && scale && B >= 0 && F >= 1, PTREC_EINVAL, "fm_head_fwd_h2: bad argument");
+  PTREC_CHECK_ARG(ptrec_fm_head_supported(F, D, nd), PTREC_EUNSUPPORTED, "fm_head_fwd_h2: unsupported shape");
+  PTREC_CHECK_ARG(aligned16(v) && v_row_stride % 4 == 0 && v_row_stride >= (int64_t)F * D, PTREC_EALIGN,
+                  "fm_head_fwd_h2: v misaligned");
+  PTREC_CHECK_ARG(!deep_in || (aligned16(deep_in) && deep_in_row_stride % 4 == 0 &&
+                               deep_in_row_stride >= (int64_t)F * D + nd),
+                  PTREC_EALIGN, "fm_head_fwd_h2: deep_in misaligned");
+  PTREC_CHECK_ARG(nd == 0 || x != nullptr, PTREC_EINVAL, "fm_head_fwd_h2: dense features without x");
+  PTREC_CHECK_ARG(aligned16(planes) && planes_ld % 8 == 0 && planes_ld >= (int64_t)F * D + nd, PTREC_EALIGN,
+                  "fm_head_fwd_h2: plane pitch must be a multiple of 8 >= F*D + nd");
+  if (B == 0) return PTREC_OK;
+  fm_head_fwd_kernel<<<(unsigned)ceil_div(B, kHdWarps), kHdWarps * 32, 0, (cudaStream_t)stream>>>(
+      v, v_row_stride, w1, w1_row_stride, nd ? x : nullptr, x_row_stride, wd, bias, B, F, F * D / 4, D / 4, nd, logit,
+      deep_in, deep_in_row_stride, reinterpret_cast<__nv_bfloat16*>(planes), planes_ld, B * planes_ld, scale,
+      reinterpret_cast<uint32_t*>(max_out));
   PTREC_LAUNCH_CHECK("fm_head_fwd_kernel");
   return PTREC_OK;
 }
@@ -375,12 +482,52 @@ extern "C" int ptrec_rowdot_bwd(const float* h, int64_t h_row_stride, const floa
   const size_t smem = (size_t)kHdWarps * H * sizeof(float);
   float* part = grad_w ? reinterpret_cast<float*>(workspace) : nullptr;
   if (H <= 512)
-    rowdot_bwd_kernel<4><<<grid, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, grad_h, grad_h_row_stride, part);
+    rowdot_bwd_kernel<4, false><<<grid, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, grad_h, grad_h_row_stride,
+                                                                   part, nullptr, 0, 0, nullptr, nullptr, nullptr);
   else
-    rowdot_bwd_kernel<8><<<grid, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, grad_h, grad_h_row_stride, part);
+    rowdot_bwd_kernel<8, false><<<grid, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, grad_h, grad_h_row_stride,
+                                                                   part, nullptr, 0, 0, nullptr, nullptr, nullptr);
   PTREC_LAUNCH_CHECK("rowdot_bwd_kernel");
   if (grad_w) {
     head_reduce_kernel<<<(unsigned)ceil_div(H, 32), 1024, 0, st>>>(part, grid, H, grad_w, H, nullptr);
+    PTREC_LAUNCH_CHECK("head_reduce_kernel");
+  }
+  return PTREC_OK;
+}
+
+// rowdot backward handing the masked gradient to the K6 fused tower as planes (see rowdot_bwd_kernel<., true>):
+// workspace = 2 x ptrec_rowdot_bwd_workspace_bytes(H) (g_w partials, column-sum partials)
+extern "C" int ptrec_rowdot_bwd_h2(const float* h, int64_t h_row_stride, const float* w, const float* g, int64_t B,
+                                   int32_t H, void* planes, int64_t planes_ld, const float* scale, float* max_out,
+                                   float* colsum, float* grad_w, void* workspace, size_t workspace_bytes, void* stream) {
+  PTREC_CHECK_ARG(h && w && g && planes && scale && B >= 0, PTREC_EINVAL, "rowdot_bwd_h2: bad argument");
+  PTREC_CHECK_ARG(ptrec_rowdot_supported(H), PTREC_EUNSUPPORTED, "rowdot_bwd_h2: H must be a multiple of 4 <= %d", kHdMaxH);
+  PTREC_CHECK_ARG(aligned16(h) && aligned16(w) && h_row_stride % 4 == 0 && aligned16(planes) && planes_ld % 8 == 0 &&
+                      planes_ld >= H, PTREC_EALIGN, "rowdot_bwd_h2: misaligned");
+  const size_t one = ptrec_rowdot_bwd_workspace_bytes(H);
+  PTREC_CHECK_ARG(workspace && workspace_bytes >= 2 * one, PTREC_EWORKSPACE, "rowdot_bwd_h2: workspace too small");
+  if (B == 0) return PTREC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (int)std::min<int64_t>(head_grid(), ceil_div(B, kHdWarps));
+  const size_t smem = (size_t)kHdWarps * H * sizeof(float);
+  float* part = grad_w ? reinterpret_cast<float*>(workspace) : nullptr;
+  float* cs_part = colsum ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + one) : nullptr;
+  unsigned short* pl = reinterpret_cast<unsigned short*>(planes);
+  if (H <= 512)
+    rowdot_bwd_kernel<4, true><<<grid, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, nullptr, 0, part, pl,
+                                                                  planes_ld, B * planes_ld, scale,
+                                                                  reinterpret_cast<uint32_t*>(max_out), cs_part);
+  else
+    rowdot_bwd_kernel<8, true><<<grid, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, nullptr, 0, part, pl,
+                                                                  planes_ld, B * planes_ld, scale,
+                                                                  reinterpret_cast<uint32_t*>(max_out), cs_part);
+  PTREC_LAUNCH_CHECK("rowdot_bwd_kernel");
+  if (grad_w) {
+    head_reduce_kernel<<<(unsigned)ceil_div(H, 32), 1024, 0, st>>>(part, grid, H, grad_w, H, nullptr);
+    PTREC_LAUNCH_CHECK("head_reduce_kernel");
+  }
+  if (colsum) {
+    head_reduce_kernel<<<(unsigned)ceil_div(H, 32), 1024, 0, st>>>(cs_part, grid, H, colsum, H, nullptr);
     PTREC_LAUNCH_CHECK("head_reduce_kernel");
   }
   return PTREC_OK;

@@ -73,7 +73,7 @@ class FM(IModel):
         mlp = getattr(self, "mlp", None)
         units = mlp.mlp[0].linear.out_features if (want_deep_in and mlp is not None) else 0
         fused = fm_head(v, w, x, self.dense_linear.weight if x is not None else None, self.global_bias, want_deep_in,
-                        tower_units=units)
+                        tower_units=units, tower=mlp if want_deep_in else None)  # deep_in goes to self.mlp only
         if fused is not None:
             return fused
         logit = w.sum(dim=(1, 2)) + self.fm2(v) + self.global_bias
@@ -118,7 +118,7 @@ class DeepFM(FM):
     def _deep_logit(self, deep_in: Tensor) -> Tensor:
         from .layer.interaction import row_dot
         h = self.mlp(deep_in)
-        y = row_dot(h, self.deep_out.weight)
+        y = row_dot(h, self.deep_out.weight, tower_handoff=True)  # h has no other consumer
         return y if y is not None else self.deep_out(h).squeeze(-1)
 
     def forward(self, data: Dict[str, Tensor]):

@@ -12,7 +12,7 @@ pairs accumulated in fp32; include/ptrec_b200.h).  The ReLU
 mask and the bias gradient are fused into the pass that splits the incoming gradient.  ``PTREC_TC_LINEAR=0`` selects
 the stock ``nn.Linear`` path (cuBLAS fp32) for A/B measurements."""
 import os
-from typing import List
+from typing import List, Optional
 
 import torch
 from torch.nn import Dropout, Linear, Module, ReLU, Sequential
@@ -179,6 +179,17 @@ class _TowerScales:
         return cs
 
 
+class _TowerCall:
+    """One forward (+ backward) of a fused tower: the scales it reads, and what its neighbours hand over in the tower's
+    own operand format — the producer of its input (``fm_head(..., tower=mlp)``: planes of x) and the consumer of its
+    output (``row_dot(..., tower_handoff=True)``: planes of the masked output gradient + the last bias gradient)."""
+
+    def __init__(self, mlp, cs):
+        self.mlp, self.cs = mlp, cs
+        self.in_planes = None      # planes of the tower input, written by its producer
+        self.grad = None           # (planes of the last pre-activation gradient, last bias gradient)
+
+
 class _TcMLP(torch.autograd.Function):
     """The whole Linear -> ReLU stack on K6 with nothing between two GEMMs: the epilogue of layer l writes relu(x W^T + b)
     as the fp16 planes layer l + 1 consumes (and its weight gradient re-reads MN-major) plus one bit per element (> 0);
@@ -186,14 +197,18 @@ class _TcMLP(torch.autograd.Function):
     and its column sums (bias gradient).  fp32 is materialised only for the tower's output and its input gradient."""
 
     @staticmethod
-    def forward(ctx, x, mlp, *params):
+    def forward(ctx, x, mlp, call, *params):
         sl: _TowerScales = mlp._scales
         L = sl.L
-        cs = sl.roll()
+        if call is None:
+            call = _TowerCall(mlp, sl.roll())
+        cs = call.cs
         sc = lambda i: cs[i:i + 1]
         need_dx = ctx.needs_input_grad[0]
         any_grad = any(ctx.needs_input_grad)
-        px, _, _ = ops.tc_split2h_prescaled(x, sc(sl.i_x()), sl.max_word(sl.i_x()))
+        px = call.in_planes   # the producer of x wrote them (x itself is then not materialised)
+        if px is None:
+            px, _, _ = ops.tc_split2h_prescaled(x, sc(sl.i_x()), sl.max_word(sl.i_x()))
         acts, masks, pwts = [px], [], []
         y = None
         for l in range(L):
@@ -212,6 +227,7 @@ class _TcMLP(torch.autograd.Function):
         if getattr(mlp, "_keep_masks", False):  # test introspection: the ReLU decisions this forward took
             mlp._last_masks = list(masks)
         ctx.scales = sl
+        ctx.call = call
         ctx.dims = [(params[2 * l].shape[0], params[2 * l].shape[1]) for l in range(L)]
         ctx.has_bias = [params[2 * l + 1] is not None for l in range(L)]
         if any_grad:
@@ -235,8 +251,12 @@ class _TcMLP(torch.autograd.Function):
         if gy.stride(-1) != 1:
             gy = gy.contiguous()
         grads = [None] * (2 * L)
-        pg, _, db = ops.tc_split2h_prescaled(gy, sc(sl.i_g(L - 1)), sl.max_word(sl.i_g(L - 1)), relu_ref=y,
-                                             want_colsum=ctx.has_bias[L - 1] and need[2 + 2 * (L - 1) + 1])
+        if ctx.call.grad is not None:   # the consumer of y handed its gradient over as planes (gy is not materialised)
+            pg, db = ctx.call.grad
+            ctx.call.grad = None
+        else:
+            pg, _, db = ops.tc_split2h_prescaled(gy, sc(sl.i_g(L - 1)), sl.max_word(sl.i_g(L - 1)), relu_ref=y,
+                                                 want_colsum=ctx.has_bias[L - 1] and need[3 + 2 * (L - 1) + 1])
         dx = None
         for l in range(L - 1, -1, -1):
             N, K = ctx.dims[l]
@@ -244,17 +264,17 @@ class _TcMLP(torch.autograd.Function):
             if l > 0:    # g W, masked by the ReLU of layer l - 1, as planes + bias gradient of layer l - 1
                 _, pg_prev, _, db_prev = ops.tc_gemm_split2h_fused(
                     pg, sc(sl.i_g(l)), pwts[l], sc(sl.i_w(l)), N, want_out=False, out_scale=sc(sl.i_g(l - 1)),
-                    mask_in=masks[l - 1], want_colsum=ctx.has_bias[l - 1] and need[2 + 2 * (l - 1) + 1],
+                    mask_in=masks[l - 1], want_colsum=ctx.has_bias[l - 1] and need[3 + 2 * (l - 1) + 1],
                     max_out=sl.max_word(sl.i_g(l - 1)))
             elif need[0]:
                 dx, _, _, _ = ops.tc_gemm_split2h_fused(pg, sc(sl.i_g(0)), pwts[0], sc(sl.i_w(0)), N)
-            if need[2 + 2 * l]:
+            if need[3 + 2 * l]:
                 dw = ops.tc_gemm_split2h_tn(pg, sc(sl.i_g(l)), N, acts[l], sc(sl.i_in(l)), K)   # g^T x  [N, K]
                 grads[2 * l] = dw if dw.is_contiguous() else dw.contiguous()
             grads[2 * l + 1] = db
             pg, db = pg_prev, db_prev
         sl.bwd_ready = True
-        return (dx, None, *grads)
+        return (dx, None, None, *grads)
 
 
 def tc_fused_enabled() -> bool:
@@ -303,20 +323,46 @@ class MLP(Module):
         sl.fwd_ready = True
         return h
 
+    def tower_call(self, x_like) -> Optional["_TowerCall"]:
+        """For the producer of this tower's input (``fm_head(..., tower=mlp)``): if the next ``forward`` will run fused
+        — ``x_like`` has the input's shape / dtype / device — roll the scales now and return the call record, so the
+        producer can write the input directly as planes (``call.cs[0:1]`` = its scale, ``call.mlp._scales.max_word(0)``
+        = where its maximum goes, ``call.in_planes`` = the planes).  None otherwise: the producer writes fp32."""
+        self._pending = None
+        if not self._fused_eligible(x_like):
+            return None
+        sl = self._scales
+        if sl is None or sl.device != x_like.device or sl.L != len(self.mlp):
+            return None
+        want_grad = torch.is_grad_enabled()
+        if not sl.fwd_ready or (want_grad and not sl.bwd_ready):
+            return None
+        self._pending = _TowerCall(self, sl.roll())
+        return self._pending
+
     def forward(self, x):
-        if not self._fused_eligible(x):
+        call, self._pending = getattr(self, "_pending", None), None
+        if call is not None and getattr(x, "_ptrec_tower_in", None) is not call:
+            call = None        # someone else's tensor: a call record only pairs with the input written for it
+        if call is None and getattr(x, "_ptrec_tower_in", None) is not None:
+            raise RuntimeError("this tensor was written as the planes of another fused-tower call; its fp32 values do not exist")
+        if call is None and not self._fused_eligible(x):
             return self.mlp(x)
         if self._scales is None or self._scales.device != x.device or self._scales.L != len(self.mlp):
             self._scales = _TowerScales(len(self.mlp), x.device)
         sl = self._scales
         want_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
-        if not sl.fwd_ready or (want_grad and not sl.bwd_ready):
+        if call is None and (not sl.fwd_ready or (want_grad and not sl.bwd_ready)):
             return self._forward_recording(x, want_grad)
         x2 = x if x.stride(-1) == 1 else x.contiguous()
         params = []
         for d in self.mlp:
             params += [d.linear.weight, d.linear.bias]
-        return _TcMLP.apply(x2, self, *params)
+        if call is None:
+            call = _TowerCall(self, sl.roll())
+        y = _TcMLP.apply(x2, self, call, *params)
+        y._ptrec_tower_out = call   # row_dot(..., tower_handoff=True) hands the gradient of y back as planes
+        return y
 
     # picked up by IModel.train_step (non-synchronising) and IModel._check_device_flags (once per epoch)
     def poll_errors(self) -> None:

@@ -18,9 +18,17 @@ class _FMHead(torch.autograd.Function):
     """K8: first-order sum + FM second order + dense linear term + bias -> logit, and the tower input [v | x]."""
 
     @staticmethod
-    def forward(ctx, v2d, w1, x, wd, bias, F, D, want_deep_in, want_planes):
+    def forward(ctx, v2d, w1, x, wd, bias, F, D, want_deep_in, want_planes, call=None):
         planes = None
-        if want_deep_in and want_planes:
+        if call is not None:
+            # the K6 fused tower reads its input as fp16 planes: write those, and no fp32 copy (deep_in is an
+            # allocation that only carries the autograd edge; MLP.forward pairs it with the call record)
+            sl = call.mlp._scales
+            logit, call.in_planes = ops.fm_head_fwd_h2(v2d, w1, x, wd, bias, F, D, call.cs[sl.i_x():sl.i_x() + 1],
+                                                       sl.max_word(sl.i_x()))
+            nd = 0 if x is None else x.shape[1]
+            deep_in = v2d.new_empty(v2d.shape[0], (F * D + nd + 3) // 4 * 4)[:, :F * D + nd]
+        elif want_deep_in and want_planes:
             logit, deep_in, planes = ops.fm_head_fwd(v2d, w1, x, wd, bias, F, D, True, True)
         else:
             logit, deep_in = ops.fm_head_fwd(v2d, w1, x, wd, bias, F, D, want_deep_in)
@@ -50,22 +58,33 @@ class _FMHead(torch.autograd.Function):
                 g_deep_in = buf[:, :g_deep_in.shape[1]]
         gv, gw1, gwd, gb = ops.fm_head_bwd(v2d, x, wd, g_logit.contiguous(), g_deep_in, F, D, want_w1=need[1],
                                            want_wd=need[3] and wd is not None, want_bias=need[4])
-        return gv if need[0] else None, gw1, None, gwd, gb, None, None, None, None
+        return gv if need[0] else None, gw1, None, gwd, gb, None, None, None, None, None
 
 
 class _RowDot(torch.autograd.Function):
-    """K8: y[b] = h[b, :] . w — the Linear(H, 1, bias=False) closing a tower."""
+    """K8: y[b] = h[b, :] . w — the Linear(H, 1, bias=False) closing a tower.  ``call``: h is the output of a K6 fused
+    tower (dense._TowerCall) and has no other consumer: the backward writes the gradient of the tower's last
+    pre-activation as that tower's operand planes (+ its bias gradient) instead of an fp32 gradient of h."""
 
     @staticmethod
-    def forward(ctx, h, w):
+    def forward(ctx, h, w, call=None):
         ctx.save_for_backward(h, w)
+        ctx.call = call
         return ops.rowdot_fwd(h, w)
 
     @staticmethod
     def backward(ctx, g):
         h, w = ctx.saved_tensors
+        call = ctx.call
+        if call is not None and ctx.needs_input_grad[0]:
+            sl = call.mlp._scales
+            i = sl.i_g(sl.L - 1)
+            planes, db, gw = ops.rowdot_bwd_h2(h, w, g.contiguous(), call.cs[i:i + 1], sl.max_word(i), True,
+                                               ctx.needs_input_grad[1])
+            call.grad = (planes, db)
+            return h.new_empty(h.shape), gw, None   # not materialised: the tower's backward reads call.grad
         gh, gw = ops.rowdot_bwd(h, w, g.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
-        return gh, gw
+        return gh, gw, None
 
 
 def fm_head_enabled() -> bool:
@@ -73,12 +92,14 @@ def fm_head_enabled() -> bool:
     return os.environ.get("PTREC_FM_HEAD", "1") != "0"
 
 
-def fm_head(v: Tensor, w1, x, wd, bias, want_deep_in: bool, tower_units: int = 0):
+def fm_head(v: Tensor, w1, x, wd, bias, want_deep_in: bool, tower_units: int = 0, tower=None):
     """``v [B, F, D]``, ``w1 [B, F, 1]`` or None, ``x [B, nd]`` or None, ``wd`` = Linear(nd, 1).weight or None,
     ``bias`` scalar parameter or None -> ``(logit [B], deep_in [B, F*D + nd] or None)``; None if K8 does not cover
     the shape (the caller composes K3 + library ops instead).  ``tower_units``: width of the Dense layer that will
     consume ``deep_in``; when that layer runs on K6 the head also writes its bf16 operand planes
-    (``deep_in._ptrec_planes``), sparing the layer its split pass."""
+    (``deep_in._ptrec_planes``), sparing the layer its split pass.  ``tower``: the ``MLP`` that is the ONLY consumer of
+    ``deep_in``; when its next forward runs fused (K6 fused tower) the head writes the tower's fp16 operand planes and
+    no fp32 ``deep_in`` at all (the returned tensor then only carries the autograd edge to that MLP)."""
     B, F, D = v.shape
     nd = 0 if x is None else x.shape[1]
     if not (v.is_cuda and v.dtype == torch.float32 and fm_head_enabled() and ops.fm_head_supported(F, D, nd)):
@@ -87,27 +108,48 @@ def fm_head(v: Tensor, w1, x, wd, bias, want_deep_in: bool, tower_units: int = 0
     if not (v2d.stride(1) == 1 and v2d.stride(0) % 4 == 0 and v2d.data_ptr() % 16 == 0):
         v2d = v2d.contiguous()
     from . import dense
-    want_planes = (want_deep_in and tower_units > 0 and dense.tc_linear_enabled() and ops.tc_mode() == "bf16x3"
+    nd_ = 0 if x is None else x.shape[1]
+    call = None
+    if want_deep_in and tower is not None and hasattr(tower, "tower_call"):
+        call = tower.tower_call(_Meta(B, F * D + nd_, v))
+    want_planes = (call is None and want_deep_in and tower_units > 0 and dense.tc_linear_enabled() and ops.tc_mode() == "bf16x3"
                    and B * (F * D + nd) * tower_units >= dense.TC_MIN_MACS)
     logit, deep_in, planes = _FMHead.apply(v2d, w1.reshape(B, F).contiguous() if w1 is not None else None,
                                            x.contiguous() if x is not None else None,
                                            wd.reshape(-1) if (wd is not None and x is not None) else None,
                                            bias.reshape(1) if bias is not None else None, F, D, want_deep_in,
-                                           want_planes)
+                                           want_planes, call)
     if not want_deep_in:
         return logit, None
+    if call is not None:
+        deep_in._ptrec_tower_in = call
+        return logit, deep_in
     if planes.numel():
         deep_in._ptrec_planes = planes
     return logit, deep_in
 
 
-def row_dot(h: Tensor, weight: Tensor):
-    """``Linear(H, 1, bias=False)(h).squeeze(-1)`` as one pass; None if the shape is not covered."""
+class _Meta:
+    """Shape / dtype / device of a tensor that does not exist yet (what ``MLP.tower_call`` needs to decide)."""
+
+    def __init__(self, rows: int, cols: int, like: Tensor):
+        self.shape, self.dtype, self.device, self.is_cuda = (rows, cols), like.dtype, like.device, like.is_cuda
+
+    def dim(self):
+        return 2
+
+
+def row_dot(h: Tensor, weight: Tensor, tower_handoff: bool = False):
+    """``Linear(H, 1, bias=False)(h).squeeze(-1)`` as one pass; None if the shape is not covered.
+    ``tower_handoff``: the caller guarantees that ``h`` — the output of an ``MLP`` — has no other consumer; when that
+    MLP ran as a K6 fused tower, the backward then hands the gradient over in the tower's operand format (no fp32
+    gradient of ``h`` is written)."""
     if not (h.is_cuda and h.dtype == torch.float32 and h.dim() == 2 and fm_head_enabled()
             and ops.rowdot_supported(h.shape[1]) and h.stride(1) == 1 and h.stride(0) % 4 == 0
             and h.data_ptr() % 16 == 0):
         return None
-    return _RowDot.apply(h, weight.reshape(-1))
+    call = getattr(h, "_ptrec_tower_out", None) if tower_handoff else None
+    return _RowDot.apply(h, weight.reshape(-1), call)
 
 
 class CrossNet(nn.Module):

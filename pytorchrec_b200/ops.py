@@ -404,6 +404,45 @@ def fm_head_bwd(v: torch.Tensor, x: Optional[torch.Tensor], wd: Optional[torch.T
     return gv, gw1, gwd, gb
 
 
+def fm_head_fwd_h2(v: torch.Tensor, w1: Optional[torch.Tensor], x: Optional[torch.Tensor], wd: Optional[torch.Tensor],
+                   bias: Optional[torch.Tensor], F: int, D: int, scale: torch.Tensor, max_out: torch.Tensor):
+    """``fm_head_fwd`` whose tower input leaves as the two fp16 planes of the K6 fused tower, split with ``scale`` (a
+    one-element view of the tower's carried scales); no fp32 tower input is written.
+    Returns (logit [B], planes [2, B, pad8(F*D+nd)] fp16)."""
+    lib = _lib.load()
+    _require_cuda(v, w1, x, wd, bias, scale, max_out)
+    B = v.shape[0]
+    nd = 0 if x is None else x.shape[1]
+    dev = v.device
+    logit = torch.empty(B, dtype=torch.float32, device=dev)
+    ld = _pad8(F * D + nd)
+    planes = torch.empty(2, B, ld, dtype=torch.float16, device=dev)
+    _lib.check(lib.ptrec_fm_head_fwd_h2(_ptr(v), v.stride(0), _ptr(w1), w1.stride(0) if w1 is not None else 0, _ptr(x),
+                                        x.stride(0) if x is not None else 0, _ptr(wd), _ptr(bias), B, F, D, nd,
+                                        _ptr(logit), None, 0, _ptr(planes), ld, _ptr(scale), _ptr(max_out),
+                                        _stream(dev)), "ptrec_fm_head_fwd_h2")
+    return logit, planes
+
+
+def rowdot_bwd_h2(h: torch.Tensor, w: torch.Tensor, g: torch.Tensor, scale: torch.Tensor, max_out: torch.Tensor,
+                  want_colsum: bool, want_w: bool):
+    """Backward of ``rowdot`` behind a fused tower: (planes [2, B, pad8(H)] fp16 of (g (x) w) * (h > 0) split with
+    ``scale``, colsum [H] or None, grad_w [H] or None).  No fp32 gradient of h is written."""
+    lib = _lib.load()
+    _require_cuda(h, w, g, scale, max_out)
+    B, H = h.shape
+    dev = h.device
+    ld = _pad8(H)
+    planes = torch.empty(2, B, ld, dtype=torch.float16, device=dev)
+    colsum = torch.empty(H, dtype=torch.float32, device=dev) if want_colsum else None
+    gw = torch.empty(H, dtype=torch.float32, device=dev) if want_w else None
+    ws = _workspace("rowdot_h2", 2 * lib.ptrec_rowdot_bwd_workspace_bytes(H), dev)
+    _lib.check(lib.ptrec_rowdot_bwd_h2(_ptr(h), h.stride(0), _ptr(w), _ptr(g), B, H, _ptr(planes), ld, _ptr(scale),
+                                       _ptr(max_out), _ptr(colsum), _ptr(gw), _ptr(ws), ws.numel(), _stream(dev)),
+               "ptrec_rowdot_bwd_h2")
+    return planes, colsum, gw
+
+
 def rowdot_supported(H: int) -> bool:
     return bool(_lib.load().ptrec_rowdot_supported(H))
 

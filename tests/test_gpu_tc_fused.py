@@ -206,3 +206,53 @@ def test_fused_mlp_flags_a_tensor_that_outgrows_its_scale(monkeypatch):
     with torch.no_grad():
         mlp(x)
     mlp.check_errors()
+
+
+def test_tower_neighbours_hand_over_planes_and_deepfm_trains_identically(monkeypatch):
+    """fm_head(..., tower=mlp) writes the tower input as planes, row_dot(..., tower_handoff=True) hands the output
+    gradient back as planes: a DeepFM trained that way equals one trained with the hand-offs switched off (fp32
+    tensors + split passes) up to the rounding of one extra fp32 store, and the launch count drops."""
+    import numpy as np
+    from pytorchrec_b200.feature_column import CategoricalColumnWithIdentity as Col
+    from pytorchrec_b200.feature_column import NumericColumn
+    from pytorchrec_b200.metric import LogLoss
+    from pytorchrec_b200.model import DeepFM
+    from pytorchrec_b200.model.layer import dense, interaction
+    from pytorchrec_b200.optim import SparseSGD
+    monkeypatch.setattr(dense, "TC_MIN_MACS", 0)
+    F, nd, D, B = 6, 3, 16, 1024
+    rows = [50 + 13 * f for f in range(F)]
+    scols = [Col(rows[f], f"C{f}") for f in range(F)]
+    dcols = [NumericColumn(f"I{j}", 0.0, 1.0, 0.5, 0.25) for j in range(nd)]
+    lab = Col(2, "label")
+
+    def run(handoff: bool):
+        if not handoff:
+            monkeypatch.setattr(dense.MLP, "tower_call", lambda self, x_like: None)
+            real = interaction.row_dot
+            monkeypatch.setattr(interaction, "row_dot", lambda h, w, tower_handoff=False: real(h, w, False))
+        m = DeepFM(scols, dcols, lab, D, [64, 32], random_seed=7)
+        m.compile(SparseSGD(m.get_parameters(), lr=0.2), torch.nn.BCEWithLogitsLoss(), [LogLoss()], DEV)
+        rng = np.random.default_rng(3)
+        lib = _lib.load()
+        losses, launches = [], []
+        for step in range(5):
+            batch = {f"C{f}": torch.from_numpy(rng.integers(0, rows[f], size=B).astype(np.int32)) for f in range(F)}
+            batch.update({f"I{j}": torch.from_numpy(rng.random(B).astype(np.float32)) for j in range(nd)})
+            batch["label"] = torch.from_numpy(rng.integers(0, 2, size=B).astype(np.int32))
+            n0 = lib.ptrec_launch_count()
+            losses.append(m.train_step(batch)["loss"].item())
+            launches.append(lib.ptrec_launch_count() - n0)
+        m.mlp.check_errors()
+        monkeypatch.undo()
+        monkeypatch.setattr(dense, "TC_MIN_MACS", 0)
+        return losses, launches, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+
+    l1, n1, sd1 = run(True)
+    l0, n0, sd0 = run(False)
+    assert n1[-1] <= n0[-1] - 2, (n1, n0)        # split(x) and split(g) are gone (the column sums moved, not vanished)
+    for a, b in zip(l1, l0):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (l1, l0)
+    for k in sd1:
+        d = (sd1[k].double() - sd0[k].double()).abs().max().item()
+        assert d <= 2e-6 * max(1.0, sd0[k].abs().max().item()), (k, d)
