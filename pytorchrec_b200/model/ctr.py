@@ -85,10 +85,20 @@ class FM(IModel):
             deep_in = torch.cat([flat, x], dim=1) if x is not None else flat
         return logit, deep_in
 
+    def _lookups(self, data):
+        """(v [B, F, D], w [B, F, 1]): the first-order tables (4-byte rows, latency-bound) are looked up — and, in
+        the backward, updated — on a second stream beside the embedding tables."""
+        from .layer.embedding import aux_stream
+        v = self.embeddings(data)
+        with aux_stream(v.device if v.is_cuda else None) as aux:
+            w = self.first_order(data)
+        aux.join(w)
+        return v, w
+
     def forward(self, data: Dict[str, Tensor]):
-        v = self.embeddings(data)  # [B, F, D]
+        v, w = self._lookups(data)  # [B, F, D], [B, F, 1]
         x = _dense_matrix(self.dense_columns, data)
-        logit, _ = self._head(data, v, self.first_order(data), x, False)
+        logit, _ = self._head(data, v, w, x, False)
         return logit, self._target(data)
 
 
@@ -122,9 +132,9 @@ class DeepFM(FM):
         return y if y is not None else self.deep_out(h).squeeze(-1)
 
     def forward(self, data: Dict[str, Tensor]):
-        v = self.embeddings(data)
+        v, w = self._lookups(data)
         x = _dense_matrix(self.dense_columns, data)
-        logit, deep_in = self._head(data, v, self.first_order(data), x, True)
+        logit, deep_in = self._head(data, v, w, x, True)
         return logit + self._deep_logit(deep_in), self._target(data)
 
 

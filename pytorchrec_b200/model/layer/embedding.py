@@ -79,7 +79,8 @@ class EmbeddingGroup:
         # modules reading the same columns (e.g. FM's embedding and first-order tables) share one sort
         srt = shared.get("sort") if shared is not None else None
         if srt is not None and shared.get("sort_event") is not None:
-            torch.cuda.current_stream(ids.device).wait_event(shared.pop("sort_event"))  # join the early sort
+            # join the early sort; the event stays: a second consumer may run on another stream (aux_stream below)
+            torch.cuda.current_stream(ids.device).wait_event(shared["sort_event"])
         if srt is None:
             srt = ops.sort_dedup(tables, layout, ids, lens, batch)
             if shared is not None:
@@ -110,6 +111,43 @@ class EmbeddingGroup:
 
 
 _SIDE_STREAMS: Dict[torch.device, "torch.cuda.Stream"] = {}
+_AUX_STREAMS: Dict[torch.device, "torch.cuda.Stream"] = {}
+
+
+class aux_stream:
+    """``with aux_stream(device) as s:`` runs a small, independent lookup (FM's first-order tables: 4-byte rows) on a
+    second stream forked from the current one, so that its latency-bound gather — and, because autograd runs a
+    node's backward on its forward's stream, its fused update — overlaps the wide tables' kernels instead of queueing
+    behind them.  ``s.join(t)`` before the first use of a result on the main stream.  A no-op object on CPU or with
+    ``PTREC_AUX_STREAM=0``.  Captured in a step graph as a fork / join."""
+
+    def __init__(self, device):
+        import os
+        self.on = device is not None and torch.device(device).type == "cuda" and os.environ.get("PTREC_AUX_STREAM", "1") != "0"
+        self.device = device
+
+    def __enter__(self):
+        if self.on:
+            self.main = torch.cuda.current_stream(self.device)
+            self.side = _AUX_STREAMS.get(self.device)
+            if self.side is None:
+                self.side = _AUX_STREAMS[self.device] = torch.cuda.Stream(self.device)
+            self.side.wait_stream(self.main)
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self, *tensors) -> None:
+        if self.on:
+            self.main.wait_stream(self.side)
+            for t in tensors:
+                if t is not None:
+                    t.record_stream(self.main)
 
 
 def _early_sort_enabled() -> bool:
