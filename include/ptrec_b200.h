@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 21
+#define PTREC_ABI_VERSION 22
 
 /* error codes */
 #define PTREC_OK 0
@@ -531,6 +531,16 @@ int ptrec_tc_gemm_split2h_fused(const void* a_planes, const float* scale_a, int6
                                 float* out, int64_t ldo, void* out_planes, int64_t out_planes_ld, const float* out_scale,
                                 const uint32_t* mask_in, uint32_t* mask_out, int64_t mask_ld, float* colsum,
                                 float* absmax_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K9 the loss closing train_step (torchrec/model/IModel.py:121 with BCEWithLogitsLoss(reduction='mean')): forward and
+ * gradient in one launch.  loss[0] = mean_i (max(x,0) - x t + log1p(exp(-|x|))); grad[i] = (sigmoid(x_i) - t_i) / n
+ * (grad may be NULL).  Deterministic (fixed summation order).  workspace: ptrec_bce_logits_workspace_bytes(), zero
+ * before the first call and owned by this entry point afterwards.
+ */
+size_t ptrec_bce_logits_workspace_bytes(void);
+int ptrec_bce_logits_mean(const float* logits, const float* target, int64_t n, float* loss, float* grad,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * C1 row-wise sharding: pack / unpack either side of the all-to-all (NCCL, issued by the host through

@@ -13,6 +13,8 @@ from abc import ABC, abstractmethod
 from typing import Any, Dict, List, Optional
 
 import numpy as np
+import os
+
 import torch
 from torch.nn import Module
 from torch.nn.modules.loss import _Loss  # noqa
@@ -351,12 +353,25 @@ class IModel(Module, ABC):
     def _train_step_body(self, data: Dict):
         """forward, loss, zero_grad, backward, [gradient hook], step — IModel.py:120-124."""
         prediction, target = self(data)
-        loss = self.compiled_loss(prediction, target)
+        loss = self._apply_loss(prediction, target)
         self.compiled_optimizers.zero_grad()
         loss.backward()
         self._before_optimizer_step()
         self.compiled_optimizers.step(closure=None)
         return loss
+
+    def _apply_loss(self, prediction, target):
+        """``self.compiled_loss(prediction, target)``; a plain ``BCEWithLogitsLoss()`` on CUDA runs as K9 (forward and
+        gradient in one launch, ``PTREC_FUSED_LOSS=0`` keeps the module)."""
+        lf = self.compiled_loss
+        if (type(lf) is torch.nn.BCEWithLogitsLoss and lf.reduction == "mean" and lf.weight is None
+                and lf.pos_weight is None and torch.is_tensor(prediction) and prediction.is_cuda
+                and os.environ.get("PTREC_FUSED_LOSS", "1") != "0"):
+            from .. import ops
+            out = ops.bce_logits_mean(prediction, target)
+            if out is not None:
+                return out
+        return lf(prediction, target)
 
     def _flag_pollers(self) -> list:
         p = self.__dict__.get("_pollers")

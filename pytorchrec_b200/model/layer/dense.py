@@ -179,6 +179,9 @@ class _TowerScales:
         return cs
 
 
+_W_STREAMS = {}   # device -> side stream of the ahead-of-time weight splits
+
+
 class _TowerCall:
     """One forward (+ backward) of a fused tower: the scales it reads, and what its neighbours hand over in the tower's
     own operand format — the producer of its input (``fm_head(..., tower=mlp)``: planes of x) and the consumer of its
@@ -188,6 +191,8 @@ class _TowerCall:
         self.mlp, self.cs = mlp, cs
         self.in_planes = None      # planes of the tower input, written by its producer
         self.grad = None           # (planes of the last pre-activation gradient, last bias gradient)
+        self.w_planes = None       # [(planes of W_l, transposed planes or None)] when prepared ahead (MLP.tower_call)
+        self.w_event = None        # ... on a side stream: recorded when they are complete
 
 
 class _TcMLP(torch.autograd.Function):
@@ -211,10 +216,20 @@ class _TcMLP(torch.autograd.Function):
             px, _, _ = ops.tc_split2h_prescaled(x, sc(sl.i_x()), sl.max_word(sl.i_x()))
         acts, masks, pwts = [px], [], []
         y = None
+        if call.w_planes is not None:   # split ahead of time beside the producer of x (MLP.tower_call)
+            main = torch.cuda.current_stream(x.device)
+            main.wait_event(call.w_event)
+            for pw, pwt in call.w_planes:
+                pw.record_stream(main)
+                if pwt is not None:
+                    pwt.record_stream(main)
         for l in range(L):
             W, b = params[2 * l], params[2 * l + 1]
-            pw, pwt, _ = ops.tc_split2h_prescaled(W, sc(sl.i_w(l)), sl.max_word(sl.i_w(l)),
-                                                  want_t=any_grad and (l > 0 or need_dx))
+            if call.w_planes is not None:
+                pw, pwt = call.w_planes[l]
+            else:
+                pw, pwt, _ = ops.tc_split2h_prescaled(W, sc(sl.i_w(l)), sl.max_word(sl.i_w(l)),
+                                                      want_t=any_grad and (l > 0 or need_dx))
             pwts.append(pwt)
             last = l == L - 1
             y, py, mask, _ = ops.tc_gemm_split2h_fused(
@@ -337,8 +352,23 @@ class MLP(Module):
         want_grad = torch.is_grad_enabled()
         if not sl.fwd_ready or (want_grad and not sl.bwd_ready):
             return None
-        self._pending = _TowerCall(self, sl.roll())
-        return self._pending
+        call = self._pending = _TowerCall(self, sl.roll())
+        # the weights' planes depend on nothing the producer of x computes: split them on a side stream while it runs
+        dev = x_like.device
+        main = torch.cuda.current_stream(dev)
+        side = _W_STREAMS.get(dev)
+        if side is None:
+            side = _W_STREAMS[dev] = torch.cuda.Stream(dev)
+        side.wait_stream(main)   # the roll above (and the optimizer step that wrote the weights)
+        with torch.cuda.stream(side):
+            call.w_planes = []
+            for l, d in enumerate(self.mlp):
+                pw, pwt, _ = ops.tc_split2h_prescaled(d.linear.weight.detach(), call.cs[sl.i_w(l):sl.i_w(l) + 1],
+                                                      sl.max_word(sl.i_w(l)), want_t=want_grad)
+                call.w_planes.append((pw, pwt))
+            call.w_event = torch.cuda.Event()
+            call.w_event.record(side)
+        return call
 
     def forward(self, x):
         call, self._pending = getattr(self, "_pending", None), None

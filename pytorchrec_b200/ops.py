@@ -907,6 +907,44 @@ def tc_gemm_split2h_fused(a_planes: torch.Tensor, scale_a: torch.Tensor, b_plane
 
 
 # ----------------------------------------------------------------------------------------------
+# K9 BCEWithLogitsLoss(reduction='mean'): forward + gradient in one launch
+# ----------------------------------------------------------------------------------------------
+_BCE_WS: Dict[tuple, torch.Tensor] = {}
+
+
+class _BCELogitsMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target):
+        lib = _lib.load()
+        dev = logits.device
+        key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+        ws = _BCE_WS.get(key)
+        if ws is None:   # zero once: the kernel leaves its ticket counter at zero
+            ws = _BCE_WS[key] = torch.zeros(lib.ptrec_bce_logits_workspace_bytes(), dtype=torch.uint8, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        grad = torch.empty_like(logits) if ctx.needs_input_grad[0] else None
+        _lib.check(lib.ptrec_bce_logits_mean(_ptr(logits), _ptr(target), logits.numel(), _ptr(loss), _ptr(grad),
+                                             _ptr(ws), ws.numel(), _stream(dev)), "ptrec_bce_logits_mean")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None
+
+
+def bce_logits_mean(logits: torch.Tensor, target: torch.Tensor) -> Optional[torch.Tensor]:
+    """``BCEWithLogitsLoss()(logits, target)`` (mean reduction, no weights) in one launch; None if the inputs are not
+    contiguous fp32 CUDA tensors of one shape (the caller then uses the module)."""
+    if not (logits.is_cuda and target.is_cuda and logits.dtype == torch.float32 and target.dtype == torch.float32
+            and logits.shape == target.shape and logits.is_contiguous() and target.is_contiguous()
+            and logits.numel() >= 1 and not target.requires_grad):
+        return None
+    return _BCELogitsMean.apply(logits, target)
+
+
+# ----------------------------------------------------------------------------------------------
 # K5 DCN-v2 cross layers (tcgen05)
 # ----------------------------------------------------------------------------------------------
 def _check_bf16_2d(*ts):

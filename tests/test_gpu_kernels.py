@@ -765,3 +765,26 @@ def test_producer_written_planes_are_the_exact_split_of_the_fp32_result(tc_mode)
     x = torch.randn(300, 13, generator=gen).to(DEV)
     logit, deep_in, planes = ops.fm_head_fwd(v, None, x, None, None, 26, 16, True, True)
     assert torch.equal(deep_in, torch.cat([v, x], 1)) and torch.equal(planes, ops.tc_split3(deep_in)[0])
+
+
+# ------------------------------------------------------------------------------------------ K9 loss
+@pytest.mark.parametrize("n", [1, 5, 4096, 16384, 300001])
+def test_bce_logits_mean_matches_torch(n):
+    """K9 against ``torch.nn.BCEWithLogitsLoss()`` (the loss IModel.train_step applies, torchrec/model/IModel.py:121):
+    value and gradient, saturated logits included; bit-reproducible from run to run."""
+    gen = torch.Generator().manual_seed(n)
+    x = (4.0 * torch.randn(n, generator=gen))
+    x[::7] = 60.0 * torch.sign(x[::7])          # saturated both ways
+    t = (torch.rand(n, generator=gen) < 0.3).float()
+    xd = x.to(DEV).requires_grad_(True)
+    loss = ops.bce_logits_mean(xd, t.to(DEV))
+    (2.5 * loss).backward()
+    xr = x.double().requires_grad_(True)
+    ref = torch.nn.BCEWithLogitsLoss()(xr, t.double())
+    (2.5 * ref).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-6 * max(1.0, abs(ref.item()))
+    np.testing.assert_allclose(xd.grad.cpu().double().numpy(), xr.grad.numpy(), rtol=2e-6, atol=1e-7 / n)
+    again = ops.bce_logits_mean(x.to(DEV), t.to(DEV))
+    assert again.item() == loss.item()
+    if n > 2:
+        assert ops.bce_logits_mean(x.to(DEV)[::2], t.to(DEV)[::2]) is None   # non-contiguous: the caller uses the module
