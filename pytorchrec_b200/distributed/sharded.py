@@ -185,6 +185,49 @@ def _side_stream(dev) -> "torch.cuda.Stream":
     return st
 
 
+_AUX: Dict[torch.device, "torch.cuda.Stream"] = {}
+
+
+def _aux_stream(dev) -> "torch.cuda.Stream":
+    """Second compute stream: the narrow widths of a slot (the first-order column: 4-byte rows, latency-bound) are
+    gathered and updated beside the wide one instead of behind it (PTREC_AUX_STREAM=0: same stream)."""
+    st = _AUX.get(dev)
+    if st is None:
+        st = _AUX[dev] = torch.cuda.Stream(dev)
+    return st
+
+
+def _aux_enabled() -> bool:
+    import os
+    return os.environ.get("PTREC_AUX_STREAM", "1") != "0"
+
+
+def _owner_updates(mod, C, srt, recv_g, dev) -> None:
+    """Owner-side segment-sum + fused optimizer update of every width; widths after the first on the aux stream."""
+    main = torch.cuda.current_stream(dev)
+    use_aux = _aux_enabled() and len(mod.dims) > 1
+    aux = _aux_stream(dev) if use_aux else None
+    prepared = []
+    for k, D in enumerate(mod.dims):
+        eg = mod.egroups[k]
+        bind = eg.binding()
+        if bind is None:
+            raise RuntimeError("row-wise sharded tables need a pytorchrec_b200.optim sparse optimizer")
+        s1, s2, args = bind[0]._fused_prepare(eg, bind[1])  # may interleave weight | state: before taking pointers
+        tables = eg.table_set.refresh([t.weight.data for t in eg.tables])
+        prepared.append((tables, s1, s2, args))
+    if use_aux:
+        aux.wait_stream(main)   # gradient rows landed (barrier), sort joined
+    for k, (tables, s1, s2, args) in enumerate(prepared):
+        if use_aux and k > 0:
+            with torch.cuda.stream(aux):
+                ops.bwd_fused(tables, s1, s2, mod.owner_layout(C, k), C, srt, recv_g, None, args, grad_row_stride=mod.slot_width)
+        else:
+            ops.bwd_fused(tables, s1, s2, mod.owner_layout(C, k), C, srt, recv_g, None, args, grad_row_stride=mod.slot_width)
+    if use_aux:
+        main.wait_stream(aux)
+
+
 class _PeerLookup(torch.autograd.Function):
     """The same lookup with the exchange inside the kernels (peer loads / stores over NVLink), see module docstring."""
 
@@ -225,10 +268,23 @@ class _PeerLookup(torch.autograd.Function):
             ctx.early = (ret_pos, srt, C, ev)
         flat = ids.reshape(-1)
         outs = []
+        main = torch.cuda.current_stream(dev)
+        use_aux = _aux_enabled() and len(mod.dims) > 1
+        if use_aux:
+            aux = _aux_stream(dev)
+            aux.wait_stream(main)
         for k, D in enumerate(mod.dims):
-            out = ops.gather_fwd_sharded(mod._shard_ptrs[k], mod._rows_global, mod.world, mod._row_stride[k],
-                                         mod.plain_layout(k), flat, B, err_flag=mod.egroups[k].err_flag(dev))
+            if use_aux and k > 0:
+                with torch.cuda.stream(aux):
+                    out = ops.gather_fwd_sharded(mod._shard_ptrs[k], mod._rows_global, mod.world, mod._row_stride[k],
+                                                 mod.plain_layout(k), flat, B, err_flag=mod.egroups[k].err_flag(dev))
+                out.record_stream(main)
+            else:
+                out = ops.gather_fwd_sharded(mod._shard_ptrs[k], mod._rows_global, mod.world, mod._row_stride[k],
+                                             mod.plain_layout(k), flat, B, err_flag=mod.egroups[k].err_flag(dev))
             outs.append(out.view(B, F, D))
+        if use_aux:
+            main.wait_stream(aux)
         ctx.mod, ctx.shape = mod, (F, B)
         ctx.save_for_backward(ids)
         return tuple(outs)
@@ -255,15 +311,7 @@ class _PeerLookup(torch.autograd.Function):
             gs.append(g if g.is_contiguous() else g.contiguous())
         mod.scatter_grads(gs, ret_pos, pb, B, F, C)
         mod.barrier(ops.PeerSync.GRADS, dev)  # every rank's gradient rows have landed in every owner's buffer
-        recv_g = pb["recv_g"]
-        for k, D in enumerate(mod.dims):
-            eg = mod.egroups[k]
-            bind = eg.binding()
-            if bind is None:
-                raise RuntimeError("row-wise sharded tables need a pytorchrec_b200.optim sparse optimizer")
-            s1, s2, args = bind[0]._fused_prepare(eg, bind[1])  # may interleave weight | state: before taking pointers
-            tables = eg.table_set.refresh([t.weight.data for t in eg.tables])
-            ops.bwd_fused(tables, s1, s2, mod.owner_layout(C, k), C, srt, recv_g, None, args, grad_row_stride=S)
+        _owner_updates(mod, C, srt, pb["recv_g"], dev)
         mod._dirty = True   # tables changed, buffers recycled: a fence must precede the next peer access
         return (None, None) + (None,) * (len(mod.dims) * len(mod.columns))
 
@@ -325,15 +373,7 @@ class _PushLookup(torch.autograd.Function):
         mod.barrier(ops.PeerSync.GRADS, dev)  # every rank's gradient rows have landed in every owner's buffer
         srt, ev = ctx.early
         torch.cuda.current_stream(dev).wait_event(ev)  # join the early sort
-        recv_g = pb["recv_g"]
-        for k, D in enumerate(mod.dims):
-            eg = mod.egroups[k]
-            bind = eg.binding()
-            if bind is None:
-                raise RuntimeError("row-wise sharded tables need a pytorchrec_b200.optim sparse optimizer")
-            s1, s2, args = bind[0]._fused_prepare(eg, bind[1])  # may interleave weight | state: before taking pointers
-            tables = eg.table_set.refresh([t.weight.data for t in eg.tables])
-            ops.bwd_fused(tables, s1, s2, mod.owner_layout(C, k), C, srt, recv_g, None, args, grad_row_stride=S)
+        _owner_updates(mod, C, srt, pb["recv_g"], dev)
         mod._dirty = True   # tables changed, buffers recycled: a fence must precede the next exchange
         return (None, None) + (None,) * (len(mod.dims) * len(mod.columns))
 
