@@ -563,10 +563,38 @@ def kernel_roofline(a, model, resident, dev, tensor=True):
     lookups = F * B
 
     def time_it(fn, reps):
+        """Average GPU time of one call: `reps` calls (rotating operands) captured in ONE CUDA graph and replayed, CUDA
+        events around the replays on the launching stream — no host enqueue time between the launches, which for these
+        20 us kernels is as long as the kernels themselves.  Falls back to an eager launch loop if capture fails."""
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()
+        graph = None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(2):
+                    fn(i)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for i in range(reps):
+                    fn(i)
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception:  # noqa: BLE001 — a kernel wrapper that cannot be captured is timed eagerly
+            graph = None
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if graph is not None:
+            e0.record()
+            for _ in range(3):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / (3 * reps) * 1e-3
         e0.record()
         for i in range(reps):
             fn(i)
@@ -628,11 +656,19 @@ def kernel_roofline(a, model, resident, dev, tensor=True):
         hxs = [ops.tc_split2h(x) for x in xs]
         hgs = [ops.tc_split2h(g) for g in gs]
         hw = ops.tc_split2h(lin.weight.detach())
-        t_gemm = time_it(lambda i: ops.tc_gemm_split2h(hxs[i % 4][0], hxs[i % 4][3], hw[0], hw[3], K, bias=bias, relu=True), 40)
+        t_plain = time_it(lambda i: ops.tc_gemm_split2h(hxs[i % 4][0], hxs[i % 4][3], hw[0], hw[3], K, bias=bias, relu=True), 40)
+        # the form the fused tower launches for a hidden layer: bias + ReLU, the result written as the next layer's
+        # fp16 planes + the ReLU bit mask + its maximum (no fp32 output, no split pass afterwards)
+        oscale = torch.full((1,), 2.0 ** 4, device=dev)
+        omax = torch.zeros(1, device=dev)
+        t_gemm = time_it(lambda i: ops.tc_gemm_split2h_fused(hxs[i % 4][0], hxs[i % 4][3], hw[0], hw[3], K, bias=bias, relu=True,
+                                                             want_out=False, out_scale=oscale, want_mask=True, max_out=omax), 40)
         t_wgrad = time_it(lambda i: ops.tc_gemm_split2h_tn(hgs[i % 4][0], hgs[i % 4][3], N, hxs[i % 4][0],
                                                            hxs[i % 4][3], K), 20)
         t_split = time_it(lambda i: ops.tc_split2h(xs[i % 4]), 40)
-        pairs, planes, fmt, kname = 3, 2, "fp16", "gemm_split2h"
+        pairs, planes, fmt, kname = 3, 2, "fp16", "gemm_split2h_fused"
+        kernels["tc_linear_fwd(gemm_split2h, fp32 out)"] = {"seconds": t_plain, "M": B, "N": N, "K": K,
+                                                             "TFLOPs_fp16": 2.0 * 3 * B * N * K / t_plain / 1e12}
     else:
         pxs = [ops.tc_split3(x)[0] for x in xs]
         pgs = [ops.tc_split3(g)[0] for g in gs]

@@ -68,17 +68,13 @@ fm_head_fwd_kernel(const float* __restrict__ v, int64_t vs, const float* __restr
       }
       if (hrow && q < n_chunks) {
         const float tv[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
-        unsigned short p0[4], p1[4];
+        uint32_t p0[2], p1[2];
+        split2h_pair(tv[0], tv[1], hs, p0[0], p1[0]);
+        split2h_pair(tv[2], tv[3], hs, p0[1], p1[1]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __half a0, a1;
-          split2h(tv[i], hs, a0, a1);
-          p0[i] = __half_as_ushort(a0);
-          p1[i] = __half_as_ushort(a1);
-          amax = fmaxf(amax, fabsf(tv[i]));
-        }
-        *reinterpret_cast<uint2*>(hrow + q * 4) = *reinterpret_cast<const uint2*>(p0);
-        *reinterpret_cast<uint2*>(hrow + pl_plane + q * 4) = *reinterpret_cast<const uint2*>(p1);
+        for (int i = 0; i < 4; ++i) amax = fmaxf(amax, fabsf(tv[i]));
+        *reinterpret_cast<uint2*>(hrow + q * 4) = make_uint2(p0[0], p0[1]);
+        *reinterpret_cast<uint2*>(hrow + pl_plane + q * 4) = make_uint2(p1[0], p1[1]);
       }
     }
   }
@@ -288,18 +284,14 @@ rowdot_bwd_kernel(const float* __restrict__ h, int64_t hs, const float* __restri
       if (H2 && q < nq) {
         const float tv[4] = {t[u].x > 0.f ? gb * wv[u].x : 0.f, t[u].y > 0.f ? gb * wv[u].y : 0.f,
                              t[u].z > 0.f ? gb * wv[u].z : 0.f, t[u].w > 0.f ? gb * wv[u].w : 0.f};
-        unsigned short p0[4], p1[4];
+        uint32_t p0[2], p1[2];
+        split2h_pair(tv[0], tv[1], hsc, p0[0], p1[0]);
+        split2h_pair(tv[2], tv[3], hsc, p0[1], p1[1]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __half a0, a1;
-          split2h(tv[i], hsc, a0, a1);
-          p0[i] = __half_as_ushort(a0);
-          p1[i] = __half_as_ushort(a1);
-          amax = fmaxf(amax, fabsf(tv[i]));
-        }
+        for (int i = 0; i < 4; ++i) amax = fmaxf(amax, fabsf(tv[i]));
         unsigned short* o = planes + b * pl_ld + q * 4;
-        *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(p0);
-        *reinterpret_cast<uint2*>(o + pl_plane) = *reinterpret_cast<const uint2*>(p1);
+        *reinterpret_cast<uint2*>(o) = make_uint2(p0[0], p0[1]);
+        *reinterpret_cast<uint2*>(o + pl_plane) = make_uint2(p1[0], p1[1]);
         cs[u].x += tv[0]; cs[u].y += tv[1]; cs[u].z += tv[2]; cs[u].w += tv[3];
       }
     }

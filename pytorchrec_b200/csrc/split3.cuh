@@ -54,4 +54,16 @@ __device__ __forceinline__ void split2h(float v, float scale, __half& h0, __half
   h1 = __float2half_rn(r * kH2Second);
 }
 
+// two values at once through the packed conversions (F2FP.F16.F32.PACK_AB / HADD2.F32): the single-value F2F runs on a
+// slow pipe and was 256 instructions per thread and tile in the fused GEMM epilogue.  Same roundings, same bits.
+// p0 = {h0(v0) low half, h0(v1) high half}, p1 likewise for the second plane.
+__device__ __forceinline__ void split2h_pair(float v0, float v1, float scale, uint32_t& p0, uint32_t& p1) {
+  const float x0 = v0 * scale, x1 = v1 * scale;  // exact (power of two)
+  const __half2 h0 = __floats2half2_rn(x0, x1);
+  const float2 f0 = __half22float2(h0);
+  const __half2 h1 = __floats2half2_rn((x0 - f0.x) * kH2Second, (x1 - f0.y) * kH2Second);
+  p0 = *reinterpret_cast<const uint32_t*>(&h0);
+  p1 = *reinterpret_cast<const uint32_t*>(&h1);
+}
+
 }  // namespace ptrec

@@ -146,24 +146,28 @@ __global__ void __launch_bounds__(kSpThreads) split_kernel(const Split3Args a) {
           if (!(m[i] > 0.f)) v[i] = 0.f;
       }
     }
-    unsigned short pl[NP][4];
+    __align__(8) unsigned short pl[NP][4];
+    if (NP == 3) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (NP == 3) {
+      for (int i = 0; i < 4; ++i) {
         __nv_bfloat16 b0, b1, b2;
         split3(v[i], b0, b1, b2);
         pl[0][i] = __bfloat16_as_ushort(b0);
         pl[1][i] = __bfloat16_as_ushort(b1);
         pl[NP - 1][i] = __bfloat16_as_ushort(b2);
-      } else {
-        __half h0, h1;
-        split2h(v[i], scale, h0, h1);
-        pl[0][i] = __half_as_ushort(h0);
-        pl[1][i] = __half_as_ushort(h1);
-        amax = fmaxf(amax, fabsf(v[i]));
       }
-      cs[i] += v[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i += 2) {
+        uint32_t q0, q1;
+        split2h_pair(v[i], v[i + 1], scale, q0, q1);
+        *reinterpret_cast<uint32_t*>(&pl[0][i]) = q0;
+        *reinterpret_cast<uint32_t*>(&pl[1][i]) = q1;
+        amax = fmaxf(amax, fmaxf(fabsf(v[i]), fabsf(v[i + 1])));
+      }
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cs[i] += v[i];
     if (a.planes != nullptr && r < a.R && c < a.Cp) {  // Cp % 8 == 0, c % 4 == 0: the group of 4 is inside the pitch
       unsigned short* o = a.planes + (int64_t)r * a.pl_ld + c;
 #pragma unroll
@@ -857,12 +861,20 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
             uint32_t keep = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);  // TMEM columns >= N hold nothing
             keep = row < M ? (keep & (cl == 0 ? mw.x : mw.y)) : 0u;
             uint32_t bits = 0u;
+            if (__all_sync(0xffffffffu, keep == 0xffffffffu)) {  // interior chunk, nothing masked: no selects
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float t = ((keep >> j) & 1u) ? x[j] : 0.f;
-              bits |= (t > 0.f ? 1u : 0u) << j;
-              amax = fmaxf(amax, fabsf(t));
-              x[j] = t;
+              for (int j = 0; j < 32; ++j) {
+                bits |= (x[j] > 0.f ? 1u : 0u) << j;
+                amax = fmaxf(amax, fabsf(x[j]));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float t = ((keep >> j) & 1u) ? x[j] : 0.f;
+                bits |= (t > 0.f ? 1u : 0u) << j;
+                amax = fmaxf(amax, fabsf(t));
+                x[j] = t;
+              }
             }
             mo[cl] = bits;
           }
@@ -887,13 +899,7 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
             for (int g = 0; g < 32; g += 16) {  // 16 columns at a time (register pressure), two fp16 per word
               uint32_t p0[8], p1[8];
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                __half a0, a1, b0, b1;
-                split2h(x[g + j], oscale, a0, a1);
-                split2h(x[g + j + 1], oscale, b0, b1);
-                p0[j >> 1] = (uint32_t)__half_as_ushort(a0) | ((uint32_t)__half_as_ushort(b0) << 16);
-                p1[j >> 1] = (uint32_t)__half_as_ushort(a1) | ((uint32_t)__half_as_ushort(b1) << 16);
-              }
+              for (int j = 0; j < 16; j += 2) split2h_pair(x[g + j], x[g + j + 1], oscale, p0[j >> 1], p1[j >> 1]);
 #pragma unroll
               for (int h = 0; h < 2; ++h) {  // 64 B per row and plane, 16-byte chunk j4 at j4 ^ ((row >> 1) & 3): SWIZZLE_64B
                 const int j4 = (g >> 3) + h;

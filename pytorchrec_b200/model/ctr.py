@@ -179,7 +179,16 @@ class DCN(IModel):
         x = _dense_matrix(self.dense_columns, data)
         flat = v.reshape(v.shape[0], -1)
         x0 = torch.cat([flat, x], dim=1) if x is not None else flat
-        logit = self.out(torch.cat([self.cross(x0), self.mlp(x0)], dim=1)).squeeze(-1)
+        # Linear(concat(cross, deep)) = Linear_c(cross) + Linear_d(deep): the concatenation is never materialised, and
+        # the deep half closes the tower with K8's row-dot, whose backward hands the tower its gradient as planes
+        from .layer.interaction import row_dot
+        d = x0.shape[1]
+        w = self.out.weight                                  # [1, d + H]
+        c, h = self.cross(x0), self.mlp(x0)
+        deep = row_dot(h, w[0, d:], tower_handoff=True)      # h has no other consumer
+        if deep is None:
+            deep = torch.nn.functional.linear(h, w[:, d:]).squeeze(-1)
+        logit = torch.nn.functional.linear(c, w[:, :d]).squeeze(-1) + deep
         target = self.label_column.get_feature_data(data)
         return logit, (target.float() if target is not None else None)
 

@@ -149,7 +149,10 @@ def row_dot(h: Tensor, weight: Tensor, tower_handoff: bool = False):
             and h.data_ptr() % 16 == 0):
         return None
     call = getattr(h, "_ptrec_tower_out", None) if tower_handoff else None
-    return _RowDot.apply(h, weight.reshape(-1), call)
+    wv = weight.reshape(-1)
+    if wv.data_ptr() % 16 != 0 or wv.stride(0) != 1:   # e.g. a column slice of a wider Linear: the kernels read 16 bytes at a time
+        wv = wv.clone()
+    return _RowDot.apply(h, wv, call)
 
 
 class CrossNet(nn.Module):
