@@ -16,13 +16,13 @@ timeout 300 ncu --set full --clock-control none --import-source on \
     -o gpurun_out/r2_ncu_full_embedding -f python tools/run_update_once.py > gpurun_out/ncu_full_emb.log 2>&1
 echo "embedding capture rc=$?"
 ncu -i gpurun_out/r2_ncu_full_embedding.ncu-rep --page raw --csv > gpurun_out/r2_ncu_full_embedding_raw.csv 2>> gpurun_out/ncu_full_emb.log
-# K6 GEMM / split at the cfg2 tower shape
-timeout 100 python tools/run_tc_once.py > /dev/null 2>&1 || { echo "run_tc_once failed"; exit 1; }
-timeout 300 ncu --set full --clock-control none --import-source on \
-    -k regex:'gemm_split3_2sm_kernel|split_kernel' --launch-skip 8 -c 3 \
-    -o gpurun_out/r2_ncu_full_k6 -f python tools/run_tc_once.py > gpurun_out/ncu_full_k6.log 2>&1
+# K6 fused-tower GEMMs (forward: planes + bit mask out; input gradient: bit mask in, planes + column sums out; plain fp32)
+# at the cfg2 hidden-layer shape
+timeout 100 python tools/run_tc_fused_once.py > /dev/null 2>&1 || { echo "run_tc_fused_once failed"; exit 1; }
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'gemm_split3_2sm_kernel' --launch-skip 3 -c 3 \
+    -o gpurun_out/r2_ncu_full_k6_fused -f python tools/run_tc_fused_once.py > gpurun_out/ncu_full_k6.log 2>&1
 echo "k6 capture rc=$?"
-ncu -i gpurun_out/r2_ncu_full_k6.ncu-rep --page raw --csv > gpurun_out/r2_ncu_full_k6_raw.csv 2>> gpurun_out/ncu_full_k6.log
+ncu -i gpurun_out/r2_ncu_full_k6_fused.ncu-rep --page raw --csv > gpurun_out/r2_ncu_full_k6_fused_raw.csv 2>> gpurun_out/ncu_full_k6.log
 # K4 on tensor cores at the cfg4 shape
 timeout 100 python tools/run_din_once.py > /dev/null 2>&1 || { echo "run_din_once failed"; exit 1; }
 timeout 300 ncu --set full --clock-control none --import-source on \

@@ -9,9 +9,10 @@ for r in csv.DictReader(lines):
         rows.append((r["Kernel Name"], float(r["Metric Value"].replace(",", "")), r["Metric Unit"]))
 unit = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}
 starts = [i for i, r in enumerate(rows) if "gather_onehot_kernel<4" in r[0] or "gather_onehot_kernel<(int)4" in r[0]]
-if len(starts) < 2:
+pairs = [(a, b) for a, b in zip(starts, starts[1:]) if b - a >= 20]  # a train step, not the kernel-timing loops after it
+if not pairs:
     sys.exit("fewer than two steps in the list")
-a, b = starts[-2], starts[-1]
+a, b = min(pairs, key=lambda ab: ab[1] - ab[0])  # (the last one also spans the set-up of the kernel timings)
 step = rows[a:b]
 tot = sum(t * unit[u] for _, t, u in step)
 agg = collections.OrderedDict()
