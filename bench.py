@@ -59,8 +59,12 @@ def parse():
     ap.add_argument("--no-cfg5", action="store_true", help="skip the cfg5 sub-record")
     ap.add_argument("--no-models", action="store_true", help="skip the cfg3 / cfg4 model records (N = 1)")
     ap.add_argument("--sub-steps", type=int, default=20, help="timed steps of the cfg5 / cfg3 / cfg4 sub-records")
-    ap.add_argument("--pipelined-loss", action="store_true",
-                    help="e2e: read step k's loss from a pinned buffer after step k+1 is enqueued (experimental)")
+    ap.add_argument("--per-key-h2d", action="store_true",
+                    help="e2e: host batches as separately pinned tensors (one H2D copy per key) instead of one packed pinned buffer")
+    ap.add_argument("--sync-loss", action="store_true",
+                    help="e2e: report the variant that calls loss.item() (a host synchronisation) after every step; by "
+                         "default step k's loss is copied to a pinned word every step and read by the host once step "
+                         "k+1 is enqueued (both variants are measured and printed)")
     return ap.parse_args()
 
 
@@ -238,19 +242,24 @@ def measure_deepfm(a, dev, rank, world, lib, steps, warmup, with_e2e, sampler=No
                          dist=a.id_dist, pin=True) for i in range(n_pool)]
     resident = [model.stage(b) for b in host]  # HBM-resident batches, each in one packed buffer
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    # end-to-end batches: assembled by the "loader" in ONE pinned buffer each (IModel.pack_host), so that a step's input
+    # moves with a single H2D copy instead of 40 (one per key: ~0.25 ms of host time per step, more than the GPU's idle
+    # margin); a plain dict of separately pinned tensors (--per-key-h2d) takes the 40-copy path
+    if not a.per_key_h2d:
+        host = [model.pack_host(b) for b in host]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(batches, n, read_loss):
+    def timed(batches, n, read_loss, pipelined=False):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
         if read_loss:  # end to end: the data-loader pattern of IModel.fit (prefetch batch k+1 while step k runs)
             model.prefetch(batches[0])
-        if read_loss and a.pipelined_loss:
+        if read_loss and pipelined:
             # every step's loss still reaches the host inside the timed region, but through a pinned buffer read AFTER
             # the next step has been enqueued, so the device does not idle while the host issues the next launch
             pin = torch.empty(2, dtype=torch.float32).pin_memory()
@@ -295,7 +304,7 @@ def measure_deepfm(a, dev, rank, world, lib, steps, warmup, with_e2e, sampler=No
     l0 = launch_total()
     ms = timed(resident, steps, read_loss=False)
     launches = launch_total() - l0
-    ms_e2e = None
+    ms_e2e = ms_e2e_sync = None
     if with_e2e:
         model.prefetch(host[0])
         for i in range(max(warmup, 3)):  # warm the end-to-end path too (pinned staging, copy stream, prefetch buffers)
@@ -303,12 +312,18 @@ def measure_deepfm(a, dev, rank, world, lib, steps, warmup, with_e2e, sampler=No
             model.prefetch(host[(i + 1) % n_pool])
             logs["loss"].item()
         model.train_step(host[max(warmup, 3) % n_pool])
-        ms_e2e = timed(host, steps, read_loss=True)
+        # (a) every step: H2D of the batch (prefetched on the copy stream), train_step, D2H of the loss into a pinned
+        #     word that the host reads once the NEXT step is enqueued (asynchronous logging: the device never waits for
+        #     the host); (b) the same with `loss.item()` — a full host synchronisation — after every step
+        ms_e2e = timed(host, steps, read_loss=True, pipelined=not a.sync_loss)
+        model.prefetch(host[0])
+        ms_e2e_sync = timed(host, steps, read_loss=True, pipelined=False)
     for m in model.modules():  # overflowed exchange lists / out-of-range ids invalidate the run: raise, don't report
         chk = getattr(m, "check_errors", None) or getattr(m, "check_index_errors", None)
         if chk is not None and m is not model:
             chk()
-    return dict(model=model, resident=resident, host=host, ms=ms, ms_e2e=ms_e2e, launches=int(launches), h2d=h2d)
+    return dict(model=model, resident=resident, host=host, ms=ms, ms_e2e=ms_e2e, ms_e2e_sync=ms_e2e_sync,
+                launches=int(launches), h2d=h2d)
 
 
 def _release(res, world):
@@ -351,7 +366,16 @@ def run_b200(a):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(a, world),
             "e2e": {"value": total / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": res["h2d"],
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps,
+                    "host_batches": ("dict of separately pinned tensors: one H2D copy per key" if a.per_key_h2d else
+                                     "one pinned packed buffer per batch (IModel.pack_host): one H2D copy per step, issued "
+                                     "on the copy stream while the previous step runs"),
+                    "loss_read": ("loss.item() after every step (host synchronisation per step)" if a.sync_loss else
+                                  "every step's loss is copied to a pinned host word inside the step's stream and read by "
+                                  "the host once the next step is enqueued (asynchronous logging; the last one "
+                                  "synchronously, inside the timed region)"),
+                    "sync_each_step": {"value": total / (res["ms_e2e_sync"] / 1e3), "ms_per_step": res["ms_e2e_sync"] / a.steps,
+                                       "loss_read": "loss.item() after every step"}},
             "gpu_launches": res["launches"], "clocks": clocks}
     if rank == 0:
         roof, line["kernels"], roof2, line["roofline_hbm_all"] = kernel_roofline(a, res["model"], res["resident"], dev)

@@ -218,6 +218,8 @@ def _owner_updates(mod, C, srt, recv_g, dev) -> None:
         prepared.append((tables, s1, s2, args))
     if use_aux:
         aux.wait_stream(main)   # gradient rows landed (barrier), sort joined
+        for t in (srt.sorted_keys, srt.perm, srt.seg_start, srt.seg_meta, srt.n_seg):
+            t.record_stream(aux)   # allocated on another stream: not to be recycled before the aux update has read them
     for k, (tables, s1, s2, args) in enumerate(prepared):
         if use_aux and k > 0:
             with torch.cuda.stream(aux):

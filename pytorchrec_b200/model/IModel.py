@@ -81,6 +81,11 @@ def _drop_lookup_cache(module, args):
         args[0].pop(_LOOKUP_CACHE_KEY, None)
 
 
+import weakref
+
+_LIVE_MODELS: "weakref.WeakSet" = weakref.WeakSet()   # for the at-exit drain of pytorchrec_b200/__init__.py
+
+
 class _GraphedTrainStep:
     """Whole-step CUDA graph (forward, loss, zero_grad, backward with the fused sparse update, dense
     optimizer step) keyed by the batch signature.  The first ``warmup`` steps of a signature run eagerly —
@@ -167,6 +172,7 @@ class IModel(Module, ABC):
     def __init__(self, random_seed: int, **kwargs):  # noqa
         set_torch_seed(random_seed)
         super().__init__()
+        _LIVE_MODELS.add(self)
         self.stop_training = False
         self.best_state_dict = None
         self.history: Optional[History] = None
@@ -303,6 +309,20 @@ class IModel(Module, ABC):
             packer = self._packers[sig] = BatchPacker(data, dev)
         return packer.stage(data)
 
+    def pack_host(self, data: Dict) -> Dict:
+        """N1: ``data`` (host tensors) re-assembled in ONE pinned buffer laid out like the device-side packed batch —
+        what a loader worker / collate function hands over when it builds the batch in page-locked memory.  Still a
+        ``Dict[str, Tensor]``; ``prefetch`` / ``train_step`` then move it with a single DMA instead of one per key."""
+        dev = self.compiled_device
+        if dev is None or dev.type != "cuda":
+            return data
+        from ..utils.ingest import BatchPacker
+        sig = tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in data.items()))
+        packer = self._packers.get(sig)
+        if packer is None:
+            packer = self._packers[sig] = BatchPacker(data, dev)
+        return packer.pack_host(data)
+
     def _take_prefetched(self, data: Dict):
         """(device views, packer, release) of a batch handed to ``prefetch`` earlier, or None.  The current stream is
         made to wait for the transfer; ``release()`` must be called once the step's reads of the views are enqueued."""
@@ -356,6 +376,9 @@ class IModel(Module, ABC):
         loss = self._apply_loss(prediction, target)
         self.compiled_optimizers.zero_grad()
         loss.backward()
+        if loss.is_cuda:
+            from .layer.embedding import join_aux_streams
+            join_aux_streams(loss.device)   # lookups placed on the aux stream update their tables there
         self._before_optimizer_step()
         self.compiled_optimizers.step(closure=None)
         return loss

@@ -81,6 +81,14 @@ class EmbeddingGroup:
         if srt is not None and shared.get("sort_event") is not None:
             # join the early sort; the event stays: a second consumer may run on another stream (aux_stream below)
             torch.cuda.current_stream(ids.device).wait_event(shared["sort_event"])
+        if grad_out.is_cuda:
+            # this backward may run on the aux stream (autograd runs a node on its forward's stream): everything it
+            # reads that was allocated on another stream must not be recycled before its kernels have finished
+            cur = torch.cuda.current_stream(grad_out.device)
+            for t in (grad_out, ids, lens, bag_scale) + ((srt.sorted_keys, srt.perm, srt.seg_start, srt.seg_meta, srt.n_seg)
+                                                         if srt is not None else ()):
+                if t is not None:
+                    t.record_stream(cur)
         if srt is None:
             srt = ops.sort_dedup(tables, layout, ids, lens, batch)
             if shared is not None:
@@ -112,6 +120,7 @@ class EmbeddingGroup:
 
 _SIDE_STREAMS: Dict[torch.device, "torch.cuda.Stream"] = {}
 _AUX_STREAMS: Dict[torch.device, "torch.cuda.Stream"] = {}
+_AUX_USED: Dict[torch.device, bool] = {}   # the aux stream was forked since the last join_aux_streams
 
 
 class aux_stream:
@@ -133,6 +142,7 @@ class aux_stream:
             if self.side is None:
                 self.side = _AUX_STREAMS[self.device] = torch.cuda.Stream(self.device)
             self.side.wait_stream(self.main)
+            _AUX_USED[torch.device(self.device)] = True
             self.ctx = torch.cuda.stream(self.side)
             self.ctx.__enter__()
         return self
@@ -148,6 +158,16 @@ class aux_stream:
             for t in tensors:
                 if t is not None:
                     t.record_stream(self.main)
+
+
+def join_aux_streams(device) -> None:
+    """Make the current stream wait for whatever the aux stream still runs (a backward that autograd placed there):
+    called by ``IModel`` between ``backward()`` and ``optimizer.step()``."""
+    if device is None or not _AUX_USED.pop(torch.device(device), False):
+        return   # nothing forked in this step (waiting on a stream outside a running graph capture would invalidate it)
+    side = _AUX_STREAMS.get(torch.device(device))
+    if side is not None:
+        torch.cuda.current_stream(device).wait_stream(side)
 
 
 def _early_sort_enabled() -> bool:

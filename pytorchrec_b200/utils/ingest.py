@@ -22,6 +22,14 @@ class PackedBatch(dict):
     signature: tuple = ()
 
 
+class PackedHostBatch(dict):
+    """A HOST batch whose tensors are typed views of ONE pinned buffer (``buffer``) in a ``BatchPacker``'s layout —
+    what a collate function / loader worker produces when it assembles the batch directly in page-locked memory
+    (``IModel.pack_host``).  Still the reference's ``Dict[str, Tensor]``; moves to the device with a single DMA."""
+    buffer: Tensor = None
+    signature: tuple = ()
+
+
 class BatchPacker:
     def __init__(self, example: Dict[str, Tensor], device: torch.device, n_staging: int = 2):
         self.device = device
@@ -56,9 +64,22 @@ class BatchPacker:
         out.buffer, out.signature = buf, self.signature()
         return out
 
+    def pack_host(self, batch: Dict[str, Tensor]) -> PackedHostBatch:
+        """``batch`` assembled in ONE pinned buffer of this packer's layout (host memcpy per key, done once — by the
+        loader, outside the training loop); ``load`` then moves it with a single H2D copy."""
+        buf = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
+        out = PackedHostBatch({k: self._view(buf, dt, shp, o, n) for k, dt, shp, o, n in self.layout})
+        for k in out:
+            out[k].copy_(batch[k])
+        out.buffer, out.signature = buf, self.signature()
+        return out
+
     def load(self, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
         """Pack ``batch`` (host tensors of the example's shapes / dtypes) and enqueue the single H2D copy on the
         current stream.  Returns the dict of device views (same objects every call)."""
+        if isinstance(batch, PackedHostBatch) and batch.signature == self.signature():
+            self.dev.copy_(batch.buffer, non_blocking=True)   # already packed in page-locked memory: one DMA
+            return dict(self.views)
         if all(batch[k].is_pinned() for k, _, _, _, _ in self.layout):
             # already page-locked (e.g. a pinning DataLoader): DMA straight into the device views, no host re-pack
             for k, _, _, _, _ in self.layout:

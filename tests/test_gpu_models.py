@@ -660,8 +660,10 @@ def _lib_launches():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("graph", [False, True])
-def test_prefetched_batches_train_exactly_like_direct_ones(graph):
-    """N1: prefetch(batch k+1) during step k (copy stream, double-buffered) gives bit-identical training."""
+@pytest.mark.parametrize("packed_host", [False, True])
+def test_prefetched_batches_train_exactly_like_direct_ones(graph, packed_host):
+    """N1: prefetch(batch k+1) during step k (copy stream, double-buffered) gives bit-identical training — from plain
+    host dicts and from batches the loader assembled in one pinned buffer (``IModel.pack_host``: one DMA per step)."""
     scols, dcols, lab, rows = _ctr_setup(F=5, nd=2)
     models = []
     for _ in range(2):
@@ -672,6 +674,9 @@ def test_prefetched_batches_train_exactly_like_direct_ones(graph):
         models.append(m)
     direct, pre = models
     batches = [_ctr_batch(rows, len(dcols), 128, seed=40 + s) for s in range(7)]
+    if packed_host:
+        batches = [pre.pack_host(b) for b in batches]
+        assert batches[0].buffer.is_pinned() and all(not v.is_cuda for v in batches[0].values())
     pre.prefetch(batches[0])
     for i, b in enumerate(batches):
         la = direct.train_step({k: v.clone() for k, v in b.items()})["loss"]
