@@ -189,47 +189,55 @@ class _FusedSparseOptimizer(Optimizer):
                 states.append(st)
             staged.append((gi, dg, ps, states))
         launches = []
+        # Parameters are bucketed by what the kernel needs to be told once per launch: the hyper-parameters of their
+        # group and their step counter (torch.optim keeps one per parameter; a parameter that skipped a step lags
+        # behind).  Groups with identical hyper-parameters — the usual case: the reference's get_parameters() returns
+        # several groups that differ in nothing the dense optimizer uses — share ONE launch.
+        merged: Dict[tuple, list] = {}
         for gi, dg, ps, states in staged:
-            # torch.optim keeps one step counter per parameter (a parameter that skipped a step lags behind):
-            # one launch per distinct counter value — a single launch in the usual case
-            buckets: Dict[int, list] = {}
+            betas = dg.get("betas", (0.0, 0.0))
+            hyper = (float(dg["lr"]), float(dg.get("eps", 0.0)), float(betas[0]), float(betas[1]),
+                     float(dg.get("weight_decay", 0.0)), float(dg.get("lr_decay", 0.0)))
             for i, st in enumerate(states):
                 step = 1
                 if kind != _lib.OPT_SGD:
                     st["step"] += 1
                     step = int(st["step"].item())
-                buckets.setdefault(step, []).append(i)
-            for bi, (step, idx) in enumerate(sorted(buckets.items())):
-                bps = [ps[i] for i in idx]
-                if kind == _lib.OPT_ADAGRAD:
-                    s1, s2 = [states[i]["sum"] for i in idx], [None] * len(idx)
-                elif kind == _lib.OPT_LAZY_ADAM:
-                    s1, s2 = [states[i]["exp_avg"] for i in idx], [states[i]["exp_avg_sq"] for i in idx]
-                else:
-                    s1 = s2 = [None] * len(idx)
-                key = tuple((p.data_ptr(), p.grad.data_ptr(), a.data_ptr() if a is not None else 0,
-                             b.data_ptr() if b is not None else 0) for p, a, b in zip(bps, s1, s2))
-                cached = self._dense_plan.get((gi, bi))
-                if cached is None or cached[0] != key:
-                    import numpy as np
-                    rec = np.zeros((len(bps), 5), dtype=np.int64)
-                    starts = np.zeros(len(bps) + 1, dtype=np.int32)
-                    for i, (p, k4) in enumerate(zip(bps, key)):
-                        rec[i, :4] = k4
-                        rec[i, 4] = p.numel()
-                        starts[i + 1] = starts[i] + (p.numel() + chunk - 1) // chunk
-                    dev = bps[0].device
-                    # pinned staging: this may run inside a CUDA-graph capture (the captured copy node re-reads the
-                    # pinned buffers on replay, so they are kept alive with the plan)
-                    h_rec, h_starts = torch.from_numpy(rec).pin_memory(), torch.from_numpy(starts).pin_memory()
-                    cached = (key, h_rec.to(dev, non_blocking=True), h_starts.to(dev, non_blocking=True),
-                              int(starts[-1]), h_rec, h_starts)
-                    self._dense_plan[(gi, bi)] = cached
-                betas = dg.get("betas", (0.0, 0.0))
-                args = OptimArgs(kind=kind, step=step, lr=dg["lr"], eps=dg.get("eps", 0.0), beta1=betas[0],
-                                 beta2=betas[1], weight_decay=dg.get("weight_decay", 0.0),
-                                 lr_decay=dg.get("lr_decay", 0.0))
-                launches.append(((gi, bi), cached, len(bps), args, bps[0].device))
+                merged.setdefault((hyper, step), []).append((ps[i], st))
+        for bi, ((hyper, step), items) in enumerate(sorted(merged.items(), key=lambda kv: kv[0])):
+            gi = "merged"
+            dg = {"lr": hyper[0], "eps": hyper[1], "betas": (hyper[2], hyper[3]), "weight_decay": hyper[4],
+                  "lr_decay": hyper[5]}
+            bps = [p for p, _ in items]
+            if kind == _lib.OPT_ADAGRAD:
+                s1, s2 = [st["sum"] for _, st in items], [None] * len(items)
+            elif kind == _lib.OPT_LAZY_ADAM:
+                s1, s2 = [st["exp_avg"] for _, st in items], [st["exp_avg_sq"] for _, st in items]
+            else:
+                s1 = s2 = [None] * len(items)
+            key = tuple((p.data_ptr(), p.grad.data_ptr(), a.data_ptr() if a is not None else 0,
+                         b.data_ptr() if b is not None else 0) for p, a, b in zip(bps, s1, s2))
+            cached = self._dense_plan.get((gi, bi))
+            if cached is None or cached[0] != key:
+                import numpy as np
+                rec = np.zeros((len(bps), 5), dtype=np.int64)
+                starts = np.zeros(len(bps) + 1, dtype=np.int32)
+                for i, (p, k4) in enumerate(zip(bps, key)):
+                    rec[i, :4] = k4
+                    rec[i, 4] = p.numel()
+                    starts[i + 1] = starts[i] + (p.numel() + chunk - 1) // chunk
+                dev = bps[0].device
+                # pinned staging: this may run inside a CUDA-graph capture (the captured copy node re-reads the
+                # pinned buffers on replay, so they are kept alive with the plan)
+                h_rec, h_starts = torch.from_numpy(rec).pin_memory(), torch.from_numpy(starts).pin_memory()
+                cached = (key, h_rec.to(dev, non_blocking=True), h_starts.to(dev, non_blocking=True),
+                          int(starts[-1]), h_rec, h_starts)
+                self._dense_plan[(gi, bi)] = cached
+            betas = dg.get("betas", (0.0, 0.0))
+            args = OptimArgs(kind=kind, step=step, lr=dg["lr"], eps=dg.get("eps", 0.0), beta1=betas[0],
+                             beta2=betas[1], weight_decay=dg.get("weight_decay", 0.0),
+                             lr_decay=dg.get("lr_decay", 0.0))
+            launches.append(((gi, bi), cached, len(bps), args, bps[0].device))
         # phase 2: launches.  With a peer reducer attached (row-wise sharded models on NVLink peer memory) the
         # data-parallel mean of the gradients is fused in: pack every group's gradients into this rank's symmetric
         # stage, ONE barrier, then each K7 launch sums the ranks' stages itself (csrc/peer_sync.cu).
