@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 22
+#define PTREC_ABI_VERSION 23
 
 /* error codes */
 #define PTREC_OK 0
@@ -300,6 +300,11 @@ int ptrec_din_attn_pool_bwd(const float* q, int64_t q_stride, const float* keys,
  *          g_u_prev (may be NULL) receives g_x (.) x0, i.e. the g_u of the layer below
  *   wgrad  grad_w [d_out, d_in] fp32 = g_u^T x_l   (workspace: ptrec_dcn_cross_wgrad_workspace_bytes)
  */
+/* Round 2: the three entry points run on the CTA-pair GEMM kernel of K6 with one bf16 operand plane (256 x 256 pair tiles,
+ * TMA-store epilogue with the cross-layer arithmetic fused, MN-major operands for the weight gradient); the 128 x 128
+ * single-CTA kernel of round 1 stays selectable: */
+void ptrec_set_dcn_2sm(int32_t enabled);
+int32_t ptrec_dcn_2sm_enabled(void);
 int ptrec_dcn_cross_fwd(const void* x_l, const void* x0, const void* weight, const float* bias, int64_t B,
                         int32_t d, int64_t ld, void* out, void* u_out, void* stream);
 int ptrec_dcn_cross_dgrad(const void* g_u, const void* weight_t, const void* g_out, const void* x0, int64_t B,

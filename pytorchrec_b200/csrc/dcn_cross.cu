@@ -19,6 +19,7 @@
 //     (cp.async.bulk.tensor.2d.global.shared), so every global access of the epilogue is a full coalesced tile.
 // Every mbarrier wait is bounded (trap instead of hang).
 #include "tcgen05.cuh"
+#include "gemm2sm.cuh"
 
 namespace ptrec {
 
@@ -373,6 +374,14 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, i
 
 using namespace ptrec;
 
+// Round 2: the cross GEMMs run on the CTA-pair kernel of tc_linear.cu (one bf16 operand plane, 256 x 256 pair tiles,
+// 16 epilogue warps, TMA stores, MN-major operands for the weight gradient: no transposed copies).  The 128 x 128
+// single-CTA kernel of this file stays selectable (identical results up to summation order; the tests run both).
+static int g_dcn_2sm = 1;
+extern "C" void ptrec_set_dcn_2sm(int32_t enabled) { g_dcn_2sm = enabled ? 1 : 0; }
+extern "C" int32_t ptrec_dcn_2sm_enabled(void) { return g_dcn_2sm; }
+extern "C" int32_t ptrec_tc_gemm_split3_default_splits(int64_t M, int64_t N, int64_t K);
+
 static int check_cross(const void* a, const void* b, const void* c, int64_t B, int32_t d, int64_t ld) {
   PTREC_CHECK_ARG(a && b && c, PTREC_EINVAL, "dcn_cross: null pointer");
   PTREC_CHECK_ARG(B > 0 && B < (int64_t)0x7fffffff && d >= 8 && d % 8 == 0 && ld >= d && ld % 8 == 0, PTREC_EINVAL,
@@ -386,6 +395,12 @@ extern "C" int ptrec_dcn_cross_fwd(const void* x_l, const void* x0, const void* 
   int rc = check_cross(x_l, x0, weight, B, d, ld);
   if (rc != PTREC_OK) return rc;
   PTREC_CHECK_ARG(out && aligned16(out) && aligned16(x0) && (!u_out || aligned16(u_out)), PTREC_EALIGN, "dcn_cross_fwd: alignment");
+  if (g_dcn_2sm) {
+    Bf16Gemm g{};
+    g.mn_major = false; g.A = x_l; g.lda = ld; g.B = weight; g.ldb = d; g.M = B; g.N = d; g.K = d; g.bias = bias;
+    g.dcn_mode = 1; g.p0 = x0; g.p1 = x_l; g.pld = ld; g.o0 = out; g.o1 = u_out; g.splits = 1;
+    return gemm_bf16_2sm(g, (cudaStream_t)stream);
+  }
   EpiArgs ep{};
   ep.mode = EPI_CROSS_FWD;
   ep.ld = ld;
@@ -403,6 +418,12 @@ extern "C" int ptrec_dcn_cross_dgrad(const void* g_u, const void* weight_t, cons
   if (rc != PTREC_OK) return rc;
   PTREC_CHECK_ARG(x0 && g_x && aligned16(g_x) && aligned16(x0) && aligned16(g_out) && (!g_u_prev || aligned16(g_u_prev)),
                   PTREC_EALIGN, "dcn_cross_dgrad: alignment");
+  if (g_dcn_2sm) {
+    Bf16Gemm g{};
+    g.mn_major = false; g.A = g_u; g.lda = ld; g.B = weight_t; g.ldb = d; g.M = B; g.N = d; g.K = d; g.bias = nullptr;
+    g.dcn_mode = 2; g.p0 = g_out; g.p1 = x0; g.pld = ld; g.o0 = g_x; g.o1 = g_u_prev; g.splits = 1;
+    return gemm_bf16_2sm(g, (cudaStream_t)stream);
+  }
   EpiArgs ep{};
   ep.mode = EPI_CROSS_DGRAD;
   ep.ld = ld;
@@ -435,6 +456,15 @@ extern "C" int ptrec_dcn_cross_wgrad(const void* g_u, const void* x_l, int64_t B
                   "dcn_cross_wgrad: workspace too small");
   PTREC_CHECK_ARG(aligned16(grad_w) && d % 4 == 0, PTREC_EALIGN, "dcn_cross_wgrad: grad_w alignment");
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_dcn_2sm) {
+    // gW[i, j] = sum_b g_u[b, i] x_l[b, j]: both stored matrices are read MN-major (the batch is their row index)
+    Bf16Gemm g{};
+    g.mn_major = true; g.A = g_u; g.lda = ld; g.B = x_l; g.ldb = ld; g.M = d; g.N = d; g.K = B;
+    g.dcn_mode = 0; g.out = grad_w; g.ldo = d;
+    g.splits = std::min<int>(16, std::max<int>(1, ptrec_tc_gemm_split3_default_splits(d, d, B)));
+    g.workspace = workspace; g.workspace_bytes = workspace_bytes;
+    return gemm_bf16_2sm(g, st);
+  }
   const int64_t ldt = (int64_t)align_up((size_t)B, 8);
   __nv_bfloat16* gt = reinterpret_cast<__nv_bfloat16*>(workspace);
   __nv_bfloat16* xt = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(workspace) +

@@ -25,6 +25,7 @@
 //           epilogue); correct, measured slower than the 256-wide tiles, selectable with ptrec_tc_set_bn.
 #include "tcgen05.cuh"
 #include "split3.cuh"
+#include "gemm2sm.cuh"
 
 namespace ptrec {
 
@@ -288,7 +289,7 @@ template <int NP> struct LinCfg {
   static constexpr int kStages = NP == 3 ? 3 : 4;
   static constexpr uint32_t kStageBytes = NP * (kLTileA + kLTileB);
   // instruction descriptor: D = fp32 (bit 4); A / B format bf16 (1 at bits 7 / 10) or fp16 (0)
-  static constexpr uint32_t kIdescFmt = NP == 3 ? ((1u << 4) | (1u << 7) | (1u << 10)) : (1u << 4);
+  static constexpr uint32_t kIdescFmt = NP == 2 ? (1u << 4) : ((1u << 4) | (1u << 7) | (1u << 10));
 };
 constexpr uint32_t kLTmemCols = 512;                   // main [0, 256) + correction [256, 512)
 constexpr size_t kLSmem = (size_t)3 * 72 * 1024 + 1024 /*align*/ + 2048 /*barriers + bias slice*/;
@@ -316,6 +317,15 @@ struct LinEpi {
   uint32_t* mask_out;         // same layout: bit set where the result (after bias / ReLU) is > 0
   int64_t mask_ld;            // words per row, a multiple of 4 >= ceil(N / 32)
   float* colsum_part;         // [ceil(M / 32)][N] column sums of the masked result per 32-row block (bias gradient)
+  // CTA-pair kernel with ONE operand plane (NP = 1: a plain bf16 GEMM) — the DCN-v2 cross layers (K5, dcn_cross.cu):
+  //   dcn_mode 1 (forward):        u = acc + bias;  o0 = dp0 * u + dp1 (dp0 = x0, dp1 = x_l);  o1 = u
+  //   dcn_mode 2 (input gradient): g_x = acc + dp0 (dp0 = g_out);  o0 = g_x;  o1 = g_x * dp1 (dp1 = x0)
+  // dp0 / dp1 are bf16 [M][dld]; o0 / o1 leave through the tensor maps p / q (bf16 [M][dld], o1 optional)
+  int dcn_mode;
+  const __nv_bfloat16* dp0;
+  const __nv_bfloat16* dp1;
+  int64_t dld;
+  int dcn_o1;
 };
 
 // acc = main + correction.  bf16 x 3: plain sum.  fp16 x 2: the correction accumulator holds 2^11 (A0 B1 + A1 B0) of
@@ -331,6 +341,8 @@ struct LinMaps {
   // CTA-pair kernel: where the epilogue's TMA stores go.  c: fp32 result (col, row, split-K slab), boxes of 32 x 32,
   // 128-byte swizzle; p: fp16 planes of the result (col, row, plane), boxes of 32 x 32 x 1, 64-byte swizzle
   CUtensorMap c, p;
+  CUtensorMap q;     // NP = 1 (DCN epilogue): second bf16 output
+  CUtensorMap r0, r1;  // NP = 1 (DCN epilogue): the two bf16 epilogue operands dp0 / dp1, boxes of 32 x 32, 64-byte swizzle
 };
 
 // K-major, 64B swizzle (rows of 32 bf16): 8-row atoms of 512 B; LBO unused (1), SBO = 512 B
@@ -648,18 +660,27 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
   // a stage = NP planes of A (128 rows) and of this CTA's B half: fp16 x 2, BK 32: 32 KB -> 5 stages; bf16 x 3: 48 KB -> 3
   constexpr uint32_t k2Tile = 128 * BK * 2;     // any plane tile: 128 rows (or 2 boxes of 64 mn) x BK 16-bit elements
   constexpr uint32_t k2StageBytes = 2 * NP * k2Tile; // A planes, then B planes (B = this CTA's half)
-  constexpr int k2Stages = (int)(k2StageBudget / k2StageBytes);
-  static_assert(k2Stages >= 1, "a stage exceeds the shared-memory budget");
+  // NP = 1 (K5): one plane leaves TMEM columns [256, 512) free, so the accumulator is double-buffered (the MMAs of tile
+  // i + 1 run under the epilogue of tile i), and every epilogue warp owns 8 KB: the four 32 x 32 bf16 boxes of its two
+  // epilogue operands (both 32-column chunks), fetched by TMA while the tile's MMAs run and overwritten in place by the
+  // two results, which leave by TMA stores — no per-thread global access in the epilogue.
+  constexpr int kAcc = NP == 1 ? 2 : 1;
+  constexpr uint32_t kWarpStg = NP == 1 ? 8192u : 4096u;
+  constexpr uint32_t kStaging = k2EpiWarps * kWarpStg;
+  static_assert(kStaging >= k2Staging, "staging");
+  constexpr int k2Stages = (int)((k2StageBudget + k2Staging - kStaging) / k2StageBytes);
+  static_assert(k2Stages >= 1 && 2 * k2Stages + 2 * kAcc + 1 <= 32, "a stage exceeds the shared-memory budget / barrier block");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* staging = smem + (size_t)k2Stages * k2StageBytes;  // 1024-byte aligned: the stages are multiples of 1 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + k2Staging);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStaging);
   uint64_t* full = bars;                    // [k2Stages]  (the leader's are the ones in use)
   uint64_t* empty = bars + k2Stages;        // [k2Stages]
-  uint64_t* acc_full = bars + 2 * k2Stages; // [1]
-  uint64_t* acc_empty = acc_full + 1;       // [1]  (leader's)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
-  float* s_bias = reinterpret_cast<float*>(bars + 16);  // [256]
+  uint64_t* acc_full = bars + 2 * k2Stages; // [kAcc]
+  uint64_t* acc_empty = acc_full + kAcc;    // [kAcc]  (leader's)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAcc);
+  float* s_bias = reinterpret_cast<float*>(bars + 32);  // [256], 256 bytes into the barrier block (up to 15 stages of barriers before it)
+  uint64_t* in_bar = bars + 32 + 128;  // [k2EpiWarps] (NP = 1): a warp's epilogue operands have landed; ends 1408 B into the block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -670,6 +691,19 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
   const int total_kb = (K + BK - 1) / BK;
   const int kb_per_split = (total_kb + splits - 1) / splits;
   const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  // NP = 1 (K5): column tiles of equal width (a multiple of 32: the epilogue's chunk) instead of 256, 256, ... remainder,
+  // and the column tile is the FAST index of the tile order: the tiles that run at the same time share row blocks of A,
+  // which is then read from HBM once (with rows fastest, the d = 848 cross layer re-read its 55 MB input from HBM for
+  // every one of its 4 column tiles: the kernel ran at the HBM rate, 20k cycles per tile for 7k cycles of MMAs)
+  int bn = 256;
+  if (NP == 1) {
+    bn = (((N + tiles_n - 1) / tiles_n) + 31) & ~31;
+    if ((tiles_n - 1) * bn >= N) bn = 256;
+  }
+#define K2_TILE_MN(mn, m_idx, n_idx)                       \
+  int m_idx, n_idx;                                        \
+  if (NP == 1) { n_idx = (mn) % tiles_n; m_idx = (mn) / tiles_n; } \
+  else { m_idx = (mn) % tiles_m; n_idx = (mn) / tiles_m; }
   K6_STAMP(0);
 
   if (threadIdx.x == 0) {
@@ -677,8 +711,12 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 2 * k2EpiWarps);  // the epilogue warps of both CTAs
+    for (int b = 0; b < kAcc; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 2 * k2EpiWarps);  // the epilogue warps of both CTAs
+    }
+    if (NP == 1)
+      for (int w = 0; w < k2EpiWarps; ++w) mbar_init(&in_bar[w], 1);
     fence_mbar_init();
   }
   cluster_sync_all();  // the peer's barriers exist before anything arrives on them
@@ -700,8 +738,9 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
       int kbg = 0;
       for (int tile = cid; tile < n_tiles; tile += n_clusters) {
         const int mn = tile % mn_tiles, split = tile / mn_tiles;
-        const int m0 = (mn % tiles_m) * 256 + rank * 128, n0 = (mn / tiles_m) * 256;
-        const int n_eff = min(256, (N - n0 + 15) & ~15);
+        K2_TILE_MN(mn, m_idx, n_idx)
+        const int m0 = m_idx * 256 + rank * 128, n0 = n_idx * bn;
+        const int n_eff = min(bn, (N - n0 + 15) & ~15);
         const int nb0 = n0 + rank * (n_eff >> 1);  // this CTA's half of the B tile
         const int kb0 = split * kb_per_split, num_kb = max(0, min(total_kb - kb0, kb_per_split));
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
@@ -731,13 +770,16 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
     if (lane == 0 && rank == 0) {
       int kbg = 0, it = 0;
       for (int tile = cid; tile < n_tiles; tile += n_clusters, ++it) {
-        mbar_wait(acc_empty, (it & 1) ^ 1);
+        const int ab = it % kAcc;
+        mbar_wait(&acc_empty[ab], ((it / kAcc) & 1) ^ 1);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base;
-        const uint32_t tmem_c = tmem_base + 256u;
+        const uint32_t tmem_d = tmem_base + (uint32_t)ab * 256u;
+        const uint32_t tmem_c = tmem_base + 256u;  // NP > 1 only
         const int mn = tile % mn_tiles;
-        const int n0 = (mn / tiles_m) * 256;
-        const int n_eff = min(256, (N - n0 + 15) & ~15);
+        K2_TILE_MN(mn, m_idx, n_idx)
+        (void)m_idx;
+        const int n0 = n_idx * bn;
+        const int n_eff = min(bn, (N - n0 + 15) & ~15);
         const uint32_t idesc = LinCfg<NP>::kIdescFmt | ((uint32_t)(n_eff >> 3) << 17) |
                                ((uint32_t)(256 >> 4) << 24) | (MN_MAJOR ? ((1u << 15) | (1u << 16)) : 0u);
         const int kb0 = (tile / mn_tiles) * kb_per_split, num_kb = max(0, min(total_kb - kb0, kb_per_split));
@@ -764,21 +806,21 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
           for (int k = 0; k < BK / kLUmmaK; ++k) {
             const uint64_t o = MN_MAJOR ? (uint64_t)(k * 128) : (uint64_t)(k * 2);
             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            if (NP == 3) {
+            if constexpr (NP == 3) {
               umma_bf16_2sm(tmem_c, ad[0] + o, bd[NP - 1] + o, idesc, acc);
               umma_bf16_2sm(tmem_c, ad[NP - 1] + o, bd[0] + o, idesc, 1u);
               umma_bf16_2sm(tmem_c, ad[1] + o, bd[1] + o, idesc, 1u);
               umma_bf16_2sm(tmem_c, ad[0] + o, bd[1] + o, idesc, 1u);
               umma_bf16_2sm(tmem_c, ad[1] + o, bd[0] + o, idesc, 1u);
-            } else {
+            } else if constexpr (NP == 2) {
               umma_bf16_2sm(tmem_c, ad[0] + o, bd[1] + o, idesc, acc);
               umma_bf16_2sm(tmem_c, ad[1] + o, bd[0] + o, idesc, 1u);
-            }
+            }  // NP == 1: a plain bf16 product, main accumulator only
             umma_bf16_2sm(tmem_d, ad[0] + o, bd[0] + o, idesc, acc);
           }
           umma_commit_2sm(&empty[s]);
         }
-        umma_commit_2sm(acc_full);
+        umma_commit_2sm(&acc_full[ab]);
       }
     }
   } else {
@@ -798,48 +840,71 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
     const float inv_b = (NP == 2) ? 1.f / ep.scale_b[0] : 1.f;
     const bool want_h2 = NP == 2 && ep.h2_planes != nullptr;
     const float oscale = want_h2 ? ep.h2_scale[0] : 1.f;
-    unsigned char* stg = staging + e * 4096;  // this warp's staging box
+    unsigned char* stg = staging + e * kWarpStg;  // this warp's staging box(es)
+    const bool dcn = NP == 1 && ep.dcn_mode != 0;
     const bool masked = NP == 2 && (ep.mask_in != nullptr || ep.mask_out != nullptr || ep.colsum_part != nullptr ||
                                     ep.absmax_out != nullptr || want_h2);
     const bool has_bias = ep.bias != nullptr;
     float amax = 0.f;
-    int it = 0;
+    int it = 0, nin = 0;  // nin: operand fetches of this warp so far (the parity of its barrier)
     for (int tile = cid; tile < n_tiles; tile += n_clusters, ++it) {
       const int mn = tile % mn_tiles, split = tile / mn_tiles;
-      const int m0 = (mn % tiles_m) * 256 + rank * 128, n0 = (mn / tiles_m) * 256;
-      if (has_bias) {
+      K2_TILE_MN(mn, m_idx, n_idx)
+      const int m0 = m_idx * 256 + rank * 128, n0 = n_idx * bn;
+      const int n_end = min(N, n0 + bn);  // columns of this tile
+      const int ab = it % kAcc;
+      if (has_bias) {  // the two barriers keep every epilogue warp inside the same tile: one bias slice is enough
         asm volatile("bar.sync 2, %0;" ::"n"(32 * k2EpiWarps) : "memory");
         if (et < 256) s_bias[et] = (n0 + et < N) ? ep.bias[n0 + et] : 0.f;
         asm volatile("bar.sync 2, %0;" ::"n"(32 * k2EpiWarps) : "memory");
       }
       const int row = m0 + r, col0 = n0 + grp * 64;
-      const bool live = col0 < N;
+      const bool live = col0 < n_end;
+      if (dcn && live) {
+        // this tile's epilogue operands: boxes of 32 rows x 32 columns (2 KB), chunk cl at stg + cl * 4096 (dp0) and
+        // + 2048 (dp1); requested before the accumulator is waited for.  The previous tile's stores have read the boxes.
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          const int nch = col0 + 32 < n_end ? 2 : 1;
+          mbar_arrive_expect_tx(&in_bar[e], (uint32_t)nch * 4096u);  // loads of clipped boxes still deliver every byte
+          for (int cl = 0; cl < nch; ++cl) {
+            tma_load_3d(stg + cl * 4096, &maps.r0, col0 + cl * 32, m0 + q * 32, 0, &in_bar[e]);
+            tma_load_3d(stg + cl * 4096 + 2048, &maps.r1, col0 + cl * 32, m0 + q * 32, 0, &in_bar[e]);
+          }
+        }
+        __syncwarp();
+      }
       uint2 mw = make_uint2(0xffffffffu, 0xffffffffu);
       if (NP == 2 && ep.mask_in != nullptr && live && row < M)  // requested before the accumulator is waited for
         mw = *reinterpret_cast<const uint2*>(ep.mask_in + (int64_t)row * ep.mask_ld + (col0 >> 5));
       K6_STAMP(1 + 4 * it);
-      mbar_wait(acc_full, it & 1);
+      mbar_wait(&acc_full[ab], (it / kAcc) & 1);
       tcgen05_fence_after();
       K6_STAMP(2 + 4 * it);
-      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 64);
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 256 + grp * 64);
       uint32_t mo[2] = {0u, 0u};
 #pragma unroll
       for (int cl = 0; cl < 2; ++cl) {
         const int cc0 = col0 + cl * 32;
-        const bool on = cc0 < N;  // warp-uniform; a narrow remainder tile leaves chunks (or the whole warp) empty
+        const bool on = cc0 < n_end;  // warp-uniform; a narrow tile leaves chunks (or the whole warp) empty
         float x[32];
         if (on) {
-          uint32_t w[32];
-          tmem_ld32_async(tacc + cl * 32, reinterpret_cast<uint32_t*>(x));
-          tmem_ld32_async(tacc + 256 + cl * 32, w);
-          tmem_wait_ld();
+          if constexpr (NP == 1) {
+            tmem_ld32_async(tacc + cl * 32, reinterpret_cast<uint32_t*>(x));
+            tmem_wait_ld();
+          } else {
+            uint32_t w[32];
+            tmem_ld32_async(tacc + cl * 32, reinterpret_cast<uint32_t*>(x));
+            tmem_ld32_async(tacc + 256 + cl * 32, w);
+            tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = lin_combine<NP>(x[j], __uint_as_float(w[j]), inv_a, inv_b);
+            for (int j = 0; j < 32; ++j) x[j] = lin_combine<NP>(x[j], __uint_as_float(w[j]), inv_a, inv_b);
+          }
         }
         if (cl == 1) {
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_leader(acc_empty);
+          if (lane == 0) mbar_arrive_leader(&acc_empty[ab]);
           K6_STAMP(3 + 4 * it);
         }
         if (on) {
@@ -878,7 +943,48 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
             }
             mo[cl] = bits;
           }
-          if (ep.out != nullptr) {
+          if (dcn) {
+            // DCN-v2 cross layer epilogue: this thread's row of the two bf16 operand boxes (32 columns = 64 bytes each,
+            // SWIZZLE_64B: 16-byte chunk g of row l at g ^ ((l >> 1) & 3)) is read 8 columns at a time and overwritten
+            // by the two bf16 results; rows / columns outside the matrices were zero-filled by the loads and are
+            // clipped by the stores
+            unsigned char* box = stg + cl * 4096;
+            if (cl == 0) mbar_wait(&in_bar[e], (nin++) & 1);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int o = lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4);
+              const uint4 qa = *reinterpret_cast<const uint4*>(box + o);
+              const uint4 qb = *reinterpret_cast<const uint4*>(box + 2048 + o);
+              const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&qa);
+              const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&qb);
+              uint32_t w0[4], w1[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 a = __bfloat1622float2(ha[i]), b = __bfloat1622float2(hb[i]);
+                const float v0 = x[8 * g + 2 * i], v1 = x[8 * g + 2 * i + 1];
+                float2 o0, o1;
+                if (ep.dcn_mode == 1) {   // u = acc + bias (added above); x0 * u + x_l; u
+                  o0 = make_float2(a.x * v0 + b.x, a.y * v1 + b.y);
+                  o1 = make_float2(v0, v1);
+                } else {                  // g_x = acc + g_out; g_x; g_x * x0
+                  o0 = make_float2(v0 + a.x, v1 + a.y);
+                  o1 = make_float2(o0.x * b.x, o0.y * b.y);
+                }
+                const __nv_bfloat162 p0 = __floats2bfloat162_rn(o0.x, o0.y), p1 = __floats2bfloat162_rn(o1.x, o1.y);
+                w0[i] = *reinterpret_cast<const uint32_t*>(&p0);
+                w1[i] = *reinterpret_cast<const uint32_t*>(&p1);
+              }
+              *reinterpret_cast<uint4*>(box + o) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+              *reinterpret_cast<uint4*>(box + 2048 + o) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&maps.p, box, cc0, m0 + q * 32, 0);
+              if (ep.dcn_o1) tma_store_3d(&maps.q, box + 2048, cc0, m0 + q * 32, 0);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          } else if (ep.out != nullptr) {
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the box's last store has read it
             __syncwarp();
 #pragma unroll
@@ -942,9 +1048,9 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
         *reinterpret_cast<uint2*>(ep.mask_out + (int64_t)row * ep.mask_ld + (col0 >> 5)) = make_uint2(mo[0], mo[1]);
       K6_STAMP(4 + 4 * it);
     }
-    K6_STAMP(13);
+    K6_STAMP(30);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's TMA stores have landed
-    K6_STAMP(14);
+    K6_STAMP(31);
     if (ep.absmax_out != nullptr) {  // one combining atomic per warp (non-negative floats order as uints)
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -1173,7 +1279,7 @@ static int make_map3(CUtensorMap* map, const void* base, int64_t rows, int64_t c
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
   cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, np == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+  CUresult r = enc(map, np == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                    const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1191,7 +1297,7 @@ static int make_map3_mn(CUtensorMap* map, const void* base, int64_t k_rows, int6
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
   cuuint32_t box[3] = {64, (cuuint32_t)bk, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, np == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+  CUresult r = enc(map, np == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                    const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1202,15 +1308,16 @@ static int make_map3_mn(CUtensorMap* map, const void* base, int64_t k_rows, int6
 // Output of the CTA-pair kernel's TMA stores: 3-D (cols, rows, slab) over [slabs][rows][ld], boxes of 32 x 32 x 1.
 // fp32 result: slab = split-K partial, 128-byte swizzle; fp16 planes: slab = plane, 64-byte swizzle.
 static int make_map_out(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int64_t slab,
-                        int64_t slabs, bool f16) {
+                        int64_t slabs, bool f16, bool bf16 = false) {
   EncodeTiledFn enc = get_encode();
   PTREC_CHECK_ARG(enc != nullptr, PTREC_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if (bf16) f16 = true;  // 16-bit elements, 64-byte swizzle; only the element type differs
   const cuuint64_t esz = f16 ? 2 : 4;
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)slabs};
   cuuint64_t strides[2] = {(cuuint64_t)ld * esz, (cuuint64_t)slab * esz};
   cuuint32_t box[3] = {32, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+  CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 3,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1439,6 +1546,7 @@ static int gemm_split_impl(int np, bool mn_major, const void* a_planes, const fl
   ep.absmax_out = reinterpret_cast<uint32_t*>(absmax_out);
   ep.h2_planes = nullptr; ep.h2_ld = 0; ep.h2_plane = 0; ep.h2_scale = nullptr;
   ep.mask_in = nullptr; ep.mask_out = nullptr; ep.mask_ld = 0; ep.colsum_part = nullptr;
+  ep.dcn_mode = 0; ep.dp0 = nullptr; ep.dp1 = nullptr; ep.dld = 0; ep.dcn_o1 = 0;
   if (two_sm && !db && ep.out != nullptr) {  // the CTA-pair kernel stores through TMA
     rc = make_map_out(&maps.c, ep.out, M, N, ldo, M * ldo, splits, false);
     if (rc != PTREC_OK) return rc;
@@ -1505,6 +1613,73 @@ extern "C" int ptrec_tc_gemm_split2h_tn(const void* a_planes, const float* scale
   return gemm_split_impl(2, true, a_planes, scale_a, M, lda, b_planes, scale_b, N, ldb, K, nullptr, 0, out, ldo,
                          nullptr, 0, nullptr, splits, workspace, workspace_bytes, stream);
 }
+
+// ---- NP = 1: the CTA-pair kernel as a plain bf16 GEMM (K5, the DCN-v2 cross layers; declared in gemm2sm.cuh) ----
+namespace ptrec {
+
+int gemm_bf16_2sm(const Bf16Gemm& g, cudaStream_t st) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  PTREC_CHECK_ARG(sms >= 2, PTREC_EUNSUPPORTED, "gemm_bf16_2sm needs CTA pairs");
+  PTREC_CHECK_ARG(g.A && g.B && g.M >= 1 && g.N >= 1 && g.K >= 1 && aligned16(g.A) && aligned16(g.B) && g.lda % 8 == 0 &&
+                      g.ldb % 8 == 0, PTREC_EALIGN, "gemm_bf16_2sm: operands");
+  static bool attr_set = false;
+  if (!attr_set) {
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<false, 32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
+    PTREC_CUDA(cudaFuncSetAttribute(gemm_split3_2sm_kernel<true, 32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem));
+    attr_set = true;
+  }
+  const int bk = 32;
+  LinMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc = g.mn_major ? make_map3_mn(&maps.a, g.A, g.K, g.M, g.lda, g.K * g.lda, bk, 1)
+                      : make_map3(&maps.a, g.A, g.M, g.K, g.lda, g.M * g.lda, kLBM, bk, 1);
+  if (rc != PTREC_OK) return rc;
+  rc = g.mn_major ? make_map3_mn(&maps.b, g.B, g.K, g.N, g.ldb, g.K * g.ldb, bk, 1)
+                  : make_map3(&maps.b, g.B, g.N, g.K, g.ldb, g.N * g.ldb, 128, bk, 1);
+  if (rc != PTREC_OK) return rc;
+  int splits = g.splits < 1 ? 1 : g.splits;
+  const int total_kb = (int)ceil_div(g.K, (int64_t)bk);
+  if (splits > total_kb) splits = total_kb;
+  while (splits > 1 && (int64_t)(splits - 1) * ceil_div(total_kb, splits) >= total_kb) --splits;
+  LinEpi ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.bias = g.bias; ep.relu = 0; ep.splits = splits; ep.ldo = g.ldo;
+  ep.dcn_mode = g.dcn_mode; ep.dp0 = reinterpret_cast<const __nv_bfloat16*>(g.p0);
+  ep.dp1 = reinterpret_cast<const __nv_bfloat16*>(g.p1); ep.dld = g.pld; ep.dcn_o1 = g.o1 != nullptr;
+  if (g.dcn_mode != 0) {
+    PTREC_CHECK_ARG(!g.mn_major && splits == 1 && g.p0 && g.p1 && g.o0 && g.pld % 8 == 0 && g.N % 8 == 0 && aligned16(g.p0) &&
+                        aligned16(g.p1) && aligned16(g.o0) && (!g.o1 || aligned16(g.o1)), PTREC_EALIGN,
+                    "gemm_bf16_2sm: cross-layer epilogue operands");
+    if ((rc = make_map_out(&maps.p, g.o0, g.M, g.N, g.pld, g.M * g.pld, 1, false, true)) != PTREC_OK) return rc;
+    if (g.o1 && (rc = make_map_out(&maps.q, g.o1, g.M, g.N, g.pld, g.M * g.pld, 1, false, true)) != PTREC_OK) return rc;
+    if ((rc = make_map_out(&maps.r0, g.p0, g.M, g.N, g.pld, g.M * g.pld, 1, false, true)) != PTREC_OK) return rc;
+    if ((rc = make_map_out(&maps.r1, g.p1, g.M, g.N, g.pld, g.M * g.pld, 1, false, true)) != PTREC_OK) return rc;
+  } else {
+    PTREC_CHECK_ARG(g.out && aligned16(g.out) && g.ldo % 4 == 0 && g.ldo >= (g.N + 3) / 4 * 4, PTREC_EALIGN,
+                    "gemm_bf16_2sm: fp32 output");
+    PTREC_CHECK_ARG(splits == 1 || (g.workspace && g.workspace_bytes >= (size_t)splits * g.M * g.ldo * sizeof(float)),
+                    PTREC_EWORKSPACE, "gemm_bf16_2sm: workspace too small for %d split-K partials", splits);
+    ep.out = splits > 1 ? reinterpret_cast<float*>(g.workspace) : g.out;
+    if ((rc = make_map_out(&maps.c, ep.out, g.M, g.N, g.ldo, g.M * g.ldo, splits, false)) != PTREC_OK) return rc;
+  }
+  const int64_t pair_tiles = ceil_div(g.N, (int64_t)256) * ceil_div(g.M, (int64_t)256) * splits;
+  const unsigned grid2 = (unsigned)(2 * std::min<int64_t>(pair_tiles, sms / 2));
+  if (g.mn_major)
+    gemm_split3_2sm_kernel<true, 32, 1><<<grid2, k2Threads, k2Smem, st>>>(maps, (int)g.M, (int)g.N, (int)g.K, ep);
+  else
+    gemm_split3_2sm_kernel<false, 32, 1><<<grid2, k2Threads, k2Smem, st>>>(maps, (int)g.M, (int)g.N, (int)g.K, ep);
+  PTREC_LAUNCH_CHECK("gemm_split3_2sm_kernel<.,32,1>");
+  if (g.dcn_mode == 0 && splits > 1) {
+    const int64_t n = g.M * g.ldo;
+    partial_reduce_kernel<<<(unsigned)ceil_div(n / 4, (int64_t)256), 256, 0, st>>>(ep.out, splits, n, g.out);
+    PTREC_LAUNCH_CHECK("partial_reduce_kernel");
+  }
+  return PTREC_OK;
+}
+
+}  // namespace ptrec
 
 // ---- the fused tower: carried scales, prescaled split, GEMM epilogue that writes its consumer's operand planes ----
 extern "C" int ptrec_tc_scale_roll(float* slots, int32_t n_slots, float* call_scales, int32_t* err, void* stream) {

@@ -952,6 +952,16 @@ def _check_bf16_2d(*ts):
         assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and t.data_ptr() % 16 == 0
 
 
+def set_dcn_2sm(enabled: bool) -> None:
+    """K5 kernel choice: the CTA-pair GEMM of K6 with one bf16 plane (default) or the 128 x 128 single-CTA kernel of
+    round 1 (csrc/dcn_cross.cu); same results up to summation order."""
+    _lib.load().ptrec_set_dcn_2sm(1 if enabled else 0)
+
+
+def dcn_2sm_enabled() -> bool:
+    return bool(_lib.load().ptrec_dcn_2sm_enabled())
+
+
 def dcn_cross_fwd(x_l: torch.Tensor, x0: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
                   want_u: bool = True):
     """out = x0 * (x_l @ weight.T + bias) + x_l  (bf16 [B, d]); returns (out, u or None)."""

@@ -477,8 +477,17 @@ def _bf16(t):
     return t.to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("B,d", [(128, 128), (256, 64), (1000, 848), (4096, 896), (130, 72)])
-def test_dcn_cross_fwd_matches_fp32_reference(B, d):
+@pytest.fixture(params=["pair", "single"])
+def dcn_kernel(request):
+    """K5 runs on the CTA-pair GEMM (default) or on the single-CTA kernel of round 1; the tests cover both."""
+    ops.set_dcn_2sm(request.param == "pair")
+    yield request.param
+    ops.set_dcn_2sm(True)
+
+
+@pytest.mark.parametrize("B,d", [(128, 128), (256, 64), (1000, 848), (4096, 896), (130, 72), (33000, 848), (8, 8),
+                                 (777, 1032)])
+def test_dcn_cross_fwd_matches_fp32_reference(B, d, dcn_kernel):
     """bf16 operands, fp32 accumulate: compare with the same bf16-rounded inputs multiplied in fp32 (tolerance 1e-2)."""
     g = torch.Generator().manual_seed(B + d)
     x0, xl = torch.randn(B, d, generator=g) * 0.5, torch.randn(B, d, generator=g) * 0.5
@@ -491,8 +500,8 @@ def test_dcn_cross_fwd_matches_fp32_reference(B, d):
     np.testing.assert_allclose(out.float().cpu().numpy(), out_ref.numpy(), rtol=1e-2, atol=1e-2)
 
 
-@pytest.mark.parametrize("B,d", [(256, 128), (1000, 848)])
-def test_dcn_cross_dgrad_wgrad(B, d):
+@pytest.mark.parametrize("B,d", [(256, 128), (1000, 848), (33000, 848), (130, 72), (777, 1032)])
+def test_dcn_cross_dgrad_wgrad(B, d, dcn_kernel):
     g = torch.Generator().manual_seed(B * 3 + d)
     x0, xl, go = (torch.randn(B, d, generator=g) * 0.5 for _ in range(3))
     W = torch.randn(d, d, generator=g) / d ** 0.5
@@ -507,7 +516,7 @@ def test_dcn_cross_dgrad_wgrad(B, d):
     np.testing.assert_allclose(gw.cpu().numpy(), gw_ref.numpy(), rtol=1e-2, atol=1e-2 * B ** 0.5 * 0.25)
 
 
-def test_cross_net_autograd_matches_oracle():
+def test_cross_net_autograd_matches_oracle(dcn_kernel):
     from oracle import ref_models
     B, d, L = 512, 845, 3
     g = torch.Generator().manual_seed(1)

@@ -24,7 +24,7 @@ t = buf.cpu().view(148, 32).double()
 t0 = t[:, 0][t[:, 0] > 0].min()
 names = {0: "entry", 1: "t0 wait", 2: "t0 acc ready", 16: "  pass0 drained", 17: "  chunk0 out", 24: "   c1 computed", 25: "   c1 box free", 26: "   c1 staged", 27: "   c1 fenced", 18: "  chunk1 out",
          20: "  pass1 drained", 3: "t0 tmem free", 21: "  chunk2 out", 22: "  chunk3 out", 4: "t0 stored", 5: "t1 wait",
-         6: "t1 acc ready", 7: "t1 tmem free", 8: "t1 stored", 13: "loop done", 14: "stores landed"}
+         6: "t1 acc ready", 7: "t1 tmem free", 8: "t1 stored", 30: "loop done", 31: "stores landed"}
 print(f"launch {e0.elapsed_time(e1) * 1e3:.1f} us (event); SM cycles after each CTA's own entry: min / median / max over CTAs")
 for s, n in names.items():
     ok = (t[:, s] > 0) & (t[:, 0] > 0)
