@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 23
+#define PTREC_ABI_VERSION 24
 
 /* error codes */
 #define PTREC_OK 0
@@ -330,6 +330,14 @@ size_t ptrec_dcn_bwd_layer_workspace_bytes(int64_t B, int32_t dp);
 int ptrec_dcn_bwd_layer(const void* g_out, const void* u, const void* g_u, int64_t B, int32_t d, int32_t dp, float* g_x0,
                         int32_t accumulate, float* grad_bias, void* workspace, size_t workspace_bytes, void* stream);
 int ptrec_dcn_bwd_final(const float* g_x0, const void* g_out, int64_t B, int32_t d, int32_t dp, float* out, void* stream);
+/* The cross half of DCN's closing Linear(concat(cross, deep)) -> 1, read from / written to the bf16 tensors of the cross
+ * layers (no fp32 [B, d] copy of x_L, no fp32 [B, d] gradient):
+ *   head_fwd  y[b] = sum_{c < d} x_L[b, c] w[c]
+ *   head_bwd  g_out = bf16(g_y (x) w) zero padded, g_u = g_out * x0, grad_w[c] = sum_b g_y[b] x_L[b, c]
+ *             (workspace: ptrec_dcn_bwd_layer_workspace_bytes(B, dp); fixed-order sums) */
+int ptrec_dcn_head_fwd(const void* x_l, int64_t B, int32_t d, int32_t dp, const float* w, float* y, void* stream);
+int ptrec_dcn_head_bwd(const float* g_y, const float* w, const void* x_l, const void* x0, int64_t B, int32_t d, int32_t dp,
+                       void* g_out, void* g_u, float* grad_w, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K8 the FM head: first-order sum + second-order interaction + dense-feature linear term + bias in one pass, and

@@ -256,6 +256,10 @@ rowdot_bwd_kernel(const float* __restrict__ h, int64_t hs, const float* __restri
   extern __shared__ float s_acc[];  // [kHdWarps][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = H / 4;
+  // blockIdx.y: a block of 32 * MAXC column quads (a row wider than 128 * MAXC columns is walked by several CTAs: with one
+  // warp per whole 1024-column row the kernel held 4 x 32 accumulators per thread and ran at a quarter of the HBM rate)
+  const int qbase = blockIdx.y * 32 * MAXC;
+  const int k_lo = qbase * 4, k_hi = min(H, (qbase + 32 * MAXC) * 4);
   float4 a[MAXC], wv[MAXC], cs[H2 ? MAXC : 1];
   const float hsc = H2 ? *h2_scale : 1.f;
   float amax = 0.f;
@@ -263,7 +267,7 @@ rowdot_bwd_kernel(const float* __restrict__ h, int64_t hs, const float* __restri
   for (int u = 0; u < MAXC; ++u) {
     a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (H2) cs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int q = lane + u * 32;
+    const int q = qbase + lane + u * 32;
     wv[u] = q < nq ? *reinterpret_cast<const float4*>(w + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int64_t b = (int64_t)blockIdx.x * kHdWarps + warp; b < B; b += (int64_t)gridDim.x * kHdWarps) {
@@ -273,12 +277,12 @@ rowdot_bwd_kernel(const float* __restrict__ h, int64_t hs, const float* __restri
     float4 t[MAXC];
 #pragma unroll
     for (int u = 0; u < MAXC; ++u) {
-      const int q = lane + u * 32;
+      const int q = qbase + lane + u * 32;
       t[u] = q < nq ? ldg_stream_f4(row + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < MAXC; ++u) {
-      const int q = lane + u * 32;
+      const int q = qbase + lane + u * 32;
       a[u].x += gb * t[u].x; a[u].y += gb * t[u].y; a[u].z += gb * t[u].z; a[u].w += gb * t[u].w;
       if (orow && q < nq) st_f4(orow + q * 4, make_float4(gb * wv[u].x, gb * wv[u].y, gb * wv[u].z, gb * wv[u].w));
       if (H2 && q < nq) {
@@ -304,11 +308,11 @@ rowdot_bwd_kernel(const float* __restrict__ h, int64_t hs, const float* __restri
     if (cs_part != nullptr) {  // fixed-order per-CTA column sums of the masked gradient (bias gradient)
 #pragma unroll
       for (int u = 0; u < MAXC; ++u) {
-        const int q = lane + u * 32;
+        const int q = qbase + lane + u * 32;
         if (q < nq) *reinterpret_cast<float4*>(&s_acc[(size_t)warp * H + q * 4]) = cs[u];
       }
       __syncthreads();
-      for (int k = threadIdx.x; k < H; k += blockDim.x) {
+      for (int k = k_lo + threadIdx.x; k < k_hi; k += blockDim.x) {
         float s = 0.f;
 #pragma unroll
         for (int wi = 0; wi < kHdWarps; ++wi) s += s_acc[(size_t)wi * H + k];
@@ -320,11 +324,11 @@ rowdot_bwd_kernel(const float* __restrict__ h, int64_t hs, const float* __restri
   if (part == nullptr) return;
 #pragma unroll
   for (int u = 0; u < MAXC; ++u) {
-    const int q = lane + u * 32;
+    const int q = qbase + lane + u * 32;
     if (q < nq) *reinterpret_cast<float4*>(&s_acc[(size_t)warp * H + q * 4]) = a[u];
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+  for (int k = k_lo + threadIdx.x; k < k_hi; k += blockDim.x) {
     float s = 0.f;
 #pragma unroll
     for (int wi = 0; wi < kHdWarps; ++wi) s += s_acc[(size_t)wi * H + k];
@@ -473,12 +477,9 @@ extern "C" int ptrec_rowdot_bwd(const float* h, int64_t h_row_stride, const floa
   const int grid = (int)std::min<int64_t>(head_grid(), ceil_div(B, kHdWarps));
   const size_t smem = (size_t)kHdWarps * H * sizeof(float);
   float* part = grad_w ? reinterpret_cast<float*>(workspace) : nullptr;
-  if (H <= 512)
-    rowdot_bwd_kernel<4, false><<<grid, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, grad_h, grad_h_row_stride,
-                                                                   part, nullptr, 0, 0, nullptr, nullptr, nullptr);
-  else
-    rowdot_bwd_kernel<8, false><<<grid, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, grad_h, grad_h_row_stride,
-                                                                   part, nullptr, 0, 0, nullptr, nullptr, nullptr);
+  const dim3 grid2((unsigned)grid, (unsigned)ceil_div(H, 512));
+  rowdot_bwd_kernel<4, false><<<grid2, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, grad_h, grad_h_row_stride,
+                                                                  part, nullptr, 0, 0, nullptr, nullptr, nullptr);
   PTREC_LAUNCH_CHECK("rowdot_bwd_kernel");
   if (grad_w) {
     head_reduce_kernel<<<(unsigned)ceil_div(H, 32), 1024, 0, st>>>(part, grid, H, grad_w, H, nullptr);
@@ -505,14 +506,10 @@ extern "C" int ptrec_rowdot_bwd_h2(const float* h, int64_t h_row_stride, const f
   float* part = grad_w ? reinterpret_cast<float*>(workspace) : nullptr;
   float* cs_part = colsum ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + one) : nullptr;
   unsigned short* pl = reinterpret_cast<unsigned short*>(planes);
-  if (H <= 512)
-    rowdot_bwd_kernel<4, true><<<grid, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, nullptr, 0, part, pl,
-                                                                  planes_ld, B * planes_ld, scale,
-                                                                  reinterpret_cast<uint32_t*>(max_out), cs_part);
-  else
-    rowdot_bwd_kernel<8, true><<<grid, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, nullptr, 0, part, pl,
-                                                                  planes_ld, B * planes_ld, scale,
-                                                                  reinterpret_cast<uint32_t*>(max_out), cs_part);
+  const dim3 grid2((unsigned)grid, (unsigned)ceil_div(H, 512));
+  rowdot_bwd_kernel<4, true><<<grid2, kHdWarps * 32, smem, st>>>(h, h_row_stride, w, g, B, H, nullptr, 0, part, pl,
+                                                                 planes_ld, B * planes_ld, scale,
+                                                                 reinterpret_cast<uint32_t*>(max_out), cs_part);
   PTREC_LAUNCH_CHECK("rowdot_bwd_kernel");
   if (grad_w) {
     head_reduce_kernel<<<(unsigned)ceil_div(H, 32), 1024, 0, st>>>(part, grid, H, grad_w, H, nullptr);

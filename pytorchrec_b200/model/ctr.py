@@ -184,11 +184,11 @@ class DCN(IModel):
         from .layer.interaction import row_dot
         d = x0.shape[1]
         w = self.out.weight                                  # [1, d + H]
-        c, h = self.cross(x0), self.mlp(x0)
+        c, h = self.cross.forward_head(x0, w[0, :d]), self.mlp(x0)   # c [B]: the cross half of the closing Linear
         deep = row_dot(h, w[0, d:], tower_handoff=True)      # h has no other consumer
         if deep is None:
             deep = torch.nn.functional.linear(h, w[:, d:]).squeeze(-1)
-        logit = torch.nn.functional.linear(c, w[:, :d]).squeeze(-1) + deep
+        logit = c + deep
         target = self.label_column.get_feature_data(data)
         return logit, (target.float() if target is not None else None)
 

@@ -168,6 +168,11 @@ class CrossNet(nn.Module):
     def forward(self, x0: Tensor) -> Tensor:
         return ops.cross_net(x0, [m.weight for m in self.layers], [m.bias for m in self.layers])
 
+    def forward_head(self, x0: Tensor, head_w: Tensor) -> Tensor:
+        """``forward(x0) @ head_w`` ([B]): the cross half of a closing ``Linear(concat(cross, deep), 1)`` fused with the
+        last cross layer's bf16 output (no fp32 [B, d] tensor either way)."""
+        return ops.cross_net_head(x0, [m.weight for m in self.layers], [m.bias for m in self.layers], head_w)
+
 
 class AttentionPooling(nn.Module):
     """DIN attention pooling: ``pooled = sum_{l < len} a_l k_l`` with the activation unit

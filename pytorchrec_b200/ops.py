@@ -1015,7 +1015,9 @@ class _CrossNet(torch.autograd.Function):
     gradients, the transposed weights) is one launch of csrc/dcn_glue.cu."""
 
     @staticmethod
-    def forward(ctx, x0f, n_layers, *params):
+    def forward(ctx, x0f, n_layers, head_w, *params):
+        """head_w: None -> the fp32 [B, d] output of the last layer; an fp32 [d] vector -> y [B] = x_L . head_w (the cross
+        half of DCN's closing Linear) computed from the bf16 x_L, with its backward fused into the chain's first step."""
         lib = _lib.load()
         weights, biases = params[:n_layers], params[n_layers:]
         B, d = x0f.shape
@@ -1039,9 +1041,15 @@ class _CrossNet(torch.autograd.Function):
             wts.append(w16t)
             xs.append(x)
             us.append(u)
+        ctx.d, ctx.n, ctx.head = d, n_layers, head_w is not None
+        if head_w is not None:
+            hw = head_w.detach().float().contiguous()
+            y = torch.empty(B, dtype=torch.float32, device=dev)
+            _lib.check(lib.ptrec_dcn_head_fwd(_ptr(x), B, d, dp, _ptr(hw), _ptr(y), st), "ptrec_dcn_head_fwd")
+            ctx.save_for_backward(*xs[:-1], *us, *wts, x, hw)
+            return y.to(x0f.dtype)
         out = torch.empty(B, d, dtype=torch.float32, device=dev)
         _lib.check(lib.ptrec_dcn_unpack(_ptr(x), B, d, dp, _ptr(out), st), "ptrec_dcn_unpack")
-        ctx.d, ctx.n = d, n_layers
         ctx.save_for_backward(*xs[:-1], *us, *wts)
         return out.to(x0f.dtype)
 
@@ -1050,20 +1058,28 @@ class _CrossNet(torch.autograd.Function):
         lib = _lib.load()
         n, d = ctx.n, ctx.d
         saved = ctx.saved_tensors
-        xs, us, wts = saved[:n], saved[n:2 * n], saved[2 * n:]
+        xs, us, wts = saved[:n], saved[n:2 * n], saved[2 * n:3 * n]
         x0 = xs[0]
         B, dp = x0.shape
         dev = g.device
         st = _stream(dev)
         g = g.float()
-        if g.stride(1) != 1:
-            g = g.contiguous()
         g_out = torch.empty(B, dp, dtype=torch.bfloat16, device=dev)
         g_u = torch.empty(B, dp, dtype=torch.bfloat16, device=dev)
-        _lib.check(lib.ptrec_dcn_bwd_init(_ptr(g), g.stride(0), _ptr(x0), B, d, dp, _ptr(g_out), _ptr(g_u), st),
-                   "ptrec_dcn_bwd_init")
-        g_x0 = torch.empty(B, dp, dtype=torch.float32, device=dev)
         ws = _workspace("dcn_bwd_layer", lib.ptrec_dcn_bwd_layer_workspace_bytes(B, dp), dev)
+        g_head = None
+        if ctx.head:
+            x_last, hw = saved[3 * n], saved[3 * n + 1]
+            g = g.contiguous()
+            g_head = torch.empty(d, dtype=torch.float32, device=dev)
+            _lib.check(lib.ptrec_dcn_head_bwd(_ptr(g), _ptr(hw), _ptr(x_last), _ptr(x0), B, d, dp, _ptr(g_out), _ptr(g_u),
+                                              _ptr(g_head), _ptr(ws), ws.numel(), st), "ptrec_dcn_head_bwd")
+        else:
+            if g.stride(1) != 1:
+                g = g.contiguous()
+            _lib.check(lib.ptrec_dcn_bwd_init(_ptr(g), g.stride(0), _ptr(x0), B, d, dp, _ptr(g_out), _ptr(g_u), st),
+                       "ptrec_dcn_bwd_init")
+        g_x0 = torch.empty(B, dp, dtype=torch.float32, device=dev)
         gws, gbs = [None] * n, [None] * n
         for l in range(n - 1, -1, -1):
             gbs[l] = torch.empty(d, dtype=torch.float32, device=dev)
@@ -1074,13 +1090,21 @@ class _CrossNet(torch.autograd.Function):
             g_out, g_u = dcn_cross_dgrad(g_u, wts[l], g_out, x0, want_prev=l > 0)
         out = torch.empty(B, d, dtype=torch.float32, device=dev)  # x0 is also layer 0's x_l: + the chain's g_out
         _lib.check(lib.ptrec_dcn_bwd_final(_ptr(g_x0), _ptr(g_out), B, d, dp, _ptr(out), st), "ptrec_dcn_bwd_final")
-        return (out, None, *gws, *gbs)
+        return (out, None, g_head, *gws, *gbs)
 
 
 def cross_net(x0: torch.Tensor, weights, biases) -> torch.Tensor:
     """L DCN-v2 cross layers ``x <- x0 * (x W_l^T + b_l) + x`` on tensor cores (bf16, fp32 accumulate)."""
     _require_cuda(x0)
-    return _CrossNet.apply(x0.contiguous(), len(weights), *weights, *biases)
+    return _CrossNet.apply(x0.contiguous(), len(weights), None, *weights, *biases)
+
+
+def cross_net_head(x0: torch.Tensor, weights, biases, head_w: torch.Tensor) -> torch.Tensor:
+    """``cross_net(x0) @ head_w`` ([B]; head_w fp32 [d]) without the fp32 [B, d] output: the row dot reads the last
+    layer's bf16 result, its backward writes the chain's bf16 gradient operands directly."""
+    _require_cuda(x0, head_w)
+    assert head_w.dim() == 1 and head_w.numel() == x0.shape[1]
+    return _CrossNet.apply(x0.contiguous(), len(weights), head_w, *weights, *biases)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -545,6 +545,89 @@ def test_cross_net_autograd_matches_oracle(dcn_kernel):
         close(bd[l].grad, br[l].grad, f"grad b{l}")
 
 
+@pytest.mark.parametrize("B,d", [(64, 8), (1000, 845), (4099, 77), (513, 1030)])
+def test_cross_net_head_matches_unfused_head(B, d):
+    """cross_net_head(x0, W, b, w) == cross_net(x0, W, b) @ w: same bf16 chain, the row dot and its backward fused
+    (the head reads / writes the chain's bf16 tensors, so forward and gradients agree to fp32 summation order, and the
+    gradients that pass through bf16(g_y (x) w) agree exactly in their bf16 operands)."""
+    g = torch.Generator().manual_seed(B + 7 * d)
+    L = 2
+    x0 = (torch.randn(B, d, generator=g) * 0.3).to(DEV)
+    Ws = [(torch.randn(d, d, generator=g) / d ** 0.5).to(DEV) for _ in range(L)]
+    bs = [(torch.randn(d, generator=g) * 0.1).to(DEV) for _ in range(L)]
+    w = (torch.randn(d, generator=g) / d ** 0.5).to(DEV)
+    gy = torch.randn(B, generator=g).to(DEV)
+
+    def run(fused):
+        leaves = [t.clone().requires_grad_(True) for t in (x0, w, *Ws, *bs)]
+        x, hw, W, b = leaves[0], leaves[1], leaves[2:2 + L], leaves[2 + L:]
+        y = ops.cross_net_head(x, W, b, hw) if fused else ops.cross_net(x, W, b) @ hw
+        y.backward(gy)
+        return y.detach(), [t.grad for t in leaves]
+
+    y1, g1 = run(True)
+    y0, g0 = run(False)
+    scale = y0.abs().max().item()
+    assert (y1 - y0).abs().max().item() <= 1e-5 * max(scale, 1.0) * d ** 0.5
+    for a, b_, what in zip(g1, g0, ["x0", "head w"] + [f"W{l}" for l in range(L)] + [f"b{l}" for l in range(L)]):
+        err = ((a - b_).norm() / b_.norm().clamp_min(1e-30)).item()
+        assert err < 2e-5, f"grad {what}: relative error {err:.2e}"
+
+
+def test_dcn_head_kernels_match_fp32_reference():
+    lib = _lib.load()
+    B, d = 777, 845
+    dp = (d + 7) // 8 * 8
+    g = torch.Generator().manual_seed(5)
+    xl = torch.zeros(B, dp, dtype=torch.bfloat16)
+    x0 = torch.zeros(B, dp, dtype=torch.bfloat16)
+    xl[:, :d] = (torch.randn(B, d, generator=g) * 0.5).to(torch.bfloat16)
+    x0[:, :d] = (torch.randn(B, d, generator=g) * 0.5).to(torch.bfloat16)
+    w, gy = torch.randn(d, generator=g), torch.randn(B, generator=g)
+    xld, x0d, wd, gyd = xl.to(DEV), x0.to(DEV), w.to(DEV), gy.to(DEV)
+    y = torch.empty(B, device=DEV)
+    _lib.check(lib.ptrec_dcn_head_fwd(xld.data_ptr(), B, d, dp, wd.data_ptr(), y.data_ptr(), None), "head_fwd")
+    y_ref = xl[:, :d].double() @ w.double()
+    np.testing.assert_allclose(y.cpu().double().numpy(), y_ref.numpy(), rtol=1e-5, atol=1e-5 * d ** 0.5)
+    g_out = torch.full((B, dp), 7.0, dtype=torch.bfloat16, device=DEV)
+    g_u = torch.full((B, dp), 7.0, dtype=torch.bfloat16, device=DEV)
+    gw = torch.empty(d, device=DEV)
+    nb = lib.ptrec_dcn_bwd_layer_workspace_bytes(B, dp)
+    ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.ptrec_dcn_head_bwd(gyd.data_ptr(), wd.data_ptr(), xld.data_ptr(), x0d.data_ptr(), B, d, dp,
+                                      g_out.data_ptr(), g_u.data_ptr(), gw.data_ptr(), ws.data_ptr(), nb, None), "head_bwd")
+    go_ref = torch.zeros(B, dp, dtype=torch.bfloat16)
+    go_ref[:, :d] = (gy[:, None] * w[None, :]).to(torch.bfloat16)   # fp32 product rounded to bf16: bit-exact
+    assert torch.equal(g_out.cpu(), go_ref), "g_out = bf16(g_y (x) w), zero padded"
+    gu_ref = (go_ref.float() * x0.float()).to(torch.bfloat16)
+    assert torch.equal(g_u.cpu(), gu_ref), "g_u = bf16(g_out * x0)"
+    gw_ref = (gy.double()[:, None] * xl[:, :d].double()).sum(0)
+    np.testing.assert_allclose(gw.cpu().double().numpy(), gw_ref.numpy(), rtol=1e-5, atol=1e-5 * B ** 0.5)
+
+
+@pytest.mark.parametrize("B,d", [(50, 13), (1000, 845), (33, 1030)])
+def test_dcn_pack_unpack_final_unaligned_rows(B, d):
+    """The fp32 side of the glue kernels has rows of d floats (any d): pack / unpack round trip and bwd_final are exact."""
+    lib = _lib.load()
+    dp = (d + 7) // 8 * 8
+    g = torch.Generator().manual_seed(d)
+    x = torch.randn(B, d, generator=g).to(DEV)
+    xb = torch.full((B, dp), 3.0, dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.ptrec_dcn_pack_input(x.data_ptr(), d, B, d, dp, xb.data_ptr(), None), "pack")
+    assert torch.equal(xb[:, :d], x.to(torch.bfloat16)) and (xb[:, d:] == 0).all()
+    out = torch.empty(B, d, device=DEV)
+    _lib.check(lib.ptrec_dcn_unpack(xb.data_ptr(), B, d, dp, out.data_ptr(), None), "unpack")
+    assert torch.equal(out, x.to(torch.bfloat16).float())
+    gx0 = torch.randn(B, dp, generator=g).to(DEV)
+    fin = torch.empty(B, d, device=DEV)
+    _lib.check(lib.ptrec_dcn_bwd_final(gx0.data_ptr(), xb.data_ptr(), B, d, dp, fin.data_ptr(), None), "final")
+    assert torch.equal(fin, gx0[:, :d] + xb[:, :d].float())
+    go = torch.empty(B, dp, dtype=torch.bfloat16, device=DEV)
+    gu = torch.empty(B, dp, dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.ptrec_dcn_bwd_init(x.data_ptr(), d, xb.data_ptr(), B, d, dp, go.data_ptr(), gu.data_ptr(), None), "init")
+    assert torch.equal(go, xb) and torch.equal(gu, (xb.float() * xb.float()).to(torch.bfloat16))
+
+
 # ------------------------------------------------------------------------------------------ DIN attention pooling
 @pytest.fixture(params=["simt", "tensor_core_fwd", "tensor_core_fwd_bwd"])
 def din_build(request):
@@ -738,7 +821,7 @@ def test_fm_head_forward_backward_match_torch(B, F, D, nd):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,H", [(1000, 400), (64, 1024), (257, 32)])
+@pytest.mark.parametrize("B,H", [(1000, 400), (64, 1024), (257, 32), (3000, 1024), (500, 640)])
 def test_row_dot_matches_linear(B, H):
     from pytorchrec_b200.model.layer.interaction import row_dot
     gen = torch.Generator().manual_seed(H)
