@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 24
+#define PTREC_ABI_VERSION 25
 
 /* error codes */
 #define PTREC_OK 0
@@ -289,6 +289,26 @@ int ptrec_din_attn_pool_bwd(const float* q, int64_t q_stride, const float* keys,
                             const float* W3, const float* b3, const float* g_pooled, float* g_q, float* g_keys,
                             int64_t gk_stride_b, int64_t gk_stride_l, float* grad_params, void* workspace,
                             size_t workspace_bytes, void* stream);
+
+/* K4 with the key gather fused in (round 2; tensor-core builds only: PTREC_EUNSUPPORTED otherwise, and the caller gathers).
+ * The keys of the attention unit are rows of two fp32 tables (DIN: item and category), DQ / 2 columns each:
+ *   key (b, l) = [ table0[ids0[b * ids_stride_b + ids_offset + l]] | table1[ids1[b * ids_stride_b + ids_offset + l]] ]
+ * row_stride = the tables' row pitch in floats (a table interleaved with its optimizer state has pitch 2D or 4D); an id
+ * outside [0, rows) raises *err_flag (may be NULL) and reads as a zero row.  q, the outputs and the workspace are those of
+ * ptrec_din_attn_pool_fwd / _bwd; g_keys still leaves as dense rows (the fused table update consumes them). */
+int ptrec_din_attn_pool_fwd_ids(const float* q, int64_t q_stride, const float* table0, const float* table1,
+                                int64_t row_stride0, int64_t row_stride1, int64_t rows0, int64_t rows1, const int64_t* ids0,
+                                const int64_t* ids1, int64_t ids_stride_b, int64_t ids_offset, int32_t* err_flag,
+                                const int32_t* lens, int64_t B, int32_t L, int32_t DQ, int32_t H1, int32_t H2,
+                                const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                                const float* b3, float* out, float* scores, void* stream);
+int ptrec_din_attn_pool_bwd_ids(const float* q, int64_t q_stride, const float* table0, const float* table1,
+                                int64_t row_stride0, int64_t row_stride1, int64_t rows0, int64_t rows1, const int64_t* ids0,
+                                const int64_t* ids1, int64_t ids_stride_b, int64_t ids_offset, const int32_t* lens, int64_t B,
+                                int32_t L, int32_t DQ, int32_t H1, int32_t H2, const float* W1, const float* b1,
+                                const float* W2, const float* b2, const float* W3, const float* b3, const float* g_pooled,
+                                float* g_q, float* g_keys, int64_t gk_stride_b, int64_t gk_stride_l, float* grad_params,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K5 DCN-v2 cross layer on tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM).

@@ -11,6 +11,7 @@
 // The backward recomputes the unit, emits key / query gradients, and accumulates the weight gradients of all its
 // samples in registers (4x4 register tiles of two small GEMMs per sample); per-CTA partials are reduced in a
 // fixed order by a second kernel, so results are run-to-run bit-reproducible (no floating-point atomics).
+#include "din_keys.cuh"
 #include "common.cuh"
 
 namespace ptrec {
@@ -443,11 +444,12 @@ namespace ptrec {
 // din_attn_tc.cu: the forward on the tensor cores (PTREC_EUNSUPPORTED when the shape has no such build)
 int din_fwd_tc(const float* q, int64_t qs, const float* keys, int64_t ksb, int64_t ksl, const int32_t* lens, int64_t B,
                int L, int DQ, int H1, int H2, const float* W1, const float* b1, const float* W2, const float* b2,
-               const float* W3, const float* b3, float* out, float* scores, cudaStream_t st);
+               const float* W3, const float* b3, float* out, float* scores, cudaStream_t st,
+               const DinKeyIds* kid = nullptr);
 int din_bwd_tc(const float* q, int64_t qs, const float* keys, int64_t ksb, int64_t ksl, const int32_t* lens, int64_t B,
                int L, int DQ, int H1, int H2, const float* W1, const float* b1, const float* W2, const float* b2,
                const float* W3, const float* b3, const float* g_pooled, float* g_q, float* g_keys, int64_t gksb,
-               int64_t gksl, float* partials, int* n_rows, cudaStream_t st);
+               int64_t gksl, float* partials, int* n_rows, cudaStream_t st, const DinKeyIds* kid = nullptr);
 }  // namespace ptrec
 
 using namespace ptrec;
@@ -539,4 +541,79 @@ extern "C" int ptrec_din_attn_pool_bwd(const float* q, int64_t q_stride, const f
   }
   PTREC_DIN_DISPATCH(din_bwd_launch, q, q_stride, keys, k_stride_b, k_stride_l, lens, B, L, W1, b1, W2, b2, W3, b3,
                      g_pooled, g_q, g_keys, gk_stride_b, gk_stride_l, grad_params, partials, st);
+}
+
+// ---- K4 with the key gather fused in (tensor-core builds only; din_keys.cuh) ---------------------------------------
+static int din_ids_fill(DinKeyIds* kid, const float* table0, const float* table1, int64_t row_stride0, int64_t row_stride1,
+                        int64_t rows0, int64_t rows1, const int64_t* ids0, const int64_t* ids1, int64_t ids_stride_b,
+                        int64_t ids_offset, int32_t* err_flag, int32_t DQ) {
+  PTREC_CHECK_ARG(table0 && table1 && ids0 && ids1 && rows0 >= 1 && rows1 >= 1 && ids_stride_b >= 1 && ids_offset >= 0,
+                  PTREC_EINVAL, "din_attn_pool_ids: bad argument");
+  PTREC_CHECK_ARG(aligned16(table0) && aligned16(table1) && row_stride0 % 4 == 0 && row_stride1 % 4 == 0 &&
+                      row_stride0 >= DQ / 2 && row_stride1 >= DQ / 2, PTREC_EALIGN,
+                  "din_attn_pool_ids: tables must be 16-byte aligned fp32 with a row pitch that is a multiple of 4 floats");
+  kid->base[0] = table0; kid->base[1] = table1;
+  kid->stride[0] = row_stride0; kid->stride[1] = row_stride1;
+  kid->rows[0] = rows0; kid->rows[1] = rows1;
+  kid->ids[0] = ids0; kid->ids[1] = ids1;
+  kid->ids_sb = ids_stride_b; kid->ids_off = ids_offset;
+  kid->err = err_flag;
+  return PTREC_OK;
+}
+
+extern "C" int ptrec_din_attn_pool_fwd_ids(const float* q, int64_t q_stride, const float* table0, const float* table1,
+                                           int64_t row_stride0, int64_t row_stride1, int64_t rows0, int64_t rows1,
+                                           const int64_t* ids0, const int64_t* ids1, int64_t ids_stride_b,
+                                           int64_t ids_offset, int32_t* err_flag, const int32_t* lens, int64_t B, int32_t L,
+                                           int32_t DQ, int32_t H1, int32_t H2, const float* W1, const float* b1,
+                                           const float* W2, const float* b2, const float* W3, const float* b3, float* out,
+                                           float* scores, void* stream) {
+  int rc = din_check(q, table0, B, L, DQ, H1, H2, q_stride, 4, 4);
+  if (rc != PTREC_OK) return rc;
+  PTREC_CHECK_ARG(W1 && b1 && W2 && b2 && W3 && b3 && out, PTREC_EINVAL, "din_attn_pool_fwd_ids: null pointer");
+  if (!(g_din_tc & 1)) return PTREC_EUNSUPPORTED;
+  DinKeyIds kid;
+  rc = din_ids_fill(&kid, table0, table1, row_stride0, row_stride1, rows0, rows1, ids0, ids1, ids_stride_b, ids_offset,
+                    err_flag, DQ);
+  if (rc != PTREC_OK) return rc;
+  if (B == 0) return PTREC_OK;
+  return din_fwd_tc(q, q_stride, nullptr, 0, 0, lens, B, L, DQ, H1, H2, W1, b1, W2, b2, W3, b3, out, scores,
+                    (cudaStream_t)stream, &kid);
+}
+
+extern "C" int ptrec_din_attn_pool_bwd_ids(const float* q, int64_t q_stride, const float* table0, const float* table1,
+                                           int64_t row_stride0, int64_t row_stride1, int64_t rows0, int64_t rows1,
+                                           const int64_t* ids0, const int64_t* ids1, int64_t ids_stride_b,
+                                           int64_t ids_offset, const int32_t* lens, int64_t B, int32_t L, int32_t DQ,
+                                           int32_t H1, int32_t H2, const float* W1, const float* b1, const float* W2,
+                                           const float* b2, const float* W3, const float* b3, const float* g_pooled,
+                                           float* g_q, float* g_keys, int64_t gk_stride_b, int64_t gk_stride_l,
+                                           float* grad_params, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = din_check(q, table0, B, L, DQ, H1, H2, q_stride, 4, 4);
+  if (rc != PTREC_OK) return rc;
+  PTREC_CHECK_ARG(W1 && b1 && W2 && b2 && W3 && b3 && g_pooled && g_q && g_keys && grad_params && workspace, PTREC_EINVAL,
+                  "din_attn_pool_bwd_ids: null pointer");
+  PTREC_CHECK_ARG(aligned16(g_keys) && gk_stride_b % 4 == 0 && gk_stride_l % 4 == 0, PTREC_EALIGN,
+                  "din_attn_pool_bwd_ids: g_keys alignment");
+  PTREC_CHECK_ARG(workspace_bytes >= ptrec_din_attn_pool_bwd_workspace_bytes(B, DQ, H1, H2), PTREC_EWORKSPACE,
+                  "din_attn_pool_bwd_ids: workspace too small");
+  if (!(g_din_tc & 2)) return PTREC_EUNSUPPORTED;
+  DinKeyIds kid;
+  rc = din_ids_fill(&kid, table0, table1, row_stride0, row_stride1, rows0, rows1, ids0, ids1, ids_stride_b, ids_offset,
+                    nullptr, DQ);
+  if (rc != PTREC_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) {
+    PTREC_CUDA(cudaMemsetAsync(grad_params, 0, (size_t)ptrec_din_attn_pool_grad_floats(DQ, H1, H2) * sizeof(float), st));
+    return PTREC_OK;
+  }
+  float* partials = reinterpret_cast<float*>(workspace);
+  int n_rows = 0;
+  rc = din_bwd_tc(q, q_stride, nullptr, 0, 0, lens, B, L, DQ, H1, H2, W1, b1, W2, b2, W3, b3, g_pooled, g_q, g_keys,
+                  gk_stride_b, gk_stride_l, partials, &n_rows, st, &kid);
+  if (rc != PTREC_OK) return rc;
+  const int n = ptrec_din_attn_pool_grad_floats(DQ, H1, H2);
+  din_reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(partials, n_rows, n, grad_params);
+  PTREC_LAUNCH_CHECK("din_reduce_partials_kernel");
+  return PTREC_OK;
 }

@@ -20,6 +20,7 @@
 // i.e. 8 x 8 core matrices of 128 contiguous bytes, LBO = 128 (next core matrix along K), SBO = K / 8 * 128 (next 8 rows).
 #include <cuda_fp16.h>
 
+#include "din_keys.cuh"
 #include "tcgen05.cuh"
 
 namespace ptrec {
@@ -126,7 +127,7 @@ din_fwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
                   const int32_t* __restrict__ lens, int64_t B, int L, const float* __restrict__ W1,
                   const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
                   const float* __restrict__ W3, const float* __restrict__ b3, float* __restrict__ out,
-                  float* __restrict__ scores) {
+                  float* __restrict__ scores, const DinKeyIds kid) {
   using S = DinTcSmem<DQ, H1, H2>;
   constexpr int H2P = S::H2P;
   static_assert(DQ % 16 == 0 && H1 % 16 == 0 && H1 <= 128 && DQ <= 64, "MMA shape constraints");
@@ -241,7 +242,20 @@ din_fwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
       // ---- operand A of G1: this thread's key row (zeros past the end of the history) ----------------------------
       float kk[DQ];
       float kmax = 0.f;
-      if (t < n) {
+      if (t < n && kid.ids[0] != nullptr) {  // gather fused in: the two halves of the key are table rows
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const int64_t id = kid.ids[p][b * kid.ids_sb + kid.ids_off + l0 + t];
+          const bool ok = (uint64_t)id < (uint64_t)kid.rows[p];
+          if (!ok && kid.err != nullptr) *kid.err = 1;
+          const float* kp = kid.base[p] + (ok ? id : 0) * kid.stride[p];
+#pragma unroll
+          for (int x = 0; x < DQ / 2; x += 4) {
+            const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(kp + x)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            kk[p * (DQ / 2) + x] = v.x; kk[p * (DQ / 2) + x + 1] = v.y; kk[p * (DQ / 2) + x + 2] = v.z; kk[p * (DQ / 2) + x + 3] = v.w;
+          }
+        }
+      } else if (t < n) {
         const float* kp = keys + b * ksb + (int64_t)(l0 + t) * ksl;
 #pragma unroll
         for (int x = 0; x < DQ; x += 4) {
@@ -381,7 +395,8 @@ din_fwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
 template <int DQ, int H1, int H2>
 static int din_fwd_tc_launch(const float* q, int64_t qs, const float* keys, int64_t ksb, int64_t ksl, const int32_t* lens,
                              int64_t B, int L, const float* W1, const float* b1, const float* W2, const float* b2,
-                             const float* W3, const float* b3, float* out, float* scores, cudaStream_t st) {
+                             const float* W3, const float* b3, float* out, float* scores, cudaStream_t st,
+                             const DinKeyIds& kid) {
   const size_t smem = sizeof(DinTcSmem<DQ, H1, H2>) + 1024;
   PTREC_CUDA(cudaFuncSetAttribute(din_fwd_tc_kernel<DQ, H1, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148;
@@ -389,7 +404,7 @@ static int din_fwd_tc_launch(const float* q, int64_t qs, const float* keys, int6
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(B < (int64_t)sms * 2 ? B : (int64_t)sms * 2);  // two CTAs per SM (~100 KB of shared memory each)
   din_fwd_tc_kernel<DQ, H1, H2><<<grid, kTcPos, smem, st>>>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3,
-                                                             out, scores);
+                                                             out, scores, kid);
   PTREC_LAUNCH_CHECK("din_fwd_tc_kernel");
   return PTREC_OK;
 }
@@ -490,7 +505,7 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
                   const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
                   const float* __restrict__ W3, const float* __restrict__ b3, const float* __restrict__ g_pooled,
                   float* __restrict__ g_q, float* __restrict__ g_keys, int64_t gksb, int64_t gksl,
-                  float* __restrict__ partials) {
+                  float* __restrict__ partials, const DinKeyIds kid) {
   using S = DinTcBwdSmem<DQ, H1, H2>;
   constexpr int H2P = S::H2P, DQE = S::DQE, H1E = S::H1E;
   static_assert(DQ == 32 && H1 % 16 == 0 && H1E <= 128 && H1 + 1 <= kTcPos, "MMA shape / team split constraints");
@@ -630,7 +645,17 @@ din_bwd_tc_kernel(const float* __restrict__ q, int64_t q_stride, const float* __
       constexpr int kHalf = DQ / 2;
       float kk[kHalf];
       float kmax = 0.f, gpart = 0.f;
-      if (live) {
+      if (live && kid.ids[0] != nullptr) {  // gather fused in: team p reads its half from table p
+        const int64_t id = kid.ids[team][b * kid.ids_sb + kid.ids_off + l0 + r];
+        const bool ok = (uint64_t)id < (uint64_t)kid.rows[team];
+        if (!ok && kid.err != nullptr) *kid.err = 1;
+        const float* kp = kid.base[team] + (ok ? id : 0) * kid.stride[team];
+#pragma unroll
+        for (int x = 0; x < kHalf; x += 4) {
+          const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(kp + x)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          kk[x] = v.x; kk[x + 1] = v.y; kk[x + 2] = v.z; kk[x + 3] = v.w;
+        }
+      } else if (live) {
         const float* kp = keys + b * ksb + (int64_t)(l0 + r) * ksl + team * kHalf;
 #pragma unroll
         for (int x = 0; x < kHalf; x += 4) {
@@ -1009,12 +1034,13 @@ template <int DQ, int H1, int H2>
 static int din_bwd_tc_launch(const float* q, int64_t qs, const float* keys, int64_t ksb, int64_t ksl, const int32_t* lens,
                              int64_t B, int L, const float* W1, const float* b1, const float* W2, const float* b2,
                              const float* W3, const float* b3, const float* g_pooled, float* g_q, float* g_keys,
-                             int64_t gksb, int64_t gksl, float* partials, int* n_rows, cudaStream_t st) {
+                             int64_t gksb, int64_t gksl, float* partials, int* n_rows, cudaStream_t st,
+                             const DinKeyIds& kid) {
   const size_t smem = sizeof(DinTcBwdSmem<DQ, H1, H2>) + 1024;
   PTREC_CUDA(cudaFuncSetAttribute(din_bwd_tc_kernel<DQ, H1, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)((B + kTcBwdGroup - 1) / kTcBwdGroup);
   din_bwd_tc_kernel<DQ, H1, H2><<<grid, kTcBwdThreads, smem, st>>>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3,
-                                                             g_pooled, g_q, g_keys, gksb, gksl, partials);
+                                                             g_pooled, g_q, g_keys, gksb, gksl, partials, kid);
   PTREC_LAUNCH_CHECK("din_bwd_tc_kernel");
   *n_rows = grid;
   return PTREC_OK;
@@ -1024,28 +1050,34 @@ static int din_bwd_tc_launch(const float* q, int64_t qs, const float* keys, int6
 int din_bwd_tc(const float* q, int64_t qs, const float* keys, int64_t ksb, int64_t ksl, const int32_t* lens, int64_t B,
                int L, int DQ, int H1, int H2, const float* W1, const float* b1, const float* W2, const float* b2,
                const float* W3, const float* b3, const float* g_pooled, float* g_q, float* g_keys, int64_t gksb,
-               int64_t gksl, float* partials, int* n_rows, cudaStream_t st) {
+               int64_t gksl, float* partials, int* n_rows, cudaStream_t st, const DinKeyIds* kid_in) {
+  DinKeyIds kid;
+  memset(&kid, 0, sizeof(kid));
+  if (kid_in != nullptr) kid = *kid_in;
   if (DQ == 32 && H1 == 80 && H2 == 40)
     return din_bwd_tc_launch<32, 80, 40>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3, g_pooled, g_q, g_keys,
-                                         gksb, gksl, partials, n_rows, st);
+                                         gksb, gksl, partials, n_rows, st, kid);
   if (DQ == 32 && H1 == 64 && H2 == 32)
     return din_bwd_tc_launch<32, 64, 32>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3, g_pooled, g_q, g_keys,
-                                         gksb, gksl, partials, n_rows, st);
+                                         gksb, gksl, partials, n_rows, st, kid);
   return PTREC_EUNSUPPORTED;
 }
 
 // entry used by din_attn.cu's dispatcher: PTREC_OK, or PTREC_EUNSUPPORTED when this shape has no tensor-core build
 int din_fwd_tc(const float* q, int64_t qs, const float* keys, int64_t ksb, int64_t ksl, const int32_t* lens, int64_t B,
                int L, int DQ, int H1, int H2, const float* W1, const float* b1, const float* W2, const float* b2,
-               const float* W3, const float* b3, float* out, float* scores, cudaStream_t st) {
+               const float* W3, const float* b3, float* out, float* scores, cudaStream_t st, const DinKeyIds* kid_in) {
+  DinKeyIds kid;
+  memset(&kid, 0, sizeof(kid));
+  if (kid_in != nullptr) kid = *kid_in;
   if (DQ == 32 && H1 == 80 && H2 == 40)
-    return din_fwd_tc_launch<32, 80, 40>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3, out, scores, st);
+    return din_fwd_tc_launch<32, 80, 40>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3, out, scores, st, kid);
   if (DQ == 32 && H1 == 64 && H2 == 32)
-    return din_fwd_tc_launch<32, 64, 32>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3, out, scores, st);
+    return din_fwd_tc_launch<32, 64, 32>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3, out, scores, st, kid);
   if (DQ == 16 && H1 == 80 && H2 == 40)
-    return din_fwd_tc_launch<16, 80, 40>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3, out, scores, st);
+    return din_fwd_tc_launch<16, 80, 40>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3, out, scores, st, kid);
   if (DQ == 16 && H1 == 64 && H2 == 32)
-    return din_fwd_tc_launch<16, 64, 32>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3, out, scores, st);
+    return din_fwd_tc_launch<16, 64, 32>(q, qs, keys, ksb, ksl, lens, B, L, W1, b1, W2, b2, W3, b3, out, scores, st, kid);
   return PTREC_EUNSUPPORTED;
 }
 

@@ -235,11 +235,11 @@ class DIN(IModel):
         his_i, his_c = self.his_iid_column.get_feature_data(data), self.his_cid_column.get_feature_data(data)
         lens = self.his_len_column.get_feature_data(data)
         B, L = his_i.shape
-        flat = {self.iid_column.feature_name: torch.cat([cand_i.unsqueeze(1), his_i], dim=1).reshape(-1),
-                self.cid_column.feature_name: torch.cat([cand_c.unsqueeze(1), his_c], dim=1).reshape(-1)}
-        seq = self.seq_emb(flat).view(B, 1 + L, 2 * D)      # [B, 1+L, item||cate]
-        q, keys = seq[:, 0], seq[:, 1:]
-        pooled = self.attention(q, keys, lens)
+        # one lookup for candidate + history ([B, 1+L, item||cate]: q = row 0, keys = rows 1..); on the tensor-core
+        # builds K4 reads the history rows from the tables by id and only the candidate rows are gathered
+        q, pooled = self.seq_emb.lookup_attention(
+            {self.iid_column.feature_name: cand_i, self.cid_column.feature_name: cand_c},
+            {self.iid_column.feature_name: his_i, self.cid_column.feature_name: his_c}, lens, self.attention)
         user = self.user_emb(self.uid_column.get_feature_data(data))
         logit = self.out(self.mlp(torch.cat([user, q, pooled], dim=1))).squeeze(-1)
         target = self.label_column.get_feature_data(data)

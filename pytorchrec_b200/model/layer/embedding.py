@@ -15,6 +15,7 @@ owned by a ``pytorchrec_b200.optim`` sparse optimizer the row update happens ins
 ``[rows, D]`` tensor by default (``sparse=False`` — what the reference's models produce, so ``adam`` / ``adamw`` /
 ``sgd`` with weight decay keep working unchanged), a coalesced ``torch.sparse_coo_tensor`` with ``sparse=True``.
 """
+import os
 from typing import Dict, List, Optional, Sequence, Union
 
 import torch
@@ -214,6 +215,55 @@ class _FusedLookup(torch.autograd.Function):
             grad_out = grad_out.contiguous()
         grads = ctx.group.apply_backward(ctx.layout, ids, lens, bag_scale, ctx.batch, grad_out, ctx.shared)
         return (None, None, None, None, None, None, *grads)
+
+
+class _FusedLookupAttention(torch.autograd.Function):
+    """DIN's history lookup and attention pooling as ONE node: K4 reads the keys from the item / category tables by id
+    (no gathered [B, L, 2D] tensor), the candidate rows (the query) are the only rows gathered; the backward writes the
+    key gradients and the query gradient into one [B, 1 + L, 2D] buffer that feeds the same sort / dedup / fused update
+    as ``_FusedLookup`` (one update per table and step, as with the materialised lookup)."""
+
+    @staticmethod
+    def forward(ctx, group: EmbeddingGroup, layout, ids, shared, B, L, lens, blocks, *rest):
+        att, weights = rest[:6], rest[6:]
+        dev = ids.device
+        tables = group.table_set.refresh([w.detach() for w in weights])
+        batch = B * (1 + L)
+        if (shared is not None and "sort" not in shared and any(ctx.needs_input_grad[14:]) and _early_sort_enabled()):
+            _start_early_sort(tables, layout, ids, None, batch, shared)
+        F = len(blocks)
+        q_ids = ids.view(F, B, 1 + L)[:, :, 0].contiguous().view(-1)
+        q, _ = ops.gather_pool_fwd(tables, layout, q_ids, None, B, want_scale=False, err_flag=group.err_flag(dev))
+        # user column p: its ids are block blocks[p][0] of `ids`, its table is weights[blocks[p][1]]
+        tabs = [weights[t].detach() for _, t in blocks]
+        idl = [ids[k * batch:(k + 1) * batch] for k, _ in blocks]
+        params = tuple(p.detach() for p in att)
+        pooled = ops.din_attn_pool_fwd_ids(q, tabs, idl, 1 + L, 1, group.err_flag(dev), lens, L, params)
+        ctx.group, ctx.layout, ctx.shared, ctx.B, ctx.L, ctx.blocks = group, layout, shared, B, L, blocks
+        ctx.save_for_backward(ids, lens, q, *att, *weights)
+        return q, pooled
+
+    @staticmethod
+    def backward(ctx, g_q_out, g_pooled):
+        ids, lens, q = ctx.saved_tensors[:3]
+        att = ctx.saved_tensors[3:9]
+        weights = ctx.saved_tensors[9:]
+        B, L = ctx.B, ctx.L
+        DQ = q.shape[1]
+        batch = B * (1 + L)
+        if g_pooled is None:
+            g_pooled = torch.zeros_like(q)
+        g_seq = torch.empty(B, 1 + L, DQ, dtype=torch.float32, device=q.device)
+        tabs = [weights[t].detach() for _, t in ctx.blocks]
+        idl = [ids[k * batch:(k + 1) * batch] for k, _ in ctx.blocks]
+        g_q, gp = ops.din_attn_pool_bwd_ids(q, tabs, idl, 1 + L, 1, lens, L, tuple(p.detach() for p in att), g_pooled,
+                                            g_seq[:, 1:])
+        if g_q_out is not None:
+            torch.add(g_q, g_q_out, out=g_seq[:, 0])
+        else:
+            g_seq[:, 0] = g_q
+        grads = ctx.group.apply_backward(ctx.layout, ids, None, None, batch, g_seq.view(batch, DQ), ctx.shared)
+        return (None,) * 8 + tuple(gp) + tuple(grads)
 
 
 class EmbeddingTable(nn.Module):
@@ -416,3 +466,36 @@ class MultiTableEmbedding(nn.ModuleList):
     def check_index_errors(self) -> None:
         if self._group is not None:
             self._group.check_index_errors()
+
+    def lookup_attention(self, cand: Dict[str, Tensor], hist: Dict[str, Tensor], lens: Optional[Tensor], attention):
+        """DIN: ``seq = self({cand_f || hist_f}) -> q = seq[:, 0], keys = seq[:, 1:]; pooled = attention(q, keys, lens)``
+        with the history rows read by K4 straight from the tables (``_FusedLookupAttention``) where that build exists
+        (two fp32 tables of width D with 2D = 32, tensor-core forward and backward; ``PTREC_DIN_FUSED_GATHER=0``
+        switches it off), else the materialised lookup.  ``cand``: name -> [B] ids, ``hist``: name -> [B, L] ids (this
+        module's column names).  Returns (q [B, F*D], pooled [B, F*D])."""
+        names = list(self.feature_names)
+        first = cand[names[0]]
+        B, L = hist[names[0]].shape
+        flat = {n: torch.cat([cand[n].unsqueeze(1), hist[n]], dim=1).reshape(-1) for n in names}
+        fc = (attention.fc1, attention.fc2, attention.fc3)
+        fused = (first.is_cuda and len(names) == 2 and self.emb_size * 2 == 32 and len(set(self._table_of)) == 2
+                 and all(t.weight.dtype == torch.float32 for t in self.tables)
+                 and ops.din_ids_supported(2 * self.emb_size, fc[0].out_features, fc[1].out_features)
+                 and os.environ.get("PTREC_DIN_FUSED_GATHER", "1") != "0")
+        if not fused:
+            seq = self(flat).view(B, 1 + L, len(names) * self.emb_size)
+            q, keys = seq[:, 0], seq[:, 1:]
+            return q, attention(q, keys, lens)
+        if self._group is None:
+            self._group = EmbeddingGroup(self.tables, self.emb_size)
+        layout = self._layout_for((1,) * len(names))
+        ids = torch.cat([flat[names[i]].reshape(-1) for i in self._order]).long().contiguous()
+        shared = {"ids": ids, "lens": None}
+        for t in self.tables:
+            t._tag()
+        blocks = tuple((self._order.index(i), self._table_of[i]) for i in range(len(names)))
+        if lens is not None:
+            lens = lens.to(torch.int32).contiguous()
+        return _FusedLookupAttention.apply(self._group, layout, ids, shared, B, L, lens, blocks,
+                                           fc[0].weight, fc[0].bias, fc[1].weight, fc[1].bias, fc[2].weight, fc[2].bias,
+                                           *[t.weight for t in self.tables])

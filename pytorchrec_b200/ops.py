@@ -1154,6 +1154,61 @@ def din_attn_pool_bwd(q, keys, lens, params, g_pooled):
     return g_q, g_keys, (gW1.view(H1, 4 * DQ), gb1, gW2.view(H2, H1), gb2, gW3.view(1, H2), gb3)
 
 
+def _din_id_args(tables, ids, DQ):
+    t0, t1 = tables
+    i0, i1 = ids
+    for t in (t0, t1):
+        assert t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.shape[1] == DQ // 2
+    for i in (i0, i1):
+        assert i.dtype == torch.int64 and i.is_contiguous()
+    return (_ptr(t0), _ptr(t1), t0.stride(0), t1.stride(0), t0.shape[0], t1.shape[0], _ptr(i0), _ptr(i1))
+
+
+def din_ids_supported(DQ: int, H1: int, H2: int) -> bool:
+    """K4 reads its keys by id (no gathered [B, L, DQ] tensor) where forward AND backward have a tensor-core build."""
+    return _lib.load().ptrec_din_tc_enabled() == 3 and DQ == 32 and (H1, H2) in ((80, 40), (64, 32))
+
+
+def din_attn_pool_fwd_ids(q, tables, ids, ids_stride_b: int, ids_offset: int, err_flag, lens, L: int, params):
+    """``din_attn_pool_fwd`` with key (b, l) = [tables[0][ids[0][b * ids_stride_b + ids_offset + l]] | tables[1][...]]."""
+    lib = _lib.load()
+    _require_cuda(q, *tables, *ids, lens, *params)
+    W1, b1, W2, b2, W3, b3 = params
+    B, DQ = q.shape
+    H1, H2 = W1.shape[0], W2.shape[0]
+    if lens is not None:
+        lens = lens.to(torch.int32).contiguous()
+    out = torch.empty(B, DQ, dtype=torch.float32, device=q.device)
+    _lib.check(lib.ptrec_din_attn_pool_fwd_ids(_ptr(q), q.stride(0), *_din_id_args(tables, ids, DQ), ids_stride_b, ids_offset,
+                                               _ptr(err_flag), _ptr(lens), B, L, DQ, H1, H2, *[_ptr(p) for p in params],
+                                               _ptr(out), None, _stream(q.device)), "ptrec_din_attn_pool_fwd_ids")
+    return out
+
+
+def din_attn_pool_bwd_ids(q, tables, ids, ids_stride_b: int, ids_offset: int, lens, L: int, params, g_pooled, g_keys):
+    """Backward of the above; ``g_keys`` is a caller-provided [B, L, DQ] view (strides honoured) that receives the key
+    gradients as dense rows.  Returns (g_q, parameter gradients)."""
+    lib = _lib.load()
+    _require_cuda(q, g_pooled, g_keys, *tables, *ids, lens, *params)
+    W1, b1, W2, b2, W3, b3 = params
+    B, DQ = q.shape
+    H1, H2 = W1.shape[0], W2.shape[0]
+    if lens is not None:
+        lens = lens.to(torch.int32).contiguous()
+    g_pooled = g_pooled.contiguous()
+    g_q = torch.empty(B, DQ, dtype=torch.float32, device=q.device)
+    n = lib.ptrec_din_attn_pool_grad_floats(DQ, H1, H2)
+    flat = torch.empty(n, dtype=torch.float32, device=q.device)
+    ws = _workspace("din_bwd", lib.ptrec_din_attn_pool_bwd_workspace_bytes(B, DQ, H1, H2), q.device)
+    _lib.check(lib.ptrec_din_attn_pool_bwd_ids(_ptr(q), q.stride(0), *_din_id_args(tables, ids, DQ), ids_stride_b, ids_offset,
+                                               _ptr(lens), B, L, DQ, H1, H2, *[_ptr(p) for p in params], _ptr(g_pooled),
+                                               _ptr(g_q), _ptr(g_keys), g_keys.stride(0), g_keys.stride(1), _ptr(flat),
+                                               _ptr(ws), ws.numel(), _stream(q.device)), "ptrec_din_attn_pool_bwd_ids")
+    sizes = [H1 * 4 * DQ, H1, H2 * H1, H2, H2, 1]
+    gW1, gb1, gW2, gb2, gW3, gb3 = torch.split(flat, sizes)
+    return g_q, (gW1.view(H1, 4 * DQ), gb1, gW2.view(H2, H1), gb2, gW3.view(1, H2), gb3)
+
+
 class _DinAttnPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, keys, lens, W1, b1, W2, b2, W3, b3):

@@ -880,3 +880,42 @@ def test_bce_logits_mean_matches_torch(n):
     assert again.item() == loss.item()
     if n > 2:
         assert ops.bce_logits_mean(x.to(DEV)[::2], t.to(DEV)[::2]) is None   # non-contiguous: the caller uses the module
+
+
+@pytest.mark.parametrize("B,L,hidden,interleaved", [(37, 100, (80, 40), False), (300, 50, (64, 32), True), (5, 130, (80, 40), True)])
+def test_din_keys_by_id_equal_gathered_keys(B, L, hidden, interleaved):
+    """K4 with the gather fused in: reading key (b, l) from the two tables by id gives bit-identical outputs and gradients
+    to the same kernels fed with the gathered [B, L, DQ] tensor (same arithmetic, only the address of the rows differs);
+    tables interleaved with optimizer state (row pitch 2D) included; an id out of range raises the error word."""
+    lib = _lib.load()
+    if lib.ptrec_din_tc_enabled() != 3:
+        pytest.skip("tensor-core K4 builds switched off")
+    D, DQ = 16, 32
+    H1, H2 = hidden
+    g = torch.Generator().manual_seed(B * L)
+    rows = (1000, 57)
+    store = [torch.randn(r, 2 * D if interleaved else D, generator=g).to(DEV) for r in rows]
+    tabs = [st[:, :D] for st in store]
+    ids = [torch.randint(0, r, (B, 1 + L), generator=g).to(DEV) for r in rows]
+    lens = torch.randint(0, L + 1, (B,), generator=g).to(DEV)
+    lens[0] = L
+    params = [(torch.randn(sh, generator=g) * 0.2).to(DEV) for sh in ((H1, 4 * DQ), (H1,), (H2, H1), (H2,), (1, H2), (1,))]
+    seq = torch.cat([tabs[0][ids[0]], tabs[1][ids[1]]], dim=2)           # [B, 1 + L, DQ]
+    q, keys = seq[:, 0].contiguous(), seq[:, 1:].contiguous()
+    gp = torch.randn(B, DQ, generator=g).to(DEV)
+    out_ref, _ = ops.din_attn_pool_fwd(q, keys, lens, params)
+    gq_ref, gk_ref, gpar_ref = ops.din_attn_pool_bwd(q, keys, lens, params, gp)
+    flat_ids = [i.reshape(-1).contiguous() for i in ids]
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out = ops.din_attn_pool_fwd_ids(q, tabs, flat_ids, 1 + L, 1, err, lens, L, params)
+    assert torch.equal(out, out_ref) and int(err.item()) == 0
+    g_seq = torch.full((B, 1 + L, DQ), 7.0, device=DEV)
+    gq, gpar = ops.din_attn_pool_bwd_ids(q, tabs, flat_ids, 1 + L, 1, lens, L, params, gp, g_seq[:, 1:])
+    assert torch.equal(gq, gq_ref) and torch.equal(g_seq[:, 1:], gk_ref)
+    assert (g_seq[:, 0] == 7.0).all(), "row 0 of the buffer belongs to the caller"
+    for a, b in zip(gpar, gpar_ref):
+        assert torch.equal(a, b)
+    bad = [i.clone() for i in flat_ids]
+    bad[1][1] = rows[1]                                                   # sample 0, position 0 (< lens[0])
+    ops.din_attn_pool_fwd_ids(q, tabs, bad, 1 + L, 1, err, lens, L, params)
+    assert int(err.item()) == 1

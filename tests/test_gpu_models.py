@@ -504,6 +504,28 @@ def _din_batch(cols, B, L, seed):
             "label": torch.from_numpy(rng.integers(0, 2, size=B))}
 
 
+def test_din_fused_key_gather_trains_identically(monkeypatch):
+    """DIN with K4 reading the history rows from the tables by id (default) == DIN with the materialised [B, 1+L, 2D]
+    lookup (PTREC_DIN_FUSED_GATHER=0): same losses and bit-identical weights after Adagrad steps, and the fused path
+    launches no gather over the B * (1 + L) slots."""
+    from pytorchrec_b200.model import DIN
+    c = _din_setup()
+    args = (c["uid"], c["iid"], c["cid"], c["his_iid"], c["his_cid"], c["his_len"], c["label"])
+
+    def run(fused):
+        monkeypatch.setenv("PTREC_DIN_FUSED_GATHER", "1" if fused else "0")
+        m = DIN(*args, emb_size=16, layers=[64, 32], random_seed=11)
+        m.compile(SparseAdagrad(m.get_parameters(), lr=0.02, eps=1e-6), torch.nn.BCEWithLogitsLoss(), [LogLoss()], DEV)
+        losses = [m.train_step(_din_batch(c, 200, 100, seed=40 + s))["loss"].item() for s in range(4)]
+        return losses, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+
+    l1, sd1 = run(True)
+    l0, sd0 = run(False)
+    assert l1 == l0, (l1, l0)
+    for k in sd1:
+        assert torch.equal(sd1[k], sd0[k]), k
+
+
 @pytest.mark.parametrize("opt_name", ["sgd", "adagrad"])
 def test_din_matches_oracle_twin(opt_name):
     from pytorchrec_b200.model import DIN
