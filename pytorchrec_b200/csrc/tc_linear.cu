@@ -661,11 +661,14 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
   constexpr uint32_t k2Tile = 128 * BK * 2;     // any plane tile: 128 rows (or 2 boxes of 64 mn) x BK 16-bit elements
   constexpr uint32_t k2StageBytes = 2 * NP * k2Tile; // A planes, then B planes (B = this CTA's half)
   // NP = 1 (K5): one plane leaves TMEM columns [256, 512) free, so the accumulator is double-buffered (the MMAs of tile
-  // i + 1 run under the epilogue of tile i), and every epilogue warp owns 8 KB: the four 32 x 32 bf16 boxes of its two
-  // epilogue operands (both 32-column chunks), fetched by TMA while the tile's MMAs run and overwritten in place by the
-  // two results, which leave by TMA stores — no per-thread global access in the epilogue.
+  // i + 1 run under the epilogue of tile i).  Every epilogue warp's 4 KB staging holds the two 32 x 32 bf16 boxes of its
+  // epilogue operands for ONE 32-column chunk, fetched by TMA (chunk 0 while the tile's MMAs run, chunk 1 once chunk 0's
+  // stores have read the boxes) and overwritten in place by the two results, which leave by TMA stores: no per-thread
+  // global access in the epilogue.  (Boxes for both chunks — 8 KB per warp — left 6 operand stages = 96 KB in flight per
+  // SM, and the mainloop ran at the rate that many bytes cover the L2 / HBM latency: 18k cycles per tile for 6k cycles
+  // of MMAs; the exposed fetch of chunk 1 hides under the next tile's mainloop.)
   constexpr int kAcc = NP == 1 ? 2 : 1;
-  constexpr uint32_t kWarpStg = NP == 1 ? 8192u : 4096u;
+  constexpr uint32_t kWarpStg = 4096u;
   constexpr uint32_t kStaging = k2EpiWarps * kWarpStg;
   static_assert(kStaging >= k2Staging, "staging");
   constexpr int k2Stages = (int)((k2StageBudget + k2Staging - kStaging) / k2StageBytes);
@@ -860,20 +863,18 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
       }
       const int row = m0 + r, col0 = n0 + grp * 64;
       const bool live = col0 < n_end;
-      if (dcn && live) {
-        // this tile's epilogue operands: boxes of 32 rows x 32 columns (2 KB), chunk cl at stg + cl * 4096 (dp0) and
-        // + 2048 (dp1); requested before the accumulator is waited for.  The previous tile's stores have read the boxes.
+      // a chunk's epilogue operands: boxes of 32 rows x 32 columns (2 KB), dp0 at stg, dp1 at stg + 2048, requested once
+      // the previous stores have read the boxes (loads of clipped boxes still deliver every byte)
+      auto fetch_operands = [&](int cl) {
         if (lane == 0) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          const int nch = col0 + 32 < n_end ? 2 : 1;
-          mbar_arrive_expect_tx(&in_bar[e], (uint32_t)nch * 4096u);  // loads of clipped boxes still deliver every byte
-          for (int cl = 0; cl < nch; ++cl) {
-            tma_load_3d(stg + cl * 4096, &maps.r0, col0 + cl * 32, m0 + q * 32, 0, &in_bar[e]);
-            tma_load_3d(stg + cl * 4096 + 2048, &maps.r1, col0 + cl * 32, m0 + q * 32, 0, &in_bar[e]);
-          }
+          mbar_arrive_expect_tx(&in_bar[e], 4096u);
+          tma_load_3d(stg, &maps.r0, col0 + cl * 32, m0 + q * 32, 0, &in_bar[e]);
+          tma_load_3d(stg + 2048, &maps.r1, col0 + cl * 32, m0 + q * 32, 0, &in_bar[e]);
         }
         __syncwarp();
-      }
+      };
+      if (dcn && live) fetch_operands(0);  // before the accumulator is waited for
       uint2 mw = make_uint2(0xffffffffu, 0xffffffffu);
       if (NP == 2 && ep.mask_in != nullptr && live && row < M)  // requested before the accumulator is waited for
         mw = *reinterpret_cast<const uint2*>(ep.mask_in + (int64_t)row * ep.mask_ld + (col0 >> 5));
@@ -948,8 +949,8 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
             // SWIZZLE_64B: 16-byte chunk g of row l at g ^ ((l >> 1) & 3)) is read 8 columns at a time and overwritten
             // by the two bf16 results; rows / columns outside the matrices were zero-filled by the loads and are
             // clipped by the stores
-            unsigned char* box = stg + cl * 4096;
-            if (cl == 0) mbar_wait(&in_bar[e], (nin++) & 1);
+            unsigned char* box = stg;
+            mbar_wait(&in_bar[e], (nin++) & 1);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const int o = lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4);
@@ -984,6 +985,7 @@ gemm_split3_2sm_kernel(const __grid_constant__ LinMaps maps, int M, int N, int K
               if (ep.dcn_o1) tma_store_3d(&maps.q, box + 2048, cc0, m0 + q * 32, 0);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+            if (cl == 0 && cc0 + 32 < n_end) fetch_operands(1);
           } else if (ep.out != nullptr) {
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the box's last store has read it
             __syncwarp();
