@@ -375,10 +375,16 @@ class IModel(Module, ABC):
         prediction, target = self(data)
         loss = self._apply_loss(prediction, target)
         self.compiled_optimizers.zero_grad()
-        loss.backward()
+        from .layer import dense as _dense
+        _dense._DEFER_JOIN[0] = loss.is_cuda   # side-stream weight gradients are joined below, not inside backward()
+        try:
+            loss.backward()
+        finally:
+            _dense._DEFER_JOIN[0] = False
         if loss.is_cuda:
             from .layer.embedding import join_aux_streams
-            join_aux_streams(loss.device)   # lookups placed on the aux stream update their tables there
+            # lookups placed on the aux stream update their tables there; the tower's weight gradients run on theirs
+            join_aux_streams(loss.device)
         self._before_optimizer_step()
         self.compiled_optimizers.step(closure=None)
         return loss

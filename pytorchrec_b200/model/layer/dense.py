@@ -180,6 +180,22 @@ class _TowerScales:
 
 
 _W_STREAMS = {}   # device -> side stream of the ahead-of-time weight splits
+_G_STREAMS = {}   # device -> side stream of the tower's weight-gradient GEMMs
+_DEFER_JOIN = [False]   # True inside IModel's train step: the join happens once, before the optimizer step
+
+
+def _wgrad_stream(dev):
+    """The fused tower's weight-gradient GEMMs (and their split-K reductions) feed nothing but the optimizer, so they run
+    on a side stream beside the input-gradient chain, whose result the rest of the backward (head, embedding update)
+    waits for; ``join_aux_streams`` (IModel, between backward and the optimizer step) joins it.  ``PTREC_WGRAD_STREAM=0``
+    keeps them on the main stream."""
+    import os
+    if os.environ.get("PTREC_WGRAD_STREAM", "1") == "0":
+        return None
+    s = _G_STREAMS.get(dev)
+    if s is None:
+        s = _G_STREAMS[dev] = torch.cuda.Stream(dev)
+    return s
 
 
 class _TowerCall:
@@ -243,6 +259,7 @@ class _TcMLP(torch.autograd.Function):
             mlp._last_masks = list(masks)
         ctx.scales = sl
         ctx.call = call
+        ctx.params = params if any_grad else None
         ctx.dims = [(params[2 * l].shape[0], params[2 * l].shape[1]) for l in range(L)]
         ctx.has_bias = [params[2 * l + 1] is not None for l in range(L)]
         if any_grad:
@@ -273,9 +290,29 @@ class _TcMLP(torch.autograd.Function):
             pg, _, db = ops.tc_split2h_prescaled(gy, sc(sl.i_g(L - 1)), sl.max_word(sl.i_g(L - 1)), relu_ref=y,
                                                  want_colsum=ctx.has_bias[L - 1] and need[3 + 2 * (L - 1) + 1])
         dx = None
+        # weight gradients on a side stream — only when autograd will adopt them as fresh .grad tensors (an existing
+        # .grad would be accumulated into on the main stream, without waiting for the side stream)
+        side = None
+        if gy.is_cuda and all(p is None or p.grad is None for p in (ctx.params or ())):
+            side = _wgrad_stream(gy.device)
+        if side is not None:
+            main = torch.cuda.current_stream(gy.device)
+            if _DEFER_JOIN[0]:
+                from .embedding import register_join_stream
+                register_join_stream(gy.device, side)
         for l in range(L - 1, -1, -1):
             N, K = ctx.dims[l]
             pg_prev = db_prev = None
+            if need[3 + 2 * l] and side is not None:   # g^T x  [N, K], forked before this layer's input-gradient GEMM
+                side.wait_stream(main)       # pg of this layer (and, the first time, everything before the backward)
+                with torch.cuda.stream(side):
+                    dw = ops.tc_gemm_split2h_tn(pg, sc(sl.i_g(l)), N, acts[l], sc(sl.i_in(l)), K)
+                    dw = dw if dw.is_contiguous() else dw.contiguous()
+                pg.record_stream(side)
+                acts[l].record_stream(side)
+                cs.record_stream(side)
+                dw.record_stream(main)       # consumed by the optimizer on the main stream after the join
+                grads[2 * l] = dw
             if l > 0:    # g W, masked by the ReLU of layer l - 1, as planes + bias gradient of layer l - 1
                 _, pg_prev, _, db_prev = ops.tc_gemm_split2h_fused(
                     pg, sc(sl.i_g(l)), pwts[l], sc(sl.i_w(l)), N, want_out=False, out_scale=sc(sl.i_g(l - 1)),
@@ -283,11 +320,13 @@ class _TcMLP(torch.autograd.Function):
                     max_out=sl.max_word(sl.i_g(l - 1)))
             elif need[0]:
                 dx, _, _, _ = ops.tc_gemm_split2h_fused(pg, sc(sl.i_g(0)), pwts[0], sc(sl.i_w(0)), N)
-            if need[3 + 2 * l]:
+            if need[3 + 2 * l] and side is None:
                 dw = ops.tc_gemm_split2h_tn(pg, sc(sl.i_g(l)), N, acts[l], sc(sl.i_in(l)), K)   # g^T x  [N, K]
                 grads[2 * l] = dw if dw.is_contiguous() else dw.contiguous()
             grads[2 * l + 1] = db
             pg, db = pg_prev, db_prev
+        if side is not None and not _DEFER_JOIN[0]:
+            main.wait_stream(side)   # a caller that reads .grad right after backward() (no IModel step around it)
         sl.bwd_ready = True
         return (dx, None, None, *grads)
 

@@ -161,10 +161,24 @@ class aux_stream:
                     t.record_stream(self.main)
 
 
+_JOIN_STREAMS: Dict[torch.device, list] = {}   # other side streams forked since the last join (dense.py: weight gradients)
+
+
+def register_join_stream(device, stream) -> None:
+    """``stream`` was forked from the current stream during this step's backward: ``join_aux_streams`` joins it."""
+    lst = _JOIN_STREAMS.setdefault(torch.device(device), [])
+    if all(s is not stream for s in lst):
+        lst.append(stream)
+
+
 def join_aux_streams(device) -> None:
-    """Make the current stream wait for whatever the aux stream still runs (a backward that autograd placed there):
-    called by ``IModel`` between ``backward()`` and ``optimizer.step()``."""
-    if device is None or not _AUX_USED.pop(torch.device(device), False):
+    """Make the current stream wait for whatever the side streams still run (a backward that autograd placed on the aux
+    stream, the tower's weight-gradient GEMMs): called by ``IModel`` between ``backward()`` and ``optimizer.step()``."""
+    if device is None:
+        return
+    for s in _JOIN_STREAMS.pop(torch.device(device), []):
+        torch.cuda.current_stream(device).wait_stream(s)
+    if not _AUX_USED.pop(torch.device(device), False):
         return   # nothing forked in this step (waiting on a stream outside a running graph capture would invalidate it)
     side = _AUX_STREAMS.get(torch.device(device))
     if side is not None:
