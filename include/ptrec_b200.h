@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTREC_ABI_VERSION 25
+#define PTREC_ABI_VERSION 26
 
 /* error codes */
 #define PTREC_OK 0
@@ -105,6 +105,12 @@ typedef struct ptrec_optim_args {
 int ptrec_abi_version(void);
 const char* ptrec_last_error(void); /* thread-local, valid until the next failing call */
 int64_t ptrec_launch_count(void);   /* kernels launched by this library since load (process-wide) */
+/* Gradient-finalising reductions off the critical path: while a stream is set, the entry points that end in a reduction
+ * of per-CTA partials into a bias / weight-vector gradient (ptrec_tc_gemm_split2h_fused with colsum, ptrec_rowdot_bwd_h2,
+ * ptrec_fm_head_bwd) launch that reduction on it, behind an event recorded on the producer's stream.  The caller joins the
+ * stream before it reads those gradients and gives every call in flight its own workspace.  NULL (default): reductions
+ * follow their producer on its stream. */
+void ptrec_set_reduce_stream(void* stream);
 /* cudaLimitMaxL2FetchGranularity of the current device (32 / 64 / 128 bytes): random row reads narrower
  * than the limit over-fetch from HBM.  Affects the whole device context; the caller decides. */
 int ptrec_set_l2_fetch_granularity(int32_t bytes);

@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libptrec_b200.so")
 
-ABI_VERSION = 25
+ABI_VERSION = 26
 
 # enums (mirror include/ptrec_b200.h)
 F32, BF16 = 0, 1
@@ -115,6 +115,7 @@ PROTOTYPES = {
                                             c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32]
                                     + [c_void_p] * 6 + [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
                                                         c_size_t, c_void_p]),
+    "ptrec_set_reduce_stream": (None, [c_void_p]),
     "ptrec_dcn_head_fwd": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "ptrec_dcn_head_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -20,6 +20,36 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
+static std::atomic<cudaStream_t> g_reduce_stream{nullptr};
+void set_reduce_stream(cudaStream_t s) { g_reduce_stream.store(s, std::memory_order_relaxed); }
+
+cudaStream_t reduce_stream_after(cudaStream_t producer) {
+  cudaStream_t rs = g_reduce_stream.load(std::memory_order_relaxed);
+  if (rs == nullptr || rs == producer) return producer;
+  // a small ring of timing-less events: an event may be re-recorded while an older wait on it is still pending (the
+  // wait captured the record it followed)
+  constexpr int kEvents = 32;
+  static cudaEvent_t ring[kEvents];
+  static std::atomic<int> made{0}, next{0};
+  if (made.load(std::memory_order_acquire) == 0) {
+    int expected = 0;
+    if (made.compare_exchange_strong(expected, -1)) {
+      bool ok = true;
+      for (int i = 0; i < kEvents; ++i) ok = ok && cudaEventCreateWithFlags(&ring[i], cudaEventDisableTiming) == cudaSuccess;
+      made.store(ok ? 1 : -2, std::memory_order_release);
+    }
+  }
+  while (made.load(std::memory_order_acquire) == -1) {
+  }
+  if (made.load(std::memory_order_acquire) != 1) return producer;
+  cudaEvent_t ev = ring[next.fetch_add(1, std::memory_order_relaxed) % kEvents];
+  if (cudaEventRecord(ev, producer) != cudaSuccess || cudaStreamWaitEvent(rs, ev, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return producer;
+  }
+  return rs;
+}
+
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
   return PTREC_ECUDA;
@@ -28,6 +58,8 @@ int cuda_fail(cudaError_t e, const char* what) {
 }  // namespace ptrec
 
 extern "C" int ptrec_abi_version(void) { return PTREC_ABI_VERSION; }
+namespace ptrec { void set_reduce_stream(cudaStream_t s); }
+extern "C" void ptrec_set_reduce_stream(void* stream) { ptrec::set_reduce_stream((cudaStream_t)stream); }
 extern "C" const char* ptrec_last_error(void) { return ptrec::g_err; }
 namespace ptrec { long long launches(); }
 extern "C" int64_t ptrec_launch_count(void) { return (int64_t)ptrec::launches(); }

@@ -32,6 +32,12 @@ void count_launch();  // every kernel launch of this library is counted (ptrec_l
     if (_e != cudaSuccess) return ::ptrec::cuda_fail(_e, #call); \
   } while (0)
 
+// Gradient-finalising reductions (per-CTA partials -> bias / weight-vector gradients) feed nothing but the optimizer.
+// With ptrec_set_reduce_stream(s) set, the entry points that end in such a reduction launch it on `s` behind an event
+// recorded on the producer's stream, so it leaves the backward's critical path; the caller joins `s` before the
+// optimizer step and gives every call in flight its own partial buffer.  Returns `producer` when no stream is set.
+cudaStream_t reduce_stream_after(cudaStream_t producer);
+
 #define PTREC_LAUNCH_CHECK(name)                                          \
   do {                                                                    \
     ::ptrec::count_launch();                                              \

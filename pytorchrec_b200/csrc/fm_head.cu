@@ -439,7 +439,8 @@ extern "C" int ptrec_fm_head_bwd(const float* v, int64_t v_row_stride, const flo
 #undef PTREC_HEAD_BWD
   PTREC_LAUNCH_CHECK("fm_head_bwd_kernel");
   if (need_part) {
-    head_reduce_kernel<<<(unsigned)ceil_div(nd + 1, 32), 1024, 0, st>>>(part, grid, nd + 1, grad_wd, nd, grad_bias);
+    cudaStream_t rs = reduce_stream_after(st);
+    head_reduce_kernel<<<(unsigned)ceil_div(nd + 1, 32), 1024, 0, rs>>>(part, grid, nd + 1, grad_wd, nd, grad_bias);
     PTREC_LAUNCH_CHECK("head_reduce_kernel");
   }
   return PTREC_OK;
@@ -511,12 +512,13 @@ extern "C" int ptrec_rowdot_bwd_h2(const float* h, int64_t h_row_stride, const f
                                                                  planes_ld, B * planes_ld, scale,
                                                                  reinterpret_cast<uint32_t*>(max_out), cs_part);
   PTREC_LAUNCH_CHECK("rowdot_bwd_kernel");
+  cudaStream_t rs = (grad_w || colsum) ? reduce_stream_after(st) : st;
   if (grad_w) {
-    head_reduce_kernel<<<(unsigned)ceil_div(H, 32), 1024, 0, st>>>(part, grid, H, grad_w, H, nullptr);
+    head_reduce_kernel<<<(unsigned)ceil_div(H, 32), 1024, 0, rs>>>(part, grid, H, grad_w, H, nullptr);
     PTREC_LAUNCH_CHECK("head_reduce_kernel");
   }
   if (colsum) {
-    head_reduce_kernel<<<(unsigned)ceil_div(H, 32), 1024, 0, st>>>(cs_part, grid, H, colsum, H, nullptr);
+    head_reduce_kernel<<<(unsigned)ceil_div(H, 32), 1024, 0, rs>>>(cs_part, grid, H, colsum, H, nullptr);
     PTREC_LAUNCH_CHECK("head_reduce_kernel");
   }
   return PTREC_OK;

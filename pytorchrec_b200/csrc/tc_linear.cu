@@ -1575,7 +1575,8 @@ static int gemm_split_impl(int np, bool mn_major, const void* a_planes, const fl
     const int rc2 = gemm_launch<2>(false, true, false, bk, sms, maps, M, N, K, ep, out, st);
     if (rc2 != PTREC_OK) return rc2;
     if (fu->colsum) {
-      colsum_reduce_kernel<<<(unsigned)ceil_div(N, (int64_t)32), 256, 0, st>>>(ep.colsum_part, (int)ceil_div(M, (int64_t)32),
+      cudaStream_t rs = reduce_stream_after(st);
+      colsum_reduce_kernel<<<(unsigned)ceil_div(N, (int64_t)32), 256, 0, rs>>>(ep.colsum_part, (int)ceil_div(M, (int64_t)32),
                                                                                 (int)N, fu->colsum);
       PTREC_LAUNCH_CHECK("colsum_reduce_kernel");
     }

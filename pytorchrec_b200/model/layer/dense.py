@@ -184,6 +184,44 @@ _G_STREAMS = {}   # device -> side stream of the tower's weight-gradient GEMMs
 _DEFER_JOIN = [False]   # True inside IModel's train step: the join happens once, before the optimizer step
 
 
+class side_reductions:
+    """``with side_reductions(device) as sr:`` around ONE library call that ends in a gradient-finalising reduction (bias /
+    weight-vector gradients from per-CTA partials: ``tc_gemm_split2h_fused(want_colsum=True)``, ``rowdot_bwd_h2``,
+    ``fm_head_bwd``): inside an ``IModel`` train step the reduction runs on the weight-gradient side stream behind an event
+    on the producer's stream (``ptrec_set_reduce_stream``) and leaves the backward's critical path; ``sr.adopt(t, ...)``
+    for the tensors it writes.  Every call in flight needs its own partial buffer (``ws_tag``).  Elsewhere: a no-op.
+    ``PTREC_REDUCE_STREAM=0`` switches it off."""
+
+    def __init__(self, device):
+        self.device, self.on, self.side = device, False, None
+
+    def __enter__(self):
+        import os
+        dev = self.device
+        if (_DEFER_JOIN[0] and dev is not None and torch.device(dev).type == "cuda"
+                and os.environ.get("PTREC_REDUCE_STREAM", "1") != "0"):
+            side = _wgrad_stream(dev)
+            if side is not None:
+                from ... import _lib
+                from .embedding import register_join_stream
+                register_join_stream(dev, side)
+                _lib.load().ptrec_set_reduce_stream(side.cuda_stream)
+                self.on, self.side = True, side
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            from ... import _lib
+            _lib.load().ptrec_set_reduce_stream(None)
+        return False
+
+    def adopt(self, *tensors) -> None:
+        if self.on:
+            for t in tensors:
+                if t is not None:
+                    t.record_stream(self.side)
+
+
 def _wgrad_stream(dev):
     """The fused tower's weight-gradient GEMMs (and their split-K reductions) feed nothing but the optimizer, so they run
     on a side stream beside the input-gradient chain, whose result the rest of the backward (head, embedding update)
@@ -314,10 +352,12 @@ class _TcMLP(torch.autograd.Function):
                 dw.record_stream(main)       # consumed by the optimizer on the main stream after the join
                 grads[2 * l] = dw
             if l > 0:    # g W, masked by the ReLU of layer l - 1, as planes + bias gradient of layer l - 1
-                _, pg_prev, _, db_prev = ops.tc_gemm_split2h_fused(
-                    pg, sc(sl.i_g(l)), pwts[l], sc(sl.i_w(l)), N, want_out=False, out_scale=sc(sl.i_g(l - 1)),
-                    mask_in=masks[l - 1], want_colsum=ctx.has_bias[l - 1] and need[3 + 2 * (l - 1) + 1],
-                    max_out=sl.max_word(sl.i_g(l - 1)))
+                with side_reductions(gy.device) as sr:   # the column-sum reduce (bias gradient) leaves the chain
+                    _, pg_prev, _, db_prev = ops.tc_gemm_split2h_fused(
+                        pg, sc(sl.i_g(l)), pwts[l], sc(sl.i_w(l)), N, want_out=False, out_scale=sc(sl.i_g(l - 1)),
+                        mask_in=masks[l - 1], want_colsum=ctx.has_bias[l - 1] and need[3 + 2 * (l - 1) + 1],
+                        max_out=sl.max_word(sl.i_g(l - 1)), ws_tag=str(l) if sr.on else "")
+                    sr.adopt(db_prev)
             elif need[0]:
                 dx, _, _, _ = ops.tc_gemm_split2h_fused(pg, sc(sl.i_g(0)), pwts[0], sc(sl.i_w(0)), N)
             if need[3 + 2 * l] and side is None:

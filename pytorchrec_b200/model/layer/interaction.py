@@ -56,8 +56,11 @@ class _FMHead(torch.autograd.Function):
                 buf = g_deep_in.new_empty(g_deep_in.shape[0], (g_deep_in.shape[1] + 3) // 4 * 4)
                 buf[:, :g_deep_in.shape[1]] = g_deep_in
                 g_deep_in = buf[:, :g_deep_in.shape[1]]
-        gv, gw1, gwd, gb = ops.fm_head_bwd(v2d, x, wd, g_logit.contiguous(), g_deep_in, F, D, want_w1=need[1],
-                                           want_wd=need[3] and wd is not None, want_bias=need[4])
+        from .dense import side_reductions
+        with side_reductions(g_logit.device) as sr:   # the partial reduction (grad wd, grad bias) leaves the chain
+            gv, gw1, gwd, gb = ops.fm_head_bwd(v2d, x, wd, g_logit.contiguous(), g_deep_in, F, D, want_w1=need[1],
+                                               want_wd=need[3] and wd is not None, want_bias=need[4])
+            sr.adopt(gwd, gb)
         return gv if need[0] else None, gw1, None, gwd, gb, None, None, None, None, None
 
 
@@ -79,8 +82,11 @@ class _RowDot(torch.autograd.Function):
         if call is not None and ctx.needs_input_grad[0]:
             sl = call.mlp._scales
             i = sl.i_g(sl.L - 1)
-            planes, db, gw = ops.rowdot_bwd_h2(h, w, g.contiguous(), call.cs[i:i + 1], sl.max_word(i), True,
-                                               ctx.needs_input_grad[1])
+            from .dense import side_reductions
+            with side_reductions(g.device) as sr:   # the two partial reductions (last bias gradient, grad w) leave the chain
+                planes, db, gw = ops.rowdot_bwd_h2(h, w, g.contiguous(), call.cs[i:i + 1], sl.max_word(i), True,
+                                                   ctx.needs_input_grad[1])
+                sr.adopt(db, gw)
             call.grad = (planes, db)
             return h.new_empty(h.shape), gw, None   # not materialised: the tower's backward reads call.grad
         gh, gw = ops.rowdot_bwd(h, w, g.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])

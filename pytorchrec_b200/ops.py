@@ -877,7 +877,8 @@ def mask_words(n: int) -> int:
 def tc_gemm_split2h_fused(a_planes: torch.Tensor, scale_a: torch.Tensor, b_planes: torch.Tensor, scale_b: torch.Tensor,
                           K: int, bias: Optional[torch.Tensor] = None, relu: bool = False, want_out: bool = True,
                           out_scale: Optional[torch.Tensor] = None, mask_in: Optional[torch.Tensor] = None,
-                          want_mask: bool = False, want_colsum: bool = False, max_out: Optional[torch.Tensor] = None):
+                          want_mask: bool = False, want_colsum: bool = False, max_out: Optional[torch.Tensor] = None,
+                          ws_tag: str = ""):
     """A[M, K] B[N, K]^T (+ bias) (ReLU) (* mask_in) on the CTA-pair fp16 x 2 kernel, handed over in the consumer's
     format.  Returns (out fp32 [M, N] or None, planes [2, M, pad16(N)] fp16 split with ``out_scale`` or None,
     mask int32 [M, mask_words(N)] of the positive entries or None, colsum [N] or None)."""
@@ -895,7 +896,8 @@ def tc_gemm_split2h_fused(a_planes: torch.Tensor, scale_a: torch.Tensor, b_plane
     if mask_in is not None:
         assert mask_in.dtype == torch.int32 and tuple(mask_in.shape) == (M, mw) and mask_in.is_contiguous()
     colsum = torch.empty(N, dtype=torch.float32, device=dev) if want_colsum else None
-    ws = _workspace("tc_gemm_fused", lib.ptrec_tc_gemm_fused_workspace_bytes(M, N), dev) if want_colsum else None
+    # ws_tag: calls whose column-sum reduce may still be in flight on another stream keep separate partial buffers
+    ws = _workspace("tc_gemm_fused" + ws_tag, lib.ptrec_tc_gemm_fused_workspace_bytes(M, N), dev) if want_colsum else None
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
     _lib.check(lib.ptrec_tc_gemm_split2h_fused(
@@ -1042,6 +1044,7 @@ class _CrossNet(torch.autograd.Function):
             xs.append(x)
             us.append(u)
         ctx.d, ctx.n, ctx.head = d, n_layers, head_w is not None
+        ctx.params = params
         if head_w is not None:
             hw = head_w.detach().float().contiguous()
             y = torch.empty(B, dtype=torch.float32, device=dev)
@@ -1081,12 +1084,30 @@ class _CrossNet(torch.autograd.Function):
                        "ptrec_dcn_bwd_init")
         g_x0 = torch.empty(B, dp, dtype=torch.float32, device=dev)
         gws, gbs = [None] * n, [None] * n
+        # the weight-gradient GEMMs feed nothing but the optimizer: inside an IModel train step they run on the tower's
+        # weight-gradient side stream beside the chain (joined before the optimizer step), as in dense._TcMLP.backward
+        from .model.layer import dense as _dense
+        side = None
+        if _dense._DEFER_JOIN[0] and all(p.grad is None for p in ctx.params):
+            side = _dense._wgrad_stream(dev)
+        if side is not None:
+            from .model.layer.embedding import register_join_stream
+            main = torch.cuda.current_stream(dev)
+            register_join_stream(dev, side)
         for l in range(n - 1, -1, -1):
             gbs[l] = torch.empty(d, dtype=torch.float32, device=dev)
             # d out / d x0 = u: g_x0 (+)= g_out * u_l; bias gradient = column sums of g_u
             _lib.check(lib.ptrec_dcn_bwd_layer(_ptr(g_out), _ptr(us[l]), _ptr(g_u), B, d, dp, _ptr(g_x0), int(l != n - 1),
                                                _ptr(gbs[l]), _ptr(ws), ws.numel(), st), "ptrec_dcn_bwd_layer")
-            gws[l] = dcn_cross_wgrad(g_u, xs[l])[:d, :d]
+            if side is not None:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    gws[l] = dcn_cross_wgrad(g_u, xs[l])[:d, :d].contiguous()
+                g_u.record_stream(side)
+                xs[l].record_stream(side)
+                gws[l].record_stream(main)
+            else:
+                gws[l] = dcn_cross_wgrad(g_u, xs[l])[:d, :d]
             g_out, g_u = dcn_cross_dgrad(g_u, wts[l], g_out, x0, want_prev=l > 0)
         out = torch.empty(B, d, dtype=torch.float32, device=dev)  # x0 is also layer 0's x_l: + the chain's g_out
         _lib.check(lib.ptrec_dcn_bwd_final(_ptr(g_x0), _ptr(g_out), B, d, dp, _ptr(out), st), "ptrec_dcn_bwd_final")
