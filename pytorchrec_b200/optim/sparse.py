@@ -52,6 +52,7 @@ class _FusedSparseOptimizer(Optimizer):
         self._ptr_cache: Dict[int, tuple] = {}
         self._interleaved: Dict[int, torch.Tensor] = {}  # id(param) -> [rows, stride] buffer holding weight | state
         self._dense_plan: Dict[tuple, tuple] = {}        # (dense group, step bucket) -> (pointer key, descriptors, chunk starts, n)
+        self._retired_plans: list = []                   # plans superseded during a graph capture (their pinned buffers outlive it)
         # set by data-parallel models whose replicas exchange over NVLink peer memory (distributed/sharded.py):
         # object with .world, .stage(key, n_floats, device) -> (stage, peer pointer array), .barrier(), .fallback(params)
         self._peer_reduce = None
@@ -230,6 +231,13 @@ class _FusedSparseOptimizer(Optimizer):
                 # pinned staging: this may run inside a CUDA-graph capture (the captured copy node re-reads the
                 # pinned buffers on replay, so they are kept alive with the plan)
                 h_rec, h_starts = torch.from_numpy(rec).pin_memory(), torch.from_numpy(starts).pin_memory()
+                old = self._dense_plan.get((gi, bi))
+                if old is not None and torch.cuda.is_current_stream_capturing():
+                    # freeing a pinned buffer makes the host allocator record an event on every stream that used it; if
+                    # that stream is part of the running capture (the dense step may run on the weight-gradient side
+                    # stream) the event is a captured one and the allocator's later cudaEventQuery fails
+                    # (cudaErrorInvalidValue at the next pin_memory()): superseded plans outlive the capture
+                    self._retired_plans.append(old)
                 cached = (key, h_rec.to(dev, non_blocking=True), h_starts.to(dev, non_blocking=True),
                           int(starts[-1]), h_rec, h_starts)
                 self._dense_plan[(gi, bi)] = cached
