@@ -276,6 +276,38 @@ def test_cuda_graph_train_step_equals_eager():
         m.train_step(_ctr_batch(rows, len(dcols), 256, seed=1))
 
 
+@pytest.mark.parametrize("model_name", ["deepfm", "dcn"])
+@pytest.mark.parametrize("graphed", [False, True], ids=["eager", "graph"])
+def test_side_stream_gradients_train_identically(monkeypatch, model_name, graphed):
+    """The fused tower's weight-gradient GEMMs (PTREC_WGRAD_STREAM) and the gradient-finalising reductions
+    (PTREC_REDUCE_STREAM) run on a side stream beside the input-gradient chain inside an IModel train step: every
+    kernel is deterministic and the join precedes the optimizer step, so many steps with the side streams on equal the
+    same steps with everything on the main stream bit for bit — a missing dependency shows up as a difference."""
+    from pytorchrec_b200.model import DCN
+    from pytorchrec_b200.model.layer import dense
+    monkeypatch.setattr(dense, "TC_MIN_MACS", 0)       # small layers on the fused tower too
+    scols, dcols, lab, rows = _ctr_setup()
+
+    def run(side: str):
+        monkeypatch.setenv("PTREC_WGRAD_STREAM", side)
+        monkeypatch.setenv("PTREC_REDUCE_STREAM", side)
+        if model_name == "deepfm":
+            m = DeepFM(scols, dcols, lab, 16, [64, 48, 32], random_seed=9)
+        else:
+            m = DCN(scols, dcols, lab, 16, 2, [64, 32], random_seed=9)
+        m.compile(SparseAdagrad(m.get_parameters(), lr=0.05), torch.nn.BCEWithLogitsLoss(), [LogLoss()], DEV)
+        if graphed:
+            m.enable_cuda_graph(True, warmup=3)
+        losses = [m.train_step(_ctr_batch(rows, len(dcols), 2048, seed=70 + s, zipf=True))["loss"].item() for s in range(25)]
+        return losses, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+
+    l1, sd1 = run("1")
+    l0, sd0 = run("0")
+    assert l1 == l0
+    for k in sd1:
+        assert torch.equal(sd1[k], sd0[k]), k
+
+
 @pytest.mark.parametrize("peer", ["push", "1", "0"], ids=["push", "pull_peer_memory", "all_to_all"])
 def test_sharded_deepfm_matches_unsharded_on_two_gpus(peer):
     """Row-wise sharded tables (owners push rows over NVLink; requesters pull from peer memory; NCCL all-to-all) + the
