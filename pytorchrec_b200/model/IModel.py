@@ -377,6 +377,9 @@ class IModel(Module, ABC):
         self.compiled_optimizers.zero_grad()
         from .layer import dense as _dense
         _dense._DEFER_JOIN[0] = loss.is_cuda   # side-stream weight gradients are joined below, not inside backward()
+        if loss.is_cuda:
+            from .layer.embedding import reset_join_streams
+            reset_join_streams(loss.device)
         try:
             loss.backward()
         finally:

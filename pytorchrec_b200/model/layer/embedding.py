@@ -171,6 +171,14 @@ def register_join_stream(device, stream) -> None:
         lst.append(stream)
 
 
+def reset_join_streams(device) -> None:
+    """Start of a train step's backward: forget side streams registered by a step that did not reach its join (an
+    exception between backward and the optimizer step) — joining a stream that is not part of a running graph capture
+    would invalidate the capture."""
+    if device is not None:
+        _JOIN_STREAMS.pop(torch.device(device), None)
+
+
 def join_aux_streams(device) -> None:
     """Make the current stream wait for whatever the side streams still run (a backward that autograd placed on the aux
     stream, the tower's weight-gradient GEMMs): called by ``IModel`` between ``backward()`` and ``optimizer.step()``."""
