@@ -297,3 +297,38 @@ def test_fit_drives_the_reference_callback_lifecycle_and_save_weights_stores_wei
     for k, v in emb.state_dict().items():
         assert torch.equal(loaded[k], v) and loaded[k].is_contiguous()
         assert loaded[k].untyped_storage().nbytes() == v.numel() * v.element_size(), k
+
+
+def test_side_stream_bookkeeping_is_inert_off_the_gpu_and_outside_a_train_step():
+    """Host logic of the backward's side streams (model/layer/dense.py, embedding.py): registrations are per device,
+    deduplicated, dropped by ``reset_join_streams`` (a step that never reached its join) and consumed by
+    ``join_aux_streams``; ``side_reductions`` does nothing — and does not touch the library's reduce stream — unless an
+    ``IModel`` train step on a CUDA device is running."""
+    from pytorchrec_b200.model.layer import dense, embedding
+
+    class FakeStream:
+        pass
+
+    dev = torch.device("cuda", 0)
+    a, b = FakeStream(), FakeStream()
+    embedding.reset_join_streams(dev)
+    embedding.register_join_stream(dev, a)
+    embedding.register_join_stream(dev, a)
+    embedding.register_join_stream("cuda:0", b)
+    assert embedding._JOIN_STREAMS[dev] == [a, b]
+    embedding.reset_join_streams(dev)
+    assert dev not in embedding._JOIN_STREAMS
+    embedding.join_aux_streams(None)          # CPU model: nothing to join
+
+    assert dense._DEFER_JOIN == [False]
+    with dense.side_reductions(None) as sr:   # CPU tensors
+        assert not sr.on
+        sr.adopt(torch.zeros(1), None)
+    with dense.side_reductions(dev) as sr:    # CUDA device but no train step around: stays on the producer's stream
+        assert not sr.on
+    dense._DEFER_JOIN[0] = True
+    try:
+        with dense.side_reductions(None) as sr:
+            assert not sr.on
+    finally:
+        dense._DEFER_JOIN[0] = False
